@@ -1,0 +1,132 @@
+/*
+ * pna_cuda.h -- C ABI of libpna_cuda.so, the B200 (sm_100a) implementation of PNA's per-entry
+ * data-chunk pipeline.  This is the drop-in boundary: the three internal seams of `libpna`
+ * (reference = ChanTsune/Portable-Network-Archive v0.37.0, paths relative to /root/reference)
+ * are replaced by the batch calls below; everything is POD, `extern "C"`, no exceptions cross.
+ *
+ *   seam 1  CRC     format::chunk_crc / validate_chunk_crc        lib/src/format/chunk.rs:7,16
+ *                   (callers io::read_chunk lib/src/io.rs:141, bytes::read_chunk lib/src/bytes.rs:64,
+ *                    Chunk::crc lib/src/chunk/traits.rs:49)                      -> pna_cuda_crc32
+ *   seam 2  decode  decrypt_reader + decompress_reader             lib/src/entry/read.rs:59,171
+ *                   (NormalEntry::reader lib/src/entry.rs:1150,
+ *                    SolidEntry::entries lib/src/entry.rs:567)                   -> pna_cuda_decode_batch
+ *   seam 3  encode  get_writer = compression_writer(encryption_writer)  lib/src/entry/write.rs:189,251,268
+ *                   (FileEntryBuilder lib/src/entry/builder/file.rs:65-140, EntryBuilderCore::build
+ *                    lib/src/entry/builder.rs:171, write_chunk CRC lib/src/io.rs:183) -> pna_cuda_encode_batch
+ *
+ * Ownership: the caller owns every host buffer for the duration of a call; the library owns all
+ * device memory.  Nothing returned must be freed except pna_ctx / pna_plan handles and
+ * pna_cuda_host_alloc() memory.
+ * Errors: the function return is a context-level error (bad argument, CUDA failure); per-entry
+ * results are in status[] and map 1:1 to the reference's io::ErrorKind classes (see enum).
+ * Threading: a pna_ctx serialises batch calls internally; use one ctx per host thread / per GPU for
+ * concurrency (entries shard by entry across GPUs; the path has no collective).
+ * There is NO CPU fallback: every entry point fails with PNA_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef PNA_CUDA_H
+#define PNA_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-entry status == reference io::ErrorKind class */
+enum {
+    PNA_OK = 0,
+    PNA_E_INVALID_DATA = 1,   /* "broken chunk" format/chunk.rs:18; bad PKCS#7 cipher/block/read.rs:101; corrupt zstd */
+    PNA_E_UNEXPECTED_EOF = 2, /* partial CBC block block/read.rs:90; stream shorter than IV entry/read.rs:80; truncated zstd frame */
+    PNA_E_INVALID_INPUT = 3,  /* "corrupt deflate stream" (flate2 zio); bad key length stream/read.rs:27 */
+    PNA_E_UNSUPPORTED = 4,    /* xz / GCM / unknown codes entry/read.rs:152-163,184-187 */
+    PNA_E_NOSPACE = 5,        /* out.cap too small; out.len = required size (two-pass sizing contract) */
+    PNA_E_OOM = 6,            /* util/io.rs:19 */
+    PNA_E_INTERNAL = 7,
+    PNA_E_CUDA = 8,           /* context-level: CUDA runtime/driver failure or no device */
+    PNA_E_BAD_ARG = 9
+};
+
+/* header byte codes, lib/src/entry/options.rs:237-247,483-491,596-604 */
+enum { PNA_COMPRESSION_NO = 0, PNA_COMPRESSION_DEFLATE = 1, PNA_COMPRESSION_ZSTD = 2, PNA_COMPRESSION_XZ = 4 };
+enum { PNA_ENCRYPTION_NO = 0, PNA_ENCRYPTION_AES = 1, PNA_ENCRYPTION_CAMELLIA = 2 };
+enum { PNA_CIPHER_CBC = 0, PNA_CIPHER_CTR = 1, PNA_CIPHER_GCM = 2 };
+
+typedef struct pna_ctx pna_ctx;   /* one device: streams, device arenas, pinned staging */
+typedef struct pna_plan pna_plan; /* a batch resident in HBM (used for kernel-only timing and re-runs) */
+
+typedef struct { const uint8_t* ptr; uint64_t len; } pna_span;        /* borrowed host memory */
+typedef struct { uint8_t* ptr; uint64_t cap; uint64_t len; } pna_buf; /* caller-owned output; library sets len */
+
+/* One entry's data stream: the FDAT (or SDAT) bodies in order.  The 16-byte IV is the stream prefix when
+ * encryption != 0 and may straddle bodies (lib/src/entry/read.rs:79-103; chunk boundaries are arbitrary,
+ * lib/src/chunk/types.rs:315-320). */
+typedef struct {
+    const pna_span* bodies;
+    uint32_t n_bodies;
+    uint8_t compression, encryption, cipher_mode, _pad; /* FHED bytes [3],[4],[5] / SHED [2],[3],[4] */
+    uint8_t key[32];                                    /* KDF output (host side, lib/src/hash.rs:45); ignored if encryption==0 */
+    uint64_t raw_size_hint;                             /* fSIZ (lib/src/entry.rs:817) or UINT64_MAX */
+} pna_decode_desc;
+
+/* One entry to build: plaintext in, IV || cipher(compress(plain)) out (lib/src/entry/write.rs:268-273). */
+typedef struct {
+    pna_span plain;
+    uint8_t compression, encryption, cipher_mode, _pad;
+    int32_t level;          /* <0: reference default (zstd 3 compress/zstandard.rs:46, deflate 6 compress/deflate.rs:89) */
+    uint8_t key[32];
+    uint8_t iv[16];         /* caller-drawn (lib/src/entry/write.rs:108-111, random.rs:8) */
+    uint32_t max_chunk_size; /* FDAT body cap for CRC emission; 0 = u32::MAX - one body (lib/src/util/io.rs:24-33) */
+} pna_encode_desc;
+
+/* ---- context ---- */
+int pna_cuda_init(pna_ctx** out, int device_id);
+void pna_cuda_destroy(pna_ctx* ctx);
+const char* pna_cuda_strerror(int32_t status);
+const char* pna_cuda_last_error(pna_ctx* ctx);   /* text of the last context-level failure */
+/* pinned host memory for end-to-end paths (cudaHostAlloc); pageable buffers are accepted everywhere too */
+void* pna_cuda_host_alloc(pna_ctx* ctx, uint64_t bytes);
+void pna_cuda_host_free(pna_ctx* ctx, void* p);
+/* the CUDA stream every kernel of this ctx is launched on (cudaStream_t), for CUDA-event timing by callers */
+void* pna_cuda_stream(pna_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py "gpu_launches") */
+uint64_t pna_cuda_launch_count(pna_ctx* ctx);
+
+/* ---- seam 1: chunk CRC ---- */
+/* crc_out[i] = CRC-32/ISO-HDLC over spans[i] (the caller passes type||data, lib/src/format/chunk.rs:7-12). */
+int pna_cuda_crc32(pna_ctx* ctx, const pna_span* type_and_data, uint32_t n, uint32_t* crc_out);
+/* Whole-archive variant for the index pass: `image` is uploaded once, spans are (offset,len) pairs inside it. */
+int pna_cuda_crc32_image(pna_ctx* ctx, const uint8_t* image, uint64_t image_len, const uint64_t* span_off,
+                         const uint64_t* span_len, uint32_t n, uint32_t* crc_out);
+
+/* ---- seam 2: decode ---- */
+int pna_cuda_decode_batch(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_buf* out, int32_t* status);
+/* staged form: upload once, run the kernels any number of times on HBM-resident input, fetch once */
+int pna_cuda_decode_plan_create(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_plan** plan);
+int pna_cuda_decode_plan_run(pna_plan* plan);                 /* asynchronous on pna_cuda_stream(ctx) after first call */
+int pna_cuda_decode_plan_fetch(pna_plan* plan, pna_buf* out, int32_t* status);
+/* stream / decoded byte totals of a plan (algorithmic bytes for the roofline: C and U) */
+int pna_cuda_plan_stats(pna_plan* plan, uint64_t* stream_bytes, uint64_t* plain_bytes, uint64_t* launches_per_run);
+void pna_cuda_plan_destroy(pna_plan* plan);
+
+/* ---- seam 3: encode ---- */
+/* out[i] receives IV || cipher(compress(plain)) (no IV when encryption==0).  fdat_crc_out (optional) receives,
+ * per entry, crc32("FDAT" || body) for each body of at most max_chunk_size bytes; crc_count_out[i] = number
+ * written for entry i, laid out consecutively (caller sizes it with pna_cuda_encode_crc_count). */
+uint64_t pna_cuda_encode_bound(const pna_encode_desc* desc);
+uint64_t pna_cuda_encode_crc_count(const pna_encode_desc* desc);
+int pna_cuda_encode_batch(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_buf* out,
+                          uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status);
+int pna_cuda_encode_plan_create(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_plan** plan);
+int pna_cuda_encode_plan_run(pna_plan* plan);
+int pna_cuda_encode_plan_fetch(pna_plan* plan, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out,
+                               int32_t* status);
+
+/* ---- block-cipher primitives (test hooks for the KATs in lib/src/cipher.rs:256-292) ---- */
+/* ECB over n 16-byte blocks with the same key schedule the stream kernels use. */
+int pna_cuda_ecb(pna_ctx* ctx, int encryption, int encrypt, const uint8_t key[32], const uint8_t* in, uint64_t n_bytes,
+                 uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,157 @@
+// host_core.cpp -- g++ build of the PNA_HD algorithmic cores (the very code the kernels run)
+// so that the CPU-only test tier can pin them against the oracle.  Test infrastructure.
+#include "../../portable-network-archive_b200/csrc/cipher_core.cuh"
+using namespace pna;
+static AesTables g_aes; static CamelliaTables g_cam; static bool g_init = false;
+static void init() { if (!g_init) { aes_make_tables(&g_aes); camellia_make_tables(&g_cam); g_init = true; } }
+extern "C" {
+int hc_ecb(int encryption, int encrypt, const uint8_t* key, const uint8_t* in, size_t n, uint8_t* out) {
+    init();
+    if (encryption == 1) {
+        AesKey K; aes256_expand_key(&g_aes, key, &K);
+        TabView te{g_aes.te0, 1, 0}, td{g_aes.td0, 1, 0};
+        for (size_t i = 0; i + 16 <= n; i += 16) {
+            uint32_t s[4]; memcpy(s, in + i, 16);
+            if (encrypt) aes256_encrypt_block(s, K.rk, te); else aes256_decrypt_block(s, K.dk, td, g_aes.inv_sbox);
+            memcpy(out + i, s, 16);
+        }
+        return 0;
+    }
+    if (encryption == 2) {
+        CamelliaKey K; camellia256_expand_key(&g_cam, key, &K);
+        for (size_t i = 0; i + 16 <= n; i += 16) {
+            uint32_t s[4]; memcpy(s, in + i, 16);
+            camellia256_crypt_block(s, encrypt ? K.ek : K.dk, &g_cam.sp_hi[0][0], &g_cam.sp_lo[0][0]);
+            memcpy(out + i, s, 16);
+        }
+        return 0;
+    }
+    return 4;
+}
+void hc_ctr_add(const uint8_t* iv, uint64_t add, uint8_t* out) {
+    uint32_t a[4], o[4]; memcpy(a, iv, 16); ctr128be_add(a, add, o); memcpy(out, o, 16);
+}
+}
+
+// ---- CRC emulation: the warp algorithm with the lanes looped on the host
+#include "../../portable-network-archive_b200/csrc/crc32_core.cuh"
+static CrcConsts g_crc; static bool g_crc_init = false;
+extern "C" uint32_t hc_crc_span(const uint8_t* img, uint64_t S, uint64_t E) {
+    if (!g_crc_init) { crc_make_consts(&g_crc); g_crc_init = true; }
+    uint32_t acc = 0xFFFFFFFFu;
+    for (uint64_t t = S; t < E || t == S; t += CRC_TILE) {
+        uint64_t te = t + CRC_TILE < E ? t + CRC_TILE : E;
+        uint32_t x = 0;
+        for (int lane = 0; lane < 32; lane++) x ^= crc_tile_lane(img, t, te, lane, &g_crc.U[0][0], g_crc.lane_k);
+        uint32_t raw = crc_multmodp(x, g_crc.inv_z[(16 - (te & 15)) & 15]);
+        uint32_t sh = (te - t) == CRC_TILE ? g_crc.x_tile : crc_x2nmodp(g_crc.x2n, te - t, 3);
+        acc = crc_multmodp(sh, acc) ^ raw;
+        if (te >= E) break;
+    }
+    return ~acc;
+}
+
+// ---- zstd: the kernels' phases run serially on the host (scan -> parse -> resolve -> entropy -> prefix -> LZ)
+#include "../../portable-network-archive_b200/csrc/zstd_core.cuh"
+#include <vector>
+extern "C" { int hc_site = 0; }
+extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uint64_t cap, uint64_t* out_len,
+                              uint32_t* stats /* [nblocks, nseq, nlit] optional */) {
+    using namespace pna::zs;
+    *out_len = 0;
+    std::vector<uint8_t> arena(len + 64, 0);
+    memcpy(arena.data(), in, len);
+    const uint8_t* comp = arena.data();
+    const uint32_t* words = (const uint32_t*)arena.data();
+    uint32_t nb = 0;
+    int32_t st = scan_entry(comp, 0, len, 0, nullptr, &nb);
+    if (st != ST_OK) { hc_site = 1; return st; }
+    std::vector<ZBlock> blocks(nb ? nb : 1);
+    scan_entry(comp, 0, len, 0, blocks.data(), &nb);
+    uint64_t lit_total = 0, seq_total = 0;
+    for (uint32_t i = 0; i < nb; i++) {
+        blocks[i].status = parse_block(comp, blocks[i]);
+        if (blocks[i].status) { hc_site = 2; return blocks[i].status; }
+        blocks[i].lit_off = lit_total; blocks[i].seq_off = seq_total;
+        if (blocks[i].type == BT_COMPRESSED) {
+            if (blocks[i].lit_type >= LT_COMPRESSED) lit_total += blocks[i].lit_regen;
+            seq_total += blocks[i].nseq;
+        }
+    }
+    st = resolve_sources(blocks.data(), 0, nb);
+    if (st) { hc_site = 3; return st; }
+    std::vector<uint8_t> lits(lit_total + 8);
+    std::vector<uint32_t> sll(seq_total + 1), sml(seq_total + 1), sof(seq_total + 1);
+    std::vector<SeqEntry> tll(512), tof(512), tml(512);
+    std::vector<uint16_t> huf(1 << HUF_LOG_MAX);
+    for (uint32_t i = 0; i < nb; i++) {
+        ZBlock& b = blocks[i];
+        if (b.type != BT_COMPRESSED) continue;
+        if (b.lit_type >= LT_COMPRESSED) {
+            const ZBlock& hb = blocks[b.huf_src];
+            uint8_t weights[257]; FseEntry fse[64]; int hlog = 0;
+            int hdr = huf_read_table(words, comp, hb.src + hb.lit_pos, hb.lit_csize, huf.data(), &hlog, weights, fse);
+            if (hdr < 0) { hc_site = 4; return ST_INVALID_DATA; }
+            uint32_t skip = b.lit_type == LT_COMPRESSED ? (uint32_t)hdr : 0;
+            if (skip > b.lit_csize) { hc_site = 5; return ST_INVALID_DATA; }
+            uint64_t at = b.src + b.lit_pos + skip; uint32_t clen = b.lit_csize - skip;
+            uint8_t* dst = lits.data() + b.lit_off;
+            if (b.lit_streams == 1) {
+                if (!huf_decode_stream(words, comp, at, clen, huf.data(), hlog, dst, b.lit_regen)) { hc_site = 6; return ST_INVALID_DATA; }
+            } else {
+                if (clen < 6) { hc_site = 7; return ST_INVALID_DATA; }
+                uint32_t s1 = load_le16(comp + at), s2 = load_le16(comp + at + 2), s3 = load_le16(comp + at + 4);
+                if ((uint64_t)s1 + s2 + s3 + 6 > clen) { hc_site = 8; return ST_INVALID_DATA; }
+                uint32_t s4 = clen - 6 - s1 - s2 - s3;
+                uint32_t seg = (b.lit_regen + 3) / 4;
+                if (seg * 3 > b.lit_regen) { hc_site = 9; return ST_INVALID_DATA; }
+                uint32_t sz[4] = {s1, s2, s3, s4};
+                uint64_t o = at + 6;
+                for (int k = 0; k < 4; k++) {
+                    uint32_t cnt = k < 3 ? seg : b.lit_regen - 3 * seg;
+                    if (!huf_decode_stream(words, comp, o, sz[k], huf.data(), hlog, dst + (uint64_t)k * seg, cnt)) { hc_site = 10; return ST_INVALID_DATA; }
+                    o += sz[k];
+                }
+            }
+        }
+        if (b.nseq) {
+            int16_t norm[64]; uint16_t nxt[64];
+            int l0 = seq_table_for(comp, blocks.data(), b, 0, tll.data(), norm, nxt);
+            int l1 = seq_table_for(comp, blocks.data(), b, 1, tof.data(), norm, nxt);
+            int l2 = seq_table_for(comp, blocks.data(), b, 2, tml.data(), norm, nxt);
+            if (l0 < 0 || l1 < 0 || l2 < 0) { hc_site = 11; return ST_INVALID_DATA; }
+            st = decode_sequences(words, comp, b, tll.data(), tof.data(), tml.data(), l0, l1, l2, sll.data() + b.seq_off,
+                                  sml.data() + b.seq_off, sof.data() + b.seq_off);
+            if (st) { hc_site = 12; return st; }
+        }
+    }
+    uint64_t total = 0;
+    st = prefix_entry(blocks.data(), 0, nb, 0, &total);
+    if (st) { hc_site = 13; return st; }
+    *out_len = total;
+    if (stats) { stats[0] = nb; stats[1] = (uint32_t)seq_total; stats[2] = (uint32_t)lit_total; }
+    if (total > cap) return ST_NOSPACE;
+    for (uint32_t i = 0; i < nb; i++) {
+        ZBlock& b = blocks[i];
+        uint8_t* o = out + b.out_off;
+        if (b.type == BT_RAW) { memcpy(o, comp + b.src, b.size); continue; }
+        if (b.type == BT_RLE) { memset(o, comp[b.src], b.size); continue; }
+        const uint8_t* lit; uint32_t stride = 1;
+        if (b.lit_type == LT_RAW) lit = comp + b.src + b.lit_pos;
+        else if (b.lit_type == LT_RLE) { lit = comp + b.src + b.lit_pos; stride = 0; }
+        else lit = lits.data() + b.lit_off;
+        uint64_t op = 0, lp = 0;
+        for (uint32_t s = 0; s < b.nseq; s++) {
+            uint32_t ll = sll[b.seq_off + s], ml = sml[b.seq_off + s];
+            uint32_t off = resolve_rep(sof[b.seq_off + s], b.rep_in);
+            for (uint32_t k = 0; k < ll; k++) o[op + k] = lit[(lp + k) * stride];
+            op += ll; lp += ll;
+            if (off == 0 || off > (b.out_off + op) - b.frame_out) { hc_site = 14; return ST_INVALID_DATA; }
+            for (uint32_t k = 0; k < ml; k++) o[op + k] = o[op + k - off];
+            op += ml;
+        }
+        for (uint64_t k = lp; k < b.lit_regen; k++) o[op++] = lit[k * stride];
+        if (op != b.out_size) return ST_INTERNAL;
+    }
+    return ST_OK;
+}
