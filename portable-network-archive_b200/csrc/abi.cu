@@ -1,0 +1,729 @@
+// abi.cu -- C ABI of libpna_cuda.so (see include/pna_cuda.h): context, batch plans, host<->device
+// staging and the kernel launch sequences for the PNA data-chunk pipeline on B200 (sm_100a).
+//
+// No CPU fallback lives here: every compute step is a kernel from kernels_*.cuh.  The host side
+// only indexes (offsets, tiles, key schedules) and moves bytes.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pna_cuda.h"
+#include "kernels_crc_cipher.cuh"
+#include "kernels_inflate.cuh"
+#include "kernels_zstd.cuh"
+#include "kernels_encode.cuh"
+
+using namespace pna;
+
+// ------------------------------------------------------------------------------------------------
+struct pna_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    CrcConsts* d_crc = nullptr;
+    AesTables* d_aes = nullptr;
+    CamelliaTables* d_cam = nullptr;
+    AesTables h_aes;
+    CamelliaTables h_cam;
+    bool fail(const char* what, cudaError_t e) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return false;
+    }
+};
+
+#define CK(call)                                                       \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) { ctx->fail(#call, e__); return PNA_E_CUDA; } \
+    } while (0)
+#define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
+
+template <class T>
+struct DevArr {   // growable device array (never shrinks); freed with the owner
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DevArr() { release(); }
+    DevArr() = default;
+    DevArr(const DevArr&) = delete;
+    DevArr& operator=(const DevArr&) = delete;
+};
+
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// Host span -> device image staging with range coalescing: spans that lie close together in host
+// memory (e.g. the FDAT bodies of one mmap'd archive) travel in one cudaMemcpyAsync.
+struct Stager {
+    struct Range { const uint8_t* host; uint64_t len; uint64_t dev_off; };
+    std::vector<Range> ranges;
+    uint64_t total = 0;
+    static constexpr uint64_t GAP = 64 * 1024;
+    // returns the device offset of the span
+    uint64_t add(const uint8_t* p, uint64_t len) {
+        if (len == 0) return total;
+        if (!ranges.empty()) {
+            Range& r = ranges.back();
+            const uint8_t* end = r.host + r.len;
+            if (p >= r.host && p <= end + GAP) {
+                uint64_t off = r.dev_off + (uint64_t)(p - r.host);
+                if (p + len > end) { r.len = (uint64_t)(p + len - r.host); total = r.dev_off + r.len; }
+                return off;
+            }
+        }
+        uint64_t dev = align_up(total, 256) + ((uintptr_t)p & 15);   // keep the host pointer's 16-byte phase
+        ranges.push_back({p, len, dev});
+        total = dev + len;
+        return dev;
+    }
+    int upload(pna_ctx* ctx, uint8_t* d_base) {
+        for (const Range& r : ranges) CK(cudaMemcpyAsync(d_base + r.dev_off, r.host, r.len, cudaMemcpyHostToDevice, ctx->stream));
+        return PNA_OK;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct pna_plan {
+    pna_ctx* ctx = nullptr;
+    int kind = 0;   // 0 decode, 1 encode
+    uint32_t n = 0;
+    bool prepared = false, need_sizing = false;
+    uint64_t stream_bytes = 0, plain_bytes = 0, launches_per_run = 0;
+    // host metadata
+    std::vector<EntryRec> h_entries;
+    std::vector<Segment> h_segs;
+    std::vector<DevKeys> h_keys;
+    std::vector<CipherTile> h_tiles[5];   // 0 gather, 1 aes-ctr, 2 aes-cbc, 3 camellia-ctr, 4 camellia-cbc
+    std::vector<uint32_t> h_store, h_deflate;
+    std::vector<zs::ZEntry> h_ze;
+    std::vector<CopyJob> h_copy;
+    uint64_t image_bytes = 0, buf_bytes = 0, out_bytes = 0;
+    // device
+    DevArr<uint8_t> d_buf, d_out, d_lits;
+    DevArr<EntryRec> d_entries, d_entries_init;
+    DevArr<Segment> d_segs;
+    DevArr<DevKeys> d_keys;
+    DevArr<CipherTile> d_tiles[5];
+    DevArr<uint32_t> d_deflate, d_sll, d_sml, d_sof;
+    DevArr<zs::ZEntry> d_ze;
+    DevArr<zs::ZBlock> d_blocks;
+    DevArr<uint64_t> d_lit_base, d_seq_base;
+    DevArr<CopyJob> d_copy;
+    uint32_t n_blocks = 0;
+    uint64_t lit_total = 0, seq_total = 0;
+    // encode side
+    enc::EncodePlan* enc = nullptr;
+    ~pna_plan() {
+        d_buf.release(); d_out.release(); d_lits.release(); d_entries.release(); d_entries_init.release();
+        d_segs.release(); d_keys.release();
+        for (auto& t : d_tiles) t.release();
+        d_deflate.release(); d_sll.release(); d_sml.release(); d_sof.release(); d_ze.release(); d_blocks.release();
+        d_lit_base.release(); d_seq_base.release(); d_copy.release();
+        if (enc) enc::destroy(enc);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* pna_cuda_strerror(int32_t s) {
+    switch (s) {
+        case PNA_OK: return "ok";
+        case PNA_E_INVALID_DATA: return "invalid data";
+        case PNA_E_UNEXPECTED_EOF: return "unexpected end of stream";
+        case PNA_E_INVALID_INPUT: return "invalid input";
+        case PNA_E_UNSUPPORTED: return "unsupported";
+        case PNA_E_NOSPACE: return "output buffer too small";
+        case PNA_E_OOM: return "out of memory";
+        case PNA_E_INTERNAL: return "internal error";
+        case PNA_E_CUDA: return "CUDA failure";
+        case PNA_E_BAD_ARG: return "bad argument";
+        default: return "unknown";
+    }
+}
+
+extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
+    if (!out) return PNA_E_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return PNA_E_CUDA;   // no fallback: fail loudly
+    if (device_id < 0 || device_id >= count) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = new pna_ctx();
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return PNA_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess || prop.major < 10) { delete ctx; return PNA_E_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PNA_E_CUDA; }
+    CrcConsts* hc = new CrcConsts();
+    crc_make_consts(hc);
+    aes_make_tables(&ctx->h_aes);
+    camellia_make_tables(&ctx->h_cam);
+    bool ok = cudaMalloc(&ctx->d_crc, sizeof(CrcConsts)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_aes, sizeof(AesTables)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_cam, sizeof(CamelliaTables)) == cudaSuccess &&
+              cudaMemcpy(ctx->d_crc, hc, sizeof(CrcConsts), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->d_aes, &ctx->h_aes, sizeof(AesTables), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->d_cam, &ctx->h_cam, sizeof(CamelliaTables), cudaMemcpyHostToDevice) == cudaSuccess;
+    delete hc;
+    // opt in to the large dynamic shared memory the table-driven kernels use
+    const int aes_smem = 256 * 32 * 4 + 256, cam_smem = 2 * 2048 * 4;
+    ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(ecb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(inf::inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
+    ok = ok && enc::init_attributes();
+    if (!ok) { pna_cuda_destroy(ctx); return PNA_E_CUDA; }
+    *out = ctx;
+    return PNA_OK;
+}
+
+extern "C" void pna_cuda_destroy(pna_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->d_crc) cudaFree(ctx->d_crc);
+    if (ctx->d_aes) cudaFree(ctx->d_aes);
+    if (ctx->d_cam) cudaFree(ctx->d_cam);
+    delete ctx;
+}
+extern "C" const char* pna_cuda_last_error(pna_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" void* pna_cuda_host_alloc(pna_ctx* ctx, uint64_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void pna_cuda_host_free(pna_ctx* ctx, void* p) { if (p) cudaFreeHost(p); }
+extern "C" void* pna_cuda_stream(pna_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t pna_cuda_launch_count(pna_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// seam 1: CRC
+static int crc_run(pna_ctx* ctx, const uint8_t* d_img, const std::vector<uint64_t>& off, const uint64_t* len, uint32_t n,
+                   uint32_t* crc_out) {
+    std::vector<CrcTile> tiles;
+    std::vector<uint32_t> first(n);
+    tiles.reserve(n);
+    for (uint32_t i = 0; i < n; i++) {
+        first[i] = (uint32_t)tiles.size();
+        uint64_t o = off[i], l = len[i];
+        do {
+            uint32_t t = (uint32_t)std::min<uint64_t>(l, CRC_TILE);
+            tiles.push_back({o, t, i});
+            o += t; l -= t;
+        } while (l);
+    }
+    const uint32_t nt = (uint32_t)tiles.size();
+    DevArr<CrcTile> d_tiles; DevArr<uint32_t> d_first, d_raw, d_crc;
+    CK(d_tiles.reserve(nt)); CK(d_first.reserve(n)); CK(d_raw.reserve(nt)); CK(d_crc.reserve(n));
+    int rc = PNA_OK;
+    do {
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(d_tiles.p, tiles.data(), nt * sizeof(CrcTile), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(d_first.p, first.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+            ctx->fail("crc upload", e); rc = PNA_E_CUDA; break;
+        }
+        const uint32_t warps_per_cta = 8;
+        uint32_t grid = std::min<uint32_t>((nt + warps_per_cta - 1) / warps_per_cta, (uint32_t)ctx->sm_count * 8);
+        crc_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, d_tiles.p, nt, ctx->d_crc, d_raw.p);
+        ctx->launches++;
+        crc_combine_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_tiles.p, d_raw.p, d_first.p, n, nt, ctx->d_crc, d_crc.p);
+        ctx->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess ||
+            (e = cudaMemcpyAsync(crc_out, d_crc.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+            ctx->fail("crc run", e); rc = PNA_E_CUDA; break;
+        }
+    } while (0);
+    d_tiles.release(); d_first.release(); d_raw.release(); d_crc.release();
+    return rc;
+}
+
+extern "C" int pna_cuda_crc32(pna_ctx* ctx, const pna_span* spans, uint32_t n, uint32_t* crc_out) {
+    if (!ctx || (!spans && n) || (!crc_out && n)) return PNA_E_BAD_ARG;
+    if (n == 0) return PNA_OK;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Stager st;
+    std::vector<uint64_t> off(n), len(n);
+    for (uint32_t i = 0; i < n; i++) { off[i] = st.add(spans[i].ptr, spans[i].len); len[i] = spans[i].len; }
+    DevArr<uint8_t> d_img;
+    CK(d_img.reserve(st.total + 64));
+    int rc = st.upload(ctx, d_img.p);
+    if (rc == PNA_OK) rc = crc_run(ctx, d_img.p, off, len.data(), n, crc_out);
+    cudaStreamSynchronize(ctx->stream);
+    d_img.release();
+    return rc;
+}
+
+extern "C" int pna_cuda_crc32_image(pna_ctx* ctx, const uint8_t* image, uint64_t image_len, const uint64_t* span_off,
+                                    const uint64_t* span_len, uint32_t n, uint32_t* crc_out) {
+    if (!ctx || (!image && image_len) || ((!span_off || !span_len || !crc_out) && n)) return PNA_E_BAD_ARG;
+    if (n == 0) return PNA_OK;
+    for (uint32_t i = 0; i < n; i++)
+        if (span_off[i] > image_len || span_len[i] > image_len - span_off[i]) return PNA_E_BAD_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    DevArr<uint8_t> d_img;
+    CK(d_img.reserve(image_len + 64));
+    cudaError_t e = cudaMemcpyAsync(d_img.p, image, image_len, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = PNA_OK;
+    if (e != cudaSuccess) { ctx->fail("image upload", e); rc = PNA_E_CUDA; }
+    std::vector<uint64_t> off(span_off, span_off + n);
+    if (rc == PNA_OK) rc = crc_run(ctx, d_img.p, off, span_len, n, crc_out);
+    cudaStreamSynchronize(ctx->stream);
+    d_img.release();
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// seam 2: decode
+static int variant_of(const EntryRec& e) {
+    if (e.encryption == 0) return 0;
+    return (e.encryption == 1 ? 1 : 3) + (e.cipher_mode == 1 ? 0 : 1);
+}
+
+static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint64_t* caps, pna_plan* P) {
+    P->ctx = ctx; P->kind = 0; P->n = n;
+    P->h_entries.resize(n);
+    Stager st;
+    std::map<std::array<uint8_t, 33>, int> key_ids;
+    uint64_t comp_extra = 0;   // bytes needed in the comp region (decrypted / gathered streams)
+    std::vector<uint8_t> needs_copy(n, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        const pna_decode_desc& d = descs[i];
+        EntryRec& e = P->h_entries[i];
+        memset(&e, 0, sizeof e);
+        e.compression = d.compression; e.encryption = d.encryption; e.cipher_mode = d.cipher_mode;
+        e.seg_begin = P->h_segs.size();
+        e.key_idx = -1;
+        uint64_t pos = 0;
+        for (uint32_t b = 0; b < d.n_bodies; b++) {
+            if (d.bodies[b].len == 0) continue;
+            if (!d.bodies[b].ptr) return PNA_E_BAD_ARG;
+            P->h_segs.push_back({st.add(d.bodies[b].ptr, d.bodies[b].len), pos});
+            pos += d.bodies[b].len;
+        }
+        e.n_segs = (uint32_t)(P->h_segs.size() - e.seg_begin);
+        e.stream_len = pos;
+        P->stream_bytes += pos;
+        // host-side validation == the reference's dispatch (entry/read.rs:59-190)
+        if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD)
+            e.status = ST_UNSUPPORTED;
+        else if (d.encryption != PNA_ENCRYPTION_NO && d.encryption != PNA_ENCRYPTION_AES && d.encryption != PNA_ENCRYPTION_CAMELLIA)
+            e.status = ST_UNSUPPORTED;
+        else if (d.encryption != 0 && d.cipher_mode != PNA_CIPHER_CBC && d.cipher_mode != PNA_CIPHER_CTR)
+            e.status = ST_UNSUPPORTED;
+        else if (d.encryption != 0 && pos < 16)
+            e.status = ST_UNEXPECTED_EOF;   // read_exact(iv)
+        else if (d.encryption != 0 && d.cipher_mode == PNA_CIPHER_CBC && ((pos - 16) < 16 || (pos - 16) % 16))
+            e.status = ST_UNEXPECTED_EOF;   // cipher/block/read.rs:36,90
+        if (e.status != ST_OK) continue;
+        if (d.encryption) {
+            std::array<uint8_t, 33> k;
+            k[0] = d.encryption;
+            memcpy(k.data() + 1, d.key, 32);
+            auto it = key_ids.find(k);
+            if (it == key_ids.end()) {
+                DevKeys dk;
+                memset(&dk, 0, sizeof dk);
+                if (d.encryption == 1) {
+                    AesKey ak; aes256_expand_key(&ctx->h_aes, d.key, &ak);
+                    memcpy(dk.aes_rk, ak.rk, sizeof ak.rk); memcpy(dk.aes_dk, ak.dk, sizeof ak.dk);
+                } else {
+                    CamelliaKey ck; camellia256_expand_key(&ctx->h_cam, d.key, &ck);
+                    memcpy(dk.cam_ek, ck.ek, sizeof ck.ek); memcpy(dk.cam_dk, ck.dk, sizeof ck.dk);
+                }
+                it = key_ids.emplace(k, (int)P->h_keys.size()).first;
+                P->h_keys.push_back(dk);
+            }
+            e.key_idx = it->second;
+            e.comp_len = pos - 16;   // CBC: rewritten by the kernel after unpadding
+            needs_copy[i] = 1;
+        } else {
+            e.comp_len = pos;
+            needs_copy[i] = e.n_segs > 1;
+        }
+        if (needs_copy[i]) comp_extra += align_up(e.comp_len, 16) + 16;
+    }
+    P->image_bytes = align_up(st.total, 256);
+    // comp region right behind the image
+    uint64_t cur = P->image_bytes;
+    for (uint32_t i = 0; i < n; i++) {
+        EntryRec& e = P->h_entries[i];
+        if (e.status != ST_OK) continue;
+        if (needs_copy[i]) {
+            e.comp_off = cur;
+            cur += align_up(e.comp_len, 16) + 16;
+            const uint64_t nb = (e.comp_len + 15) / 16;
+            std::vector<CipherTile>& tv = P->h_tiles[variant_of(e)];
+            for (uint64_t b0 = 0; b0 < nb; b0 += CIPHER_TILE_BLOCKS)
+                tv.push_back({i, (uint32_t)std::min<uint64_t>(CIPHER_TILE_BLOCKS, nb - b0), b0});
+        } else {
+            e.comp_off = e.n_segs ? P->h_segs[e.seg_begin].img_off : 0;
+        }
+    }
+    P->buf_bytes = cur + 256;
+    // decode lists
+    bool all_caps = true;
+    for (uint32_t i = 0; i < n; i++) {
+        EntryRec& e = P->h_entries[i];
+        uint64_t cap = caps ? caps[i] : descs[i].raw_size_hint;
+        e.out_cap = cap;
+        if (e.status != ST_OK) { e.out_cap = 0; continue; }
+        if (cap == UINT64_MAX) all_caps = false;
+        if (e.compression == PNA_COMPRESSION_NO) P->h_store.push_back(i);
+        else if (e.compression == PNA_COMPRESSION_DEFLATE) P->h_deflate.push_back(i);
+        else { zs::ZEntry z; memset(&z, 0, sizeof z); z.entry = i; P->h_ze.push_back(z); }
+    }
+    P->need_sizing = !all_caps;
+    // device arrays + upload
+    CK(P->d_buf.reserve(P->buf_bytes));
+    CK(P->d_entries.reserve(n)); CK(P->d_entries_init.reserve(n));
+    CK(P->d_segs.reserve(P->h_segs.size()));
+    CK(P->d_keys.reserve(P->h_keys.size()));
+    int rc = st.upload(ctx, P->d_buf.p);
+    if (rc) return rc;
+    if (!P->h_segs.empty()) CK(cudaMemcpyAsync(P->d_segs.p, P->h_segs.data(), P->h_segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, ctx->stream));
+    if (!P->h_keys.empty()) CK(cudaMemcpyAsync(P->d_keys.p, P->h_keys.data(), P->h_keys.size() * sizeof(DevKeys), cudaMemcpyHostToDevice, ctx->stream));
+    for (int v = 0; v < 5; v++) {
+        if (P->h_tiles[v].empty()) continue;
+        CK(P->d_tiles[v].reserve(P->h_tiles[v].size()));
+        CK(cudaMemcpyAsync(P->d_tiles[v].p, P->h_tiles[v].data(), P->h_tiles[v].size() * sizeof(CipherTile), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!P->h_deflate.empty()) {
+        CK(P->d_deflate.reserve(P->h_deflate.size()));
+        CK(cudaMemcpyAsync(P->d_deflate.p, P->h_deflate.data(), P->h_deflate.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));   // the borrowed host spans may go away after this call
+    return PNA_OK;
+}
+
+// assign out_off for every entry from its out_cap; (re)allocates d_out and uploads the entry table
+static int decode_layout_out(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    uint64_t cur = 0;
+    for (EntryRec& e : P->h_entries) {
+        e.out_off = cur;
+        if (e.status == ST_OK && e.out_cap != UINT64_MAX) cur += align_up(e.out_cap, 16);
+    }
+    P->out_bytes = cur;
+    CK(P->d_out.reserve(cur + 256));
+    // store entries: comp -> out copies in <= 256 KiB pieces
+    P->h_copy.clear();
+    for (uint32_t i : P->h_store) {
+        const EntryRec& e = P->h_entries[i];
+        uint64_t len = std::min(e.comp_len, e.out_cap);
+        for (uint64_t o = 0; o < len; o += 256 * 1024) P->h_copy.push_back({e.out_off + o, e.comp_off + o, std::min<uint64_t>(256 * 1024, len - o)});
+    }
+    if (!P->h_copy.empty()) {
+        CK(P->d_copy.reserve(P->h_copy.size()));
+        CK(cudaMemcpyAsync(P->d_copy.p, P->h_copy.data(), P->h_copy.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(P->d_entries_init.p, P->h_entries.data(), P->n * sizeof(EntryRec), cudaMemcpyHostToDevice, ctx->stream));
+    return PNA_OK;
+}
+
+static int launch_cipher(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    const int aes_smem = 256 * 32 * 4 + 256, cam_smem = 2 * 2048 * 4;
+    for (int v = 0; v < 5; v++) {
+        const uint32_t nt = (uint32_t)P->h_tiles[v].size();
+        if (!nt) continue;
+        const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)ctx->sm_count * (v == 1 || v == 2 ? 4 : 6));
+#define ARGS P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_tiles[v].p, nt, P->d_keys.p, ctx->d_aes, ctx->d_cam
+        switch (v) {
+            case 0: decrypt_tiles_kernel<0, 1><<<grid, 256, 0, ctx->stream>>>(ARGS); break;
+            case 1: decrypt_tiles_kernel<1, 1><<<grid, 256, aes_smem, ctx->stream>>>(ARGS); break;
+            case 2: decrypt_tiles_kernel<1, 0><<<grid, 256, aes_smem, ctx->stream>>>(ARGS); break;
+            case 3: decrypt_tiles_kernel<2, 1><<<grid, 256, cam_smem, ctx->stream>>>(ARGS); break;
+            case 4: decrypt_tiles_kernel<2, 0><<<grid, 256, cam_smem, ctx->stream>>>(ARGS); break;
+        }
+#undef ARGS
+        LAUNCHED();
+    }
+    return PNA_OK;
+}
+
+static int launch_zstd_front(pna_plan* P, bool with_count) {   // scan .. resolve
+    pna_ctx* ctx = P->ctx;
+    const uint32_t nz = (uint32_t)P->h_ze.size();
+    if (!nz) return PNA_OK;
+    if (with_count) {
+        zs::zstd_count_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz);
+        LAUNCHED();
+        return PNA_OK;
+    }
+    zs::zstd_fill_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
+    LAUNCHED();
+    if (P->n_blocks) {
+        zs::zstd_parse_kernel<<<(P->n_blocks + 127) / 128, 128, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_blocks.p, P->n_blocks);
+        LAUNCHED();
+    }
+    zs::zstd_resolve_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
+    LAUNCHED();
+    return PNA_OK;
+}
+static int launch_zstd_entropy(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    const uint32_t nz = (uint32_t)P->h_ze.size();
+    if (!nz) return PNA_OK;
+    if (P->n_blocks) {
+        zs::zstd_entropy_kernel<<<P->n_blocks, 64, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_blocks.p, P->n_blocks,
+                                                                    P->d_lit_base.p, P->d_seq_base.p, P->d_lits.p, P->d_sll.p,
+                                                                    P->d_sml.p, P->d_sof.p);
+        LAUNCHED();
+    }
+    zs::zstd_prefix_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
+    LAUNCHED();
+    return PNA_OK;
+}
+static int launch_zstd_lz(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    const uint32_t nz = (uint32_t)P->h_ze.size();
+    if (!nz) return PNA_OK;
+    zs::zstd_lz_kernel<<<(nz + 3) / 4, 128, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p, P->d_lits.p,
+                                                             P->d_sll.p, P->d_sml.p, P->d_sof.p, P->d_out.p);
+    LAUNCHED();
+    return PNA_OK;
+}
+static int launch_inflate(pna_plan* P, int size_only) {
+    pna_ctx* ctx = P->ctx;
+    const uint32_t nd = (uint32_t)P->h_deflate.size();
+    if (!nd) return PNA_OK;
+    inf::inflate_kernel<<<(nd + inf::INFLATE_CTA - 1) / inf::INFLATE_CTA, inf::INFLATE_CTA, sizeof(inf::Tables) * inf::INFLATE_CTA,
+                          ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_deflate.p, nd, P->d_out.p, size_only);
+    LAUNCHED();
+    return PNA_OK;
+}
+static int launch_store(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    const uint32_t nc = (uint32_t)P->h_copy.size();
+    if (!nc) return PNA_OK;
+    const uint32_t grid = std::min<uint32_t>((nc + 7) / 8, (uint32_t)ctx->sm_count * 8);
+    copy_jobs_kernel<<<grid, 256, 0, ctx->stream>>>(P->d_out.p, P->d_buf.p, P->d_copy.p, nc);
+    LAUNCHED();
+    return PNA_OK;
+}
+
+// One-time preparation: learn block / literal / sequence counts (and output sizes when no hint was
+// given), allocate, lay out.  Runs the front kernels once; launch_all() re-runs everything.
+static int decode_prepare(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    int rc;
+    const uint32_t nz = (uint32_t)P->h_ze.size();
+    CK(cudaMemcpyAsync(P->d_entries.p, P->h_entries.data(), P->n * sizeof(EntryRec), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_cipher(P))) return rc;
+    if (nz) {
+        CK(P->d_ze.reserve(nz));
+        CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = launch_zstd_front(P, true))) return rc;
+        CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        uint64_t nb = 0;
+        for (auto& z : P->h_ze) { z.blk_begin = (uint32_t)nb; nb += z.blk_count; }
+        if (nb > 0xFFFFFFF0ull) return PNA_E_OOM;
+        P->n_blocks = (uint32_t)nb;
+        CK(P->d_blocks.reserve(nb));
+        CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = launch_zstd_front(P, false))) return rc;
+        CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        uint64_t lit = 0, seq = 0;
+        std::vector<uint64_t> lb(P->n, 0), sb(P->n, 0);
+        for (auto& z : P->h_ze) {
+            z.lit_base = lit; z.seq_base = seq;
+            lb[z.entry] = lit; sb[z.entry] = seq;
+            lit += z.lit_total; seq += z.seq_total;
+        }
+        P->lit_total = lit; P->seq_total = seq;
+        CK(P->d_lits.reserve(lit + 256));
+        CK(P->d_sll.reserve(seq + 32)); CK(P->d_sml.reserve(seq + 32)); CK(P->d_sof.reserve(seq + 32));
+        CK(P->d_lit_base.reserve(P->n)); CK(P->d_seq_base.reserve(P->n));
+        CK(cudaMemcpyAsync(P->d_lit_base.p, lb.data(), P->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->d_seq_base.p, sb.data(), P->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // lb/sb are locals
+    }
+    if (P->need_sizing) {
+        // exact sizes: zstd from the entropy+prefix stages, deflate from a count-only pass, store = comp_len
+        if ((rc = launch_zstd_entropy(P))) return rc;
+        if ((rc = launch_inflate(P, 1))) return rc;
+        std::vector<EntryRec> dev(P->n);
+        CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t i = 0; i < P->n; i++) {
+            EntryRec& e = P->h_entries[i];
+            if (e.status != ST_OK || e.out_cap != UINT64_MAX) continue;
+            if (dev[i].status != ST_OK) { e.out_cap = 0; continue; }   // will fail again in the real run
+            e.out_cap = e.compression == PNA_COMPRESSION_NO ? dev[i].comp_len : dev[i].out_len;
+            if (e.compression == PNA_COMPRESSION_NO) e.comp_len = dev[i].comp_len;
+        }
+    }
+    if ((rc = decode_layout_out(P))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    P->prepared = true;
+    return PNA_OK;
+}
+
+static int decode_launch_all(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    int rc;
+    const uint64_t l0 = ctx->launches;
+    CK(cudaMemcpyAsync(P->d_entries.p, P->d_entries_init.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = launch_cipher(P))) return rc;
+    if ((rc = launch_zstd_front(P, false))) return rc;
+    if ((rc = launch_zstd_entropy(P))) return rc;
+    if ((rc = launch_zstd_lz(P))) return rc;
+    if ((rc = launch_inflate(P, 0))) return rc;
+    if ((rc = launch_store(P))) return rc;
+    P->launches_per_run = ctx->launches - l0;
+    return PNA_OK;
+}
+
+static int decode_plan_create_ex(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint64_t* caps, pna_plan** plan) {
+    if (!ctx || !plan || (!descs && n)) return PNA_E_BAD_ARG;
+    *plan = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    pna_plan* P = new pna_plan();
+    int rc = decode_plan_build(ctx, descs, n, caps, P);
+    if (rc) { delete P; return rc; }
+    *plan = P;
+    return PNA_OK;
+}
+extern "C" int pna_cuda_decode_plan_create(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_plan** plan) {
+    return decode_plan_create_ex(ctx, descs, n, nullptr, plan);
+}
+extern "C" int pna_cuda_decode_plan_run(pna_plan* P) {
+    if (!P || P->kind != 0) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (P->n == 0) return PNA_OK;
+    if (!P->prepared) { int rc = decode_prepare(P); if (rc) return rc; }
+    return decode_launch_all(P);
+}
+extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* status) {
+    if (!P || P->kind != 0 || ((!out || !status) && P->n)) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (P->n == 0) return PNA_OK;
+    if (!P->prepared) return PNA_E_BAD_ARG;
+    std::vector<EntryRec> dev(P->n);
+    CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t plain = 0;
+    for (uint32_t i = 0; i < P->n; i++) {
+        const EntryRec& e = dev[i];
+        int32_t st = e.status;
+        uint64_t len = e.compression == PNA_COMPRESSION_NO ? e.comp_len : e.out_len;
+        if (P->h_entries[i].status != ST_OK) { st = P->h_entries[i].status; len = 0; }
+        if (st == ST_OK && len > e.out_cap) st = ST_NOSPACE;
+        if (st == ST_OK && len > out[i].cap) st = ST_NOSPACE;
+        out[i].len = (st == ST_OK || st == ST_NOSPACE) ? len : 0;
+        status[i] = st;
+        if (st == ST_OK && len) {
+            CK(cudaMemcpyAsync(out[i].ptr, P->d_out.p + e.out_off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            plain += len;
+        }
+    }
+    P->plain_bytes = plain;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PNA_OK;
+}
+extern "C" int pna_cuda_plan_stats(pna_plan* P, uint64_t* stream_bytes, uint64_t* plain_bytes, uint64_t* launches_per_run) {
+    if (!P) return PNA_E_BAD_ARG;
+    if (stream_bytes) *stream_bytes = P->stream_bytes;
+    if (plain_bytes) *plain_bytes = P->plain_bytes;
+    if (launches_per_run) *launches_per_run = P->launches_per_run;
+    return PNA_OK;
+}
+extern "C" void pna_cuda_plan_destroy(pna_plan* P) {
+    if (!P) return;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete P;
+}
+extern "C" int pna_cuda_decode_batch(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_buf* out, int32_t* status) {
+    if (!ctx || ((!descs || !out || !status) && n)) return PNA_E_BAD_ARG;
+    if (n == 0) return PNA_OK;
+    std::vector<uint64_t> caps(n);
+    for (uint32_t i = 0; i < n; i++) caps[i] = out[i].cap;
+    pna_plan* P = nullptr;
+    int rc = decode_plan_create_ex(ctx, descs, n, caps.data(), &P);
+    if (rc) return rc;
+    rc = pna_cuda_decode_plan_run(P);
+    if (rc == PNA_OK) rc = pna_cuda_decode_plan_fetch(P, out, status);
+    pna_cuda_plan_destroy(P);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-cipher test hook
+extern "C" int pna_cuda_ecb(pna_ctx* ctx, int encryption, int encrypt, const uint8_t key[32], const uint8_t* in, uint64_t n_bytes,
+                            uint8_t* out) {
+    if (!ctx || !key || (!in && n_bytes) || (!out && n_bytes)) return PNA_E_BAD_ARG;
+    if (encryption != 1 && encryption != 2) return PNA_E_BAD_ARG;
+    const uint64_t nb = n_bytes / 16;
+    if (!nb) return PNA_OK;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    DevKeys dk;
+    memset(&dk, 0, sizeof dk);
+    if (encryption == 1) {
+        AesKey ak; aes256_expand_key(&ctx->h_aes, key, &ak);
+        memcpy(dk.aes_rk, ak.rk, sizeof ak.rk); memcpy(dk.aes_dk, ak.dk, sizeof ak.dk);
+    } else {
+        CamelliaKey ck; camellia256_expand_key(&ctx->h_cam, key, &ck);
+        memcpy(dk.cam_ek, ck.ek, sizeof ck.ek); memcpy(dk.cam_dk, ck.dk, sizeof ck.dk);
+    }
+    DevArr<uint8_t> d_in, d_out; DevArr<DevKeys> d_key;
+    CK(d_in.reserve(nb * 16 + 64)); CK(d_out.reserve(nb * 16)); CK(d_key.reserve(1));
+    int rc = PNA_OK;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_in.p, in, nb * 16, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_key.p, &dk, sizeof dk, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+        ctx->fail("ecb upload", e); rc = PNA_E_CUDA;
+    }
+    if (rc == PNA_OK) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((nb + 255) / 256, (uint64_t)ctx->sm_count * 4);
+        ecb_kernel<<<grid, 256, 256 * 32 * 4 + 256, ctx->stream>>>(encryption, encrypt, d_key.p, ctx->d_aes, ctx->d_cam, d_in.p, nb, d_out.p);
+        ctx->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess ||
+            (e = cudaMemcpyAsync(out, d_out.p, nb * 16, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+            ctx->fail("ecb run", e); rc = PNA_E_CUDA;
+        }
+    }
+    d_in.release(); d_out.release(); d_key.release();
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// seam 3: encode -- implemented in encode_host.cuh on top of kernels_encode.cuh
+#include "encode_host.cuh"

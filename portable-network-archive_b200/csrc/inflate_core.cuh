@@ -1,0 +1,264 @@
+// inflate_core.cuh -- zlib (RFC 1950) / DEFLATE (RFC 1951) decode, one stream per thread, PNA_HD.
+//
+// Replaces `flate2::bufread::ZlibDecoder` at /root/reference/lib/src/entry/read.rs:179
+// (flate2 1.1.9 -> miniz_oxide 0.8.5, not vendored).  Error behaviour follows flate2's zio::read:
+// a corrupt stream is io::ErrorKind::InvalidInput ("corrupt deflate stream"); a TRUNCATED stream
+// returns the bytes produced so far without an error; bytes after the Adler-32 trailer are ignored.
+//
+// Sizing contract: when the output does not fit, decoding continues in count-only mode (the symbol
+// stream never depends on output bytes), and ST_NOSPACE is returned with the exact decoded length.
+#pragma once
+#include "common.cuh"
+
+namespace pna {
+namespace inf {
+
+constexpr int MAXBITS = 15, MAXL = 288, MAXD = 30;
+constexpr int FAST_BITS = 9;
+
+// Per-stream decoding tables (canonical Huffman): an FB-bit direct table in front of the
+// count/symbol arrays (FB = 0: no direct table).  fast[] entry: (symbol << 4) | length, 0 = not
+// resolvable in FB bits.  The literal/length code gets a 9-bit table, the distance code none, so that
+// one stream's tables are 1.7 KB and 64 streams fit one CTA's shared memory.
+template <int NSYM, int FB>
+struct Huff {
+    uint16_t count[MAXBITS + 1];
+    uint16_t symbol[NSYM];
+    uint16_t fast[FB ? (1 << FB) : 1];
+};
+struct Tables {
+    Huff<MAXL, FAST_BITS> len;
+    Huff<MAXD + 2, 0> dist;
+    uint16_t _pad;   // odd number of 32-bit words per stream: lanes start on different banks
+};
+
+struct Bits {
+    const uint8_t* p;
+    uint64_t n, pos;
+    uint64_t buf;
+    int cnt;
+    PNA_HD void init(const uint8_t* in, uint64_t len) { p = in; n = len; pos = 0; buf = 0; cnt = 0; }
+    PNA_HD void fill(int need) {
+        while (cnt < need) {
+            if (pos < n) buf |= (uint64_t)p[pos] << cnt;   // zeros beyond the end; overrun() tells
+            pos++;
+            cnt += 8;
+        }
+    }
+    PNA_HD uint64_t consumed_bits() const { return pos * 8 - (uint64_t)cnt; }
+    PNA_HD bool overrun() const { return consumed_bits() > n * 8; }   // consumed bits that do not exist
+    PNA_HD void align_byte() { pos = (consumed_bits() + 7) / 8; buf = 0; cnt = 0; }
+    PNA_HD uint32_t get(int k) {
+        if (k == 0) return 0;
+        fill(k);
+        uint32_t v = (uint32_t)buf & ((1u << k) - 1u);
+        buf >>= k; cnt -= k;
+        return v;
+    }
+};
+
+PNA_HD uint32_t rev_bits(uint32_t v, int n) {
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+
+// canonical table from code lengths; returns 0 ok, <0 over-subscribed, >0 incomplete (puff semantics)
+template <int NSYM, int FB>
+PNA_HD int build(Huff<NSYM, FB>* h, const uint8_t* length, int n) {
+    for (int l = 0; l <= MAXBITS; l++) h->count[l] = 0;
+    for (int s = 0; s < n; s++) h->count[length[s]]++;
+    if (FB) for (int i = 0; i < (1 << FB); i++) h->fast[i] = 0;
+    if (h->count[0] == n) return 0;
+    int left = 1;
+    for (int l = 1; l <= MAXBITS; l++) {
+        left <<= 1;
+        left -= h->count[l];
+        if (left < 0) return left;
+    }
+    uint16_t offs[MAXBITS + 1];
+    offs[1] = 0;
+    for (int l = 1; l < MAXBITS; l++) offs[l + 1] = offs[l] + h->count[l];
+    for (int s = 0; s < n; s++)
+        if (length[s]) h->symbol[offs[length[s]]++] = (uint16_t)s;
+    // fast table: canonical codes, bit-reversed because DEFLATE packs Huffman codes MSB first
+    if (FB) {
+        uint32_t code = 0;
+        int idx = 0;
+        for (int l = 1; l <= FB; l++) {
+            for (int k = 0; k < h->count[l]; k++, idx++, code++) {
+                uint32_t r = rev_bits(code, l);
+                uint16_t e = (uint16_t)((h->symbol[idx] << 4) | l);
+                for (uint32_t f = r; f < (1u << FB); f += (1u << l)) h->fast[f] = e;
+            }
+            code <<= 1;
+        }
+    }
+    return left;
+}
+
+template <int NSYM, int FB>
+PNA_HD int decode_sym(Bits& b, const Huff<NSYM, FB>* h) {
+    b.fill(MAXBITS);
+    if (FB) {
+        uint16_t e = h->fast[(uint32_t)b.buf & ((1u << FB) - 1u)];
+        if (e) {
+            int l = e & 15;
+            b.buf >>= l; b.cnt -= l;
+            return e >> 4;
+        }
+    }
+    // slow path: canonical walk, one bit at a time (puff)
+    int code = 0, first = 0, index = 0;
+    uint64_t bits = b.buf;
+    for (int l = 1; l <= MAXBITS; l++) {
+        code |= (int)(bits & 1);
+        bits >>= 1;
+        int count = h->count[l];
+        if (code - count < first) {
+            b.buf >>= l; b.cnt -= l;
+            return h->symbol[index + (code - first)];
+        }
+        index += count;
+        first += count;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+PNA_HD uint32_t len_base(int s) {   // s = symbol - 257
+    return s < 8 ? (uint32_t)(3 + s) : s == 28 ? 258u : (uint32_t)(((4 + (s & 3)) << ((s >> 2) - 1)) + 3);
+}
+PNA_HD int len_extra(int s) { return s < 8 ? 0 : s == 28 ? 0 : (s >> 2) - 1; }
+PNA_HD uint32_t dist_base(int s) { return s < 4 ? (uint32_t)(1 + s) : (uint32_t)(((2 + (s & 1)) << ((s >> 1) - 1)) + 1); }
+PNA_HD int dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
+
+// Decode one zlib stream.  `t` is per-thread scratch.  Returns status; *out_len = bytes produced
+// (exact decoded length even when it exceeds cap -> ST_NOSPACE).
+PNA_HD int32_t inflate_zlib(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, Tables* t) {
+    *out_len = 0;
+    if (n == 0) return ST_OK;   // nothing in, nothing out (zio::read: eof with no data -> Ok(0))
+    if (n < 2) return ST_OK;    // truncated header: short read, no error
+    uint32_t cmf = in[0], flg = in[1];
+    if (((cmf << 8) | flg) % 31 != 0 || (cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 0x20)) return ST_INVALID_INPUT;
+    Bits b;
+    b.init(in + 2, n - 2);
+    uint64_t op = 0;
+    uint32_t a1 = 1, a2 = 0;       // Adler-32 running sums
+    uint32_t a_pending = 0;        // bytes since the last modulo
+    bool counting = false;         // true once the output no longer fits
+#define PNA_INF_TRUNC() do { *out_len = op; return counting ? ST_NOSPACE : ST_OK; } while (0)
+#define PNA_INF_EMIT(c_) do { uint8_t c__ = (uint8_t)(c_); if (op < cap) { out[op] = c__; a1 += c__; a2 += a1; \
+        if (++a_pending == 5552) { a1 %= 65521u; a2 %= 65521u; a_pending = 0; } } else counting = true; op++; } while (0)
+    int last = 0;
+    while (!last) {
+        last = (int)b.get(1);
+        int type = (int)b.get(2);
+        if (b.overrun()) PNA_INF_TRUNC();
+        if (type == 0) {
+            b.align_byte();
+            if (b.pos + 4 > b.n) PNA_INF_TRUNC();
+            uint32_t len = load_le16(b.p + b.pos), nlen = load_le16(b.p + b.pos + 2);
+            b.pos += 4;
+            if (len != (~nlen & 0xFFFFu)) return ST_INVALID_INPUT;
+            uint64_t avail = b.n - b.pos;
+            uint32_t take = len <= avail ? len : (uint32_t)avail;
+            for (uint32_t i = 0; i < take; i++) PNA_INF_EMIT(b.p[b.pos + i]);
+            b.pos += take;
+            if (take < len) PNA_INF_TRUNC();
+            continue;
+        }
+        if (type == 3) return ST_INVALID_INPUT;
+        if (type == 1) {
+            uint8_t lengths[MAXL];
+            int s = 0;
+            for (; s < 144; s++) lengths[s] = 8;
+            for (; s < 256; s++) lengths[s] = 9;
+            for (; s < 280; s++) lengths[s] = 7;
+            for (; s < 288; s++) lengths[s] = 8;
+            build(&t->len, lengths, 288);
+            for (s = 0; s < 30; s++) lengths[s] = 5;
+            build(&t->dist, lengths, 30);
+        } else {
+            uint8_t lengths[MAXL + MAXD + 2];
+            int nlen = (int)b.get(5) + 257, ndist = (int)b.get(5) + 1, ncode = (int)b.get(4) + 4;
+            if (b.overrun()) PNA_INF_TRUNC();
+            if (nlen > 286 || ndist > 30) return ST_INVALID_INPUT;
+            const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            int i = 0;
+            for (; i < ncode; i++) lengths[order[i]] = (uint8_t)b.get(3);
+            for (; i < 19; i++) lengths[order[i]] = 0;
+            if (b.overrun()) PNA_INF_TRUNC();
+            if (build(&t->len, lengths, 19) != 0) return ST_INVALID_INPUT;  // code-length code must be complete
+            i = 0;
+            while (i < nlen + ndist) {
+                int sym = decode_sym(b, &t->len);
+                if (b.overrun()) PNA_INF_TRUNC();
+                if (sym < 0) return ST_INVALID_INPUT;
+                if (sym < 16) lengths[i++] = (uint8_t)sym;
+                else {
+                    int rep, val = 0;
+                    if (sym == 16) {
+                        if (i == 0) return ST_INVALID_INPUT;
+                        val = lengths[i - 1];
+                        rep = 3 + (int)b.get(2);
+                    } else if (sym == 17) rep = 3 + (int)b.get(3);
+                    else rep = 11 + (int)b.get(7);
+                    if (b.overrun()) PNA_INF_TRUNC();
+                    if (i + rep > nlen + ndist) return ST_INVALID_INPUT;
+                    while (rep--) lengths[i++] = (uint8_t)val;
+                }
+            }
+            if (lengths[256] == 0) return ST_INVALID_INPUT;
+            int err = build(&t->len, lengths, nlen);
+            if (err && (err < 0 || nlen != t->len.count[0] + t->len.count[1])) return ST_INVALID_INPUT;
+            err = build(&t->dist, lengths + nlen, ndist);
+            if (err && (err < 0 || ndist != t->dist.count[0] + t->dist.count[1])) return ST_INVALID_INPUT;
+        }
+        // symbols
+        for (;;) {
+            int sym = decode_sym(b, &t->len);
+            if (b.overrun()) PNA_INF_TRUNC();
+            if (sym < 0) return ST_INVALID_INPUT;
+            if (sym < 256) {
+                PNA_INF_EMIT(sym);
+            } else if (sym == 256) {
+                break;
+            } else {
+                sym -= 257;
+                if (sym >= 29) return ST_INVALID_INPUT;
+                uint32_t len = len_base(sym) + b.get(len_extra(sym));
+                int ds = decode_sym(b, &t->dist);
+                if (b.overrun()) PNA_INF_TRUNC();
+                if (ds < 0 || ds >= 30) return ST_INVALID_INPUT;
+                uint32_t dist = dist_base(ds) + b.get(dist_extra(ds));
+                if (b.overrun()) PNA_INF_TRUNC();
+                if (dist > op) return ST_INVALID_INPUT;
+                if (op + len <= cap) {
+                    for (uint32_t k = 0; k < len; k++) PNA_INF_EMIT(out[op - dist]);
+                } else {
+                    for (uint32_t k = 0; k < len; k++) {
+                        if (op < cap) PNA_INF_EMIT(out[op - dist]);
+                        else { counting = true; op++; }
+                    }
+                }
+            }
+        }
+    }
+    *out_len = op;
+    if (counting) return ST_NOSPACE;
+    // Adler-32 trailer (big endian) after discarding to the byte boundary
+    uint64_t tpos = (b.consumed_bits() + 7) / 8;
+    if (tpos + 4 > b.n) return ST_OK;  // truncated trailer: short read, no error
+    const uint8_t* tr = b.p + tpos;
+    uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
+    a1 %= 65521u; a2 %= 65521u;
+    if (want != ((a2 << 16) | a1)) return ST_INVALID_INPUT;
+    return ST_OK;
+#undef PNA_INF_TRUNC
+#undef PNA_INF_EMIT
+}
+
+}  // namespace inf
+}  // namespace pna

@@ -155,3 +155,10 @@ extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uin
     }
     return ST_OK;
 }
+
+// ---- inflate (one stream per thread on the GPU; same function here)
+#include "../../portable-network-archive_b200/csrc/inflate_core.cuh"
+extern "C" int hc_inflate(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+    static pna::inf::Tables t;
+    return pna::inf::inflate_zlib(in, n, out, cap, out_len, &t);
+}

@@ -1,0 +1,286 @@
+"""GPU tier: the CUDA path through the C ABI vs the CPU oracle, bit-exact (integer/byte work)."""
+import hashlib
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import corpus
+from test_oracle import KAT_CBC
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------- seam 1: CRC
+def test_crc_kats(ctx):
+    got = ctx.crc32([b"FDAT" + bytes([0xAA, 0xBB, 0xCC, 0xDD]), b"FDAT" + bytes([1, 2, 3]), b"AEND", b""])
+    assert [int(x) for x in got] == [0x47F32B10, 2776590148, 0x6BF6486D, 0]
+
+
+def test_crc_ragged_spans(ctx, oracle):
+    rnd = random.Random(2)
+    blob = os.urandom(3_000_000)
+    spans = []
+    for n in [0, 1, 2, 3, 4, 15, 16, 17, 31, 32, 33, 511, 512, 513, 4095, 4096, 65535, 65536, 65537, 131072, 1_000_003]:
+        s = rnd.randrange(0, len(blob) - n + 1)
+        spans.append(blob[s:s + n])
+    spans += [blob[s:s + rnd.randrange(0, 3000)] for s in (rnd.randrange(0, len(blob) - 3000) for _ in range(2000))]
+    got = ctx.crc32(spans)
+    assert [int(x) for x in got] == [zlib.crc32(s) for s in spans]
+    assert int(got[5]) == oracle.crc32(spans[5])
+
+
+def test_crc_image_every_alignment(ctx):
+    img = np.frombuffer(os.urandom(200_000), dtype=np.uint8)
+    offs, lens = [], []
+    for a in range(0, 40):
+        for n in (0, 1, 7, 16, 100, 513, 70_000):
+            offs.append(1000 + a)
+            lens.append(n)
+    got = ctx.crc32_image(img, offs, lens)
+    want = [zlib.crc32(img[o:o + n].tobytes()) for o, n in zip(offs, lens)]
+    assert [int(x) for x in got] == want
+
+
+def test_crc_checksum_of_checksums_large(ctx):
+    """Size-independent property at BASELINE scale: crc(A||B) == combine(crc(A), crc(B)) (zlib identity)."""
+    blob = np.frombuffer(np.random.default_rng(1).bytes(64 << 20), dtype=np.uint8)
+    whole = int(ctx.crc32([blob])[0])
+    assert whole == zlib.crc32(blob.tobytes())
+    parts = ctx.crc32_image(blob, [0, 10_000_001], [10_000_001, blob.size - 10_000_001])
+    c = zlib.crc32(blob[10_000_001:].tobytes(), int(parts[0]))
+    assert c == whole
+
+
+# ------------------------------------------------------------------------------------------- ciphers
+def test_block_cipher_kats(ctx, oracle):
+    key, iv, pt = bytes([0x11]) * 32, bytes([0x22]) * 16, b"PNA test vector!"
+    for enc in (1, 2):
+        want = bytes.fromhex(KAT_CBC[enc])
+        b0 = ctx.ecb(enc, True, key, bytes(a ^ b for a, b in zip(pt, iv)))
+        assert b0 == want[:16]
+        b1 = ctx.ecb(enc, True, key, bytes(a ^ 16 for a in b0))
+        assert b1 == want[16:]
+        assert ctx.ecb(enc, False, key, want[:16]) == bytes(a ^ b for a, b in zip(pt, iv))
+        data = os.urandom(16 * 1000)
+        k2 = os.urandom(32)
+        assert ctx.ecb(enc, True, k2, data) == oracle.ecb(enc, True, k2, data)
+        assert ctx.ecb(enc, False, k2, data) == oracle.ecb(enc, False, k2, data)
+
+
+def _mk(oracle, plain, comp, enc, mode, key, split=None, hint=True, level=-1):
+    stream = oracle.encode_stream(plain, comp, level, enc, mode, key, os.urandom(16))
+    if split is None:
+        bodies = [stream]
+    else:
+        cuts = sorted(set(min(c, len(stream)) for c in split))
+        bodies = [stream[a:b] for a, b in zip([0] + cuts, cuts + [len(stream)])]
+    return {"bodies": bodies, "compression": comp, "encryption": enc, "cipher_mode": mode, "key": key,
+            "raw_size_hint": len(plain) if hint else None}
+
+
+CIPHERS = [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1)]
+
+
+@pytest.mark.parametrize("comp", [0, 1, 2])
+def test_decode_cross_product(ctx, oracle, comp):
+    """archive.rs:221-362: every (compression x cipher x mode), sizes incl. empty and block-boundary cases."""
+    key = os.urandom(32)
+    entries, want = [], []
+    for i, n in enumerate([0, 1, 15, 16, 17, 31, 32, 33, 1000, 16384, 131072, 131073, 700_000]):
+        for enc, mode in CIPHERS:
+            plain = corpus.make_file(100 * comp + i, n)
+            entries.append(_mk(oracle, plain, comp, enc, mode, key, hint=(i % 2 == 0)))
+            want.append(plain)
+    outs, st, lens = ctx.decode_batch(entries)
+    assert st == [0] * len(entries)
+    for o, w in zip(outs, want):
+        assert o.tobytes() == w
+    # with exact caps in one call (raw_size_hint path)
+    outs, st, _ = ctx.decode_batch(entries, caps=[len(w) for w in want])
+    assert st == [0] * len(entries) and all(o.tobytes() == w for o, w in zip(outs, want))
+
+
+def test_decode_adversarial_chunk_splits(ctx, oracle):
+    """IV and cipher blocks straddling FDAT boundaries; 1-byte and 16-byte chunks (util/io.rs:24-33,
+    archive.rs:969 chunk_split_one_byte, fixture solid_zstd_aes_cbc.pna with 16-byte SDATs)."""
+    key = os.urandom(32)
+    plain = corpus.make_file(3, 5000)
+    entries, want = [], []
+    for comp in (0, 1, 2):
+        for enc, mode in CIPHERS:
+            for split in ([1], [7], [15, 16, 17], [16], list(range(1, 200)), list(range(16, 4000, 16)), [3, 40, 41, 2000]):
+                entries.append(_mk(oracle, plain, comp, enc, mode, key, split=split))
+                want.append(plain)
+    outs, st, _ = ctx.decode_batch(entries)
+    assert st == [0] * len(entries)
+    assert all(o.tobytes() == w for o, w in zip(outs, want))
+
+
+def test_decode_error_classes(ctx, oracle, pna):
+    key = os.urandom(32)
+    plain = corpus.make_file(4, 3000)
+    good = _mk(oracle, plain, 2, 1, 0, key)
+    s = bytes(good["bodies"][0])
+    cases = [
+        (dict(good, bodies=[s[:10]]), pna.E_UNEXPECTED_EOF),                   # shorter than the IV  entry/read.rs:80
+        (dict(good, bodies=[s[:16 + 24]]), pna.E_UNEXPECTED_EOF),              # partial CBC block     block/read.rs:90
+        (dict(good, bodies=[s[:16]]), pna.E_UNEXPECTED_EOF),                   # no first block       block/read.rs:36
+        (dict(good, key=os.urandom(32)), None),                               # wrong key: bad pad or corrupt zstd
+        (dict(good, compression=4), pna.E_UNSUPPORTED),                        # xz
+        (dict(good, cipher_mode=2), pna.E_UNSUPPORTED),                        # GCM
+        (dict(good, encryption=7), pna.E_UNSUPPORTED),
+    ]
+    z = _mk(oracle, plain, 2, 0, 0, key)
+    zs = bytes(z["bodies"][0])
+    cases += [(dict(z, bodies=[zs[:len(zs) // 2]]), pna.E_UNEXPECTED_EOF),     # truncated frame
+              (dict(z, bodies=[b"\x00" + zs[1:]]), pna.E_INVALID_DATA)]        # bad magic
+    d = _mk(oracle, plain, 1, 0, 0, key)
+    ds = bytearray(bytes(d["bodies"][0]))
+    ds[0] ^= 0x0F
+    cases += [(dict(d, bodies=[bytes(ds)]), pna.E_INVALID_INPUT)]              # "corrupt deflate stream"
+    tr = bytes(d["bodies"][0])[:-8]
+    entries = [c for c, _ in cases] + [dict(d, bodies=[tr], raw_size_hint=None)]
+    outs, st, lens = ctx.decode_batch(entries, caps=[len(plain) + 64] * len(entries))
+    for (c, want), got in zip(cases, st):
+        if want is None:
+            assert got != 0
+        else:
+            assert got == want, (want, got)
+    # truncated zlib stream: flate2 returns the bytes decoded so far without an error
+    assert st[-1] == 0 and outs[-1].tobytes() == oracle.decompress(1, tr, len(plain) + 64)
+    # too-small output: NOSPACE with the required length
+    outs, st, lens = ctx.decode_batch([good, z, d], caps=[10, 10, 10])
+    assert st == [pna.E_NOSPACE] * 3 and list(lens) == [len(plain)] * 3
+
+
+def test_zstd_levels_and_shapes(ctx, oracle):
+    key = os.urandom(32)
+    entries, want = [], []
+    for level in (1, 3, 7, 12, 19):
+        for i, n in enumerate([200, 70_000, 400_000]):
+            plain = corpus.make_file(500 + 10 * level + i, n)
+            entries.append(_mk(oracle, plain, 2, 0, 0, key, level=level, hint=False))
+            want.append(plain)
+    for plain in (bytes(1 << 20), os.urandom(300_000), b"ab" * 200_000, bytes(range(256)) * 3000):
+        entries.append(_mk(oracle, plain, 2, 0, 0, key, hint=True))
+        want.append(plain)
+    c = oracle.compress(2, want[0], 3)
+    entries.append({"bodies": [c, c], "compression": 2, "raw_size_hint": None})   # concatenated frames
+    want.append(want[0] + want[0])
+    outs, st, _ = ctx.decode_batch(entries)
+    assert st == [0] * len(entries)
+    assert all(o.tobytes() == w for o, w in zip(outs, want))
+
+
+def test_zstd_corruption_never_crashes_and_matches_when_accepted(ctx, oracle):
+    rnd = random.Random(5)
+    plain = corpus.make_file(8, 60_000)
+    c = oracle.compress(2, plain, 3)
+    entries, refs = [], []
+    for _ in range(200):
+        b = bytearray(c)
+        b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        entries.append({"bodies": [bytes(b)], "compression": 2, "raw_size_hint": None})
+        try:
+            refs.append(oracle.decompress(2, bytes(b), len(plain) + 4096))
+        except oracle.OracleError:
+            refs.append(None)
+    outs, st, _ = ctx.decode_batch(entries, caps=[len(plain) + 4096] * len(entries))
+    disagree = 0
+    for o, s, r in zip(outs, st, refs):
+        if s == 0 and r is not None:
+            assert o.tobytes() == r
+        elif (s == 0) != (r is not None):
+            disagree += 1
+    assert disagree <= 6
+
+
+# ------------------------------------------------------------------------------------------- golden archives
+def test_golden_archives_through_archive_api(ctx, pna, golden):
+    """lib/tests/extract_compatibility.rs:104-213, extract_solid_compatibility.rs:96-112 read like this."""
+    for name, info in golden["archives"].items():
+        if name.startswith("multipart"):
+            continue
+        buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+        opts = pna.ReadOptions.with_password(golden["password"])
+        opts._keys.update({k: bytes.fromhex(v) for k, v in info["keys"].items()})   # KDF precomputed by make_golden.py
+        archive = pna.Archive.read_header(buf, ctx)      # indexes + checks every chunk CRC on the GPU
+        if info["expect"] != "ok":
+            with pytest.raises(pna.PnaError) as ei:
+                list(archive.read_all(opts))
+            assert ei.value.kind == pna.E_UNSUPPORTED
+            continue
+        got = [(e.name, d) for e, d in archive.read_all(opts)]
+        assert [n for n, _ in got] == [e["name"] for e in info["entries"]], name
+        for (n, d), e in zip(got, info["entries"]):
+            assert len(d) == e["size"] and hashlib.sha256(d).hexdigest() == e["sha256"], (name, n)
+
+
+def test_entry_reader_single(ctx, pna, golden):
+    info = golden["archives"]["zstd_aes_ctr.pna"]
+    buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+    opts = pna.ReadOptions.with_password(golden["password"])
+    opts._keys.update({k: bytes.fromhex(v) for k, v in info["keys"].items()})
+    n = 0
+    for e in pna.Archive.read_header(buf, ctx).entries():
+        if e.data_kind == pna.DataKind.FILE:
+            d = e.reader(opts)
+            assert hashlib.sha256(d).hexdigest() == info["entries"][n]["sha256"]
+            n += 1
+    assert n == 9   # extract_compatibility.rs:8-92 asserts exactly 9 file entries
+
+
+def test_broken_chunk_detected(ctx, pna, golden):
+    """io.rs:297-376 / bytes.rs:161-232: a flipped data byte -> InvalidData 'broken chunk'."""
+    info = golden["archives"]["zstd.pna"]
+    buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8).copy()
+    buf[5000] ^= 0x40
+    with pytest.raises(pna.PnaError) as ei:
+        pna.Archive.read_header(buf, ctx)
+    assert ei.value.kind == pna.E_INVALID_DATA and "broken chunk" in str(ei.value)
+
+
+def test_multipart_entry(ctx, pna, golden):
+    """extract_multipart_compatibility.rs:36: one entry's FDAT stream continues in the next part."""
+    mod = __import__("importlib").import_module("portable-network-archive_b200.archive")
+    bodies, hdr = [], None
+    for part in ("multipart.part1.pna", "multipart.part2.pna"):
+        buf = np.fromfile(os.path.join(golden["dir"], "ref", part), dtype=np.uint8)
+        for ch in mod.index_archive(buf, 8):
+            if ch.ty == b"FHED":
+                hdr = bytes(buf[ch.off:ch.off + ch.length])
+            if ch.ty == b"FDAT":
+                bodies.append(buf[ch.off:ch.off + ch.length])
+    outs, st, _ = ctx.decode_batch([{"bodies": bodies, "compression": hdr[3], "encryption": hdr[4], "cipher_mode": hdr[5]}])
+    want = open(os.path.join(golden["dir"], "ref", "multipart_test.txt"), "rb").read()
+    assert st == [0] and outs[0].tobytes() == want
+
+
+# ------------------------------------------------------------------------------------------- scale properties
+def test_large_batch_property(ctx, oracle):
+    """BASELINE cfg2 shape at reduced count: 4 MiB files, zstd 3 + AES-256-CTR; SHA-256 per entry vs source."""
+    key = os.urandom(32)
+    files = [corpus.make_file(9000 + i, 4 << 20) for i in range(24)]
+    entries = [_mk(oracle, f, 2, 1, 1, key) for f in files]
+    plan = ctx.decode_plan(entries)
+    plan.run()
+    plan.run()    # idempotent: a second run over the HBM-resident input gives the same bytes
+    outs, st, _ = plan.fetch([len(f) for f in files])
+    assert st == [0] * len(files)
+    for o, f in zip(outs, files):
+        assert hashlib.sha256(o.tobytes()).digest() == hashlib.sha256(f).digest()
+    plan.close()
+
+
+def test_many_small_deflate_camellia_cbc(ctx, oracle):
+    """BASELINE cfg3 shape at reduced count: <=16 KiB files, zlib 6 + Camellia-256-CBC."""
+    key = os.urandom(32)
+    rnd = random.Random(4)
+    files = [corpus.make_file(20000 + i, rnd.randrange(1, 16385)) for i in range(3000)]
+    entries = [_mk(oracle, f, 1, 2, 0, key) for f in files]
+    outs, st, _ = ctx.decode_batch(entries, caps=[len(f) for f in files])
+    assert st == [0] * len(files)
+    assert all(o.tobytes() == f for o, f in zip(outs, files))

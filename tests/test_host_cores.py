@@ -1,0 +1,140 @@
+"""CPU tier: the PNA_HD cores (the code the kernels execute) compiled with g++ and pinned on the oracle."""
+import ctypes as C
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import corpus
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hc(built):
+    L = C.CDLL(os.path.join(HERE, "host", "libpna_hostcore.so"))
+    L.hc_crc_span.restype = C.c_uint32
+    L.hc_crc_span.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64]
+    L.hc_zstd_decode.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
+    L.hc_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.hc_ecb.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p]
+    return L
+
+
+def _dec(fn, c, cap):
+    out = C.create_string_buffer(cap or 1)
+    n = C.c_uint64(0)
+    st = fn(c, len(c), out, cap, C.byref(n)) if fn.__name__ == "hc_inflate" else fn(c, len(c), out, cap, C.byref(n), None)
+    return st, out.raw[:n.value] if st == 0 else n.value
+
+
+def test_block_ciphers(hc, oracle):
+    for enc in (1, 2):
+        for _ in range(8):
+            key, data = os.urandom(32), os.urandom(16 * 33)
+            out = C.create_string_buffer(len(data))
+            hc.hc_ecb(enc, 1, key, data, len(data), out)
+            ref = oracle.ecb(enc, True, key, data)
+            assert out.raw == ref
+            hc.hc_ecb(enc, 0, key, ref, len(data), out)
+            assert out.raw == data
+
+
+def test_crc_tiles(hc):
+    img = os.urandom(300000) + bytes(64)
+    rnd = random.Random(1)
+    cases = [(0, 0), (5, 5), (0, 1), (3, 4), (0, 16), (1, 17), (15, 16), (0, 511), (0, 512), (0, 513), (7, 1000),
+             (100, 65636), (100, 65637), (33, 200000), (0, 300000)]
+    cases += [(s, min(300000, s + rnd.choice([0, 1, 3, 20, 100, 600, 5000, 70000, 140000])))
+              for s in (rnd.randrange(0, 299000) for _ in range(100))]
+    for s, e in cases:
+        assert hc.hc_crc_span(img, s, e) == zlib.crc32(img[s:e]), (s, e)
+
+
+@pytest.mark.parametrize("level", [1, 3, 9, 19])
+def test_zstd_core_roundtrip(hc, oracle, level):
+    rnd = random.Random(level)
+    for i, n in enumerate([0, 1, 100, 5000, 140000, 400000 if level <= 3 else 150000]):
+        d = corpus.make_file(1000 * level + i, n) if i % 2 else (os.urandom(n // 3) + bytes(n - n // 3))
+        c = oracle.compress(2, d, level)
+        st, o = _dec(hc.hc_zstd_decode, c, len(d))
+        assert st == 0 and o == d, (level, n, st)
+        if n:
+            st, need = _dec(hc.hc_zstd_decode, c, n - 1)
+            assert st == 5 and need == n
+    d = corpus.make_file(77, 50000)
+    c = oracle.compress(2, d, level)
+    st, o = _dec(hc.hc_zstd_decode, c + c, 2 * len(d))   # concatenated frames (zstd-rs Decoder keeps going)
+    assert st == 0 and o == d + d
+    for cut in (1, 3, 5, 9, len(c) // 2, len(c) - 1):
+        assert _dec(hc.hc_zstd_decode, c[:cut], len(d))[0] != 0
+
+
+def test_zstd_core_golden(hc, oracle, golden):
+    for name in ("zstd.pna", "zstd_with_raw_file_size.pna", "solid_zstd.pna"):
+        info = golden["archives"][name]
+        buf = open(os.path.join(golden["dir"], info["file"]), "rb").read()
+        for e in oracle.read_archive(buf):
+            ref = oracle.decompress(2, e.stream)
+            st, o = _dec(hc.hc_zstd_decode, e.stream, len(ref))
+            assert st == 0 and o == ref, (name, e.name)
+
+
+def test_zstd_core_corruption_agrees_with_libzstd(hc, oracle):
+    rnd = random.Random(9)
+    d = corpus.make_file(5, 60000)
+    c = oracle.compress(2, d, 3)
+    disagree = 0
+    for _ in range(300):
+        b = bytearray(c)
+        b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        st, o = _dec(hc.hc_zstd_decode, bytes(b), len(d) + 4096)
+        try:
+            ref = oracle.decompress(2, bytes(b), len(d) + 4096)
+            rst = 0
+        except oracle.OracleError as ex:
+            rst, ref = ex.status, None
+        if st == 0 and rst == 0:
+            assert o == ref           # both accept: bytes must be identical
+        elif (st == 0) != (rst == 0):
+            disagree += 1             # libzstd versions differ on a few malformed-but-decodable streams
+    assert disagree <= 6
+
+
+def test_inflate_core(hc, oracle, golden):
+    for i, n in enumerate([0, 1, 5, 100, 1000, 16384, 70000, 300000]):
+        for lvl in (0, 1, 6, 9):
+            d = corpus.make_file(i, n)
+            c = zlib.compress(d, lvl)
+            st, o = _dec(hc.hc_inflate, c, len(d))
+            assert st == 0 and o == d
+            assert _dec(hc.hc_inflate, c + b"trailing", len(d)) == (0, d)
+            if n:
+                assert _dec(hc.hc_inflate, c, n // 2) == (5, n)
+            co = zlib.compressobj(lvl, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+            c2 = co.compress(d) + co.flush()
+            assert _dec(hc.hc_inflate, c2, len(d)) == (0, d)
+    info = golden["archives"]["deflate.pna"]
+    for e in oracle.read_archive(open(os.path.join(golden["dir"], info["file"]), "rb").read()):
+        ref = oracle.decompress(1, e.stream)
+        assert _dec(hc.hc_inflate, e.stream, len(ref)) == (0, ref)
+
+
+def test_inflate_core_corruption_and_truncation(hc, oracle):
+    rnd = random.Random(3)
+    d = corpus.make_file(11, 20000)
+    c = zlib.compress(d, 6)
+    for _ in range(300):
+        b = bytearray(c)
+        b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        st, o = _dec(hc.hc_inflate, bytes(b), len(d) + 500)
+        try:
+            ref, rst = oracle.decompress(1, bytes(b), len(d) + 500), 0
+        except oracle.OracleError as ex:
+            ref, rst = None, ex.status
+        assert (st == 0) == (rst == 0) and (st != 0 or o == ref)
+    for cut in (0, 1, 2, 3, 10, len(c) // 2, len(c) - 5, len(c) - 1):   # flate2 zio::read: truncated -> short Ok
+        st, o = _dec(hc.hc_inflate, c[:cut], len(d))
+        assert st == 0 and o == oracle.decompress(1, c[:cut], len(d))
