@@ -39,14 +39,18 @@ __global__ void zstd_count_kernel(const uint8_t* __restrict__ buf, EntryRec* ent
     set_status(entries, e, st);
     ze[i].blk_count = st == ST_OK && entries[e].status == ST_OK ? nb : 0;
 }
-__global__ void zstd_fill_kernel(const uint8_t* __restrict__ buf, const EntryRec* entries, const ZEntry* ze, uint32_t nz,
+// Re-walks the frames (the entry table is reset at the start of every run, so the status has to be
+// re-established here too) and records the blocks of entries whose walk succeeded.
+__global__ void zstd_fill_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, const ZEntry* ze, uint32_t nz,
                                  ZBlock* blocks) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nz) return;
-    if (ze[i].blk_count == 0) return;
     const uint32_t e = ze[i].entry;
+    if (entries[e].status != ST_OK) return;
     uint32_t nb = 0;
-    scan_entry(buf, entries[e].comp_off, entries[e].comp_len, e, blocks + ze[i].blk_begin, &nb);
+    int32_t st = scan_entry(buf, entries[e].comp_off, entries[e].comp_len, e,
+                            ze[i].blk_count ? blocks + ze[i].blk_begin : nullptr, &nb);
+    set_status(entries, e, st);
 }
 __global__ void zstd_parse_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, ZBlock* blocks, uint32_t n_blocks) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
