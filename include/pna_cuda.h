@@ -102,10 +102,20 @@ int pna_cuda_crc32_image(pna_ctx* ctx, const uint8_t* image, uint64_t image_len,
 int pna_cuda_decode_batch(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_buf* out, int32_t* status);
 /* staged form: upload once, run the kernels any number of times on HBM-resident input, fetch once */
 int pna_cuda_decode_plan_create(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_plan** plan);
+/* Same, with seam 1 fused in: crc_spans are the chunks' type||data ranges (normally 4 bytes before each body in the
+ * same archive buffer, so they ride on the same upload), crc_expect the stored CRCs, crc_entry[i] the entry the
+ * chunk belongs to (-1: archive-level chunk).  A mismatch marks the entry PNA_E_INVALID_DATA ("broken chunk",
+ * lib/src/format/chunk.rs:16-21) before it is decoded; pna_cuda_plan_crc_results returns all computed CRCs. */
+int pna_cuda_decode_plan_create_crc(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const pna_span* crc_spans,
+                                    const uint32_t* crc_expect, const int32_t* crc_entry, uint32_t n_spans, pna_plan** plan);
+int pna_cuda_plan_crc_results(pna_plan* plan, uint32_t* crc_out, uint32_t* n_broken);
 int pna_cuda_decode_plan_run(pna_plan* plan);                 /* asynchronous on pna_cuda_stream(ctx) after first call */
 int pna_cuda_decode_plan_fetch(pna_plan* plan, pna_buf* out, int32_t* status);
 /* stream / decoded byte totals of a plan (algorithmic bytes for the roofline: C and U) */
 int pna_cuda_plan_stats(pna_plan* plan, uint64_t* stream_bytes, uint64_t* plain_bytes, uint64_t* launches_per_run);
+/* per-stage device time (CUDA events on pna_cuda_stream) of the plan's last run; returns the number of stages */
+int pna_cuda_plan_stage_ms(pna_plan* plan, float* ms, uint32_t cap);
+const char* pna_cuda_stage_name(uint32_t stage);
 void pna_cuda_plan_destroy(pna_plan* plan);
 
 /* ---- seam 3: encode ---- */

@@ -124,8 +124,8 @@ static void ctr_add(uint8_t ctr[16], uint64_t add) { /* 128-bit big-endian add *
     }
 }
 /* CTR128-BE keystream XOR (both directions).  cipher.rs:26,33; stream/read.rs:39-43 */
-int pna_oracle_ctr(int encryption, const uint8_t key[32], const uint8_t iv[16], const uint8_t* in, size_t n,
-                   uint8_t* out) {
+int pna_oracle_ctr_restated(int encryption, const uint8_t key[32], const uint8_t iv[16], const uint8_t* in, size_t n,
+                            uint8_t* out) {
     blk_t b = {0};
     int rc = blk_init(&b, encryption, key, 1);
     if (rc) return rc;
@@ -144,6 +144,24 @@ int pna_oracle_ctr(int encryption, const uint8_t key[32], const uint8_t iv[16], 
         done += k;
     }
     blk_free(&b);
+    return ORA_OK;
+}
+/* Same function through OpenSSL's own CTR mode (full-width 128-bit big-endian counter == ctr::Ctr128BE); this is the
+ * pipelined AES-NI path and is what the CPU baseline times.  tests/test_oracle.py checks it against the restated
+ * counter above. */
+int pna_oracle_ctr(int encryption, const uint8_t key[32], const uint8_t iv[16], const uint8_t* in, size_t n,
+                   uint8_t* out) {
+    const EVP_CIPHER* ci = encryption == 1 ? EVP_aes_256_ctr() : encryption == 2 ? EVP_camellia_256_ctr() : NULL;
+    if (!ci) return ORA_UNSUPPORTED;
+    EVP_CIPHER_CTX* c = EVP_CIPHER_CTX_new();
+    if (!c) return ORA_OOM;
+    if (EVP_EncryptInit_ex(c, ci, NULL, key, iv) != 1) { EVP_CIPHER_CTX_free(c); return ORA_INTERNAL; }
+    while (n) {
+        int k = n > (1u << 30) ? (1 << 30) : (int)n, ol = 0;
+        EVP_EncryptUpdate(c, out, &ol, in, k);
+        in += k; out += k; n -= (size_t)k;
+    }
+    EVP_CIPHER_CTX_free(c);
     return ORA_OK;
 }
 /* CBC decrypt + PKCS#7 unpad.  cipher/block/read.rs:31-116 */

@@ -61,6 +61,7 @@ def lib():
         L.pna_oracle_chunk_crc.restype = C.c_uint32
         L.pna_oracle_chunk_crc.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
         L.pna_oracle_ctr.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p]
+        L.pna_oracle_ctr_restated.argtypes = L.pna_oracle_ctr.argtypes
         L.pna_oracle_cbc_decrypt.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p,
                                              C.POINTER(C.c_size_t)]
         L.pna_oracle_cbc_encrypt.argtypes = L.pna_oracle_cbc_decrypt.argtypes
@@ -103,6 +104,14 @@ def chunk_crc(ty: bytes, data: bytes) -> int:
 def ctr(encryption: int, key: bytes, iv: bytes, data: bytes) -> bytes:
     out = C.create_string_buffer(len(data) or 1)
     rc = lib().pna_oracle_ctr(encryption, key, iv, data, len(data), out)
+    if rc:
+        raise OracleError(rc, "ctr")
+    return out.raw[:len(data)]
+
+
+def ctr_restated(encryption: int, key: bytes, iv: bytes, data: bytes) -> bytes:
+    out = C.create_string_buffer(len(data) or 1)
+    rc = lib().pna_oracle_ctr_restated(encryption, key, iv, data, len(data), out)
     if rc:
         raise OracleError(rc, "ctr")
     return out.raw[:len(data)]

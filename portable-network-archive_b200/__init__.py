@@ -60,6 +60,20 @@ class DecodePlan:
         self.ctx.L.pna_cuda_plan_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
         return {"stream_bytes": a.value, "plain_bytes": b.value, "launches_per_run": c.value}
 
+    def crc_results(self):
+        """(computed CRC per registered chunk span, number of mismatches) of the last run."""
+        n = getattr(self, "n_crc", 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        broken = C.c_uint32(0)
+        self.ctx._ck(self.ctx.L.pna_cuda_plan_crc_results(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(broken)),
+                     "plan_crc_results")
+        return out[:n], int(broken.value)
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * 16)()
+        n = self.ctx.L.pna_cuda_plan_stage_ms(self.h, ms, 16)
+        return {self.ctx.L.pna_cuda_stage_name(i).decode(): float(ms[i]) for i in range(max(n, 0))}
+
     def close(self):
         if self.h:
             self.ctx.L.pna_cuda_plan_destroy(self.h)
@@ -164,11 +178,26 @@ class Context:
             d.raw_size_hint = UINT64_MAX if h is None else int(h)
         return descs, keep
 
-    def decode_plan(self, entries) -> DecodePlan:
+    def decode_plan(self, entries, crc=None) -> DecodePlan:
+        """Upload a batch once (pna_plan).  crc = (ptrs u64[], lens u64[], expect u32[], entry_of i32[]) fuses the
+        chunk-CRC check (seam 1) into the plan: spans are host addresses of type||data inside the archive buffer."""
         descs, keep = self._descs(entries)
         h = C.c_void_p()
-        self._ck(self.L.pna_cuda_decode_plan_create(self.h, descs, len(entries), C.byref(h)), "decode_plan_create")
-        return DecodePlan(self, h, len(entries), None)
+        if crc is None:
+            self._ck(self.L.pna_cuda_decode_plan_create(self.h, descs, len(entries), C.byref(h)), "decode_plan_create")
+            return DecodePlan(self, h, len(entries), None)
+        ptrs, lens, expect, entry_of = crc
+        n = len(ptrs)
+        sp = np.zeros(n, dtype=[("ptr", "<u8"), ("len", "<u8")])
+        sp["ptr"], sp["len"] = ptrs, lens
+        expect = np.ascontiguousarray(expect, dtype=np.uint32)
+        entry_of = np.ascontiguousarray(entry_of, dtype=np.int32)
+        self._ck(self.L.pna_cuda_decode_plan_create_crc(
+            self.h, descs, len(entries), sp.ctypes.data_as(C.POINTER(_ffi.Span)), expect.ctypes.data_as(C.POINTER(C.c_uint32)),
+            entry_of.ctypes.data_as(C.POINTER(C.c_int32)), n, C.byref(h)), "decode_plan_create_crc")
+        p = DecodePlan(self, h, len(entries), None)
+        p.n_crc = n
+        return p
 
     def decode_batch(self, entries, caps=None):
         """One-shot decode through pna_cuda_decode_batch.  Returns (outputs, statuses, lens).  When caps is None

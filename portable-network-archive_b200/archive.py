@@ -378,6 +378,24 @@ class Archive:
                 pend, size = [], 0
         yield from self._flush(pend, options)
 
+    def extract_plan(self, options: ReadOptions | None = None):
+        """The whole extract hot path as ONE device plan: CRC check of every chunk of the archive (seam 1) fused
+        with decrypt+decompress of every FILE entry (seam 2) over a single upload of the archive bytes.
+        Returns (plan, entries); plan.run(); plan.fetch(sizes)."""
+        ents = [e for e in self.entries() if isinstance(e, NormalEntry) and e.data_kind == DataKind.FILE]
+        owner = {}
+        for i, e in enumerate(ents):
+            for ch in e.chunks:
+                owner[ch.off] = i
+        base = self._buf.ctypes.data
+        n = len(self._chunks)
+        ptrs = np.fromiter((base + c.off - 4 for c in self._chunks), dtype=np.uint64, count=n)
+        lens = np.fromiter((c.length + 4 for c in self._chunks), dtype=np.uint64, count=n)
+        expect = np.fromiter((c.crc for c in self._chunks), dtype=np.uint32, count=n)
+        entry_of = np.fromiter((owner.get(c.off, -1) for c in self._chunks), dtype=np.int32, count=n)
+        plan = self._ctx.decode_plan([e._desc(options) for e in ents], crc=(ptrs, lens, expect, entry_of))
+        return plan, ents
+
     def _flush(self, pend, options):
         if not pend:
             return

@@ -48,19 +48,71 @@ struct pna_ctx {
     } while (0)
 #define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 
+// Device memory cache: batch calls reuse the arenas of earlier calls instead of paying cudaMalloc/cudaFree
+// (milliseconds for multi-GiB arenas) on every pna_cuda_decode_batch / encode_batch.
+struct DevCache {
+    struct Blk { void* p; size_t bytes; int dev; };
+    std::mutex mu;
+    std::vector<Blk> free_list;
+    std::map<void*, std::pair<size_t, int>> live;
+    cudaError_t alloc(void** out, size_t bytes) {
+        if (bytes < ((size_t)64 << 10)) bytes = (bytes + 4095) & ~(size_t)4095;
+        else bytes = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> g(mu);
+        int best = -1;
+        for (int i = 0; i < (int)free_list.size(); i++) {
+            const Blk& b = free_list[i];
+            if (b.dev != dev || b.bytes < bytes || b.bytes > bytes + bytes / 2 + ((size_t)4 << 20)) continue;
+            if (best < 0 || b.bytes < free_list[best].bytes) best = i;
+        }
+        if (best >= 0) {
+            *out = free_list[best].p;
+            live[*out] = {free_list[best].bytes, dev};
+            free_list.erase(free_list.begin() + best);
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) {   // give cached blocks back to the driver and retry once
+            cudaGetLastError();
+            for (const Blk& b : free_list) if (b.dev == dev) cudaFree(b.p);
+            free_list.erase(std::remove_if(free_list.begin(), free_list.end(), [&](const Blk& b) { return b.dev == dev; }), free_list.end());
+            e = cudaMalloc(out, bytes);
+        }
+        if (e == cudaSuccess) live[*out] = {bytes, dev};
+        return e;
+    }
+    void release(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.find(p);
+        if (it == live.end()) { cudaFree(p); return; }
+        free_list.push_back({p, it->second.first, it->second.second});
+        live.erase(it);
+    }
+    void trim(int dev) {
+        std::lock_guard<std::mutex> g(mu);
+        for (const Blk& b : free_list) if (b.dev == dev) cudaFree(b.p);
+        free_list.erase(std::remove_if(free_list.begin(), free_list.end(), [&](const Blk& b) { return b.dev == dev; }), free_list.end());
+    }
+};
+static DevCache g_dev_cache;
+
 template <class T>
-struct DevArr {   // growable device array (never shrinks); freed with the owner
+struct DevArr {   // growable device array (never shrinks); returned to the cache with the owner
     T* p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (n <= cap && p) return cudaSuccess;
+        if (p) g_dev_cache.release(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        void* q = nullptr;
+        cudaError_t e = g_dev_cache.alloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) { p = (T*)q; cap = std::max<size_t>(n, 1); }
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) g_dev_cache.release(p); p = nullptr; cap = 0; }
     ~DevArr() { release(); }
     DevArr() = default;
     DevArr(const DevArr&) = delete;
@@ -77,9 +129,22 @@ struct Stager {
     std::vector<Range> ranges;
     uint64_t total = 0;
     static constexpr uint64_t GAP = 64 * 1024;
+    bool sealed = false;   // after the CRC spans were registered: later spans first try to resolve inside a range
     // returns the device offset of the span
     uint64_t add(const uint8_t* p, uint64_t len) {
         if (len == 0) return total;
+        if (sealed) {   // ranges are sorted by host address (spans were registered in ascending order)
+            size_t lo = 0, hi = ranges.size();
+            while (lo < hi) { size_t mid = (lo + hi) / 2; if (ranges[mid].host <= p) lo = mid + 1; else hi = mid; }
+            if (lo > 0) {
+                const Range& r = ranges[lo - 1];
+                if (p >= r.host && p + len <= r.host + r.len) return r.dev_off + (uint64_t)(p - r.host);
+            }
+            sealed = false;   // not covered (bodies without CRC spans): fall back to appending
+            uint64_t off = add(p, len);
+            sealed = true;
+            return off;
+        }
         if (!ranges.empty()) {
             Range& r = ranges.back();
             const uint8_t* end = r.host + r.len;
@@ -99,6 +164,9 @@ struct Stager {
         return PNA_OK;
     }
 };
+
+constexpr int PNA_N_STAGES = 8;
+static const char* const PNA_STAGE_NAMES[PNA_N_STAGES] = {"crc", "cipher", "zstd_scan", "zstd_entropy", "zstd_prefix", "zstd_lz", "inflate", "store"};
 
 // ------------------------------------------------------------------------------------------------
 struct pna_plan {
@@ -129,9 +197,23 @@ struct pna_plan {
     DevArr<CopyJob> d_copy;
     uint32_t n_blocks = 0;
     uint64_t lit_total = 0, seq_total = 0;
+    // per-stage CUDA events of the last run (cipher, zstd scan, entropy, prefix, lz, inflate, store)
+    cudaEvent_t ev[PNA_N_STAGES + 1] = {};
+    bool ev_ready = false, ev_recorded = false;
+    bool sized_entropy = false;   // prepare() already ran entropy+prefix / inflate sizing on the live table
+    DevArr<uint64_t> d_layout;
+    // optional chunk-CRC verification riding on the same uploaded image (seam 1 fused into the plan)
+    std::vector<CrcTile> h_crc_tiles;
+    std::vector<uint32_t> h_crc_first, h_crc_expect;
+    std::vector<int32_t> h_crc_entry;
+    DevArr<CrcTile> d_crc_tiles;
+    DevArr<uint32_t> d_crc_first, d_crc_expect, d_crc_raw, d_crc_val, d_crc_broken;
+    DevArr<int32_t> d_crc_entry;
+    uint32_t n_crc = 0;
     // encode side
     enc::EncodePlan* enc = nullptr;
     ~pna_plan() {
+        if (ev_ready) for (auto& e : ev) cudaEventDestroy(e);
         d_buf.release(); d_out.release(); d_lits.release(); d_entries.release(); d_entries_init.release();
         d_segs.release(); d_keys.release();
         for (auto& t : d_tiles) t.release();
@@ -201,6 +283,7 @@ extern "C" void pna_cuda_destroy(pna_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    g_dev_cache.trim(ctx->device);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->d_aes) cudaFree(ctx->d_aes);
     if (ctx->d_cam) cudaFree(ctx->d_cam);
@@ -304,10 +387,28 @@ static int variant_of(const EntryRec& e) {
     return (e.encryption == 1 ? 1 : 3) + (e.cipher_mode == 1 ? 0 : 1);
 }
 
-static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint64_t* caps, pna_plan* P) {
+struct CrcReq { const pna_span* spans; const uint32_t* expect; const int32_t* entry_of; uint32_t n; };
+static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint64_t* caps, const CrcReq* crc,
+                             pna_plan* P) {
     P->ctx = ctx; P->kind = 0; P->n = n;
     P->h_entries.resize(n);
     Stager st;
+    // chunk spans (type||data) first: they start 4 bytes before the bodies, so bodies fall into the same ranges
+    // when both are registered in address order; spans and bodies may also interleave arbitrarily.
+    std::vector<uint64_t> crc_off;
+    if (crc && crc->n) {
+        // merge-register spans and bodies in ascending host address order so that ranges coalesce
+        P->n_crc = crc->n;
+        crc_off.resize(crc->n);
+        std::vector<uint32_t> order(crc->n);
+        for (uint32_t i = 0; i < crc->n; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return crc->spans[a].ptr < crc->spans[b].ptr; });
+        for (uint32_t k : order) {
+            if (crc->spans[k].len && !crc->spans[k].ptr) return PNA_E_BAD_ARG;
+            crc_off[k] = st.add(crc->spans[k].ptr, crc->spans[k].len);
+        }
+        st.sealed = true;   // bodies now only look up / extend; see Stager::add
+    }
     std::map<std::array<uint8_t, 33>, int> key_ids;
     uint64_t comp_extra = 0;   // bytes needed in the comp region (decrypted / gathered streams)
     std::vector<uint8_t> needs_copy(n, 0);
@@ -368,6 +469,20 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
         if (needs_copy[i]) comp_extra += align_up(e.comp_len, 16) + 16;
     }
     P->image_bytes = align_up(st.total, 256);
+    if (P->n_crc) {
+        P->h_crc_first.resize(P->n_crc);
+        P->h_crc_expect.assign(crc->expect, crc->expect + crc->n);
+        P->h_crc_entry.assign(crc->entry_of, crc->entry_of + crc->n);
+        for (uint32_t i = 0; i < P->n_crc; i++) {
+            P->h_crc_first[i] = (uint32_t)P->h_crc_tiles.size();
+            uint64_t o = crc_off[i], l = crc->spans[i].len;
+            do {
+                uint32_t t = (uint32_t)std::min<uint64_t>(l, CRC_TILE);
+                P->h_crc_tiles.push_back({o, t, i});
+                o += t; l -= t;
+            } while (l);
+        }
+    }
     // comp region right behind the image
     uint64_t cur = P->image_bytes;
     for (uint32_t i = 0; i < n; i++) {
@@ -416,6 +531,15 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
         CK(P->d_deflate.reserve(P->h_deflate.size()));
         CK(cudaMemcpyAsync(P->d_deflate.p, P->h_deflate.data(), P->h_deflate.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (P->n_crc) {
+        const size_t nt = P->h_crc_tiles.size();
+        CK(P->d_crc_tiles.reserve(nt)); CK(P->d_crc_first.reserve(P->n_crc)); CK(P->d_crc_expect.reserve(P->n_crc));
+        CK(P->d_crc_entry.reserve(P->n_crc)); CK(P->d_crc_raw.reserve(nt)); CK(P->d_crc_val.reserve(P->n_crc)); CK(P->d_crc_broken.reserve(1));
+        CK(cudaMemcpyAsync(P->d_crc_tiles.p, P->h_crc_tiles.data(), nt * sizeof(CrcTile), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->d_crc_first.p, P->h_crc_first.data(), P->n_crc * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->d_crc_expect.p, P->h_crc_expect.data(), P->n_crc * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->d_crc_entry.p, P->h_crc_entry.data(), P->n_crc * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));   // the borrowed host spans may go away after this call
     return PNA_OK;
 }
@@ -442,6 +566,30 @@ static int decode_layout_out(pna_plan* P) {
         CK(cudaMemcpyAsync(P->d_copy.p, P->h_copy.data(), P->h_copy.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaMemcpyAsync(P->d_entries_init.p, P->h_entries.data(), P->n * sizeof(EntryRec), cudaMemcpyHostToDevice, ctx->stream));
+    return PNA_OK;
+}
+
+__global__ void crc_check_kernel(const uint32_t* __restrict__ crc, const uint32_t* __restrict__ expect,
+                                 const int32_t* __restrict__ entry_of, EntryRec* entries, uint32_t n, uint32_t* broken) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || crc[i] == expect[i]) return;
+    atomicAdd(broken, 1u);
+    if (entry_of[i] >= 0) atomicCAS(&entries[entry_of[i]].status, ST_OK, ST_INVALID_DATA);   // "broken chunk"
+}
+static int launch_crc(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    if (!P->n_crc) return PNA_OK;
+    const uint32_t nt = (uint32_t)P->h_crc_tiles.size();
+    CK(cudaMemsetAsync(P->d_crc_broken.p, 0, sizeof(uint32_t), ctx->stream));
+    const uint32_t grid = std::min<uint32_t>((nt + 7) / 8, (uint32_t)ctx->sm_count * 8);
+    crc_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(P->d_buf.p, P->d_crc_tiles.p, nt, ctx->d_crc, P->d_crc_raw.p);
+    LAUNCHED();
+    crc_combine_kernel<<<(P->n_crc + 127) / 128, 128, 0, ctx->stream>>>(P->d_crc_tiles.p, P->d_crc_raw.p, P->d_crc_first.p, P->n_crc, nt,
+                                                                       ctx->d_crc, P->d_crc_val.p);
+    LAUNCHED();
+    crc_check_kernel<<<(P->n_crc + 127) / 128, 128, 0, ctx->stream>>>(P->d_crc_val.p, P->d_crc_expect.p, P->d_crc_entry.p, P->d_entries.p,
+                                                                     P->n_crc, P->d_crc_broken.p);
+    LAUNCHED();
     return PNA_OK;
 }
 
@@ -495,6 +643,12 @@ static int launch_zstd_entropy(pna_plan* P) {
                                                                     P->d_sml.p, P->d_sof.p);
         LAUNCHED();
     }
+    return PNA_OK;
+}
+static int launch_zstd_prefix(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    const uint32_t nz = (uint32_t)P->h_ze.size();
+    if (!nz) return PNA_OK;
     zs::zstd_prefix_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
     LAUNCHED();
     return PNA_OK;
@@ -534,6 +688,7 @@ static int decode_prepare(pna_plan* P) {
     int rc;
     const uint32_t nz = (uint32_t)P->h_ze.size();
     CK(cudaMemcpyAsync(P->d_entries.p, P->h_entries.data(), P->n * sizeof(EntryRec), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_crc(P))) return rc;
     if ((rc = launch_cipher(P))) return rc;
     if (nz) {
         CK(P->d_ze.reserve(nz));
@@ -569,7 +724,9 @@ static int decode_prepare(pna_plan* P) {
     if (P->need_sizing) {
         // exact sizes: zstd from the entropy+prefix stages, deflate from a count-only pass, store = comp_len
         if ((rc = launch_zstd_entropy(P))) return rc;
+        if ((rc = launch_zstd_prefix(P))) return rc;
         if ((rc = launch_inflate(P, 1))) return rc;
+        P->sized_entropy = true;
         std::vector<EntryRec> dev(P->n);
         CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -587,34 +744,98 @@ static int decode_prepare(pna_plan* P) {
     return PNA_OK;
 }
 
-static int decode_launch_all(pna_plan* P) {
+__global__ void set_layout_kernel(EntryRec* entries, const uint64_t* __restrict__ off_cap, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    entries[i].out_off = off_cap[2 * i];
+    entries[i].out_cap = off_cap[2 * i + 1];
+}
+
+#define STAGE(i) do { if (P->ev_ready) CK(cudaEventRecord(P->ev[i], ctx->stream)); } while (0)
+// fresh = true: full pipeline from the pristine entry table (every run after the first).
+// fresh = false: continue right after decode_prepare(), which already decrypted and scanned (and, when it had
+// to size outputs, entropy-decoded) on the live table -- so a one-shot pna_cuda_decode_batch does no work twice.
+static int decode_launch_all(pna_plan* P, bool fresh) {
     pna_ctx* ctx = P->ctx;
     int rc;
     const uint64_t l0 = ctx->launches;
-    CK(cudaMemcpyAsync(P->d_entries.p, P->d_entries_init.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToDevice, ctx->stream));
-    if ((rc = launch_cipher(P))) return rc;
-    if ((rc = launch_zstd_front(P, false))) return rc;
-    if ((rc = launch_zstd_entropy(P))) return rc;
+    if (!P->ev_ready) {
+        for (auto& e : P->ev) CK(cudaEventCreate(&e));
+        P->ev_ready = true;
+    }
+    if (fresh) {
+        CK(cudaMemcpyAsync(P->d_entries.p, P->d_entries_init.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToDevice, ctx->stream));
+        STAGE(0);
+        if ((rc = launch_crc(P))) return rc;
+        STAGE(1);
+        if ((rc = launch_cipher(P))) return rc;
+        STAGE(2);
+        if ((rc = launch_zstd_front(P, false))) return rc;
+        STAGE(3);
+        if ((rc = launch_zstd_entropy(P))) return rc;
+        STAGE(4);
+        if ((rc = launch_zstd_prefix(P))) return rc;
+    } else {
+        std::vector<uint64_t> oc(2 * (size_t)P->n);
+        for (uint32_t i = 0; i < P->n; i++) { oc[2 * i] = P->h_entries[i].out_off; oc[2 * i + 1] = P->h_entries[i].out_cap; }
+        CK(P->d_layout.reserve(oc.size()));
+        CK(cudaMemcpyAsync(P->d_layout.p, oc.data(), oc.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        set_layout_kernel<<<(P->n + 127) / 128, 128, 0, ctx->stream>>>(P->d_entries.p, P->d_layout.p, P->n);
+        LAUNCHED();
+        CK(cudaStreamSynchronize(ctx->stream));   // oc is a local
+        STAGE(0); STAGE(1); STAGE(2); STAGE(3);
+        if (!P->sized_entropy) {
+            if ((rc = launch_zstd_entropy(P))) return rc;
+            STAGE(4);
+            if ((rc = launch_zstd_prefix(P))) return rc;
+        } else STAGE(4);
+    }
+    STAGE(5);
     if ((rc = launch_zstd_lz(P))) return rc;
+    STAGE(6);
     if ((rc = launch_inflate(P, 0))) return rc;
+    STAGE(7);
     if ((rc = launch_store(P))) return rc;
-    P->launches_per_run = ctx->launches - l0;
+    STAGE(8);
+    P->ev_recorded = true;
+    if (fresh) P->launches_per_run = ctx->launches - l0;
     return PNA_OK;
 }
 
-static int decode_plan_create_ex(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint64_t* caps, pna_plan** plan) {
+static int decode_plan_create_ex(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint64_t* caps, const CrcReq* crc,
+                                 pna_plan** plan) {
     if (!ctx || !plan || (!descs && n)) return PNA_E_BAD_ARG;
     *plan = nullptr;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     pna_plan* P = new pna_plan();
-    int rc = decode_plan_build(ctx, descs, n, caps, P);
+    int rc = decode_plan_build(ctx, descs, n, caps, crc, P);
     if (rc) { delete P; return rc; }
     *plan = P;
     return PNA_OK;
 }
 extern "C" int pna_cuda_decode_plan_create(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_plan** plan) {
-    return decode_plan_create_ex(ctx, descs, n, nullptr, plan);
+    return decode_plan_create_ex(ctx, descs, n, nullptr, nullptr, plan);
+}
+extern "C" int pna_cuda_decode_plan_create_crc(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const pna_span* crc_spans,
+                                               const uint32_t* crc_expect, const int32_t* crc_entry, uint32_t n_spans,
+                                               pna_plan** plan) {
+    if (n_spans && (!crc_spans || !crc_expect || !crc_entry)) return PNA_E_BAD_ARG;
+    for (uint32_t i = 0; i < n_spans; i++) if (crc_entry[i] >= (int64_t)n) return PNA_E_BAD_ARG;
+    CrcReq rq{crc_spans, crc_expect, crc_entry, n_spans};
+    return decode_plan_create_ex(ctx, descs, n, nullptr, &rq, plan);
+}
+extern "C" int pna_cuda_plan_crc_results(pna_plan* P, uint32_t* crc_out, uint32_t* n_broken) {
+    if (!P) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (n_broken) *n_broken = 0;
+    if (!P->n_crc || !P->prepared) return PNA_OK;
+    if (crc_out) CK(cudaMemcpyAsync(crc_out, P->d_crc_val.p, P->n_crc * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_broken) CK(cudaMemcpyAsync(n_broken, P->d_crc_broken.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PNA_OK;
 }
 extern "C" int pna_cuda_decode_plan_run(pna_plan* P) {
     if (!P || P->kind != 0) return PNA_E_BAD_ARG;
@@ -622,8 +843,12 @@ extern "C" int pna_cuda_decode_plan_run(pna_plan* P) {
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     if (P->n == 0) return PNA_OK;
-    if (!P->prepared) { int rc = decode_prepare(P); if (rc) return rc; }
-    return decode_launch_all(P);
+    if (!P->prepared) {
+        int rc = decode_prepare(P);
+        if (rc) return rc;
+        return decode_launch_all(P, false);
+    }
+    return decode_launch_all(P, true);
 }
 extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* status) {
     if (!P || P->kind != 0 || ((!out || !status) && P->n)) return PNA_E_BAD_ARG;
@@ -661,6 +886,20 @@ extern "C" int pna_cuda_plan_stats(pna_plan* P, uint64_t* stream_bytes, uint64_t
     if (launches_per_run) *launches_per_run = P->launches_per_run;
     return PNA_OK;
 }
+extern "C" int pna_cuda_plan_stage_ms(pna_plan* P, float* ms, uint32_t cap) {
+    if (!P) return -1;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!P->ev_recorded) return 0;
+    if (cudaEventSynchronize(P->ev[PNA_N_STAGES]) != cudaSuccess) return -1;
+    for (int i = 0; i < PNA_N_STAGES && (uint32_t)i < cap; i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, P->ev[i], P->ev[i + 1]);
+        ms[i] = t;
+    }
+    return PNA_N_STAGES;
+}
+extern "C" const char* pna_cuda_stage_name(uint32_t i) { return i < (uint32_t)PNA_N_STAGES ? PNA_STAGE_NAMES[i] : ""; }
 extern "C" void pna_cuda_plan_destroy(pna_plan* P) {
     if (!P) return;
     pna_ctx* ctx = P->ctx;
@@ -675,7 +914,7 @@ extern "C" int pna_cuda_decode_batch(pna_ctx* ctx, const pna_decode_desc* descs,
     std::vector<uint64_t> caps(n);
     for (uint32_t i = 0; i < n; i++) caps[i] = out[i].cap;
     pna_plan* P = nullptr;
-    int rc = decode_plan_create_ex(ctx, descs, n, caps.data(), &P);
+    int rc = decode_plan_create_ex(ctx, descs, n, caps.data(), nullptr, &P);
     if (rc) return rc;
     rc = pna_cuda_decode_plan_run(P);
     if (rc == PNA_OK) rc = pna_cuda_decode_plan_fetch(P, out, status);

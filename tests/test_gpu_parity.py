@@ -284,3 +284,54 @@ def test_many_small_deflate_camellia_cbc(ctx, oracle):
     outs, st, _ = ctx.decode_batch(entries, caps=[len(f) for f in files])
     assert st == [0] * len(files)
     assert all(o.tobytes() == f for o, f in zip(outs, files))
+
+
+def _write_archive(pna, oracle, files, comp, enc, mode, password=b"pw", flip=None):
+    """PNA container around oracle-encoded streams: FHED,fSIZ,PHSF,FDAT(iv),FDAT(body),FEND (entry.rs:895-912)."""
+    import struct
+    opts = pna.WriteOptions(compression=comp, encryption=enc, cipher_mode=mode, password=password if enc else None,
+                            kdf_params={"i": 1})
+    out = bytearray(b"\x89PNA\r\n\x1a\n")
+
+    def chunk(ty, data):
+        out.extend(struct.pack(">I", len(data)) + ty + data + struct.pack(">I", zlib.crc32(ty + data)))
+    chunk(b"AHED", bytes(8))
+    for i, f in enumerate(files):
+        s = oracle.encode_stream(f, comp, -1, enc, mode, opts.key, os.urandom(16))
+        chunk(b"FHED", bytes([0, 0, 0, comp, enc, mode]) + f"f{i}.bin".encode())
+        chunk(b"fSIZ", len(f).to_bytes(8, "big").lstrip(b"\0"))
+        if enc:
+            chunk(b"PHSF", opts.phsf.encode())
+            chunk(b"FDAT", s[:16])
+            s = s[16:]
+        chunk(b"FDAT", s)
+        chunk(b"FEND", b"")
+    chunk(b"AEND", b"")
+    return bytes(out), opts
+
+
+def test_extract_plan_fused_crc(ctx, pna, oracle):
+    """Whole hot path as one plan: chunk CRC check + AES-CTR + zstd over one upload; a flipped body byte marks
+    exactly that entry 'broken chunk' (format/chunk.rs:16-21) and leaves the others intact."""
+    files = [corpus.make_file(300 + i, 200_000 + 1000 * i) for i in range(12)]
+    raw, opts = _write_archive(pna, oracle, files, 2, 1, 1)
+    buf = np.frombuffer(raw, dtype=np.uint8).copy()
+    ro = pna.ReadOptions.with_password(b"pw")
+    a = pna.Archive.read_header(buf, ctx, verify=False)
+    plan, ents = a.extract_plan(ro)
+    plan.run()
+    outs, st, _ = plan.fetch([len(f) for f in files])
+    crcs, broken = plan.crc_results()
+    assert st == [0] * 12 and broken == 0 and all(o.tobytes() == f for o, f in zip(outs, files))
+    assert [int(c) for c in crcs] == [c.crc for c in a._chunks]
+    plan.close()
+    victim = ents[5].chunks[-2]            # the FDAT body of entry 5
+    buf[victim.off + victim.length // 2] ^= 1
+    a = pna.Archive.read_header(buf, ctx, verify=False)
+    plan, ents = a.extract_plan(ro)
+    plan.run()
+    plan.run()
+    outs, st, _ = plan.fetch([len(f) for f in files])
+    _, broken = plan.crc_results()
+    assert broken == 1 and st[5] == pna.E_INVALID_DATA and [s for i, s in enumerate(st) if i != 5] == [0] * 11
+    plan.close()

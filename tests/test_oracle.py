@@ -42,6 +42,8 @@ def test_ctr_matches_full_width_be_counter(oracle):
         d = os.urandom(1000)
         e = Cipher(algorithms.AES(key), modes.CTR(iv)).encryptor()
         assert oracle.ctr(1, key, iv, d) == e.update(d) + e.finalize()
+        for enc in (1, 2):   # OpenSSL's CTR mode == the restated Ctr128BE counter, both ciphers
+            assert oracle.ctr(enc, key, iv, d) == oracle.ctr_restated(enc, key, iv, d)
 
 
 def test_golden_archives(oracle, golden):
