@@ -113,6 +113,9 @@ int pna_cuda_decode_plan_run(pna_plan* plan);                 /* asynchronous on
 int pna_cuda_decode_plan_fetch(pna_plan* plan, pna_buf* out, int32_t* status);
 /* stream / decoded byte totals of a plan (algorithmic bytes for the roofline: C and U) */
 int pna_cuda_plan_stats(pna_plan* plan, uint64_t* stream_bytes, uint64_t* plain_bytes, uint64_t* launches_per_run);
+/* zstd work of a prepared plan: blocks, sequences (8-byte records between the entropy and LZ stages) and
+ * Huffman-coded literal bytes (16-byte padded per block) -- the per-stage algorithmic bytes in DESIGN.md */
+int pna_cuda_plan_counts(pna_plan* plan, uint64_t* n_blocks, uint64_t* n_sequences, uint64_t* literal_bytes);
 /* per-stage device time (CUDA events on pna_cuda_stream) of the plan's last run; returns the number of stages */
 int pna_cuda_plan_stage_ms(pna_plan* plan, float* ms, uint32_t cap);
 const char* pna_cuda_stage_name(uint32_t stage);

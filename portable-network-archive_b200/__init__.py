@@ -60,6 +60,11 @@ class DecodePlan:
         self.ctx.L.pna_cuda_plan_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
         return {"stream_bytes": a.value, "plain_bytes": b.value, "launches_per_run": c.value}
 
+    def counts(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.ctx.L.pna_cuda_plan_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"blocks": a.value, "sequences": b.value, "literal_bytes": c.value}
+
     def crc_results(self):
         """(computed CRC per registered chunk span, number of mismatches) of the last run."""
         n = getattr(self, "n_crc", 0)

@@ -165,8 +165,8 @@ struct Stager {
     }
 };
 
-constexpr int PNA_N_STAGES = 8;
-static const char* const PNA_STAGE_NAMES[PNA_N_STAGES] = {"crc", "cipher", "zstd_scan", "zstd_entropy", "zstd_prefix", "zstd_lz", "inflate", "store"};
+constexpr int PNA_N_STAGES = 9;
+static const char* const PNA_STAGE_NAMES[PNA_N_STAGES] = {"crc", "cipher", "zstd_scan", "zstd_seq", "zstd_lit", "zstd_prefix", "zstd_lz", "inflate", "store"};
 
 // ------------------------------------------------------------------------------------------------
 struct pna_plan {
@@ -190,7 +190,8 @@ struct pna_plan {
     DevArr<Segment> d_segs;
     DevArr<DevKeys> d_keys;
     DevArr<CipherTile> d_tiles[5];
-    DevArr<uint32_t> d_deflate, d_sll, d_sml, d_sof;
+    DevArr<uint32_t> d_deflate, d_seq_order, d_lit_order, d_counts;
+    DevArr<zs::SeqRec> d_seqs;
     DevArr<zs::ZEntry> d_ze;
     DevArr<zs::ZBlock> d_blocks;
     DevArr<uint64_t> d_lit_base, d_seq_base;
@@ -217,7 +218,7 @@ struct pna_plan {
         d_buf.release(); d_out.release(); d_lits.release(); d_entries.release(); d_entries_init.release();
         d_segs.release(); d_keys.release();
         for (auto& t : d_tiles) t.release();
-        d_deflate.release(); d_sll.release(); d_sml.release(); d_sof.release(); d_ze.release(); d_blocks.release();
+        d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
         if (enc) enc::destroy(enc);
     }
@@ -273,6 +274,9 @@ extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
     ok = ok && cudaFuncSetAttribute(ecb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(zs::zstd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::SEQ_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(zs::zstd_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LIT_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(zs::zstd_lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LZ_SMEM_BYTES) == cudaSuccess;
     ok = ok && enc::init_attributes();
     if (!ok) { pna_cuda_destroy(ctx); return PNA_E_CUDA; }
     *out = ctx;
@@ -631,18 +635,27 @@ static int launch_zstd_front(pna_plan* P, bool with_count) {   // scan .. resolv
     }
     zs::zstd_resolve_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
     LAUNCHED();
+    zs::zstd_order_kernel<<<1, 1024, 0, ctx->stream>>>(P->d_entries.p, P->d_blocks.p, P->n_blocks, P->d_seq_order.p, P->d_lit_order.p,
+                                                      P->d_counts.p);
+    LAUNCHED();
     return PNA_OK;
 }
-static int launch_zstd_entropy(pna_plan* P) {
+static int launch_zstd_seq(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
-    const uint32_t nz = (uint32_t)P->h_ze.size();
-    if (!nz) return PNA_OK;
-    if (P->n_blocks) {
-        zs::zstd_entropy_kernel<<<P->n_blocks, 64, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_blocks.p, P->n_blocks,
-                                                                    P->d_lit_base.p, P->d_seq_base.p, P->d_lits.p, P->d_sll.p,
-                                                                    P->d_sml.p, P->d_sof.p);
-        LAUNCHED();
-    }
+    if (P->h_ze.empty() || !P->n_blocks) return PNA_OK;
+    const uint32_t grid = std::min<uint32_t>((P->n_blocks + 31) / 32, (uint32_t)ctx->sm_count * 2);
+    zs::zstd_seq_kernel<<<grid, 32, zs::SEQ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_blocks.p, P->d_seq_order.p,
+                                                                      P->d_counts.p, P->d_seq_base.p, P->d_seqs.p);
+    LAUNCHED();
+    return PNA_OK;
+}
+static int launch_zstd_lit(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    if (P->h_ze.empty() || !P->n_blocks) return PNA_OK;
+    const uint32_t grid = std::min<uint32_t>((P->n_blocks + zs::LIT_SLOTS - 1) / zs::LIT_SLOTS, (uint32_t)ctx->sm_count * 3);
+    zs::zstd_lit_kernel<<<grid, 32, zs::LIT_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_blocks.p, P->d_lit_order.p,
+                                                                      P->d_counts.p, P->d_lit_base.p, P->d_lits.p);
+    LAUNCHED();
     return PNA_OK;
 }
 static int launch_zstd_prefix(pna_plan* P) {
@@ -657,8 +670,9 @@ static int launch_zstd_lz(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
     const uint32_t nz = (uint32_t)P->h_ze.size();
     if (!nz) return PNA_OK;
-    zs::zstd_lz_kernel<<<(nz + 3) / 4, 128, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p, P->d_lits.p,
-                                                             P->d_sll.p, P->d_sml.p, P->d_sof.p, P->d_out.p);
+    const uint32_t grid = std::min<uint32_t>((nz + zs::LZ_WARPS - 1) / zs::LZ_WARPS, (uint32_t)ctx->sm_count);
+    zs::zstd_lz_kernel<<<grid, 32 * zs::LZ_WARPS, zs::LZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p,
+                                                                                   P->d_lits.p, P->d_seqs.p, P->d_out.p, P->d_counts.p);
     LAUNCHED();
     return PNA_OK;
 }
@@ -701,6 +715,7 @@ static int decode_prepare(pna_plan* P) {
         if (nb > 0xFFFFFFF0ull) return PNA_E_OOM;
         P->n_blocks = (uint32_t)nb;
         CK(P->d_blocks.reserve(nb));
+        CK(P->d_seq_order.reserve(nb)); CK(P->d_lit_order.reserve(nb)); CK(P->d_counts.reserve(8));
         CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = launch_zstd_front(P, false))) return rc;
         CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
@@ -714,7 +729,7 @@ static int decode_prepare(pna_plan* P) {
         }
         P->lit_total = lit; P->seq_total = seq;
         CK(P->d_lits.reserve(lit + 256));
-        CK(P->d_sll.reserve(seq + 32)); CK(P->d_sml.reserve(seq + 32)); CK(P->d_sof.reserve(seq + 32));
+        CK(P->d_seqs.reserve(seq + 32));
         CK(P->d_lit_base.reserve(P->n)); CK(P->d_seq_base.reserve(P->n));
         CK(cudaMemcpyAsync(P->d_lit_base.p, lb.data(), P->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(P->d_seq_base.p, sb.data(), P->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -723,7 +738,8 @@ static int decode_prepare(pna_plan* P) {
     }
     if (P->need_sizing) {
         // exact sizes: zstd from the entropy+prefix stages, deflate from a count-only pass, store = comp_len
-        if ((rc = launch_zstd_entropy(P))) return rc;
+        if ((rc = launch_zstd_seq(P))) return rc;
+        if ((rc = launch_zstd_lit(P))) return rc;
         if ((rc = launch_zstd_prefix(P))) return rc;
         if ((rc = launch_inflate(P, 1))) return rc;
         P->sized_entropy = true;
@@ -772,8 +788,10 @@ static int decode_launch_all(pna_plan* P, bool fresh) {
         STAGE(2);
         if ((rc = launch_zstd_front(P, false))) return rc;
         STAGE(3);
-        if ((rc = launch_zstd_entropy(P))) return rc;
+        if ((rc = launch_zstd_seq(P))) return rc;
         STAGE(4);
+        if ((rc = launch_zstd_lit(P))) return rc;
+        STAGE(5);
         if ((rc = launch_zstd_prefix(P))) return rc;
     } else {
         std::vector<uint64_t> oc(2 * (size_t)P->n);
@@ -785,18 +803,20 @@ static int decode_launch_all(pna_plan* P, bool fresh) {
         CK(cudaStreamSynchronize(ctx->stream));   // oc is a local
         STAGE(0); STAGE(1); STAGE(2); STAGE(3);
         if (!P->sized_entropy) {
-            if ((rc = launch_zstd_entropy(P))) return rc;
+            if ((rc = launch_zstd_seq(P))) return rc;
             STAGE(4);
+            if ((rc = launch_zstd_lit(P))) return rc;
+            STAGE(5);
             if ((rc = launch_zstd_prefix(P))) return rc;
-        } else STAGE(4);
+        } else { STAGE(4); STAGE(5); }
     }
-    STAGE(5);
-    if ((rc = launch_zstd_lz(P))) return rc;
     STAGE(6);
-    if ((rc = launch_inflate(P, 0))) return rc;
+    if ((rc = launch_zstd_lz(P))) return rc;
     STAGE(7);
-    if ((rc = launch_store(P))) return rc;
+    if ((rc = launch_inflate(P, 0))) return rc;
     STAGE(8);
+    if ((rc = launch_store(P))) return rc;
+    STAGE(9);
     P->ev_recorded = true;
     if (fresh) P->launches_per_run = ctx->launches - l0;
     return PNA_OK;
@@ -884,6 +904,13 @@ extern "C" int pna_cuda_plan_stats(pna_plan* P, uint64_t* stream_bytes, uint64_t
     if (stream_bytes) *stream_bytes = P->stream_bytes;
     if (plain_bytes) *plain_bytes = P->plain_bytes;
     if (launches_per_run) *launches_per_run = P->launches_per_run;
+    return PNA_OK;
+}
+extern "C" int pna_cuda_plan_counts(pna_plan* P, uint64_t* n_blocks, uint64_t* n_sequences, uint64_t* literal_bytes) {
+    if (!P) return PNA_E_BAD_ARG;
+    if (n_blocks) *n_blocks = P->n_blocks;
+    if (n_sequences) *n_sequences = P->seq_total;
+    if (literal_bytes) *literal_bytes = P->lit_total;
     return PNA_OK;
 }
 extern "C" int pna_cuda_plan_stage_ms(pna_plan* P, float* ms, uint32_t cap) {

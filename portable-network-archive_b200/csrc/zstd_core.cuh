@@ -50,6 +50,8 @@ struct ZBlock {
     uint8_t mode[3];
     uint8_t _pad;
     int32_t status;
+    uint32_t esc_n;                    // sequences whose ll or ml did not fit 16 bits (SeqRec escapes)
+    uint32_t esc_idx[4], esc_ll[4], esc_ml[4];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -284,6 +286,248 @@ PNA_HD int seq_table_for(const uint8_t* comp, const ZBlock* blocks, const ZBlock
 }
 
 // ---------------------------------------------------------------------------------------------
+// Compact sequence tables for the lane-per-block decoder (kernels_zstd.cuh zstd_seq_kernel): one
+// 16-bit entry per state = code << 10 | ns, where ns in [count, 2*count) is the FSE "next state
+// number" of that cell.  nbBits = log - highbit(ns) and newState = (ns << nbBits) - size follow from
+// it, so a block's three tables take 2.5 KB and 32 blocks (one per lane) fit one warp's 80 KB of
+// shared memory, interleaved by lane (stride 32) so that the lanes' halfwords share words pairwise.
+struct Tab16 {
+    uint16_t* p;
+    uint32_t stride;
+    PNA_HD uint32_t get(uint32_t i) const { return p[i * stride]; }
+    PNA_HD void set(uint32_t i, uint32_t v) const { p[i * stride] = (uint16_t)v; }
+};
+constexpr uint32_t TAB16_LL = 0, TAB16_ML = 512, TAB16_OF = 1024, TAB16_TOTAL = 1280;
+
+PNA_HD void fse_build_tab16(const Tab16& t, const int16_t* norm, int n_sym, int log, uint16_t* next_of) {
+    const int size = 1 << log;
+    int high = size - 1;
+    for (int s = 0; s < n_sym; s++) {
+        if (norm[s] == -1) { t.set((uint32_t)high--, (uint32_t)s << 10); next_of[s] = 1; }
+        else next_of[s] = (uint16_t)norm[s];
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+    int pos = 0;
+    for (int s = 0; s < n_sym; s++) {
+        for (int i = 0; i < norm[s]; i++) {
+            t.set((uint32_t)pos, (uint32_t)s << 10);
+            pos = (pos + step) & mask;
+            while (pos > high) pos = (pos + step) & mask;
+        }
+    }
+    for (int u = 0; u < size; u++) {
+        uint32_t s = t.get((uint32_t)u) >> 10;
+        uint32_t ns = next_of[s]++;
+        t.set((uint32_t)u, (s << 10) | ns);
+    }
+}
+// kind: 0 LL, 1 OF, 2 ML.  Returns the accuracy log or -1.
+PNA_HD int seq_tab16_for(const uint8_t* comp, const ZBlock* blocks, const ZBlock& b, int kind, const Tab16& t,
+                         int16_t* norm, uint16_t* next_of) {
+    const int max_sym = kind == 0 ? LL_MAXSYM : kind == 1 ? OF_MAXSYM : ML_MAXSYM;
+    const int max_log = kind == 0 ? LL_LOG_MAX : kind == 1 ? OF_LOG_MAX : ML_LOG_MAX;
+    int src = b.tsrc[kind];
+    if (src < 0) {
+        int log = kind == 1 ? 5 : 6;
+        int n = kind == 0 ? 36 : kind == 1 ? 29 : 53;
+        for (int s = 0; s < n; s++) norm[s] = (int16_t)predef_norm(kind, s);
+        fse_build_tab16(t, norm, n, log, next_of);
+        return log;
+    }
+    const ZBlock& sb = blocks[src];
+    const uint8_t* d = comp + sb.src + sb.desc[kind];
+    uint32_t avail = sb.size - sb.desc[kind];
+    if (sb.mode[kind] == SM_RLE) {
+        if (avail < 1 || d[0] > max_sym) return -1;
+        t.set(0, ((uint32_t)d[0] << 10) | 1u);   // ns = 1: nbBits 0, newState 0
+        return 0;
+    }
+    int log = 0, n_sym = 0;
+    if (fse_read_ncount(d, avail, max_sym, max_log, norm, &log, &n_sym) < 0) return -1;
+    fse_build_tab16(t, norm, n_sym, log, next_of);
+    return log;
+}
+// extra-bit counts from the code alone (the bit position depends on them: kept to a few ALU ops)
+PNA_HD uint32_t ll_xbits(uint32_t c) {
+    return c < 16 ? 0u : c >= 25 ? c - 19u : (uint32_t)((0x433221111ull >> (4 * (c - 16))) & 15u);
+}
+PNA_HD uint32_t ml_xbits(uint32_t c) {
+    return c < 32 ? 0u : c >= 43 ? c - 36u : (uint32_t)((0x54433221111ull >> (4 * (c - 32))) & 15u);
+}
+
+// Backward bit window: 64 bits held left-aligned in a register, refilled 32 bits at a time from the
+// aligned word below (prefetched one refill ahead, so the load latency is off the decode chain).
+// `remain` counts the unread bits of the stream; it only ever decreases, so one check at the end
+// (== 0 for sequences, >= 0 for Huffman) is equivalent to libzstd's per-step over-read checks.
+struct BitWin {
+    const uint32_t* words;
+    uint64_t w;
+    int32_t cnt;      // valid bits in w
+    int64_t wp;       // index of the prefetched word
+    uint32_t nx;      // words[wp]
+    int64_t remain;
+    PNA_HD bool init(const uint32_t* wd, const uint8_t* bytes, uint64_t begin, uint64_t len) {
+        words = wd;
+        w = 0; cnt = 0; wp = 0; nx = 0; remain = 0;
+        if (len == 0) return false;
+        const uint8_t last = bytes[begin + len - 1];
+        if (last == 0) return false;
+        remain = (int64_t)(len - 1) * 8 + highbit32(last);
+        const uint64_t top = begin * 8 + (uint64_t)remain - 1;   // absolute index of the first bit to read
+        const int64_t wi = (int64_t)(top >> 5);
+        const uint32_t sh = 31u - (uint32_t)(top & 31);
+        const uint64_t hi = wd[wi], lo = wi >= 1 ? wd[wi - 1] : 0u;
+        w = ((hi << 32) | lo) << sh;
+        cnt = 64 - (int32_t)sh;
+        wp = wi - 2;
+        nx = wp >= 0 ? wd[wp] : 0u;
+        return true;
+    }
+    PNA_HD void refill() {   // afterwards cnt >= 33
+        if (cnt <= 32) {
+            w |= (uint64_t)nx << (32 - cnt);
+            cnt += 32;
+            wp--;
+            nx = wp >= 0 ? words[wp] : 0u;
+        }
+    }
+    PNA_HD uint32_t take(uint32_t n) {   // 0 <= n <= 32, n <= cnt
+        const uint32_t v = (uint32_t)((w >> 1) >> (63 - n));
+        w <<= n;
+        cnt -= (int32_t)n;
+        remain -= n;
+        return v;
+    }
+    PNA_HD uint32_t peek(uint32_t n) const { return (uint32_t)((w >> 1) >> (63 - n)); }   // 1 <= n <= 32
+    PNA_HD void skip(uint32_t n) { w <<= n; cnt -= (int32_t)n; remain -= n; }
+};
+
+// One sequence record as the LZ stage reads it: x = offset (absolute, or symbolic REP_SYM form),
+// y = min(ll, 0xFFFF) | min(ml, 0xFFFF) << 16; values >= 0xFFFF are listed in the block's escapes.
+struct SeqRec { uint32_t x, y; };
+constexpr uint32_t SEQ_ESC = 0xFFFFu;
+constexpr int SEQ_ESC_MAX = 4;
+
+// 64 stream bits ending just below bit `pos` (pos = number of unread bits), left-aligned: the next
+// bit to read is bit 63.  wb = aligned word holding the stream's first byte, b0 = bit offset of that
+// byte inside it.  Three aligned loads (independent, L1-resident) + two funnel shifts; positions
+// below the stream start read the bytes in front of it (>= 11 bytes of frame/block headers, so the
+// two words below wb exist) and are rejected by the final pos == 0 check.
+PNA_HD uint64_t bits_window(const uint32_t* wb, uint32_t b0, int32_t pos) {
+    const int32_t top = (int32_t)b0 + pos - 1;          // relative index of the first bit to read (>= -1)
+    const int32_t wi = top >> 5;                        // arithmetic shift: -1 -> word -1
+    const uint32_t sh = 31u - ((uint32_t)top & 31u);
+    const uint32_t h = wb[wi], m = wb[wi - 1], l = wb[wi - 2];
+#if defined(__CUDA_ARCH__)
+    const uint32_t whi = __funnelshift_l(m, h, sh), wlo = __funnelshift_l(l, m, sh);
+#else
+    const uint32_t whi = sh ? (h << sh) | (m >> (32 - sh)) : h, wlo = sh ? (m << sh) | (l >> (32 - sh)) : m;
+#endif
+    return ((uint64_t)whi << 32) | wlo;
+}
+// n bits (0..32) of window W starting `skip` bits below its top (skip + n <= 64)
+PNA_HD uint32_t win_bits(uint64_t W, uint32_t skip, uint32_t n) {
+    return (uint32_t)(((W << skip) >> 1) >> (63 - n));
+}
+
+// Sequence decode of one block by ONE thread (a lane of zstd_seq_kernel).  Position-based bit
+// reader: per sequence one 64-bit window is fetched at the current bit position while the three
+// table cells are looked up; all fields of the sequence (<= 64 bits in every stream the reference
+// writes; longer ones take a second window) are cut out of it, and only
+//   state -> table cell -> bit counts -> next position / next state
+// is loop-carried.  Errors are collected in a flag (no early exits inside the loop).
+// llb/mlb: value baselines by code.  Same accept/reject behaviour as decode_sequences().
+PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll,
+                                  const Tab16& tof, const Tab16& tml, int lll, int lof, int lml,
+                                  const uint32_t* llb, const uint32_t* mlb, SeqRec* out, uint32_t* esc_n,
+                                  uint32_t* esc_idx, uint32_t* esc_ll, uint32_t* esc_ml) {
+    const uint64_t begin = b.src + b.bs_pos;
+    const uint32_t len = b.bs_len, nseq = b.nseq, lit_regen = b.lit_regen;
+    if (len == 0) return ST_INVALID_DATA;
+    const uint8_t last = comp[begin + len - 1];
+    if (last == 0) return ST_INVALID_DATA;
+    const uint32_t* wb = words + (begin >> 2);
+    const uint32_t b0 = (uint32_t)(begin & 3) * 8;
+    int32_t pos = (int32_t)(len - 1) * 8 + highbit32(last);
+    const uint32_t ulll = (uint32_t)lll, ulof = (uint32_t)lof, ulml = (uint32_t)lml;
+    if (pos < (int32_t)(ulll + ulof + ulml)) return ST_INVALID_DATA;
+    uint64_t W = bits_window(wb, b0, pos);
+    uint32_t sll = win_bits(W, 0, ulll), sof = win_bits(W, ulll, ulof), sml = win_bits(W, ulll + ulof, ulml);
+    pos -= (int32_t)(ulll + ulof + ulml);
+    uint32_t rep0 = REP_SYM | (0u << 29), rep1 = REP_SYM | (1u << 29), rep2 = REP_SYM | (2u << 29);
+    uint32_t lit_sum = 0, match_sum = 0;     // < 2^32: nseq < 2^17 values < 2^17 each
+    const uint32_t zll = 1u << lll, zof = 1u << lof, zml = 1u << lml;
+    uint32_t ne = 0;
+    uint32_t err = 0;
+    for (uint32_t i = 0; i < nseq; i++) {
+        W = bits_window(wb, b0, pos);
+        const uint32_t ell = tll.get(sll), eof = tof.get(sof), eml = tml.get(sml);
+        const uint32_t cll = ell >> 10, cof = eof >> 10, cml = eml >> 10;
+        const uint32_t xll = ll_xbits(cll), xml = ml_xbits(cml);
+        const uint32_t nsl = ell & 1023u, nsm = eml & 1023u, nso = eof & 1023u;
+        const uint32_t nbl = ulll - (uint32_t)highbit32(nsl), nbm = ulml - (uint32_t)highbit32(nsm),
+                       nbo = ulof - (uint32_t)highbit32(nso);
+        const uint32_t xb = cof + xml + xll;                 // value bits: offset, match length, literal length
+        const bool more = i + 1 < nseq;
+        const uint32_t nbs = more ? nbl + nbm + nbo : 0u;    // the last sequence updates no state
+        uint32_t ofx, mlx, llx, y;
+        if (xb + nbs <= 64u) {
+            ofx = win_bits(W, 0, cof);
+            const uint32_t x = win_bits(W, cof, xml + xll);
+            mlx = x >> xll; llx = x & ((1u << xll) - 1u);
+            y = win_bits(W, xb, nbs);
+        } else {   // > 64 bits in one sequence (offset codes > 22 with long length codes): second window for the states
+            ofx = win_bits(W, 0, cof);
+            const uint32_t x = win_bits(W, cof, xml + xll);
+            mlx = x >> xll; llx = x & ((1u << xll) - 1u);
+            const int32_t p2 = pos - (int32_t)xb;
+            y = p2 >= 0 ? win_bits(bits_window(wb, b0, p2), 0, nbs) : 0u;
+        }
+        pos -= (int32_t)(xb + nbs);
+        err |= (uint32_t)(pos < 0);
+        pos = pos < 0 ? 0 : pos;                             // keep the reads inside the arena on corrupt input
+        const uint32_t ofv = (1u << cof) + ofx;
+        const uint32_t ml = mlb[cml] + mlx;
+        const uint32_t ll = llb[cll] + llx;
+        // repeat-offset logic (RFC 8878 3.1.1.5), branch-free; offsets may be symbolic (REP_SYM) in the block's incoming history
+        const bool is_new = ofv > 3;
+        const uint32_t idx = ofv - 1 + (ll == 0 ? 1u : 0u);                     // meaningful when !is_new: 0..3
+        const uint32_t dec = (rep0 & REP_SYM) ? rep0 + 1 : rep0 - 1;            // "rep0 - 1" (symbolic: delta + 1)
+        const uint32_t cand = idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : dec;
+        const uint32_t off = is_new ? ofv - 3 : cand;
+        err |= (uint32_t)(is_new && (off & REP_SYM) != 0);
+        err |= (uint32_t)(!is_new && idx == 3 && ((rep0 & REP_SYM) ? (off & 0x1FFFFFFFu) == 0 : off == 0));
+        const bool sh2 = is_new || idx >= 2, sh1 = is_new || idx >= 1;
+        rep2 = sh2 ? rep1 : rep2;
+        rep1 = sh1 ? rep0 : rep1;
+        rep0 = off;
+        if (ll >= SEQ_ESC || ml >= SEQ_ESC) {
+            if (ne < (uint32_t)SEQ_ESC_MAX) { esc_idx[ne] = i; esc_ll[ne] = ll; esc_ml[ne] = ml; }
+            else err |= 1u;                                  // > 4 such sequences cannot fit a 128 KiB block
+            ne++;
+        }
+        SeqRec r;
+        r.x = off;
+        r.y = (ll < SEQ_ESC ? ll : SEQ_ESC) | ((ml < SEQ_ESC ? ml : SEQ_ESC) << 16);
+        out[i] = r;
+        lit_sum += ll; match_sum += ml;
+        sll = ((nsl << nbl) - zll) + (y >> (nbm + nbo));
+        sml = ((nsm << nbm) - zml) + ((y >> nbo) & ((1u << nbm) - 1u));
+        sof = ((nso << nbo) - zof) + (y & ((1u << nbo) - 1u));
+        if (!more) { sll = 0; sml = 0; sof = 0; }
+    }
+    if (err || pos != 0) return ST_INVALID_DATA;
+    if (lit_sum > lit_regen) return ST_INVALID_DATA;
+    const uint64_t outsz = (uint64_t)lit_regen + match_sum;
+    if (outsz > BLOCK_MAX) return ST_INVALID_DATA;
+    b.out_size = (uint32_t)outsz;
+    b.lit_used = lit_sum;
+    b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
+    *esc_n = ne;
+    return ST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Huffman tree description -> single-symbol decode table (libzstd HUF_readStats + HUF_readDTableX1).
 // table: uint16_t[1<<log] entries (sym | nbBits<<8).  weights: uint8_t[256] scratch.  fse: FseEntry[64] scratch.
 // Returns header bytes consumed (>0) or -1; *table_log receives the log.
@@ -394,6 +638,36 @@ PNA_HD bool huf_decode_stream(const uint32_t* words, const uint8_t* comp, uint64
     // libzstd >= 1.5.4's fast Huffman loops validate the produced length only, not that every bit of
     // the stream was consumed; leftover bits are therefore accepted, an over-read is not.
     return true;
+}
+
+// Same stream decode on the register bit window (kernels_zstd.cuh zstd_lit_kernel): two symbols per
+// refill, output gathered into aligned 32-bit stores.  Table stride lets 4 lanes share one table.
+PNA_HD bool huf_decode_stream_w(const uint32_t* words, const uint8_t* comp, uint64_t begin, uint32_t len,
+                                const uint16_t* table, int log, uint8_t* dst, uint32_t count) {
+    BitWin bw;
+    if (!bw.init(words, comp, begin, len)) return false;
+    const uint32_t ulog = (uint32_t)log;
+    uint32_t i = 0;
+#define PNA_HUF_SYM(var_) do { const uint32_t e__ = table[bw.peek(ulog)]; var_ = e__ & 0xFFu; bw.skip(e__ >> 8); } while (0)
+    // head: bytes until dst is 4-byte aligned
+    while (i < count && (((uintptr_t)(dst + i)) & 3) != 0) {
+        bw.refill();
+        uint32_t s; PNA_HUF_SYM(s);
+        dst[i++] = (uint8_t)s;
+    }
+    for (; i + 4 <= count; i += 4) {
+        uint32_t s0, s1, s2, s3;
+        bw.refill(); PNA_HUF_SYM(s0); PNA_HUF_SYM(s1);
+        bw.refill(); PNA_HUF_SYM(s2); PNA_HUF_SYM(s3);
+        *reinterpret_cast<uint32_t*>(dst + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+    }
+    for (; i < count; i++) {
+        bw.refill();
+        uint32_t s; PNA_HUF_SYM(s);
+        dst[i] = (uint8_t)s;
+    }
+#undef PNA_HUF_SYM
+    return bw.remain >= 0;   // leftover bits are accepted (libzstd >= 1.5.4 fast loops), an over-read is not
 }
 
 // ---------------------------------------------------------------------------------------------

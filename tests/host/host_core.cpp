@@ -81,8 +81,11 @@ extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uin
     st = resolve_sources(blocks.data(), 0, nb);
     if (st) { hc_site = 3; return st; }
     std::vector<uint8_t> lits(lit_total + 8);
-    std::vector<uint32_t> sll(seq_total + 1), sml(seq_total + 1), sof(seq_total + 1);
-    std::vector<SeqEntry> tll(512), tof(512), tml(512);
+    std::vector<SeqRec> seqs(seq_total + 1);
+    std::vector<uint16_t> tab16(TAB16_TOTAL);
+    uint32_t llb[36], mlb[53];
+    for (int c = 0; c < 36; c++) { llb[c] = ll_base(c); if (ll_xbits(c) != (uint32_t)ll_bits(c)) return ST_INTERNAL; }
+    for (int c = 0; c < 53; c++) { mlb[c] = ml_base(c); if (ml_xbits(c) != (uint32_t)ml_bits(c)) return ST_INTERNAL; }
     std::vector<uint16_t> huf(1 << HUF_LOG_MAX);
     for (uint32_t i = 0; i < nb; i++) {
         ZBlock& b = blocks[i];
@@ -97,7 +100,7 @@ extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uin
             uint64_t at = b.src + b.lit_pos + skip; uint32_t clen = b.lit_csize - skip;
             uint8_t* dst = lits.data() + b.lit_off;
             if (b.lit_streams == 1) {
-                if (!huf_decode_stream(words, comp, at, clen, huf.data(), hlog, dst, b.lit_regen)) { hc_site = 6; return ST_INVALID_DATA; }
+                if (!huf_decode_stream_w(words, comp, at, clen, huf.data(), hlog, dst, b.lit_regen)) { hc_site = 6; return ST_INVALID_DATA; }
             } else {
                 if (clen < 6) { hc_site = 7; return ST_INVALID_DATA; }
                 uint32_t s1 = load_le16(comp + at), s2 = load_le16(comp + at + 2), s3 = load_le16(comp + at + 4);
@@ -109,19 +112,20 @@ extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uin
                 uint64_t o = at + 6;
                 for (int k = 0; k < 4; k++) {
                     uint32_t cnt = k < 3 ? seg : b.lit_regen - 3 * seg;
-                    if (!huf_decode_stream(words, comp, o, sz[k], huf.data(), hlog, dst + (uint64_t)k * seg, cnt)) { hc_site = 10; return ST_INVALID_DATA; }
+                    if (!huf_decode_stream_w(words, comp, o, sz[k], huf.data(), hlog, dst + (uint64_t)k * seg, cnt)) { hc_site = 10; return ST_INVALID_DATA; }
                     o += sz[k];
                 }
             }
         }
         if (b.nseq) {
             int16_t norm[64]; uint16_t nxt[64];
-            int l0 = seq_table_for(comp, blocks.data(), b, 0, tll.data(), norm, nxt);
-            int l1 = seq_table_for(comp, blocks.data(), b, 1, tof.data(), norm, nxt);
-            int l2 = seq_table_for(comp, blocks.data(), b, 2, tml.data(), norm, nxt);
+            Tab16 tll{tab16.data() + TAB16_LL, 1}, tof{tab16.data() + TAB16_OF, 1}, tml{tab16.data() + TAB16_ML, 1};
+            int l0 = seq_tab16_for(comp, blocks.data(), b, 0, tll, norm, nxt);
+            int l1 = seq_tab16_for(comp, blocks.data(), b, 1, tof, norm, nxt);
+            int l2 = seq_tab16_for(comp, blocks.data(), b, 2, tml, norm, nxt);
             if (l0 < 0 || l1 < 0 || l2 < 0) { hc_site = 11; return ST_INVALID_DATA; }
-            st = decode_sequences(words, comp, b, tll.data(), tof.data(), tml.data(), l0, l1, l2, sll.data() + b.seq_off,
-                                  sml.data() + b.seq_off, sof.data() + b.seq_off);
+            st = decode_sequences16(words, comp, b, tll, tof, tml, l0, l1, l2, llb, mlb, seqs.data() + b.seq_off, &b.esc_n,
+                                    b.esc_idx, b.esc_ll, b.esc_ml);
             if (st) { hc_site = 12; return st; }
         }
     }
@@ -142,8 +146,11 @@ extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uin
         else lit = lits.data() + b.lit_off;
         uint64_t op = 0, lp = 0;
         for (uint32_t s = 0; s < b.nseq; s++) {
-            uint32_t ll = sll[b.seq_off + s], ml = sml[b.seq_off + s];
-            uint32_t off = resolve_rep(sof[b.seq_off + s], b.rep_in);
+            const SeqRec r = seqs[b.seq_off + s];
+            uint32_t ll = r.y & 0xFFFFu, ml = r.y >> 16;
+            if (ll == SEQ_ESC || ml == SEQ_ESC)
+                for (uint32_t q = 0; q < b.esc_n; q++) if (b.esc_idx[q] == s) { ll = b.esc_ll[q]; ml = b.esc_ml[q]; }
+            uint32_t off = resolve_rep(r.x, b.rep_in);
             for (uint32_t k = 0; k < ll; k++) o[op + k] = lit[(lp + k) * stride];
             op += ll; lp += ll;
             if (off == 0 || off > (b.out_off + op) - b.frame_out) { hc_site = 14; return ST_INVALID_DATA; }
