@@ -389,6 +389,9 @@ struct BitWin {
             cnt += 32;
             wp--;
             nx = wp >= 0 ? words[wp] : 0u;
+#if defined(__CUDA_ARCH__)
+            if (wp >= 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + wp - 32));
+#endif
         }
     }
     PNA_HD uint32_t take(uint32_t n) {   // 0 <= n <= 32, n <= cnt
@@ -461,6 +464,14 @@ PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZB
     uint32_t err = 0;
     for (uint32_t i = 0; i < nseq; i++) {
         W = bits_window(wb, b0, pos);
+#if defined(__CUDA_ARCH__)
+        // the stream is consumed downwards ~2 bytes per sequence: pull the sector 128 bytes below into L1 now, so
+        // that no lane of the warp (32 independent streams) ever waits on L2/HBM inside the chain
+        {
+            const uint32_t* pf = wb + (((int32_t)b0 + pos) >> 5) - 32;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf < words ? words : pf));
+        }
+#endif
         const uint32_t ell = tll.get(sll), eof = tof.get(sof), eml = tml.get(sml);
         const uint32_t cll = ell >> 10, cof = eof >> 10, cml = eml >> 10;
         const uint32_t xll = ll_xbits(cll), xml = ml_xbits(cml);
