@@ -1,0 +1,259 @@
+// encode_core.cuh -- bitstream writers of the encode seam (PNA_HD: shared by the sm_100a kernels and the
+// g++ host test build): zstd compressed blocks (RFC 8878) and zlib/DEFLATE fixed-Huffman blocks (RFC 1950/1951)
+// from the (literal length, match length, offset) sequences the LZ77 matcher (kernels_encode.cuh) produces.
+//
+// Replaces `compression_writer` /root/reference/lib/src/entry/write.rs:251-265 (zstd::Encoder level 3,
+// flate2::ZlibEncoder level 6).  Encoded BYTES are not unique and are not pinned by any reference test
+// (SURVEY 8c): the contract is that the reference's decoders (libzstd / zlib inflate) reproduce the plaintext,
+// and the size ratio is reported against the reference's encoder at the same level.
+//
+// Stream shapes written here:
+//   zstd   one frame per entry: magic, FHD 0x00 (no content size / checksum / dictionary -- like the
+//          reference's streaming encoder), Window_Descriptor 0x38 (128 KiB), one block per 32 KiB segment.
+//          Compressed block = Raw_Literals + sequences coded with the PREDEFINED FSE tables (mode byte 0x00),
+//          real offsets only (no repeat codes).  A block that does not shrink becomes a Raw_Block.
+//   zlib   0x78 0x9C, per segment one fixed-Huffman block followed by an empty stored block (the Z_SYNC_FLUSH
+//          marker 00 00 FF FF) so that segments stay byte aligned and can be produced independently; the last
+//          segment's block carries BFINAL; Adler-32 big endian.  A segment that does not shrink is a stored block.
+#pragma once
+#include "common.cuh"
+#include "zstd_core.cuh"
+
+namespace pna {
+namespace enc {
+
+constexpr uint32_t SEG = 32 * 1024;        // bytes per independently matched segment (= zstd block, deflate block)
+constexpr uint32_t MIN_MATCH = 4, MAX_MATCH = 258;
+constexpr uint32_t SEG_SEQ_MAX = SEG / MIN_MATCH;   // sequences a segment can hold
+
+struct Seq { uint32_t off; uint32_t llml; };   // ll | ml << 16 (ll <= 32768, ml <= 258)
+
+// FSE compression tables of the three predefined distributions (libzstd FSE_buildCTable semantics)
+struct FseCTab {
+    uint16_t state[64];     // tableU16
+    int32_t dfs[56];        // deltaFindState per symbol
+    uint32_t dnb[56];       // deltaNbBits per symbol
+    uint32_t log;
+};
+struct EncTables {
+    FseCTab ll, of, ml;
+    uint8_t ll_code[64];    // ll < 64 -> code
+    uint8_t ml_code[128];   // (ml - 3) < 128 -> code
+};
+
+inline void fse_build_ctab(FseCTab* T, int kind) {
+    const int log = kind == 1 ? 5 : 6, n = kind == 0 ? 36 : kind == 1 ? 29 : 53, size = 1 << log;
+    int16_t norm[56];
+    for (int s = 0; s < n; s++) norm[s] = (int16_t)zs::predef_norm(kind, s);
+    uint32_t cumul[57];
+    uint8_t sym_of[64];
+    int high = size - 1;
+    cumul[0] = 0;
+    for (int u = 1; u <= n; u++) {
+        if (norm[u - 1] == -1) { cumul[u] = cumul[u - 1] + 1; sym_of[high--] = (uint8_t)(u - 1); }
+        else cumul[u] = cumul[u - 1] + (uint32_t)norm[u - 1];
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+    int pos = 0;
+    for (int s = 0; s < n; s++)
+        for (int i = 0; i < norm[s]; i++) {
+            sym_of[pos] = (uint8_t)s;
+            pos = (pos + step) & mask;
+            while (pos > high) pos = (pos + step) & mask;
+        }
+    for (int u = 0; u < size; u++) { int s = sym_of[u]; T->state[cumul[s]++] = (uint16_t)(size + u); }
+    int total = 0;
+    for (int s = 0; s < n; s++) {
+        if (norm[s] == 0) { T->dnb[s] = ((uint32_t)(log + 1) << 16) - (1u << log); T->dfs[s] = 0; }
+        else if (norm[s] == -1 || norm[s] == 1) { T->dnb[s] = ((uint32_t)log << 16) - (1u << log); T->dfs[s] = total - 1; total++; }
+        else {
+            const uint32_t max_bits = (uint32_t)log - (uint32_t)highbit32((uint32_t)norm[s] - 1);
+            const uint32_t min_state_plus = (uint32_t)norm[s] << max_bits;
+            T->dnb[s] = (max_bits << 16) - min_state_plus;
+            T->dfs[s] = total - norm[s];
+            total += norm[s];
+        }
+    }
+    T->log = (uint32_t)log;
+}
+inline void make_enc_tables(EncTables* E) {
+    fse_build_ctab(&E->ll, 0); fse_build_ctab(&E->of, 1); fse_build_ctab(&E->ml, 2);
+    for (uint32_t v = 0; v < 64; v++) {
+        int c = 0;
+        while (c + 1 < 36 && zs::ll_base(c + 1) <= v) c++;
+        E->ll_code[v] = (uint8_t)c;
+    }
+    for (uint32_t v = 0; v < 128; v++) {   // v = ml - 3
+        int c = 0;
+        while (c + 1 < 53 && zs::ml_base(c + 1) <= v + 3) c++;
+        E->ml_code[v] = (uint8_t)c;
+    }
+}
+
+// forward little-endian bit writer into 4-byte aligned memory
+struct BitOut {
+    uint8_t* p;
+    uint64_t acc;
+    uint32_t n;        // bits in acc
+    uint32_t bytes;    // bytes written
+    PNA_HD void init(uint8_t* dst) { p = dst; acc = 0; n = 0; bytes = 0; }
+    PNA_HD void add(uint32_t v, uint32_t nb) {   // nb <= 32; v may carry garbage above nb bits
+        if (nb == 0) return;
+        const uint64_t m = nb >= 32 ? 0xFFFFFFFFull : ((1ull << nb) - 1ull);
+        acc |= ((uint64_t)v & m) << n;
+        n += nb;
+        if (n >= 32) {
+            *reinterpret_cast<uint32_t*>(p + bytes) = (uint32_t)acc;
+            bytes += 4;
+            acc >>= 32;
+            n -= 32;
+        }
+    }
+    PNA_HD uint32_t finish() {   // flush whole bytes (zero padded); returns total bytes
+        while (n > 0) { p[bytes++] = (uint8_t)acc; acc >>= 8; n = n > 8 ? n - 8 : 0; }
+        return bytes;
+    }
+};
+
+struct FseCState { uint32_t v; };
+PNA_HD void fse_init_state(FseCState& s, const FseCTab& t, uint32_t sym) {
+    const uint32_t nb = (t.dnb[sym] + (1u << 15)) >> 16;
+    const uint32_t value = (nb << 16) - t.dnb[sym];
+    s.v = t.state[(value >> nb) + (uint32_t)t.dfs[sym]];
+}
+PNA_HD void fse_encode(BitOut& b, FseCState& s, const FseCTab& t, uint32_t sym) {
+    const uint32_t nb = (s.v + t.dnb[sym]) >> 16;
+    b.add(s.v, nb);
+    s.v = t.state[(int32_t)(s.v >> nb) + t.dfs[sym]];
+}
+
+PNA_HD uint32_t ll_code_of(const EncTables& E, uint32_t ll) { return ll < 64 ? E.ll_code[ll] : (uint32_t)highbit32(ll) + 19u; }
+PNA_HD uint32_t ml_code_of(const EncTables& E, uint32_t mlb) { return mlb < 128 ? E.ml_code[mlb] : (uint32_t)highbit32(mlb) + 36u; }
+
+// Sequences section of one block (nseq >= 1): Number_of_Sequences, mode byte 0 (predefined x3), FSE bitstream.
+// dst must be 4-byte aligned, cap bytes.  Returns (offset of first byte << 24) | length, or 0xFFFFFFFF when the
+// section would not fit cap (the caller then emits the segment as a Raw_Block).
+PNA_HD uint32_t zstd_write_sequences(const EncTables& E, const Seq* seqs, uint32_t nseq, uint8_t* dst, uint32_t cap) {
+    // header is written after the bitstream at its front; bitstream starts 4-byte aligned at dst + 4
+    BitOut b;
+    b.init(dst + 4);
+    FseCState sll, sof, sml;
+    {
+        const Seq q = seqs[nseq - 1];
+        const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = q.off + 3u;
+        const uint32_t cl = ll_code_of(E, ll), cm = ml_code_of(E, mlb), co = (uint32_t)highbit32(ob);
+        fse_init_state(sml, E.ml, cm);
+        fse_init_state(sof, E.of, co);
+        fse_init_state(sll, E.ll, cl);
+        b.add(ll, (uint32_t)zs::ll_bits((int)cl));
+        b.add(mlb, (uint32_t)zs::ml_bits((int)cm));
+        b.add(ob, co);
+    }
+    for (uint32_t i = nseq - 1; i-- > 0;) {
+        const Seq q = seqs[i];
+        const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = q.off + 3u;
+        const uint32_t cl = ll_code_of(E, ll), cm = ml_code_of(E, mlb), co = (uint32_t)highbit32(ob);
+        fse_encode(b, sof, E.of, co);
+        fse_encode(b, sml, E.ml, cm);
+        fse_encode(b, sll, E.ll, cl);
+        b.add(ll, (uint32_t)zs::ll_bits((int)cl));
+        b.add(mlb, (uint32_t)zs::ml_bits((int)cm));
+        b.add(ob, co);
+        if (b.bytes + 32 > cap) return 0xFFFFFFFFu;
+    }
+    if (b.bytes + 32 > cap) return 0xFFFFFFFFu;
+    b.add(sml.v, E.ml.log);
+    b.add(sof.v, E.of.log);
+    b.add(sll.v, E.ll.log);
+    b.add(1, 1);
+    const uint32_t bs = b.finish();
+    // Number_of_Sequences (1-3 bytes) + modes byte, right-aligned against the bitstream
+    uint8_t h[4];
+    uint32_t hn;
+    if (nseq < 128) { h[0] = (uint8_t)nseq; hn = 1; }
+    else if (nseq < 0x7F00) { h[0] = (uint8_t)((nseq >> 8) + 0x80); h[1] = (uint8_t)nseq; hn = 2; }
+    else { h[0] = 0xFF; h[1] = (uint8_t)(nseq - 0x7F00); h[2] = (uint8_t)((nseq - 0x7F00) >> 8); hn = 3; }
+    h[hn++] = 0;   // Symbol_Compression_Modes: predefined LL / OF / ML
+    for (uint32_t k = 0; k < hn; k++) dst[4 - hn + k] = h[k];
+    return (4 - hn) << 24 | (hn + bs);   // high byte: offset of the first valid byte inside dst
+}
+
+// Raw_Literals section header for `n` literal bytes; returns header length (1..3)
+PNA_HD uint32_t zstd_raw_lit_header(uint32_t n, uint8_t* h) {
+    if (n < 32) { h[0] = (uint8_t)(n << 3); return 1; }
+    if (n < 4096) { h[0] = (uint8_t)((n << 4) | 4u); h[1] = (uint8_t)(n >> 4); return 2; }
+    h[0] = (uint8_t)((n << 4) | 12u); h[1] = (uint8_t)(n >> 4); h[2] = (uint8_t)(n >> 12);
+    return 3;
+}
+PNA_HD void zstd_block_header(uint32_t last, uint32_t type, uint32_t size, uint8_t* h) {
+    const uint32_t v = last | (type << 1) | (size << 3);
+    h[0] = (uint8_t)v; h[1] = (uint8_t)(v >> 8); h[2] = (uint8_t)(v >> 16);
+}
+
+// ------------------------------------------------------------------------------------------------ deflate
+PNA_HD uint32_t rev_bits_n(uint32_t v, int n) {
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+// fixed literal/length code (RFC 1951 3.2.6), returned bit-reversed for the LSB-first writer: value | nbits << 16
+PNA_HD uint32_t fixed_litlen(uint32_t sym) {
+    uint32_t code, nb;
+    if (sym < 144) { code = 0x30 + sym; nb = 8; }
+    else if (sym < 256) { code = 0x190 + (sym - 144); nb = 9; }
+    else if (sym < 280) { code = sym - 256; nb = 7; }
+    else { code = 0xC0 + (sym - 280); nb = 8; }
+    return rev_bits_n(code, (int)nb) | (nb << 16);
+}
+PNA_HD void deflate_len_sym(uint32_t len, uint32_t* sym, uint32_t* xb, uint32_t* xv) {   // len 3..258
+    if (len == 258) { *sym = 285; *xb = 0; *xv = 0; return; }
+    const uint32_t l = len - 3;
+    if (l < 8) { *sym = 257 + l; *xb = 0; *xv = 0; return; }
+    const uint32_t hb = (uint32_t)highbit32(l);        // >= 3
+    const uint32_t eb = hb - 2;
+    *sym = 257 + 4 * eb + ((l >> eb) & 3) + 4;         // 265 + 4*(eb-1) + top two bits below the leading one
+    *xb = eb; *xv = l & ((1u << eb) - 1u);
+}
+PNA_HD void deflate_dist_sym(uint32_t dist, uint32_t* sym, uint32_t* xb, uint32_t* xv) {   // dist 1..32768
+    const uint32_t d = dist - 1;
+    if (d < 4) { *sym = d; *xb = 0; *xv = 0; return; }
+    const uint32_t hb = (uint32_t)highbit32(d);        // >= 2
+    const uint32_t eb = hb - 1;
+    *sym = 2 * hb + ((d >> eb) & 1);
+    *xb = eb; *xv = d & ((1u << eb) - 1u);
+}
+// One segment as a fixed-Huffman block (+ sync marker unless final).  lits = the segment's literal bytes in
+// order, n_lit_total of them (sequence literal runs first, the rest trail).  dst 4-byte aligned, room for
+// 9/8 * len + 16.  Returns bytes written.
+PNA_HD uint32_t deflate_write_segment(const Seq* seqs, uint32_t nseq, const uint8_t* lits, uint32_t n_lit_total, bool final_seg,
+                                      uint8_t* dst) {
+    BitOut b;
+    b.init(dst);
+    b.add((final_seg ? 1u : 0u) | (1u << 1), 3);   // BFINAL, BTYPE=01
+    uint32_t lp = 0;
+    for (uint32_t i = 0; i < nseq; i++) {
+        const Seq q = seqs[i];
+        const uint32_t ll = q.llml & 0xFFFFu, ml = q.llml >> 16;
+        for (uint32_t k = 0; k < ll; k++) { const uint32_t c = fixed_litlen(lits[lp + k]); b.add(c & 0xFFFFu, c >> 16); }
+        lp += ll;
+        uint32_t sym, xb, xv;
+        deflate_len_sym(ml, &sym, &xb, &xv);
+        const uint32_t c = fixed_litlen(sym);
+        b.add(c & 0xFFFFu, c >> 16);
+        b.add(xv, xb);
+        deflate_dist_sym(q.off, &sym, &xb, &xv);
+        b.add(rev_bits_n(sym, 5), 5);
+        b.add(xv, xb);
+    }
+    for (; lp < n_lit_total; lp++) { const uint32_t c = fixed_litlen(lits[lp]); b.add(c & 0xFFFFu, c >> 16); }
+    { const uint32_t c = fixed_litlen(256); b.add(c & 0xFFFFu, c >> 16); }
+    if (!final_seg) {
+        b.add(0, 3);                               // empty stored block, not final
+        if (b.n & 7) b.add(0, 8 - (b.n & 7));      // to the byte boundary
+        b.add(0x0000u, 16); b.add(0xFFFFu, 16);    // LEN = 0, NLEN = ~0
+    }
+    return b.finish();
+}
+
+}  // namespace enc
+}  // namespace pna

@@ -1,12 +1,336 @@
-// encode_host.cuh -- host side of seam 3 (included at the end of abi.cu).
-extern "C" uint64_t pna_cuda_encode_bound(const pna_encode_desc* d) { return d ? d->plain.len + d->plain.len / 8 + 1024 + 48 : 0; }
+// encode_host.cuh -- host side of seam 3 (included at the end of abi.cu): layout of the work arena, the launch
+// sequence  match -> block writers -> layout -> encrypt -> FDAT CRC,  and the fetch.  The run is fully
+// asynchronous: everything that depends on produced lengths is resolved on the device.
+namespace pna { namespace enc {
+
+struct EncodePlan {
+    std::vector<EncEntry> h_entries;
+    std::vector<SegRec> h_segs;
+    std::vector<DevKeys> h_keys;
+    std::vector<CipherTile> h_tiles[3];       // 0 none (gather), 1 aes-ctr, 2 camellia-ctr
+    std::vector<uint32_t> h_cbc[2];           // aes, camellia
+    std::vector<CrcTileSrc> h_crc_src;
+    std::vector<uint32_t> h_crc_first;        // first tile of every body
+    std::vector<uint32_t> crc_body_begin;     // per entry: first body
+    std::vector<uint32_t> crc_body_size;      // per entry: max_chunk_size (bytes per body)
+    uint64_t work_bytes = 0, out_bytes = 0, n_pieces = 0, seq_total = 0;
+    DevArr<uint8_t> d_work, d_out;
+    DevArr<EncEntry> d_entries, d_entries_init;
+    DevArr<SegRec> d_segs;
+    DevArr<Seq> d_seqs;
+    DevArr<Segment> d_pieces;
+    DevArr<DevKeys> d_keys;
+    DevArr<CipherTile> d_tiles[3];
+    DevArr<uint32_t> d_cbc[2], d_crc_first, d_crc_raw, d_crc_val;
+    DevArr<CrcTileSrc> d_crc_src;
+    DevArr<CrcTile> d_crc_tiles;
+    DevArr<EncTables> d_tables;
+    uint32_t fdat_init = 0;
+};
+void destroy(EncodePlan* p) { delete p; }
+bool init_attributes() {
+    const int aes_smem = 256 * 32 * 4, cam_smem = 2 * 2048 * 4;
+    return cudaFuncSetAttribute(lz_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(encrypt_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(encrypt_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(cbc_encrypt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(cbc_encrypt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
+}
+}}  // namespace pna::enc
+
+using pna::enc::EncodePlan;
+using pna::enc::EncEntry;
+
+static uint64_t enc_nsegs(uint64_t len) { return (len + enc::SEG - 1) / enc::SEG; }
+// upper bound of the compressed stream (before IV / padding): raw-block / stored-block fallbacks bound every segment
+static uint64_t enc_comp_bound(uint8_t compression, uint64_t len) {
+    if (compression == PNA_COMPRESSION_ZSTD) return len + 3 * enc_nsegs(len) + 9;
+    if (compression == PNA_COMPRESSION_DEFLATE) return len + 5 * enc_nsegs(len) + 8;
+    return len;
+}
+extern "C" uint64_t pna_cuda_encode_bound(const pna_encode_desc* d) {
+    if (!d) return 0;
+    return enc_comp_bound(d->compression, d->plain.len) + (d->encryption ? 32 : 0);
+}
 extern "C" uint64_t pna_cuda_encode_crc_count(const pna_encode_desc* d) {
     if (!d) return 0;
-    uint64_t cap = d->max_chunk_size ? d->max_chunk_size : 0xFFFFFFFFull;
-    uint64_t b = pna_cuda_encode_bound(d);
-    return (b + cap - 1) / cap + 1;
+    const uint64_t cap = d->max_chunk_size ? d->max_chunk_size : 0xFFFFFFFFull;
+    const uint64_t body = pna_cuda_encode_bound(d) - (d->encryption ? 16 : 0);
+    return (body + cap - 1) / cap + 1;
 }
-extern "C" int pna_cuda_encode_batch(pna_ctx*, const pna_encode_desc*, uint32_t, pna_buf*, uint32_t*, uint32_t*, int32_t*) { return PNA_E_INTERNAL; }
-extern "C" int pna_cuda_encode_plan_create(pna_ctx*, const pna_encode_desc*, uint32_t, pna_plan**) { return PNA_E_INTERNAL; }
-extern "C" int pna_cuda_encode_plan_run(pna_plan*) { return PNA_E_INTERNAL; }
-extern "C" int pna_cuda_encode_plan_fetch(pna_plan*, pna_buf*, uint32_t*, uint32_t*, int32_t*) { return PNA_E_INTERNAL; }
+
+static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_plan* P) {
+    P->ctx = ctx; P->kind = 1; P->n = n;
+    EncodePlan* E = new EncodePlan();
+    P->enc = E;
+    E->h_entries.resize(n);
+    std::map<std::array<uint8_t, 33>, int> key_ids;
+    // work arena: [plain | literals (same layout) | per-segment tmp | per-entry header scratch]
+    uint64_t plain_total = 0, nsegs_total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const pna_encode_desc& d = descs[i];
+        EncEntry& e = E->h_entries[i];
+        memset(&e, 0, sizeof e);
+        if (d.plain.len && !d.plain.ptr) return PNA_E_BAD_ARG;
+        e.plain_off = plain_total; e.plain_len = d.plain.len;
+        plain_total += align_up(d.plain.len, 16) + 16;
+        e.compression = d.compression; e.encryption = d.encryption; e.cipher_mode = d.cipher_mode;
+        memcpy(e.iv, d.iv, 16);
+        e.key_idx = -1;
+        if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD)
+            e.status = ST_UNSUPPORTED;   // xz: entry/write.rs:264 has it, this path does not
+        else if (d.encryption != PNA_ENCRYPTION_NO && d.encryption != PNA_ENCRYPTION_AES && d.encryption != PNA_ENCRYPTION_CAMELLIA)
+            e.status = ST_UNSUPPORTED;
+        else if (d.encryption != 0 && d.cipher_mode != PNA_CIPHER_CBC && d.cipher_mode != PNA_CIPHER_CTR)
+            e.status = ST_UNSUPPORTED;
+        if (e.status != ST_OK) continue;
+        if (d.compression != PNA_COMPRESSION_NO) { e.seg_begin = (uint32_t)nsegs_total; e.n_segs = (uint32_t)enc_nsegs(d.plain.len); nsegs_total += e.n_segs; }
+        if (d.encryption) {
+            std::array<uint8_t, 33> k;
+            k[0] = d.encryption;
+            memcpy(k.data() + 1, d.key, 32);
+            auto it = key_ids.find(k);
+            if (it == key_ids.end()) {
+                DevKeys dk;
+                memset(&dk, 0, sizeof dk);
+                if (d.encryption == 1) {
+                    AesKey ak; aes256_expand_key(&ctx->h_aes, d.key, &ak);
+                    memcpy(dk.aes_rk, ak.rk, sizeof ak.rk); memcpy(dk.aes_dk, ak.dk, sizeof ak.dk);
+                } else {
+                    CamelliaKey ck; camellia256_expand_key(&ctx->h_cam, d.key, &ck);
+                    memcpy(dk.cam_ek, ck.ek, sizeof ck.ek); memcpy(dk.cam_dk, ck.dk, sizeof ck.dk);
+                }
+                it = key_ids.emplace(k, (int)E->h_keys.size()).first;
+                E->h_keys.push_back(dk);
+            }
+            e.key_idx = it->second;
+        }
+    }
+    if (nsegs_total > 0xFFFFFFF0ull) return PNA_E_OOM;
+    const uint64_t lit_base = align_up(plain_total, 256);
+    const uint64_t tmp_base = lit_base + align_up(plain_total, 256);
+    const uint64_t hdr_base = tmp_base + nsegs_total * enc::TMP_SEG;
+    E->work_bytes = hdr_base + (uint64_t)n * 32 + 256;
+    E->h_segs.resize(nsegs_total);
+    uint64_t out_cur = 0, piece_cur = 0, crc_bodies = 0;
+    E->crc_body_begin.resize(n); E->crc_body_size.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        EncEntry& e = E->h_entries[i];
+        const pna_encode_desc& d = descs[i];
+        e.hdr_off = hdr_base + (uint64_t)i * 32;
+        e.piece_begin = piece_cur;
+        e.out_off = out_cur;
+        E->crc_body_begin[i] = (uint32_t)crc_bodies;
+        E->crc_body_size[i] = d.max_chunk_size ? d.max_chunk_size : 0xFFFFFFFFu;
+        if (e.status != ST_OK) continue;
+        for (uint32_t k = 0; k < e.n_segs; k++) {
+            enc::SegRec& s = E->h_segs[e.seg_begin + k];
+            memset(&s, 0, sizeof s);
+            s.plain_off = e.plain_off + (uint64_t)k * enc::SEG;
+            s.lit_off = lit_base + s.plain_off;
+            s.tmp_off = tmp_base + (uint64_t)(e.seg_begin + k) * enc::TMP_SEG;
+            s.seq_off = (uint64_t)(e.seg_begin + k) * enc::SEG_SEQ_MAX;
+            s.len = (uint32_t)std::min<uint64_t>(enc::SEG, e.plain_len - (uint64_t)k * enc::SEG);
+            s.entry = i;
+            s.last = k + 1 == e.n_segs;
+        }
+        piece_cur += 3 + 3 * (uint64_t)e.n_segs;
+        const uint64_t bound = enc_comp_bound(e.compression, e.plain_len) + (e.encryption ? 32 : 0);
+        e.out_cap = bound;
+        out_cur += align_up(bound, 16) + 16;
+        // cipher work from the bound: CTR / none tiles, CBC list
+        const uint64_t cb = enc_comp_bound(e.compression, e.plain_len);
+        if (e.encryption && e.cipher_mode == PNA_CIPHER_CBC) E->h_cbc[e.encryption - 1].push_back(i);
+        else {
+            std::vector<CipherTile>& tv = E->h_tiles[e.encryption];
+            const uint64_t nb = (cb + 15) / 16;
+            uint64_t b0 = 0;
+            do {   // at least one tile per entry: it also writes the IV
+                tv.push_back(CipherTile{i, (uint32_t)std::min<uint64_t>(CIPHER_TILE_BLOCKS, nb > b0 ? nb - b0 : 0), b0});
+                b0 += CIPHER_TILE_BLOCKS;
+            } while (b0 < nb);
+        }
+        // FDAT bodies after the IV (the IV is its own chunk, lib/src/entry/builder.rs:62-69)
+        const uint64_t iv_len = e.encryption ? 16 : 0, mcs = E->crc_body_size[i];
+        const uint64_t nbody = (bound - iv_len + mcs - 1) / mcs + 1;
+        for (uint64_t b = 0; b < nbody; b++) {
+            E->h_crc_first.push_back((uint32_t)E->h_crc_src.size());
+            const uint64_t lo = iv_len + b * mcs;
+            uint64_t l = mcs;
+            uint64_t o = lo;
+            do {
+                const uint32_t t = (uint32_t)std::min<uint64_t>(l, CRC_TILE);
+                E->h_crc_src.push_back({o, t, i, (uint32_t)(crc_bodies + b)});
+                o += t; l -= t;
+            } while (l && o < bound + 16);
+        }
+        crc_bodies += nbody;
+    }
+    E->n_pieces = piece_cur;
+    E->out_bytes = out_cur;
+    E->seq_total = nsegs_total * enc::SEG_SEQ_MAX;
+    if (crc_bodies > 0xFFFFFFF0ull || E->h_crc_src.size() > 0xFFFFFFF0ull) return PNA_E_OOM;
+    // device arrays + upload
+    CK(E->d_work.reserve(E->work_bytes)); CK(E->d_out.reserve(E->out_bytes + 256));
+    CK(E->d_entries.reserve(n)); CK(E->d_entries_init.reserve(n));
+    CK(E->d_segs.reserve(nsegs_total)); CK(E->d_seqs.reserve(E->seq_total + 8)); CK(E->d_pieces.reserve(piece_cur + 1));
+    CK(E->d_keys.reserve(E->h_keys.size())); CK(E->d_tables.reserve(1));
+    for (uint32_t i = 0; i < n; i++)
+        if (descs[i].plain.len && E->h_entries[i].status == ST_OK)
+            CK(cudaMemcpyAsync(E->d_work.p + E->h_entries[i].plain_off, descs[i].plain.ptr, descs[i].plain.len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(E->d_entries_init.p, E->h_entries.data(), n * sizeof(EncEntry), cudaMemcpyHostToDevice, ctx->stream));
+    if (nsegs_total) CK(cudaMemcpyAsync(E->d_segs.p, E->h_segs.data(), nsegs_total * sizeof(enc::SegRec), cudaMemcpyHostToDevice, ctx->stream));
+    if (!E->h_keys.empty()) CK(cudaMemcpyAsync(E->d_keys.p, E->h_keys.data(), E->h_keys.size() * sizeof(DevKeys), cudaMemcpyHostToDevice, ctx->stream));
+    static enc::EncTables h_tables; static bool h_tables_init = false;
+    if (!h_tables_init) { enc::make_enc_tables(&h_tables); h_tables_init = true; }
+    CK(cudaMemcpyAsync(E->d_tables.p, &h_tables, sizeof h_tables, cudaMemcpyHostToDevice, ctx->stream));
+    for (int v = 0; v < 3; v++) {
+        if (E->h_tiles[v].empty()) continue;
+        CK(E->d_tiles[v].reserve(E->h_tiles[v].size()));
+        CK(cudaMemcpyAsync(E->d_tiles[v].p, E->h_tiles[v].data(), E->h_tiles[v].size() * sizeof(CipherTile), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (int v = 0; v < 2; v++) {
+        if (E->h_cbc[v].empty()) continue;
+        CK(E->d_cbc[v].reserve(E->h_cbc[v].size()));
+        CK(cudaMemcpyAsync(E->d_cbc[v].p, E->h_cbc[v].data(), E->h_cbc[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const size_t nt = E->h_crc_src.size(), nb = E->h_crc_first.size();
+    if (nt) {
+        CK(E->d_crc_src.reserve(nt)); CK(E->d_crc_tiles.reserve(nt)); CK(E->d_crc_raw.reserve(nt));
+        CK(E->d_crc_first.reserve(nb)); CK(E->d_crc_val.reserve(nb));
+        CK(cudaMemcpyAsync(E->d_crc_src.p, E->h_crc_src.data(), nt * sizeof(enc::CrcTileSrc), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(E->d_crc_first.p, E->h_crc_first.data(), nb * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    {   // register value after the chunk type: chunk CRC covers type || data (lib/src/format/chunk.rs:7-12)
+        uint32_t c = 0xFFFFFFFFu;
+        const uint8_t ty[4] = {'F', 'D', 'A', 'T'};
+        for (int k = 0; k < 4; k++) { c ^= ty[k]; for (int b = 0; b < 8; b++) c = (c >> 1) ^ (CRC_POLY & (0u - (c & 1u))); }
+        E->fdat_init = c;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));   // the borrowed plaintext may go away after this call
+    for (uint32_t i = 0; i < n; i++) P->plain_bytes += descs[i].plain.len;
+    return PNA_OK;
+}
+
+static int encode_launch_all(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    EncodePlan* E = P->enc;
+    const uint64_t l0 = ctx->launches;
+    const uint32_t n = P->n, nsegs = (uint32_t)E->h_segs.size();
+    CK(cudaMemcpyAsync(E->d_entries.p, E->d_entries_init.p, n * sizeof(EncEntry), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nsegs) {
+        enc::lz_match_kernel<<<(nsegs + enc::ENC_WARPS - 1) / enc::ENC_WARPS, 32 * enc::ENC_WARPS, enc::MATCH_SMEM_BYTES, ctx->stream>>>(
+            E->d_work.p, E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p);
+        LAUNCHED();
+        enc::enc_block_kernel<<<(nsegs + 127) / 128, 128, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p,
+                                                                           E->d_entries.p);
+        LAUNCHED();
+    }
+    enc::enc_layout_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, E->d_entries.p, n, E->d_pieces.p);
+    LAUNCHED();
+    const int aes_smem = 256 * 32 * 4, cam_smem = 2 * 2048 * 4;
+    for (int v = 0; v < 3; v++) {
+        const uint32_t nt = (uint32_t)E->h_tiles[v].size();
+        if (!nt) continue;
+        const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)ctx->sm_count * (v == 1 ? 4 : 6));
+#define ARGS E->d_work.p, E->d_pieces.p, E->d_entries.p, E->d_tiles[v].p, nt, E->d_keys.p, ctx->d_aes, ctx->d_cam, E->d_out.p
+        if (v == 0) enc::encrypt_tiles_kernel<0><<<grid, 256, 0, ctx->stream>>>(ARGS);
+        else if (v == 1) enc::encrypt_tiles_kernel<1><<<grid, 256, aes_smem, ctx->stream>>>(ARGS);
+        else enc::encrypt_tiles_kernel<2><<<grid, 256, cam_smem, ctx->stream>>>(ARGS);
+#undef ARGS
+        LAUNCHED();
+    }
+    for (int v = 0; v < 2; v++) {
+        const uint32_t nc = (uint32_t)E->h_cbc[v].size();
+        if (!nc) continue;
+#define ARGS E->d_work.p, E->d_pieces.p, E->d_entries.p, E->d_cbc[v].p, nc, E->d_keys.p, ctx->d_aes, ctx->d_cam, E->d_out.p
+        if (v == 0) enc::cbc_encrypt_kernel<1><<<(nc + 63) / 64, 64, aes_smem, ctx->stream>>>(ARGS);
+        else enc::cbc_encrypt_kernel<2><<<(nc + 63) / 64, 64, cam_smem, ctx->stream>>>(ARGS);
+#undef ARGS
+        LAUNCHED();
+    }
+    const uint32_t nt = (uint32_t)E->h_crc_src.size(), nb = (uint32_t)E->h_crc_first.size();
+    if (nt) {
+        enc::crc_clip_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(E->d_crc_src.p, nt, E->d_entries.p, E->d_crc_tiles.p);
+        LAUNCHED();
+        const uint32_t grid = std::min<uint32_t>((nt + 7) / 8, (uint32_t)ctx->sm_count * 8);
+        crc_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(E->d_out.p, E->d_crc_tiles.p, nt, ctx->d_crc, E->d_crc_raw.p);
+        LAUNCHED();
+        crc_combine_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(E->d_crc_tiles.p, E->d_crc_raw.p, E->d_crc_first.p, nb, nt, ctx->d_crc,
+                                                                     E->d_crc_val.p, E->fdat_init);
+        LAUNCHED();
+    }
+    P->launches_per_run = ctx->launches - l0;
+    P->prepared = true;
+    return PNA_OK;
+}
+
+extern "C" int pna_cuda_encode_plan_create(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_plan** plan) {
+    if (!ctx || !plan || (!descs && n)) return PNA_E_BAD_ARG;
+    *plan = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    pna_plan* P = new pna_plan();
+    int rc = n ? encode_plan_build(ctx, descs, n, P) : (P->ctx = ctx, P->kind = 1, PNA_OK);
+    if (rc) { delete P; return rc; }
+    *plan = P;
+    return PNA_OK;
+}
+extern "C" int pna_cuda_encode_plan_run(pna_plan* P) {
+    if (!P || P->kind != 1) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (P->n == 0) return PNA_OK;
+    return encode_launch_all(P);
+}
+extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status) {
+    if (!P || P->kind != 1 || ((!out || !status) && P->n)) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (P->n == 0) return PNA_OK;
+    if (!P->prepared) return PNA_E_BAD_ARG;
+    EncodePlan* E = P->enc;
+    std::vector<EncEntry> dev(P->n);
+    std::vector<uint32_t> crcs(E->h_crc_first.size());
+    CK(cudaMemcpyAsync(dev.data(), E->d_entries.p, P->n * sizeof(EncEntry), cudaMemcpyDeviceToHost, ctx->stream));
+    if (fdat_crc_out && !crcs.empty())
+        CK(cudaMemcpyAsync(crcs.data(), E->d_crc_val.p, crcs.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t stream_bytes = 0, crc_pos = 0;
+    for (uint32_t i = 0; i < P->n; i++) {
+        const EncEntry& e = dev[i];
+        int32_t st = e.status;
+        uint64_t len = st == ST_OK ? e.out_len : 0;
+        if (st == ST_OK && len > out[i].cap) st = ST_NOSPACE;
+        out[i].len = (st == ST_OK || st == ST_NOSPACE) ? e.out_len : 0;
+        status[i] = st;
+        uint32_t nbody = 0;
+        if (st == ST_OK) {
+            if (len) CK(cudaMemcpyAsync(out[i].ptr, E->d_out.p + e.out_off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            stream_bytes += len;
+            const uint64_t iv_len = e.encryption ? 16 : 0, mcs = E->crc_body_size[i];
+            nbody = (uint32_t)((len - iv_len + mcs - 1) / mcs);
+            if (fdat_crc_out)
+                for (uint32_t b = 0; b < nbody; b++) fdat_crc_out[crc_pos + b] = crcs[E->crc_body_begin[i] + b];
+        }
+        if (crc_count_out) crc_count_out[i] = nbody;
+        crc_pos += nbody;
+    }
+    P->stream_bytes = stream_bytes;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PNA_OK;
+}
+extern "C" int pna_cuda_encode_batch(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_buf* out, uint32_t* fdat_crc_out,
+                                     uint32_t* crc_count_out, int32_t* status) {
+    if (!ctx || ((!descs || !out || !status) && n)) return PNA_E_BAD_ARG;
+    if (n == 0) return PNA_OK;
+    pna_plan* P = nullptr;
+    int rc = pna_cuda_encode_plan_create(ctx, descs, n, &P);
+    if (rc) return rc;
+    rc = pna_cuda_encode_plan_run(P);
+    if (rc == PNA_OK) rc = pna_cuda_encode_plan_fetch(P, out, fdat_crc_out, crc_count_out, status);
+    pna_cuda_plan_destroy(P);
+    return rc;
+}

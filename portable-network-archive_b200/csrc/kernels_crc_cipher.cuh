@@ -58,11 +58,12 @@ __global__ void __launch_bounds__(256) crc_tiles_kernel(const uint8_t* __restric
 // combine the tiles of each span: acc <- acc * x^(8 len) ^ raw ; crc = ~acc
 __global__ void crc_combine_kernel(const CrcTile* __restrict__ tiles, const uint32_t* __restrict__ raw,
                                    const uint32_t* __restrict__ span_first_tile, uint32_t n_spans, uint32_t n_tiles,
-                                   const CrcConsts* __restrict__ C, uint32_t* __restrict__ crc_out) {
+                                   const CrcConsts* __restrict__ C, uint32_t* __restrict__ crc_out,
+                                   uint32_t init = 0xFFFFFFFFu /* register before the span: ~crc of a prefix (e.g. "FDAT") */) {
     uint32_t sp = blockIdx.x * blockDim.x + threadIdx.x;
     if (sp >= n_spans) return;
     uint32_t t0 = span_first_tile[sp], t1 = sp + 1 < n_spans ? span_first_tile[sp + 1] : n_tiles;
-    uint32_t acc = 0xFFFFFFFFu;
+    uint32_t acc = init;
     for (uint32_t t = t0; t < t1; t++) {
         uint32_t len = tiles[t].len;
         uint32_t sh = len == CRC_TILE ? C->x_tile : crc_x2nmodp(C->x2n, len, 3);

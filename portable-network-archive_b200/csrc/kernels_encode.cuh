@@ -1,9 +1,398 @@
-// kernels_encode.cuh -- encode-side kernels (K6/K7 + cipher encrypt + FDAT CRC).  Placeholder until the
-// encoders land: the entry points report PNA_E_INTERNAL so nothing silently falls back.
+// kernels_encode.cuh -- sm_100a kernels of the encode seam (K6/K7 + cipher encrypt + FDAT CRC):
+//   lz_match_kernel      (warp per 32 KiB segment)  warp-synchronous greedy LZ77: 32 positions per step, candidates
+//                        from a shared-memory hash table AND from the step's own lanes (__match_any_sync), greedy
+//                        parse of the step by pointer doubling with shuffles, sequences + literals compacted by ballots
+//   enc_block_kernel     (lane per segment)         zstd block (predefined-FSE sequences, raw literals) or deflate
+//                        fixed-Huffman block, written by the PNA_HD writers of encode_core.cuh
+//   enc_layout_kernel    (thread per entry)         frame header / trailer, piece list of the compressed stream, Adler-32
+//   encrypt_tiles_kernel (thread per 16-byte block) gather the pieces, AES/Camellia CTR (or plain copy) into the output
+//   cbc_encrypt_kernel   (lane per entry)           CBC is a serial chain per stream: entry-level parallelism only
+//   crc_clip_kernel      clips the bound-based CRC tile table to the produced stream lengths (no host round trip)
 #pragma once
+#include <cuda_runtime.h>
 #include "common.cuh"
-namespace pna { namespace enc {
-struct EncodePlan {};
-inline bool init_attributes() { return true; }
-inline void destroy(EncodePlan* p) { delete p; }
-}}
+#include "encode_core.cuh"
+#include "kernels_crc_cipher.cuh"
+
+namespace pna {
+namespace enc {
+
+struct SegRec {            // one segment (host fills the first group, kernels the second)
+    uint64_t plain_off;    // all offsets are relative to the work arena
+    uint64_t lit_off;
+    uint64_t tmp_off;      // 16 bytes of head + body
+    uint64_t seq_off;      // index into the Seq arena
+    uint32_t len, entry, last, _pad;
+    uint32_t nseq, nlit;
+    uint32_t head_len, raw;        // raw: pieces = head + plain; else head + literals + tail (zstd) / body (deflate)
+    uint32_t tail_off, tail_len;   // inside the body
+    uint64_t adler_a, adler_b;     // sum of bytes, sum of (len - k) * byte_k
+};
+constexpr uint32_t TMP_HEAD = 16;
+constexpr uint32_t TMP_SEG = TMP_HEAD + SEG + SEG / 8 + 112;   // 36992: head + worst fixed-Huffman body, multiple of 16
+
+struct EncEntry {
+    uint64_t plain_off, plain_len;
+    uint64_t piece_begin;          // first Segment of this entry's piece list
+    uint64_t hdr_off;              // 32 bytes of scratch in the work arena: frame header at +0, trailer at +16
+    uint64_t out_off, out_cap;
+    uint64_t comp_len, out_len;    // device written
+    uint32_t seg_begin, n_segs;
+    uint32_t n_pieces;             // device written
+    int32_t key_idx;
+    int32_t status;
+    uint8_t compression, encryption, cipher_mode, _pad;
+    uint8_t iv[16];
+};
+
+constexpr int ENC_WARPS = 5;
+constexpr int HLOG = 12;
+struct MatchSmem {
+    uint8_t data[SEG + 272];       // segment + zero tail (compare loops may look MAX_MATCH past a position)
+    uint16_t table[1 << HLOG];
+};
+constexpr uint32_t MATCH_SMEM_BYTES = (uint32_t)sizeof(MatchSmem) * ENC_WARPS;
+static_assert(sizeof(MatchSmem) % 16 == 0, "16-byte aligned per warp");
+
+__global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t* __restrict__ work_ro, uint8_t* __restrict__ work,
+                                                                  SegRec* __restrict__ segs, uint32_t nsegs, Seq* __restrict__ seqs) {
+    extern __shared__ __align__(16) uint8_t match_smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
+    if (s >= nsegs) return;
+    MatchSmem* const S = reinterpret_cast<MatchSmem*>(match_smem_raw) + (threadIdx.x >> 5);
+    const SegRec sr = segs[s];
+    const uint32_t len = sr.len;
+    // ---- load the segment (16-byte rows), zero the tail, clear the table, Adler partial sums on the way
+    uint64_t ad_a = 0, ad_b = 0;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(work_ro + sr.plain_off);
+        const uint32_t rows = (len + 15) / 16;
+        for (uint32_t i = lane; i < (SEG + 272) / 16; i += 32) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (i < rows) {
+                v = src[i];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t keep[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p0 = i * 16 + 4 * k;
+                    uint32_t m = p0 + 4 <= len ? 0xFFFFFFFFu : p0 >= len ? 0u : (0xFFFFFFFFu >> (8 * (4 - (len - p0))));
+                    keep[k] = w[k] & m;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t byte = (keep[k] >> (8 * b)) & 0xFF;
+                        const uint32_t p = p0 + b;
+                        ad_a += byte;
+                        if (p < len) ad_b += (uint64_t)(len - p) * byte;
+                    }
+                }
+                v = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+            }
+            reinterpret_cast<uint4*>(S->data)[i] = v;
+        }
+        for (uint32_t i = lane; i < (1u << HLOG) * 2 / 16; i += 32) reinterpret_cast<uint4*>(S->table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ad_a += __shfl_xor_sync(0xFFFFFFFFu, ad_a, o); ad_b += __shfl_xor_sync(0xFFFFFFFFu, ad_b, o); }
+    }
+    __syncwarp();
+    const uint8_t* const d = S->data;
+    Seq* const sq = seqs + sr.seq_off;
+    uint8_t* const lits = work + sr.lit_off;
+    uint32_t nseq = 0, nlit = 0, lit_at_last = 0;   // literals emitted before the last match
+    uint32_t carry = 0;                              // first position of the next step that is not covered by a match
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t p = base + lane;
+        const bool valid = p + 4 <= len;
+        const uint32_t v = (uint32_t)d[p] | ((uint32_t)d[p + 1] << 8) | ((uint32_t)d[p + 2] << 16) | ((uint32_t)d[p + 3] << 24);
+        const uint32_t h = (v * 2654435761u) >> (32 - HLOG);
+        const uint32_t ct = valid ? S->table[h] : 0xFFFFu;
+        // nearest lower lane of this step with the same 4 bytes
+        const uint32_t vm = __match_any_sync(0xFFFFFFFFu, valid ? (unsigned long long)v : (0x100000000ull | (unsigned)lane));
+        const uint32_t lower = vm & lt;
+        const uint32_t cw = lower ? base + (31u - (uint32_t)__clz((int)lower)) : 0xFFFFu;
+        __syncwarp();
+        {   // insert: the highest lane of each hash group wins (deterministic), every position is inserted
+            const uint32_t hm = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u | (unsigned)lane));
+            if (valid && lane == 31 - __clz((int)hm)) S->table[h] = (uint16_t)p;
+        }
+        if (carry >= 32) { carry -= 32; continue; }   // the whole step lies inside a match
+        // ---- match lengths against both candidates in one loop
+        uint32_t best = 0, boff = 0;
+        if (valid) {
+            const uint32_t maxlen = len - p < MAX_MATCH ? len - p : MAX_MATCH;
+            bool aw = cw != 0xFFFFu, at = ct != 0xFFFFu && ct != cw;
+            uint32_t lw = 0, ltb = 0, k = 0;
+            while (k < maxlen && (aw || at)) {
+                const uint8_t c = d[p + k];
+                if (aw && d[cw + k] != c) { aw = false; lw = k; }
+                if (at && d[ct + k] != c) { at = false; ltb = k; }
+                k++;
+            }
+            if (aw) lw = k;
+            if (at) ltb = k;
+            if (lw >= MIN_MATCH && lw >= ltb) { best = lw; boff = p - cw; }
+            else if (ltb >= MIN_MATCH) { best = ltb; boff = p - ct; }
+        }
+        // ---- greedy parse of the step: orbit of `carry` under p -> p + (match ? len : 1), by pointer doubling
+        uint32_t J = (uint32_t)lane + (best ? best : 1u);
+        bool M = (uint32_t)lane == carry;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const uint32_t bits = (M && J < 32) ? (1u << J) : 0u;
+            const uint32_t all = __reduce_or_sync(0xFFFFFFFFu, bits);
+            M = M || ((all >> lane) & 1u);
+            const uint32_t Jn = __shfl_sync(0xFFFFFFFFu, J, (int)(J & 31));
+            J = J < 32 ? Jn : J;
+        }
+        const uint32_t carry_out = __shfl_sync(0xFFFFFFFFu, J, (int)carry) - 32u;
+        const bool is_match = M && best != 0;
+        const bool is_lit = M && best == 0 && p < len;
+        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, is_match), lmask = __ballot_sync(0xFFFFFFFFu, is_lit);
+        if (is_match) {
+            const uint32_t prev = mmask & lt;
+            uint32_t ll;
+            if (prev) { const uint32_t pl = 31u - (uint32_t)__clz((int)prev); ll = (uint32_t)__popc(lmask & lt & ~((2u << pl) - 1u)); }
+            else ll = (uint32_t)__popc(lmask & lt) + (nlit - lit_at_last);
+            Seq q;
+            q.off = boff;
+            q.llml = ll | (best << 16);
+            sq[nseq + (uint32_t)__popc(prev)] = q;
+        }
+        if (is_lit) lits[nlit + (uint32_t)__popc(lmask & lt)] = d[p];
+        if (mmask) {
+            const uint32_t lastm = 31u - (uint32_t)__clz((int)mmask);
+            lit_at_last = nlit + (uint32_t)__popc(lmask & ((1u << lastm) - 1u));
+        }
+        nseq += (uint32_t)__popc(mmask);
+        nlit += (uint32_t)__popc(lmask);
+        carry = carry_out;
+    }
+    if (lane == 0) {
+        segs[s].nseq = nseq; segs[s].nlit = nlit;
+        segs[s].adler_a = ad_a; segs[s].adler_b = ad_b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ work, SegRec* __restrict__ segs, uint32_t nsegs,
+                                                        const Seq* __restrict__ seqs, const EncTables* __restrict__ tables,
+                                                        const EncEntry* __restrict__ entries) {
+    __shared__ EncTables T;
+    for (uint32_t i = threadIdx.x; i < sizeof(EncTables) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&T)[i] = reinterpret_cast<const uint32_t*>(tables)[i];
+    __syncthreads();
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsegs) return;
+    SegRec& sr = segs[s];
+    const uint32_t len = sr.len, nseq = sr.nseq, nlit = sr.nlit, last = sr.last;
+    uint8_t* const head = work + sr.tmp_off;
+    uint8_t* const body = head + TMP_HEAD;
+    const Seq* sq = seqs + sr.seq_off;
+    if (entries[sr.entry].compression == 2) {
+        uint32_t ssz = 1, soff = 0;
+        bool fits = true;
+        if (nseq) {
+            const uint32_t r = zstd_write_sequences(T, sq, nseq, body, TMP_SEG - TMP_HEAD);
+            if (r == 0xFFFFFFFFu) fits = false;
+            soff = r >> 24; ssz = r & 0xFFFFFFu;
+        } else body[0] = 0;
+        uint8_t lh[3];
+        const uint32_t lhn = zstd_raw_lit_header(nlit, lh);
+        const uint32_t csize = lhn + nlit + ssz;
+        if (!fits || csize >= len) {
+            zstd_block_header(last, 0, len, head);
+            sr.head_len = 3; sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0;
+        } else {
+            zstd_block_header(last, 2, csize, head);
+            for (uint32_t k = 0; k < lhn; k++) head[3 + k] = lh[k];
+            sr.head_len = 3 + lhn; sr.raw = 0; sr.tail_off = soff; sr.tail_len = ssz;
+        }
+    } else {
+        const uint32_t sz = deflate_write_segment(sq, nseq, work + sr.lit_off, nlit, last != 0, body);
+        if (sz >= len + 5) {
+            head[0] = (uint8_t)(last ? 1 : 0); head[1] = (uint8_t)len; head[2] = (uint8_t)(len >> 8);
+            head[3] = (uint8_t)~len; head[4] = (uint8_t)(~len >> 8);
+            sr.head_len = 5; sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0;
+        } else { sr.head_len = 0; sr.raw = 0; sr.tail_off = 0; sr.tail_len = sz; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void enc_layout_kernel(uint8_t* __restrict__ work, const SegRec* __restrict__ segs, EncEntry* __restrict__ entries,
+                                  uint32_t n, Segment* __restrict__ pieces) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EncEntry& e = entries[i];
+    if (e.status != ST_OK) { e.comp_len = 0; e.n_pieces = 0; return; }
+    Segment* P = pieces + e.piece_begin;
+    uint64_t pos = 0;
+    uint32_t np = 0;
+    auto add = [&](uint64_t off, uint64_t len) { if (len) { P[np].img_off = off; P[np].pos = pos; np++; pos += len; } };
+    uint8_t* h = work + e.hdr_off;
+    if (e.compression == 0) add(e.plain_off, e.plain_len);
+    else if (e.compression == 2) {
+        h[0] = 0x28; h[1] = 0xB5; h[2] = 0x2F; h[3] = 0xFD; h[4] = 0x00; h[5] = 0x38;
+        if (e.n_segs == 0) { zstd_block_header(1, 0, 0, h + 6); add(e.hdr_off, 9); }
+        else add(e.hdr_off, 6);
+        for (uint32_t k = e.seg_begin; k < e.seg_begin + e.n_segs; k++) {
+            const SegRec& s = segs[k];
+            add(s.tmp_off, s.head_len);
+            if (s.raw) add(s.plain_off, s.len);
+            else { add(s.lit_off, s.nlit); add(s.tmp_off + TMP_HEAD + s.tail_off, s.tail_len); }
+        }
+    } else {
+        h[0] = 0x78; h[1] = 0x9C;
+        if (e.n_segs == 0) { h[2] = 0x03; h[3] = 0x00; add(e.hdr_off, 4); }
+        else add(e.hdr_off, 2);
+        uint64_t a = 1, b = e.plain_len % 65521u, o = 0;
+        for (uint32_t k = e.seg_begin; k < e.seg_begin + e.n_segs; k++) {
+            const SegRec& s = segs[k];
+            if (s.raw) { add(s.tmp_off, s.head_len); add(s.plain_off, s.len); }
+            else add(s.tmp_off + TMP_HEAD, s.tail_len);
+            a = (a + s.adler_a) % 65521u;
+            const uint64_t rest = (e.plain_len - o - s.len) % 65521u;
+            b = (b + s.adler_b % 65521u + rest * (s.adler_a % 65521u)) % 65521u;
+            o += s.len;
+        }
+        const uint32_t ad = (uint32_t)((b << 16) | a);
+        h[16] = (uint8_t)(ad >> 24); h[17] = (uint8_t)(ad >> 16); h[18] = (uint8_t)(ad >> 8); h[19] = (uint8_t)ad;
+        add(e.hdr_off + 16, 4);
+    }
+    e.n_pieces = np;
+    e.comp_len = pos;
+    const uint64_t hdr = e.encryption ? 16 : 0;
+    e.out_len = e.encryption && e.cipher_mode == 0 ? hdr + (pos / 16 + 1) * 16 : hdr + pos;
+    if (e.out_len > e.out_cap) { e.status = ST_NOSPACE; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTR encrypt (or plain gather) of the piece list into the output: out = [IV |] E_K(IV + i) ^ stream.
+// Tiles are built on the host from the stream-length BOUND; blocks past the produced length do nothing.
+template <int ENC /*0 none, 1 aes, 2 camellia*/>
+__global__ void __launch_bounds__(256) encrypt_tiles_kernel(const uint8_t* __restrict__ work, const Segment* __restrict__ pieces,
+                                                            const EncEntry* __restrict__ entries,
+                                                            const CipherTile* __restrict__ tiles, uint32_t n_tiles,
+                                                            const DevKeys* __restrict__ keys, const AesTables* __restrict__ aes,
+                                                            const CamelliaTables* __restrict__ cam, uint8_t* __restrict__ out) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* s_tab = smem;
+    if (ENC == 1) { for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_tab[i] = aes->te0[i >> 5]; }
+    else if (ENC == 2) {
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) { s_tab[i] = (&cam->sp_hi[0][0])[i]; s_tab[2048 + i] = (&cam->sp_lo[0][0])[i]; }
+    }
+    __shared__ uint32_t s_key32[60];
+    __shared__ uint64_t s_key64[34];
+    __shared__ int s_key_idx;
+    if (threadIdx.x == 0) s_key_idx = -2;
+    __syncthreads();
+    const TabView tv{s_tab, 32, (uint32_t)(threadIdx.x & 31)};
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const CipherTile tl = tiles[t];
+        const EncEntry& e = entries[tl.entry];
+        if (e.status != ST_OK) continue;
+        const uint64_t clen = e.comp_len;
+        if (ENC != 0 && e.key_idx != s_key_idx) {
+            __syncthreads();
+            const DevKeys* k = keys + e.key_idx;
+            if (ENC == 1) { if (threadIdx.x < 60) s_key32[threadIdx.x] = k->aes_rk[threadIdx.x]; }
+            else { if (threadIdx.x < 34) s_key64[threadIdx.x] = k->cam_ek[threadIdx.x]; }
+            if (threadIdx.x == 0) s_key_idx = e.key_idx;
+            __syncthreads();
+        }
+        const Segment* sg = pieces + e.piece_begin;
+        uint8_t* dst = out + e.out_off + (ENC ? 16 : 0);
+        uint32_t iv[4] = {0, 0, 0, 0};
+        if (ENC) {
+            for (int k = 0; k < 16; k++) iv[k >> 2] |= (uint32_t)e.iv[k] << (8 * (k & 3));
+            if (tl.first_block == 0 && threadIdx.x < 16) out[e.out_off + threadIdx.x] = e.iv[threadIdx.x];
+        }
+        for (uint32_t j = threadIdx.x; j < tl.n_blocks; j += blockDim.x) {
+            const uint64_t bi = tl.first_block + j;
+            if (bi * 16 >= clen) break;
+            const uint32_t have = (uint32_t)(clen - bi * 16 >= 16 ? 16 : clen - bi * 16);
+            uint32_t c[4] = {0, 0, 0, 0};
+            if (have == 16) load_stream16(work, sg, e.n_pieces, clen, bi * 16, c);
+            else for (uint32_t k = 0; k < have; k++) c[k >> 2] |= (uint32_t)load_stream1(work, sg, e.n_pieces, bi * 16 + k) << (8 * (k & 3));
+            uint32_t o[4] = {c[0], c[1], c[2], c[3]};
+            if (ENC != 0) {
+                ctr128be_add(iv, bi, o);
+                if (ENC == 1) aes256_encrypt_block(o, s_key32, tv);
+                else camellia256_crypt_block(o, s_key64, s_tab, s_tab + 2048);
+                o[0] ^= c[0]; o[1] ^= c[1]; o[2] ^= c[2]; o[3] ^= c[3];
+            }
+            if (have == 16) *reinterpret_cast<uint4*>(dst + bi * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            else for (uint32_t k = 0; k < have; k++) dst[bi * 16 + k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
+// CBC encrypt: C_i = E_K(P_i ^ C_{i-1}), PKCS#7 always appends (lib/src/cipher/block/write.rs:48-57,124).
+// One lane per entry -- the chain is serial; list[] = indices of the CBC entries of this cipher.
+template <int ENC>
+__global__ void __launch_bounds__(64) cbc_encrypt_kernel(const uint8_t* __restrict__ work, const Segment* __restrict__ pieces,
+                                                         const EncEntry* __restrict__ entries, const uint32_t* __restrict__ list,
+                                                         uint32_t n, const DevKeys* __restrict__ keys,
+                                                         const AesTables* __restrict__ aes, const CamelliaTables* __restrict__ cam,
+                                                         uint8_t* __restrict__ out) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* s_tab = smem;
+    if (ENC == 1) { for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_tab[i] = aes->te0[i >> 5]; }
+    else { for (int i = threadIdx.x; i < 2048; i += blockDim.x) { s_tab[i] = (&cam->sp_hi[0][0])[i]; s_tab[2048 + i] = (&cam->sp_lo[0][0])[i]; } }
+    __syncthreads();
+    const TabView tv{s_tab, 32, (uint32_t)(threadIdx.x & 31)};
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const EncEntry& e = entries[list[i]];
+    if (e.status != ST_OK) return;
+    const DevKeys* k = keys + e.key_idx;
+    const Segment* sg = pieces + e.piece_begin;
+    const uint64_t clen = e.comp_len, nblk = clen / 16 + 1;
+    uint8_t* dst = out + e.out_off;
+    uint32_t prev[4] = {0, 0, 0, 0};
+    for (int q = 0; q < 16; q++) { prev[q >> 2] |= (uint32_t)e.iv[q] << (8 * (q & 3)); dst[q] = e.iv[q]; }
+    for (uint64_t bi = 0; bi < nblk; bi++) {
+        uint32_t c[4] = {0, 0, 0, 0};
+        if ((bi + 1) * 16 <= clen) load_stream16(work, sg, e.n_pieces, clen, bi * 16, c);
+        else {
+            const uint32_t have = (uint32_t)(clen - bi * 16), pad = 16 - have;
+            for (uint32_t q = 0; q < 16; q++) {
+                const uint32_t b = q < have ? load_stream1(work, sg, e.n_pieces, bi * 16 + q) : pad;
+                c[q >> 2] |= b << (8 * (q & 3));
+            }
+        }
+        c[0] ^= prev[0]; c[1] ^= prev[1]; c[2] ^= prev[2]; c[3] ^= prev[3];
+        if (ENC == 1) aes256_encrypt_block(c, k->aes_rk, tv);
+        else camellia256_crypt_block(c, k->cam_ek, s_tab, s_tab + 2048);
+        *reinterpret_cast<uint4*>(dst + 16 + bi * 16) = make_uint4(c[0], c[1], c[2], c[3]);
+        prev[0] = c[0]; prev[1] = c[1]; prev[2] = c[2]; prev[3] = c[3];
+    }
+}
+
+// FDAT-body CRC tiles come from the host with bound-based geometry: tile = bytes [rel, rel + cap) of entry
+// tl.span's output (span field reused as entry index until clipped).  Clip to the produced length.
+struct CrcTileSrc { uint64_t rel; uint32_t cap, entry, span; };
+__global__ void crc_clip_kernel(const CrcTileSrc* __restrict__ src, uint32_t n, const EncEntry* __restrict__ entries,
+                                CrcTile* __restrict__ tiles) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CrcTileSrc s = src[i];
+    const EncEntry& e = entries[s.entry];
+    const uint64_t end = e.status == ST_OK ? e.out_len : 0;
+    uint64_t len = s.rel < end ? end - s.rel : 0;
+    if (len > s.cap) len = s.cap;
+    CrcTile t;
+    t.begin = len ? e.out_off + s.rel : e.out_off;   // empty tiles stay inside the arena (16-byte aligned: no load at all)
+    t.len = (uint32_t)len;
+    t.span = s.span;
+    tiles[i] = t;
+}
+
+// host-side plan state (encode_host.cuh)
+struct EncodePlan;
+void destroy(EncodePlan* p);
+bool init_attributes();
+
+}  // namespace enc
+}  // namespace pna

@@ -169,3 +169,76 @@ extern "C" int hc_inflate(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t 
     static pna::inf::Tables t;
     return pna::inf::inflate_zlib(in, n, out, cap, out_len, &t);
 }
+
+// ---- encode: the PNA_HD bitstream writers driven by a plain greedy matcher (test-side stand-in for the
+// warp-synchronous matcher of kernels_encode.cuh); output must decode with libzstd / zlib (checked in Python)
+#include "../../portable-network-archive_b200/csrc/encode_core.cuh"
+static pna::enc::EncTables g_enc; static bool g_enc_init = false;
+static void greedy_segment(const uint8_t* d, uint32_t len, std::vector<pna::enc::Seq>& seqs, std::vector<uint8_t>& lits) {
+    using namespace pna::enc;
+    std::vector<int32_t> head(1 << 13, -1);
+    uint32_t p = 0, run = 0;
+    while (p < len) {
+        uint32_t best = 0, bo = 0;
+        if (p + 4 <= len) {
+            uint32_t v; memcpy(&v, d + p, 4);
+            uint32_t h = (v * 2654435761u) >> 19;
+            int32_t c = head[h];
+            head[h] = (int32_t)p;
+            if (c >= 0) {
+                uint32_t mx = len - p < MAX_MATCH ? len - p : MAX_MATCH, k = 0;
+                while (k < mx && d[c + k] == d[p + k]) k++;
+                if (k >= MIN_MATCH) { best = k; bo = p - (uint32_t)c; }
+            }
+        }
+        if (best) { seqs.push_back({bo, run | (best << 16)}); run = 0; p += best; }
+        else { lits.push_back(d[p]); run++; p++; }
+    }
+}
+extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, uint8_t* out) {
+    using namespace pna::enc;
+    if (!g_enc_init) { make_enc_tables(&g_enc); g_enc_init = true; }
+    uint64_t o = 0;
+    const uint64_t nseg = len ? (len + SEG - 1) / SEG : 0;
+    if (compression == 2) {
+        const uint8_t fh[6] = {0x28, 0xB5, 0x2F, 0xFD, 0x00, 0x38};
+        memcpy(out, fh, 6); o = 6;
+        if (nseg == 0) { zstd_block_header(1, 0, 0, out + o); o += 3; return o; }
+    } else {
+        out[0] = 0x78; out[1] = 0x9C; o = 2;
+        if (nseg == 0) { out[o++] = 0x03; out[o++] = 0x00; }
+    }
+    uint32_t a1 = 1, a2 = 0;
+    for (uint64_t i = 0; i < len; i++) { a1 = (a1 + in[i]) % 65521u; a2 = (a2 + a1) % 65521u; }
+    for (uint64_t s = 0; s < nseg; s++) {
+        const uint8_t* d = in + s * SEG;
+        const uint32_t n = (uint32_t)(len - s * SEG < SEG ? len - s * SEG : SEG);
+        const bool last = s + 1 == nseg;
+        std::vector<Seq> seqs; std::vector<uint8_t> lits;
+        greedy_segment(d, n, seqs, lits);
+        std::vector<uint8_t> tmp(2 * SEG + 64);
+        uint8_t* t4 = tmp.data() + ((4 - ((uintptr_t)tmp.data() & 3)) & 3);
+        if (compression == 2) {
+            uint32_t ssz = 1, soff = 0;
+            if (!seqs.empty()) { uint32_t r = zstd_write_sequences(g_enc, seqs.data(), (uint32_t)seqs.size(), t4, 2 * SEG); soff = r >> 24; ssz = r & 0xFFFFFF; }
+            else { t4[0] = 0; }
+            uint8_t lh[3]; uint32_t lhn = zstd_raw_lit_header((uint32_t)lits.size(), lh);
+            uint32_t csize = lhn + (uint32_t)lits.size() + ssz;
+            if (csize >= n) { zstd_block_header(last, 0, n, out + o); o += 3; memcpy(out + o, d, n); o += n; }
+            else {
+                zstd_block_header(last, 2, csize, out + o); o += 3;
+                memcpy(out + o, lh, lhn); o += lhn;
+                memcpy(out + o, lits.data(), lits.size()); o += lits.size();
+                memcpy(out + o, t4 + soff, ssz); o += ssz;
+            }
+        } else {
+            uint32_t sz = deflate_write_segment(seqs.data(), (uint32_t)seqs.size(), lits.data(), (uint32_t)lits.size(), last, t4);
+            if (sz >= n + 5) {   // stored block
+                out[o++] = last ? 1 : 0; out[o++] = (uint8_t)n; out[o++] = (uint8_t)(n >> 8); out[o++] = (uint8_t)~n; out[o++] = (uint8_t)(~n >> 8);
+                memcpy(out + o, d, n); o += n;
+            } else { memcpy(out + o, t4, sz); o += sz; }
+        }
+    }
+    if (compression != 2) { const uint32_t ad = (a2 << 16) | a1; out[o++] = ad >> 24; out[o++] = ad >> 16; out[o++] = ad >> 8; out[o++] = ad; }
+    return o;
+}

@@ -138,3 +138,20 @@ def test_inflate_core_corruption_and_truncation(hc, oracle):
     for cut in (0, 1, 2, 3, 10, len(c) // 2, len(c) - 5, len(c) - 1):   # flate2 zio::read: truncated -> short Ok
         st, o = _dec(hc.hc_inflate, c[:cut], len(d))
         assert st == 0 and o == oracle.decompress(1, c[:cut], len(d))
+
+
+@pytest.mark.parametrize("comp", [1, 2])
+def test_encode_writers_decode_with_reference_codecs(hc, oracle, comp):
+    """zstd block / deflate fixed-Huffman writers (encode_core.cuh): what they emit must decode, bit-exact, with the
+    codecs the reference links (libzstd, zlib)."""
+    hc.hc_encode.restype = C.c_uint64
+    hc.hc_encode.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p]
+    rnd = random.Random(comp)
+    cases = [b"", b"a", b"abcd" * 3, bytes(70000), os.urandom(40000), corpus.make_file(7, 200000), corpus.make_file(8, 32768),
+             corpus.make_file(9, 32769), b"xyz" * 30000, bytes(rnd.randrange(4) for _ in range(100000))]
+    for d in cases:
+        out = C.create_string_buffer(len(d) + len(d) // 4 + 256)
+        n = hc.hc_encode(comp, d, len(d), out)
+        assert oracle.decompress(comp, out.raw[:n]) == d, (comp, len(d))
+        if len(d) > 50000 and d[:4] != os.urandom(4) and len(set(d[:1000])) < 200:
+            assert n < len(d)
