@@ -74,6 +74,27 @@ def make_shard(rank: int, entries: int, threads: int):
     return files, streams, key
 
 
+def make_shard_encode_only(files, key, threads: int):
+    """The reference's create dataflow on the host (oracle): `threads` workers, one entry each."""
+    import pna_oracle as O
+    L = O.lib()
+    n = len(files)
+    jobs = (O.EncJob * n)()
+    outs = []
+    for j, f in enumerate(files):
+        cap = L.pna_oracle_encode_bound(2, len(f))
+        o = C.create_string_buffer(cap)
+        outs.append(o)
+        jobs[j].plain = C.cast(C.c_char_p(f), C.c_void_p)
+        jobs[j].len = len(f)
+        jobs[j].compression, jobs[j].encryption, jobs[j].cipher_mode, jobs[j].level = 2, 1, 1, 3
+        C.memmove(jobs[j].key, key, 32)
+        jobs[j].out = C.cast(o, C.c_void_p)
+        jobs[j].cap = cap
+    L.pna_oracle_encode_batch_mt(jobs, n, threads, None)
+    assert all(jobs[j].status == 0 for j in range(n))
+
+
 def build_archive(streams, sizes, phsf: str, into=None):
     """PNA container bytes (signature, AHED, entries, AEND); chunk CRCs via zlib (input preparation)."""
     parts = [b"\x89PNA\r\n\x1a\n"]
@@ -172,6 +193,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--entries", type=int, default=1024, help="4 MiB files per GPU (cfg2: 8192 over 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--workers", type=int, default=2, help="host worker threads / contexts of the end-to-end path")
+    ap.add_argument("--group-mib", type=int, default=4096, help="compressed MiB per pipelined entry group (end-to-end path)")
+    ap.add_argument("--create", type=int, default=1, help="also measure the create path (GPU zstd + AES-CTR + CRC) on the same files")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -273,37 +297,115 @@ def main():
     del outs
     plan.close()
 
-    # ---- end to end through the C ABI with host buffers (pinned): plan_create (H2D) + run + fetch (D2H)
-    out_pinned = ctx.pinned(U)
-    bufs = (pna._ffi.Buf * E)()
-    pos = 0
-    for i, n in enumerate(sizes):
-        bufs[i].ptr = out_pinned.ctypes.data + pos
-        bufs[i].cap = n
-        pos += n
-    stv = (C.c_int32 * E)()
+    # ---- end to end through the reference-facing host API (C++ pna::Archive over the C ABI) with HOST buffers:
+    # index pass over the pinned archive bytes, then entry groups pipelined over `--workers` contexts (H2D + chunk CRC
+    # check + decrypt + decode + D2H into pinned output), everything inside the timed region
+    host = importlib.import_module("portable-network-archive_b200._host")
+    out_pinned = ctx.pinned(U + 16 * E + 64)
     e2e_times = []
     for it in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
-        p2, _ = archive.extract_plan(ro)
-        p2.run()
-        p2.fetch_into(bufs, stv)
+        ha = host.HostArchive(archive_buf)
+        ha.set_key(opts.phsf, key)
+        _, offs, stv = ha.extract_files(out=out_pinned, device=local_rank, workers=args.workers, group_bytes=args.group_mib << 20, verify=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        p2.close()
+        ha.close()
         if it > 0:
             e2e_times.append(dt)
     if e2e_times:
-        assert list(stv) == [0] * E and out_pinned[:sizes[0]].tobytes() == files[0]
+        assert stv == [0] * E
+        for k in range(0, E, max(1, E // 16)):
+            assert out_pinned[int(offs[k]):int(offs[k]) + sizes[k]].tobytes() == files[k], "e2e output differs from the source file"
     e2e_s = max_over_ranks(statistics.median(e2e_times)) if e2e_times else float('nan')
+
+    # ---- create path (BASELINE config 4 shape: GPU zstd encode + AES-256-CTR + FDAT CRC-32) on the same files
+    create = None
+    if args.create:
+        import pna_oracle as O
+        rng = np.random.Generator(np.random.PCG64(99 + rank))
+        plain_pinned = ctx.pinned(U)
+        pos = 0
+        views = []
+        for f in files:
+            plain_pinned[pos:pos + len(f)] = np.frombuffer(f, dtype=np.uint8)
+            views.append(plain_pinned[pos:pos + len(f)])
+            pos += len(f)
+        ents = [{"plain": v, "compression": 2, "level": 3, "encryption": 1, "cipher_mode": 1, "key": key, "iv": rng.bytes(16),
+                 "max_chunk_size": 0} for v in views]
+        eplan = ctx.encode_plan(ents)
+        for _ in range(max(args.warmup, 1)):
+            eplan.run()
+        torch.cuda.synchronize()
+        l1 = ctx.launch_count
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(args.steps):
+            eplan.run()
+        c1.record(stream)
+        barrier()
+        c_ms = max_over_ranks(c0.elapsed_time(c1) / args.steps)
+        c_launches = ctx.launch_count - l1
+        c_stage = eplan.stage_ms()
+        outp = ctx.pinned(sum(eplan.bounds))
+        streams_gpu, crcs_gpu, cst = eplan.fetch(into=outp)
+        assert cst == [0] * E
+        c_gpu = sum(int(s.size) for s in streams_gpu)
+        for k in range(0, E, max(1, E // 8)):   # the reference pipeline must read what we wrote, CRCs must match
+            s = streams_gpu[k].tobytes()
+            assert O.decode_stream(s, 2, 1, 1, key, None) == files[k], "GPU-created stream is not reference-readable"
+            assert int(crcs_gpu[k][0]) == O.chunk_crc(b"FDAT", s[16:])
+        eplan.close()
+        ce2e = []
+        names = [f"corpus/{i:07d}.bin" for i in range(E)]
+        arch_out = ctx.pinned(int(U * 1.02) + (64 << 20))
+        ivs = rng.bytes(16 * E)
+        for it in range(args.e2e_steps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            blob = host.create_archive(list(zip(names, views)), compression=2, level=3, encryption=1, cipher_mode=1, key=key, phsf=opts.phsf,
+                                       ivs=ivs, max_chunk_size=0, device=local_rank, workers=args.workers, group_bytes=1024 << 20,
+                                       out=arch_out)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it > 0:
+                ce2e.append(dt)
+        if ce2e:   # the created archive must extract bit-exactly with the reference reader (oracle) -- sample -- and with ours
+            got = O.extract_all(blob[:min(blob.size, 64 << 20)].tobytes() if False else blob.tobytes(), PASSWORD, _keys={opts.phsf: key}) if E <= 64 else None
+            hb = host.HostArchive(blob)
+            hb.set_key(opts.phsf, key)
+            o2, of2, st2 = hb.extract_files(device=local_rank, workers=args.workers)
+            assert st2 == [0] * E
+            for k in range(0, E, max(1, E // 16)):
+                assert o2[int(of2[k]):int(of2[k]) + sizes[k]].tobytes() == files[k]
+            if got is not None:
+                assert [d for _, d in got] == files
+            del o2
+            hb.close()
+        ce2e_s = max_over_ranks(statistics.median(ce2e)) if ce2e else float("nan")
+        create = {"metric": "create_uncompressed_GBps", "value": world * U / (c_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": c_ms,
+                  "e2e": {"value": world * U / ce2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U), "d2h_bytes_per_step": int(c_gpu),
+                          "ms_per_step": ce2e_s * 1e3},
+                  "codec": "gpu zstd (32 KiB blocks, predefined FSE, raw literals) + aes-256-ctr + crc32", "stage_ms": c_stage,
+                  "gpu_launches": c_launches, "ratio": U / c_gpu, "c_gpu_over_c_ref": c_gpu / Cbytes,
+                  "checked": "sampled streams decoded by the oracle (libzstd + OpenSSL) == source files; FDAT CRCs == zlib crc32"}
+        del outp, plain_pinned
 
     # ---- CPU baseline on this box's cores (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
+    cpu_create = None
     if rank == 0 and world == 1:
         sample = min(E, 256)
         cpu_decode(streams[:sample], sizes[:sample], key, ncpu)
         dt, _ = cpu_decode(streams[:sample], sizes[:sample], key, ncpu, repeat=3)
+        if args.create:
+            t0 = time.perf_counter()
+            make_shard_encode_only(files[:sample], key, ncpu)
+            dtc = time.perf_counter() - t0
+            cpu_create = {"value": sum(sizes[:sample]) / dtc / 1e9, "unit": "GB/s", "cores": ncpu, "kind": "port",
+                          "sample": f"{sample} x 4 MiB entries, oracle encode (libzstd level 3 streaming + OpenSSL AES-256-CTR), {ncpu} threads"}
         cpu = {"value": sum(sizes[:sample]) / dt / 1e9, "unit": "GB/s", "cores": ncpu, "kind": "port",
                "sample": f"{sample} x 4 MiB entries x3 passes (oracle: libzstd + OpenSSL AES-NI + zlib crc32; 1 CRC thread + "
                          f"{ncpu} worker threads, reference extract dataflow)"}
@@ -337,10 +439,14 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": world * U / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(archive_buf.size),
                     "d2h_bytes_per_step": int(U), "ms_per_step": e2e_s * 1e3,
-                    "path": "pna_cuda_decode_plan_create_crc + run + fetch with pinned host buffers, host clock, synchronised"},
+                    "path": f"pna::Archive::read_header_from_slice + extract_files (C++ host layer, {args.workers} contexts, {args.group_mib} MiB groups): index pass, H2D, chunk CRC check, decrypt, decode, D2H to pinned buffers; host clock"},
             "roofline": roof}
     if cpu:
         line["cpu_baseline"] = cpu
+    if create:
+        if cpu_create:
+            create["cpu_baseline"] = cpu_create
+        line["create"] = create
     print(json.dumps(line))
 
 

@@ -131,8 +131,13 @@ int pna_cuda_encode_batch(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n
                           uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status);
 int pna_cuda_encode_plan_create(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_plan** plan);
 int pna_cuda_encode_plan_run(pna_plan* plan);
+/* produced stream length of every entry (waits for the run): lets the caller place the streams before fetching them */
+int pna_cuda_encode_plan_lengths(pna_plan* plan, uint64_t* out_len, int32_t* status);
 int pna_cuda_encode_plan_fetch(pna_plan* plan, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out,
                                int32_t* status);
+
+/* stage names of an encode plan for pna_cuda_plan_stage_ms (first 5 entries: lz_match, block_write, layout, cipher, crc) */
+const char* pna_cuda_encode_stage_name(uint32_t stage);
 
 /* ---- block-cipher primitives (test hooks for the KATs in lib/src/cipher.rs:256-292) ---- */
 /* ECB over n 16-byte blocks with the same key schedule the stream kernels use. */

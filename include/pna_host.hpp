@@ -1,0 +1,154 @@
+// pna_host.hpp -- C++ host layer above the C ABI (include/pna_cuda.h): the reference's container logic for the
+// data-chunk path, mirroring `libpna` names and behaviour (reference = ChanTsune/Portable-Network-Archive v0.37.0,
+// Rust; this image has no Rust toolchain, so the host side is C++ as the reference is compiled code).
+//
+//   pna::Archive::read_header_from_slice   lib/src/archive/read/slice.rs:17  (signature lib/src/format/signature.rs:6,
+//                                          AHED lib/src/archive/header.rs:27-56, chunk walk lib/src/bytes.rs:39-111)
+//   pna::NormalEntry / pna::SolidEntry     lib/src/entry.rs:457-483, 665-737, 757-886  (FHED/SHED bytes
+//                                          lib/src/entry/header.rs:123-162,274-296)
+//   pna::ReadOptions (key cache)           lib/src/entry/options.rs:79-112,1344-1390   (KDF itself is host work supplied
+//                                          by the caller, lib/src/hash.rs:45-85)
+//   pna::Archive::extract_files            the CLI extract loop cli/src/command/extract.rs:868-1019 folded into GPU
+//                                          batches: chunk CRC check + decrypt + decompress via pna_cuda_decode_plan_*,
+//                                          several pna_ctx (one per worker thread) so that H2D, kernels and D2H of
+//                                          consecutive entry groups overlap
+//   pna::FileEntryBuilder / Archive::create   lib/src/entry/builder/file.rs:41-140, lib/src/entry.rs:895-912,
+//                                          lib/src/archive/write.rs:92,368,545, lib/src/io.rs:183-197
+//
+// No entry byte is processed on the CPU here: the host only walks 12-byte chunk frames, groups them and moves bytes.
+#ifndef PNA_HOST_HPP
+#define PNA_HOST_HPP
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+#include <array>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pna_cuda.h"
+
+namespace pna {
+
+struct Error : std::runtime_error {   // io::Error mirror: kind = PNA_E_* (== io::ErrorKind class)
+    int kind;
+    Error(int k, const std::string& m) : std::runtime_error(m), kind(k) {}
+};
+
+struct RawChunk {        // lib/src/chunk.rs RawChunk, data borrowed from the archive slice
+    char ty[4];
+    uint64_t off;        // offset of the data field
+    uint32_t len;
+    uint32_t crc;        // stored CRC (big endian on the wire)
+};
+
+enum class DataKind : uint8_t { File = 0, Directory = 1, SymbolicLink = 2, HardLink = 3 };
+
+struct EntryInfo {       // NormalEntry (kind 0) or SolidEntry (kind 1) as the index pass sees it
+    uint8_t kind = 0, data_kind = 0, compression = 0, encryption = 0, cipher_mode = 0;
+    std::string name, phsf;
+    bool has_phsf = false;
+    uint64_t raw_file_size = UINT64_MAX;     // fSIZ
+    uint64_t compressed_size = 0;
+    std::vector<pna_span> bodies;            // FDAT / SDAT bodies, in order
+    uint32_t chunk_begin = 0, chunk_end = 0; // chunk index range [begin, end) incl. FHED..FEND
+};
+
+class ReadOptions {      // options.rs:1344; keys: PHSF string -> derived 32-byte key (KeyCache, options.rs:79)
+public:
+    bool has_password = false;
+    std::map<std::string, std::array<uint8_t, 32>> keys;
+    void set_key(const std::string& phsf, const uint8_t key[32]) { has_password = true; std::array<uint8_t, 32> k; for (int i = 0; i < 32; i++) k[i] = key[i]; keys[phsf] = k; }
+};
+
+struct FileOut {         // one FILE entry to extract: where it lives and where its bytes go
+    std::string name;
+    uint64_t size = UINT64_MAX;   // decoded size when known (fSIZ or sizing pass)
+    int32_t status = 0;
+};
+
+class Archive {
+public:
+    static Archive read_header_from_slice(const uint8_t* buf, size_t len);
+    const std::vector<RawChunk>& chunks() const { return chunks_; }
+    const std::vector<EntryInfo>& entries() const { return entries_; }
+    uint32_t archive_number() const { return archive_number_; }
+
+    // Decodes solid entries (their inner archives stay resident in host memory), lists every FILE entry in archive order
+    // and learns the decoded size of the ones that carry no fSIZ (sizing pass on the GPU).
+    void prepare(const ReadOptions& opt, int device);
+    const std::vector<FileOut>& files() const { return files_; }
+    // Extract all FILE entries into out[offsets[i] .. offsets[i+1]) (offsets from files()[i].size, caller-computed).
+    // verify: chunk CRCs of the whole archive are checked on the GPU, fused with the decode batches.
+    void extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
+                       uint64_t group_bytes, bool verify);
+
+private:
+    struct FileRef { uint32_t owner; uint32_t entry; };   // owner: 0 = top-level archive, k+1 = inner archive of solid k
+    struct Inner { std::vector<uint8_t> bytes; std::vector<RawChunk> chunks; std::vector<EntryInfo> entries; };
+    const uint8_t* buf_ = nullptr;
+    size_t len_ = 0;
+    uint32_t archive_number_ = 0;
+    std::vector<RawChunk> chunks_;
+    std::vector<EntryInfo> entries_;
+    std::vector<Inner> inner_;
+    std::vector<FileRef> refs_;
+    std::vector<FileOut> files_;
+    bool prepared_ = false;
+};
+
+struct WriteOptions {    // options.rs:1035
+    uint8_t compression = 0, encryption = 0, cipher_mode = 1;
+    int32_t level = -1;
+    uint8_t key[32] = {0};
+    std::string phsf;    // recorded in the PHSF chunk when encryption != 0
+};
+struct FileEntryBuilder {   // builder/file.rs:41: plaintext is borrowed until Archive::create returns
+    std::string name;
+    pna_span data{nullptr, 0};
+    uint8_t iv[16] = {0};   // caller-drawn (entry/write.rs:108-111)
+};
+// Archive::write_header + add_entry per file + finalize, with one GPU encode batch per worker group.
+std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
+                                    int device, int workers, uint64_t group_bytes);
+// Same, written straight into a caller buffer (pinned memory makes the stream copies true DMA); returns the archive length.
+uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
+                             int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap);
+
+}  // namespace pna
+extern "C" {
+#endif
+
+/* flat C view for bindings (tests/bench use it through ctypes) */
+typedef struct pnah_archive pnah_archive;
+typedef struct {
+    uint8_t kind, data_kind, compression, encryption, cipher_mode;
+    uint32_t n_bodies;
+    uint64_t compressed_size, raw_file_size;
+    const char* name;
+    const char* phsf; /* NULL when absent */
+} pnah_entry_info;
+int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, uint64_t errcap);
+void pnah_close(pnah_archive* a);
+uint32_t pnah_entry_count(pnah_archive* a);
+int pnah_entry_get(pnah_archive* a, uint32_t i, pnah_entry_info* info);
+uint32_t pnah_chunk_count(pnah_archive* a);
+int pnah_set_key(pnah_archive* a, const char* phsf, const uint8_t key[32]);
+int pnah_prepare(pnah_archive* a, int device, char* err, uint64_t errcap);
+uint32_t pnah_file_count(pnah_archive* a);
+int pnah_file_get(pnah_archive* a, uint32_t i, const char** name, uint64_t* size);
+int pnah_extract_files(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
+                       uint64_t group_bytes, int verify, char* err, uint64_t errcap);
+int pnah_create(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs,
+                uint8_t compression, int32_t level, uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf,
+                uint32_t max_chunk_size, int device, int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap, uint64_t* out_len,
+                char* err, uint64_t errcap);
+uint64_t pnah_create_bound(uint32_t n, const char* const* names, const uint64_t* lens, uint8_t compression, uint8_t encryption,
+                           const char* phsf, uint32_t max_chunk_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

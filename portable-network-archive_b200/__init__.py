@@ -91,6 +91,58 @@ class DecodePlan:
             pass
 
 
+class EncodePlan:
+    """A create batch resident in HBM (pna_plan, encode kind)."""
+
+    def __init__(self, ctx, handle, n, bounds, ncrc):
+        self.ctx, self.h, self.n, self.bounds, self.ncrc = ctx, handle, n, bounds, ncrc
+
+    def run(self):
+        self.ctx._ck(self.ctx.L.pna_cuda_encode_plan_run(self.h), "encode_plan_run")
+
+    def fetch(self, into=None):
+        """Returns (streams, crc lists, statuses).  `into`: optional pinned uint8 array that receives the streams."""
+        n = self.n
+        bufs = (_ffi.Buf * max(n, 1))()
+        if into is None:
+            outs = [np.empty(b, dtype=np.uint8) for b in self.bounds]
+        else:
+            outs, pos = [], 0
+            for b in self.bounds:
+                outs.append(into[pos:pos + b])
+                pos += b
+        for i, o in enumerate(outs):
+            bufs[i].ptr = o.ctypes.data
+            bufs[i].cap = self.bounds[i]
+        crcs = np.zeros(sum(self.ncrc) + 1, dtype=np.uint32)
+        cnt = np.zeros(max(n, 1), dtype=np.uint32)
+        st = (C.c_int32 * max(n, 1))()
+        self.ctx._ck(self.ctx.L.pna_cuda_encode_plan_fetch(self.h, bufs, crcs.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                         cnt.ctypes.data_as(C.POINTER(C.c_uint32)), st), "encode_plan_fetch")
+        res, crc_lists, pos = [], [], 0
+        for i in range(n):
+            res.append(outs[i][:bufs[i].len])
+            crc_lists.append(crcs[pos:pos + int(cnt[i])].copy())
+            pos += int(cnt[i])
+        return res, crc_lists, list(st)[:n]
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * 16)()
+        n = self.ctx.L.pna_cuda_plan_stage_ms(self.h, ms, 16)
+        return {self.ctx.L.pna_cuda_encode_stage_name(i).decode(): float(ms[i]) for i in range(min(max(n, 0), 5))}
+
+    def close(self):
+        if self.h:
+            self.ctx.L.pna_cuda_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU (pna_ctx).  Entries shard across GPUs by entry: use one Context per device/rank."""
 
@@ -226,13 +278,9 @@ class Context:
         return [o[:bufs[i].len] if st[i] == OK else o[:0] for i, o in enumerate(outs)], list(st), [b.len for b in bufs]
 
     # ---- seam 3
-    def encode_batch(self, entries):
-        """entries: dicts {plain, compression, level, encryption, cipher_mode, key, iv, max_chunk_size}.
-        Returns (streams, fdat_crcs per entry, statuses)."""
+    def _enc_descs(self, entries):
         n = len(entries)
-        if n == 0:
-            return [], [], []
-        descs = (_ffi.EncodeDesc * n)()
+        descs = (_ffi.EncodeDesc * max(n, 1))()
         keep = []
         for i, e in enumerate(entries):
             p = _as_u8(e["plain"])
@@ -247,6 +295,24 @@ class Context:
             C.memmove(d.key, e.get("key") or bytes(32), 32)
             C.memmove(d.iv, e.get("iv") or bytes(16), 16)
             d.max_chunk_size = e.get("max_chunk_size", 0)
+        return descs, keep
+
+    def encode_plan(self, entries) -> "EncodePlan":
+        """Upload a create batch once (pna_plan); run() launches match -> block writers -> layout -> cipher -> CRC."""
+        descs, keep = self._enc_descs(entries)
+        h = C.c_void_p()
+        self._ck(self.L.pna_cuda_encode_plan_create(self.h, descs, len(entries), C.byref(h)), "encode_plan_create")
+        bounds = [int(self.L.pna_cuda_encode_bound(C.byref(descs[i]))) for i in range(len(entries))]
+        ncrc = [int(self.L.pna_cuda_encode_crc_count(C.byref(descs[i]))) for i in range(len(entries))]
+        return EncodePlan(self, h, len(entries), bounds, ncrc)
+
+    def encode_batch(self, entries):
+        """entries: dicts {plain, compression, level, encryption, cipher_mode, key, iv, max_chunk_size}.
+        Returns (streams, fdat_crcs per entry, statuses)."""
+        n = len(entries)
+        if n == 0:
+            return [], [], []
+        descs, keep = self._enc_descs(entries)
         bounds = [int(self.L.pna_cuda_encode_bound(C.byref(descs[i]))) for i in range(n)]
         ncrc = [int(self.L.pna_cuda_encode_crc_count(C.byref(descs[i]))) for i in range(n)]
         outs = [np.empty(b, dtype=np.uint8) for b in bounds]

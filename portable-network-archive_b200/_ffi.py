@@ -17,8 +17,8 @@ EXPORTS = [
     "pna_cuda_init", "pna_cuda_destroy", "pna_cuda_strerror", "pna_cuda_last_error", "pna_cuda_host_alloc",
     "pna_cuda_host_free", "pna_cuda_stream", "pna_cuda_launch_count", "pna_cuda_crc32", "pna_cuda_crc32_image",
     "pna_cuda_decode_batch", "pna_cuda_decode_plan_create", "pna_cuda_decode_plan_create_crc", "pna_cuda_plan_crc_results", "pna_cuda_decode_plan_run", "pna_cuda_decode_plan_fetch",
-    "pna_cuda_plan_stats", "pna_cuda_plan_counts", "pna_cuda_plan_stage_ms", "pna_cuda_stage_name", "pna_cuda_plan_destroy", "pna_cuda_encode_bound", "pna_cuda_encode_crc_count",
-    "pna_cuda_encode_batch", "pna_cuda_encode_plan_create", "pna_cuda_encode_plan_run", "pna_cuda_encode_plan_fetch",
+    "pna_cuda_plan_stats", "pna_cuda_plan_counts", "pna_cuda_plan_stage_ms", "pna_cuda_stage_name", "pna_cuda_encode_stage_name", "pna_cuda_plan_destroy", "pna_cuda_encode_bound", "pna_cuda_encode_crc_count",
+    "pna_cuda_encode_batch", "pna_cuda_encode_plan_create", "pna_cuda_encode_plan_run", "pna_cuda_encode_plan_lengths", "pna_cuda_encode_plan_fetch",
     "pna_cuda_ecb",
 ]
 
@@ -85,6 +85,8 @@ def lib():
     L.pna_cuda_decode_plan_run.argtypes = [vp]
     L.pna_cuda_decode_plan_fetch.argtypes = [vp, C.POINTER(Buf), i32p]
     L.pna_cuda_plan_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.pna_cuda_encode_stage_name.restype = C.c_char_p
+    L.pna_cuda_encode_stage_name.argtypes = [u32]
     L.pna_cuda_plan_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.pna_cuda_plan_stage_ms.argtypes = [vp, C.POINTER(C.c_float), u32]
     L.pna_cuda_stage_name.argtypes = [u32]
@@ -98,6 +100,7 @@ def lib():
     L.pna_cuda_encode_batch.argtypes = [vp, C.POINTER(EncodeDesc), u32, C.POINTER(Buf), C.POINTER(u32), C.POINTER(u32), i32p]
     L.pna_cuda_encode_plan_create.argtypes = [vp, C.POINTER(EncodeDesc), u32, C.POINTER(vp)]
     L.pna_cuda_encode_plan_run.argtypes = [vp]
+    L.pna_cuda_encode_plan_lengths.argtypes = [vp, C.POINTER(u64), i32p]
     L.pna_cuda_encode_plan_fetch.argtypes = [vp, C.POINTER(Buf), C.POINTER(u32), C.POINTER(u32), i32p]
     L.pna_cuda_ecb.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, vp, u64, vp]
     _lib = L

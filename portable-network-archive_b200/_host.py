@@ -1,0 +1,172 @@
+"""ctypes binding of libpna_host.so -- the C++ host layer (include/pna_host.hpp) above the C ABI: index pass, entry
+grouping, pipelined multi-context extract, archive writer.  KDF stays here in Python (host work in the reference too)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _ffi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpna_host.so")
+EXPORTS = ["pnah_open", "pnah_close", "pnah_entry_count", "pnah_entry_get", "pnah_chunk_count", "pnah_set_key", "pnah_prepare",
+           "pnah_file_count", "pnah_file_get", "pnah_extract_files", "pnah_create", "pnah_create_bound"]
+
+
+class EntryInfo(C.Structure):
+    _fields_ = [("kind", C.c_uint8), ("data_kind", C.c_uint8), ("compression", C.c_uint8), ("encryption", C.c_uint8),
+                ("cipher_mode", C.c_uint8), ("n_bodies", C.c_uint32), ("compressed_size", C.c_uint64),
+                ("raw_file_size", C.c_uint64), ("name", C.c_char_p), ("phsf", C.c_char_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _ffi.lib()   # libpna_cuda.so first (rpath $ORIGIN resolves it as well)
+        L = C.CDLL(LIB_PATH)
+        vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+        L.pnah_open.argtypes = [vp, u64, C.POINTER(vp), C.c_char_p, u64]
+        L.pnah_close.argtypes = [vp]
+        L.pnah_close.restype = None
+        L.pnah_entry_count.argtypes = [vp]
+        L.pnah_entry_count.restype = u32
+        L.pnah_chunk_count.argtypes = [vp]
+        L.pnah_chunk_count.restype = u32
+        L.pnah_entry_get.argtypes = [vp, u32, C.POINTER(EntryInfo)]
+        L.pnah_set_key.argtypes = [vp, C.c_char_p, C.c_char_p]
+        L.pnah_prepare.argtypes = [vp, C.c_int, C.c_char_p, u64]
+        L.pnah_file_count.argtypes = [vp]
+        L.pnah_file_count.restype = u32
+        L.pnah_file_get.argtypes = [vp, u32, C.POINTER(C.c_char_p), C.POINTER(u64)]
+        L.pnah_extract_files.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(C.c_int32), C.c_int, C.c_int, u64, C.c_int, C.c_char_p, u64]
+        L.pnah_create.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(u64), C.c_char_p, C.c_uint8, C.c_int32,
+                                  C.c_uint8, C.c_uint8, C.c_char_p, C.c_char_p, u32, C.c_int, C.c_int, u64, vp, u64, C.POINTER(u64),
+                                  C.c_char_p, u64]
+        L.pnah_create_bound.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(u64), C.c_uint8, C.c_uint8, C.c_char_p, u32]
+        L.pnah_create_bound.restype = u64
+        _lib = L
+    return _lib
+
+
+class HostError(Exception):
+    def __init__(self, kind, msg):
+        super().__init__(msg)
+        self.kind = kind
+
+
+class HostArchive:
+    """pna::Archive (C++): read_header_from_slice + batched, pipelined extract of every FILE entry."""
+
+    def __init__(self, data):
+        self.L = lib()
+        self.buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = self.L.pnah_open(self.buf.ctypes.data, self.buf.size, C.byref(h), err, 512)
+        if rc:
+            raise HostError(rc, err.value.decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pnah_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_chunks(self):
+        return int(self.L.pnah_chunk_count(self.h))
+
+    def entries(self):
+        out = []
+        for i in range(self.L.pnah_entry_count(self.h)):
+            e = EntryInfo()
+            self.L.pnah_entry_get(self.h, i, C.byref(e))
+            out.append({"kind": e.kind, "data_kind": e.data_kind, "compression": e.compression, "encryption": e.encryption,
+                        "cipher_mode": e.cipher_mode, "n_bodies": e.n_bodies, "compressed_size": e.compressed_size,
+                        "raw_file_size": None if e.raw_file_size == _ffi.UINT64_MAX else e.raw_file_size,
+                        "name": e.name.decode() if e.name else "", "phsf": e.phsf.decode() if e.phsf else None})
+        return out
+
+    def set_password(self, password: bytes, key_cache: dict | None = None):
+        """ReadOptions::with_password: derive one key per distinct PHSF (KDF = host work, lib/src/hash.rs:45-85)."""
+        from .archive import derive_key
+        cache = key_cache if key_cache is not None else {}
+        for e in self.entries():
+            if e["phsf"] and e["phsf"] not in cache:
+                cache[e["phsf"]] = derive_key(e["phsf"], password)
+        for phsf, key in cache.items():
+            self.L.pnah_set_key(self.h, phsf.encode(), key)
+
+    def set_key(self, phsf: str, key: bytes):
+        self.L.pnah_set_key(self.h, phsf.encode(), key)
+
+    def prepare(self, device=0):
+        err = C.create_string_buffer(512)
+        rc = self.L.pnah_prepare(self.h, device, err, 512)
+        if rc:
+            raise HostError(rc, err.value.decode())
+
+    def files(self):
+        out = []
+        for i in range(self.L.pnah_file_count(self.h)):
+            name, size = C.c_char_p(), C.c_uint64()
+            st = self.L.pnah_file_get(self.h, i, C.byref(name), C.byref(size))
+            out.append((name.value.decode(), int(size.value), st))
+        return out
+
+    def extract_files(self, out: np.ndarray | None = None, device=0, workers=3, group_bytes=256 << 20, verify=True):
+        """Returns (out buffer, offsets, statuses).  `out`: optional (pinned) uint8 array of sum(sizes) bytes."""
+        self.prepare(device)
+        files = self.files()
+        offs = np.zeros(len(files) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([(s + 15) // 16 * 16 for _, s, _ in files], dtype=np.uint64)
+        if out is None:
+            out = np.empty(int(offs[-1]) + 16, dtype=np.uint8)
+        st = (C.c_int32 * max(len(files), 1))()
+        err = C.create_string_buffer(512)
+        rc = self.L.pnah_extract_files(self.h, out.ctypes.data, offs.ctypes.data_as(C.POINTER(C.c_uint64)), st, device, workers,
+                                       group_bytes, int(verify), err, 512)
+        if rc:
+            raise HostError(rc, err.value.decode())
+        return out, offs, list(st)[:len(files)]
+
+    def read_all(self, **kw):
+        out, offs, st = self.extract_files(**kw)
+        res = []
+        for i, (name, size, _) in enumerate(self.files()):
+            res.append((name, st[i], out[int(offs[i]):int(offs[i]) + size].tobytes() if st[i] == 0 else None))
+        return res
+
+
+def create_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, key=None, phsf=None, ivs=None, max_chunk_size=0,
+                   device=0, workers=3, group_bytes=256 << 20, out=None):
+    """files: list of (name, bytes-like).  Returns the archive bytes (numpy view of `out` when given)."""
+    L = lib()
+    n = len(files)
+    arrs = [f[1] if isinstance(f[1], np.ndarray) else np.frombuffer(f[1], dtype=np.uint8) for f in files]
+    names = (C.c_char_p * max(n, 1))(*[f[0].encode() for f in files])
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+    lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrs])
+    if ivs is None and encryption:
+        ivs = os.urandom(16 * n)
+    bound = int(L.pnah_create_bound(n, names, lens, compression, encryption, (phsf or "").encode(), max_chunk_size))
+    if out is None:
+        out = np.empty(bound, dtype=np.uint8)
+    olen = C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    rc = L.pnah_create(n, names, ptrs, lens, ivs, compression, level, encryption, cipher_mode, key or bytes(32), (phsf or "").encode(),
+                       max_chunk_size, device, workers, group_bytes, out.ctypes.data, out.size, C.byref(olen), err, 512)
+    if rc:
+        raise HostError(rc, err.value.decode())
+    return out[:olen.value]

@@ -217,17 +217,26 @@ static int encode_launch_all(pna_plan* P) {
     EncodePlan* E = P->enc;
     const uint64_t l0 = ctx->launches;
     const uint32_t n = P->n, nsegs = (uint32_t)E->h_segs.size();
+    if (!P->ev_ready) {
+        for (auto& e : P->ev) CK(cudaEventCreate(&e));
+        P->ev_ready = true;
+    }
     CK(cudaMemcpyAsync(E->d_entries.p, E->d_entries_init.p, n * sizeof(EncEntry), cudaMemcpyDeviceToDevice, ctx->stream));
+    STAGE(0);
     if (nsegs) {
         enc::lz_match_kernel<<<(nsegs + enc::ENC_WARPS - 1) / enc::ENC_WARPS, 32 * enc::ENC_WARPS, enc::MATCH_SMEM_BYTES, ctx->stream>>>(
             E->d_work.p, E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p);
         LAUNCHED();
+        STAGE(1);
         enc::enc_block_kernel<<<(nsegs + 127) / 128, 128, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p,
                                                                            E->d_entries.p);
         LAUNCHED();
     }
+    else STAGE(1);
+    STAGE(2);
     enc::enc_layout_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, E->d_entries.p, n, E->d_pieces.p);
     LAUNCHED();
+    STAGE(3);
     const int aes_smem = 256 * 32 * 4, cam_smem = 2 * 2048 * 4;
     for (int v = 0; v < 3; v++) {
         const uint32_t nt = (uint32_t)E->h_tiles[v].size();
@@ -249,6 +258,7 @@ static int encode_launch_all(pna_plan* P) {
 #undef ARGS
         LAUNCHED();
     }
+    STAGE(4);
     const uint32_t nt = (uint32_t)E->h_crc_src.size(), nb = (uint32_t)E->h_crc_first.size();
     if (nt) {
         enc::crc_clip_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(E->d_crc_src.p, nt, E->d_entries.p, E->d_crc_tiles.p);
@@ -260,9 +270,16 @@ static int encode_launch_all(pna_plan* P) {
                                                                      E->d_crc_val.p, E->fdat_init);
         LAUNCHED();
     }
+    STAGE(5);
+    for (int k = 6; k <= PNA_N_STAGES; k++) STAGE(k);
+    P->ev_recorded = true;
     P->launches_per_run = ctx->launches - l0;
     P->prepared = true;
     return PNA_OK;
+}
+extern "C" const char* pna_cuda_encode_stage_name(uint32_t i) {
+    static const char* const names[5] = {"lz_match", "block_write", "layout", "cipher", "crc"};
+    return i < 5 ? names[i] : "";
 }
 
 extern "C" int pna_cuda_encode_plan_create(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_plan** plan) {
@@ -283,6 +300,19 @@ extern "C" int pna_cuda_encode_plan_run(pna_plan* P) {
     CK(cudaSetDevice(ctx->device));
     if (P->n == 0) return PNA_OK;
     return encode_launch_all(P);
+}
+extern "C" int pna_cuda_encode_plan_lengths(pna_plan* P, uint64_t* out_len, int32_t* status) {
+    if (!P || P->kind != 1 || ((!out_len || !status) && P->n)) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (P->n == 0) return PNA_OK;
+    if (!P->prepared) return PNA_E_BAD_ARG;
+    std::vector<EncEntry> dev(P->n);
+    CK(cudaMemcpyAsync(dev.data(), P->enc->d_entries.p, P->n * sizeof(EncEntry), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < P->n; i++) { status[i] = dev[i].status; out_len[i] = dev[i].status == ST_OK ? dev[i].out_len : 0; }
+    return PNA_OK;
 }
 extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status) {
     if (!P || P->kind != 1 || ((!out || !status) && P->n)) return PNA_E_BAD_ARG;

@@ -1,0 +1,597 @@
+// host_api.cpp -- implementation of include/pna_host.hpp: the container logic of the reference's data-chunk path in
+// C++ above the C ABI of libpna_cuda.so.  Built by __graft_entry__.build() into libpna_host.so (g++, links libpna_cuda.so).
+// Entry bytes are never touched by the CPU here; see the header for the reference file:line each piece follows.
+#include "../../include/pna_host.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+namespace pna {
+
+static const uint8_t SIGNATURE[8] = {0x89, 'P', 'N', 'A', 0x0D, 0x0A, 0x1A, 0x0A};
+static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static inline void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
+static inline bool ty_is(const RawChunk& c, const char* t) { return memcmp(c.ty, t, 4) == 0; }
+
+// ---- contexts: one pna_ctx per worker thread and device, kept for the life of the process
+static std::mutex g_pool_mu;
+static std::map<int, std::vector<pna_ctx*>> g_pool;
+struct CtxLease {
+    pna_ctx* ctx = nullptr;
+    int device;
+    explicit CtxLease(int dev) : device(dev) {
+        {
+            std::lock_guard<std::mutex> g(g_pool_mu);
+            auto& v = g_pool[dev];
+            if (!v.empty()) { ctx = v.back(); v.pop_back(); }
+        }
+        if (!ctx && pna_cuda_init(&ctx, dev) != PNA_OK) throw Error(PNA_E_CUDA, "pna_cuda_init failed: no usable sm_100 device (there is no CPU fallback)");
+    }
+    ~CtxLease() { if (ctx) { std::lock_guard<std::mutex> g(g_pool_mu); g_pool[device].push_back(ctx); } }
+};
+static void ck(pna_ctx* ctx, int rc, const char* what) {
+    if (rc != PNA_OK) throw Error(rc, std::string(what) + ": " + pna_cuda_strerror(rc) + " / " + pna_cuda_last_error(ctx));
+}
+
+// ---- index pass: walk chunk frames without touching chunk data (bytes::skip_chunk semantics, lib/src/bytes.rs:90)
+static void index_chunks(const uint8_t* buf, size_t len, size_t pos, std::vector<RawChunk>& out) {
+    while (pos < len) {
+        if (len - pos < 12) throw Error(PNA_E_UNEXPECTED_EOF, "truncated chunk");
+        RawChunk c;
+        c.len = be32(buf + pos);
+        memcpy(c.ty, buf + pos + 4, 4);
+        for (int k = 0; k < 4; k++)
+            if (!((c.ty[k] >= 'A' && c.ty[k] <= 'Z') || (c.ty[k] >= 'a' && c.ty[k] <= 'z'))) throw Error(PNA_E_INVALID_DATA, "invalid chunk type");   // chunk/types.rs:204
+        if (len - pos - 12 < c.len) throw Error(PNA_E_UNEXPECTED_EOF, "truncated chunk body");
+        c.off = pos + 8;
+        c.crc = be32(buf + pos + 8 + c.len);
+        out.push_back(c);
+        pos += 12 + (size_t)c.len;
+    }
+}
+static inline bool is_critical(const RawChunk& c) { return (c.ty[0] & 0x20) == 0; }
+
+// next_raw_item (archive/read.rs:46-73) + TryFrom<RawEntry> (entry.rs:665-737, 757-886)
+static void group_entries(const uint8_t* buf, const std::vector<RawChunk>& ch, std::vector<EntryInfo>& out) {
+    size_t i = 0;
+    while (i < ch.size()) {
+        const RawChunk& c = ch[i];
+        if (ty_is(c, "AEND") || ty_is(c, "ANXT")) break;
+        const bool normal = ty_is(c, "FHED"), solid = ty_is(c, "SHED");
+        if (!normal && !solid) { i++; continue; }   // AHED and archive-level ancillary chunks
+        EntryInfo e;
+        e.kind = solid ? 1 : 0;
+        e.chunk_begin = (uint32_t)i;
+        const uint8_t* h = buf + c.off;
+        if (normal) {
+            if (c.len < 6) throw Error(PNA_E_INVALID_DATA, "entry header too short");
+            if (h[0] != 0 || h[1] != 0) throw Error(PNA_E_UNSUPPORTED, "entry version is not supported");
+            e.data_kind = h[2]; e.compression = h[3]; e.encryption = h[4]; e.cipher_mode = h[5];
+            e.name.assign((const char*)h + 6, c.len - 6);
+        } else {
+            if (c.len != 5) throw Error(PNA_E_INVALID_DATA, "solid header must be 5 bytes");
+            if (h[0] != 0 || h[1] != 0) throw Error(PNA_E_UNSUPPORTED, "entry version is not supported");
+            e.compression = h[2]; e.encryption = h[3]; e.cipher_mode = h[4];
+        }
+        const char* end_ty = normal ? "FEND" : "SEND";
+        const char* dat_ty = normal ? "FDAT" : "SDAT";
+        size_t j = i + 1;
+        bool closed = false;
+        for (; j < ch.size(); j++) {
+            const RawChunk& d = ch[j];
+            if (ty_is(d, end_ty)) { closed = true; j++; break; }
+            if (ty_is(d, "ANXT") || ty_is(d, "AEND")) break;   // split archive: the entry continues in the next part (archive/read.rs:118)
+            if (ty_is(d, dat_ty)) { e.bodies.push_back({buf + d.off, d.len}); e.compressed_size += d.len; }
+            else if (ty_is(d, "PHSF")) { e.phsf.assign((const char*)buf + d.off, d.len); e.has_phsf = true; }
+            else if (normal && ty_is(d, "fSIZ")) {
+                uint64_t v = 0;
+                const uint32_t n = d.len > 16 ? 16 : d.len;       // u128_from_be_bytes_last
+                for (uint32_t k = d.len - n; k < d.len; k++) v = (v << 8) | buf[d.off + k];
+                e.raw_file_size = v;
+            } else if (is_critical(d)) throw Error(PNA_E_INVALID_DATA, "unknown critical chunk type");   // entry.rs:716,848
+        }
+        if (!closed) throw Error(PNA_E_UNEXPECTED_EOF, "entry without end chunk");
+        e.chunk_end = (uint32_t)j;
+        out.push_back(std::move(e));
+        i = j;
+    }
+}
+
+Archive Archive::read_header_from_slice(const uint8_t* buf, size_t len) {
+    Archive a;
+    if (len < 8 || memcmp(buf, SIGNATURE, 8) != 0) throw Error(PNA_E_INVALID_DATA, "it is not PNA");
+    a.buf_ = buf; a.len_ = len;
+    index_chunks(buf, len, 8, a.chunks_);
+    if (a.chunks_.empty() || !ty_is(a.chunks_[0], "AHED")) throw Error(PNA_E_INVALID_DATA, "expected `AHED` chunk");
+    if (a.chunks_[0].len != 8) throw Error(PNA_E_INVALID_DATA, "bad archive header");
+    const uint8_t* h = buf + a.chunks_[0].off;
+    if (h[0] != 0) throw Error(PNA_E_UNSUPPORTED, "archive version is not supported");   // archive/header.rs:47
+    a.archive_number_ = be32(h + 4);
+    group_entries(buf, a.chunks_, a.entries_);
+    return a;
+}
+
+static bool cipher_supported(const EntryInfo& e) {
+    return (e.encryption == PNA_ENCRYPTION_AES || e.encryption == PNA_ENCRYPTION_CAMELLIA) &&
+           (e.cipher_mode == PNA_CIPHER_CBC || e.cipher_mode == PNA_CIPHER_CTR);
+}
+// decrypt_reader's key path (entry/read.rs:45-78): returns false with a per-entry status when the key is unavailable
+static int32_t fill_desc(const EntryInfo& e, const ReadOptions& opt, pna_decode_desc& d) {
+    memset(&d, 0, sizeof d);
+    d.bodies = e.bodies.data(); d.n_bodies = (uint32_t)e.bodies.size();
+    d.compression = e.compression; d.encryption = e.encryption; d.cipher_mode = e.cipher_mode;
+    d.raw_size_hint = e.raw_file_size;
+    if (e.encryption != PNA_ENCRYPTION_NO && cipher_supported(e)) {
+        if (!opt.has_password) return PNA_E_INVALID_INPUT;                 // "password was not provided"
+        if (!e.has_phsf) return PNA_E_INVALID_DATA;                        // "`PHSF` chunk not found"
+        auto it = opt.keys.find(e.phsf);
+        if (it == opt.keys.end()) return PNA_E_INVALID_INPUT;
+        memcpy(d.key, it->second.data(), 32);
+    }
+    return PNA_OK;
+}
+
+void Archive::prepare(const ReadOptions& opt, int device) {
+    if (prepared_) return;
+    CtxLease L(device);
+    inner_.clear(); refs_.clear(); files_.clear();
+    // 1. solid entries: decode the SDAT stream (sizing call, then the real one), index + verify the inner chunks
+    for (size_t k = 0; k < entries_.size(); k++) {
+        const EntryInfo& e = entries_[k];
+        if (e.kind != 1) continue;
+        Inner in;
+        pna_decode_desc d;
+        int32_t st = fill_desc(e, opt, d);
+        if (st != PNA_OK) throw Error(st, "solid entry: key unavailable");
+        d.raw_size_hint = UINT64_MAX;
+        pna_buf ob{nullptr, 0, 0};
+        ck(L.ctx, pna_cuda_decode_batch(L.ctx, &d, 1, &ob, &st), "solid sizing");
+        if (st != PNA_OK && st != PNA_E_NOSPACE) throw Error(st, "solid entry: decode failed");
+        in.bytes.resize(ob.len + 16);
+        ob.ptr = in.bytes.data(); ob.cap = ob.len;
+        ck(L.ctx, pna_cuda_decode_batch(L.ctx, &d, 1, &ob, &st), "solid decode");
+        if (st != PNA_OK) throw Error(st, "solid entry: decode failed");
+        in.bytes.resize(ob.len);
+        index_chunks(in.bytes.data(), in.bytes.size(), 0, in.chunks);       // entry.rs:401-423: chunks, CRC checked as read
+        if (!in.chunks.empty()) {
+            std::vector<uint64_t> off(in.chunks.size()), len(in.chunks.size());
+            std::vector<uint32_t> crc(in.chunks.size());
+            for (size_t c = 0; c < in.chunks.size(); c++) { off[c] = in.chunks[c].off - 4; len[c] = (uint64_t)in.chunks[c].len + 4; }
+            ck(L.ctx, pna_cuda_crc32_image(L.ctx, in.bytes.data(), in.bytes.size(), off.data(), len.data(), (uint32_t)off.size(), crc.data()), "solid inner crc");
+            for (size_t c = 0; c < in.chunks.size(); c++)
+                if (crc[c] != in.chunks[c].crc) throw Error(PNA_E_INVALID_DATA, "broken chunk (inside solid entry)");
+        }
+        group_entries(in.bytes.data(), in.chunks, in.entries);
+        inner_.push_back(std::move(in));
+    }
+    // 2. FILE entries in archive order
+    uint32_t solid_no = 0;
+    for (size_t k = 0; k < entries_.size(); k++) {
+        const EntryInfo& e = entries_[k];
+        if (e.kind == 1) {
+            const Inner& in = inner_[solid_no];
+            for (size_t q = 0; q < in.entries.size(); q++)
+                if (in.entries[q].kind == 0 && in.entries[q].data_kind == (uint8_t)DataKind::File) refs_.push_back({solid_no + 1, (uint32_t)q});
+            solid_no++;
+        } else if (e.data_kind == (uint8_t)DataKind::File) refs_.push_back({0, (uint32_t)k});
+    }
+    // 3. sizes: fSIZ, else a sizing pass (cap 0 -> PNA_E_NOSPACE with the length)
+    files_.resize(refs_.size());
+    std::vector<uint32_t> unknown;
+    for (size_t i = 0; i < refs_.size(); i++) {
+        const EntryInfo& e = refs_[i].owner ? inner_[refs_[i].owner - 1].entries[refs_[i].entry] : entries_[refs_[i].entry];
+        files_[i].name = e.name;
+        files_[i].size = e.raw_file_size;
+        if (e.raw_file_size == UINT64_MAX) unknown.push_back((uint32_t)i);
+    }
+    if (!unknown.empty()) {
+        std::vector<pna_decode_desc> descs(unknown.size());
+        std::vector<pna_buf> bufs(unknown.size(), pna_buf{nullptr, 0, 0});
+        std::vector<int32_t> st(unknown.size(), 0), pre(unknown.size(), 0);
+        for (size_t u = 0; u < unknown.size(); u++) {
+            const FileRef r = refs_[unknown[u]];
+            const EntryInfo& e = r.owner ? inner_[r.owner - 1].entries[r.entry] : entries_[r.entry];
+            pre[u] = fill_desc(e, opt, descs[u]);
+            if (pre[u] != PNA_OK) { descs[u].n_bodies = 0; descs[u].encryption = 0; descs[u].compression = 0; }
+        }
+        ck(L.ctx, pna_cuda_decode_batch(L.ctx, descs.data(), (uint32_t)descs.size(), bufs.data(), st.data()), "sizing pass");
+        for (size_t u = 0; u < unknown.size(); u++) {
+            FileOut& f = files_[unknown[u]];
+            if (pre[u] != PNA_OK) { f.status = pre[u]; f.size = 0; }
+            else if (st[u] == PNA_OK || st[u] == PNA_E_NOSPACE) f.size = bufs[u].len;
+            else { f.status = st[u]; f.size = 0; }
+        }
+    }
+    prepared_ = true;
+}
+
+void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
+                            uint64_t group_bytes, bool verify) {
+    if (!prepared_) prepare(opt, device);
+    const size_t n = refs_.size();
+    // groups of consecutive files of the same owner, cut when the compressed bytes reach group_bytes
+    struct Group { size_t lo, hi; };
+    std::vector<Group> groups;
+    {
+        size_t lo = 0;
+        uint64_t acc = 0;
+        for (size_t i = 0; i < n; i++) {
+            const EntryInfo& e = refs_[i].owner ? inner_[refs_[i].owner - 1].entries[refs_[i].entry] : entries_[refs_[i].entry];
+            const bool cut = i > lo && (refs_[i].owner != refs_[lo].owner || acc >= group_bytes);
+            if (cut) { groups.push_back({lo, i}); lo = i; acc = 0; }
+            acc += e.compressed_size;
+        }
+        if (lo < n) groups.push_back({lo, n});
+    }
+    // chunk ranges of the top-level archive covered by each top-level group (contiguous, together all chunks)
+    std::vector<std::pair<uint32_t, uint32_t>> crange(groups.size(), {0, 0});
+    if (verify) {
+        int first_top = -1, last_top = -1;
+        for (size_t g = 0; g < groups.size(); g++) if (refs_[groups[g].lo].owner == 0) { if (first_top < 0) first_top = (int)g; last_top = (int)g; }
+        uint32_t prev_end = 0;
+        for (size_t g = 0; g < groups.size(); g++) {
+            if (refs_[groups[g].lo].owner != 0) continue;
+            const uint32_t end = (int)g == last_top ? (uint32_t)chunks_.size() : entries_[refs_[groups[g].hi - 1].entry].chunk_end;
+            crange[g] = {(int)g == first_top ? 0u : prev_end, end};
+            prev_end = end;
+        }
+        if (first_top < 0 && !chunks_.empty()) {   // no top-level FILE entry at all: verify the archive's chunks in one call
+            CtxLease L(device);
+            std::vector<uint64_t> off(chunks_.size()), len(chunks_.size());
+            std::vector<uint32_t> crc(chunks_.size());
+            for (size_t c = 0; c < chunks_.size(); c++) { off[c] = chunks_[c].off - 4; len[c] = (uint64_t)chunks_[c].len + 4; }
+            ck(L.ctx, pna_cuda_crc32_image(L.ctx, buf_, len_, off.data(), len.data(), (uint32_t)off.size(), crc.data()), "archive crc");
+            for (size_t c = 0; c < chunks_.size(); c++) if (crc[c] != chunks_[c].crc) throw Error(PNA_E_INVALID_DATA, "broken chunk");
+        }
+    }
+    std::atomic<size_t> next{0};
+    std::mutex err_mu;
+    std::string err_msg;
+    int err_kind = 0;
+    auto work = [&]() {
+        try {
+            CtxLease L(device);
+            for (;;) {
+                const size_t g = next.fetch_add(1);
+                if (g >= groups.size()) break;
+                const Group G = groups[g];
+                const uint32_t m = (uint32_t)(G.hi - G.lo);
+                std::vector<pna_decode_desc> descs(m);
+                std::vector<pna_buf> bufs(m);
+                std::vector<int32_t> st(m, 0), pre(m, 0);
+                for (uint32_t k = 0; k < m; k++) {
+                    const FileRef r = refs_[G.lo + k];
+                    const EntryInfo& e = r.owner ? inner_[r.owner - 1].entries[r.entry] : entries_[r.entry];
+                    pre[k] = files_[G.lo + k].status ? files_[G.lo + k].status : fill_desc(e, opt, descs[k]);
+                    if (pre[k] != PNA_OK) { memset(&descs[k], 0, sizeof descs[k]); descs[k].raw_size_hint = 0; }
+                    else descs[k].raw_size_hint = files_[G.lo + k].size;
+                    bufs[k] = pna_buf{out + offsets[G.lo + k], offsets[G.lo + k + 1] - offsets[G.lo + k], 0};
+                }
+                pna_plan* plan = nullptr;
+                const bool top = refs_[G.lo].owner == 0;
+                if (verify && top && crange[g].second > crange[g].first) {
+                    const uint32_t c0 = crange[g].first, c1 = crange[g].second, nc = c1 - c0;
+                    std::vector<pna_span> spans(nc);
+                    std::vector<uint32_t> expect(nc);
+                    std::vector<int32_t> owner(nc, -1);
+                    for (uint32_t c = 0; c < nc; c++) { spans[c] = {buf_ + chunks_[c0 + c].off - 4, (uint64_t)chunks_[c0 + c].len + 4}; expect[c] = chunks_[c0 + c].crc; }
+                    for (uint32_t k = 0; k < m; k++) {
+                        const EntryInfo& e = entries_[refs_[G.lo + k].entry];
+                        for (uint32_t c = e.chunk_begin; c < e.chunk_end; c++) owner[c - c0] = (int32_t)k;
+                    }
+                    ck(L.ctx, pna_cuda_decode_plan_create_crc(L.ctx, descs.data(), m, spans.data(), expect.data(), owner.data(), nc, &plan), "plan_create_crc");
+                } else ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, descs.data(), m, &plan), "plan_create");
+                int rc = pna_cuda_decode_plan_run(plan);
+                if (rc == PNA_OK) rc = pna_cuda_decode_plan_fetch(plan, bufs.data(), st.data());
+                uint32_t broken = 0;
+                if (rc == PNA_OK && verify && top) rc = pna_cuda_plan_crc_results(plan, nullptr, &broken);
+                pna_cuda_plan_destroy(plan);
+                ck(L.ctx, rc, "decode plan");
+                bool any_entry_broken = false;
+                for (uint32_t k = 0; k < m; k++) {
+                    status[G.lo + k] = pre[k] != PNA_OK ? pre[k] : st[k];
+                    if (st[k] == PNA_E_INVALID_DATA) any_entry_broken = true;
+                }
+                if (broken && !any_entry_broken) throw Error(PNA_E_INVALID_DATA, "broken chunk");   // an archive-level / non-file chunk
+            }
+        } catch (const Error& e) {
+            std::lock_guard<std::mutex> g(err_mu);
+            if (err_msg.empty()) { err_msg = e.what(); err_kind = e.kind; }
+        }
+    };
+    const int nw = std::max(1, std::min<int>(workers, (int)std::max<size_t>(groups.size(), 1)));
+    std::vector<std::thread> th;
+    for (int w = 1; w < nw; w++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (!err_msg.empty()) throw Error(err_kind, err_msg);
+}
+
+// ---------------------------------------------------------------------------------------------- create
+static inline void wr_be32(uint8_t* p, uint32_t x) { p[0] = x >> 24; p[1] = x >> 16; p[2] = x >> 8; p[3] = x; }
+static uint64_t entry_frame_bound(const std::string& name, uint64_t stream_bound, const std::string& phsf, bool enc, uint32_t mcs) {
+    const uint64_t cap = mcs ? mcs : 0xFFFFFFFFull;
+    const uint64_t nbody = stream_bound / cap + 2;
+    return 12 + 6 + name.size() + 12 + 16 + (enc ? 12 + phsf.size() + 12 + 16 : 0) + nbody * 12 + stream_bound + 12;
+}
+
+// Archive::write_header + add_entry per file + finalize (archive/write.rs:92,368,545; wire order entry.rs:895-912), written
+// straight into `out`: every worker encodes one group of files on its own pna_ctx, learns the produced stream lengths,
+// takes its place behind the previous group, and lets the GPU copy the streams to their final position (D2H).
+uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
+                             int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap) {
+    const size_t n = files.size();
+    struct Group { size_t lo, hi; };
+    std::vector<Group> groups;
+    {
+        size_t lo = 0;
+        uint64_t acc = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (i > lo && acc >= group_bytes) { groups.push_back({lo, i}); lo = i; acc = 0; }
+            acc += files[i].data.len;
+        }
+        if (lo < n) groups.push_back({lo, n});
+    }
+    const bool enc = opt.encryption != PNA_ENCRYPTION_NO;
+    const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull, iv_len = enc ? 16 : 0;
+    if (cap < 8 + 20 + 12) throw Error(PNA_E_NOSPACE, "archive buffer too small");
+    memcpy(out, SIGNATURE, 8);
+    // group g starts at base[g]; base[g+1] is published by the worker of group g as soon as it knows its size
+    std::vector<uint64_t> base(groups.size() + 1, 0);
+    std::vector<uint8_t> ready(groups.size() + 1, 0);
+    base[0] = 8 + 20; ready[0] = 1;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<size_t> next{0};
+    std::string err_msg;
+    int err_kind = 0;
+    bool failed = false;
+    auto work = [&]() {
+        size_t g = 0;
+        try {
+            CtxLease L(device);
+            for (;;) {
+                g = next.fetch_add(1);
+                if (g >= groups.size()) break;
+                const Group G = groups[g];
+                const uint32_t m = (uint32_t)(G.hi - G.lo);
+                std::vector<pna_encode_desc> descs(m);
+                uint64_t crc_total = 0;
+                for (uint32_t k = 0; k < m; k++) {
+                    const FileEntryBuilder& f = files[G.lo + k];
+                    pna_encode_desc& d = descs[k];
+                    memset(&d, 0, sizeof d);
+                    d.plain = f.data;
+                    d.compression = opt.compression; d.encryption = opt.encryption; d.cipher_mode = opt.cipher_mode; d.level = opt.level;
+                    memcpy(d.key, opt.key, 32); memcpy(d.iv, f.iv, 16);
+                    d.max_chunk_size = max_chunk_size;
+                    crc_total += pna_cuda_encode_crc_count(&d);
+                }
+                pna_plan* plan = nullptr;
+                ck(L.ctx, pna_cuda_encode_plan_create(L.ctx, descs.data(), m, &plan), "encode_plan_create");
+                struct PlanGuard { pna_plan* p; ~PlanGuard() { if (p) pna_cuda_plan_destroy(p); } } guard{plan};
+                ck(L.ctx, pna_cuda_encode_plan_run(plan), "encode_plan_run");
+                // metadata chunks (type || data, contiguous) and their CRCs in one GPU batch while the encode kernels run
+                std::vector<uint8_t> meta;
+                struct MetaRef { size_t off; uint32_t len; };
+                std::vector<MetaRef> refs;
+                auto add_meta = [&](const char* ty, const uint8_t* data, uint32_t len) {
+                    refs.push_back({meta.size(), len + 4});
+                    meta.insert(meta.end(), ty, ty + 4);
+                    if (len) meta.insert(meta.end(), data, data + len);
+                };
+                for (uint32_t k = 0; k < m; k++) {
+                    const FileEntryBuilder& f = files[G.lo + k];
+                    std::vector<uint8_t> hdr = {0, 0, (uint8_t)DataKind::File, opt.compression, opt.encryption, opt.cipher_mode};
+                    hdr.insert(hdr.end(), f.name.begin(), f.name.end());
+                    add_meta("FHED", hdr.data(), (uint32_t)hdr.size());
+                    uint8_t sz[8];
+                    for (int b = 0; b < 8; b++) sz[b] = (uint8_t)(f.data.len >> (8 * (7 - b)));
+                    int skip = 0;
+                    while (skip < 8 && sz[skip] == 0) skip++;                       // entry.rs:901-903: minimal big-endian bytes
+                    add_meta("fSIZ", sz + skip, (uint32_t)(8 - skip));
+                    if (enc) {
+                        add_meta("PHSF", (const uint8_t*)opt.phsf.data(), (uint32_t)opt.phsf.size());
+                        add_meta("FDAT", f.iv, 16);                                 // the IV is its own chunk (builder.rs:62-69)
+                    }
+                    add_meta("FEND", nullptr, 0);
+                }
+                std::vector<pna_span> spans(refs.size());
+                std::vector<uint32_t> mcrc(refs.size());
+                for (size_t r = 0; r < refs.size(); r++) spans[r] = {meta.data() + refs[r].off, refs[r].len};
+                {
+                    CtxLease L2(device);   // a second context: the encode plan's stream stays busy meanwhile
+                    ck(L2.ctx, pna_cuda_crc32(L2.ctx, spans.data(), (uint32_t)spans.size(), mcrc.data()), "metadata crc");
+                }
+                std::vector<uint64_t> lens(m);
+                std::vector<int32_t> st(m);
+                ck(L.ctx, pna_cuda_encode_plan_lengths(plan, lens.data(), st.data()), "encode_plan_lengths");
+                // layout of this group
+                std::vector<uint64_t> entry_pos(m + 1, 0);
+                const size_t metas_per_entry = enc ? 5 : 3;
+                for (uint32_t k = 0; k < m; k++) {
+                    if (st[k] != PNA_OK) throw Error(st[k], files[G.lo + k].name + ": encode failed");
+                    uint64_t sz = 0;
+                    for (size_t q = 0; q < metas_per_entry; q++) sz += 8 + refs[k * metas_per_entry + q].len;   // len + (type||data) + crc
+                    const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
+                    sz += nb * 12 + D;
+                    entry_pos[k + 1] = entry_pos[k] + sz;
+                }
+                uint64_t my_base;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return ready[g] || failed; });
+                    if (failed) return;
+                    my_base = base[g];
+                    base[g + 1] = my_base + entry_pos[m];
+                    ready[g + 1] = 1;
+                    cv.notify_all();
+                }
+                if (my_base + entry_pos[m] + 12 > cap) throw Error(PNA_E_NOSPACE, "archive buffer too small");
+                // fetch: single-body streams go straight to their final place (the 16 IV bytes land on the frame bytes in front
+                // of the data and are overwritten by them afterwards); multi-body streams pass through a staging buffer
+                std::vector<pna_buf> bufs(m);
+                std::vector<std::vector<uint8_t>> stage(m);
+                std::vector<uint64_t> data_pos(m);
+                for (uint32_t k = 0; k < m; k++) {
+                    uint64_t p = my_base + entry_pos[k];
+                    for (size_t q = 0; q + 1 < metas_per_entry; q++) p += 8 + refs[k * metas_per_entry + q].len;
+                    data_pos[k] = p;   // first FDAT body frame starts here
+                    const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
+                    if (nb <= 1) bufs[k] = pna_buf{out + p + 8 - iv_len, lens[k], 0};
+                    else { stage[k].resize(lens[k]); bufs[k] = pna_buf{stage[k].data(), lens[k], 0}; }
+                }
+                std::vector<uint32_t> crcs(crc_total + 1), ncrc(m, 0);
+                ck(L.ctx, pna_cuda_encode_plan_fetch(plan, bufs.data(), crcs.data(), ncrc.data(), st.data()), "encode_plan_fetch");
+                size_t cpos = 0;
+                for (uint32_t k = 0; k < m; k++) {
+                    if (st[k] != PNA_OK) throw Error(st[k], files[G.lo + k].name + ": fetch failed");
+                    uint8_t* w = out + my_base + entry_pos[k];
+                    auto put_meta = [&](size_t r) {
+                        const MetaRef& mr = refs[r];
+                        wr_be32(w, mr.len - 4); memcpy(w + 4, meta.data() + mr.off, mr.len); wr_be32(w + 4 + mr.len, mcrc[r]);
+                        w += 8 + mr.len;
+                    };
+                    const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
+                    // bodies first where they were staged, then the frames around them (which also repair the IV overlap)
+                    uint8_t* body_w = out + data_pos[k];
+                    for (uint64_t b = 0; b < nb; b++) {
+                        const uint64_t o = b * mcs, l = std::min<uint64_t>(mcs, D - o);
+                        if (nb > 1) memcpy(body_w + 8, stage[k].data() + iv_len + o, l);
+                        wr_be32(body_w + 8 + l, crcs[cpos + b]);
+                        body_w += 12 + l;
+                    }
+                    for (size_t q = 0; q + 1 < metas_per_entry; q++) put_meta(k * metas_per_entry + q);   // FHED, fSIZ, [PHSF, FDAT(iv)]
+                    body_w = out + data_pos[k];
+                    for (uint64_t b = 0; b < nb; b++) {
+                        const uint64_t o = b * mcs, l = std::min<uint64_t>(mcs, D - o);
+                        wr_be32(body_w, (uint32_t)l); memcpy(body_w + 4, "FDAT", 4);
+                        body_w += 12 + l;
+                    }
+                    w = body_w;
+                    put_meta(k * metas_per_entry + metas_per_entry - 1);   // FEND
+                    cpos += ncrc[k];
+                }
+            }
+        } catch (const Error& e) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (err_msg.empty()) { err_msg = e.what(); err_kind = e.kind; }
+            failed = true;
+            cv.notify_all();
+        }
+    };
+    const int nw = std::max(1, std::min<int>(workers, (int)std::max<size_t>(groups.size(), 1)));
+    std::vector<std::thread> th;
+    for (int w = 1; w < nw; w++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (!err_msg.empty()) throw Error(err_kind, err_msg);
+    // archive framing: AHED right behind the signature, AEND behind the last group (archive/write.rs:92,545)
+    const uint64_t end = base[groups.size()];
+    if (end + 12 > cap) throw Error(PNA_E_NOSPACE, "archive buffer too small");
+    {
+        CtxLease L(device);
+        const uint8_t ahed[12] = {'A', 'H', 'E', 'D', 0, 0, 0, 0, 0, 0, 0, 0}, aend[4] = {'A', 'E', 'N', 'D'};
+        pna_span sp[2] = {{ahed, 12}, {aend, 4}};
+        uint32_t c[2];
+        ck(L.ctx, pna_cuda_crc32(L.ctx, sp, 2, c), "archive crc");
+        wr_be32(out + 8, 8); memcpy(out + 12, ahed, 12); wr_be32(out + 24, c[0]);
+        wr_be32(out + end, 0); memcpy(out + end + 4, aend, 4); wr_be32(out + end + 8, c[1]);
+    }
+    return end + 12;
+}
+
+std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
+                                    int device, int workers, uint64_t group_bytes) {
+    uint64_t bound = 8 + 20 + 12;
+    for (const auto& f : files) {
+        pna_encode_desc d;
+        memset(&d, 0, sizeof d);
+        d.plain.len = f.data.len; d.compression = opt.compression; d.encryption = opt.encryption;
+        bound += entry_frame_bound(f.name, pna_cuda_encode_bound(&d), opt.phsf, opt.encryption != 0, max_chunk_size);
+    }
+    std::vector<uint8_t> out(bound);
+    out.resize(create_archive_into(files, opt, max_chunk_size, device, workers, group_bytes, out.data(), out.size()));
+    return out;
+}
+
+}  // namespace pna
+
+// ---------------------------------------------------------------------------------------------- flat C view
+struct pnah_archive {
+    pna::Archive a;
+    pna::ReadOptions opt;
+};
+static int fail(const pna::Error& e, char* err, uint64_t cap) {
+    if (err && cap) { strncpy(err, e.what(), cap - 1); err[cap - 1] = 0; }
+    return e.kind ? e.kind : PNA_E_INTERNAL;
+}
+extern "C" {
+int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, uint64_t errcap) {
+    try {
+        pnah_archive* h = new pnah_archive{pna::Archive::read_header_from_slice(buf, len), {}};
+        *out = h;
+        return PNA_OK;
+    } catch (const pna::Error& e) { *out = nullptr; return fail(e, err, errcap); }
+}
+void pnah_close(pnah_archive* a) { delete a; }
+uint32_t pnah_entry_count(pnah_archive* a) { return (uint32_t)a->a.entries().size(); }
+uint32_t pnah_chunk_count(pnah_archive* a) { return (uint32_t)a->a.chunks().size(); }
+int pnah_entry_get(pnah_archive* a, uint32_t i, pnah_entry_info* info) {
+    if (i >= a->a.entries().size()) return PNA_E_BAD_ARG;
+    const pna::EntryInfo& e = a->a.entries()[i];
+    info->kind = e.kind; info->data_kind = e.data_kind; info->compression = e.compression; info->encryption = e.encryption;
+    info->cipher_mode = e.cipher_mode; info->n_bodies = (uint32_t)e.bodies.size(); info->compressed_size = e.compressed_size;
+    info->raw_file_size = e.raw_file_size; info->name = e.name.c_str(); info->phsf = e.has_phsf ? e.phsf.c_str() : nullptr;
+    return PNA_OK;
+}
+int pnah_set_key(pnah_archive* a, const char* phsf, const uint8_t key[32]) { a->opt.set_key(phsf, key); return PNA_OK; }
+int pnah_prepare(pnah_archive* a, int device, char* err, uint64_t errcap) {
+    try { a->a.prepare(a->opt, device); return PNA_OK; } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
+uint32_t pnah_file_count(pnah_archive* a) { return (uint32_t)a->a.files().size(); }
+int pnah_file_get(pnah_archive* a, uint32_t i, const char** name, uint64_t* size) {
+    if (i >= a->a.files().size()) return PNA_E_BAD_ARG;
+    *name = a->a.files()[i].name.c_str(); *size = a->a.files()[i].size;
+    return a->a.files()[i].status;
+}
+int pnah_extract_files(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
+                       uint64_t group_bytes, int verify, char* err, uint64_t errcap) {
+    try { a->a.extract_files(a->opt, out, offsets, status, device, workers, group_bytes, verify != 0); return PNA_OK; }
+    catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
+uint64_t pnah_create_bound(uint32_t n, const char* const* names, const uint64_t* lens, uint8_t compression, uint8_t encryption,
+                           const char* phsf, uint32_t max_chunk_size) {
+    uint64_t t = 8 + 20 + 12;
+    for (uint32_t i = 0; i < n; i++) {
+        pna_encode_desc d;
+        memset(&d, 0, sizeof d);
+        d.plain.len = lens[i]; d.compression = compression; d.encryption = encryption;
+        t += pna::entry_frame_bound(names[i], pna_cuda_encode_bound(&d), phsf ? phsf : "", encryption != 0, max_chunk_size);
+    }
+    return t;
+}
+int pnah_create(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs,
+                uint8_t compression, int32_t level, uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf,
+                uint32_t max_chunk_size, int device, int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap, uint64_t* out_len,
+                char* err, uint64_t errcap) {
+    try {
+        std::vector<pna::FileEntryBuilder> files(n);
+        for (uint32_t i = 0; i < n; i++) {
+            files[i].name = names[i];
+            files[i].data = pna_span{data[i], lens[i]};
+            if (ivs) memcpy(files[i].iv, ivs + 16 * (size_t)i, 16);
+        }
+        pna::WriteOptions opt;
+        opt.compression = compression; opt.level = level; opt.encryption = encryption; opt.cipher_mode = cipher_mode;
+        if (key) memcpy(opt.key, key, 32);
+        if (phsf) opt.phsf = phsf;
+        *out_len = pna::create_archive_into(files, opt, max_chunk_size, device, workers, group_bytes, out, cap);
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
+}

@@ -1,0 +1,123 @@
+"""C++ host layer (include/pna_host.hpp, libpna_host.so): index pass + entry grouping on the CPU tier, pipelined extract and
+archive creation on the GPU tier.  Reads like lib/tests/extract_compatibility.rs / extract_solid_compatibility.rs."""
+import ctypes as C
+import hashlib
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host(pna):
+    return importlib.import_module("portable-network-archive_b200._host")
+
+
+def test_host_exports_match_header(host):
+    hdr = open(os.path.join(ROOT, "include", "pna_host.hpp")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pnah_\w+)\s*\(", hdr))
+    lib = C.CDLL(os.path.join(ROOT, "portable-network-archive_b200", "libpna_host.so"))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(host.EXPORTS)
+
+
+def test_index_pass_matches_python_mirror_on_every_fixture(host, pna, golden):
+    """The index pass touches only the 12-byte chunk frames (bytes.rs:90); entry grouping = archive/read.rs:46-73."""
+    mod = importlib.import_module("portable-network-archive_b200.archive")
+    for name, info in golden["archives"].items():
+        buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+        if name.startswith("multipart.part1"):   # the entry continues in part 2: a single slice ends inside it
+            with pytest.raises(host.HostError) as ei:
+                host.HostArchive(buf)
+            assert ei.value.kind == pna.E_UNEXPECTED_EOF
+            continue
+        a = host.HostArchive(buf)
+        chunks = mod.index_archive(buf, 8)
+        assert a.n_chunks == len(chunks), name
+        ents = a.entries()
+        if name.startswith("multipart"):
+            continue
+        n_fhed = sum(1 for c in chunks if c.ty == b"FHED")
+        n_shed = sum(1 for c in chunks if c.ty == b"SHED")
+        assert sum(1 for e in ents if e["kind"] == 0) == n_fhed and sum(1 for e in ents if e["kind"] == 1) == n_shed, name
+        assert sum(e["n_bodies"] for e in ents) == sum(1 for c in chunks if c.ty in (b"FDAT", b"SDAT")), name
+
+
+def test_index_pass_errors(host):
+    with pytest.raises(host.HostError) as ei:
+        host.HostArchive(b"not a pna archive at all")
+    assert ei.value.kind == 1   # InvalidData "it is not PNA"
+    good = np.fromfile(os.path.join(ROOT, "tests", "golden", "ref", "zstd.pna"), dtype=np.uint8)
+    with pytest.raises(host.HostError) as ei:
+        host.HostArchive(good[:1000].copy())
+    assert ei.value.kind == 2   # UnexpectedEof: truncated chunk
+    bad = good.copy()
+    bad[12] = ord("1")          # chunk type must be ASCII letters (chunk/types.rs:204)
+    with pytest.raises(host.HostError) as ei:
+        host.HostArchive(bad)
+    assert ei.value.kind == 1
+
+
+@pytest.mark.gpu
+def test_golden_archives_through_cpp_host(host, pna, ctx, golden):
+    for name, info in golden["archives"].items():
+        if name.startswith("multipart"):
+            continue
+        buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+        a = host.HostArchive(buf)
+        for phsf, key in info["keys"].items():
+            a.set_key(phsf, bytes.fromhex(key))
+        if info["expect"] != "ok":
+            with pytest.raises(host.HostError) as ei:
+                r = a.read_all()
+                bad = [s for _, s, _ in r if s]
+                if bad:
+                    raise host.HostError(bad[0], "entry status")
+            assert ei.value.kind == pna.E_UNSUPPORTED, name
+            continue
+        got = a.read_all(workers=2, group_bytes=20_000)
+        assert [n for n, _, _ in got] == [e["name"] for e in info["entries"]], name
+        for (n, st, d), e in zip(got, info["entries"]):
+            assert st == 0 and len(d) == e["size"] and hashlib.sha256(d).hexdigest() == e["sha256"], (name, n)
+
+
+@pytest.mark.gpu
+def test_broken_chunk_detected_by_cpp_host(host, pna, ctx, golden):
+    info = golden["archives"]["zstd.pna"]
+    buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8).copy()
+    buf[5000] ^= 0x40
+    a = host.HostArchive(buf)
+    out, offs, st = a.extract_files()
+    assert st.count(pna.E_INVALID_DATA) == 1 and st.count(0) == len(st) - 1     # the entry owning the broken chunk
+    # a broken archive-level chunk (AHED data) is an archive error
+    buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8).copy()
+    buf[8 + 8 + 5] ^= 1
+    with pytest.raises(host.HostError) as ei:
+        host.HostArchive(buf).extract_files()
+    assert ei.value.kind == pna.E_INVALID_DATA
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("comp,enc,mode", [(2, 1, 1), (1, 2, 0), (0, 0, 0), (2, 0, 0)])
+def test_create_with_cpp_host_is_reference_readable(host, pna, ctx, oracle, comp, enc, mode):
+    """create path end to end (FileEntryBuilder -> add_entry -> finalize in C++): the oracle's restatement of the reference
+    reader must list and extract the same files; then our own C++ reader too (cli/tests/cli/encrypt.rs round trip)."""
+    opts = pna.WriteOptions(compression=comp, encryption=enc, cipher_mode=mode, password=b"pw", kdf_params={"i": 1000})
+    files = [(f"dir/f{i:03d}.bin", corpus.make_file(300 + i, n)) for i, n in enumerate([0, 1, 100, 70_000, 400_000, 33_000] * 5)]
+    blob = host.create_archive(files, compression=comp, encryption=enc, cipher_mode=mode, key=opts.key, phsf=opts.phsf,
+                               max_chunk_size=60_000, workers=2, group_bytes=300_000)
+    got = list(oracle.extract_all(blob.tobytes(), b"pw"))
+    assert got == files
+    a = host.HostArchive(blob)
+    if enc:
+        a.set_key(opts.phsf, opts.key)
+    back = a.read_all(workers=2, group_bytes=300_000)
+    assert [(n, d) for n, _, d in back] == files and all(s == 0 for _, s, _ in back)
