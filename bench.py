@@ -43,11 +43,14 @@ def _gen(i):
     return corpus.make_file(i, FILE_SIZE)
 
 
-def make_shard(rank: int, entries: int, threads: int):
-    """Plain files + oracle-encoded streams (zstd 3 + AES-256-CTR) of this rank's shard.  Not timed."""
+def make_shard(rank: int, entries: int, threads: int, world: int = 1):
+    """Plain files + oracle-encoded streams (zstd 3 + AES-256-CTR) of this rank's shard.  Not timed.
+    The global corpus has world x entries files; the rank's share comes from the same LPT partition by entry that the
+    extract path uses (portable-network-archive_b200/shard.py) -- no collective, every rank derives it alone."""
     import multiprocessing as mp
     import pna_oracle as O
-    idx = range(rank * entries, (rank + 1) * entries)
+    shard = importlib.import_module("portable-network-archive_b200.shard")
+    idx = shard.rank_entries([FILE_SIZE] * (entries * world), rank, world)
     with mp.get_context("fork").Pool(max(1, min(threads, 64))) as pool:
         files = pool.map(_gen, idx, chunksize=4)
     key = bytes(range(32))
@@ -254,7 +257,7 @@ def main():
         return float(t.item())
 
     # ---- inputs (not timed)
-    files, streams, key = make_shard(rank, E, threads)
+    files, streams, key = make_shard(rank, E, threads, world)
     sizes = [len(f) for f in files]
     U = sum(sizes)
     opts = pna.WriteOptions(compression=2, encryption=1, cipher_mode=1, password=PASSWORD, kdf_params={"i": 1000})

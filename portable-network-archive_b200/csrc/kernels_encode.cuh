@@ -108,44 +108,54 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
         const uint32_t v = (uint32_t)d[p] | ((uint32_t)d[p + 1] << 8) | ((uint32_t)d[p + 2] << 16) | ((uint32_t)d[p + 3] << 24);
         const uint32_t h = (v * 2654435761u) >> (32 - HLOG);
         const uint32_t ct = valid ? S->table[h] : 0xFFFFu;
-        // nearest lower lane of this step with the same 4 bytes
-        const uint32_t vm = __match_any_sync(0xFFFFFFFFu, valid ? (unsigned long long)v : (0x100000000ull | (unsigned)lane));
-        const uint32_t lower = vm & lt;
-        const uint32_t cw = lower ? base + (31u - (uint32_t)__clz((int)lower)) : 0xFFFFu;
+        // one MATCH on the hash groups the lanes: the nearest lower lane of my group is the in-step candidate when its four
+        // bytes really are mine (else a hash collision: no in-step candidate), the highest lane of each group inserts
+        const uint32_t hm = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u | (unsigned)lane));
+        const uint32_t lower = hm & lt;
+        const int t1 = 31 - __clz((int)(lower | 1u));
+        const uint32_t vt = __shfl_sync(0xFFFFFFFFu, v, t1);
+        const uint32_t cw = (valid && lower && vt == v) ? base + (uint32_t)t1 : 0xFFFFu;
         __syncwarp();
-        {   // insert: the highest lane of each hash group wins (deterministic), every position is inserted
-            const uint32_t hm = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u | (unsigned)lane));
-            if (valid && lane == 31 - __clz((int)hm)) S->table[h] = (uint16_t)p;
-        }
+        if (valid && lane == 31 - __clz((int)hm)) S->table[h] = (uint16_t)p;   // deterministic; every position is inserted
         if (carry >= 32) { carry -= 32; continue; }   // the whole step lies inside a match
-        // ---- match lengths against both candidates in one loop
+        // ---- match lengths against both candidates in one loop, four bytes per step (unaligned words from two
+        // aligned shared loads + funnel shift; the zero tail behind the segment makes the over-read harmless)
         uint32_t best = 0, boff = 0;
         if (valid) {
             const uint32_t maxlen = len - p < MAX_MATCH ? len - p : MAX_MATCH;
             bool aw = cw != 0xFFFFu, at = ct != 0xFFFFu && ct != cw;
             uint32_t lw = 0, ltb = 0, k = 0;
+            auto ld32 = [&](uint32_t pos) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(d + (pos & ~3u));
+                return __funnelshift_r(q[0], q[1], (pos & 3u) * 8u);
+            };
             while (k < maxlen && (aw || at)) {
-                const uint8_t c = d[p + k];
-                if (aw && d[cw + k] != c) { aw = false; lw = k; }
-                if (at && d[ct + k] != c) { at = false; ltb = k; }
-                k++;
+                const uint32_t x = ld32(p + k);
+                if (aw) { const uint32_t df = x ^ ld32(cw + k); if (df) { aw = false; lw = k + ((uint32_t)__ffs((int)df) - 1u) / 8u; } }
+                if (at) { const uint32_t df = x ^ ld32(ct + k); if (df) { at = false; ltb = k + ((uint32_t)__ffs((int)df) - 1u) / 8u; } }
+                k += 4;
             }
-            if (aw) lw = k;
-            if (at) ltb = k;
+            if (aw) lw = maxlen;
+            if (at) ltb = maxlen;
+            lw = lw < maxlen ? lw : maxlen;
+            ltb = ltb < maxlen ? ltb : maxlen;
             if (lw >= MIN_MATCH && lw >= ltb) { best = lw; boff = p - cw; }
             else if (ltb >= MIN_MATCH) { best = ltb; boff = p - ct; }
         }
         // ---- greedy parse of the step: orbit of `carry` under p -> p + (match ? len : 1), by pointer doubling
         uint32_t J = (uint32_t)lane + (best ? best : 1u);
-        bool M = (uint32_t)lane == carry;
+        bool M = (uint32_t)lane >= carry;                      // no match anywhere in the step: everything from carry on is a literal
+        if (__any_sync(0xFFFFFFFFu, best != 0)) {
+            M = (uint32_t)lane == carry;
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const uint32_t bits = (M && J < 32) ? (1u << J) : 0u;
-            const uint32_t all = __reduce_or_sync(0xFFFFFFFFu, bits);
-            M = M || ((all >> lane) & 1u);
-            const uint32_t Jn = __shfl_sync(0xFFFFFFFFu, J, (int)(J & 31));
-            J = J < 32 ? Jn : J;
-        }
+            for (int r = 0; r < 5; r++) {
+                const uint32_t bits = (M && J < 32) ? (1u << J) : 0u;
+                const uint32_t all = __reduce_or_sync(0xFFFFFFFFu, bits);
+                M = M || ((all >> lane) & 1u);
+                const uint32_t Jn = __shfl_sync(0xFFFFFFFFu, J, (int)(J & 31));
+                J = J < 32 ? Jn : J;
+            }
+        } else J = 32;                                         // carry_out = 0
         const uint32_t carry_out = __shfl_sync(0xFFFFFFFFu, J, (int)carry) - 32u;
         const bool is_match = M && best != 0;
         const bool is_lit = M && best == 0 && p < len;
