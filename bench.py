@@ -413,6 +413,9 @@ def main():
                "sample": f"{sample} x 4 MiB entries x3 passes (oracle: libzstd + OpenSSL AES-NI + zlib crc32; 1 CRC thread + "
                          f"{ncpu} worker threads, reference extract dataflow)"}
 
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}
@@ -434,6 +437,15 @@ def main():
             "traffic": None, "stage_ms": stage_ms, "stage_share": {k: v / sum(stage_ms.values()) for k, v in stage_ms.items()},
             "step_algorithmic_GBps": step_alg / (ms_step * 1e-3) / 1e9, "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+    roof["algorithmic_bytes"] = alg[dom]
+    try:   # DRAM bytes of the dominant kernel per launch from the committed ncu --set full capture of this same configuration
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        k = tr["kernels"].get(dom + "_kernel")
+        if k and E == 1024:
+            roof["traffic"] = k["dram_read_bytes"] + k["dram_write_bytes"]
+            roof["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, one launch, same --entries)"
+    except Exception:
+        pass
     value = world * U / (ms_step * 1e-3) / 1e9
     line = {"metric": "extract_uncompressed_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
