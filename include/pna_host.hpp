@@ -139,6 +139,7 @@ int pnah_set_key(pnah_archive* a, const char* phsf, const uint8_t key[32]);
 int pnah_prepare(pnah_archive* a, int device, char* err, uint64_t errcap);
 uint32_t pnah_file_count(pnah_archive* a);
 int pnah_file_get(pnah_archive* a, uint32_t i, const char** name, uint64_t* size);
+int pnah_file_sizes(pnah_archive* a, uint64_t* sizes, int32_t* status /* may be NULL */);   /* bulk form of pnah_file_get */
 int pnah_extract_files(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                        uint64_t group_bytes, int verify, char* err, uint64_t errcap);
 int pnah_create(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs,

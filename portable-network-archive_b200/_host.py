@@ -12,7 +12,7 @@ from . import _ffi
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpna_host.so")
 EXPORTS = ["pnah_open", "pnah_close", "pnah_entry_count", "pnah_entry_get", "pnah_chunk_count", "pnah_set_key", "pnah_prepare",
-           "pnah_file_count", "pnah_file_get", "pnah_extract_files", "pnah_create", "pnah_create_bound"]
+           "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound"]
 
 
 class EntryInfo(C.Structure):
@@ -43,6 +43,7 @@ def lib():
         L.pnah_file_count.argtypes = [vp]
         L.pnah_file_count.restype = u32
         L.pnah_file_get.argtypes = [vp, u32, C.POINTER(C.c_char_p), C.POINTER(u64)]
+        L.pnah_file_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_int32)]
         L.pnah_extract_files.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(C.c_int32), C.c_int, C.c_int, u64, C.c_int, C.c_char_p, u64]
         L.pnah_create.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(u64), C.c_char_p, C.c_uint8, C.c_int32,
                                   C.c_uint8, C.c_uint8, C.c_char_p, C.c_char_p, u32, C.c_int, C.c_int, u64, vp, u64, C.POINTER(u64),
@@ -128,18 +129,20 @@ class HostArchive:
     def extract_files(self, out: np.ndarray | None = None, device=0, workers=3, group_bytes=256 << 20, verify=True):
         """Returns (out buffer, offsets, statuses).  `out`: optional (pinned) uint8 array of sum(sizes) bytes."""
         self.prepare(device)
-        files = self.files()
-        offs = np.zeros(len(files) + 1, dtype=np.uint64)
-        offs[1:] = np.cumsum([(s + 15) // 16 * 16 for _, s, _ in files], dtype=np.uint64)
+        nf = int(self.L.pnah_file_count(self.h))
+        sizes = np.zeros(max(nf, 1), dtype=np.uint64)
+        self.L.pnah_file_sizes(self.h, sizes.ctypes.data_as(C.POINTER(C.c_uint64)), None)
+        offs = np.zeros(nf + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum((sizes[:nf] + np.uint64(15)) // np.uint64(16) * np.uint64(16), dtype=np.uint64)
         if out is None:
             out = np.empty(int(offs[-1]) + 16, dtype=np.uint8)
-        st = (C.c_int32 * max(len(files), 1))()
+        st = (C.c_int32 * max(nf, 1))()
         err = C.create_string_buffer(512)
         rc = self.L.pnah_extract_files(self.h, out.ctypes.data, offs.ctypes.data_as(C.POINTER(C.c_uint64)), st, device, workers,
                                        group_bytes, int(verify), err, 512)
         if rc:
             raise HostError(rc, err.value.decode())
-        return out, offs, list(st)[:len(files)]
+        return out, offs, list(st)[:nf]
 
     def read_all(self, **kw):
         out, offs, st = self.extract_files(**kw)

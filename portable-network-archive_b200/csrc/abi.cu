@@ -643,8 +643,9 @@ static int launch_zstd_front(pna_plan* P, bool with_count) {   // scan .. resolv
 static int launch_zstd_seq(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
     if (P->h_ze.empty() || !P->n_blocks) return PNA_OK;
-    const uint32_t grid = std::min<uint32_t>((P->n_blocks + 31) / 32, (uint32_t)ctx->sm_count * 2);
-    zs::zstd_seq_kernel<<<grid, 32, zs::SEQ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_blocks.p, P->d_seq_order.p,
+    const uint32_t per_cta = zs::SEQ_LANES * zs::SEQ_WARPS;
+    const uint32_t grid = std::min<uint32_t>((P->n_blocks + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count);
+    zs::zstd_seq_kernel<<<grid, 32 * zs::SEQ_WARPS, zs::SEQ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_blocks.p, P->d_seq_order.p,
                                                                       P->d_counts.p, P->d_seq_base.p, P->d_seqs.p);
     LAUNCHED();
     return PNA_OK;
@@ -680,7 +681,7 @@ static int launch_inflate(pna_plan* P, int size_only) {
     pna_ctx* ctx = P->ctx;
     const uint32_t nd = (uint32_t)P->h_deflate.size();
     if (!nd) return PNA_OK;
-    inf::inflate_kernel<<<(nd + inf::INFLATE_CTA - 1) / inf::INFLATE_CTA, inf::INFLATE_CTA, sizeof(inf::Tables) * inf::INFLATE_CTA,
+    inf::inflate_kernel<<<(nd + inf::INFLATE_CTA - 1) / inf::INFLATE_CTA, 32 * inf::INFLATE_CTA, sizeof(inf::Tables) * inf::INFLATE_CTA,
                           ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_deflate.p, nd, P->d_out.p, size_only);
     LAUNCHED();
     return PNA_OK;
@@ -881,6 +882,16 @@ extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* st
     CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     uint64_t plain = 0;
+    // D2H: entries whose host buffers mirror the device layout (same distance between starts, inside the previous
+    // buffer's capacity) travel in ONE cudaMemcpyAsync -- a million small files must not mean a million copies
+    uint8_t* run_host = nullptr;
+    uint64_t run_dev = 0, run_len = 0;
+    auto flush_run = [&]() -> int {
+        if (run_len) CK(cudaMemcpyAsync(run_host, P->d_out.p + run_dev, run_len, cudaMemcpyDeviceToHost, ctx->stream));
+        run_len = 0;
+        return PNA_OK;
+    };
+    uint32_t prev = UINT32_MAX;
     for (uint32_t i = 0; i < P->n; i++) {
         const EntryRec& e = dev[i];
         int32_t st = e.status;
@@ -891,9 +902,27 @@ extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* st
         out[i].len = (st == ST_OK || st == ST_NOSPACE) ? len : 0;
         status[i] = st;
         if (st == ST_OK && len) {
-            CK(cudaMemcpyAsync(out[i].ptr, P->d_out.p + e.out_off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            bool merged = false;
+            if (run_len && prev != UINT32_MAX) {
+                const uint64_t d_host = (uint64_t)(out[i].ptr - out[prev].ptr), d_dev = e.out_off - dev[prev].out_off;
+                if (out[i].ptr > out[prev].ptr && d_host == d_dev && d_host <= out[prev].cap && run_dev + run_len <= e.out_off &&
+                    run_host + (e.out_off - run_dev) == out[i].ptr) {
+                    run_len = e.out_off - run_dev + len;
+                    merged = true;
+                }
+            }
+            if (!merged) {
+                int rc = flush_run();
+                if (rc) return rc;
+                run_host = out[i].ptr; run_dev = e.out_off; run_len = len;
+            }
+            prev = i;
             plain += len;
         }
+    }
+    {
+        int rc = flush_run();
+        if (rc) return rc;
     }
     P->plain_bytes = plain;
     CK(cudaStreamSynchronize(ctx->stream));

@@ -5,7 +5,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -249,7 +252,8 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
         }
     }
     std::atomic<size_t> next{0};
-    std::mutex err_mu;
+    const auto t_begin = std::chrono::steady_clock::now();
+    std::mutex err_mu, h2d_mu;
     std::string err_msg;
     int err_kind = 0;
     auto work = [&]() {
@@ -273,6 +277,7 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
                 }
                 pna_plan* plan = nullptr;
                 const bool top = refs_[G.lo].owner == 0;
+                const auto t0 = std::chrono::steady_clock::now();
                 if (verify && top && crange[g].second > crange[g].first) {
                     const uint32_t c0 = crange[g].first, c1 = crange[g].second, nc = c1 - c0;
                     std::vector<pna_span> spans(nc);
@@ -283,10 +288,22 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
                         const EntryInfo& e = entries_[refs_[G.lo + k].entry];
                         for (uint32_t c = e.chunk_begin; c < e.chunk_end; c++) owner[c - c0] = (int32_t)k;
                     }
+                    std::lock_guard<std::mutex> h2d(h2d_mu);   // one group's upload at a time: PCIe is the shared resource, and the
                     ck(L.ctx, pna_cuda_decode_plan_create_crc(L.ctx, descs.data(), m, spans.data(), expect.data(), owner.data(), nc, &plan), "plan_create_crc");
-                } else ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, descs.data(), m, &plan), "plan_create");
+                } else {                                        // next group's H2D then overlaps this group's kernels / D2H
+                    std::lock_guard<std::mutex> h2d(h2d_mu);
+                    ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, descs.data(), m, &plan), "plan_create");
+                }
+                const auto t1 = std::chrono::steady_clock::now();
                 int rc = pna_cuda_decode_plan_run(plan);
+                const auto t2 = std::chrono::steady_clock::now();
                 if (rc == PNA_OK) rc = pna_cuda_decode_plan_fetch(plan, bufs.data(), st.data());
+                if (getenv("PNA_HOST_TRACE")) {
+                    const auto t3 = std::chrono::steady_clock::now();
+                    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                    fprintf(stderr, "[pna_host] group %zu (%u entries): create(H2D) %.1f ms (from %.1f), run(launch) %.1f ms, fetch(wait+D2H) %.1f ms\n", g, m,
+                            ms(t0, t1), ms(t_begin, t0), ms(t1, t2), ms(t2, t3));
+                }
                 uint32_t broken = 0;
                 if (rc == PNA_OK && verify && top) rc = pna_cuda_plan_crc_results(plan, nullptr, &broken);
                 pna_cuda_plan_destroy(plan);
@@ -558,6 +575,11 @@ int pnah_file_get(pnah_archive* a, uint32_t i, const char** name, uint64_t* size
     if (i >= a->a.files().size()) return PNA_E_BAD_ARG;
     *name = a->a.files()[i].name.c_str(); *size = a->a.files()[i].size;
     return a->a.files()[i].status;
+}
+int pnah_file_sizes(pnah_archive* a, uint64_t* sizes, int32_t* status) {
+    const auto& f = a->a.files();
+    for (size_t i = 0; i < f.size(); i++) { sizes[i] = f[i].size; if (status) status[i] = f[i].status; }
+    return PNA_OK;
 }
 int pnah_extract_files(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                        uint64_t group_bytes, int verify, char* err, uint64_t errcap) {

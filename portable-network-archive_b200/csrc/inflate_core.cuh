@@ -39,6 +39,14 @@ struct Bits {
     int cnt;
     PNA_HD void init(const uint8_t* in, uint64_t len) { p = in; n = len; pos = 0; buf = 0; cnt = 0; }
     PNA_HD void fill(int need) {
+        if (cnt >= need) return;
+        if (cnt <= 32 && pos + 4 <= n) {   // four input bytes per refill: the loads are independent, one latency instead of four
+            const uint32_t b0 = p[pos], b1 = p[pos + 1], b2 = p[pos + 2], b3 = p[pos + 3];
+            buf |= (uint64_t)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24)) << cnt;
+            pos += 4;
+            cnt += 32;
+            if (cnt >= need) return;
+        }
         while (cnt < need) {
             if (pos < n) buf |= (uint64_t)p[pos] << cnt;   // zeros beyond the end; overrun() tells
             pos++;
@@ -236,7 +244,15 @@ PNA_HD int32_t inflate_zlib(const uint8_t* in, uint64_t n, uint8_t* out, uint64_
                 if (b.overrun()) PNA_INF_TRUNC();
                 if (dist > op) return ST_INVALID_INPUT;
                 if (op + len <= cap) {
-                    for (uint32_t k = 0; k < len; k++) PNA_INF_EMIT(out[op - dist]);
+                    uint32_t k = 0;
+                    if (dist >= 8) {   // eight source bytes are loaded before the first of them is stored: the loads overlap
+                        for (; k + 8 <= len; k += 8) {
+                            uint8_t t[8];
+                            for (int q = 0; q < 8; q++) t[q] = out[op - dist + q];
+                            for (int q = 0; q < 8; q++) PNA_INF_EMIT(t[q]);
+                        }
+                    }
+                    for (; k < len; k++) PNA_INF_EMIT(out[op - dist]);
                 } else {
                     for (uint32_t k = 0; k < len; k++) {
                         if (op < cap) PNA_INF_EMIT(out[op - dist]);

@@ -150,48 +150,58 @@ __global__ void __launch_bounds__(1024) zstd_order_kernel(const EntryRec* __rest
 // ------------------------------------------------------------------------------------------------
 // Sequence stage: ONE LANE per block.  The FSE chain (table lookup -> bit counts -> next state) is serial
 // per block, so throughput = blocks in flight / chain latency, and blocks in flight = shared memory /
-// table bytes.  16-bit cells (zstd_core.cuh Tab16) make a block's three tables 2.5 KB; a warp holds 32
-// blocks' tables interleaved by lane in 80 KB, two such warps are resident per SM.
-constexpr uint32_t SEQ_SMEM_BYTES = TAB16_TOTAL * 32 * sizeof(uint16_t);   // 81920
-__global__ void __launch_bounds__(32) zstd_seq_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, ZBlock* blocks,
-                                                      const uint32_t* __restrict__ order, uint32_t* counts,
-                                                      const uint64_t* __restrict__ seq_base_of_entry, SeqRec* __restrict__ seqs) {
-    extern __shared__ uint16_t stab[];
+// table bytes.  16-bit cells (zstd_core.cuh Tab16) make a block's three tables 2.5 KB: 88 blocks fill the
+// SM's 227 KB.  One CTA of 4 warps per SM (one warp per scheduler), 22 active lanes per warp, each warp's
+// 22 tables interleaved by lane; the warps take batches of 22 blocks independently (no CTA barrier).
+constexpr uint32_t SEQ_LANES = 22, SEQ_WARPS = 4;
+constexpr uint32_t SEQ_SMEM_BYTES = TAB16_TOTAL * SEQ_LANES * SEQ_WARPS * sizeof(uint16_t);   // 225280
+__global__ void __launch_bounds__(32 * SEQ_WARPS) zstd_seq_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, ZBlock* blocks,
+                                                                  const uint32_t* __restrict__ order, uint32_t* counts,
+                                                                  const uint64_t* __restrict__ seq_base_of_entry,
+                                                                  SeqRec* __restrict__ seqs) {
+    extern __shared__ uint16_t stab_all[];
     __shared__ uint32_t s_llb[36], s_mlb[53];
-    const int lane = threadIdx.x;
-    for (int c = lane; c < 36; c += 32) s_llb[c] = ll_base(c);
-    for (int c = lane; c < 53; c += 32) s_mlb[c] = ml_base(c);
-    __syncwarp();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < 36; c += blockDim.x) s_llb[c] = ll_base(c);
+    for (int c = threadIdx.x; c < 53; c += blockDim.x) s_mlb[c] = ml_base(c);
+    __syncthreads();
     const uint32_t n = counts[0];
     const uint32_t* words = reinterpret_cast<const uint32_t*>(buf);
-    const Tab16 tll{stab + TAB16_LL * 32 + lane, 32}, tml{stab + TAB16_ML * 32 + lane, 32}, tof{stab + TAB16_OF * 32 + lane, 32};
+    uint16_t* const stab = stab_all + (uint32_t)warp * TAB16_TOTAL * SEQ_LANES;
+    const bool active = (uint32_t)lane < SEQ_LANES;
+    const uint32_t l = active ? (uint32_t)lane : 0u;
+    const Tab16 tll{stab + TAB16_LL * SEQ_LANES + l, SEQ_LANES}, tml{stab + TAB16_ML * SEQ_LANES + l, SEQ_LANES},
+        tof{stab + TAB16_OF * SEQ_LANES + l, SEQ_LANES};
     for (;;) {
-        uint32_t batch = 0;
-        if (lane == 0) batch = atomicAdd(&counts[2], 1u);
-        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
-        if ((uint64_t)batch * 32 >= n) break;
-        const uint32_t k = batch * 32 + lane;
-        if (k < n) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&counts[2], SEQ_LANES);
+        first = __shfl_sync(0xFFFFFFFFu, first, 0);
+        if (first >= n) break;
+        const uint32_t k = first + (uint32_t)lane;
+        if (active && k < n) {
             const uint32_t bi = order[k];
             ZBlock& gb = blocks[bi];
-            ZBlock b = gb;
+            ZBlock b;                       // only the fields the decoder reads (the rest of the 200-byte record stays in HBM)
+            b.src = gb.src; b.bs_pos = gb.bs_pos; b.bs_len = gb.bs_len; b.nseq = gb.nseq; b.lit_regen = gb.lit_regen;
+            b.tsrc[0] = gb.tsrc[0]; b.tsrc[1] = gb.tsrc[1]; b.tsrc[2] = gb.tsrc[2];
+            const uint32_t entry = gb.entry;
             int16_t norm[64];
             uint16_t next_of[64];
             const int l0 = seq_tab16_for(buf, blocks, b, 0, tll, norm, next_of);
             const int l1 = seq_tab16_for(buf, blocks, b, 1, tof, norm, next_of);
             const int l2 = seq_tab16_for(buf, blocks, b, 2, tml, norm, next_of);
             int32_t st = ST_INVALID_DATA;
+            uint32_t esc_n = 0, esc_idx[SEQ_ESC_MAX], esc_ll[SEQ_ESC_MAX], esc_ml[SEQ_ESC_MAX];
             if (l0 >= 0 && l1 >= 0 && l2 >= 0) {
-                const uint64_t so = seq_base_of_entry[b.entry] + b.seq_off;
-                st = decode_sequences16(words, buf, b, tll, tof, tml, l0, l1, l2, s_llb, s_mlb, seqs + so, &b.esc_n, b.esc_idx,
-                                        b.esc_ll, b.esc_ml);
+                const uint64_t so = seq_base_of_entry[entry] + gb.seq_off;
+                st = decode_sequences16(words, buf, b, tll, tof, tml, l0, l1, l2, s_llb, s_mlb, seqs + so, &esc_n, esc_idx, esc_ll, esc_ml);
             }
             if (st == ST_OK) {
                 gb.out_size = b.out_size; gb.lit_used = b.lit_used;
                 gb.rep_out[0] = b.rep_out[0]; gb.rep_out[1] = b.rep_out[1]; gb.rep_out[2] = b.rep_out[2];
-                gb.esc_n = b.esc_n;
-                for (uint32_t q = 0; q < b.esc_n; q++) { gb.esc_idx[q] = b.esc_idx[q]; gb.esc_ll[q] = b.esc_ll[q]; gb.esc_ml[q] = b.esc_ml[q]; }
-            } else { gb.status = st; set_status(entries, b.entry, st); }
+                gb.esc_n = esc_n;
+                for (uint32_t q = 0; q < esc_n && q < (uint32_t)SEQ_ESC_MAX; q++) { gb.esc_idx[q] = esc_idx[q]; gb.esc_ll[q] = esc_ll[q]; gb.esc_ml[q] = esc_ml[q]; }
+            } else { gb.status = st; set_status(entries, entry, st); }
         }
         __syncwarp();
     }

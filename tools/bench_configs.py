@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""Secondary BASELINE.json configurations, measured with the same machinery as bench.py (not the driver's bench line):
+  cfg3  many small files (uniform 1..16384 B), zlib level 6 + Camellia-256-CBC          -> inflate + CBC + index-pass stress
+  cfg5  N x 4 MiB files in ONE solid zstd entry (inner STORE entries, 32 KiB SDATs)       -> single-stream decode vs per-entry
+  cfg1  log-normal file sizes, zstd 3, no encryption: create + extract                    -> the CPU-runnable case
+Prints one JSON line per configuration.  Inputs come from the oracle's encoders (reference dataflow); outputs are compared
+with the source files."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import struct
+import sys
+import time
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import corpus  # noqa: E402
+import bench  # noqa: E402
+
+
+def _small(i_n):
+    i, n = i_n
+    return corpus.make_file(10_000_000 + i, n)
+
+
+def oracle_encode(files, comp, level, enc, mode, key, threads, seed=7):
+    import pna_oracle as O
+    L = O.lib()
+    n = len(files)
+    jobs = (O.EncJob * n)()
+    outs = []
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for j, f in enumerate(files):
+        cap = L.pna_oracle_encode_bound(comp, len(f)) + 64
+        o = C.create_string_buffer(cap)
+        outs.append(o)
+        jobs[j].plain = C.cast(C.c_char_p(f), C.c_void_p)
+        jobs[j].len = len(f)
+        jobs[j].compression, jobs[j].encryption, jobs[j].cipher_mode, jobs[j].level = comp, enc, mode, level
+        C.memmove(jobs[j].key, key, 32)
+        C.memmove(jobs[j].iv, rng.bytes(16), 16)
+        jobs[j].out = C.cast(o, C.c_void_p)
+        jobs[j].cap = cap
+    L.pna_oracle_encode_batch_mt(jobs, n, threads, None)
+    assert all(jobs[j].status == 0 for j in range(n))
+    return [outs[j].raw[:jobs[j].out_len] for j in range(n)]
+
+
+def cpu_decode_time(streams, sizes, comp, enc, mode, key, threads):
+    import pna_oracle as O
+    L = O.lib()
+    n = len(streams)
+    jobs = (O.Job * n)()
+    outs = []
+    for j, (s, u) in enumerate(zip(streams, sizes)):
+        o = C.create_string_buffer(max(int(u), 1))
+        outs.append(o)
+        jobs[j].stream = C.cast(C.c_char_p(s), C.c_void_p)
+        jobs[j].len = len(s)
+        jobs[j].compression, jobs[j].encryption, jobs[j].cipher_mode = comp, enc, mode
+        C.memmove(jobs[j].key, key, 32)
+        jobs[j].out = C.cast(o, C.c_void_p)
+        jobs[j].cap = int(u)
+    crc = (C.c_uint32 * n)()
+    L.pna_oracle_decode_batch_mt(jobs, n, threads, 1, crc)
+    t0 = time.perf_counter()
+    L.pna_oracle_decode_batch_mt(jobs, n, threads, 1, crc)
+    return time.perf_counter() - t0
+
+
+def chunk(parts, ty, data):
+    parts.append(struct.pack(">I", len(data)) + ty)
+    parts.append(data)
+    parts.append(struct.pack(">I", zlib.crc32(data, zlib.crc32(ty))))
+
+
+def archive_of(entries, phsf, into):
+    """entries: (name, header6, raw_size, stream, iv_len) -> FHED,fSIZ,[PHSF,FDAT(iv)],FDAT(body),FEND"""
+    parts = [b"\x89PNA\r\n\x1a\n"]
+    chunk(parts, b"AHED", bytes(8))
+    for name, hdr, n, s, iv_len in entries:
+        chunk(parts, b"FHED", hdr + name.encode())
+        chunk(parts, b"fSIZ", int(n).to_bytes(8, "big").lstrip(b"\0"))
+        if iv_len:
+            chunk(parts, b"PHSF", phsf.encode())
+            chunk(parts, b"FDAT", s[:iv_len])
+        if len(s) > iv_len:
+            chunk(parts, b"FDAT", s[iv_len:])
+        chunk(parts, b"FEND", b"")
+    chunk(parts, b"AEND", b"")
+    total = sum(len(p) for p in parts)
+    buf = into(total)
+    pos = 0
+    for p in parts:
+        buf[pos:pos + len(p)] = np.frombuffer(p, dtype=np.uint8)
+        pos += len(p)
+    return buf
+
+
+def timed_extract(host, ctx, archive_buf, phsf, key, U, nfiles, reps=3, workers=1):
+    import torch
+    out = ctx.pinned(U + 16 * nfiles + 64)
+    ts, t_index = [], []
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        ha = host.HostArchive(archive_buf)
+        t1 = time.perf_counter()
+        if phsf:
+            ha.set_key(phsf, key)
+        _, offs, st = ha.extract_files(out=out, device=0, workers=workers, group_bytes=4096 << 20, verify=True)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+        t_index.append(t1 - t0)
+        files = ha.files() if nfiles <= 4096 else None
+        ha.close()
+    return min(ts[1:]), min(t_index[1:]), out, offs, st, files
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg3-files", type=int, default=131072)
+    ap.add_argument("--cfg5-files", type=int, default=32)
+    ap.add_argument("--cfg1-files", type=int, default=2500)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    import multiprocessing as mp
+    pna = importlib.import_module("portable-network-archive_b200")
+    host = importlib.import_module("portable-network-archive_b200._host")
+    ctx = pna.Context(0)
+    ncpu = os.cpu_count() or 1
+    key = bytes(range(32))
+    opts = pna.WriteOptions(compression=1, encryption=2, cipher_mode=0, password=b"pw", kdf_params={"i": 1000})
+
+    if args.only in ("", "cfg3"):
+        n = args.cfg3_files
+        rng = np.random.Generator(np.random.PCG64(3))
+        sizes = [int(x) for x in rng.integers(1, 16385, n)]
+        with mp.get_context("fork").Pool(min(ncpu, 64)) as pool:
+            files = pool.map(_small, list(enumerate(sizes)), chunksize=256)
+        streams = oracle_encode(files, 1, 6, 2, 0, key, ncpu)
+        U, Cb = sum(sizes), sum(len(s) for s in streams)
+        buf = archive_of([(f"s/{i:07d}", bytes([0, 0, 0, 1, 2, 0]), sizes[i], streams[i], 16) for i in range(n)], opts.phsf, ctx.pinned)
+        # kernel-only through one plan
+        ha = pna.Archive.read_header(buf, ctx, verify=False) if n <= 20000 else None
+        dt, t_index, out, offs, st, flist = timed_extract(host, ctx, buf, opts.phsf, key, U, n)
+        assert st == [0] * n
+        for k in range(0, n, max(1, n // 64)):
+            assert out[int(offs[k]):int(offs[k]) + sizes[k]].tobytes() == files[k]
+        cpu_dt = cpu_decode_time(streams[:min(n, 65536)], sizes[:min(n, 65536)], 1, 2, 0, key, ncpu)
+        print(json.dumps({"config": "cfg3", "files": n, "plain_bytes": U, "stream_bytes": Cb, "chunks": 6 * n + 2,
+                          "codec": "zlib-6 + camellia-256-cbc", "e2e_GBps": U / dt / 1e9, "e2e_ms": dt * 1e3, "index_pass_ms": t_index * 1e3,
+                          "path": "pna::Archive (C++ host) index + extract_files, pinned buffers, CRC verified on GPU",
+                          "cpu_baseline_GBps": sum(sizes[:min(n, 65536)]) / cpu_dt / 1e9, "cpu_cores": ncpu}), flush=True)
+        del out, buf, files, streams
+
+    if args.only in ("", "cfg5"):
+        import pna_oracle as O
+        n = args.cfg5_files
+        files = [corpus.make_file(i, 4 << 20) for i in range(n)]
+        inner = []
+        for i, f in enumerate(files):
+            chunk(inner, b"FHED", bytes([0, 0, 0, 0, 0, 0]) + f"solid/{i:05d}.bin".encode())
+            chunk(inner, b"fSIZ", len(f).to_bytes(8, "big").lstrip(b"\0"))
+            for o in range(0, len(f), 1 << 20):
+                chunk(inner, b"FDAT", f[o:o + (1 << 20)])
+            chunk(inner, b"FEND", b"")
+        inner = b"".join(inner)
+        stream = O.compress(2, inner, 3)          # one zstd frame over the whole inner archive (window 2 MiB)
+        parts = [b"\x89PNA\r\n\x1a\n"]
+        chunk(parts, b"AHED", bytes(8))
+        chunk(parts, b"SHED", bytes([0, 0, 2, 0, 0]))
+        for o in range(0, len(stream), 32768):
+            chunk(parts, b"SDAT", stream[o:o + 32768])
+        chunk(parts, b"SEND", b"")
+        chunk(parts, b"AEND", b"")
+        blob = b"".join(parts)
+        buf = ctx.pinned(len(blob))
+        buf[:] = np.frombuffer(blob, dtype=np.uint8)
+        U = sum(len(f) for f in files)
+        dt, t_index, out, offs, st, flist = timed_extract(host, ctx, buf, None, key, U, n, reps=2)
+        assert st == [0] * n and [nm for nm, _, _ in flist] == [f"solid/{i:05d}.bin" for i in range(n)]
+        for k in range(n):
+            assert out[int(offs[k]):int(offs[k]) + len(files[k])].tobytes() == files[k]
+        # the same corpus as per-entry archive
+        streams = oracle_encode(files, 2, 3, 0, 0, key, ncpu)
+        buf2 = archive_of([(f"e/{i:05d}", bytes([0, 0, 0, 2, 0, 0]), len(files[i]), streams[i], 0) for i in range(n)], "", ctx.pinned)
+        dt2, _, out2, offs2, st2, _ = timed_extract(host, ctx, buf2, None, key, U, n, reps=2)
+        assert st2 == [0] * n
+        t0 = time.perf_counter()
+        assert O.decompress(2, stream) == inner
+        cpu_solid = time.perf_counter() - t0
+        print(json.dumps({"config": "cfg5", "files": n, "plain_bytes": U, "solid_stream_bytes": len(stream), "sdat_chunks": (len(stream) + 32767) // 32768,
+                          "solid_e2e_GBps": U / dt / 1e9, "solid_e2e_ms": dt * 1e3, "per_entry_e2e_GBps": U / dt2 / 1e9, "per_entry_e2e_ms": dt2 * 1e3,
+                          "note": "a solid entry is ONE zstd frame: the sequence stage is block-parallel (lane per block), the LZ stage runs "
+                                  "the frame on one warp; includes the sizing pass (no fSIZ on solid streams) and the inner chunk CRC check",
+                          "cpu_baseline_solid_GBps": U / cpu_solid / 1e9, "cpu_cores_solid": 1}), flush=True)
+        del out, out2
+
+    if args.only in ("", "cfg1"):
+        n = args.cfg1_files
+        sizes = [int(s) for s in corpus.lognormal_sizes(n, n * 107374)]     # 10,000 files sum to 1 GiB in the full config
+        with mp.get_context("fork").Pool(min(ncpu, 64)) as pool:
+            files = pool.map(_small, list(enumerate(sizes)), chunksize=32)
+        U = sum(sizes)
+        names = [f"c/{i:06d}" for i in range(n)]
+        plain = ctx.pinned(U + 16)
+        views, pos = [], 0
+        for f in files:
+            plain[pos:pos + len(f)] = np.frombuffer(f, dtype=np.uint8)
+            views.append(plain[pos:pos + len(f)])
+            pos += len(f)
+        arch = ctx.pinned(int(U * 1.05) + (8 << 20))
+        import torch
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            blob = host.create_archive(list(zip(names, views)), compression=2, level=3, max_chunk_size=0, device=0, workers=1,
+                                       group_bytes=4096 << 20, out=arch)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        import pna_oracle as O
+        got = list(O.extract_all(blob.tobytes(), None))
+        assert [d for _, d in got] == files, "GPU-created archive must extract bit-exactly with the reference reader"
+        dt, t_index, out, offs, st, _ = timed_extract(host, ctx, blob, None, key, U, n)
+        assert st == [0] * n
+        t0 = time.perf_counter()
+        ref_streams = oracle_encode(files, 2, 3, 0, 0, key, ncpu)
+        cpu_create = time.perf_counter() - t0
+        cpu_dt = cpu_decode_time(ref_streams, sizes, 2, 0, 0, key, ncpu)
+        c_ref = sum(len(s) for s in ref_streams)
+        print(json.dumps({"config": "cfg1", "files": n, "plain_bytes": U, "create_e2e_GBps": U / min(ts[1:]) / 1e9, "extract_e2e_GBps": U / dt / 1e9,
+                          "archive_bytes": int(blob.size), "c_gpu_over_c_ref": float(blob.size) / c_ref,
+                          "checked": "oracle.extract_all(GPU-created archive) == source files",
+                          "cpu_create_GBps": U / cpu_create / 1e9, "cpu_extract_GBps": U / cpu_dt / 1e9, "cpu_cores": ncpu}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
