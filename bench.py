@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--entries", type=int, default=1024, help="4 MiB files per GPU (cfg2: 8192 over 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--workers", type=int, default=2, help="host worker threads / contexts of the end-to-end path")
-    ap.add_argument("--group-mib", type=int, default=4096, help="compressed MiB per pipelined entry group (end-to-end path)")
+    ap.add_argument("--group-mib", type=int, default=512, help="compressed MiB per pipelined entry group (end-to-end path)")
     ap.add_argument("--create", type=int, default=1, help="also measure the create path (GPU zstd + AES-CTR + CRC) on the same files")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -454,7 +454,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": world * U / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(archive_buf.size),
                     "d2h_bytes_per_step": int(U), "ms_per_step": e2e_s * 1e3,
-                    "path": f"pna::Archive::read_header_from_slice + extract_files (C++ host layer, {args.workers} contexts, {args.group_mib} MiB groups): index pass, H2D, chunk CRC check, decrypt, decode, D2H to pinned buffers; host clock"},
+                    "path": f"pna::Archive::read_header_from_slice + extract_files (C++ host layer, {args.workers} worker threads x 2 contexts, {args.group_mib} MiB entry groups software-pipelined create->run->fetch): index pass, H2D, chunk CRC check, decrypt, decode, D2H to pinned buffers; host clock"},
             "roofline": roof}
     if cpu:
         line["cpu_baseline"] = cpu

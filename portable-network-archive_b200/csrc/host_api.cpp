@@ -253,69 +253,97 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
     }
     std::atomic<size_t> next{0};
     const auto t_begin = std::chrono::steady_clock::now();
+    const bool trace = getenv("PNA_HOST_TRACE") != nullptr;
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - t_begin).count(); };
     std::mutex err_mu, h2d_mu;
     std::string err_msg;
     int err_kind = 0;
+    // One group in flight per context; every worker thread keeps TWO contexts and software-pipelines its groups:
+    //   create(g) [H2D]  ->  run(g) [kernels, asynchronous]  ->  fetch(g-1) [D2H of the previous group]
+    // so the upload and the kernels of group g overlap the download of group g-1 (PCIe is full duplex, kernels are
+    // on their own streams).  Everything a stage needs lives in Stage, which stays alive until its fetch.
+    struct Stage {
+        size_t g = 0;
+        uint32_t m = 0;
+        bool top = false;
+        pna_plan* plan = nullptr;
+        std::vector<pna_decode_desc> descs;
+        std::vector<pna_buf> bufs;
+        std::vector<int32_t> st, pre;
+        std::vector<pna_span> spans;
+        std::vector<uint32_t> expect;
+        std::vector<int32_t> owner;
+    };
+    auto issue = [&](CtxLease& L, Stage& S, size_t g) {
+        const Group G = groups[g];
+        const uint32_t m = (uint32_t)(G.hi - G.lo);
+        S.g = g; S.m = m; S.plan = nullptr;
+        S.descs.assign(m, pna_decode_desc{}); S.bufs.resize(m); S.st.assign(m, 0); S.pre.assign(m, 0);
+        for (uint32_t k = 0; k < m; k++) {
+            const FileRef r = refs_[G.lo + k];
+            const EntryInfo& e = r.owner ? inner_[r.owner - 1].entries[r.entry] : entries_[r.entry];
+            S.pre[k] = files_[G.lo + k].status ? files_[G.lo + k].status : fill_desc(e, opt, S.descs[k]);
+            if (S.pre[k] != PNA_OK) { memset(&S.descs[k], 0, sizeof S.descs[k]); S.descs[k].raw_size_hint = 0; }
+            else S.descs[k].raw_size_hint = files_[G.lo + k].size;
+            S.bufs[k] = pna_buf{out + offsets[G.lo + k], offsets[G.lo + k + 1] - offsets[G.lo + k], 0};
+        }
+        S.top = refs_[G.lo].owner == 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        {
+            std::lock_guard<std::mutex> h2d(h2d_mu);   // one upload at a time: PCIe is the shared resource
+            if (verify && S.top && crange[g].second > crange[g].first) {
+                const uint32_t c0 = crange[g].first, c1 = crange[g].second, nc = c1 - c0;
+                S.spans.resize(nc); S.expect.resize(nc); S.owner.assign(nc, -1);
+                for (uint32_t c = 0; c < nc; c++) { S.spans[c] = {buf_ + chunks_[c0 + c].off - 4, (uint64_t)chunks_[c0 + c].len + 4}; S.expect[c] = chunks_[c0 + c].crc; }
+                for (uint32_t k = 0; k < m; k++) {
+                    const EntryInfo& e = entries_[refs_[G.lo + k].entry];
+                    for (uint32_t c = e.chunk_begin; c < e.chunk_end; c++) S.owner[c - c0] = (int32_t)k;
+                }
+                ck(L.ctx, pna_cuda_decode_plan_create_crc(L.ctx, S.descs.data(), m, S.spans.data(), S.expect.data(), S.owner.data(), nc, &S.plan), "plan_create_crc");
+            } else ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, S.descs.data(), m, &S.plan), "plan_create");
+        }
+        const auto t1 = std::chrono::steady_clock::now();
+        const int rc = pna_cuda_decode_plan_run(S.plan);
+        if (rc != PNA_OK) { pna_cuda_plan_destroy(S.plan); S.plan = nullptr; ck(L.ctx, rc, "decode_plan_run"); }
+        if (trace) fprintf(stderr, "[pna_host] group %zu (%u entries): create/H2D %.1f-%.1f ms, run/launch -%.1f ms\n", g, m, ms_since(t0), ms_since(t1),
+                           ms_since(std::chrono::steady_clock::now()));
+    };
+    auto collect = [&](CtxLease& L, Stage& S) {
+        if (!S.plan) return;
+        const Group G = groups[S.g];
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = pna_cuda_decode_plan_fetch(S.plan, S.bufs.data(), S.st.data());
+        uint32_t broken = 0;
+        if (rc == PNA_OK && verify && S.top) rc = pna_cuda_plan_crc_results(S.plan, nullptr, &broken);
+        pna_cuda_plan_destroy(S.plan);
+        S.plan = nullptr;
+        if (trace) fprintf(stderr, "[pna_host] group %zu: fetch/wait+D2H %.1f-%.1f ms\n", S.g, ms_since(t0), ms_since(std::chrono::steady_clock::now()));
+        ck(L.ctx, rc, "decode plan");
+        bool any_entry_broken = false;
+        for (uint32_t k = 0; k < S.m; k++) {
+            status[G.lo + k] = S.pre[k] != PNA_OK ? S.pre[k] : S.st[k];
+            if (S.st[k] == PNA_E_INVALID_DATA) any_entry_broken = true;
+        }
+        if (broken && !any_entry_broken) throw Error(PNA_E_INVALID_DATA, "broken chunk");   // an archive-level / non-file chunk
+    };
     auto work = [&]() {
+        Stage stage[2];
         try {
-            CtxLease L(device);
+            CtxLease L0(device), L1(device);
+            CtxLease* L[2] = {&L0, &L1};
+            int cur = 0;
+            bool have_prev = false;
             for (;;) {
                 const size_t g = next.fetch_add(1);
                 if (g >= groups.size()) break;
-                const Group G = groups[g];
-                const uint32_t m = (uint32_t)(G.hi - G.lo);
-                std::vector<pna_decode_desc> descs(m);
-                std::vector<pna_buf> bufs(m);
-                std::vector<int32_t> st(m, 0), pre(m, 0);
-                for (uint32_t k = 0; k < m; k++) {
-                    const FileRef r = refs_[G.lo + k];
-                    const EntryInfo& e = r.owner ? inner_[r.owner - 1].entries[r.entry] : entries_[r.entry];
-                    pre[k] = files_[G.lo + k].status ? files_[G.lo + k].status : fill_desc(e, opt, descs[k]);
-                    if (pre[k] != PNA_OK) { memset(&descs[k], 0, sizeof descs[k]); descs[k].raw_size_hint = 0; }
-                    else descs[k].raw_size_hint = files_[G.lo + k].size;
-                    bufs[k] = pna_buf{out + offsets[G.lo + k], offsets[G.lo + k + 1] - offsets[G.lo + k], 0};
-                }
-                pna_plan* plan = nullptr;
-                const bool top = refs_[G.lo].owner == 0;
-                const auto t0 = std::chrono::steady_clock::now();
-                if (verify && top && crange[g].second > crange[g].first) {
-                    const uint32_t c0 = crange[g].first, c1 = crange[g].second, nc = c1 - c0;
-                    std::vector<pna_span> spans(nc);
-                    std::vector<uint32_t> expect(nc);
-                    std::vector<int32_t> owner(nc, -1);
-                    for (uint32_t c = 0; c < nc; c++) { spans[c] = {buf_ + chunks_[c0 + c].off - 4, (uint64_t)chunks_[c0 + c].len + 4}; expect[c] = chunks_[c0 + c].crc; }
-                    for (uint32_t k = 0; k < m; k++) {
-                        const EntryInfo& e = entries_[refs_[G.lo + k].entry];
-                        for (uint32_t c = e.chunk_begin; c < e.chunk_end; c++) owner[c - c0] = (int32_t)k;
-                    }
-                    std::lock_guard<std::mutex> h2d(h2d_mu);   // one group's upload at a time: PCIe is the shared resource, and the
-                    ck(L.ctx, pna_cuda_decode_plan_create_crc(L.ctx, descs.data(), m, spans.data(), expect.data(), owner.data(), nc, &plan), "plan_create_crc");
-                } else {                                        // next group's H2D then overlaps this group's kernels / D2H
-                    std::lock_guard<std::mutex> h2d(h2d_mu);
-                    ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, descs.data(), m, &plan), "plan_create");
-                }
-                const auto t1 = std::chrono::steady_clock::now();
-                int rc = pna_cuda_decode_plan_run(plan);
-                const auto t2 = std::chrono::steady_clock::now();
-                if (rc == PNA_OK) rc = pna_cuda_decode_plan_fetch(plan, bufs.data(), st.data());
-                if (getenv("PNA_HOST_TRACE")) {
-                    const auto t3 = std::chrono::steady_clock::now();
-                    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-                    fprintf(stderr, "[pna_host] group %zu (%u entries): create(H2D) %.1f ms (from %.1f), run(launch) %.1f ms, fetch(wait+D2H) %.1f ms\n", g, m,
-                            ms(t0, t1), ms(t_begin, t0), ms(t1, t2), ms(t2, t3));
-                }
-                uint32_t broken = 0;
-                if (rc == PNA_OK && verify && top) rc = pna_cuda_plan_crc_results(plan, nullptr, &broken);
-                pna_cuda_plan_destroy(plan);
-                ck(L.ctx, rc, "decode plan");
-                bool any_entry_broken = false;
-                for (uint32_t k = 0; k < m; k++) {
-                    status[G.lo + k] = pre[k] != PNA_OK ? pre[k] : st[k];
-                    if (st[k] == PNA_E_INVALID_DATA) any_entry_broken = true;
-                }
-                if (broken && !any_entry_broken) throw Error(PNA_E_INVALID_DATA, "broken chunk");   // an archive-level / non-file chunk
+                issue(*L[cur], stage[cur], g);
+                if (have_prev) collect(*L[cur ^ 1], stage[cur ^ 1]);
+                have_prev = true;
+                cur ^= 1;
             }
+            if (have_prev) collect(*L[cur ^ 1], stage[cur ^ 1]);
         } catch (const Error& e) {
+            for (auto& S : stage) if (S.plan) { pna_cuda_plan_destroy(S.plan); S.plan = nullptr; }
             std::lock_guard<std::mutex> g(err_mu);
             if (err_msg.empty()) { err_msg = e.what(); err_kind = e.kind; }
         }
