@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -190,7 +191,7 @@ struct pna_plan {
     DevArr<Segment> d_segs;
     DevArr<DevKeys> d_keys;
     DevArr<CipherTile> d_tiles[5];
-    DevArr<uint32_t> d_deflate, d_seq_order, d_lit_order, d_counts;
+    DevArr<uint32_t> d_deflate, d_seq_order, d_lit_order, d_counts, d_lz_order;
     DevArr<zs::SeqRec> d_seqs;
     DevArr<zs::ZEntry> d_ze;
     DevArr<zs::ZBlock> d_blocks;
@@ -218,7 +219,7 @@ struct pna_plan {
         d_buf.release(); d_out.release(); d_lits.release(); d_entries.release(); d_entries_init.release();
         d_segs.release(); d_keys.release();
         for (auto& t : d_tiles) t.release();
-        d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_ze.release(); d_blocks.release();
+        d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
         if (enc) enc::destroy(enc);
     }
@@ -276,7 +277,8 @@ extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::SEQ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LIT_SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(zs::zstd_lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LZ_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(zs::zstd_lz_kernel<zs::LzSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LzSmall::BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(zs::zstd_lz_kernel<zs::LzBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LzBig::BYTES) == cudaSuccess;
     ok = ok && enc::init_attributes();
     if (!ok) { pna_cuda_destroy(ctx); return PNA_E_CUDA; }
     *out = ctx;
@@ -671,9 +673,16 @@ static int launch_zstd_lz(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
     const uint32_t nz = (uint32_t)P->h_ze.size();
     if (!nz) return PNA_OK;
-    const uint32_t grid = std::min<uint32_t>((nz + zs::LZ_WARPS - 1) / zs::LZ_WARPS, (uint32_t)ctx->sm_count);
-    zs::zstd_lz_kernel<<<grid, 32 * zs::LZ_WARPS, zs::LZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p,
-                                                                                   P->d_lits.p, P->d_seqs.p, P->d_out.p, P->d_counts.p);
+    // one CTA per entry, longest streams first.  Fewer entries than half the SMs (a solid archive is ONE frame): the
+    // 32-warp variant with the 128 KiB window; otherwise 4 warps per entry, 7 entries per SM.
+    const char* force = getenv("PNA_LZ_VARIANT");
+    const bool big = force ? force[0] == 'b' : nz * 2 <= (uint32_t)ctx->sm_count;
+    if (big)
+        zs::zstd_lz_kernel<zs::LzBig><<<nz, zs::LzBig::T, zs::LzBig::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_lz_order.p, nz,
+                                                                                            P->d_blocks.p, P->d_lits.p, P->d_seqs.p, P->d_out.p);
+    else
+        zs::zstd_lz_kernel<zs::LzSmall><<<nz, zs::LzSmall::T, zs::LzSmall::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_lz_order.p, nz,
+                                                                                                P->d_blocks.p, P->d_lits.p, P->d_seqs.p, P->d_out.p);
     LAUNCHED();
     return PNA_OK;
 }
@@ -708,6 +717,13 @@ static int decode_prepare(pna_plan* P) {
     if (nz) {
         CK(P->d_ze.reserve(nz));
         CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
+        // LZ stage order: longest compressed streams first (one CTA per entry, dispatched in grid order)
+        std::vector<uint32_t> lz_order(nz);
+        for (uint32_t i = 0; i < nz; i++) lz_order[i] = i;
+        std::stable_sort(lz_order.begin(), lz_order.end(), [&](uint32_t a, uint32_t b) {
+            return P->h_entries[P->h_ze[a].entry].comp_len > P->h_entries[P->h_ze[b].entry].comp_len; });
+        CK(P->d_lz_order.reserve(nz));
+        CK(cudaMemcpyAsync(P->d_lz_order.p, lz_order.data(), nz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = launch_zstd_front(P, true))) return rc;
         CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

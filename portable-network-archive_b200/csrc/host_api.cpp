@@ -315,6 +315,13 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
         int rc = pna_cuda_decode_plan_fetch(S.plan, S.bufs.data(), S.st.data());
         uint32_t broken = 0;
         if (rc == PNA_OK && verify && S.top) rc = pna_cuda_plan_crc_results(S.plan, nullptr, &broken);
+        if (trace) {
+            float ms[16] = {0};
+            const int ns = pna_cuda_plan_stage_ms(S.plan, ms, 16);
+            fprintf(stderr, "[pna_host] group %zu stages:", S.g);
+            for (int q = 0; q < ns; q++) fprintf(stderr, " %s=%.2f", pna_cuda_stage_name((uint32_t)q), ms[q]);
+            fprintf(stderr, "\n");
+        }
         pna_cuda_plan_destroy(S.plan);
         S.plan = nullptr;
         if (trace) fprintf(stderr, "[pna_host] group %zu: fetch/wait+D2H %.1f-%.1f ms\n", S.g, ms_since(t0), ms_since(std::chrono::steady_clock::now()));

@@ -45,10 +45,12 @@ struct EncEntry {
     uint8_t iv[16];
 };
 
-constexpr int ENC_WARPS = 5;
+constexpr int ENC_WARPS = 9;          // 9 warps x 8 KB of hash table per CTA, 3 CTAs per SM: 27 segments in flight per SM
 constexpr int HLOG = 12;
+// Only the hash table lives in shared memory.  The segment itself is read straight from HBM through L1/L2 (the step's own
+// 32 positions are one coalesced row, candidates are sector reads that mostly hit L2): staging the 32 KiB segment in
+// shared memory capped the kernel at 5 warps per SM, and the matcher is latency-bound -- warps in flight are what counts.
 struct MatchSmem {
-    uint8_t data[SEG + 272];       // segment + zero tail (compare loops may look MAX_MATCH past a position)
     uint16_t table[1 << HLOG];
 };
 constexpr uint32_t MATCH_SMEM_BYTES = (uint32_t)sizeof(MatchSmem) * ENC_WARPS;
@@ -63,49 +65,51 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
     MatchSmem* const S = reinterpret_cast<MatchSmem*>(match_smem_raw) + (threadIdx.x >> 5);
     const SegRec sr = segs[s];
     const uint32_t len = sr.len;
-    // ---- load the segment (16-byte rows), zero the tail, clear the table, Adler partial sums on the way
+    // ---- clear the table; Adler partial sums over the segment (16-byte rows, coalesced)
     uint64_t ad_a = 0, ad_b = 0;
     {
         const uint4* src = reinterpret_cast<const uint4*>(work_ro + sr.plain_off);
         const uint32_t rows = (len + 15) / 16;
-        for (uint32_t i = lane; i < (SEG + 272) / 16; i += 32) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (i < rows) {
-                v = src[i];
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                uint32_t keep[4];
+        for (uint32_t i = lane; i < rows; i += 32) {
+            const uint4 v = __ldg(src + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t p0 = i * 16 + 4 * k;
-                    uint32_t m = p0 + 4 <= len ? 0xFFFFFFFFu : p0 >= len ? 0u : (0xFFFFFFFFu >> (8 * (4 - (len - p0))));
-                    keep[k] = w[k] & m;
+            for (int k = 0; k < 4; k++) {
+                const uint32_t p0 = i * 16 + 4 * k;
+                const uint32_t m = p0 + 4 <= len ? 0xFFFFFFFFu : p0 >= len ? 0u : (0xFFFFFFFFu >> (8 * (4 - (len - p0))));
+                const uint32_t keep = w[k] & m;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const uint32_t byte = (keep[k] >> (8 * b)) & 0xFF;
-                        const uint32_t p = p0 + b;
-                        ad_a += byte;
-                        if (p < len) ad_b += (uint64_t)(len - p) * byte;
-                    }
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t byte = (keep >> (8 * b)) & 0xFF;
+                    const uint32_t p = p0 + b;
+                    ad_a += byte;
+                    if (p < len) ad_b += (uint64_t)(len - p) * byte;
                 }
-                v = make_uint4(keep[0], keep[1], keep[2], keep[3]);
             }
-            reinterpret_cast<uint4*>(S->data)[i] = v;
         }
         for (uint32_t i = lane; i < (1u << HLOG) * 2 / 16; i += 32) reinterpret_cast<uint4*>(S->table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { ad_a += __shfl_xor_sync(0xFFFFFFFFu, ad_a, o); ad_b += __shfl_xor_sync(0xFFFFFFFFu, ad_b, o); }
     }
     __syncwarp();
-    const uint8_t* const d = S->data;
+    // the plain region is followed by the literal region of the same arena, so reads a few hundred bytes past the
+    // segment stay inside the allocation; every length is clamped to the segment (maxlen)
+    const uint8_t* const d = work_ro + sr.plain_off;   // 16-byte aligned
+    auto ld32 = [&](uint32_t pos) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(d + (pos & ~3u));
+        return __funnelshift_r(__ldg(q), __ldg(q + 1), (pos & 3u) * 8u);
+    };
     Seq* const sq = seqs + sr.seq_off;
     uint8_t* const lits = work + sr.lit_off;
     uint32_t nseq = 0, nlit = 0, lit_at_last = 0;   // literals emitted before the last match
     uint32_t carry = 0;                              // first position of the next step that is not covered by a match
     const uint32_t lt = (1u << lane) - 1u;
+    uint32_t vn = ld32((uint32_t)lane);
     for (uint32_t base = 0; base < len; base += 32) {
         const uint32_t p = base + lane;
         const bool valid = p + 4 <= len;
-        const uint32_t v = (uint32_t)d[p] | ((uint32_t)d[p + 1] << 8) | ((uint32_t)d[p + 2] << 16) | ((uint32_t)d[p + 3] << 24);
+        const uint32_t v = vn;                                 // the four bytes at p
+        if (base + 32 < len) vn = ld32(p + 32);                // the next step's row, in flight during this step
         const uint32_t h = (v * 2654435761u) >> (32 - HLOG);
         const uint32_t ct = valid ? S->table[h] : 0xFFFFu;
         // one MATCH on the hash groups the lanes: the nearest lower lane of my group is the in-step candidate when its four
@@ -125,15 +129,18 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
             const uint32_t maxlen = len - p < MAX_MATCH ? len - p : MAX_MATCH;
             bool aw = cw != 0xFFFFu, at = ct != 0xFFFFu && ct != cw;
             uint32_t lw = 0, ltb = 0, k = 0;
-            auto ld32 = [&](uint32_t pos) {
+            // eight bytes per round (three aligned words + two funnel shifts per stream): candidate reads are L2 round
+            // trips, so fewer, wider rounds
+            auto ld64 = [&](uint32_t pos) -> uint64_t {
                 const uint32_t* q = reinterpret_cast<const uint32_t*>(d + (pos & ~3u));
-                return __funnelshift_r(q[0], q[1], (pos & 3u) * 8u);
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), sh = (pos & 3u) * 8u;
+                return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
             };
             while (k < maxlen && (aw || at)) {
-                const uint32_t x = ld32(p + k);
-                if (aw) { const uint32_t df = x ^ ld32(cw + k); if (df) { aw = false; lw = k + ((uint32_t)__ffs((int)df) - 1u) / 8u; } }
-                if (at) { const uint32_t df = x ^ ld32(ct + k); if (df) { at = false; ltb = k + ((uint32_t)__ffs((int)df) - 1u) / 8u; } }
-                k += 4;
+                const uint64_t x = ld64(p + k);
+                if (aw) { const uint64_t df = x ^ ld64(cw + k); if (df) { aw = false; lw = k + ((uint32_t)__ffsll((long long)df) - 1u) / 8u; } }
+                if (at) { const uint64_t df = x ^ ld64(ct + k); if (df) { at = false; ltb = k + ((uint32_t)__ffsll((long long)df) - 1u) / 8u; } }
+                k += 8;
             }
             if (aw) lw = maxlen;
             if (at) ltb = maxlen;
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
             q.llml = ll | (best << 16);
             sq[nseq + (uint32_t)__popc(prev)] = q;
         }
-        if (is_lit) lits[nlit + (uint32_t)__popc(lmask & lt)] = d[p];
+        if (is_lit) lits[nlit + (uint32_t)__popc(lmask & lt)] = (uint8_t)v;
         if (mmask) {
             const uint32_t lastm = 31u - (uint32_t)__clz((int)mmask);
             lit_at_last = nlit + (uint32_t)__popc(lmask & ((1u << lastm) - 1u));

@@ -1,0 +1,486 @@
+// kernels_zstd_lz.cuh -- LZ execution stage of the zstd decoder (K4): ONE CTA of W warps per entry.
+//
+// A frame's blocks are order-dependent through the window, so the parallelism inside an entry is the bytes
+// and sequences of one STEP: 32*W consecutive sequences (<= STEP output bytes) handled by 32*W threads.
+//   phase A  setup(s):    every thread writes, for each output byte of its sequence, a SOURCE CODE into idx[]:
+//                         a step-relative position (a byte this same step produces) or FLAG | shared-memory offset of
+//                         a byte that exists already (staged literal, older window byte).  Matches whose source has
+//                         left the window ("far", offset > KEEP) were fetched from HBM one step ahead into registers
+//                         and are stored straight into the window; overlapping matches (offset < length) get
+//                         periodic codes, so chains never run inside one match.
+//            front1(s+1): the next step's sequences from the cp.async-staged ring, per-warp packed scan of
+//                         (literal length, total length), published to shared memory.
+//   ---- barrier
+//   phase B  resolve(s):  byte-parallel and divergence-free -- every thread chases idx[] down to an existing byte
+//                         and copies it into the window (codes strictly decrease along a chain).
+//            front2(s+1): cross-warp bases, the cut (first long sequence / STEP overflow), positions, offset
+//                         validation, HBM fetch of far sources for the next step.
+//   ---- barrier (also OR-reduces the offset-validation flags)
+// The window is linear: when it fills, the newest KEEP bytes slide to the front (through registers).  Finished
+// 512-byte rows stream to HBM as 16-byte stores, rows distributed over the warps.  Sequences longer than SEQ_MAX
+// (or far matches > FAR_MAX bytes) go one at a time through whole-CTA copies.
+//
+// Two instantiations: LzSmall (4 warps, 16-bit codes, 29 KB of shared memory: 7 CTAs = 28 warps per SM, one wave
+// for 1024 entries on 148 SMs) and LzBig (32 warps, 32-bit codes, 128 KiB window) for batches with fewer entries
+// than SMs -- a solid archive is ONE frame.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+#include "zstd_core.cuh"
+#include "kernels_crc_cipher.cuh"   // load16_any
+
+namespace pna {
+namespace zs {
+
+struct ZEntry {          // per zstd entry, device resident
+    uint32_t entry;      // index into EntryRec[]
+    uint32_t blk_begin;  // first ZBlock
+    uint32_t blk_count;
+    uint32_t _pad;
+    uint64_t lit_base;   // literal arena base of this entry
+    uint64_t seq_base;   // sequence array base
+    uint64_t lit_total;  // device-written by zstd_resolve
+    uint64_t seq_total;
+};
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t ldcg32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+constexpr uint32_t LZ_SEQ_MAX = 255;   // ll and ml bound of the parallel path
+constexpr uint32_t LZ_FAR_MAX = 32;    // far matches up to this length are prefetched (9 words)
+
+template <int W_, typename Code_, uint32_t BUF_, uint32_t KEEP_, uint32_t STEP_, uint32_t LIT_RING_, uint32_t LIT_CH_, int CTAS_>
+struct LzCfg {
+    using Code = Code_;
+    static constexpr int W = W_, CTAS = CTAS_;
+    static constexpr uint32_t T = 32u * W_;
+    static constexpr Code FLAG = (Code)((Code)1 << (8 * sizeof(Code) - 1));
+    static constexpr uint32_t BUF = BUF_, KEEP = KEEP_, STEP = STEP_;
+    static constexpr uint32_t SEQ_RING = 4 * T;                                  // four chunks of T sequences
+    static constexpr uint32_t LIT_CH = LIT_CH_;                                  // literal bytes staged per pass (<= 16 * T)
+    static constexpr uint32_t LIT_RING = LIT_RING_, LIT_GUARD = 256;
+    static constexpr uint32_t OFF_IDX = BUF;
+    static constexpr uint32_t OFF_SEQ = OFF_IDX + STEP * (uint32_t)sizeof(Code);
+    static constexpr uint32_t OFF_LIT = OFF_SEQ + SEQ_RING * 8;
+    static constexpr uint32_t OFF_SCAN = OFF_LIT + LIT_RING + LIT_GUARD;
+    static constexpr uint32_t OFF_MISC = OFF_SCAN + (uint32_t)W * 32 * 4;
+    static constexpr uint32_t BYTES = OFF_MISC + 64 + (uint32_t)W * 4;
+    static_assert((LIT_RING & (LIT_RING - 1)) == 0 && LIT_RING >= STEP + LIT_CH, "literal ring covers one step plus one staged chunk");
+    static_assert(KEEP >= 2 * STEP + 544, "far sources fetched one step ahead are already in HBM");
+    static_assert(BUF >= KEEP + STEP + 32 && BUF >= KEEP + T + 32, "room for a step after a slide");
+    static_assert(OFF_LIT + LIT_RING + LIT_GUARD < (uint64_t)FLAG, "codes address the CTA's shared block");
+    static_assert(BUF - STEP - KEEP >= 16 * T && T <= STEP, "a slide moves the window by at least one round of pieces");
+    static_assert(LIT_CH <= 16 * T && (LIT_CH & (LIT_CH - 1)) == 0, "one 16-byte piece per thread and pass");
+};
+using LzSmall = LzCfg<4, uint16_t, 16384, 8192, 3072, 4096, 1024, 7>;
+using LzBig = LzCfg<32, uint32_t, 131072, 65536, 8192, 16384, 4096, 1>;
+
+template <class C>
+__global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* __restrict__ buf, EntryRec* entries,
+                                                               const ZEntry* __restrict__ ze, const uint32_t* __restrict__ order,
+                                                               uint32_t nz, const ZBlock* __restrict__ blocks,
+                                                               const uint8_t* __restrict__ lits, const SeqRec* __restrict__ seqs,
+                                                               uint8_t* out) {
+    using Code = typename C::Code;
+    constexpr uint32_t T = C::T;
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    extern __shared__ __align__(16) uint8_t lz_smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint8_t* const win = lz_smem;
+    Code* const idx = reinterpret_cast<Code*>(lz_smem + C::OFF_IDX);
+    SeqRec* const sring = reinterpret_cast<SeqRec*>(lz_smem + C::OFF_SEQ);
+    uint8_t* const lring = lz_smem + C::OFF_LIT;
+    uint32_t* const scan = reinterpret_cast<uint32_t*>(lz_smem + C::OFF_SCAN);   // [W][32] packed (lit << 16 | total) inclusive
+    uint32_t* const misc = reinterpret_cast<uint32_t*>(lz_smem + C::OFF_MISC);   // [0..2] broadcast slot, [16..16+W) warp stops
+    uint32_t* const wstop = misc + 16;
+
+    if (blockIdx.x >= nz) return;
+    const ZEntry z = ze[order ? order[blockIdx.x] : blockIdx.x];
+    EntryRec& er = entries[z.entry];
+    if (er.status != ST_OK) return;
+    if (er.out_len > er.out_cap) { if (tid == 0) atomicCAS(&er.status, ST_OK, ST_NOSPACE); return; }
+    // Positions are 32-bit and relative to the start of the CURRENT block (oblk = its place in HBM); they are rebased
+    // at every block, so the window start and the flush mark may be negative.  oblk + bpos and oblk + flushed stay
+    // multiples of 16 in the (16-byte aligned) entry.
+    uint8_t* oblk = out + er.out_off;
+    int32_t bpos = 0;       // position of win[0]
+    int32_t cur = 0;        // position of the next output byte
+    int32_t flushed = 0;    // HBM holds everything below
+
+    // ---- whole-CTA helpers; every one is called under uniform control flow
+    // finished 512-byte rows -> HBM (rows distributed over the warps).  force: also the 16-byte groups and the byte
+    // tail below cur (rewritten later with the same values).  Callers guarantee the window bytes are visible.
+    auto flush = [&](bool force) {
+        if (flushed + 512 <= cur) {
+            const uint32_t nrows = (uint32_t)((cur - flushed) >> 9);
+            const uint32_t w0 = (uint32_t)(flushed - bpos);
+            uint8_t* const g = oblk + (int64_t)flushed;
+            for (uint32_t r = warp; r < nrows; r += C::W) {
+                const uint4 v = *reinterpret_cast<const uint4*>(win + w0 + (r << 9) + 16 * lane);
+                *reinterpret_cast<uint4*>(g + (r << 9) + 16 * lane) = v;
+            }
+            flushed += (int32_t)(nrows << 9);
+        }
+        if (force && flushed < cur) {
+            const uint32_t n = (uint32_t)(cur - flushed);   // < 512
+            const uint32_t w0 = (uint32_t)(flushed - bpos);
+            if (warp == 0) {
+                uint8_t* const g = oblk + (int64_t)flushed;
+                if (16u * lane + 16u <= n) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(win + w0 + 16 * lane);
+                    *reinterpret_cast<uint4*>(g + 16 * lane) = v;
+                }
+                const uint32_t full = n & ~15u;
+                if (full + lane < n) g[full + lane] = win[w0 + full + lane];
+            }
+            flushed += (int32_t)(n & ~15u);
+        }
+    };
+    // make room for `need` more bytes: the newest KEEP bytes (16-byte granular) slide to the front, through registers
+    auto reserve = [&](uint32_t need) {
+        if ((uint32_t)(cur - bpos) + need <= C::BUF) return;
+        __syncthreads();
+        flush(false);
+        __syncthreads();
+        const uint32_t fill = (uint32_t)(cur - bpos);
+        const uint32_t shift = (fill - C::KEEP) & ~15u;       // fill > BUF - need >= KEEP + 32
+        const uint32_t n16 = (fill - shift + 15u) >> 4;
+        // rounds of T 16-byte pieces.  shift >= 16 * T, so what a round overwrites was read by an earlier round:
+        // one barrier per round, one register quad per thread.
+        for (uint32_t p = tid; p < n16 + tid; p += T) {   // uniform trip count: p - tid < n16
+            if (p < n16) {
+                const uint4 v = *reinterpret_cast<const uint4*>(win + shift + 16 * p);
+                *reinterpret_cast<uint4*>(win + 16 * p) = v;
+            }
+            __syncthreads();
+        }
+        bpos += (int32_t)shift;
+    };
+    // one output byte at entry position pos < cur: from the window when still there, else from HBM
+    auto read_out = [&](int64_t pos) -> uint8_t {
+        if (pos >= bpos) return win[(uint32_t)(pos - bpos)];
+        const uintptr_t a = reinterpret_cast<uintptr_t>(oblk + pos);
+        const uint32_t w = ldcg32(reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3));
+        return (uint8_t)(w >> (8 * (a & 3)));
+    };
+    // append n bytes from HBM (raw blocks, long literal runs); stride 0 = one repeated byte
+    auto emit_global = [&](const uint8_t* src, uint32_t n, uint32_t stride) {
+        uint32_t done = 0;
+        const uint32_t rep = stride ? 0u : 0x01010101u * src[0];
+        __syncthreads();
+        while (done < n) {
+            const uint32_t chunk = n - done < C::STEP ? n - done : C::STEP;
+            reserve(chunk);
+            uint8_t* d = win + (uint32_t)(cur - bpos);
+            uint32_t head = (16u - ((uint32_t)(cur - bpos) & 15u)) & 15u;
+            if (head > chunk) head = chunk;
+            if (tid < head) d[tid] = stride ? src[done + tid] : (uint8_t)rep;
+            const uint32_t body = (chunk - head) >> 4;     // 16-byte pieces into 16-byte aligned window rows
+            for (uint32_t p = tid; p < body; p += T) {
+                uint32_t w4[4] = {rep, rep, rep, rep};
+                if (stride) load16_any(src + done + head + 16 * p, w4);
+                *reinterpret_cast<uint4*>(d + head + 16 * p) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+            const uint32_t t0 = head + body * 16;
+            if (t0 + tid < chunk) d[t0 + tid] = stride ? src[done + t0 + tid] : (uint8_t)rep;
+            __syncthreads();
+            cur += (int32_t)chunk; done += chunk;
+            flush(false);
+        }
+    };
+    // match copy of any length / offset (long matches), T bytes per round; off validated by the caller
+    auto emit_match = [&](uint32_t off, uint32_t n) {
+        uint32_t done = 0;
+        __syncthreads();
+        while (done < n) {
+            const uint32_t m = n - done < T ? n - done : T;
+            reserve(T);
+            uint8_t v = 0;
+            if (tid < m) {   // byte cur+tid repeats with period off: its source is the newest copy below cur
+                const uint32_t k = tid < off ? 1u : tid / off + 1u;
+                v = read_out((int64_t)cur + tid - (int64_t)off * k);
+            }
+            if (tid < m) win[(uint32_t)(cur - bpos) + tid] = v;   // sources are below cur: no overlap with this round's writes
+            __syncthreads();
+            cur += (int32_t)m; done += m;
+            flush(false);
+        }
+    };
+
+    int32_t fail = ST_OK;
+    for (uint32_t k = z.blk_begin; k < z.blk_begin + z.blk_count && fail == ST_OK; k++) {
+        const ZBlock& b = blocks[k];
+        // the prefix pass laid the blocks out back to back: this block starts where the previous one ended.  Rebase.
+        oblk += cur; bpos -= cur; flushed -= cur; cur = 0;
+        if (b.type == BT_RAW) { emit_global(buf + b.src, b.size, 1); continue; }
+        if (b.type == BT_RLE) { emit_global(buf + b.src, b.size, 0); continue; }
+        const uint8_t* lit;
+        uint32_t lstride = 1;
+        if (b.lit_type == LT_RAW) lit = buf + b.src + b.lit_pos;
+        else if (b.lit_type == LT_RLE) { lit = buf + b.src + b.lit_pos; lstride = 0; }
+        else lit = lits + z.lit_base + b.lit_off;
+        const uint32_t lit_regen = b.lit_regen, nseq = b.nseq;
+        const SeqRec* sq = seqs + z.seq_base + b.seq_off;
+        const uint32_t rep_in[3] = {b.rep_in[0], b.rep_in[1], b.rep_in[2]};
+        const uint64_t fd64 = b.out_off - b.frame_out;                // bytes of this frame before the block
+        const uint32_t frame_dist = fd64 < 0x7FFFFFFFull ? (uint32_t)fd64 : 0x7FFFFFFFu;   // offsets beyond 2^31 are corrupt anyway
+        uint32_t lp = 0;                                              // literals consumed
+        uint32_t lit_loaded = 0;                                      // literal bytes staged so far (multiple of LIT_CH)
+        __syncthreads();                                              // the previous block's last readers are done
+        flush(false);
+        if (!lstride) {                                               // RLE literals: the stage is that byte everywhere
+            const uint8_t v = lit[0];
+            for (uint32_t i = tid; i < C::LIT_RING + C::LIT_GUARD; i += T) lring[i] = v;
+            lit_loaded = 0xFFFFFFFFu;
+        }
+        uint32_t staged = 0;                                          // sequence chunks issued so far
+        // keep chunks c .. c+3 (c = wb / T) in flight; returns how many were issued now
+        auto seq_issue = [&](uint32_t wb) -> uint32_t {
+            const uint32_t c = wb / T;
+            uint32_t issued = 0;
+            while (staged <= c + 3 && staged * T < nseq) {
+                const uint32_t i = staged * T + tid;
+                if (i < nseq) cp_async8(sring + (staged & 3u) * T + tid, sq + i);
+                cp_async_commit();
+                staged++; issued++;
+            }
+            return issued;
+        };
+        // ---- registers of the NEXT step (its front runs one step ahead)
+        uint32_t n_off = 1, n_ll = 0, n_ml = 0, n_dl = 0, n_sl = 0, n_nw = 0, n_ph = 0, n_incl = 0, n_llc = 0, n_totc = 0;
+        uint32_t n_take = 0, n_wtot = 0, n_wlit = 0;                  // uniform
+        uint32_t n_t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool n_far = false, n_farc = false, n_bad = false;
+        uint32_t n_start = 0;                                         // position where the next step begins
+        auto front1 = [&](uint32_t wb) {
+            const uint32_t i = wb + tid;
+            const bool valid = i < nseq;
+            SeqRec r{1u, 0u};
+            if (valid) r = sring[((i / T) & 3u) * T + (i % T)];
+            n_off = resolve_rep(r.x, rep_in);
+            n_ll = r.y & 0xFFFFu; n_ml = r.y >> 16;
+            bool longf = valid && (n_ll > LZ_SEQ_MAX || n_ml > LZ_SEQ_MAX);
+            n_farc = valid && !longf && n_ml > 0 && n_off > C::KEEP;
+            longf = longf || (n_farc && n_ml > LZ_FAR_MAX);
+            n_llc = (valid && !longf) ? n_ll : 0u;
+            n_totc = (valid && !longf) ? n_ll + n_ml : 0u;
+            n_incl = warp_incl_scan((n_llc << 16) | n_totc, (int)lane);
+            scan[warp * 32 + lane] = n_incl;
+            const uint32_t stop = __ballot_sync(FULL, !valid || longf);
+            if (lane == 0) wstop[warp] = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
+        };
+        auto front2 = [&]() {
+            uint32_t base_tot = 0, base_lit = 0, my_bt = 0, my_bl = 0;
+            uint32_t take = T, wtot = 0, wlit = 0;
+            bool cut = false;
+#pragma unroll 4
+            for (uint32_t w = 0; w < (uint32_t)C::W; w++) {
+                const uint32_t v = scan[w * 32 + lane];
+                const uint32_t st = wstop[w];
+                if (w == warp) { my_bt = base_tot; my_bl = base_lit; }
+                const uint32_t fl = __ballot_sync(FULL, lane >= st || base_tot + (v & 0xFFFFu) > C::STEP);
+                if (fl) {
+                    const uint32_t f = (uint32_t)__ffs(fl) - 1u;
+                    const uint32_t pv = __shfl_sync(FULL, v, f ? f - 1 : 0);
+                    take = w * 32 + f;
+                    wtot = base_tot + (f ? (pv & 0xFFFFu) : 0u);
+                    wlit = base_lit + (f ? (pv >> 16) : 0u);
+                    cut = true;
+                    break;
+                }
+                const uint32_t tv = __shfl_sync(FULL, v, 31);
+                base_tot += tv & 0xFFFFu; base_lit += tv >> 16;
+            }
+            if (!cut) { wtot = base_tot; wlit = base_lit; }
+            n_take = take; n_wtot = wtot; n_wlit = wlit;
+            const bool taken = tid < take;
+            n_dl = my_bt + (n_incl & 0xFFFFu) - n_totc;               // step-relative start of this thread's literals
+            n_sl = my_bl + (n_incl >> 16) - n_llc;                    // step-relative start in the literal stream
+            const uint32_t dmp = n_start + n_dl + n_ll;               // position of the match
+            n_bad = taken && (n_off == 0 || n_off > frame_dist + dmp);
+            n_far = n_farc && taken && !n_bad;
+            if (n_far) {   // the source has left (or will have left) the window; it is in HBM already: fetch it now
+                const uintptr_t sp = reinterpret_cast<uintptr_t>(oblk + ((int64_t)dmp - (int64_t)n_off));
+                const uint32_t* g = reinterpret_cast<const uint32_t*>(sp & ~(uintptr_t)3);
+                n_nw = ((uint32_t)(sp & 3) + n_ml + 3) >> 2;          // <= 9 words
+                n_ph = (uint32_t)(sp & 3);
+#pragma unroll
+                for (int q = 0; q < 9; q++) if ((uint32_t)q < n_nw) n_t[q] = ldcg32(g + q);
+            }
+        };
+        bool any_bad = false;
+        // full front for a step starting at sequence wb / entry position cur (block start, after a long sequence)
+        auto prime = [&](uint32_t wb) {
+            seq_issue(wb);
+            cp_async_wait_all();
+            __syncthreads();
+            n_start = (uint32_t)cur;
+            front1(wb);
+            __syncthreads();
+            front2();
+            any_bad = __syncthreads_or(n_bad) != 0;
+        };
+        uint32_t wbase = 0;
+        if (nseq) prime(0); else __syncthreads();
+        while (wbase < nseq && fail == ST_OK) {
+            // ---- take over the step prepared by the front
+            const uint32_t off = n_off, ll = n_ll, ml = n_ml, dl = n_dl, sl = n_sl, wtot = n_wtot, wlit = n_wlit, ntake = n_take;
+            const bool far = n_far;
+            const uint32_t ph = n_ph;
+            if (ntake == 0) {
+                // the first sequence is long (or a long far match): it goes alone, by whole-CTA copies
+                if (tid == 0) { misc[0] = off; misc[1] = ll; misc[2] = ml; }
+                __syncthreads();
+                const uint32_t o1 = misc[0];
+                uint32_t l1 = misc[1], m1 = misc[2];
+                if (l1 == SEQ_ESC || m1 == SEQ_ESC)
+                    for (uint32_t q = 0; q < b.esc_n && q < (uint32_t)SEQ_ESC_MAX; q++)
+                        if (b.esc_idx[q] == wbase) { l1 = b.esc_ll[q]; m1 = b.esc_ml[q]; }
+                if ((uint64_t)lp + l1 > lit_regen) { fail = ST_INVALID_DATA; break; }
+                if (l1) emit_global(lit + (size_t)lp * lstride, l1, lstride);
+                lp += l1;
+                if (o1 == 0 || o1 > frame_dist + (uint32_t)cur) { fail = ST_INVALID_DATA; break; }
+                if (m1) emit_match(o1, m1);
+                wbase += 1;
+                if (wbase < nseq) prime(wbase); else __syncthreads();
+                continue;
+            }
+            if (any_bad || (uint64_t)lp + wlit > lit_regen) { fail = ST_INVALID_DATA; break; }
+            // ---- rows finished by the previous step; room in the window; the literals this step reads
+            flush(false);
+            reserve(C::STEP);
+            if (lstride && lit_loaded < lp + wlit) {
+                if (lit_loaded + C::LIT_RING < lp) lit_loaded = lp & ~(C::LIT_CH - 1);   // a long run was copied around the stage
+                while (lit_loaded < lp + wlit) {
+                    const uint32_t p = lit_loaded + 16 * tid;
+                    if (16 * tid < C::LIT_CH && p < lit_regen) {      // 16-byte pieces, unaligned source
+                        uint32_t w4[4];
+                        load16_any(lit + p, w4);
+                        const uint32_t si = p & (C::LIT_RING - 1);
+                        const uint4 v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        *reinterpret_cast<uint4*>(lring + si) = v;
+                        if (si < C::LIT_GUARD) *reinterpret_cast<uint4*>(lring + C::LIT_RING + si) = v;
+                    }
+                    lit_loaded += C::LIT_CH;
+                }
+            }
+            const uint32_t step_start = (uint32_t)cur;               // >= 0 inside the block
+            const uint32_t sidx = (uint32_t)(cur - bpos);            // window index of the step's first byte
+            // ---- setup: source codes of this thread's bytes
+            if (tid < ntake) {
+                Code* ix = idx + dl;
+                uint32_t code = (uint32_t)C::FLAG | (C::OFF_LIT + ((lp + sl) & (C::LIT_RING - 1)));   // guard covers the wrap
+                for (uint32_t q = 0; q < ll; q++) ix[q] = (Code)(code + q);
+                ix += ll;
+                if (far) {
+                    // fetched during the previous step: the bytes go straight to their place, codes point at themselves
+                    const uint32_t d = sidx + dl + ll;
+                    // source bytes ph.. of the fetched words -> destination bytes a.. of the aligned window words:
+                    // one funnel shift per word; whole words are stored as words, the two edge words byte-wise
+                    const uint32_t a = d & 3u;
+                    const int dlt = (int)ph - (int)a;
+                    const uint32_t sh = (uint32_t)(dlt & 3) * 8u;
+                    uint32_t u[10];
+#pragma unroll
+                    for (int q = 0; q < 10; q++) u[q] = dlt < 0 ? (q ? n_t[q - 1] : 0u) : (q < 9 ? n_t[q] : 0u);
+                    uint8_t* const wrow = win + (d - a);
+#pragma unroll
+                    for (int m = 0; m < 9; m++) {
+                        const int lo = 4 * m - (int)a;                    // first destination byte of word m
+                        if (lo < (int)ml) {
+                            const uint32_t wv = __funnelshift_r(u[m], u[m + 1], sh);
+                            if (lo >= 0 && lo + 4 <= (int)ml) *reinterpret_cast<uint32_t*>(wrow + 4 * m) = wv;
+                            else {
+#pragma unroll
+                                for (int bb = 0; bb < 4; bb++)
+                                    if (lo + bb >= 0 && lo + bb < (int)ml) wrow[4 * m + bb] = (uint8_t)(wv >> (8 * bb));
+                            }
+                        }
+                    }
+                    code = (uint32_t)C::FLAG | d;
+                    for (uint32_t q = 0; q < ml; q++) ix[q] = (Code)(code + q);
+                } else if (ml) {
+                    const int32_t srel = (int32_t)(dl + ll) - (int32_t)off;             // step-relative source start
+                    const uint32_t per = off < ml ? off : ml;                            // the match repeats with this period
+                    const uint32_t nneg = srel < 0 ? ((uint32_t)(-srel) < per ? (uint32_t)(-srel) : per) : 0u;   // bytes that exist already
+                    const uint32_t ecode = (uint32_t)C::FLAG | (uint32_t)((int32_t)sidx + srel);
+                    for (uint32_t q = 0; q < nneg; q++) ix[q] = (Code)(ecode + q);
+                    for (uint32_t q = nneg; q < per; q++) ix[q] = (Code)((uint32_t)srel + q);          // >= 0: produced by this step
+                    uint32_t r = 0;
+                    for (uint32_t q = per; q < ml; q++) {                                // overlap: byte q equals byte q mod per
+                        ix[q] = (Code)(r < nneg ? ecode + r : (uint32_t)srel + r);
+                        r = r + 1 == per ? 0u : r + 1;
+                    }
+                }
+            }
+            // ---- the next step's sequences (ring), per-warp scan
+            wbase += ntake;
+            const bool more = wbase < nseq;
+            if (more) {
+                const uint32_t issued = seq_issue(wbase);
+                front1(wbase);
+                if (issued == 1) cp_async_wait_1(); else cp_async_wait_all();
+            }
+            __syncthreads();
+            // ---- resolve: byte-parallel, each thread chases its byte's code down to a byte that exists
+            {
+                uint8_t* const wd = win + sidx;
+                for (uint32_t j = tid; j < wtot; j += 4 * T) {
+                    uint32_t c0 = idx[j], c1 = j + T < wtot ? (uint32_t)idx[j + T] : (uint32_t)C::FLAG,
+                             c2 = j + 2 * T < wtot ? (uint32_t)idx[j + 2 * T] : (uint32_t)C::FLAG,
+                             c3 = j + 3 * T < wtot ? (uint32_t)idx[j + 3 * T] : (uint32_t)C::FLAG;
+                    while (!((c0 & c1 & c2 & c3) & (uint32_t)C::FLAG)) {
+                        if (!(c0 & (uint32_t)C::FLAG)) c0 = idx[c0];
+                        if (!(c1 & (uint32_t)C::FLAG)) c1 = idx[c1];
+                        if (!(c2 & (uint32_t)C::FLAG)) c2 = idx[c2];
+                        if (!(c3 & (uint32_t)C::FLAG)) c3 = idx[c3];
+                    }
+                    // path compression: later bytes of the step that chase into this one stop after one hop (a racing
+                    // reader sees the old or the new code; both lead to the same byte)
+                    idx[j] = (Code)c0;
+                    if (j + T < wtot) idx[j + T] = (Code)c1;
+                    if (j + 2 * T < wtot) idx[j + 2 * T] = (Code)c2;
+                    if (j + 3 * T < wtot) idx[j + 3 * T] = (Code)c3;
+                    constexpr uint32_t M = (uint32_t)C::FLAG - 1u;
+                    const uint8_t v0 = lz_smem[c0 & M], v1 = lz_smem[c1 & M], v2 = lz_smem[c2 & M], v3 = lz_smem[c3 & M];
+                    wd[j] = v0;
+                    if (j + T < wtot) wd[j + T] = v1;
+                    if (j + 2 * T < wtot) wd[j + 2 * T] = v2;
+                    if (j + 3 * T < wtot) wd[j + 3 * T] = v3;
+                }
+            }
+            if (more) { n_start = step_start + wtot; front2(); }
+            cur = (int32_t)(step_start + wtot);
+            lp += wlit;
+            any_bad = __syncthreads_or(more && n_bad) != 0;
+        }
+        if (fail != ST_OK) break;
+        // trailing literals of the block
+        if (lp > lit_regen || (uint32_t)cur + (lit_regen - lp) != b.out_size) { fail = ST_INVALID_DATA; break; }
+        if (lit_regen > lp) emit_global(lit + (size_t)lp * lstride, lit_regen - lp, lstride);
+    }
+    __syncthreads();
+    if (fail == ST_OK) flush(true);
+    if (fail != ST_OK && tid == 0) atomicCAS(&er.status, ST_OK, fail);
+}
+
+}  // namespace zs
+}  // namespace pna
