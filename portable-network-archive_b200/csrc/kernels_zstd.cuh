@@ -143,12 +143,52 @@ __global__ void __launch_bounds__(1024) zstd_order_kernel(const EntryRec* __rest
 // SM's 227 KB.  One CTA of 4 warps per SM (one warp per scheduler), 22 active lanes per warp, each warp's
 // 22 tables interleaved by lane; the warps take batches of 22 blocks independently (no CTA barrier).
 constexpr uint32_t SEQ_LANES = 22, SEQ_WARPS = 4;
-constexpr uint32_t SEQ_SMEM_BYTES = TAB16_TOTAL * SEQ_LANES * SEQ_WARPS * sizeof(uint16_t);   // 225280
+constexpr uint32_t SEQ_TAB_BYTES = TAB16_TOTAL * SEQ_LANES * SEQ_WARPS * sizeof(uint16_t);    // 225280
+constexpr uint32_t SEQ_SMEM_BYTES = SEQ_TAB_BYTES + SEQ_LANES * SEQ_WARPS * 64;               // + a 64-byte bitstream ring per active lane
+
+// A lane's bitstream through shared memory: 16 words (four 16-byte groups) of the stream around the read position,
+// refilled one group at a time by cp.async two groups before it is needed.  The stream is consumed downwards at
+// <= 3 words per window, so one conditional refill per window keeps groups (A>>2) and (A>>2)-1 resident and complete.
+struct RingBitSrc {
+    uint32_t* ring;            // this lane's 16 words (64-byte aligned shared memory)
+    const uint32_t* words;     // arena start: nothing below it is fetched
+    const uint32_t* gbase;     // 16-byte aligned group that holds the stream's first byte
+    uint32_t mis, b0;          // word phase of the stream start inside its group; bit offset inside its word
+    int32_t gl;                // lowest group loaded or in flight
+    __device__ __forceinline__ void fetch(int32_t g) {
+        const uint32_t* src = gbase + 4 * (int64_t)g;
+        if (src >= words) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(ring + ((uint32_t)g & 3u) * 4u);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
+            asm volatile("cp.async.commit_group;");
+        } else asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing newer will follow: drain
+    }
+    __device__ __forceinline__ void init(const uint32_t* w, uint64_t begin, int32_t pos) {
+        words = w;
+        const uint32_t* wb = w + (begin >> 2);
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(wb) >> 2) & 3u;
+        gbase = wb - mis;
+        b0 = (uint32_t)(begin & 3) * 8;
+        const int32_t a = (((int32_t)b0 + pos - 1) >> 5) + (int32_t)mis;
+        gl = (a >> 2) - 3;
+        for (int32_t g = gl + 3; g >= gl; g--) fetch(g);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __device__ __forceinline__ uint64_t window(int32_t pos) {
+        const int32_t top = (int32_t)b0 + pos - 1;
+        const int32_t a = (top >> 5) + (int32_t)mis;      // ring word index of the window's top word (>= -2 + mis)
+        const uint32_t sh = 31u - ((uint32_t)top & 31u);
+        if ((a >> 2) <= gl + 2) { gl--; fetch(gl); }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const uint32_t h = ring[(uint32_t)a & 15u], m = ring[(uint32_t)(a - 1) & 15u], l = ring[(uint32_t)(a - 2) & 15u];
+        return ((uint64_t)__funnelshift_l(m, h, sh) << 32) | __funnelshift_l(l, m, sh);
+    }
+};
 __global__ void __launch_bounds__(32 * SEQ_WARPS) zstd_seq_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, ZBlock* blocks,
                                                                   const uint32_t* __restrict__ order, uint32_t* counts,
                                                                   const uint64_t* __restrict__ seq_base_of_entry,
                                                                   SeqRec* __restrict__ seqs) {
-    extern __shared__ uint16_t stab_all[];
+    extern __shared__ __align__(64) uint16_t stab_all[];
     __shared__ uint32_t s_llb[36], s_mlb[53];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < 36; c += blockDim.x) s_llb[c] = ll_base(c);
@@ -183,7 +223,9 @@ __global__ void __launch_bounds__(32 * SEQ_WARPS) zstd_seq_kernel(const uint8_t*
             uint32_t esc_n = 0, esc_idx[SEQ_ESC_MAX], esc_ll[SEQ_ESC_MAX], esc_ml[SEQ_ESC_MAX];
             if (l0 >= 0 && l1 >= 0 && l2 >= 0) {
                 const uint64_t so = seq_base_of_entry[entry] + gb.seq_off;
-                st = decode_sequences16(words, buf, b, tll, tof, tml, l0, l1, l2, s_llb, s_mlb, seqs + so, &esc_n, esc_idx, esc_ll, esc_ml);
+                RingBitSrc src;
+                src.ring = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(stab_all) + SEQ_TAB_BYTES) + ((uint32_t)warp * SEQ_LANES + l) * 16;
+                st = decode_sequences16_from(src, words, buf, b, tll, tof, tml, l0, l1, l2, s_llb, s_mlb, seqs + so, &esc_n, esc_idx, esc_ll, esc_ml);
             }
             if (st == ST_OK) {
                 gb.out_size = b.out_size; gb.lit_used = b.lit_used;

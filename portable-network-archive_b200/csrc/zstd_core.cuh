@@ -440,21 +440,38 @@ PNA_HD uint32_t win_bits(uint64_t W, uint32_t skip, uint32_t n) {
 //   state -> table cell -> bit counts -> next position / next state
 // is loop-carried.  Errors are collected in a flag (no early exits inside the loop).
 // llb/mlb: value baselines by code.  Same accept/reject behaviour as decode_sequences().
-PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll,
-                                  const Tab16& tof, const Tab16& tml, int lll, int lof, int lml,
-                                  const uint32_t* llb, const uint32_t* mlb, SeqRec* out, uint32_t* esc_n,
-                                  uint32_t* esc_idx, uint32_t* esc_ll, uint32_t* esc_ml) {
+// Where decode_sequences16 takes its 64-bit windows from.  GlobalBitSrc: straight from the arena (three aligned loads
+// per window, the sector 128 bytes below pulled into L1 ahead of use); zstd_seq_kernel uses a per-lane shared-memory
+// ring fed by cp.async instead (kernels_zstd.cuh: RingBitSrc), which takes the HBM/L2 latency off the decode chain.
+struct GlobalBitSrc {
+    const uint32_t* words;
+    const uint32_t* wb;
+    uint32_t b0;
+    PNA_HD void init(const uint32_t* w, uint64_t begin, int32_t /*pos*/) { words = w; wb = w + (begin >> 2); b0 = (uint32_t)(begin & 3) * 8; }
+    PNA_HD uint64_t window(int32_t pos) {
+#if defined(__CUDA_ARCH__)
+        const uint32_t* pf = wb + (((int32_t)b0 + pos) >> 5) - 32;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf < words ? words : pf));
+#endif
+        return bits_window(wb, b0, pos);
+    }
+};
+
+template <class Src>
+PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll,
+                                       const Tab16& tof, const Tab16& tml, int lll, int lof, int lml,
+                                       const uint32_t* llb, const uint32_t* mlb, SeqRec* out, uint32_t* esc_n,
+                                       uint32_t* esc_idx, uint32_t* esc_ll, uint32_t* esc_ml) {
     const uint64_t begin = b.src + b.bs_pos;
     const uint32_t len = b.bs_len, nseq = b.nseq, lit_regen = b.lit_regen;
     if (len == 0) return ST_INVALID_DATA;
     const uint8_t last = comp[begin + len - 1];
     if (last == 0) return ST_INVALID_DATA;
-    const uint32_t* wb = words + (begin >> 2);
-    const uint32_t b0 = (uint32_t)(begin & 3) * 8;
     int32_t pos = (int32_t)(len - 1) * 8 + highbit32(last);
     const uint32_t ulll = (uint32_t)lll, ulof = (uint32_t)lof, ulml = (uint32_t)lml;
     if (pos < (int32_t)(ulll + ulof + ulml)) return ST_INVALID_DATA;
-    uint64_t W = bits_window(wb, b0, pos);
+    src.init(words, begin, pos);
+    uint64_t W = src.window(pos);
     uint32_t sll = win_bits(W, 0, ulll), sof = win_bits(W, ulll, ulof), sml = win_bits(W, ulll + ulof, ulml);
     pos -= (int32_t)(ulll + ulof + ulml);
     uint32_t rep0 = REP_SYM | (0u << 29), rep1 = REP_SYM | (1u << 29), rep2 = REP_SYM | (2u << 29);
@@ -462,17 +479,12 @@ PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZB
     const uint32_t zll = 1u << lll, zof = 1u << lof, zml = 1u << lml;
     uint32_t ne = 0;
     uint32_t err = 0;
+    // Software pipeline: the loop-carried part (cells -> bit counts -> next position / states) comes first, then the
+    // NEXT sequence's window and table cells are requested, and only then this sequence's values, repeat-offset
+    // logic and store run -- in the latency shadow of those loads (one warp per scheduler: nothing else hides it).
+    W = src.window(pos);
+    uint32_t ell = tll.get(sll), eof = tof.get(sof), eml = tml.get(sml);
     for (uint32_t i = 0; i < nseq; i++) {
-        W = bits_window(wb, b0, pos);
-#if defined(__CUDA_ARCH__)
-        // the stream is consumed downwards ~2 bytes per sequence: pull the sector 128 bytes below into L1 now, so
-        // that no lane of the warp (32 independent streams) ever waits on L2/HBM inside the chain
-        {
-            const uint32_t* pf = wb + (((int32_t)b0 + pos) >> 5) - 32;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf < words ? words : pf));
-        }
-#endif
-        const uint32_t ell = tll.get(sll), eof = tof.get(sof), eml = tml.get(sml);
         const uint32_t cll = ell >> 10, cof = eof >> 10, cml = eml >> 10;
         const uint32_t xll = ll_xbits(cll), xml = ml_xbits(cml);
         const uint32_t nsl = ell & 1023u, nsm = eml & 1023u, nso = eof & 1023u;
@@ -481,22 +493,25 @@ PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZB
         const uint32_t xb = cof + xml + xll;                 // value bits: offset, match length, literal length
         const bool more = i + 1 < nseq;
         const uint32_t nbs = more ? nbl + nbm + nbo : 0u;    // the last sequence updates no state
-        uint32_t ofx, mlx, llx, y;
-        if (xb + nbs <= 64u) {
-            ofx = win_bits(W, 0, cof);
-            const uint32_t x = win_bits(W, cof, xml + xll);
-            mlx = x >> xll; llx = x & ((1u << xll) - 1u);
-            y = win_bits(W, xb, nbs);
-        } else {   // > 64 bits in one sequence (offset codes > 22 with long length codes): second window for the states
-            ofx = win_bits(W, 0, cof);
-            const uint32_t x = win_bits(W, cof, xml + xll);
-            mlx = x >> xll; llx = x & ((1u << xll) - 1u);
+        const uint32_t ofx = win_bits(W, 0, cof);
+        const uint32_t x = win_bits(W, cof, xml + xll);
+        uint32_t y;
+        if (xb + nbs <= 64u) y = win_bits(W, xb, nbs);
+        else {   // > 64 bits in one sequence (offset codes > 22 with long length codes): second window for the states
             const int32_t p2 = pos - (int32_t)xb;
-            y = p2 >= 0 ? win_bits(bits_window(wb, b0, p2), 0, nbs) : 0u;
+            y = p2 >= 0 ? win_bits(src.window(p2), 0, nbs) : 0u;
         }
         pos -= (int32_t)(xb + nbs);
         err |= (uint32_t)(pos < 0);
         pos = pos < 0 ? 0 : pos;                             // keep the reads inside the arena on corrupt input
+        sll = more ? ((nsl << nbl) - zll) + (y >> (nbm + nbo)) : 0u;
+        sml = more ? ((nsm << nbm) - zml) + ((y >> nbo) & ((1u << nbm) - 1u)) : 0u;
+        sof = more ? ((nso << nbo) - zof) + (y & ((1u << nbo) - 1u)) : 0u;
+        // ---- the next sequence's loads (after the last sequence: position 0 / state 0, valid and unused)
+        W = src.window(pos);
+        ell = tll.get(sll); eof = tof.get(sof); eml = tml.get(sml);
+        // ---- this sequence's values
+        const uint32_t mlx = x >> xll, llx = x & ((1u << xll) - 1u);
         const uint32_t ofv = (1u << cof) + ofx;
         const uint32_t ml = mlb[cml] + mlx;
         const uint32_t ll = llb[cll] + llx;
@@ -522,10 +537,6 @@ PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZB
         r.y = (ll < SEQ_ESC ? ll : SEQ_ESC) | ((ml < SEQ_ESC ? ml : SEQ_ESC) << 16);
         out[i] = r;
         lit_sum += ll; match_sum += ml;
-        sll = ((nsl << nbl) - zll) + (y >> (nbm + nbo));
-        sml = ((nsm << nbm) - zml) + ((y >> nbo) & ((1u << nbm) - 1u));
-        sof = ((nso << nbo) - zof) + (y & ((1u << nbo) - 1u));
-        if (!more) { sll = 0; sml = 0; sof = 0; }
     }
     if (err || pos != 0) return ST_INVALID_DATA;
     if (lit_sum > lit_regen) return ST_INVALID_DATA;
@@ -536,6 +547,13 @@ PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZB
     b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
     *esc_n = ne;
     return ST_OK;
+}
+PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll,
+                                  const Tab16& tof, const Tab16& tml, int lll, int lof, int lml,
+                                  const uint32_t* llb, const uint32_t* mlb, SeqRec* out, uint32_t* esc_n,
+                                  uint32_t* esc_idx, uint32_t* esc_ll, uint32_t* esc_ml) {
+    GlobalBitSrc src;
+    return decode_sequences16_from(src, words, comp, b, tll, tof, tml, lll, lof, lml, llb, mlb, out, esc_n, esc_idx, esc_ll, esc_ml);
 }
 
 // ---------------------------------------------------------------------------------------------

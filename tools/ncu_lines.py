@@ -4,13 +4,16 @@ share of stall samples and of executed warp instructions per CUDA line, with the
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+kfilter = sys.argv[3] if len(sys.argv) > 3 else ""
+func = ""
 fname = ""
 hdr = None
 lines = []
 for r in rows:
     if not r: continue
     if r[0] == "File Path": fname = r[1].split("/")[-1]; continue
-    if r[0] == "Function Name": continue
+    if r[0] == "Function Name": func = r[1]; continue
+    if kfilter and kfilter not in func: continue
     if r[0] == "Line No": hdr = r; continue
     if hdr is None or len(r) < len(hdr) - 2: continue
     if r[2] != "-": continue            # SASS rows carry an address; aggregated CUDA-line rows have '-'
