@@ -111,6 +111,17 @@ int pna_cuda_decode_plan_create_crc(pna_ctx* ctx, const pna_decode_desc* descs, 
 int pna_cuda_plan_crc_results(pna_plan* plan, uint32_t* crc_out, uint32_t* n_broken);
 int pna_cuda_decode_plan_run(pna_plan* plan);                 /* asynchronous on pna_cuda_stream(ctx) after first call */
 int pna_cuda_decode_plan_fetch(pna_plan* plan, pna_buf* out, int32_t* status);
+/* decoded length and status of every entry after pna_cuda_decode_plan_run (waits for the run; PNA_E_NOSPACE + length
+ * when the entry was given a too small raw_size_hint): lets the caller size host buffers before fetching */
+int pna_cuda_decode_plan_lengths(pna_plan* plan, uint64_t* out_len, int32_t* status);
+/* Solid entries (lib/src/entry.rs:401-423): the decoded SDAT stream is itself a chunk sequence whose CRCs the reference
+ * checks as it reads, and whose STORE entries are slices of that stream.  Both work on the decoded bytes where they
+ * already are (HBM): CRC-32 of (offset, length) spans inside entry `entry`'s output, and device-to-host copies of
+ * ranges of it straight to their destinations.  pna_cuda_decode_plan_lengths must have been called. */
+int pna_cuda_decode_plan_crc32_out(pna_plan* plan, uint32_t entry, const uint64_t* span_off, const uint64_t* span_len,
+                                   uint32_t n, uint32_t* crc_out);
+int pna_cuda_decode_plan_fetch_ranges(pna_plan* plan, uint32_t entry, const uint64_t* src_off, const uint64_t* len,
+                                      uint8_t* const* dst, uint32_t n);
 /* stream / decoded byte totals of a plan (algorithmic bytes for the roofline: C and U) */
 int pna_cuda_plan_stats(pna_plan* plan, uint64_t* stream_bytes, uint64_t* plain_bytes, uint64_t* launches_per_run);
 /* zstd work of a prepared plan: blocks, sequences (8-byte records between the entropy and LZ stages) and

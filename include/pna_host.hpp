@@ -24,6 +24,7 @@
 #ifdef __cplusplus
 #include <array>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -87,7 +88,9 @@ public:
 
 private:
     struct FileRef { uint32_t owner; uint32_t entry; };   // owner: 0 = top-level archive, k+1 = inner archive of solid k
-    struct Inner { std::vector<uint8_t> bytes; std::vector<RawChunk> chunks; std::vector<EntryInfo> entries; };
+    // inner archive of a solid entry: host copy for the index pass, and the decode plan whose output (the same bytes)
+    // stays resident in HBM for the inner chunk CRC check and for range copies of STORE entries
+    struct Inner { std::vector<uint8_t> bytes; std::vector<RawChunk> chunks; std::vector<EntryInfo> entries; std::shared_ptr<pna_plan> plan; };
     const uint8_t* buf_ = nullptr;
     size_t len_ = 0;
     uint32_t archive_number_ = 0;

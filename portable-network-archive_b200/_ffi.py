@@ -17,6 +17,7 @@ EXPORTS = [
     "pna_cuda_init", "pna_cuda_destroy", "pna_cuda_strerror", "pna_cuda_last_error", "pna_cuda_host_alloc",
     "pna_cuda_host_free", "pna_cuda_stream", "pna_cuda_launch_count", "pna_cuda_crc32", "pna_cuda_crc32_image",
     "pna_cuda_decode_batch", "pna_cuda_decode_plan_create", "pna_cuda_decode_plan_create_crc", "pna_cuda_plan_crc_results", "pna_cuda_decode_plan_run", "pna_cuda_decode_plan_fetch",
+    "pna_cuda_decode_plan_lengths", "pna_cuda_decode_plan_crc32_out", "pna_cuda_decode_plan_fetch_ranges",
     "pna_cuda_plan_stats", "pna_cuda_plan_counts", "pna_cuda_plan_stage_ms", "pna_cuda_stage_name", "pna_cuda_encode_stage_name", "pna_cuda_plan_destroy", "pna_cuda_encode_bound", "pna_cuda_encode_crc_count",
     "pna_cuda_encode_batch", "pna_cuda_encode_plan_create", "pna_cuda_encode_plan_run", "pna_cuda_encode_plan_lengths", "pna_cuda_encode_plan_fetch",
     "pna_cuda_ecb",

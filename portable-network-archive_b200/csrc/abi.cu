@@ -199,6 +199,7 @@ struct pna_plan {
     DevArr<CopyJob> d_copy;
     uint32_t n_blocks = 0;
     uint64_t lit_total = 0, seq_total = 0;
+    std::vector<uint64_t> h_out_len;   // decoded length per entry (pna_cuda_decode_plan_lengths)
     // per-stage CUDA events of the last run (cipher, zstd scan, entropy, prefix, lz, inflate, store)
     cudaEvent_t ev[PNA_N_STAGES + 1] = {};
     bool ev_ready = false, ev_recorded = false;
@@ -941,6 +942,76 @@ extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* st
         if (rc) return rc;
     }
     P->plain_bytes = plain;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PNA_OK;
+}
+extern "C" int pna_cuda_decode_plan_lengths(pna_plan* P, uint64_t* out_len, int32_t* status) {
+    if (!P || P->kind != 0 || ((!out_len || !status) && P->n)) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (P->n == 0) return PNA_OK;
+    if (!P->prepared) return PNA_E_BAD_ARG;
+    std::vector<EntryRec> dev(P->n);
+    CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    P->h_out_len.assign(P->n, 0);
+    for (uint32_t i = 0; i < P->n; i++) {
+        const EntryRec& e = dev[i];
+        int32_t st = e.status;
+        uint64_t len = e.compression == PNA_COMPRESSION_NO ? e.comp_len : e.out_len;
+        if (P->h_entries[i].status != ST_OK) { st = P->h_entries[i].status; len = 0; }
+        if (st == ST_OK && len > e.out_cap) st = ST_NOSPACE;
+        out_len[i] = (st == ST_OK || st == ST_NOSPACE) ? len : 0;
+        status[i] = st;
+        if (st == ST_OK) P->h_out_len[i] = len;
+    }
+    return PNA_OK;
+}
+// the decoded bytes of `entry` as they sit in HBM after a run (lengths must have been queried)
+static int plan_entry_out(pna_plan* P, uint32_t entry, const uint8_t** base, uint64_t* len) {
+    if (!P || P->kind != 0 || entry >= P->n || !P->prepared || P->h_out_len.size() != P->n) return PNA_E_BAD_ARG;
+    *base = P->d_out.p + P->h_entries[entry].out_off;
+    *len = P->h_out_len[entry];
+    return PNA_OK;
+}
+extern "C" int pna_cuda_decode_plan_crc32_out(pna_plan* P, uint32_t entry, const uint64_t* span_off, const uint64_t* span_len,
+                                              uint32_t n, uint32_t* crc_out) {
+    const uint8_t* base = nullptr;
+    uint64_t len = 0;
+    int rc = plan_entry_out(P, entry, &base, &len);
+    if (rc) return rc;
+    if (n == 0) return PNA_OK;
+    if (!span_off || !span_len || !crc_out) return PNA_E_BAD_ARG;
+    for (uint32_t i = 0; i < n; i++) if (span_off[i] > len || span_len[i] > len - span_off[i]) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> off(span_off, span_off + n);
+    return crc_run(ctx, base, off, span_len, n, crc_out);
+}
+extern "C" int pna_cuda_decode_plan_fetch_ranges(pna_plan* P, uint32_t entry, const uint64_t* src_off, const uint64_t* len,
+                                                 uint8_t* const* dst, uint32_t n) {
+    const uint8_t* base = nullptr;
+    uint64_t total = 0;
+    int rc = plan_entry_out(P, entry, &base, &total);
+    if (rc) return rc;
+    if (n == 0) return PNA_OK;
+    if (!src_off || !len || !dst) return PNA_E_BAD_ARG;
+    for (uint32_t i = 0; i < n; i++) if (src_off[i] > total || len[i] > total - src_off[i] || (len[i] && !dst[i])) return PNA_E_BAD_ARG;
+    pna_ctx* ctx = P->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    // ranges that continue each other on both sides travel in one copy
+    uint64_t run_src = 0, run_len = 0;
+    uint8_t* run_dst = nullptr;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!len[i]) continue;
+        if (run_len && src_off[i] == run_src + run_len && dst[i] == run_dst + run_len) { run_len += len[i]; continue; }
+        if (run_len) CK(cudaMemcpyAsync(run_dst, base + run_src, run_len, cudaMemcpyDeviceToHost, ctx->stream));
+        run_src = src_off[i]; run_len = len[i]; run_dst = dst[i];
+    }
+    if (run_len) CK(cudaMemcpyAsync(run_dst, base + run_src, run_len, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return PNA_OK;
 }

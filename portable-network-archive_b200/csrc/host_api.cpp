@@ -150,21 +150,25 @@ void Archive::prepare(const ReadOptions& opt, int device) {
         pna_decode_desc d;
         int32_t st = fill_desc(e, opt, d);
         if (st != PNA_OK) throw Error(st, "solid entry: key unavailable");
-        d.raw_size_hint = UINT64_MAX;
-        pna_buf ob{nullptr, 0, 0};
-        ck(L.ctx, pna_cuda_decode_batch(L.ctx, &d, 1, &ob, &st), "solid sizing");
-        if (st != PNA_OK && st != PNA_E_NOSPACE) throw Error(st, "solid entry: decode failed");
-        in.bytes.resize(ob.len + 16);
-        ob.ptr = in.bytes.data(); ob.cap = ob.len;
-        ck(L.ctx, pna_cuda_decode_batch(L.ctx, &d, 1, &ob, &st), "solid decode");
+        d.raw_size_hint = UINT64_MAX;                                       // solid streams carry no size: the plan sizes itself
+        pna_plan* plan = nullptr;
+        ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, &d, 1, &plan), "solid plan");
+        in.plan = std::shared_ptr<pna_plan>(plan, [](pna_plan* p) { pna_cuda_plan_destroy(p); });
+        ck(L.ctx, pna_cuda_decode_plan_run(plan), "solid decode");
+        uint64_t dec_len = 0;
+        ck(L.ctx, pna_cuda_decode_plan_lengths(plan, &dec_len, &st), "solid lengths");
+        if (st != PNA_OK) throw Error(st, "solid entry: decode failed");
+        in.bytes.resize(dec_len + 16);
+        pna_buf ob{in.bytes.data(), dec_len, 0};
+        ck(L.ctx, pna_cuda_decode_plan_fetch(plan, &ob, &st), "solid fetch");
         if (st != PNA_OK) throw Error(st, "solid entry: decode failed");
         in.bytes.resize(ob.len);
         index_chunks(in.bytes.data(), in.bytes.size(), 0, in.chunks);       // entry.rs:401-423: chunks, CRC checked as read
-        if (!in.chunks.empty()) {
+        if (!in.chunks.empty()) {                                           // ... on the copy that is still in HBM
             std::vector<uint64_t> off(in.chunks.size()), len(in.chunks.size());
             std::vector<uint32_t> crc(in.chunks.size());
             for (size_t c = 0; c < in.chunks.size(); c++) { off[c] = in.chunks[c].off - 4; len[c] = (uint64_t)in.chunks[c].len + 4; }
-            ck(L.ctx, pna_cuda_crc32_image(L.ctx, in.bytes.data(), in.bytes.size(), off.data(), len.data(), (uint32_t)off.size(), crc.data()), "solid inner crc");
+            ck(L.ctx, pna_cuda_decode_plan_crc32_out(plan, 0, off.data(), len.data(), (uint32_t)off.size(), crc.data()), "solid inner crc");
             for (size_t c = 0; c < in.chunks.size(); c++)
                 if (crc[c] != in.chunks[c].crc) throw Error(PNA_E_INVALID_DATA, "broken chunk (inside solid entry)");
         }
@@ -274,10 +278,39 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
         std::vector<uint32_t> expect;
         std::vector<int32_t> owner;
     };
+    // files of a solid entry that are stored as they are (what the reference's solid writer produces): their bytes are
+    // ranges of the decoded stream that is still in HBM -- copy them out from there
+    auto store_ranges = [&](CtxLease& L, size_t g) -> bool {
+        const Group G = groups[g];
+        const uint32_t owner = refs_[G.lo].owner;
+        if (owner == 0) return false;
+        const Inner& in = inner_[owner - 1];
+        if (!in.plan) return false;
+        for (size_t i = G.lo; i < G.hi; i++) {
+            const EntryInfo& e = in.entries[refs_[i].entry];
+            if (files_[i].status || e.compression != PNA_COMPRESSION_NO || e.encryption != PNA_ENCRYPTION_NO) return false;
+        }
+        std::vector<uint64_t> src, len;
+        std::vector<uint8_t*> dst;
+        for (size_t i = G.lo; i < G.hi; i++) {
+            const EntryInfo& e = in.entries[refs_[i].entry];
+            const uint64_t cap = offsets[i + 1] - offsets[i];
+            uint64_t at = 0;
+            if (e.compressed_size > cap) { status[i] = PNA_E_NOSPACE; continue; }
+            for (const pna_span& b : e.bodies) {
+                src.push_back((uint64_t)(b.ptr - in.bytes.data())); len.push_back(b.len); dst.push_back(out + offsets[i] + at);
+                at += b.len;
+            }
+            status[i] = PNA_OK;
+        }
+        ck(L.ctx, pna_cuda_decode_plan_fetch_ranges(in.plan.get(), 0, src.data(), len.data(), dst.data(), (uint32_t)src.size()), "solid ranges");
+        return true;
+    };
     auto issue = [&](CtxLease& L, Stage& S, size_t g) {
         const Group G = groups[g];
         const uint32_t m = (uint32_t)(G.hi - G.lo);
         S.g = g; S.m = m; S.plan = nullptr;
+        if (store_ranges(L, g)) return;
         S.descs.assign(m, pna_decode_desc{}); S.bufs.resize(m); S.st.assign(m, 0); S.pre.assign(m, 0);
         for (uint32_t k = 0; k < m; k++) {
             const FileRef r = refs_[G.lo + k];

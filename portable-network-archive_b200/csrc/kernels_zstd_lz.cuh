@@ -78,7 +78,7 @@ struct LzCfg {
     static constexpr uint32_t LIT_CH = LIT_CH_;                                  // literal bytes staged per pass (<= 16 * T)
     static constexpr uint32_t LIT_RING = LIT_RING_, LIT_GUARD = 256;
     static constexpr uint32_t OFF_IDX = BUF;
-    static constexpr uint32_t OFF_SEQ = OFF_IDX + STEP * (uint32_t)sizeof(Code);
+    static constexpr uint32_t OFF_SEQ = OFF_IDX + (STEP + 8) * (uint32_t)sizeof(Code);   // idx[] is indexed from the aligned window word of the step start
     static constexpr uint32_t OFF_LIT = OFF_SEQ + SEQ_RING * 8;
     static constexpr uint32_t OFF_SCAN = OFF_LIT + LIT_RING + LIT_GUARD;
     static constexpr uint32_t OFF_MISC = OFF_SCAN + (uint32_t)W * 32 * 4;
@@ -91,7 +91,21 @@ struct LzCfg {
     static_assert(LIT_CH <= 16 * T && (LIT_CH & (LIT_CH - 1)) == 0, "one 16-byte piece per thread and pass");
 };
 using LzSmall = LzCfg<4, uint16_t, 16384, 8192, 3072, 4096, 1024, 7>;
-using LzBig = LzCfg<32, uint32_t, 131072, 65536, 8192, 16384, 4096, 1>;
+using LzBig = LzCfg<16, uint32_t, 131072, 65536, 8192, 16384, 4096, 1>;
+
+// n consecutive codes code, code+1, ... at ix: two (16-bit) codes per 32-bit store once ix is word aligned
+template <typename Code>
+__device__ __forceinline__ void fill_codes(Code* ix, uint32_t n, uint32_t code) {
+    if constexpr (sizeof(Code) == 2) {
+        if (n && (reinterpret_cast<uintptr_t>(ix) & 2)) { *ix++ = (Code)code; code++; n--; }
+        uint32_t pair = code | ((code + 1) << 16);         // no carry between the halves: codes stay below 2^16
+        uint32_t* p32 = reinterpret_cast<uint32_t*>(ix);
+        for (uint32_t q = 0; q + 2 <= n; q += 2) { *p32++ = pair; pair += 0x00020002u; }
+        if (n & 1) ix[n - 1] = (Code)(code + n - 1);
+    } else {
+        for (uint32_t q = 0; q < n; q++) ix[q] = (Code)(code + q);
+    }
+}
 
 template <class C>
 __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* __restrict__ buf, EntryRec* entries,
@@ -288,28 +302,35 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
             if (lane == 0) wstop[warp] = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
         };
         auto front2 = [&]() {
-            uint32_t base_tot = 0, base_lit = 0, my_bt = 0, my_bl = 0;
-            uint32_t take = T, wtot = 0, wlit = 0;
-            bool cut = false;
-#pragma unroll 4
-            for (uint32_t w = 0; w < (uint32_t)C::W; w++) {
-                const uint32_t v = scan[w * 32 + lane];
-                const uint32_t st = wstop[w];
-                if (w == warp) { my_bt = base_tot; my_bl = base_lit; }
-                const uint32_t fl = __ballot_sync(FULL, lane >= st || base_tot + (v & 0xFFFFu) > C::STEP);
-                if (fl) {
-                    const uint32_t f = (uint32_t)__ffs(fl) - 1u;
-                    const uint32_t pv = __shfl_sync(FULL, v, f ? f - 1 : 0);
-                    take = w * 32 + f;
-                    wtot = base_tot + (f ? (pv & 0xFFFFu) : 0u);
-                    wlit = base_lit + (f ? (pv >> 16) : 0u);
-                    cut = true;
-                    break;
-                }
-                const uint32_t tv = __shfl_sync(FULL, v, 31);
-                base_tot += tv & 0xFFFFu; base_lit += tv >> 16;
+            // lane l stands for warp l: exclusive scan of the warp totals, first warp that holds the cut
+            const uint32_t tv = lane < (uint32_t)C::W ? scan[lane * 32 + 31] : 0u;
+            const uint32_t st_l = lane < (uint32_t)C::W ? wstop[lane] : 32u;
+            const uint32_t tot_l = tv & 0xFFFFu, lit_l = tv >> 16;
+            uint32_t bt = tot_l, bl = lit_l;
+#pragma unroll
+            for (int o = 1; o < C::W; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(FULL, bt, o), y = __shfl_up_sync(FULL, bl, o);
+                if ((int)lane >= o) { bt += x; bl += y; }
             }
-            if (!cut) { wtot = base_tot; wlit = base_lit; }
+            bt -= tot_l; bl -= lit_l;                                  // exclusive
+            const uint32_t fw = __ballot_sync(FULL, lane < (uint32_t)C::W && (st_l < 32u || bt + tot_l > C::STEP));
+            uint32_t take, wtot, wlit;
+            if (fw) {
+                const uint32_t c = (uint32_t)__ffs(fw) - 1u;
+                const uint32_t cbt = __shfl_sync(FULL, bt, c), cbl = __shfl_sync(FULL, bl, c), cst = __shfl_sync(FULL, st_l, c);
+                const uint32_t v = scan[c * 32 + lane];
+                const uint32_t fl = __ballot_sync(FULL, lane >= cst || cbt + (v & 0xFFFFu) > C::STEP);   // not empty
+                const uint32_t f = (uint32_t)__ffs(fl) - 1u;
+                const uint32_t pv = __shfl_sync(FULL, v, f ? f - 1 : 0);
+                take = c * 32 + f;
+                wtot = cbt + (f ? (pv & 0xFFFFu) : 0u);
+                wlit = cbl + (f ? (pv >> 16) : 0u);
+            } else {
+                take = T;
+                wtot = __shfl_sync(FULL, bt + tot_l, C::W - 1);
+                wlit = __shfl_sync(FULL, bl + lit_l, C::W - 1);
+            }
+            const uint32_t my_bt = __shfl_sync(FULL, bt, warp), my_bl = __shfl_sync(FULL, bl, warp);
             n_take = take; n_wtot = wtot; n_wlit = wlit;
             const bool taken = tid < take;
             n_dl = my_bt + (n_incl & 0xFFFFu) - n_totc;               // step-relative start of this thread's literals
@@ -384,49 +405,55 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
             }
             const uint32_t step_start = (uint32_t)cur;               // >= 0 inside the block
             const uint32_t sidx = (uint32_t)(cur - bpos);            // window index of the step's first byte
-            // ---- setup: source codes of this thread's bytes
+            // ---- setup: source codes of this thread's bytes.  idx[] is indexed from the aligned window word that holds
+            // the step's first byte (index = step-relative position + g0), so the resolve pass reads four codes per
+            // 64-bit load and stores whole window words.
+            const uint32_t g0 = sidx & 3u;
             if (tid < ntake) {
-                Code* ix = idx + dl;
-                uint32_t code = (uint32_t)C::FLAG | (C::OFF_LIT + ((lp + sl) & (C::LIT_RING - 1)));   // guard covers the wrap
-                for (uint32_t q = 0; q < ll; q++) ix[q] = (Code)(code + q);
+                Code* ix = idx + g0 + dl;
+                fill_codes<Code>(ix, ll, (uint32_t)C::FLAG | (C::OFF_LIT + ((lp + sl) & (C::LIT_RING - 1))));   // guard covers the wrap
                 ix += ll;
                 if (far) {
-                    // fetched during the previous step: the bytes go straight to their place, codes point at themselves
+                    // fetched during the previous step: the bytes go straight to their place, codes point at themselves.
+                    // Source bytes ph.. of the fetched words -> destination bytes a.. of the aligned window words: one
+                    // funnel shift per word; whole words are stored as words, the head and tail words byte-wise.
                     const uint32_t d = sidx + dl + ll;
-                    // source bytes ph.. of the fetched words -> destination bytes a.. of the aligned window words:
-                    // one funnel shift per word; whole words are stored as words, the two edge words byte-wise
                     const uint32_t a = d & 3u;
                     const int dlt = (int)ph - (int)a;
                     const uint32_t sh = (uint32_t)(dlt & 3) * 8u;
-                    uint32_t u[10];
-#pragma unroll
-                    for (int q = 0; q < 10; q++) u[q] = dlt < 0 ? (q ? n_t[q - 1] : 0u) : (q < 9 ? n_t[q] : 0u);
                     uint8_t* const wrow = win + (d - a);
+                    const uint32_t end = a + ml;                          // row-relative end of the match
+                    const uint32_t mt = end >> 2;                         // word that holds the tail (when end & 3)
+                    uint32_t hw = 0, tw = 0;
 #pragma unroll
                     for (int m = 0; m < 9; m++) {
-                        const int lo = 4 * m - (int)a;                    // first destination byte of word m
-                        if (lo < (int)ml) {
-                            const uint32_t wv = __funnelshift_r(u[m], u[m + 1], sh);
-                            if (lo >= 0 && lo + 4 <= (int)ml) *reinterpret_cast<uint32_t*>(wrow + 4 * m) = wv;
-                            else {
-#pragma unroll
-                                for (int bb = 0; bb < 4; bb++)
-                                    if (lo + bb >= 0 && lo + bb < (int)ml) wrow[4 * m + bb] = (uint8_t)(wv >> (8 * bb));
-                            }
-                        }
+                        const uint32_t lo_w = dlt < 0 ? (m ? n_t[m - 1] : 0u) : n_t[m];
+                        const uint32_t hi_w = dlt < 0 ? n_t[m] : (m < 8 ? n_t[m + 1] : 0u);
+                        const uint32_t wv = __funnelshift_r(lo_w, hi_w, sh);
+                        if (m == 0) hw = wv;
+                        if ((uint32_t)m == mt) tw = wv;
+                        if ((m > 0 || a == 0) && 4u * m + 4u <= end) *reinterpret_cast<uint32_t*>(wrow + 4 * m) = wv;
                     }
-                    code = (uint32_t)C::FLAG | d;
-                    for (uint32_t q = 0; q < ml; q++) ix[q] = (Code)(code + q);
+                    if (a) {                                              // head word: bytes a .. min(3, end - 1)
+#pragma unroll
+                        for (uint32_t bb = 1; bb < 4; bb++) if (bb >= a && bb < end) wrow[bb] = (uint8_t)(hw >> (8 * bb));
+                    }
+                    if ((end & 3u) && (mt > 0 || a == 0)) {               // tail word: bytes 0 .. (end & 3) - 1
+#pragma unroll
+                        for (uint32_t bb = 0; bb < 3; bb++) if (bb < (end & 3u)) wrow[4 * mt + bb] = (uint8_t)(tw >> (8 * bb));
+                    }
+                    fill_codes<Code>(ix, ml, (uint32_t)C::FLAG | d);
                 } else if (ml) {
                     const int32_t srel = (int32_t)(dl + ll) - (int32_t)off;             // step-relative source start
                     const uint32_t per = off < ml ? off : ml;                            // the match repeats with this period
                     const uint32_t nneg = srel < 0 ? ((uint32_t)(-srel) < per ? (uint32_t)(-srel) : per) : 0u;   // bytes that exist already
                     const uint32_t ecode = (uint32_t)C::FLAG | (uint32_t)((int32_t)sidx + srel);
-                    for (uint32_t q = 0; q < nneg; q++) ix[q] = (Code)(ecode + q);
-                    for (uint32_t q = nneg; q < per; q++) ix[q] = (Code)((uint32_t)srel + q);          // >= 0: produced by this step
+                    const uint32_t scode = (uint32_t)((int32_t)g0 + srel);               // + q >= g0: produced by this step
+                    fill_codes<Code>(ix, nneg, ecode);
+                    fill_codes<Code>(ix + nneg, per - nneg, scode + nneg);
                     uint32_t r = 0;
                     for (uint32_t q = per; q < ml; q++) {                                // overlap: byte q equals byte q mod per
-                        ix[q] = (Code)(r < nneg ? ecode + r : (uint32_t)srel + r);
+                        ix[q] = (Code)(r < nneg ? ecode + r : scode + r);
                         r = r + 1 == per ? 0u : r + 1;
                     }
                 }
@@ -440,31 +467,42 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
                 if (issued == 1) cp_async_wait_1(); else cp_async_wait_all();
             }
             __syncthreads();
-            // ---- resolve: byte-parallel, each thread chases its byte's code down to a byte that exists
+            // ---- resolve: byte-parallel; a thread takes one aligned window word (four bytes) per round, chases each
+            // byte's code down to a byte that exists, and stores the word.  Bytes of the word outside the step (before its
+            // start / behind its end) copy themselves.
             {
-                uint8_t* const wd = win + sidx;
-                for (uint32_t j = tid; j < wtot; j += 4 * T) {
-                    uint32_t c0 = idx[j], c1 = j + T < wtot ? (uint32_t)idx[j + T] : (uint32_t)C::FLAG,
-                             c2 = j + 2 * T < wtot ? (uint32_t)idx[j + 2 * T] : (uint32_t)C::FLAG,
-                             c3 = j + 3 * T < wtot ? (uint32_t)idx[j + 3 * T] : (uint32_t)C::FLAG;
-                    while (!((c0 & c1 & c2 & c3) & (uint32_t)C::FLAG)) {
-                        if (!(c0 & (uint32_t)C::FLAG)) c0 = idx[c0];
-                        if (!(c1 & (uint32_t)C::FLAG)) c1 = idx[c1];
-                        if (!(c2 & (uint32_t)C::FLAG)) c2 = idx[c2];
-                        if (!(c3 & (uint32_t)C::FLAG)) c3 = idx[c3];
+                constexpr uint32_t FL = (uint32_t)C::FLAG, M = FL - 1u;
+                const uint32_t a0 = sidx - g0;                           // aligned window offset of idx[0]
+                const uint32_t lim = g0 + wtot;
+                const uint32_t ng = (lim + 3u) >> 2;
+                for (uint32_t G = tid; G < ng; G += T) {
+                    uint32_t c0, c1, c2, c3;
+                    if constexpr (sizeof(Code) == 2) {
+                        const uint2 cc = *reinterpret_cast<const uint2*>(idx + 4 * G);
+                        c0 = cc.x & 0xFFFFu; c1 = cc.x >> 16; c2 = cc.y & 0xFFFFu; c3 = cc.y >> 16;
+                    } else {
+                        const uint4 cc = *reinterpret_cast<const uint4*>(idx + 4 * G);
+                        c0 = cc.x; c1 = cc.y; c2 = cc.z; c3 = cc.w;
                     }
-                    // path compression: later bytes of the step that chase into this one stop after one hop (a racing
-                    // reader sees the old or the new code; both lead to the same byte)
-                    idx[j] = (Code)c0;
-                    if (j + T < wtot) idx[j + T] = (Code)c1;
-                    if (j + 2 * T < wtot) idx[j + 2 * T] = (Code)c2;
-                    if (j + 3 * T < wtot) idx[j + 3 * T] = (Code)c3;
-                    constexpr uint32_t M = (uint32_t)C::FLAG - 1u;
-                    const uint8_t v0 = lz_smem[c0 & M], v1 = lz_smem[c1 & M], v2 = lz_smem[c2 & M], v3 = lz_smem[c3 & M];
-                    wd[j] = v0;
-                    if (j + T < wtot) wd[j + T] = v1;
-                    if (j + 2 * T < wtot) wd[j + 2 * T] = v2;
-                    if (j + 3 * T < wtot) wd[j + 3 * T] = v3;
+                    if (4 * G < g0 || 4 * G + 4 > lim) {                 // first / last word of the step
+                        const uint32_t self = FL | (a0 + 4 * G);
+                        if (4 * G + 0 < g0 || 4 * G + 0 >= lim) c0 = self;
+                        if (4 * G + 1 < g0 || 4 * G + 1 >= lim) c1 = self + 1;
+                        if (4 * G + 2 < g0 || 4 * G + 2 >= lim) c2 = self + 2;
+                        if (4 * G + 3 < g0 || 4 * G + 3 >= lim) c3 = self + 3;
+                    }
+                    while (!((c0 & c1 & c2 & c3) & FL)) {
+                        if (!(c0 & FL)) c0 = idx[c0];
+                        if (!(c1 & FL)) c1 = idx[c1];
+                        if (!(c2 & FL)) c2 = idx[c2];
+                        if (!(c3 & FL)) c3 = idx[c3];
+                    }
+                    // path compression: later bytes of the step that chase into these stop after one hop (a racing reader
+                    // sees the old or the new code; both lead to the same byte)
+                    if constexpr (sizeof(Code) == 2) *reinterpret_cast<uint2*>(idx + 4 * G) = make_uint2(c0 | (c1 << 16), c2 | (c3 << 16));
+                    else *reinterpret_cast<uint4*>(idx + 4 * G) = make_uint4(c0, c1, c2, c3);
+                    const uint32_t v0 = lz_smem[c0 & M], v1 = lz_smem[c1 & M], v2 = lz_smem[c2 & M], v3 = lz_smem[c3 & M];
+                    *reinterpret_cast<uint32_t*>(win + a0 + 4 * G) = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
                 }
             }
             if (more) { n_start = step_start + wtot; front2(); }
