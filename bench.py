@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--entries", type=int, default=1024, help="4 MiB files per GPU (cfg2: 8192 over 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--workers", type=int, default=2, help="host worker threads / contexts of the end-to-end path")
-    ap.add_argument("--group-mib", type=int, default=512, help="compressed MiB per pipelined entry group (end-to-end path)")
+    ap.add_argument("--group-mib", type=int, default=128, help="compressed MiB per pipelined entry group (end-to-end path)")
     ap.add_argument("--create", type=int, default=1, help="also measure the create path (GPU zstd + AES-CTR + CRC) on the same files")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -322,6 +322,26 @@ def main():
         for k in range(0, E, max(1, E // 16)):
             assert out_pinned[int(offs[k]):int(offs[k]) + sizes[k]].tobytes() == files[k], "e2e output differs from the source file"
     e2e_s = max_over_ranks(statistics.median(e2e_times)) if e2e_times else float('nan')
+    # PCIe yardstick for the end-to-end number: pinned <-> HBM copies of 1 GiB on this box (CUDA events); the transfer
+    # floor of a step is the slower direction (full duplex), everything else of e2e is pipeline fill and host work
+    pcie = None
+    if e2e_times and rank == 0:
+        nprobe = 1 << 30
+        hbuf = torch.empty(nprobe, dtype=torch.uint8, pin_memory=True)
+        dbuf = torch.empty(nprobe, dtype=torch.uint8, device="cuda")
+        pcie = {}
+        for name, dst, src in (("h2d_GBps", dbuf, hbuf), ("d2h_GBps", hbuf, dbuf)):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pa.record()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            pb.record()
+            torch.cuda.synchronize()
+            pcie[name] = 3 * nprobe / (pa.elapsed_time(pb) * 1e-3) / 1e9
+        pcie["transfer_floor_ms"] = max(archive_buf.size / pcie["h2d_GBps"], U / pcie["d2h_GBps"]) / 1e6
+        del hbuf, dbuf
 
     # ---- create path (BASELINE config 4 shape: GPU zstd encode + AES-256-CTR + FDAT CRC-32) on the same files
     create = None
@@ -389,7 +409,7 @@ def main():
             hb.close()
         ce2e_s = max_over_ranks(statistics.median(ce2e)) if ce2e else float("nan")
         create = {"metric": "create_uncompressed_GBps", "value": world * U / (c_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": c_ms,
-                  "e2e": {"value": world * U / ce2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U), "d2h_bytes_per_step": int(c_gpu),
+                  "e2e": {"value": world * U / ce2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U) * world, "d2h_bytes_per_step": int(c_gpu) * world,
                           "ms_per_step": ce2e_s * 1e3},
                   "codec": "gpu zstd (32 KiB blocks, predefined FSE, raw literals) + aes-256-ctr + crc32", "stage_ms": c_stage,
                   "gpu_launches": c_launches, "ratio": U / c_gpu, "c_gpu_over_c_ref": c_gpu / Cbytes,
@@ -452,8 +472,8 @@ def main():
             "dtype": "u8", "data": "synthetic", "config": dict(cfg, compressed_bytes_per_gpu=Cbytes, plain_bytes_per_gpu=U,
                                                              ratio=U / Cbytes),
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": world * U / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(archive_buf.size),
-                    "d2h_bytes_per_step": int(U), "ms_per_step": e2e_s * 1e3,
+            "e2e": {"value": world * U / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(archive_buf.size) * world,
+                    "d2h_bytes_per_step": int(U) * world, "ms_per_step": e2e_s * 1e3, "pcie": pcie,
                     "path": f"pna::Archive::read_header_from_slice + extract_files (C++ host layer, {args.workers} worker threads x 2 contexts, {args.group_mib} MiB entry groups software-pipelined create->run->fetch): index pass, H2D, chunk CRC check, decrypt, decode, D2H to pinned buffers; host clock"},
             "roofline": roof}
     if cpu:
