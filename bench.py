@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--workers", type=int, default=2, help="host worker threads / contexts of the end-to-end path")
     ap.add_argument("--group-mib", type=int, default=128, help="compressed MiB per pipelined entry group (end-to-end path)")
+    ap.add_argument("--create-workers", type=int, default=4)
+    ap.add_argument("--create-group-mib", type=int, default=256)
     ap.add_argument("--create", type=int, default=1, help="also measure the create path (GPU zstd + AES-CTR + CRC) on the same files")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -389,7 +391,7 @@ def main():
             barrier()
             t0 = time.perf_counter()
             blob = host.create_archive(list(zip(names, views)), compression=2, level=3, encryption=1, cipher_mode=1, key=key, phsf=opts.phsf,
-                                       ivs=ivs, max_chunk_size=0, device=local_rank, workers=args.workers, group_bytes=1024 << 20,
+                                       ivs=ivs, max_chunk_size=0, device=local_rank, workers=args.create_workers, group_bytes=args.create_group_mib << 20,
                                        out=arch_out)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0

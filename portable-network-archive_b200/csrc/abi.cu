@@ -31,6 +31,7 @@ struct pna_ctx {
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
+    std::vector<cudaEvent_t> ev_pool;   // stage-timing events, recycled between plans (no create/destroy per batch)
     CrcConsts* d_crc = nullptr;
     AesTables* d_aes = nullptr;
     CamelliaTables* d_cam = nullptr;
@@ -61,27 +62,29 @@ struct DevCache {
         else bytes = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
         int dev = 0;
         cudaGetDevice(&dev);
-        std::lock_guard<std::mutex> g(mu);
-        int best = -1;
-        for (int i = 0; i < (int)free_list.size(); i++) {
-            const Blk& b = free_list[i];
-            if (b.dev != dev || b.bytes < bytes || b.bytes > bytes + bytes / 2 + ((size_t)4 << 20)) continue;
-            if (best < 0 || b.bytes < free_list[best].bytes) best = i;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_list.size(); i++) {
+                const Blk& b = free_list[i];
+                if (b.dev != dev || b.bytes < bytes || b.bytes > bytes + bytes / 2 + ((size_t)4 << 20)) continue;
+                if (best < 0 || b.bytes < free_list[best].bytes) best = i;
+            }
+            if (best >= 0) {
+                *out = free_list[best].p;
+                live[*out] = {free_list[best].bytes, dev};
+                free_list.erase(free_list.begin() + best);
+                return cudaSuccess;
+            }
         }
-        if (best >= 0) {
-            *out = free_list[best].p;
-            live[*out] = {free_list[best].bytes, dev};
-            free_list.erase(free_list.begin() + best);
-            return cudaSuccess;
-        }
+        // the driver call runs outside the lock: other threads keep hitting the cache meanwhile
         cudaError_t e = cudaMalloc(out, bytes);
         if (e != cudaSuccess) {   // give cached blocks back to the driver and retry once
             cudaGetLastError();
-            for (const Blk& b : free_list) if (b.dev == dev) cudaFree(b.p);
-            free_list.erase(std::remove_if(free_list.begin(), free_list.end(), [&](const Blk& b) { return b.dev == dev; }), free_list.end());
+            trim(dev);
             e = cudaMalloc(out, bytes);
         }
-        if (e == cudaSuccess) live[*out] = {bytes, dev};
+        if (e == cudaSuccess) { std::lock_guard<std::mutex> g(mu); live[*out] = {bytes, dev}; }
         return e;
     }
     void release(void* p) {
@@ -216,7 +219,7 @@ struct pna_plan {
     // encode side
     enc::EncodePlan* enc = nullptr;
     ~pna_plan() {
-        if (ev_ready) for (auto& e : ev) cudaEventDestroy(e);
+        if (ev_ready) for (auto& e : ev) { if (ctx) ctx->ev_pool.push_back(e); else cudaEventDestroy(e); }
         d_buf.release(); d_out.release(); d_lits.release(); d_entries.release(); d_entries_init.release();
         d_segs.release(); d_keys.release();
         for (auto& t : d_tiles) t.release();
@@ -290,6 +293,7 @@ extern "C" void pna_cuda_destroy(pna_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     g_dev_cache.trim(ctx->device);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->d_aes) cudaFree(ctx->d_aes);
@@ -794,7 +798,10 @@ static int decode_launch_all(pna_plan* P, bool fresh) {
     int rc;
     const uint64_t l0 = ctx->launches;
     if (!P->ev_ready) {
-        for (auto& e : P->ev) CK(cudaEventCreate(&e));
+        for (auto& e : P->ev) {
+            if (!ctx->ev_pool.empty()) { e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else CK(cudaEventCreate(&e));
+        }
         P->ev_ready = true;
     }
     if (fresh) {

@@ -218,7 +218,10 @@ static int encode_launch_all(pna_plan* P) {
     const uint64_t l0 = ctx->launches;
     const uint32_t n = P->n, nsegs = (uint32_t)E->h_segs.size();
     if (!P->ev_ready) {
-        for (auto& e : P->ev) CK(cudaEventCreate(&e));
+        for (auto& e : P->ev) {
+            if (!ctx->ev_pool.empty()) { e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else CK(cudaEventCreate(&e));
+        }
         P->ev_ready = true;
     }
     CK(cudaMemcpyAsync(E->d_entries.p, E->d_entries_init.p, n * sizeof(EncEntry), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -15,6 +15,18 @@
 
 namespace pna {
 
+// uploads in flight per process: PCIe is the shared resource; two slots let one batch's host-side set-up run under the
+// other's DMA while still staggering the workers
+struct Slots {
+    std::mutex mu;
+    std::condition_variable cv;
+    int free_;
+    explicit Slots(int n) : free_(n) {}
+    void acquire() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return free_ > 0; }); free_--; }
+    void release() { { std::lock_guard<std::mutex> lk(mu); free_++; } cv.notify_one(); }
+};
+struct SlotGuard { Slots& s; explicit SlotGuard(Slots& x) : s(x) { s.acquire(); } ~SlotGuard() { s.release(); } };
+
 static const uint8_t SIGNATURE[8] = {0x89, 'P', 'N', 'A', 0x0D, 0x0A, 0x1A, 0x0A};
 static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 static inline void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
@@ -430,11 +442,15 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
     std::vector<uint8_t> ready(groups.size() + 1, 0);
     base[0] = 8 + 20; ready[0] = 1;
     std::mutex mu;
+    Slots h2d_slots(2);
     std::condition_variable cv;
     std::atomic<size_t> next{0};
     std::string err_msg;
     int err_kind = 0;
     bool failed = false;
+    const bool trace = getenv("PNA_HOST_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     auto work = [&]() {
         size_t g = 0;
         try {
@@ -442,6 +458,7 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
             for (;;) {
                 g = next.fetch_add(1);
                 if (g >= groups.size()) break;
+                const double tl = ms_now();
                 const Group G = groups[g];
                 const uint32_t m = (uint32_t)(G.hi - G.lo);
                 std::vector<pna_encode_desc> descs(m);
@@ -457,7 +474,15 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
                     crc_total += pna_cuda_encode_crc_count(&d);
                 }
                 pna_plan* plan = nullptr;
-                ck(L.ctx, pna_cuda_encode_plan_create(L.ctx, descs.data(), m, &plan), "encode_plan_create");
+                double tr0;
+                {
+                    // one upload at a time: PCIe is the shared resource, and taking turns staggers the workers so that one
+                    // group's kernels run while the next group's plaintext is still on its way
+                    SlotGuard h2d(h2d_slots);
+                    tr0 = ms_now();
+                    ck(L.ctx, pna_cuda_encode_plan_create(L.ctx, descs.data(), m, &plan), "encode_plan_create");
+                }
+                const double tr1 = ms_now();
                 struct PlanGuard { pna_plan* p; ~PlanGuard() { if (p) pna_cuda_plan_destroy(p); } } guard{plan};
                 ck(L.ctx, pna_cuda_encode_plan_run(plan), "encode_plan_run");
                 // metadata chunks (type || data, contiguous) and their CRCs in one GPU batch while the encode kernels run
@@ -494,7 +519,9 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
                 }
                 std::vector<uint64_t> lens(m);
                 std::vector<int32_t> st(m);
+                const double tr2 = ms_now();
                 ck(L.ctx, pna_cuda_encode_plan_lengths(plan, lens.data(), st.data()), "encode_plan_lengths");
+                const double tr3 = ms_now();
                 // layout of this group
                 std::vector<uint64_t> entry_pos(m + 1, 0);
                 const size_t metas_per_entry = enc ? 5 : 3;
@@ -531,7 +558,9 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
                     else { stage[k].resize(lens[k]); bufs[k] = pna_buf{stage[k].data(), lens[k], 0}; }
                 }
                 std::vector<uint32_t> crcs(crc_total + 1), ncrc(m, 0);
+                const double tr4 = ms_now();
                 ck(L.ctx, pna_cuda_encode_plan_fetch(plan, bufs.data(), crcs.data(), ncrc.data(), st.data()), "encode_plan_fetch");
+                const double tr5 = ms_now();
                 size_t cpos = 0;
                 for (uint32_t k = 0; k < m; k++) {
                     if (st[k] != PNA_OK) throw Error(st[k], files[G.lo + k].name + ": fetch failed");
@@ -561,6 +590,8 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
                     put_meta(k * metas_per_entry + metas_per_entry - 1);   // FEND
                     cpos += ncrc[k];
                 }
+                if (trace) fprintf(stderr, "[pna_host] create group %zu (%u files): top %.1f plan_create/H2D %.1f-%.1f, run+meta -%.1f, lengths(wait) -%.1f, place -%.1f, fetch/D2H -%.1f, frames -%.1f ms\n",
+                                   g, m, tl, tr0, tr1, tr2, tr3, tr4, tr5, ms_now());
             }
         } catch (const Error& e) {
             std::lock_guard<std::mutex> lk(mu);

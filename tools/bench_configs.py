@@ -105,7 +105,7 @@ def archive_of(entries, phsf, into):
     return buf
 
 
-def timed_extract(host, ctx, archive_buf, phsf, key, U, nfiles, reps=3, workers=1):
+def timed_extract(host, ctx, archive_buf, phsf, key, U, nfiles, reps=3, workers=2, group_mib=64):
     import torch
     out = ctx.pinned(U + 16 * nfiles + 64)
     ts, t_index = [], []
@@ -115,7 +115,7 @@ def timed_extract(host, ctx, archive_buf, phsf, key, U, nfiles, reps=3, workers=
         t1 = time.perf_counter()
         if phsf:
             ha.set_key(phsf, key)
-        _, offs, st = ha.extract_files(out=out, device=0, workers=workers, group_bytes=4096 << 20, verify=True)
+        _, offs, st = ha.extract_files(out=out, device=0, workers=workers, group_bytes=group_mib << 20, verify=True)
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
         t_index.append(t1 - t0)
@@ -130,6 +130,8 @@ def main():
     ap.add_argument("--cfg5-files", type=int, default=32)
     ap.add_argument("--cfg1-files", type=int, default=2500)
     ap.add_argument("--only", default="")
+    ap.add_argument("--workers", type=int, default=2)
+    ap.add_argument("--group-mib", type=int, default=64)
     args = ap.parse_args()
     import multiprocessing as mp
     pna = importlib.import_module("portable-network-archive_b200")
@@ -150,7 +152,7 @@ def main():
         buf = archive_of([(f"s/{i:07d}", bytes([0, 0, 0, 1, 2, 0]), sizes[i], streams[i], 16) for i in range(n)], opts.phsf, ctx.pinned)
         # kernel-only through one plan
         ha = pna.Archive.read_header(buf, ctx, verify=False) if n <= 20000 else None
-        dt, t_index, out, offs, st, flist = timed_extract(host, ctx, buf, opts.phsf, key, U, n)
+        dt, t_index, out, offs, st, flist = timed_extract(host, ctx, buf, opts.phsf, key, U, n, workers=args.workers, group_mib=args.group_mib)
         assert st == [0] * n
         for k in range(0, n, max(1, n // 64)):
             assert out[int(offs[k]):int(offs[k]) + sizes[k]].tobytes() == files[k]
