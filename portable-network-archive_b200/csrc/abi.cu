@@ -185,6 +185,8 @@ struct pna_plan {
     std::vector<DevKeys> h_keys;
     std::vector<CipherTile> h_tiles[5];   // 0 gather, 1 aes-ctr, 2 aes-cbc, 3 camellia-ctr, 4 camellia-cbc
     std::vector<uint32_t> h_store, h_deflate;
+    std::vector<inf::InfStream> h_inf;          // deflate streams of the two-stage path (tokens -> LZ -> Adler)
+    std::vector<uint32_t> h_deflate_big;        // streams of 2 GiB and more: one-thread-per-stream kernel
     std::vector<zs::ZEntry> h_ze;
     std::vector<CopyJob> h_copy;
     uint64_t image_bytes = 0, buf_bytes = 0, out_bytes = 0;
@@ -199,6 +201,12 @@ struct pna_plan {
     DevArr<zs::ZEntry> d_ze;
     DevArr<zs::ZBlock> d_blocks;
     DevArr<uint64_t> d_lit_base, d_seq_base;
+    DevArr<inf::InfStream> d_inf;
+    DevArr<uint8_t> d_inf_lits;
+    DevArr<zs::SeqRec> d_inf_recs;
+    DevArr<zs::ZBlock> d_inf_blocks;
+    DevArr<zs::ZEntry> d_inf_ze;
+    DevArr<inf::InfTrailer> d_inf_tr;
     DevArr<CopyJob> d_copy;
     uint32_t n_blocks = 0;
     uint64_t lit_total = 0, seq_total = 0;
@@ -225,6 +233,7 @@ struct pna_plan {
         for (auto& t : d_tiles) t.release();
         d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
+        d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release();
         if (enc) enc::destroy(enc);
     }
 };
@@ -279,6 +288,7 @@ extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
     ok = ok && cudaFuncSetAttribute(ecb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(inf::inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inf::TOKEN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::SEQ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LIT_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_lz_kernel<zs::LzSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LzSmall::BYTES) == cudaSuccess;
@@ -524,6 +534,7 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
         else { zs::ZEntry z; memset(&z, 0, sizeof z); z.entry = i; P->h_ze.push_back(z); }
     }
     P->need_sizing = !all_caps;
+    std::stable_sort(P->h_deflate.begin(), P->h_deflate.end(), [&](uint32_t a, uint32_t b) { return P->h_entries[a].comp_len > P->h_entries[b].comp_len; });
     // device arrays + upload
     CK(P->d_buf.reserve(P->buf_bytes));
     CK(P->d_entries.reserve(n)); CK(P->d_entries_init.reserve(n));
@@ -571,6 +582,27 @@ static int decode_layout_out(pna_plan* P) {
         const EntryRec& e = P->h_entries[i];
         uint64_t len = std::min(e.comp_len, e.out_cap);
         for (uint64_t o = 0; o < len; o += 256 * 1024) P->h_copy.push_back({e.out_off + o, e.comp_off + o, std::min<uint64_t>(256 * 1024, len - o)});
+    }
+    // deflate: streams of the two-stage path with their literal / record arenas (sizes from the now final capacities)
+    P->h_inf.clear(); P->h_deflate_big.clear();
+    {
+        uint64_t lit = 0, rec = 0;
+        for (uint32_t i : P->h_deflate) {
+            const EntryRec& e = P->h_entries[i];
+            if (e.status != ST_OK) continue;
+            if (e.out_cap >= 0x7FFFFFFFull) { P->h_deflate_big.push_back(i); continue; }
+            P->h_inf.push_back({i, 0u, lit, rec});
+            lit += align_up(e.out_cap, 16) + 16;
+            rec += inf::token_rec_bound(e.out_cap);
+        }
+        const size_t ni = P->h_inf.size();
+        if (ni) {
+            CK(P->d_inf.reserve(ni)); CK(P->d_inf_lits.reserve(lit + 256)); CK(P->d_inf_recs.reserve(rec + 32));
+            CK(P->d_inf_blocks.reserve(ni)); CK(P->d_inf_ze.reserve(ni)); CK(P->d_inf_tr.reserve(ni));
+            CK(cudaMemcpyAsync(P->d_inf.p, P->h_inf.data(), ni * sizeof(inf::InfStream), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (!P->h_deflate_big.empty())
+            CK(cudaMemcpyAsync(P->d_deflate.p, P->h_deflate_big.data(), P->h_deflate_big.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (!P->h_copy.empty()) {
         CK(P->d_copy.reserve(P->h_copy.size()));
@@ -674,31 +706,59 @@ static int launch_zstd_prefix(pna_plan* P) {
     LAUNCHED();
     return PNA_OK;
 }
-static int launch_zstd_lz(pna_plan* P) {
+static int launch_zstd_lz_on(pna_plan* P, const zs::ZEntry* ze, const uint32_t* order, uint32_t nz, const zs::ZBlock* blocks,
+                             const uint8_t* lits, const zs::SeqRec* seqs) {
     pna_ctx* ctx = P->ctx;
-    const uint32_t nz = (uint32_t)P->h_ze.size();
     if (!nz) return PNA_OK;
     // one CTA per entry, longest streams first.  Fewer entries than half the SMs (a solid archive is ONE frame): the
-    // 32-warp variant with the 128 KiB window; otherwise 4 warps per entry, 7 entries per SM.
+    // 16-warp variant with the 128 KiB window; otherwise 4 warps per entry, 7 entries per SM.
     const char* force = getenv("PNA_LZ_VARIANT");
     const bool big = force ? force[0] == 'b' : nz * 2 <= (uint32_t)ctx->sm_count;
     if (big)
-        zs::zstd_lz_kernel<zs::LzBig><<<nz, zs::LzBig::T, zs::LzBig::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_lz_order.p, nz,
-                                                                                            P->d_blocks.p, P->d_lits.p, P->d_seqs.p, P->d_out.p);
+        zs::zstd_lz_kernel<zs::LzBig><<<nz, zs::LzBig::T, zs::LzBig::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, ze, order, nz, blocks, lits,
+                                                                                            seqs, P->d_out.p);
     else
-        zs::zstd_lz_kernel<zs::LzSmall><<<nz, zs::LzSmall::T, zs::LzSmall::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_lz_order.p, nz,
-                                                                                                P->d_blocks.p, P->d_lits.p, P->d_seqs.p, P->d_out.p);
+        zs::zstd_lz_kernel<zs::LzSmall><<<nz, zs::LzSmall::T, zs::LzSmall::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, ze, order, nz, blocks,
+                                                                                                lits, seqs, P->d_out.p);
     LAUNCHED();
     return PNA_OK;
 }
+// size_only (before the output layout exists): one lane per stream counts the decoded length of EVERY deflate entry.
+// Otherwise: tokens -> LZ -> Adler for the two-stage streams, the bits-to-bytes kernel for the >= 2 GiB ones.
 static int launch_inflate(pna_plan* P, int size_only) {
     pna_ctx* ctx = P->ctx;
-    const uint32_t nd = (uint32_t)P->h_deflate.size();
-    if (!nd) return PNA_OK;
-    inf::inflate_kernel<<<(nd + inf::INFLATE_CTA - 1) / inf::INFLATE_CTA, 32 * inf::INFLATE_CTA, sizeof(inf::Tables) * inf::INFLATE_CTA,
-                          ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_deflate.p, nd, P->d_out.p, size_only);
-    LAUNCHED();
+    if (size_only) {
+        const uint32_t nd = (uint32_t)P->h_deflate.size();
+        if (!nd) return PNA_OK;
+        std::vector<inf::InfStream> all(nd);
+        for (uint32_t k = 0; k < nd; k++) all[k] = {P->h_deflate[k], 0u, 0ull, 0ull};
+        CK(P->d_inf.reserve(nd));
+        CK(cudaMemcpyAsync(P->d_inf.p, all.data(), nd * sizeof(inf::InfStream), cudaMemcpyHostToDevice, ctx->stream));
+        inf::inflate_tokens_kernel<<<(nd + inf::TOKEN_CTA - 1) / inf::TOKEN_CTA, inf::TOKEN_CTA, inf::TOKEN_SMEM_BYTES, ctx->stream>>>(
+            P->d_buf.p, P->d_entries.p, P->d_inf.p, nd, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
+        LAUNCHED();
+        CK(cudaStreamSynchronize(ctx->stream));   // `all` is a local
+        return PNA_OK;
+    }
+    const uint32_t ni = (uint32_t)P->h_inf.size(), nb = (uint32_t)P->h_deflate_big.size();
+    if (ni) {
+        inf::inflate_tokens_kernel<<<(ni + inf::TOKEN_CTA - 1) / inf::TOKEN_CTA, inf::TOKEN_CTA, inf::TOKEN_SMEM_BYTES, ctx->stream>>>(
+            P->d_buf.p, P->d_entries.p, P->d_inf.p, ni, P->d_inf_lits.p, P->d_inf_recs.p, P->d_inf_blocks.p, P->d_inf_ze.p, P->d_inf_tr.p, 0);
+        LAUNCHED();
+        int rc = launch_zstd_lz_on(P, P->d_inf_ze.p, nullptr, ni, P->d_inf_blocks.p, P->d_inf_lits.p, P->d_inf_recs.p);
+        if (rc) return rc;
+        inf::inflate_adler_kernel<<<(ni + 7) / 8, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_inf.p, P->d_inf_tr.p, ni, P->d_out.p);
+        LAUNCHED();
+    }
+    if (nb) {
+        inf::inflate_kernel<<<(nb + inf::INFLATE_CTA - 1) / inf::INFLATE_CTA, 32 * inf::INFLATE_CTA, sizeof(inf::Tables) * inf::INFLATE_CTA,
+                              ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_deflate.p, nb, P->d_out.p, 0);
+        LAUNCHED();
+    }
     return PNA_OK;
+}
+static int launch_zstd_lz(pna_plan* P) {
+    return launch_zstd_lz_on(P, P->d_ze.p, P->d_lz_order.p, (uint32_t)P->h_ze.size(), P->d_blocks.p, P->d_lits.p, P->d_seqs.p);
 }
 static int launch_store(pna_plan* P) {
     pna_ctx* ctx = P->ctx;

@@ -142,23 +142,86 @@ PNA_HD int len_extra(int s) { return s < 8 ? 0 : s == 28 ? 0 : (s >> 2) - 1; }
 PNA_HD uint32_t dist_base(int s) { return s < 4 ? (uint32_t)(1 + s) : (uint32_t)(((2 + (s & 1)) << ((s >> 1) - 1)) + 1); }
 PNA_HD int dist_extra(int s) { return s < 4 ? 0 : (s >> 1) - 1; }
 
-// Decode one zlib stream.  `t` is per-thread scratch.  Returns status; *out_len = bytes produced
-// (exact decoded length even when it exceeds cap -> ST_NOSPACE).
-PNA_HD int32_t inflate_zlib(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, Tables* t) {
-    *out_len = 0;
-    if (n == 0) return ST_OK;   // nothing in, nothing out (zio::read: eof with no data -> Ok(0))
-    if (n < 2) return ST_OK;    // truncated header: short read, no error
+// Where the decoded symbols go.  DirectEmit writes the output itself (byte stores, match copies through the output,
+// Adler-32 on the way): one thread owns one stream from bits to bytes.  TokenEmit only records WHAT the stream says --
+// literal bytes into a literal buffer and one 8-byte (offset, literal run | match length << 16) record per match, the
+// same records the zstd sequence stage produces -- so that the bit-serial part of DEFLATE runs one stream per LANE
+// without any output traffic, and the LZ stage (zstd_lz_kernel, one CTA per stream) executes the copies in parallel.
+// Both keep counting when the output no longer fits (the symbol stream never depends on output bytes).
+struct DirectEmit {
+    uint8_t* out;
+    uint64_t cap, op;
+    uint32_t a1, a2, a_pending;   // Adler-32 running sums, bytes since the last modulo
+    bool counting;
+    PNA_HD void init(uint8_t* o, uint64_t c) { out = o; cap = c; op = 0; a1 = 1; a2 = 0; a_pending = 0; counting = false; }
+    PNA_HD void lit(uint8_t c) {
+        if (op < cap) {
+            out[op] = c; a1 += c; a2 += a1;
+            if (++a_pending == 5552) { a1 %= 65521u; a2 %= 65521u; a_pending = 0; }
+        } else counting = true;
+        op++;
+    }
+    PNA_HD void match(uint32_t len, uint32_t dist) {
+        if (op + len <= cap) {
+            uint32_t k = 0;
+            if (dist >= 8) {   // eight source bytes are loaded before the first of them is stored: the loads overlap
+                for (; k + 8 <= len; k += 8) {
+                    uint8_t t[8];
+                    for (int q = 0; q < 8; q++) t[q] = out[op - dist + q];
+                    for (int q = 0; q < 8; q++) lit(t[q]);
+                }
+            }
+            for (; k < len; k++) lit(out[op - dist]);
+        } else {
+            for (uint32_t k = 0; k < len; k++) {
+                if (op < cap) lit(out[op - dist]);
+                else { counting = true; op++; }
+            }
+        }
+    }
+    // Adler-32 trailer check; want = stored value
+    PNA_HD bool trailer_ok(uint32_t want) { a1 %= 65521u; a2 %= 65521u; return want == ((a2 << 16) | a1); }
+    PNA_HD void no_trailer() {}
+};
+struct TokenRec { uint32_t x, y; };   // layout of zs::SeqRec: x = offset, y = literal run | match length << 16
+constexpr uint32_t TOKEN_RUN_MAX = 65534;   // longest literal run one record carries (0xFFFF is the zstd escape value)
+struct TokenEmit {
+    uint8_t* lits;
+    TokenRec* recs;
+    uint64_t cap, op;
+    uint32_t nlit, nrec, run;
+    uint32_t want;        // stored Adler-32 (checked by the Adler pass over the finished output)
+    bool counting, has_trailer;
+    PNA_HD void init(uint8_t* l, TokenRec* r, uint64_t c) {
+        lits = l; recs = r; cap = c; op = 0; nlit = 0; nrec = 0; run = 0; want = 0; counting = false; has_trailer = false;
+    }
+    PNA_HD void lit(uint8_t c) {
+        if (op < cap) {
+            if (run == TOKEN_RUN_MAX) { recs[nrec].x = 1u; recs[nrec].y = run; nrec++; run = 0; }   // run continues in the next record
+            lits[nlit++] = c; run++;
+        } else counting = true;
+        op++;
+    }
+    PNA_HD void match(uint32_t len, uint32_t dist) {
+        if (op + len <= cap) { recs[nrec].x = dist; recs[nrec].y = run | (len << 16); nrec++; run = 0; }
+        else counting = true;
+        op += len;
+    }
+    PNA_HD bool trailer_ok(uint32_t w) { want = w; has_trailer = true; return true; }
+    PNA_HD void no_trailer() { has_trailer = false; }
+};
+
+// Decode one zlib stream into emitter `E`.  `t` is per-thread scratch.  Returns status; E.op = bytes produced
+// (exact decoded length even when it exceeds the capacity -> ST_NOSPACE).
+template <class Emit>
+PNA_HD int32_t inflate_zlib_to(Emit& E, const uint8_t* in, uint64_t n, Tables* t) {
+    if (n == 0) { E.no_trailer(); return ST_OK; }   // nothing in, nothing out (zio::read: eof with no data -> Ok(0))
+    if (n < 2) { E.no_trailer(); return ST_OK; }    // truncated header: short read, no error
     uint32_t cmf = in[0], flg = in[1];
     if (((cmf << 8) | flg) % 31 != 0 || (cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 0x20)) return ST_INVALID_INPUT;
     Bits b;
     b.init(in + 2, n - 2);
-    uint64_t op = 0;
-    uint32_t a1 = 1, a2 = 0;       // Adler-32 running sums
-    uint32_t a_pending = 0;        // bytes since the last modulo
-    bool counting = false;         // true once the output no longer fits
-#define PNA_INF_TRUNC() do { *out_len = op; return counting ? ST_NOSPACE : ST_OK; } while (0)
-#define PNA_INF_EMIT(c_) do { uint8_t c__ = (uint8_t)(c_); if (op < cap) { out[op] = c__; a1 += c__; a2 += a1; \
-        if (++a_pending == 5552) { a1 %= 65521u; a2 %= 65521u; a_pending = 0; } } else counting = true; op++; } while (0)
+#define PNA_INF_TRUNC() do { E.no_trailer(); return E.counting ? ST_NOSPACE : ST_OK; } while (0)
     int last = 0;
     while (!last) {
         last = (int)b.get(1);
@@ -172,7 +235,7 @@ PNA_HD int32_t inflate_zlib(const uint8_t* in, uint64_t n, uint8_t* out, uint64_
             if (len != (~nlen & 0xFFFFu)) return ST_INVALID_INPUT;
             uint64_t avail = b.n - b.pos;
             uint32_t take = len <= avail ? len : (uint32_t)avail;
-            for (uint32_t i = 0; i < take; i++) PNA_INF_EMIT(b.p[b.pos + i]);
+            for (uint32_t i = 0; i < take; i++) E.lit(b.p[b.pos + i]);
             b.pos += take;
             if (take < len) PNA_INF_TRUNC();
             continue;
@@ -224,56 +287,54 @@ PNA_HD int32_t inflate_zlib(const uint8_t* in, uint64_t n, uint8_t* out, uint64_
             err = build(&t->dist, lengths + nlen, ndist);
             if (err && (err < 0 || ndist != t->dist.count[0] + t->dist.count[1])) return ST_INVALID_INPUT;
         }
-        // symbols
+        // symbols.  Single-exit loop without returns inside: with one stream per LANE the literal and the match arm must
+        // reconverge every iteration (an early return inside an arm leaves the lanes split for the rest of the block).
+        int rc = -1;   // -1 continue, 0 end of block, 1 truncated, 2 invalid
         for (;;) {
             int sym = decode_sym(b, &t->len);
-            if (b.overrun()) PNA_INF_TRUNC();
-            if (sym < 0) return ST_INVALID_INPUT;
-            if (sym < 256) {
-                PNA_INF_EMIT(sym);
-            } else if (sym == 256) {
-                break;
-            } else {
+            if (b.overrun()) rc = 1;
+            else if (sym < 0) rc = 2;
+            else if (sym < 256) E.lit((uint8_t)sym);
+            else if (sym == 256) rc = 0;
+            else {
                 sym -= 257;
-                if (sym >= 29) return ST_INVALID_INPUT;
-                uint32_t len = len_base(sym) + b.get(len_extra(sym));
-                int ds = decode_sym(b, &t->dist);
-                if (b.overrun()) PNA_INF_TRUNC();
-                if (ds < 0 || ds >= 30) return ST_INVALID_INPUT;
-                uint32_t dist = dist_base(ds) + b.get(dist_extra(ds));
-                if (b.overrun()) PNA_INF_TRUNC();
-                if (dist > op) return ST_INVALID_INPUT;
-                if (op + len <= cap) {
-                    uint32_t k = 0;
-                    if (dist >= 8) {   // eight source bytes are loaded before the first of them is stored: the loads overlap
-                        for (; k + 8 <= len; k += 8) {
-                            uint8_t t[8];
-                            for (int q = 0; q < 8; q++) t[q] = out[op - dist + q];
-                            for (int q = 0; q < 8; q++) PNA_INF_EMIT(t[q]);
-                        }
-                    }
-                    for (; k < len; k++) PNA_INF_EMIT(out[op - dist]);
-                } else {
-                    for (uint32_t k = 0; k < len; k++) {
-                        if (op < cap) PNA_INF_EMIT(out[op - dist]);
-                        else { counting = true; op++; }
+                if (sym >= 29) rc = 2;
+                else {
+                    const uint32_t len = len_base(sym) + b.get(len_extra(sym));
+                    const int ds = decode_sym(b, &t->dist);
+                    if (b.overrun()) rc = 1;
+                    else if (ds < 0 || ds >= 30) rc = 2;
+                    else {
+                        const uint32_t dist = dist_base(ds) + b.get(dist_extra(ds));
+                        if (b.overrun()) rc = 1;
+                        else if (dist > E.op) rc = 2;
+                        else E.match(len, dist);
                     }
                 }
             }
+            if (rc >= 0) break;
         }
+        if (rc == 1) PNA_INF_TRUNC();
+        if (rc == 2) return ST_INVALID_INPUT;
     }
-    *out_len = op;
-    if (counting) return ST_NOSPACE;
+    if (E.counting) { E.no_trailer(); return ST_NOSPACE; }
     // Adler-32 trailer (big endian) after discarding to the byte boundary
     uint64_t tpos = (b.consumed_bits() + 7) / 8;
-    if (tpos + 4 > b.n) return ST_OK;  // truncated trailer: short read, no error
+    if (tpos + 4 > b.n) { E.no_trailer(); return ST_OK; }  // truncated trailer: short read, no error
     const uint8_t* tr = b.p + tpos;
     uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
-    a1 %= 65521u; a2 %= 65521u;
-    if (want != ((a2 << 16) | a1)) return ST_INVALID_INPUT;
+    if (!E.trailer_ok(want)) return ST_INVALID_INPUT;
     return ST_OK;
 #undef PNA_INF_TRUNC
-#undef PNA_INF_EMIT
+}
+
+// One stream from bits to bytes by one thread (see DirectEmit).
+PNA_HD int32_t inflate_zlib(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, Tables* t) {
+    DirectEmit E;
+    E.init(out, cap);
+    const int32_t st = inflate_zlib_to(E, in, n, t);
+    *out_len = (st == ST_OK || st == ST_NOSPACE) ? E.op : E.op;
+    return st;
 }
 
 }  // namespace inf
