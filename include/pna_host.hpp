@@ -49,11 +49,20 @@ enum class DataKind : uint8_t { File = 0, Directory = 1, SymbolicLink = 2, HardL
 
 struct EntryInfo {       // NormalEntry (kind 0) or SolidEntry (kind 1) as the index pass sees it
     uint8_t kind = 0, data_kind = 0, compression = 0, encryption = 0, cipher_mode = 0;
-    std::string name, phsf;
+    std::string name;
+    std::shared_ptr<const std::string> phsf_;   // PHSF string, shared by all entries that carry the same one
     bool has_phsf = false;
+    const std::string& phsf() const { static const std::string none; return phsf_ ? *phsf_ : none; }
     uint64_t raw_file_size = UINT64_MAX;     // fSIZ
     uint64_t compressed_size = 0;
-    std::vector<pna_span> bodies;            // FDAT / SDAT bodies, in order
+    struct Bodies {                          // FDAT / SDAT bodies, in order: a view into the owning archive's span pool
+        const pna_span* p = nullptr;
+        uint32_t n = 0;
+        const pna_span* data() const { return p; }
+        size_t size() const { return n; }
+        const pna_span* begin() const { return p; }
+        const pna_span* end() const { return p + n; }
+    } bodies;
     uint32_t chunk_begin = 0, chunk_end = 0; // chunk index range [begin, end) incl. FHED..FEND
 };
 
@@ -90,12 +99,13 @@ private:
     struct FileRef { uint32_t owner; uint32_t entry; };   // owner: 0 = top-level archive, k+1 = inner archive of solid k
     // inner archive of a solid entry: host copy for the index pass, and the decode plan whose output (the same bytes)
     // stays resident in HBM for the inner chunk CRC check and for range copies of STORE entries
-    struct Inner { std::vector<uint8_t> bytes; std::vector<RawChunk> chunks; std::vector<EntryInfo> entries; std::shared_ptr<pna_plan> plan; };
+    struct Inner { std::vector<uint8_t> bytes; std::vector<RawChunk> chunks; std::vector<EntryInfo> entries; std::vector<pna_span> body_pool; std::shared_ptr<pna_plan> plan; };
     const uint8_t* buf_ = nullptr;
     size_t len_ = 0;
     uint32_t archive_number_ = 0;
     std::vector<RawChunk> chunks_;
     std::vector<EntryInfo> entries_;
+    std::vector<pna_span> body_pool_;          // every FDAT / SDAT body of the top-level archive (EntryInfo::bodies point here)
     std::vector<Inner> inner_;
     std::vector<FileRef> refs_;
     std::vector<FileOut> files_;

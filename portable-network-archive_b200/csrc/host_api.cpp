@@ -53,32 +53,106 @@ static void ck(pna_ctx* ctx, int rc, const char* what) {
 }
 
 // ---- index pass: walk chunk frames without touching chunk data (bytes::skip_chunk semantics, lib/src/bytes.rs:90)
-static void index_chunks(const uint8_t* buf, size_t len, size_t pos, std::vector<RawChunk>& out) {
-    while (pos < len) {
-        if (len - pos < 12) throw Error(PNA_E_UNEXPECTED_EOF, "truncated chunk");
+static inline uint32_t ty32(const char* t) { uint32_t v; memcpy(&v, t, 4); return v; }
+static inline uint32_t ty32(const RawChunk& c) { return ty32(c.ty); }
+static const uint32_t T_AEND = ty32("AEND"), T_ANXT = ty32("ANXT"), T_FHED = ty32("FHED"), T_SHED = ty32("SHED"), T_FEND = ty32("FEND"),
+                      T_SEND = ty32("SEND"), T_FDAT = ty32("FDAT"), T_SDAT = ty32("SDAT"), T_PHSF = ty32("PHSF"), T_fSIZ = ty32("fSIZ");
+static inline bool ty_letters(uint32_t t) {   // every byte an ASCII letter (chunk/types.rs:204): bit 6 set, low five bits in 1..26
+    const uint32_t low = t & 0x1F1F1F1Fu;
+    return (t & 0xC0C0C0C0u) == 0x40404040u && !((low - 0x01010101u) & 0x80808080u) && !((0x1A1A1A1Au - low) & 0x80808080u);
+}
+// serial walk from `pos` until `stop` (the first chunk that starts at or behind it is not taken); returns where it stopped
+static size_t walk_chunks(const uint8_t* buf, size_t len, size_t pos, size_t stop, std::vector<RawChunk>& out, bool speculative, bool* broken) {
+    while (pos < len && pos < stop) {
         RawChunk c;
-        c.len = be32(buf + pos);
-        memcpy(c.ty, buf + pos + 4, 4);
-        for (int k = 0; k < 4; k++)
-            if (!((c.ty[k] >= 'A' && c.ty[k] <= 'Z') || (c.ty[k] >= 'a' && c.ty[k] <= 'z'))) throw Error(PNA_E_INVALID_DATA, "invalid chunk type");   // chunk/types.rs:204
-        if (len - pos - 12 < c.len) throw Error(PNA_E_UNEXPECTED_EOF, "truncated chunk body");
+        const bool ok_hdr = len - pos >= 12;
+        if (ok_hdr) { c.len = be32(buf + pos); memcpy(c.ty, buf + pos + 4, 4); }
+        const bool ok = ok_hdr && ty_letters(ty32(c.ty)) && len - pos - 12 >= c.len;
+        if (!ok) {
+            if (speculative) { *broken = true; return pos; }
+            if (!ok_hdr) throw Error(PNA_E_UNEXPECTED_EOF, "truncated chunk");
+            if (!ty_letters(ty32(c.ty))) throw Error(PNA_E_INVALID_DATA, "invalid chunk type");
+            throw Error(PNA_E_UNEXPECTED_EOF, "truncated chunk body");
+        }
         c.off = pos + 8;
         c.crc = be32(buf + pos + 8 + c.len);
         out.push_back(c);
         pos += 12 + (size_t)c.len;
     }
+    return pos;
+}
+// The walk is a pointer chase (every header is a cache miss, ~70 ns a chunk): archives with millions of small chunks are
+// indexed by several threads.  Thread k looks, from the start of its region, for an offset from which eight consecutive
+// well-formed chunk headers follow, and walks on from there; its list is taken only when the previous thread's walk
+// lands EXACTLY on that offset -- then the result is what the serial walk produces -- and re-walked serially otherwise.
+static void index_chunks(const uint8_t* buf, size_t len, size_t pos, std::vector<RawChunk>& out) {
+    const size_t span = len > pos ? len - pos : 0;
+    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (span < ((size_t)32 << 20) || getenv("PNA_INDEX_SERIAL")) nt = 1;
+    if (nt == 1) {
+        out.reserve(std::min<size_t>(len / 256 + 16, (size_t)1 << 24));
+        walk_chunks(buf, len, pos, len, out, false, nullptr);
+        return;
+    }
+    struct Part { size_t start = SIZE_MAX, end = 0; bool broken = false; std::vector<RawChunk> list; };
+    std::vector<Part> parts(nt);
+    std::vector<size_t> bound(nt + 1);
+    for (unsigned k = 0; k <= nt; k++) bound[k] = pos + span / nt * k;
+    bound[nt] = len;
+    auto plausible = [&](size_t p) {
+        for (int hop = 0; hop < 8 && p < len; hop++) {
+            if (len - p < 12) return false;
+            const uint32_t cl = be32(buf + p);
+            if (!ty_letters(ty32((const char*)buf + p + 4)) || len - p - 12 < cl) return false;
+            p += 12 + (size_t)cl;
+        }
+        return true;
+    };
+    auto run = [&](unsigned k) {
+        Part& P = parts[k];
+        if (k == 0) P.start = pos;
+        else {
+            const size_t lim = std::min(bound[k] + ((size_t)64 << 10), bound[k + 1]);
+            for (size_t p = bound[k]; p < lim; p++) if (plausible(p)) { P.start = p; break; }
+        }
+        if (P.start == SIZE_MAX) return;
+        P.list.reserve(span / nt / 256 + 16);
+        P.end = walk_chunks(buf, len, P.start, bound[k + 1], P.list, true, &P.broken);
+    };
+    std::vector<std::thread> th;
+    for (unsigned k = 1; k < nt; k++) th.emplace_back(run, k);
+    run(0);
+    for (auto& t : th) t.join();
+    size_t total = 0;
+    for (const Part& P : parts) total += P.list.size();
+    out.reserve(total + 16);
+    size_t at = pos;   // the authoritative walk stands here
+    for (unsigned k = 0; k < nt; k++) {
+        Part& P = parts[k];
+        if (P.start == at) {
+            out.insert(out.end(), P.list.begin(), P.list.end());
+            at = P.end;
+            if (P.broken) at = walk_chunks(buf, len, at, bound[k + 1], out, false, nullptr);   // reports the error the serial walk reports
+        } else if (at < bound[k + 1]) at = walk_chunks(buf, len, at, bound[k + 1], out, false, nullptr);
+    }
+    if (at < len) walk_chunks(buf, len, at, len, out, false, nullptr);
 }
 static inline bool is_critical(const RawChunk& c) { return (c.ty[0] & 0x20) == 0; }
 
-// next_raw_item (archive/read.rs:46-73) + TryFrom<RawEntry> (entry.rs:665-737, 757-886)
-static void group_entries(const uint8_t* buf, const std::vector<RawChunk>& ch, std::vector<EntryInfo>& out) {
-    size_t i = 0;
-    while (i < ch.size()) {
+// next_raw_item (archive/read.rs:46-73) + TryFrom<RawEntry> (entry.rs:665-737, 757-886) for the entries that START in
+// chunk range [i0, i1); `limit` = index of the first AEND / ANXT (nothing behind it is grouped).  Body spans go to
+// pool[pool_at ...] (the slice reserved for this range); equal PHSF strings are shared.
+static void group_range(const uint8_t* buf, const std::vector<RawChunk>& ch, size_t i0, size_t i1, size_t limit, std::vector<EntryInfo>& out,
+                        pna_span* pool, size_t pool_at) {
+    std::shared_ptr<const std::string> last_phsf;
+    size_t i = i0;
+    while (i < i1 && i < limit) {
         const RawChunk& c = ch[i];
-        if (ty_is(c, "AEND") || ty_is(c, "ANXT")) break;
-        const bool normal = ty_is(c, "FHED"), solid = ty_is(c, "SHED");
+        const uint32_t ct = ty32(c);
+        const bool normal = ct == T_FHED, solid = ct == T_SHED;
         if (!normal && !solid) { i++; continue; }   // AHED and archive-level ancillary chunks
-        EntryInfo e;
+        out.emplace_back();
+        EntryInfo& e = out.back();
         e.kind = solid ? 1 : 0;
         e.chunk_begin = (uint32_t)i;
         const uint8_t* h = buf + c.off;
@@ -92,17 +166,20 @@ static void group_entries(const uint8_t* buf, const std::vector<RawChunk>& ch, s
             if (h[0] != 0 || h[1] != 0) throw Error(PNA_E_UNSUPPORTED, "entry version is not supported");
             e.compression = h[2]; e.encryption = h[3]; e.cipher_mode = h[4];
         }
-        const char* end_ty = normal ? "FEND" : "SEND";
-        const char* dat_ty = normal ? "FDAT" : "SDAT";
+        const uint32_t end_ty = normal ? T_FEND : T_SEND, dat_ty = normal ? T_FDAT : T_SDAT;
+        const size_t body_first = pool_at;
         size_t j = i + 1;
         bool closed = false;
-        for (; j < ch.size(); j++) {
+        for (; j < limit; j++) {                      // ANXT / AEND at `limit`: the entry continues in the next part (archive/read.rs:118)
             const RawChunk& d = ch[j];
-            if (ty_is(d, end_ty)) { closed = true; j++; break; }
-            if (ty_is(d, "ANXT") || ty_is(d, "AEND")) break;   // split archive: the entry continues in the next part (archive/read.rs:118)
-            if (ty_is(d, dat_ty)) { e.bodies.push_back({buf + d.off, d.len}); e.compressed_size += d.len; }
-            else if (ty_is(d, "PHSF")) { e.phsf.assign((const char*)buf + d.off, d.len); e.has_phsf = true; }
-            else if (normal && ty_is(d, "fSIZ")) {
+            const uint32_t dt = ty32(d);
+            if (dt == end_ty) { closed = true; j++; break; }
+            if (dt == dat_ty) { pool[pool_at++] = {buf + d.off, d.len}; e.compressed_size += d.len; }
+            else if (dt == T_PHSF) {
+                if (!last_phsf || last_phsf->size() != d.len || memcmp(last_phsf->data(), buf + d.off, d.len) != 0)
+                    last_phsf = std::make_shared<const std::string>((const char*)buf + d.off, d.len);
+                e.phsf_ = last_phsf; e.has_phsf = true;
+            } else if (normal && dt == T_fSIZ) {
                 uint64_t v = 0;
                 const uint32_t n = d.len > 16 ? 16 : d.len;       // u128_from_be_bytes_last
                 for (uint32_t k = d.len - n; k < d.len; k++) v = (v << 8) | buf[d.off + k];
@@ -110,23 +187,86 @@ static void group_entries(const uint8_t* buf, const std::vector<RawChunk>& ch, s
             } else if (is_critical(d)) throw Error(PNA_E_INVALID_DATA, "unknown critical chunk type");   // entry.rs:716,848
         }
         if (!closed) throw Error(PNA_E_UNEXPECTED_EOF, "entry without end chunk");
+        e.bodies.p = pool + body_first;
+        e.bodies.n = (uint32_t)(pool_at - body_first);
         e.chunk_end = (uint32_t)j;
-        out.push_back(std::move(e));
         i = j;
     }
+}
+// Grouping reads every entry's header / size / PHSF chunk bodies (a few cache misses per entry): ranges of the chunk
+// list that start at an entry header are grouped by several threads and concatenated in order.
+static void group_entries(const uint8_t* buf, const std::vector<RawChunk>& ch, std::vector<EntryInfo>& out, std::vector<pna_span>& pool) {
+    const size_t nc = ch.size();
+    size_t limit = nc;
+    for (size_t i = 0; i < nc; i++) { const uint32_t t = ty32(ch[i]); if (t == T_AEND || t == T_ANXT) { limit = i; break; } }
+    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (limit < 65536 || getenv("PNA_INDEX_SERIAL")) nt = 1;
+    // range starts: the first entry header at or behind k * limit / nt.  An entry header can only be cut off from its
+    // chunks by a range start that lies INSIDE the entry, so starts are moved forward to the next header that follows an
+    // end chunk (FEND / SEND), i.e. a header at top level.
+    std::vector<size_t> start(nt + 1, limit);
+    start[0] = 0;
+    for (unsigned k = 1; k < nt; k++) {
+        size_t i = std::max(start[k - 1], limit / nt * k);
+        while (i < limit) {
+            const uint32_t t = ty32(ch[i]);
+            if ((t == T_FHED || t == T_SHED) && i > 0 && (ty32(ch[i - 1]) == T_FEND || ty32(ch[i - 1]) == T_SEND)) break;
+            i++;
+        }
+        start[k] = i;
+    }
+    std::vector<size_t> dat_before(nt + 1, 0);
+    {
+        unsigned k = 0;
+        size_t cnt = 0;
+        for (size_t i = 0; i < limit; i++) {
+            while (k < nt && start[k + 1] <= i) { k++; dat_before[k] = cnt; }
+            const uint32_t t = ty32(ch[i]);
+            cnt += t == T_FDAT || t == T_SDAT;
+        }
+        while (k < nt) { k++; dat_before[k] = cnt; }
+    }
+    pool.assign(dat_before[nt], pna_span{nullptr, 0});
+    std::vector<std::vector<EntryInfo>> parts(nt);
+    std::vector<std::string> err(nt);
+    std::vector<int> err_kind(nt, 0);
+    auto run = [&](unsigned k) {
+        try {
+            parts[k].reserve((start[k + 1] - start[k]) / 4 + 4);
+            group_range(buf, ch, start[k], start[k + 1], limit, parts[k], pool.data(), dat_before[k]);
+        } catch (const Error& e) { err[k] = e.what(); err_kind[k] = e.kind ? e.kind : PNA_E_INTERNAL; }
+    };
+    std::vector<std::thread> th;
+    for (unsigned k = 1; k < nt; k++) th.emplace_back(run, k);
+    run(0);
+    for (auto& t : th) t.join();
+    size_t total = out.size();
+    for (unsigned k = 0; k < nt; k++) {
+        if (err_kind[k]) throw Error(err_kind[k], err[k]);   // the first failing range in archive order = the serial walk's error
+        total += parts[k].size();
+    }
+    out.reserve(total);
+    for (unsigned k = 0; k < nt; k++)
+        for (EntryInfo& e : parts[k]) out.push_back(std::move(e));
 }
 
 Archive Archive::read_header_from_slice(const uint8_t* buf, size_t len) {
     Archive a;
     if (len < 8 || memcmp(buf, SIGNATURE, 8) != 0) throw Error(PNA_E_INVALID_DATA, "it is not PNA");
     a.buf_ = buf; a.len_ = len;
+    const auto t0 = std::chrono::steady_clock::now();
     index_chunks(buf, len, 8, a.chunks_);
+    const auto t1 = std::chrono::steady_clock::now();
     if (a.chunks_.empty() || !ty_is(a.chunks_[0], "AHED")) throw Error(PNA_E_INVALID_DATA, "expected `AHED` chunk");
     if (a.chunks_[0].len != 8) throw Error(PNA_E_INVALID_DATA, "bad archive header");
     const uint8_t* h = buf + a.chunks_[0].off;
     if (h[0] != 0) throw Error(PNA_E_UNSUPPORTED, "archive version is not supported");   // archive/header.rs:47
     a.archive_number_ = be32(h + 4);
-    group_entries(buf, a.chunks_, a.entries_);
+    group_entries(buf, a.chunks_, a.entries_, a.body_pool_);
+    if (getenv("PNA_HOST_TRACE"))
+        fprintf(stderr, "[pna_host] index pass: %zu chunks walked in %.1f ms, %zu entries grouped in %.1f ms\n", a.chunks_.size(),
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), a.entries_.size(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     return a;
 }
 
@@ -143,7 +283,7 @@ static int32_t fill_desc(const EntryInfo& e, const ReadOptions& opt, pna_decode_
     if (e.encryption != PNA_ENCRYPTION_NO && cipher_supported(e)) {
         if (!opt.has_password) return PNA_E_INVALID_INPUT;                 // "password was not provided"
         if (!e.has_phsf) return PNA_E_INVALID_DATA;                        // "`PHSF` chunk not found"
-        auto it = opt.keys.find(e.phsf);
+        auto it = opt.keys.find(e.phsf());
         if (it == opt.keys.end()) return PNA_E_INVALID_INPUT;
         memcpy(d.key, it->second.data(), 32);
     }
@@ -184,7 +324,7 @@ void Archive::prepare(const ReadOptions& opt, int device) {
             for (size_t c = 0; c < in.chunks.size(); c++)
                 if (crc[c] != in.chunks[c].crc) throw Error(PNA_E_INVALID_DATA, "broken chunk (inside solid entry)");
         }
-        group_entries(in.bytes.data(), in.chunks, in.entries);
+        group_entries(in.bytes.data(), in.chunks, in.entries, in.body_pool);
         inner_.push_back(std::move(in));
     }
     // 2. FILE entries in archive order
@@ -662,7 +802,7 @@ int pnah_entry_get(pnah_archive* a, uint32_t i, pnah_entry_info* info) {
     const pna::EntryInfo& e = a->a.entries()[i];
     info->kind = e.kind; info->data_kind = e.data_kind; info->compression = e.compression; info->encryption = e.encryption;
     info->cipher_mode = e.cipher_mode; info->n_bodies = (uint32_t)e.bodies.size(); info->compressed_size = e.compressed_size;
-    info->raw_file_size = e.raw_file_size; info->name = e.name.c_str(); info->phsf = e.has_phsf ? e.phsf.c_str() : nullptr;
+    info->raw_file_size = e.raw_file_size; info->name = e.name.c_str(); info->phsf = e.has_phsf ? e.phsf().c_str() : nullptr;
     return PNA_OK;
 }
 int pnah_set_key(pnah_archive* a, const char* phsf, const uint8_t key[32]) { a->opt.set_key(phsf, key); return PNA_OK; }

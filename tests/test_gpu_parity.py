@@ -335,3 +335,74 @@ def test_extract_plan_fused_crc(ctx, pna, oracle):
     _, broken = plan.crc_results()
     assert broken == 1 and st[5] == pna.E_INVALID_DATA and [s for i, s in enumerate(st) if i != 5] == [0] * 11
     plan.close()
+
+
+# ------------------------------------------------------------------------------------------- LZ stage variants
+@pytest.mark.parametrize("variant", ["s", "b"])
+def test_lz_variants_agree(ctx, oracle, variant, monkeypatch):
+    """Both instantiations of the LZ stage (4 warps / 16-bit codes, 16 warps / 32-bit codes) on the same frames: shapes
+    that drive every arm -- long literal runs, long and overlapping matches (period 1..7), far matches behind the
+    window, raw and RLE blocks, many blocks per frame."""
+    monkeypatch.setenv("PNA_LZ_VARIANT", variant)
+    rng = np.random.default_rng(11)
+    files = [
+        corpus.make_file(700, 3 << 20),
+        b"A" * 1_000_003,                                                        # RLE blocks + period-1 matches
+        (b"abcdefg" * 9 + b"XY") * 40_000,                                       # short periods, overlapping matches
+        rng.bytes(300_000),                                                      # raw blocks
+        rng.bytes(70_000) + corpus.make_file(701, 400_000) + rng.bytes(70_000),  # long literal runs around text
+        (rng.bytes(20_000) + bytes(50_000)) * 12,                                # far matches (>= 64 KiB back) + zero runs
+        b"", b"x", corpus.make_file(702, 131_072), corpus.make_file(703, 131_073),
+    ]
+    entries = [_mk(oracle, f, 2, 0, 0, b"\0" * 32, hint=(i % 2 == 0), level=(3 if i % 3 else 19)) for i, f in enumerate(files)]
+    outs, st, _ = ctx.decode_batch(entries)
+    assert st == [0] * len(files)
+    for o, f in zip(outs, files):
+        assert hashlib.sha256(o.tobytes()).digest() == hashlib.sha256(f).digest()
+
+
+def test_lz_small_variant_selected_for_many_entries(ctx, oracle):
+    """More entries than half the SMs: the 4-warp kernel, one CTA per entry, sizes from empty to a few blocks."""
+    rnd = random.Random(8)
+    files = [corpus.make_file(40_000 + i, rnd.choice([0, 1, 100, 5000, 70_000, 200_000, 300_001])) for i in range(200)]
+    entries = [_mk(oracle, f, 2, 0, 0, b"\0" * 32) for f in files]
+    outs, st, _ = ctx.decode_batch(entries, caps=[len(f) for f in files])
+    assert st == [0] * len(files) and all(o.tobytes() == f for o, f in zip(outs, files))
+
+
+# ------------------------------------------------------------------------------------------- two-stage inflate
+def test_inflate_token_path_shapes(ctx, oracle):
+    """Lane-per-stream token decode + LZ + Adler pass: stored blocks (level 0), fixed Huffman (tiny inputs), dynamic
+    blocks, literal runs longer than one record carries (65534), distance-1 runs of the maximum match length, many
+    blocks per stream, and the sizing pass (no hint)."""
+    rng = np.random.default_rng(5)
+    shapes = [
+        (rng.bytes(200_000), 0), (rng.bytes(200_000), 6), (bytes(1_000_000), 6), (b"ab" * 300_000, 9),
+        (corpus.make_file(800, 1_500_000), 6), (corpus.make_file(801, 40), 6), (b"", 6), (b"z", 6),
+        (rng.bytes(70_000) + bytes(70_000) + rng.bytes(70_000), 1), (corpus.make_file(803, 16_384), 1),
+    ]
+    for hint in (True, False):
+        entries = [_mk(oracle, p, 1, 0, 0, b"\0" * 32, hint=hint, level=lv) for p, lv in shapes]
+        outs, st, _ = ctx.decode_batch(entries)
+        assert st == [0] * len(shapes)
+        for o, (p, _) in zip(outs, shapes):
+            assert hashlib.sha256(o.tobytes()).digest() == hashlib.sha256(p).digest()
+
+
+def test_inflate_token_path_errors(ctx, oracle, pna):
+    """flate2 zio::read behaviour on the two-stage path: corrupt stream / bad Adler-32 -> InvalidInput, truncated stream
+    -> the bytes produced so far without an error (entry/read.rs:179), too small capacity -> NOSPACE with the length."""
+    plain = corpus.make_file(811, 50_000)
+    good = oracle.encode_stream(plain, 1, 6, 0, 0, b"\0" * 32, bytes(16))
+    bad_adler = good[:-1] + bytes([good[-1] ^ 1])
+    cut = good[: len(good) // 2]
+    garbage = good[:2] + bytes([0x07]) + good[3:]            # BTYPE = 3 in the first block header
+    ents = [{"bodies": [s], "compression": 1, "encryption": 0, "cipher_mode": 0} for s in (good, bad_adler, cut, garbage)]
+    outs, st, lens = ctx.decode_batch(ents)
+    assert st[0] == 0 and outs[0].tobytes() == plain
+    assert st[1] == pna.E_INVALID_INPUT and st[3] == pna.E_INVALID_INPUT
+    assert st[2] == 0 and 0 < int(lens[2]) < len(plain) and outs[2].tobytes() == plain[: int(lens[2])]
+    want_cut = oracle.decode_stream(cut, 1, 0, 0, b"\0" * 32, None)
+    assert outs[2].tobytes() == want_cut
+    outs, st, lens = ctx.decode_batch(ents[:1], caps=[1000])
+    assert st == [pna.E_NOSPACE] and int(lens[0]) == len(plain)
