@@ -413,7 +413,7 @@ def main():
         create = {"metric": "create_uncompressed_GBps", "value": world * U / (c_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": c_ms,
                   "e2e": {"value": world * U / ce2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U) * world, "d2h_bytes_per_step": int(c_gpu) * world,
                           "ms_per_step": ce2e_s * 1e3},
-                  "codec": "gpu zstd (32 KiB blocks, predefined FSE, raw literals) + aes-256-ctr + crc32", "stage_ms": c_stage,
+                  "codec": "gpu zstd (32 KiB blocks, predefined-FSE sequences, Huffman literals where the alphabet allows the direct weight form) + aes-256-ctr + crc32", "stage_ms": c_stage,
                   "gpu_launches": c_launches, "ratio": U / c_gpu, "c_gpu_over_c_ref": c_gpu / Cbytes,
                   "checked": "sampled streams decoded by the oracle (libzstd + OpenSSL) == source files; FDAT CRCs == zlib crc32"}
         del outp, plain_pinned

@@ -185,6 +185,141 @@ PNA_HD uint32_t zstd_raw_lit_header(uint32_t n, uint8_t* h) {
     h[0] = (uint8_t)((n << 4) | 12u); h[1] = (uint8_t)(n >> 4); h[2] = (uint8_t)(n >> 12);
     return 3;
 }
+// ------------------------------------------------------------------------------------------------ Huffman literals
+// Compressed_Literals_Block with four streams (RFC 8878 3.1.1.3.1.1-6, libzstd HUF_compress4X semantics):
+//   tree description in the DIRECT form (header byte 127 + L, then L four-bit weights for symbols 0..L-1; the weight of
+//   the last present symbol L is implied), which covers alphabets whose largest byte value is <= 128 -- text; anything
+//   else stays Raw_Literals (the FSE-compressed weight form is the next step) -- code lengths limited to 11 bits,
+//   canonical codes assigned like HUF_buildCTable (longest codes first, symbol order inside a length), every stream
+//   written from its LAST symbol to its first with a closing 1 bit, a 6-byte jump table in front.
+constexpr uint32_t HUF_ENC_SYMS = 129, HUF_ENC_MAXBITS = 11, HUF_ENC_MIN = 256;
+struct ByteBits {   // forward little-endian bit writer into unaligned memory
+    uint8_t* p;
+    uint64_t acc;
+    uint32_t n, bytes;
+    PNA_HD void init(uint8_t* dst) { p = dst; acc = 0; n = 0; bytes = 0; }
+    PNA_HD void add(uint32_t v, uint32_t nb) {   // nb <= 16
+        acc |= (uint64_t)v << n;
+        n += nb;
+        if (n >= 32) {
+            p[bytes] = (uint8_t)acc; p[bytes + 1] = (uint8_t)(acc >> 8); p[bytes + 2] = (uint8_t)(acc >> 16); p[bytes + 3] = (uint8_t)(acc >> 24);
+            bytes += 4; acc >>= 32; n -= 32;
+        }
+    }
+    PNA_HD uint32_t finish() { while (n > 0) { p[bytes++] = (uint8_t)acc; acc >>= 8; n = n > 8 ? n - 8 : 0; } return bytes; }
+};
+// Literals section of a block.  hdr receives the section header (<= 5 bytes, *hdr_len).  Returns the length of the
+// compressed payload written to dst (tree + jump table + streams), or 0 when the literals stay raw (the payload is then
+// the n literal bytes themselves).  dst needs n bytes of room.
+PNA_HD uint32_t zstd_write_literals(const uint8_t* lits, uint32_t n, uint8_t* dst, uint8_t* hdr, uint32_t* hdr_len) {
+    *hdr_len = zstd_raw_lit_header(n, hdr);
+    if (n < HUF_ENC_MIN) return 0;
+    uint32_t count[HUF_ENC_SYMS];
+    for (uint32_t s = 0; s < HUF_ENC_SYMS; s++) count[s] = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t c = lits[i];
+        if (c >= HUF_ENC_SYMS) return 0;
+        count[c]++;
+    }
+    // present symbols sorted by ascending count (insertion sort: <= 129 keys)
+    uint8_t order[HUF_ENC_SYMS];
+    uint32_t m = 0, last_sym = 0;
+    for (uint32_t s = 0; s < HUF_ENC_SYMS; s++) {
+        if (!count[s]) continue;
+        last_sym = s;
+        uint32_t k = m++;
+        while (k > 0 && count[order[k - 1]] > count[s]) { order[k] = order[k - 1]; k--; }
+        order[k] = (uint8_t)s;
+    }
+    if (m < 2) return 0;
+    // Huffman tree by the two-queue merge: leaves 0..m-1 (ascending), internal nodes m..2m-2 are born in ascending order
+    uint32_t wt[2 * HUF_ENC_SYMS];
+    uint16_t parent[2 * HUF_ENC_SYMS];
+    for (uint32_t k = 0; k < m; k++) wt[k] = count[order[k]];
+    uint32_t li = 0, ni = m, no = m;
+    for (uint32_t k = 0; k + 1 < m; k++) {
+        uint32_t pick[2];
+        for (int q = 0; q < 2; q++) {
+            if (li < m && (ni >= no || wt[li] <= wt[ni])) pick[q] = li++;
+            else pick[q] = ni++;
+        }
+        wt[no] = wt[pick[0]] + wt[pick[1]];
+        parent[pick[0]] = (uint16_t)no; parent[pick[1]] = (uint16_t)no;
+        no++;
+    }
+    uint8_t depth[2 * HUF_ENC_SYMS];
+    depth[no - 1] = 0;
+    for (uint32_t k = no - 1; k-- > 0;) depth[k] = (uint8_t)(depth[parent[k]] + 1);
+    // length limit (miniz's tdefl_huffman_enforce_max_code_size): fold the too-long codes into the limit, then pay the
+    // Kraft excess back by splitting the longest code that is still shorter than the limit
+    uint32_t num[33];
+    for (uint32_t l = 0; l < 33; l++) num[l] = 0;
+    for (uint32_t k = 0; k < m; k++) num[depth[k] > 32 ? 32 : depth[k]]++;
+    for (uint32_t l = HUF_ENC_MAXBITS + 1; l < 33; l++) { num[HUF_ENC_MAXBITS] += num[l]; num[l] = 0; }
+    uint32_t total = 0;
+    for (uint32_t l = HUF_ENC_MAXBITS; l > 0; l--) total += num[l] << (HUF_ENC_MAXBITS - l);
+    while (total != (1u << HUF_ENC_MAXBITS)) {
+        num[HUF_ENC_MAXBITS]--;
+        for (uint32_t l = HUF_ENC_MAXBITS - 1; l > 0; l--)
+            if (num[l]) { num[l]--; num[l + 1] += 2; break; }
+        total--;
+    }
+    // lengths: the most frequent symbols (end of `order`) take the shortest codes
+    uint8_t len_of[HUF_ENC_SYMS];
+    for (uint32_t s = 0; s < HUF_ENC_SYMS; s++) len_of[s] = 0;
+    uint32_t max_bits = 0;
+    {
+        uint32_t k = m;
+        for (uint32_t l = 1; l <= HUF_ENC_MAXBITS; l++)
+            for (uint32_t c = 0; c < num[l]; c++) { len_of[order[--k]] = (uint8_t)l; max_bits = l; }
+    }
+    // canonical codes (HUF_buildCTable): longest codes start at 0, each shorter length continues at (next value) >> 1
+    uint32_t val[HUF_ENC_MAXBITS + 2];
+    {
+        uint32_t mn = 0;
+        for (uint32_t l = max_bits; l > 0; l--) { val[l] = mn; mn += num[l]; mn >>= 1; }
+    }
+    uint32_t ctab[HUF_ENC_SYMS];   // code | nbBits << 16
+    for (uint32_t s = 0; s <= last_sym; s++) ctab[s] = len_of[s] ? (val[len_of[s]]++ | ((uint32_t)len_of[s] << 16)) : 0u;
+    // exact size before a byte is written (the payload must not outgrow the n bytes the caller reserved): code bits by the
+    // histogram, plus per stream the closing bit and the byte rounding, plus tree and jump table
+    {
+        uint64_t bits = 0;
+        for (uint32_t s = 0; s <= last_sym; s++) bits += (uint64_t)count[s] * len_of[s];
+        const uint64_t est = 1 + (last_sym + 1) / 2 + 6 + (bits + 7) / 8 + 8;
+        if (est + 8 >= n) return 0;   // not smaller than the raw literals: keep them raw
+    }
+    // ---- payload: tree description, jump table, four streams
+    uint32_t o = 0;
+    dst[o++] = (uint8_t)(127 + last_sym);
+    for (uint32_t s = 0; s < last_sym; s += 2) {
+        const uint32_t w0 = len_of[s] ? max_bits + 1 - len_of[s] : 0u;
+        const uint32_t w1 = (s + 1 < last_sym && len_of[s + 1]) ? max_bits + 1 - len_of[s + 1] : 0u;
+        dst[o++] = (uint8_t)((w0 << 4) | w1);
+    }
+    const uint32_t jump = o;
+    o += 6;
+    const uint32_t seg = (n + 3) / 4;
+    for (uint32_t q = 0; q < 4; q++) {
+        const uint32_t b0 = q * seg, b1 = q < 3 ? b0 + seg : n;
+        ByteBits bw;
+        bw.init(dst + o);
+        for (uint32_t i = b1; i-- > b0;) { const uint32_t c = ctab[lits[i]]; bw.add(c & 0xFFFFu, c >> 16); }
+        bw.add(1, 1);
+        const uint32_t sz = bw.finish();
+        if (q < 3) { dst[jump + 2 * q] = (uint8_t)sz; dst[jump + 2 * q + 1] = (uint8_t)(sz >> 8); }
+        o += sz;
+    }
+    // section header: type 2 (compressed), four streams; both sizes in 10 / 14 / 18 bits
+    const uint32_t sf = (n < 1024 && o < 1024) ? 1u : (n < 16384 && o < 16384) ? 2u : 3u;
+    const uint32_t bits = sf == 1 ? 10u : sf == 2 ? 14u : 18u;
+    const uint64_t v = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)o << (4 + bits));
+    const uint32_t hl = sf + 2;
+    for (uint32_t k = 0; k < hl; k++) hdr[k] = (uint8_t)(v >> (8 * k));
+    *hdr_len = hl;
+    return o;
+}
+
 PNA_HD void zstd_block_header(uint32_t last, uint32_t type, uint32_t size, uint8_t* h) {
     const uint32_t v = last | (type << 1) | (size << 3);
     h[0] = (uint8_t)v; h[1] = (uint8_t)(v >> 8); h[2] = (uint8_t)(v >> 16);

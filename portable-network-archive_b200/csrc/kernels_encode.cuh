@@ -26,6 +26,8 @@ struct SegRec {            // one segment (host fills the first group, kernels t
     uint32_t nseq, nlit;
     uint32_t head_len, raw;        // raw: pieces = head + plain; else head + literals + tail (zstd) / body (deflate)
     uint32_t tail_off, tail_len;   // inside the body
+    uint64_t litp_off;             // literal payload of a compressed zstd block: the literal arena (raw) or the body (Huffman)
+    uint32_t litp_len, _pad2;
     uint64_t adler_a, adler_b;     // sum of bytes, sum of (len - k) * byte_k
 };
 constexpr uint32_t TMP_HEAD = 16;
@@ -208,23 +210,30 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
     uint8_t* const body = head + TMP_HEAD;
     const Seq* sq = seqs + sr.seq_off;
     if (entries[sr.entry].compression == 2) {
+        // literals section first (Huffman-compressed into the body when that is smaller, else raw = the literal arena as it
+        // is), the sequences section behind it on the next 4-byte boundary
+        uint8_t lh[5];
+        uint32_t lhn = 0;
+        const uint32_t clit = zstd_write_literals(work + sr.lit_off, nlit, body, lh, &lhn);
+        const uint32_t lpay = clit ? clit : nlit;
+        const uint32_t sbase = clit ? (clit + 3u) & ~3u : 0u;
         uint32_t ssz = 1, soff = 0;
         bool fits = true;
         if (nseq) {
-            const uint32_t r = zstd_write_sequences(T, sq, nseq, body, TMP_SEG - TMP_HEAD);
+            const uint32_t r = zstd_write_sequences(T, sq, nseq, body + sbase, TMP_SEG - TMP_HEAD - sbase);
             if (r == 0xFFFFFFFFu) fits = false;
             soff = r >> 24; ssz = r & 0xFFFFFFu;
-        } else body[0] = 0;
-        uint8_t lh[3];
-        const uint32_t lhn = zstd_raw_lit_header(nlit, lh);
-        const uint32_t csize = lhn + nlit + ssz;
+        } else body[sbase] = 0;
+        const uint32_t csize = lhn + lpay + ssz;
         if (!fits || csize >= len) {
             zstd_block_header(last, 0, len, head);
-            sr.head_len = 3; sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0;
+            sr.head_len = 3; sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0; sr.litp_off = 0; sr.litp_len = 0;
         } else {
             zstd_block_header(last, 2, csize, head);
             for (uint32_t k = 0; k < lhn; k++) head[3 + k] = lh[k];
-            sr.head_len = 3 + lhn; sr.raw = 0; sr.tail_off = soff; sr.tail_len = ssz;
+            sr.head_len = 3 + lhn; sr.raw = 0; sr.tail_off = sbase + soff; sr.tail_len = ssz;
+            sr.litp_off = clit ? sr.tmp_off + TMP_HEAD : sr.lit_off;
+            sr.litp_len = lpay;
         }
     } else {
         const uint32_t sz = deflate_write_segment(sq, nseq, work + sr.lit_off, nlit, last != 0, body);
@@ -257,7 +266,7 @@ __global__ void enc_layout_kernel(uint8_t* __restrict__ work, const SegRec* __re
             const SegRec& s = segs[k];
             add(s.tmp_off, s.head_len);
             if (s.raw) add(s.plain_off, s.len);
-            else { add(s.lit_off, s.nlit); add(s.tmp_off + TMP_HEAD + s.tail_off, s.tail_len); }
+            else { add(s.litp_off, s.litp_len); add(s.tmp_off + TMP_HEAD + s.tail_off, s.tail_len); }
         }
     } else {
         h[0] = 0x78; h[1] = 0x9C;

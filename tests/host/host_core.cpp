@@ -222,13 +222,16 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
             uint32_t ssz = 1, soff = 0;
             if (!seqs.empty()) { uint32_t r = zstd_write_sequences(g_enc, seqs.data(), (uint32_t)seqs.size(), t4, 2 * SEG); soff = r >> 24; ssz = r & 0xFFFFFF; }
             else { t4[0] = 0; }
-            uint8_t lh[3]; uint32_t lhn = zstd_raw_lit_header((uint32_t)lits.size(), lh);
-            uint32_t csize = lhn + (uint32_t)lits.size() + ssz;
+            uint8_t lh[5]; uint32_t lhn = 0;
+            std::vector<uint8_t> cl(lits.size() + 64);
+            const uint32_t clit = zstd_write_literals(lits.data(), (uint32_t)lits.size(), cl.data(), lh, &lhn);
+            const uint32_t lpay = clit ? clit : (uint32_t)lits.size();
+            uint32_t csize = lhn + lpay + ssz;
             if (csize >= n) { zstd_block_header(last, 0, n, out + o); o += 3; memcpy(out + o, d, n); o += n; }
             else {
                 zstd_block_header(last, 2, csize, out + o); o += 3;
                 memcpy(out + o, lh, lhn); o += lhn;
-                memcpy(out + o, lits.data(), lits.size()); o += lits.size();
+                memcpy(out + o, clit ? cl.data() : lits.data(), lpay); o += lpay;
                 memcpy(out + o, t4 + soff, ssz); o += ssz;
             }
         } else {

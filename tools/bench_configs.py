@@ -202,7 +202,7 @@ def main():
         print(json.dumps({"config": "cfg5", "files": n, "plain_bytes": U, "solid_stream_bytes": len(stream), "sdat_chunks": (len(stream) + 32767) // 32768,
                           "solid_e2e_GBps": U / dt / 1e9, "solid_e2e_ms": dt * 1e3, "per_entry_e2e_GBps": U / dt2 / 1e9, "per_entry_e2e_ms": dt2 * 1e3,
                           "note": "a solid entry is ONE zstd frame: the sequence stage is block-parallel (lane per block), the LZ stage runs "
-                                  "the frame on one warp; includes the sizing pass (no fSIZ on solid streams) and the inner chunk CRC check",
+                                  "the frame on one CTA of 16 warps; the stream is decoded once, stays in HBM for the inner chunk CRC check and the range copies of the STORE entries",
                           "cpu_baseline_solid_GBps": U / cpu_solid / 1e9, "cpu_cores_solid": 1}), flush=True)
         del out, out2
 
