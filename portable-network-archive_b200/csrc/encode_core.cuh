@@ -11,7 +11,7 @@
 //   zstd   one frame per entry: magic, FHD 0x00 (no content size / checksum / dictionary -- like the
 //          reference's streaming encoder), Window_Descriptor 0x38 (128 KiB), one block per 32 KiB segment.
 //          Compressed block = Raw_Literals + sequences coded with the PREDEFINED FSE tables (mode byte 0x00),
-//          real offsets only (no repeat codes).  A block that does not shrink becomes a Raw_Block.
+//          repeat offsets are used for the history slots the block has set itself (zstd_assign_repcodes).  A block that does not shrink becomes a Raw_Block.
 //   zlib   0x78 0x9C, per segment one fixed-Huffman block followed by an empty stored block (the Z_SYNC_FLUSH
 //          marker 00 00 FF FF) so that segments stay byte aligned and can be produced independently; the last
 //          segment's block carries BFINAL; Adler-32 big endian.  A segment that does not shrink is a stored block.
@@ -130,7 +130,41 @@ PNA_HD void fse_encode(BitOut& b, FseCState& s, const FseCTab& t, uint32_t sym) 
 PNA_HD uint32_t ll_code_of(const EncTables& E, uint32_t ll) { return ll < 64 ? E.ll_code[ll] : (uint32_t)highbit32(ll) + 19u; }
 PNA_HD uint32_t ml_code_of(const EncTables& E, uint32_t mlb) { return mlb < 128 ? E.ml_code[mlb] : (uint32_t)highbit32(mlb) + 36u; }
 
+// Repeat offsets (RFC 8878 3.1.1.5), forward pass over a block's sequences: q.off (a real distance) becomes the
+// Offset_Value to code -- SEQ_REPCODE | 1..3 for a repeat offset, left as the distance (coded as distance + 3) otherwise.  Blocks are written independently and in
+// parallel, so the history a block inherits from its predecessor is unknown here: a history slot is only used once this
+// block has set it itself (`known`), which is what makes the choice valid whatever the decoder's incoming history is.
+constexpr uint32_t SEQ_REPCODE = 0x80000000u;   // Seq.off flag: the low two bits are a repeat-offset Offset_Value
+PNA_HD void zstd_assign_repcodes(Seq* seqs, uint32_t nseq) {
+    uint32_t r1 = 0, r2 = 0, r3 = 0;
+    bool k1 = false, k2 = false, k3 = false;
+    for (uint32_t i = 0; i < nseq; i++) {
+        const uint32_t off = seqs[i].off, ll = seqs[i].llml & 0xFFFFu;
+        uint32_t val;
+        if (ll != 0 && k1 && off == r1) val = 1;                                    // history unchanged
+        else if ((ll != 0 && k2 && off == r2) || (ll == 0 && k2 && off == r2)) {   // second slot: swap the first two
+            val = ll != 0 ? 2u : 1u;
+            const uint32_t t = r1; r1 = r2; r2 = t;
+            const bool kt = k1; k1 = k2; k2 = kt;
+        } else if (k3 && off == r3) {                                               // third slot: rotate
+            val = ll != 0 ? 3u : 2u;
+            const uint32_t t = r3; r3 = r2; r2 = r1; r1 = t;
+            const bool kt = k3; k3 = k2; k2 = k1; k1 = kt;
+        } else if (ll == 0 && k1 && r1 > 1 && off == r1 - 1) {                      // "first slot minus one"
+            val = 3;
+            r3 = r2; r2 = r1; r1 = off;
+            k3 = k2; k2 = k1; k1 = true;
+        } else {                                                                    // new offset: push
+            val = off + 3;
+            r3 = r2; r2 = r1; r1 = off;
+            k3 = k2; k2 = k1; k1 = true;
+        }
+        if (val <= 3) seqs[i].off = SEQ_REPCODE | val;   // only repeat offsets are written back (one store per hit, none otherwise)
+    }
+}
+
 // Sequences section of one block (nseq >= 1): Number_of_Sequences, mode byte 0 (predefined x3), FSE bitstream.
+// seqs[i].off is a distance, or SEQ_REPCODE | Offset_Value where zstd_assign_repcodes chose a repeat offset.
 // dst must be 4-byte aligned, cap bytes.  Returns (offset of first byte << 24) | length, or 0xFFFFFFFF when the
 // section would not fit cap (the caller then emits the segment as a Raw_Block).
 PNA_HD uint32_t zstd_write_sequences(const EncTables& E, const Seq* seqs, uint32_t nseq, uint8_t* dst, uint32_t cap) {
@@ -140,7 +174,7 @@ PNA_HD uint32_t zstd_write_sequences(const EncTables& E, const Seq* seqs, uint32
     FseCState sll, sof, sml;
     {
         const Seq q = seqs[nseq - 1];
-        const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = q.off + 3u;
+        const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = (q.off & SEQ_REPCODE) ? (q.off & 3u) : q.off + 3u;
         const uint32_t cl = ll_code_of(E, ll), cm = ml_code_of(E, mlb), co = (uint32_t)highbit32(ob);
         fse_init_state(sml, E.ml, cm);
         fse_init_state(sof, E.of, co);
@@ -151,7 +185,7 @@ PNA_HD uint32_t zstd_write_sequences(const EncTables& E, const Seq* seqs, uint32
     }
     for (uint32_t i = nseq - 1; i-- > 0;) {
         const Seq q = seqs[i];
-        const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = q.off + 3u;
+        const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = (q.off & SEQ_REPCODE) ? (q.off & 3u) : q.off + 3u;
         const uint32_t cl = ll_code_of(E, ll), cm = ml_code_of(E, mlb), co = (uint32_t)highbit32(ob);
         fse_encode(b, sof, E.of, co);
         fse_encode(b, sml, E.ml, cm);

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ work, SegRec* __restrict__ segs, uint32_t nsegs,
-                                                        const Seq* __restrict__ seqs, const EncTables* __restrict__ tables,
+                                                        Seq* __restrict__ seqs, const EncTables* __restrict__ tables,
                                                         const EncEntry* __restrict__ entries) {
     __shared__ EncTables T;
     for (uint32_t i = threadIdx.x; i < sizeof(EncTables) / 4; i += blockDim.x)
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
     const uint32_t len = sr.len, nseq = sr.nseq, nlit = sr.nlit, last = sr.last;
     uint8_t* const head = work + sr.tmp_off;
     uint8_t* const body = head + TMP_HEAD;
-    const Seq* sq = seqs + sr.seq_off;
+    Seq* sq = seqs + sr.seq_off;
     if (entries[sr.entry].compression == 2) {
         // literals section first (Huffman-compressed into the body when that is smaller, else raw = the literal arena as it
         // is), the sequences section behind it on the next 4-byte boundary
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
         uint32_t ssz = 1, soff = 0;
         bool fits = true;
         if (nseq) {
+            zstd_assign_repcodes(sq, nseq);
             const uint32_t r = zstd_write_sequences(T, sq, nseq, body + sbase, TMP_SEG - TMP_HEAD - sbase);
             if (r == 0xFFFFFFFFu) fits = false;
             soff = r >> 24; ssz = r & 0xFFFFFFu;

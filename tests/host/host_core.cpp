@@ -220,7 +220,7 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
         uint8_t* t4 = tmp.data() + ((4 - ((uintptr_t)tmp.data() & 3)) & 3);
         if (compression == 2) {
             uint32_t ssz = 1, soff = 0;
-            if (!seqs.empty()) { uint32_t r = zstd_write_sequences(g_enc, seqs.data(), (uint32_t)seqs.size(), t4, 2 * SEG); soff = r >> 24; ssz = r & 0xFFFFFF; }
+            if (!seqs.empty()) { zstd_assign_repcodes(seqs.data(), (uint32_t)seqs.size()); uint32_t r = zstd_write_sequences(g_enc, seqs.data(), (uint32_t)seqs.size(), t4, 2 * SEG); soff = r >> 24; ssz = r & 0xFFFFFF; }
             else { t4[0] = 0; }
             uint8_t lh[5]; uint32_t lhn = 0;
             std::vector<uint8_t> cl(lits.size() + 64);
