@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(32 * SEQ_WARPS) zstd_seq_kernel(const uint8_t*
     extern __shared__ __align__(64) uint16_t stab_all[];
     __shared__ uint32_t s_llb[36], s_mlb[53];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = threadIdx.x; c < 36; c += blockDim.x) s_llb[c] = ll_base(c);
-    for (int c = threadIdx.x; c < 53; c += blockDim.x) s_mlb[c] = ml_base(c);
+    for (int c = threadIdx.x; c < 36; c += blockDim.x) s_llb[c] = seq_pack_ll((uint32_t)c);
+    for (int c = threadIdx.x; c < 53; c += blockDim.x) s_mlb[c] = seq_pack_ml((uint32_t)c);
     __syncthreads();
     const uint32_t n = counts[0];
     const uint32_t* words = reinterpret_cast<const uint32_t*>(buf);

@@ -347,13 +347,17 @@ PNA_HD int seq_tab16_for(const uint8_t* comp, const ZBlock* blocks, const ZBlock
     fse_build_tab16(t, norm, n_sym, log, next_of);
     return log;
 }
-// extra-bit counts from the code alone (the bit position depends on them: kept to a few ALU ops)
+// code -> baseline | extra-bit count << 24: what decode_sequences16 expects in its llb / mlb tables (one shared-memory
+// load per code gives both; the bit position depends on the count)
+// extra-bit counts from the code alone
 PNA_HD uint32_t ll_xbits(uint32_t c) {
     return c < 16 ? 0u : c >= 25 ? c - 19u : (uint32_t)((0x433221111ull >> (4 * (c - 16))) & 15u);
 }
 PNA_HD uint32_t ml_xbits(uint32_t c) {
     return c < 32 ? 0u : c >= 43 ? c - 36u : (uint32_t)((0x54433221111ull >> (4 * (c - 32))) & 15u);
 }
+PNA_HD uint32_t seq_pack_ll(uint32_t c) { return ll_base((int)c) | (ll_xbits(c) << 24); }
+PNA_HD uint32_t seq_pack_ml(uint32_t c) { return ml_base((int)c) | (ml_xbits(c) << 24); }
 
 // Backward bit window: 64 bits held left-aligned in a register, refilled 32 bits at a time from the
 // aligned word below (prefetched one refill ahead, so the load latency is off the decode chain).
@@ -430,7 +434,15 @@ PNA_HD uint64_t bits_window(const uint32_t* wb, uint32_t b0, int32_t pos) {
 }
 // n bits (0..32) of window W starting `skip` bits below its top (skip + n <= 64)
 PNA_HD uint32_t win_bits(uint64_t W, uint32_t skip, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    // two 32-bit funnel shifts instead of three emulated 64-bit shifts (this sits on the decode chain)
+    const uint32_t hi = (uint32_t)(W >> 32), lo = (uint32_t)W;
+    const uint32_t a = skip >= 32u ? lo : hi, b = skip >= 32u ? 0u : lo;
+    const uint32_t t = __funnelshift_l(b, a, skip);        // shift taken mod 32: bits [skip, skip + 32) of W
+    return __funnelshift_rc(t, 0u, 32u - n);               // clamped: n == 0 -> 0
+#else
     return (uint32_t)(((W << skip) >> 1) >> (63 - n));
+#endif
 }
 
 // Sequence decode of one block by ONE thread (a lane of zstd_seq_kernel).  Position-based bit
@@ -439,7 +451,7 @@ PNA_HD uint32_t win_bits(uint64_t W, uint32_t skip, uint32_t n) {
 // writes; longer ones take a second window) are cut out of it, and only
 //   state -> table cell -> bit counts -> next position / next state
 // is loop-carried.  Errors are collected in a flag (no early exits inside the loop).
-// llb/mlb: value baselines by code.  Same accept/reject behaviour as decode_sequences().
+// llb/mlb: by code, value baseline | extra-bit count << 24 (seq_pack_ll / seq_pack_ml).  Same accept/reject behaviour as decode_sequences().
 // Where decode_sequences16 takes its 64-bit windows from.  GlobalBitSrc: straight from the arena (three aligned loads
 // per window, the sector 128 bytes below pulled into L1 ahead of use); zstd_seq_kernel uses a per-lane shared-memory
 // ring fed by cp.async instead (kernels_zstd.cuh: RingBitSrc), which takes the HBM/L2 latency off the decode chain.
@@ -486,7 +498,8 @@ PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const ui
     uint32_t ell = tll.get(sll), eof = tof.get(sof), eml = tml.get(sml);
     for (uint32_t i = 0; i < nseq; i++) {
         const uint32_t cll = ell >> 10, cof = eof >> 10, cml = eml >> 10;
-        const uint32_t xll = ll_xbits(cll), xml = ml_xbits(cml);
+        const uint32_t pll = llb[cll], pml = mlb[cml];       // baseline | extra bits << 24 (seq_pack_base)
+        const uint32_t xll = pll >> 24, xml = pml >> 24;
         const uint32_t nsl = ell & 1023u, nsm = eml & 1023u, nso = eof & 1023u;
         const uint32_t nbl = ulll - (uint32_t)highbit32(nsl), nbm = ulml - (uint32_t)highbit32(nsm),
                        nbo = ulof - (uint32_t)highbit32(nso);
@@ -513,8 +526,8 @@ PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const ui
         // ---- this sequence's values
         const uint32_t mlx = x >> xll, llx = x & ((1u << xll) - 1u);
         const uint32_t ofv = (1u << cof) + ofx;
-        const uint32_t ml = mlb[cml] + mlx;
-        const uint32_t ll = llb[cll] + llx;
+        const uint32_t ml = (pml & 0xFFFFFFu) + mlx;
+        const uint32_t ll = (pll & 0xFFFFFFu) + llx;
         // repeat-offset logic (RFC 8878 3.1.1.5), branch-free; offsets may be symbolic (REP_SYM) in the block's incoming history
         const bool is_new = ofv > 3;
         const uint32_t idx = ofv - 1 + (ll == 0 ? 1u : 0u);                     // meaningful when !is_new: 0..3

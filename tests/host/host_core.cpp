@@ -84,8 +84,8 @@ extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uin
     std::vector<SeqRec> seqs(seq_total + 1);
     std::vector<uint16_t> tab16(TAB16_TOTAL);
     uint32_t llb[36], mlb[53];
-    for (int c = 0; c < 36; c++) { llb[c] = ll_base(c); if (ll_xbits(c) != (uint32_t)ll_bits(c)) return ST_INTERNAL; }
-    for (int c = 0; c < 53; c++) { mlb[c] = ml_base(c); if (ml_xbits(c) != (uint32_t)ml_bits(c)) return ST_INTERNAL; }
+    for (int c = 0; c < 36; c++) { llb[c] = seq_pack_ll((uint32_t)c); if (ll_xbits(c) != (uint32_t)ll_bits(c)) return ST_INTERNAL; }
+    for (int c = 0; c < 53; c++) { mlb[c] = seq_pack_ml((uint32_t)c); if (ml_xbits(c) != (uint32_t)ml_bits(c)) return ST_INTERNAL; }
     std::vector<uint16_t> huf(1 << HUF_LOG_MAX);
     for (uint32_t i = 0; i < nb; i++) {
         ZBlock& b = blocks[i];
