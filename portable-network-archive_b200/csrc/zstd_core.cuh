@@ -540,14 +540,17 @@ PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const ui
         rep2 = sh2 ? rep1 : rep2;
         rep1 = sh1 ? rep0 : rep1;
         rep0 = off;
-        if (ll >= SEQ_ESC || ml >= SEQ_ESC) {
-            if (ne < (uint32_t)SEQ_ESC_MAX) { esc_idx[ne] = i; esc_ll[ne] = ll; esc_ml[ne] = ml; }
-            else err |= 1u;                                  // > 4 such sequences cannot fit a 128 KiB block
-            ne++;
-        }
         SeqRec r;
         r.x = off;
-        r.y = (ll < SEQ_ESC ? ll : SEQ_ESC) | ((ml < SEQ_ESC ? ml : SEQ_ESC) << 16);
+        r.y = ll | (ml << 16);
+        if ((ll | ml) >= SEQ_ESC) {                          // cheap superset of "a length does not fit 16 bits" (rare)
+            if (ll >= SEQ_ESC || ml >= SEQ_ESC) {
+                if (ne < (uint32_t)SEQ_ESC_MAX) { esc_idx[ne] = i; esc_ll[ne] = ll; esc_ml[ne] = ml; }
+                else err |= 1u;                              // > 4 such sequences cannot fit a 128 KiB block
+                ne++;
+            }
+            r.y = (ll < SEQ_ESC ? ll : SEQ_ESC) | ((ml < SEQ_ESC ? ml : SEQ_ESC) << 16);
+        }
         out[i] = r;
         lit_sum += ll; match_sum += ml;
     }

@@ -66,6 +66,66 @@ def test_index_pass_errors(host):
     assert ei.value.kind == 1
 
 
+def _synthetic_archive(n_entries, rnd, decoys=True):
+    """Entries with 1..3 FDAT bodies of ragged sizes; bodies carry well-formed chunk headers as DATA (decoys for the
+    speculative chunk walk) and a few are megabytes long (a thread's region can start deep inside one)."""
+    import struct
+    import zlib
+    parts = [b"\x89PNA\r\n\x1a\n"]
+
+    def chunk(ty, data):
+        parts.append(struct.pack(">I", len(data)) + ty + data + struct.pack(">I", zlib.crc32(ty + data)))
+    decoy = b"".join(struct.pack(">I", 8) + b"FDAT" + bytes(8) + bytes(4) for _ in range(12))   # 12 plausible chunks
+    chunk(b"AHED", bytes(8))
+    want = []
+    for i in range(n_entries):
+        name = f"dir/{i:07d}.bin"
+        chunk(b"FHED", bytes([0, 0, 0, 0, 0, 0]) + name.encode())
+        nb = rnd.randrange(1, 4)
+        total = 0
+        sizes = []
+        for b in range(nb):
+            n = rnd.choice([0, 1, 17, 300, 4000, 70_000]) if i % 997 else 3_000_000
+            body = (decoy * (n // len(decoy) + 1))[:n] if decoys else bytes(n)
+            chunk(b"FDAT", body)
+            sizes.append(n)
+            total += n
+        chunk(b"fSIZ", total.to_bytes(8, "big").lstrip(b"\0") or b"")
+        chunk(b"FEND", b"")
+        want.append((name, nb, total))
+    chunk(b"AEND", b"")
+    return b"".join(parts), want
+
+
+def test_parallel_index_pass_equals_serial_walk(host, monkeypatch):
+    """Archives >= 32 MiB are indexed by several threads that guess a chunk boundary inside their region and are only
+    believed when the previous thread's walk lands exactly there (host_api.cpp index_chunks / group_entries): the result
+    must be the serial walk's, decoy chunk headers inside bodies and multi-megabyte chunks notwithstanding."""
+    import random
+    blob, want = _synthetic_archive(30_000, random.Random(12))
+    assert len(blob) > (64 << 20)
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    views = []
+    for serial in (False, True):
+        if serial:
+            monkeypatch.setenv("PNA_INDEX_SERIAL", "1")
+        a = host.HostArchive(buf)
+        ents = a.entries()
+        views.append((a.n_chunks, [(e["name"], e["n_bodies"], e["compressed_size"], e["raw_file_size"]) for e in ents]))
+        a.close()
+    assert views[0] == views[1]
+    assert [(n, b, t, t) for n, b, t in want] == views[0][1]
+    # a truncated archive reports the same error either way
+    for serial in (False, True):
+        if serial:
+            monkeypatch.setenv("PNA_INDEX_SERIAL", "1")
+        else:
+            monkeypatch.delenv("PNA_INDEX_SERIAL", raising=False)
+        with pytest.raises(host.HostError) as ei:
+            host.HostArchive(buf[: len(blob) - 40_000_001].copy())
+        assert ei.value.kind == 2
+
+
 @pytest.mark.gpu
 def test_golden_archives_through_cpp_host(host, pna, ctx, golden):
     for name, info in golden["archives"].items():
