@@ -19,24 +19,53 @@ constexpr int FAST_BITS = 9;
 // Per-stream decoding tables (canonical Huffman): an FB-bit direct table in front of the
 // count/symbol arrays (FB = 0: no direct table).  fast[] entry: (symbol << 4) | length, 0 = not
 // resolvable in FB bits.  The literal/length code gets a 9-bit table, the distance code none, so that
-// one stream's tables are 1.7 KB and 64 streams fit one CTA's shared memory.
+// one stream's tables are 1.8 KB (an odd number of 32-bit words: the lanes of a warp start on different banks).
+// Codes the direct table does not resolve are found without a bit-by-bit walk: the next 15 bits, MSB first, are compared
+// against the 15 left-aligned length bounds lim[] (branch-free, no loop-carried dependency).
 template <int NSYM, int FB>
 struct Huff {
-    uint16_t count[MAXBITS + 1];
+    uint16_t lim[MAXBITS + 1];    // lim[l], l = 1..15: first code of length l+1, left-aligned to 15 bits = exclusive bound of the codes of length <= l
+    int16_t base[MAXBITS + 1];    // symbol[] index of a code of length l = base[l] + code
+    uint16_t n01;                 // symbols with code length 0 or 1 (the callers' incomplete-code rule)
     uint16_t symbol[NSYM];
     uint16_t fast[FB ? (1 << FB) : 1];
 };
 struct Tables {
     Huff<MAXL, FAST_BITS> len;
     Huff<MAXD + 2, 0> dist;
-    uint16_t _pad;   // odd number of 32-bit words per stream: lanes start on different banks
+    uint16_t _pad[3];   // 1804 bytes = 451 words: an odd number of 32-bit words per stream
 };
 
+// LSB-first bit reader.  On the device the next four input bytes are always loaded one refill AHEAD (`nx`), so the
+// load's latency (L2 every 128 bytes, L1 otherwise) is off the symbol chain: a refill only shifts a register in.
+// The arena behind every stream is padded, so the look-ahead may read (never use) a few bytes past the end.
 struct Bits {
     const uint8_t* p;
     uint64_t n, pos;
     uint64_t buf;
     int cnt;
+#if defined(__CUDA_ARCH__)
+    uint32_t nx;   // bytes [pos, pos + 4) of the input, little endian
+    PNA_HD void reload() { nx = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24); }
+    PNA_HD void init(const uint8_t* in, uint64_t len) { p = in; n = len; pos = 0; buf = 0; cnt = 0; nx = 0; if (len) reload(); }
+    PNA_HD void fill(int need) {   // need <= 32
+        if (cnt >= need) return;
+        uint32_t w = nx;
+        if (pos + 4 > n) {         // zeros beyond the end; overrun() tells
+            const uint32_t valid = pos < n ? (uint32_t)(n - pos) : 0u;
+            w = valid ? (w & (0xFFFFFFFFu >> (8u * (4u - valid)))) : 0u;
+        }
+        if (cnt <= 32) {
+            buf |= (uint64_t)w << cnt;
+            pos += 4;
+            cnt += 32;
+            reload();
+        }
+    }
+    PNA_HD void align_byte() { pos = (consumed_bits() + 7) / 8; buf = 0; cnt = 0; reload(); }
+    PNA_HD void skip_bytes(uint64_t k) { pos += k; reload(); }   // caller consumed k bytes at p + pos directly (stored block)
+#else
+    PNA_HD void reload() {}
     PNA_HD void init(const uint8_t* in, uint64_t len) { p = in; n = len; pos = 0; buf = 0; cnt = 0; }
     PNA_HD void fill(int need) {
         if (cnt >= need) return;
@@ -53,9 +82,11 @@ struct Bits {
             cnt += 8;
         }
     }
+    PNA_HD void align_byte() { pos = (consumed_bits() + 7) / 8; buf = 0; cnt = 0; }
+    PNA_HD void skip_bytes(uint64_t k) { pos += k; }
+#endif
     PNA_HD uint64_t consumed_bits() const { return pos * 8 - (uint64_t)cnt; }
     PNA_HD bool overrun() const { return consumed_bits() > n * 8; }   // consumed bits that do not exist
-    PNA_HD void align_byte() { pos = (consumed_bits() + 7) / 8; buf = 0; cnt = 0; }
     PNA_HD uint32_t get(int k) {
         if (k == 0) return 0;
         fill(k);
@@ -74,19 +105,30 @@ PNA_HD uint32_t rev_bits(uint32_t v, int n) {
 // canonical table from code lengths; returns 0 ok, <0 over-subscribed, >0 incomplete (puff semantics)
 template <int NSYM, int FB>
 PNA_HD int build(Huff<NSYM, FB>* h, const uint8_t* length, int n) {
-    for (int l = 0; l <= MAXBITS; l++) h->count[l] = 0;
-    for (int s = 0; s < n; s++) h->count[length[s]]++;
+    uint16_t count[MAXBITS + 1];
+    for (int l = 0; l <= MAXBITS; l++) { count[l] = 0; h->lim[l] = 0; h->base[l] = 0; }
+    for (int s = 0; s < n; s++) count[length[s]]++;
+    h->n01 = (uint16_t)(count[0] + count[1]);
     if (FB) for (int i = 0; i < (1 << FB); i++) h->fast[i] = 0;
-    if (h->count[0] == n) return 0;
+    if (count[0] == n) return 0;
     int left = 1;
     for (int l = 1; l <= MAXBITS; l++) {
         left <<= 1;
-        left -= h->count[l];
+        left -= count[l];
         if (left < 0) return left;
     }
     uint16_t offs[MAXBITS + 1];
     offs[1] = 0;
-    for (int l = 1; l < MAXBITS; l++) offs[l + 1] = offs[l] + h->count[l];
+    for (int l = 1; l < MAXBITS; l++) offs[l + 1] = offs[l] + count[l];
+    {   // length bounds and symbol bases of the canonical code
+        uint32_t first = 0;
+        for (int l = 1; l <= MAXBITS; l++) {
+            h->base[l] = (int16_t)((int)offs[l] - (int)first);
+            first += count[l];
+            h->lim[l] = (uint16_t)(first << (MAXBITS - l));   // <= 2^15 for a code that is not over-subscribed
+            first <<= 1;
+        }
+    }
     for (int s = 0; s < n; s++)
         if (length[s]) h->symbol[offs[length[s]]++] = (uint16_t)s;
     // fast table: canonical codes, bit-reversed because DEFLATE packs Huffman codes MSB first
@@ -94,7 +136,7 @@ PNA_HD int build(Huff<NSYM, FB>* h, const uint8_t* length, int n) {
         uint32_t code = 0;
         int idx = 0;
         for (int l = 1; l <= FB; l++) {
-            for (int k = 0; k < h->count[l]; k++, idx++, code++) {
+            for (int k = 0; k < count[l]; k++, idx++, code++) {
                 uint32_t r = rev_bits(code, l);
                 uint16_t e = (uint16_t)((h->symbol[idx] << 4) | l);
                 for (uint32_t f = r; f < (1u << FB); f += (1u << l)) h->fast[f] = e;
@@ -116,23 +158,19 @@ PNA_HD int decode_sym(Bits& b, const Huff<NSYM, FB>* h) {
             return e >> 4;
         }
     }
-    // slow path: canonical walk, one bit at a time (puff)
-    int code = 0, first = 0, index = 0;
-    uint64_t bits = b.buf;
-    for (int l = 1; l <= MAXBITS; l++) {
-        code |= (int)(bits & 1);
-        bits >>= 1;
-        int count = h->count[l];
-        if (code - count < first) {
-            b.buf >>= l; b.cnt -= l;
-            return h->symbol[index + (code - first)];
-        }
-        index += count;
-        first += count;
-        first <<= 1;
-        code <<= 1;
-    }
-    return -1;
+    // the next 15 bits MSB first; the code length is 1 + the number of length bounds the window has reached
+#if defined(__CUDA_ARCH__)
+    const uint32_t w = __brev((uint32_t)b.buf) >> 17;
+#else
+    const uint32_t w = rev_bits((uint32_t)b.buf & 0x7FFFu, MAXBITS);
+#endif
+    int l = 1;
+#pragma unroll
+    for (int k = 1; k < MAXBITS; k++) l += (int)(w >= h->lim[k]);
+    if (w >= h->lim[MAXBITS]) return -1;             // no code: incomplete set, or none at all
+    const int idx = (int)h->base[l] + (int)(w >> (MAXBITS - l));
+    b.buf >>= l; b.cnt -= l;
+    return h->symbol[idx];
 }
 
 PNA_HD uint32_t len_base(int s) {   // s = symbol - 257
@@ -231,12 +269,12 @@ PNA_HD int32_t inflate_zlib_to(Emit& E, const uint8_t* in, uint64_t n, Tables* t
             b.align_byte();
             if (b.pos + 4 > b.n) PNA_INF_TRUNC();
             uint32_t len = load_le16(b.p + b.pos), nlen = load_le16(b.p + b.pos + 2);
-            b.pos += 4;
+            b.skip_bytes(4);
             if (len != (~nlen & 0xFFFFu)) return ST_INVALID_INPUT;
             uint64_t avail = b.n - b.pos;
             uint32_t take = len <= avail ? len : (uint32_t)avail;
             for (uint32_t i = 0; i < take; i++) E.lit(b.p[b.pos + i]);
-            b.pos += take;
+            b.skip_bytes(take);
             if (take < len) PNA_INF_TRUNC();
             continue;
         }
@@ -283,9 +321,9 @@ PNA_HD int32_t inflate_zlib_to(Emit& E, const uint8_t* in, uint64_t n, Tables* t
             }
             if (lengths[256] == 0) return ST_INVALID_INPUT;
             int err = build(&t->len, lengths, nlen);
-            if (err && (err < 0 || nlen != t->len.count[0] + t->len.count[1])) return ST_INVALID_INPUT;
+            if (err && (err < 0 || nlen != t->len.n01)) return ST_INVALID_INPUT;
             err = build(&t->dist, lengths + nlen, ndist);
-            if (err && (err < 0 || ndist != t->dist.count[0] + t->dist.count[1])) return ST_INVALID_INPUT;
+            if (err && (err < 0 || ndist != t->dist.n01)) return ST_INVALID_INPUT;
         }
         // symbols.  Single-exit loop without returns inside: with one stream per LANE the literal and the match arm must
         // reconverge every iteration (an early return inside an arm leaves the lanes split for the rest of the block).

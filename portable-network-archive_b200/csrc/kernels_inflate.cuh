@@ -2,7 +2,7 @@
 //
 // Two-stage path (every stream whose decoded size is known and < 2 GiB):
 //   inflate_tokens_kernel  ONE LANE per stream.  DEFLATE's bit-serial part (dynamic/fixed Huffman tables in shared
-//                          memory, 1732 B per stream, 128 streams per SM) only records what the stream says: literal
+//                          memory, 1804 B per stream, 128 streams per SM) only records what the stream says: literal
 //                          bytes into a literal buffer and one 8-byte (distance, literal run | match length << 16) record
 //                          per match -- the records the zstd sequence stage produces.  No output byte is touched, so a
 //                          lane never waits on its own stores and the 32 lanes of a warp diverge only between the
@@ -20,11 +20,11 @@
 namespace pna {
 namespace inf {
 
-static_assert(sizeof(Tables) == 1732, "one stream's tables: odd number of 32-bit words");
+static_assert(sizeof(Tables) == 1804 && (sizeof(Tables) / 4) % 2 == 1, "one stream's tables: an odd number of 32-bit words");
 static_assert(sizeof(TokenRec) == sizeof(zs::SeqRec), "token records are sequence records");
 constexpr int INFLATE_CTA = 8;     // streams (= warps) per CTA of inflate_kernel
 constexpr int TOKEN_CTA = 128;     // streams (= threads) per CTA of inflate_tokens_kernel
-constexpr uint32_t TOKEN_SMEM_BYTES = (uint32_t)sizeof(Tables) * TOKEN_CTA;   // 221696
+constexpr uint32_t TOKEN_SMEM_BYTES = (uint32_t)sizeof(Tables) * TOKEN_CTA;   // 230912
 
 struct InfStream {      // one deflate stream of the two-stage path (host filled)
     uint32_t entry;     // index into EntryRec[]
@@ -78,9 +78,9 @@ __device__ __noinline__ int read_dynamic_tables(Bits& b, Tables* t) {
     }
     if (lengths[256] == 0) return 2;
     int err = build(&t->len, lengths, nlen);
-    if (err && (err < 0 || nlen != t->len.count[0] + t->len.count[1])) return 2;
+    if (err && (err < 0 || nlen != t->len.n01)) return 2;
     err = build(&t->dist, lengths + nlen, ndist);
-    if (err && (err < 0 || ndist != t->dist.count[0] + t->dist.count[1])) return 2;
+    if (err && (err < 0 || ndist != t->dist.n01)) return 2;
     return 0;
 }
 __device__ __noinline__ void build_fixed_tables(Tables* t) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ int32_t inflate_tokens_lane(TokenEmit& E, const uint8
                 if (b.pos + 4 > b.n) trunc();
                 else {
                     const uint32_t len = load_le16(b.p + b.pos), nlen = load_le16(b.p + b.pos + 2);
-                    b.pos += 4;
+                    b.skip_bytes(4);
                     if (len != (~nlen & 0xFFFFu)) bad();
                     else { stored_left = len; state = S_STORED; }
                 }
@@ -134,7 +134,7 @@ __device__ __forceinline__ int32_t inflate_tokens_lane(TokenEmit& E, const uint8
             else {
                 int rc = 0;
                 if (type == 1) build_fixed_tables(t);
-                else rc = read_dynamic_tables(b, t);
+                else { Bits tb = b; rc = read_dynamic_tables(tb, t); b = tb; }   // only the copy's address escapes: b stays in registers
                 if (rc == 1) trunc(); else if (rc == 2) bad(); else state = S_SYM;
             }
         }
@@ -182,7 +182,7 @@ __device__ __forceinline__ int32_t inflate_tokens_lane(TokenEmit& E, const uint8
             uint32_t take = stored_left < 256u ? stored_left : 256u;
             if (take > avail) take = (uint32_t)avail;
             for (uint32_t i = 0; i < take; i++) E.lit(b.p[b.pos + i]);
-            b.pos += take;
+            b.skip_bytes(take);
             stored_left -= take;
             if (stored_left && b.pos >= b.n) trunc();
             else if (!stored_left) state = last ? S_TRAILER : S_HDR;
