@@ -133,6 +133,7 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
             s.len = (uint32_t)std::min<uint64_t>(enc::SEG, e.plain_len - (uint64_t)k * enc::SEG);
             s.entry = i;
             s.last = k + 1 == e.n_segs;
+            s.adler = e.compression == PNA_COMPRESSION_DEFLATE;
         }
         piece_cur += 3 + 3 * (uint64_t)e.n_segs;
         const uint64_t bound = enc_comp_bound(e.compression, e.plain_len) + (e.encryption ? 32 : 0);

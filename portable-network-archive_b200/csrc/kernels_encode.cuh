@@ -22,7 +22,7 @@ struct SegRec {            // one segment (host fills the first group, kernels t
     uint64_t lit_off;
     uint64_t tmp_off;      // 16 bytes of head + body
     uint64_t seq_off;      // index into the Seq arena
-    uint32_t len, entry, last, _pad;
+    uint32_t len, entry, last, adler;   // adler: the entry is a zlib stream (its Adler-32 partial sums are wanted)
     uint32_t nseq, nlit;
     uint32_t head_len, raw;        // raw: pieces = head + plain; else head + literals + tail (zstd) / body (deflate)
     uint32_t tail_off, tail_len;   // inside the body
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
     {
         const uint4* src = reinterpret_cast<const uint4*>(work_ro + sr.plain_off);
         const uint32_t rows = (len + 15) / 16;
-        for (uint32_t i = lane; i < rows; i += 32) {
+        for (uint32_t i = lane; i < (sr.adler ? rows : 0u); i += 32) {
             const uint4 v = __ldg(src + i);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
         __syncwarp();
         if (valid && lane == 31 - __clz((int)hm)) S->table[h] = (uint16_t)p;   // deterministic; every position is inserted
         if (carry >= 32) { carry -= 32; continue; }   // the whole step lies inside a match
-        // ---- match lengths against both candidates in one loop, four bytes per step (unaligned words from two
-        // aligned shared loads + funnel shift; the zero tail behind the segment makes the over-read harmless)
+        // ---- match lengths against both candidates in one loop (lengths are clamped to the segment, so the over-read
+        // behind it is harmless)
         uint32_t best = 0, boff = 0;
-        if (valid) {
+        if (valid && (uint32_t)lane >= carry) {   // positions below `carry` lie inside the previous step's last match: never parsed
             const uint32_t maxlen = len - p < MAX_MATCH ? len - p : MAX_MATCH;
             bool aw = cw != 0xFFFFu, at = ct != 0xFFFFu && ct != cw;
             uint32_t lw = 0, ltb = 0, k = 0;
