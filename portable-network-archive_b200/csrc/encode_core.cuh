@@ -10,7 +10,8 @@
 // Stream shapes written here:
 //   zstd   one frame per entry: magic, FHD 0x00 (no content size / checksum / dictionary -- like the
 //          reference's streaming encoder), Window_Descriptor 0x38 (128 KiB), one block per 32 KiB segment.
-//          Compressed block = Raw_Literals + sequences coded with the PREDEFINED FSE tables (mode byte 0x00),
+//          Compressed block = Huffman-compressed (or raw) literals + sequences coded with the PREDEFINED FSE tables
+//          (mode byte 0x00),
 //          repeat offsets are used for the history slots the block has set itself (zstd_assign_repcodes).  A block that does not shrink becomes a Raw_Block.
 //   zlib   0x78 0x9C, per segment one fixed-Huffman block followed by an empty stored block (the Z_SYNC_FLUSH
 //          marker 00 00 FF FF) so that segments stay byte aligned and can be produced independently; the last

@@ -2,7 +2,7 @@
 //   lz_match_kernel      (warp per 32 KiB segment)  warp-synchronous greedy LZ77: 32 positions per step, candidates
 //                        from a shared-memory hash table AND from the step's own lanes (__match_any_sync), greedy
 //                        parse of the step by pointer doubling with shuffles, sequences + literals compacted by ballots
-//   enc_block_kernel     (lane per segment)         zstd block (predefined-FSE sequences, raw literals) or deflate
+//   enc_block_kernel     (lane per segment)         zstd block (predefined-FSE sequences + repeat offsets, Huffman or raw literals) or deflate
 //                        fixed-Huffman block, written by the PNA_HD writers of encode_core.cuh
 //   enc_layout_kernel    (thread per entry)         frame header / trailer, piece list of the compressed stream, Adler-32
 //   encrypt_tiles_kernel (thread per 16-byte block) gather the pieces, AES/Camellia CTR (or plain copy) into the output
