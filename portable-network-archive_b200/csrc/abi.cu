@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -78,7 +79,11 @@ struct DevCache {
             }
         }
         // the driver call runs outside the lock: other threads keep hitting the cache meanwhile
+        static const bool trace = getenv("PNA_HOST_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMalloc(out, bytes);
+        if (trace) fprintf(stderr, "[pna_cuda] cudaMalloc(%zu MiB) took %.1f ms\n", bytes >> 20,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         if (e != cudaSuccess) {   // give cached blocks back to the driver and retry once
             cudaGetLastError();
             trim(dev);

@@ -577,6 +577,46 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
     const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull, iv_len = enc ? 16 : 0;
     if (cap < 8 + 20 + 12) throw Error(PNA_E_NOSPACE, "archive buffer too small");
     memcpy(out, SIGNATURE, 8);
+    // ---- metadata chunks (type || data, contiguous) of EVERY entry plus AHED / AEND, CRCs in one GPU batch up front: the
+    // device is idle now, later these tiny kernels would queue behind the encode kernels of whole groups
+    const size_t metas_per_entry = enc ? 5 : 3;
+    std::vector<uint8_t> meta;
+    struct MetaRef { size_t off; uint32_t len; };
+    std::vector<MetaRef> refs;
+    refs.reserve(n * metas_per_entry + 2);
+    auto add_meta = [&](const char* ty, const uint8_t* data, uint32_t len) {
+        refs.push_back({meta.size(), len + 4});
+        meta.insert(meta.end(), ty, ty + 4);
+        if (len) meta.insert(meta.end(), data, data + len);
+    };
+    for (size_t i = 0; i < n; i++) {
+        const FileEntryBuilder& f = files[i];
+        const uint8_t h6[6] = {0, 0, (uint8_t)DataKind::File, opt.compression, opt.encryption, opt.cipher_mode};
+        refs.push_back({meta.size(), (uint32_t)(4 + 6 + f.name.size())});
+        meta.insert(meta.end(), {'F', 'H', 'E', 'D'});
+        meta.insert(meta.end(), h6, h6 + 6);
+        meta.insert(meta.end(), f.name.begin(), f.name.end());
+        uint8_t sz[8];
+        for (int b = 0; b < 8; b++) sz[b] = (uint8_t)(f.data.len >> (8 * (7 - b)));
+        int skip = 0;
+        while (skip < 8 && sz[skip] == 0) skip++;                       // entry.rs:901-903: minimal big-endian bytes
+        add_meta("fSIZ", sz + skip, (uint32_t)(8 - skip));
+        if (enc) {
+            add_meta("PHSF", (const uint8_t*)opt.phsf.data(), (uint32_t)opt.phsf.size());
+            add_meta("FDAT", f.iv, 16);                                 // the IV is its own chunk (builder.rs:62-69)
+        }
+        add_meta("FEND", nullptr, 0);
+    }
+    const uint8_t ahed8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    add_meta("AHED", ahed8, 8);
+    add_meta("AEND", nullptr, 0);
+    std::vector<uint32_t> mcrc(refs.size());
+    {
+        std::vector<pna_span> spans(refs.size());
+        for (size_t r = 0; r < refs.size(); r++) spans[r] = {meta.data() + refs[r].off, refs[r].len};
+        CtxLease L(device);
+        ck(L.ctx, pna_cuda_crc32(L.ctx, spans.data(), (uint32_t)spans.size(), mcrc.data()), "metadata crc");
+    }
     // group g starts at base[g]; base[g+1] is published by the worker of group g as soon as it knows its size
     std::vector<uint64_t> base(groups.size() + 1, 0);
     std::vector<uint8_t> ready(groups.size() + 1, 0);
@@ -591,149 +631,144 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
     const bool trace = getenv("PNA_HOST_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-    auto work = [&]() {
+    // Every worker keeps TWO contexts and software-pipelines its groups like extract_files does:
+    //   issue(g): upload the plaintext (taking turns on PCIe) + launch the encode kernels (asynchronous)
+    //   finish(g-1): wait for the previous group's lengths, take its place behind its predecessor, D2H the streams to their
+    //                final position, write the chunk frames around them
+    // so a group's kernels run while the next group's plaintext is on its way and the previous group's streams leave.
+    struct Stage {
         size_t g = 0;
-        try {
-            CtxLease L(device);
-            for (;;) {
-                g = next.fetch_add(1);
-                if (g >= groups.size()) break;
-                const double tl = ms_now();
-                const Group G = groups[g];
-                const uint32_t m = (uint32_t)(G.hi - G.lo);
-                std::vector<pna_encode_desc> descs(m);
-                uint64_t crc_total = 0;
-                for (uint32_t k = 0; k < m; k++) {
-                    const FileEntryBuilder& f = files[G.lo + k];
-                    pna_encode_desc& d = descs[k];
-                    memset(&d, 0, sizeof d);
-                    d.plain = f.data;
-                    d.compression = opt.compression; d.encryption = opt.encryption; d.cipher_mode = opt.cipher_mode; d.level = opt.level;
-                    memcpy(d.key, opt.key, 32); memcpy(d.iv, f.iv, 16);
-                    d.max_chunk_size = max_chunk_size;
-                    crc_total += pna_cuda_encode_crc_count(&d);
-                }
-                pna_plan* plan = nullptr;
-                double tr0;
-                {
-                    // one upload at a time: PCIe is the shared resource, and taking turns staggers the workers so that one
-                    // group's kernels run while the next group's plaintext is still on its way
-                    SlotGuard h2d(h2d_slots);
-                    tr0 = ms_now();
-                    ck(L.ctx, pna_cuda_encode_plan_create(L.ctx, descs.data(), m, &plan), "encode_plan_create");
-                }
-                const double tr1 = ms_now();
-                struct PlanGuard { pna_plan* p; ~PlanGuard() { if (p) pna_cuda_plan_destroy(p); } } guard{plan};
-                ck(L.ctx, pna_cuda_encode_plan_run(plan), "encode_plan_run");
-                // metadata chunks (type || data, contiguous) and their CRCs in one GPU batch while the encode kernels run
-                std::vector<uint8_t> meta;
-                struct MetaRef { size_t off; uint32_t len; };
-                std::vector<MetaRef> refs;
-                auto add_meta = [&](const char* ty, const uint8_t* data, uint32_t len) {
-                    refs.push_back({meta.size(), len + 4});
-                    meta.insert(meta.end(), ty, ty + 4);
-                    if (len) meta.insert(meta.end(), data, data + len);
-                };
-                for (uint32_t k = 0; k < m; k++) {
-                    const FileEntryBuilder& f = files[G.lo + k];
-                    std::vector<uint8_t> hdr = {0, 0, (uint8_t)DataKind::File, opt.compression, opt.encryption, opt.cipher_mode};
-                    hdr.insert(hdr.end(), f.name.begin(), f.name.end());
-                    add_meta("FHED", hdr.data(), (uint32_t)hdr.size());
-                    uint8_t sz[8];
-                    for (int b = 0; b < 8; b++) sz[b] = (uint8_t)(f.data.len >> (8 * (7 - b)));
-                    int skip = 0;
-                    while (skip < 8 && sz[skip] == 0) skip++;                       // entry.rs:901-903: minimal big-endian bytes
-                    add_meta("fSIZ", sz + skip, (uint32_t)(8 - skip));
-                    if (enc) {
-                        add_meta("PHSF", (const uint8_t*)opt.phsf.data(), (uint32_t)opt.phsf.size());
-                        add_meta("FDAT", f.iv, 16);                                 // the IV is its own chunk (builder.rs:62-69)
-                    }
-                    add_meta("FEND", nullptr, 0);
-                }
-                std::vector<pna_span> spans(refs.size());
-                std::vector<uint32_t> mcrc(refs.size());
-                for (size_t r = 0; r < refs.size(); r++) spans[r] = {meta.data() + refs[r].off, refs[r].len};
-                {
-                    CtxLease L2(device);   // a second context: the encode plan's stream stays busy meanwhile
-                    ck(L2.ctx, pna_cuda_crc32(L2.ctx, spans.data(), (uint32_t)spans.size(), mcrc.data()), "metadata crc");
-                }
-                std::vector<uint64_t> lens(m);
-                std::vector<int32_t> st(m);
-                const double tr2 = ms_now();
-                ck(L.ctx, pna_cuda_encode_plan_lengths(plan, lens.data(), st.data()), "encode_plan_lengths");
-                const double tr3 = ms_now();
-                // layout of this group
-                std::vector<uint64_t> entry_pos(m + 1, 0);
-                const size_t metas_per_entry = enc ? 5 : 3;
-                for (uint32_t k = 0; k < m; k++) {
-                    if (st[k] != PNA_OK) throw Error(st[k], files[G.lo + k].name + ": encode failed");
-                    uint64_t sz = 0;
-                    for (size_t q = 0; q < metas_per_entry; q++) sz += 8 + refs[k * metas_per_entry + q].len;   // len + (type||data) + crc
-                    const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
-                    sz += nb * 12 + D;
-                    entry_pos[k + 1] = entry_pos[k] + sz;
-                }
-                uint64_t my_base;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return ready[g] || failed; });
-                    if (failed) return;
-                    my_base = base[g];
-                    base[g + 1] = my_base + entry_pos[m];
-                    ready[g + 1] = 1;
-                    cv.notify_all();
-                }
-                if (my_base + entry_pos[m] + 12 > cap) throw Error(PNA_E_NOSPACE, "archive buffer too small");
-                // fetch: single-body streams go straight to their final place (the 16 IV bytes land on the frame bytes in front
-                // of the data and are overwritten by them afterwards); multi-body streams pass through a staging buffer
-                std::vector<pna_buf> bufs(m);
-                std::vector<std::vector<uint8_t>> stage(m);
-                std::vector<uint64_t> data_pos(m);
-                for (uint32_t k = 0; k < m; k++) {
-                    uint64_t p = my_base + entry_pos[k];
-                    for (size_t q = 0; q + 1 < metas_per_entry; q++) p += 8 + refs[k * metas_per_entry + q].len;
-                    data_pos[k] = p;   // first FDAT body frame starts here
-                    const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
-                    if (nb <= 1) bufs[k] = pna_buf{out + p + 8 - iv_len, lens[k], 0};
-                    else { stage[k].resize(lens[k]); bufs[k] = pna_buf{stage[k].data(), lens[k], 0}; }
-                }
-                std::vector<uint32_t> crcs(crc_total + 1), ncrc(m, 0);
-                const double tr4 = ms_now();
-                ck(L.ctx, pna_cuda_encode_plan_fetch(plan, bufs.data(), crcs.data(), ncrc.data(), st.data()), "encode_plan_fetch");
-                const double tr5 = ms_now();
-                size_t cpos = 0;
-                for (uint32_t k = 0; k < m; k++) {
-                    if (st[k] != PNA_OK) throw Error(st[k], files[G.lo + k].name + ": fetch failed");
-                    uint8_t* w = out + my_base + entry_pos[k];
-                    auto put_meta = [&](size_t r) {
-                        const MetaRef& mr = refs[r];
-                        wr_be32(w, mr.len - 4); memcpy(w + 4, meta.data() + mr.off, mr.len); wr_be32(w + 4 + mr.len, mcrc[r]);
-                        w += 8 + mr.len;
-                    };
-                    const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
-                    // bodies first where they were staged, then the frames around them (which also repair the IV overlap)
-                    uint8_t* body_w = out + data_pos[k];
-                    for (uint64_t b = 0; b < nb; b++) {
-                        const uint64_t o = b * mcs, l = std::min<uint64_t>(mcs, D - o);
-                        if (nb > 1) memcpy(body_w + 8, stage[k].data() + iv_len + o, l);
-                        wr_be32(body_w + 8 + l, crcs[cpos + b]);
-                        body_w += 12 + l;
-                    }
-                    for (size_t q = 0; q + 1 < metas_per_entry; q++) put_meta(k * metas_per_entry + q);   // FHED, fSIZ, [PHSF, FDAT(iv)]
-                    body_w = out + data_pos[k];
-                    for (uint64_t b = 0; b < nb; b++) {
-                        const uint64_t o = b * mcs, l = std::min<uint64_t>(mcs, D - o);
-                        wr_be32(body_w, (uint32_t)l); memcpy(body_w + 4, "FDAT", 4);
-                        body_w += 12 + l;
-                    }
-                    w = body_w;
-                    put_meta(k * metas_per_entry + metas_per_entry - 1);   // FEND
-                    cpos += ncrc[k];
-                }
-                if (trace) fprintf(stderr, "[pna_host] create group %zu (%u files): top %.1f plan_create/H2D %.1f-%.1f, run+meta -%.1f, lengths(wait) -%.1f, place -%.1f, fetch/D2H -%.1f, frames -%.1f ms\n",
-                                   g, m, tl, tr0, tr1, tr2, tr3, tr4, tr5, ms_now());
+        uint32_t m = 0;
+        pna_plan* plan = nullptr;
+        uint64_t crc_total = 0;
+        std::vector<pna_encode_desc> descs;
+        double t_issue0 = 0, t_issue1 = 0;
+    };
+    auto issue = [&](CtxLease& L, Stage& S, size_t g) {
+        const Group G = groups[g];
+        const uint32_t m = (uint32_t)(G.hi - G.lo);
+        S.g = g; S.m = m; S.plan = nullptr; S.crc_total = 0;
+        S.descs.assign(m, pna_encode_desc{});
+        for (uint32_t k = 0; k < m; k++) {
+            const FileEntryBuilder& f = files[G.lo + k];
+            pna_encode_desc& d = S.descs[k];
+            memset(&d, 0, sizeof d);
+            d.plain = f.data;
+            d.compression = opt.compression; d.encryption = opt.encryption; d.cipher_mode = opt.cipher_mode; d.level = opt.level;
+            memcpy(d.key, opt.key, 32); memcpy(d.iv, f.iv, 16);
+            d.max_chunk_size = max_chunk_size;
+            S.crc_total += pna_cuda_encode_crc_count(&d);
+        }
+        {
+            SlotGuard h2d(h2d_slots);   // uploads take turns: PCIe is the shared resource
+            S.t_issue0 = ms_now();
+            ck(L.ctx, pna_cuda_encode_plan_create(L.ctx, S.descs.data(), m, &S.plan), "encode_plan_create");
+        }
+        S.t_issue1 = ms_now();
+        const int rc = pna_cuda_encode_plan_run(S.plan);
+        if (rc != PNA_OK) { pna_cuda_plan_destroy(S.plan); S.plan = nullptr; ck(L.ctx, rc, "encode_plan_run"); }
+    };
+    auto finish = [&](CtxLease& L, Stage& S) {
+        if (!S.plan) return;
+        struct PlanGuard { pna_plan*& p; ~PlanGuard() { if (p) { pna_cuda_plan_destroy(p); p = nullptr; } } } guard{S.plan};
+        const size_t g = S.g;
+        const Group G = groups[g];
+        const uint32_t m = S.m;
+        const MetaRef* R = refs.data() + G.lo * metas_per_entry;        // this group's metadata chunks
+        const uint32_t* RC = mcrc.data() + G.lo * metas_per_entry;
+        std::vector<uint64_t> lens(m);
+        std::vector<int32_t> st(m);
+        const double tr2 = ms_now();
+        ck(L.ctx, pna_cuda_encode_plan_lengths(S.plan, lens.data(), st.data()), "encode_plan_lengths");
+        const double tr3 = ms_now();
+        // layout of this group
+        std::vector<uint64_t> entry_pos(m + 1, 0);
+        for (uint32_t k = 0; k < m; k++) {
+            if (st[k] != PNA_OK) throw Error(st[k], files[G.lo + k].name + ": encode failed");
+            uint64_t sz = 0;
+            for (size_t q = 0; q < metas_per_entry; q++) sz += 8 + R[k * metas_per_entry + q].len;   // len + (type||data) + crc
+            const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
+            sz += nb * 12 + D;
+            entry_pos[k + 1] = entry_pos[k] + sz;
+        }
+        uint64_t my_base;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return ready[g] || failed; });
+            if (failed) return;
+            my_base = base[g];
+            base[g + 1] = my_base + entry_pos[m];
+            ready[g + 1] = 1;
+            cv.notify_all();
+        }
+        if (my_base + entry_pos[m] + 12 > cap) throw Error(PNA_E_NOSPACE, "archive buffer too small");
+        // fetch: single-body streams go straight to their final place (the 16 IV bytes land on the frame bytes in front
+        // of the data and are overwritten by them afterwards); multi-body streams pass through a staging buffer
+        std::vector<pna_buf> bufs(m);
+        std::vector<std::vector<uint8_t>> stage(m);
+        std::vector<uint64_t> data_pos(m);
+        for (uint32_t k = 0; k < m; k++) {
+            uint64_t p = my_base + entry_pos[k];
+            for (size_t q = 0; q + 1 < metas_per_entry; q++) p += 8 + R[k * metas_per_entry + q].len;
+            data_pos[k] = p;   // first FDAT body frame starts here
+            const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
+            if (nb <= 1) bufs[k] = pna_buf{out + p + 8 - iv_len, lens[k], 0};
+            else { stage[k].resize(lens[k]); bufs[k] = pna_buf{stage[k].data(), lens[k], 0}; }
+        }
+        std::vector<uint32_t> crcs(S.crc_total + 1), ncrc(m, 0);
+        const double tr4 = ms_now();
+        ck(L.ctx, pna_cuda_encode_plan_fetch(S.plan, bufs.data(), crcs.data(), ncrc.data(), st.data()), "encode_plan_fetch");
+        const double tr5 = ms_now();
+        size_t cpos = 0;
+        for (uint32_t k = 0; k < m; k++) {
+            if (st[k] != PNA_OK) throw Error(st[k], files[G.lo + k].name + ": fetch failed");
+            uint8_t* w = out + my_base + entry_pos[k];
+            auto put_meta = [&](size_t r) {
+                const MetaRef& mr = R[r];
+                wr_be32(w, mr.len - 4); memcpy(w + 4, meta.data() + mr.off, mr.len); wr_be32(w + 4 + mr.len, RC[r]);
+                w += 8 + mr.len;
+            };
+            const uint64_t D = lens[k] - iv_len, nb = (D + mcs - 1) / mcs;
+            // bodies first where they were staged, then the frames around them (which also repair the IV overlap)
+            uint8_t* body_w = out + data_pos[k];
+            for (uint64_t b = 0; b < nb; b++) {
+                const uint64_t o = b * mcs, l = std::min<uint64_t>(mcs, D - o);
+                if (nb > 1) memcpy(body_w + 8, stage[k].data() + iv_len + o, l);
+                wr_be32(body_w + 8 + l, crcs[cpos + b]);
+                body_w += 12 + l;
             }
+            for (size_t q = 0; q + 1 < metas_per_entry; q++) put_meta(k * metas_per_entry + q);   // FHED, fSIZ, [PHSF, FDAT(iv)]
+            body_w = out + data_pos[k];
+            for (uint64_t b = 0; b < nb; b++) {
+                const uint64_t o = b * mcs, l = std::min<uint64_t>(mcs, D - o);
+                wr_be32(body_w, (uint32_t)l); memcpy(body_w + 4, "FDAT", 4);
+                body_w += 12 + l;
+            }
+            w = body_w;
+            put_meta(k * metas_per_entry + metas_per_entry - 1);   // FEND
+            cpos += ncrc[k];
+        }
+        if (trace) fprintf(stderr, "[pna_host] create group %zu (%u files): plan_create/H2D %.1f-%.1f, lengths(wait) %.1f-%.1f, fetch/D2H %.1f-%.1f, frames -%.1f ms\n",
+                           g, m, S.t_issue0, S.t_issue1, tr2, tr3, tr4, tr5, ms_now());
+    };
+    auto work = [&]() {
+        Stage stage[2];
+        try {
+            CtxLease L0(device), L1(device);
+            CtxLease* L[2] = {&L0, &L1};
+            int cur = 0;
+            bool have_prev = false;
+            for (;;) {
+                const size_t g = next.fetch_add(1);
+                if (g >= groups.size()) break;
+                issue(*L[cur], stage[cur], g);
+                if (have_prev) finish(*L[cur ^ 1], stage[cur ^ 1]);
+                have_prev = true;
+                cur ^= 1;
+            }
+            if (have_prev) finish(*L[cur ^ 1], stage[cur ^ 1]);
         } catch (const Error& e) {
+            for (auto& S : stage) if (S.plan) { pna_cuda_plan_destroy(S.plan); S.plan = nullptr; }
             std::lock_guard<std::mutex> lk(mu);
             if (err_msg.empty()) { err_msg = e.what(); err_kind = e.kind; }
             failed = true;
@@ -750,13 +785,9 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
     const uint64_t end = base[groups.size()];
     if (end + 12 > cap) throw Error(PNA_E_NOSPACE, "archive buffer too small");
     {
-        CtxLease L(device);
-        const uint8_t ahed[12] = {'A', 'H', 'E', 'D', 0, 0, 0, 0, 0, 0, 0, 0}, aend[4] = {'A', 'E', 'N', 'D'};
-        pna_span sp[2] = {{ahed, 12}, {aend, 4}};
-        uint32_t c[2];
-        ck(L.ctx, pna_cuda_crc32(L.ctx, sp, 2, c), "archive crc");
-        wr_be32(out + 8, 8); memcpy(out + 12, ahed, 12); wr_be32(out + 24, c[0]);
-        wr_be32(out + end, 0); memcpy(out + end + 4, aend, 4); wr_be32(out + end + 8, c[1]);
+        const MetaRef& ra = refs[n * metas_per_entry], & re = refs[n * metas_per_entry + 1];
+        wr_be32(out + 8, 8); memcpy(out + 12, meta.data() + ra.off, 12); wr_be32(out + 24, mcrc[n * metas_per_entry]);
+        wr_be32(out + end, 0); memcpy(out + end + 4, meta.data() + re.off, 4); wr_be32(out + end + 8, mcrc[n * metas_per_entry + 1]);
     }
     return end + 12;
 }
