@@ -372,7 +372,8 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
                             uint64_t group_bytes, bool verify) {
     if (!prepared_) prepare(opt, device);
     const size_t n = refs_.size();
-    // groups of consecutive files of the same owner, cut when the compressed bytes reach group_bytes
+    // groups of consecutive files of the same owner, cut when the compressed bytes reach group_bytes.  The first groups
+    // ramp up (1/4, 1/2 of the size): the pipeline's first download starts that much earlier.
     struct Group { size_t lo, hi; };
     std::vector<Group> groups;
     {
@@ -380,7 +381,8 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
         uint64_t acc = 0;
         for (size_t i = 0; i < n; i++) {
             const EntryInfo& e = refs_[i].owner ? inner_[refs_[i].owner - 1].entries[refs_[i].entry] : entries_[refs_[i].entry];
-            const bool cut = i > lo && (refs_[i].owner != refs_[lo].owner || acc >= group_bytes);
+            const uint64_t limit = groups.size() == 0 ? group_bytes / 4 : groups.size() == 1 ? group_bytes / 2 : group_bytes;
+            const bool cut = i > lo && (refs_[i].owner != refs_[lo].owner || acc >= limit);
             if (cut) { groups.push_back({lo, i}); lo = i; acc = 0; }
             acc += e.compressed_size;
         }
