@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--entries", type=int, default=1024, help="4 MiB files per GPU (cfg2: 8192 over 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--workers", type=int, default=2, help="host worker threads / contexts of the end-to-end path")
+    ap.add_argument("--workers", type=int, default=3, help="host worker threads / contexts of the end-to-end path")
     ap.add_argument("--group-mib", type=int, default=128, help="compressed MiB per pipelined entry group (end-to-end path)")
     ap.add_argument("--create-workers", type=int, default=4)
     ap.add_argument("--create-group-mib", type=int, default=256)
