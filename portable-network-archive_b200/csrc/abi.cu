@@ -286,7 +286,7 @@ extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
     delete hc;
     // opt in to the large dynamic shared memory the table-driven kernels use
     const int aes_smem = 256 * 32 * 4 + 256, cam_smem = 2 * 2048 * 4;
-    ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_CTR_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
@@ -651,7 +651,7 @@ static int launch_cipher(pna_plan* P) {
 #define ARGS P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_tiles[v].p, nt, P->d_keys.p, ctx->d_aes, ctx->d_cam
         switch (v) {
             case 0: decrypt_tiles_kernel<0, 1><<<grid, 256, 0, ctx->stream>>>(ARGS); break;
-            case 1: decrypt_tiles_kernel<1, 1><<<grid, 256, aes_smem, ctx->stream>>>(ARGS); break;
+            case 1: decrypt_tiles_kernel<1, 1><<<std::min<uint32_t>(nt, (uint32_t)ctx->sm_count), AES_CTR_THREADS, AES_CTR_SMEM, ctx->stream>>>(ARGS); break;
             case 2: decrypt_tiles_kernel<1, 0><<<grid, 256, aes_smem, ctx->stream>>>(ARGS); break;
             case 3: decrypt_tiles_kernel<2, 1><<<grid, 256, cam_smem, ctx->stream>>>(ARGS); break;
             case 4: decrypt_tiles_kernel<2, 0><<<grid, 256, cam_smem, ctx->stream>>>(ARGS); break;

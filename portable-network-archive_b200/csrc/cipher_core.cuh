@@ -97,6 +97,28 @@ inline void aes256_expand_key(const AesTables* T, const uint8_t key[32], AesKey*
 }
 
 // s[4] in/out, rk = 60 words (any address space).  te = Te0 view, sb = (Te0>>8)&0xff gives S.
+// Same cipher with the four rotations of Te0 as four tables (Te_k[x] = rotl(Te0[x], 8k)): no rotate per lookup.  Used by the
+// CTR tile kernels, which are instruction-issue bound (16 lookups + 12 rotates + xors per round and column set).
+template <class Tab>
+PNA_HD void aes256_encrypt_block4(uint32_t s[4], const uint32_t* rk, const Tab& t0, const Tab& t1, const Tab& t2, const Tab& t3) {
+    uint32_t a = s[0] ^ rk[0], b = s[1] ^ rk[1], c = s[2] ^ rk[2], d = s[3] ^ rk[3];
+#pragma unroll
+    for (int r = 1; r < 14; r++) {
+        const uint32_t na = t0(a & 0xFF) ^ t1((b >> 8) & 0xFF) ^ t2((c >> 16) & 0xFF) ^ t3(d >> 24) ^ rk[4 * r + 0];
+        const uint32_t nb = t0(b & 0xFF) ^ t1((c >> 8) & 0xFF) ^ t2((d >> 16) & 0xFF) ^ t3(a >> 24) ^ rk[4 * r + 1];
+        const uint32_t nc = t0(c & 0xFF) ^ t1((d >> 8) & 0xFF) ^ t2((a >> 16) & 0xFF) ^ t3(b >> 24) ^ rk[4 * r + 2];
+        const uint32_t nd = t0(d & 0xFF) ^ t1((a >> 8) & 0xFF) ^ t2((b >> 16) & 0xFF) ^ t3(c >> 24) ^ rk[4 * r + 3];
+        a = na; b = nb; c = nc; d = nd;
+    }
+    // last round: S-box bytes.  Te0 = (2s, s, s, 3s): byte 1 of Te0[x] is s; in Te_k it sits at byte (1 + k) & 3
+#define PNA_SB0(x) ((t0(x) >> 8) & 0xFFu)
+    s[0] = (PNA_SB0(a & 0xFF) | (t1((b >> 8) & 0xFF) & 0xFF0000u) >> 8 | (t2((c >> 16) & 0xFF) & 0xFF000000u) >> 8 | (t3(d >> 24) & 0xFFu) << 24) ^ rk[56];
+    s[1] = (PNA_SB0(b & 0xFF) | (t1((c >> 8) & 0xFF) & 0xFF0000u) >> 8 | (t2((d >> 16) & 0xFF) & 0xFF000000u) >> 8 | (t3(a >> 24) & 0xFFu) << 24) ^ rk[57];
+    s[2] = (PNA_SB0(c & 0xFF) | (t1((d >> 8) & 0xFF) & 0xFF0000u) >> 8 | (t2((a >> 16) & 0xFF) & 0xFF000000u) >> 8 | (t3(b >> 24) & 0xFFu) << 24) ^ rk[58];
+    s[3] = (PNA_SB0(d & 0xFF) | (t1((a >> 8) & 0xFF) & 0xFF0000u) >> 8 | (t2((b >> 16) & 0xFF) & 0xFF000000u) >> 8 | (t3(c >> 24) & 0xFFu) << 24) ^ rk[59];
+#undef PNA_SB0
+}
+
 template <class Tab>
 PNA_HD void aes256_encrypt_block(uint32_t s[4], const uint32_t* rk, const Tab& te) {
     uint32_t a = s[0] ^ rk[0], b = s[1] ^ rk[1], c = s[2] ^ rk[2], d = s[3] ^ rk[3];

@@ -139,8 +139,12 @@ struct DevKeys {   // one per distinct (cipher, key)
 
 // dynamic shared memory layout: [AES table 256*32 u32 (replicated)] or [Camellia sp_hi|sp_lo 2*2048 u32],
 // then per-CTA key words.
+// AES-CTR (ENC 1, MODE 1) runs 1024 threads per CTA over FOUR replicated tables (128 KB of shared memory, one CTA per SM);
+// every other variant 256 threads over one table.
+constexpr int AES_CTR_THREADS = 1024;
+constexpr int AES_CTR_SMEM = 4 * 256 * 32 * 4 + 256;
 template <int ENC /*1 aes, 2 camellia, 0 none*/, int MODE /*0 cbc, 1 ctr*/>
-__global__ void __launch_bounds__(256) decrypt_tiles_kernel(uint8_t* __restrict__ buf, const Segment* __restrict__ segs,
+__global__ void __launch_bounds__(ENC == 1 && MODE == 1 ? AES_CTR_THREADS : 256) decrypt_tiles_kernel(uint8_t* __restrict__ buf, const Segment* __restrict__ segs,
                                                             EntryRec* __restrict__ entries,
                                                             const CipherTile* __restrict__ tiles, uint32_t n_tiles,
                                                             const DevKeys* __restrict__ keys,
@@ -149,8 +153,11 @@ __global__ void __launch_bounds__(256) decrypt_tiles_kernel(uint8_t* __restrict_
     extern __shared__ uint32_t smem[];
     uint32_t* s_tab = smem;
     uint8_t* s_isb = nullptr;
-    if (ENC == 1) {
-        const uint32_t* src = MODE == 1 ? aes->te0 : aes->td0;
+    if (ENC == 1 && MODE == 1) {
+        for (int i = threadIdx.x; i < 4 * 256 * 32; i += blockDim.x)                       // [k][x*32 + lane] = rotl(Te0[x], 8k)
+            s_tab[i] = rotl32(aes->te0[(i >> 5) & 255], 8 * (i >> 13));
+    } else if (ENC == 1) {
+        const uint32_t* src = aes->td0;
         for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_tab[i] = src[i >> 5];   // [x*32 + lane]
         s_isb = reinterpret_cast<uint8_t*>(smem + 256 * 32);
         if (MODE == 0) for (int i = threadIdx.x; i < 256; i += blockDim.x) s_isb[i] = aes->inv_sbox[i];
@@ -195,8 +202,10 @@ __global__ void __launch_bounds__(256) decrypt_tiles_kernel(uint8_t* __restrict_
             if (ENC == 0) { o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = c[3]; }
             else if (MODE == 1) {   // CTR: keystream = E(IV + bi)
                 ctr128be_add(iv, bi, o);
-                if (ENC == 1) aes256_encrypt_block(o, s_key32, tv);
-                else camellia256_crypt_block(o, s_key64, s_tab, s_tab + 2048);
+                if (ENC == 1) {
+                    const TabView t1{s_tab + 8192, 32, tv.lane}, t2{s_tab + 16384, 32, tv.lane}, t3{s_tab + 24576, 32, tv.lane};
+                    aes256_encrypt_block4(o, s_key32, tv, t1, t2, t3);
+                } else camellia256_crypt_block(o, s_key64, s_tab, s_tab + 2048);
                 o[0] ^= c[0]; o[1] ^= c[1]; o[2] ^= c[2]; o[3] ^= c[3];
             } else {                // CBC: P = D(C_i) ^ C_{i-1}
                 uint32_t prev[4];
