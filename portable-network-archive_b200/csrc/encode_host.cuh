@@ -31,7 +31,7 @@ void destroy(EncodePlan* p) { delete p; }
 bool init_attributes() {
     const int aes_smem = 256 * 32 * 4, cam_smem = 2 * 2048 * 4;
     return cudaFuncSetAttribute(lz_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_SMEM_BYTES) == cudaSuccess &&
-           cudaFuncSetAttribute(encrypt_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(encrypt_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_CTR_SMEM) == cudaSuccess &&
            cudaFuncSetAttribute(encrypt_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess &&
            cudaFuncSetAttribute(cbc_encrypt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess &&
            cudaFuncSetAttribute(cbc_encrypt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
@@ -248,7 +248,7 @@ static int encode_launch_all(pna_plan* P) {
         const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)ctx->sm_count * (v == 1 ? 4 : 6));
 #define ARGS E->d_work.p, E->d_pieces.p, E->d_entries.p, E->d_tiles[v].p, nt, E->d_keys.p, ctx->d_aes, ctx->d_cam, E->d_out.p
         if (v == 0) enc::encrypt_tiles_kernel<0><<<grid, 256, 0, ctx->stream>>>(ARGS);
-        else if (v == 1) enc::encrypt_tiles_kernel<1><<<grid, 256, aes_smem, ctx->stream>>>(ARGS);
+        else if (v == 1) enc::encrypt_tiles_kernel<1><<<std::min<uint32_t>(nt, (uint32_t)ctx->sm_count), AES_CTR_THREADS, AES_CTR_SMEM, ctx->stream>>>(ARGS);
         else enc::encrypt_tiles_kernel<2><<<grid, 256, cam_smem, ctx->stream>>>(ARGS);
 #undef ARGS
         LAUNCHED();

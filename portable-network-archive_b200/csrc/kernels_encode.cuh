@@ -298,14 +298,16 @@ __global__ void enc_layout_kernel(uint8_t* __restrict__ work, const SegRec* __re
 // CTR encrypt (or plain gather) of the piece list into the output: out = [IV |] E_K(IV + i) ^ stream.
 // Tiles are built on the host from the stream-length BOUND; blocks past the produced length do nothing.
 template <int ENC /*0 none, 1 aes, 2 camellia*/>
-__global__ void __launch_bounds__(256) encrypt_tiles_kernel(const uint8_t* __restrict__ work, const Segment* __restrict__ pieces,
+__global__ void __launch_bounds__(ENC == 1 ? AES_CTR_THREADS : 256) encrypt_tiles_kernel(const uint8_t* __restrict__ work, const Segment* __restrict__ pieces,
                                                             const EncEntry* __restrict__ entries,
                                                             const CipherTile* __restrict__ tiles, uint32_t n_tiles,
                                                             const DevKeys* __restrict__ keys, const AesTables* __restrict__ aes,
                                                             const CamelliaTables* __restrict__ cam, uint8_t* __restrict__ out) {
     extern __shared__ uint32_t smem[];
     uint32_t* s_tab = smem;
-    if (ENC == 1) { for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_tab[i] = aes->te0[i >> 5]; }
+    if (ENC == 1) {   // four replicated tables [k][x*32 + lane] = rotl(Te0[x], 8k), 1024 threads per CTA (see decrypt_tiles_kernel)
+        for (int i = threadIdx.x; i < 4 * 256 * 32; i += blockDim.x) s_tab[i] = rotl32(aes->te0[(i >> 5) & 255], 8 * (i >> 13));
+    }
     else if (ENC == 2) {
         for (int i = threadIdx.x; i < 2048; i += blockDim.x) { s_tab[i] = (&cam->sp_hi[0][0])[i]; s_tab[2048 + i] = (&cam->sp_lo[0][0])[i]; }
     }
@@ -345,7 +347,10 @@ __global__ void __launch_bounds__(256) encrypt_tiles_kernel(const uint8_t* __res
             uint32_t o[4] = {c[0], c[1], c[2], c[3]};
             if (ENC != 0) {
                 ctr128be_add(iv, bi, o);
-                if (ENC == 1) aes256_encrypt_block(o, s_key32, tv);
+                if (ENC == 1) {
+                    const TabView t1{s_tab + 8192, 32, tv.lane}, t2{s_tab + 16384, 32, tv.lane}, t3{s_tab + 24576, 32, tv.lane};
+                    aes256_encrypt_block4(o, s_key32, tv, t1, t2, t3);
+                }
                 else camellia256_crypt_block(o, s_key64, s_tab, s_tab + 2048);
                 o[0] ^= c[0]; o[1] ^= c[1]; o[2] ^= c[2]; o[3] ^= c[3];
             }
