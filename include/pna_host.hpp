@@ -81,6 +81,11 @@ struct FileOut {         // one FILE entry to extract: where it lives and where 
 
 class Archive {
 public:
+    Archive() = default;
+    Archive(Archive&&) = default;               // entries hold views into body_pool_: movable, not copyable
+    Archive& operator=(Archive&&) = default;
+    Archive(const Archive&) = delete;
+    Archive& operator=(const Archive&) = delete;
     static Archive read_header_from_slice(const uint8_t* buf, size_t len);
     const std::vector<RawChunk>& chunks() const { return chunks_; }
     const std::vector<EntryInfo>& entries() const { return entries_; }
