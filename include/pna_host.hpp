@@ -99,6 +99,11 @@ public:
     // verify: chunk CRCs of the whole archive are checked on the GPU, fused with the decode batches.
     void extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                        uint64_t group_bytes, bool verify);
+    // Same for the files [first, last) only (file i lands at out + offsets[i] - offsets[first]): windows of a large archive.
+    // With verify, windows must be taken in archive order (each call checks the chunks up to its last entry).
+    void extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
+                       uint64_t group_bytes, bool verify, size_t first, size_t last);
+    void restart_verify() { crc_next_chunk_ = 0; }
 
 private:
     struct FileRef { uint32_t owner; uint32_t entry; };   // owner: 0 = top-level archive, k+1 = inner archive of solid k
@@ -115,6 +120,7 @@ private:
     std::vector<FileRef> refs_;
     std::vector<FileOut> files_;
     bool prepared_ = false;
+    uint32_t crc_next_chunk_ = 0;              // top-level chunks already handed to a CRC check by extract_range
 };
 
 struct WriteOptions {    // options.rs:1035
@@ -135,6 +141,25 @@ std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, 
 uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
                              int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap);
 
+// ---- the file-system side of the path (SURVEY 8f "next", item 1): the CLI's extract / create data flow around the kernels
+struct IoStats {
+    uint64_t files = 0, dirs = 0, skipped = 0, bytes = 0;   // skipped: links and other non-file kinds, entries that failed
+    double index_ms = 0, gpu_ms = 0, io_ms = 0, total_ms = 0;
+};
+// lib/src/entry/name.rs:148 `sanitize`: only normal path components survive ("", ".", ".." and roots are dropped)
+std::string sanitize_entry_name(const std::string& name);
+// `pna extract` (cli/src/command/extract.rs:868-1019 run_extract_archive over an mmap, :1301-1366 extract_file_entry): index
+// the archive (caller: read_header_from_slice over the mapping), decode on the GPU in windows of at most window_bytes of
+// output (pinned, double-buffered) and write the files with io_threads writers while the next window decodes.
+// status (optional) receives one code per files() entry.
+IoStats extract_to_dir(Archive& a, const ReadOptions& opt, const std::string& out_dir, int device, int workers, uint64_t group_bytes,
+                       uint64_t window_bytes, int io_threads, bool verify, int32_t* status);
+// `pna create` (cli/src/command/core.rs:889-913 write_from_path, create.rs:575 create_archive_file): read the files with
+// io_threads readers into pinned memory, one GPU encode pass, write the archive file.
+IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>& name_and_path, const WriteOptions& opt,
+                          uint32_t max_chunk_size, const std::string& archive_path, int device, int workers, uint64_t group_bytes,
+                          int io_threads);
+
 }  // namespace pna
 extern "C" {
 #endif
@@ -148,7 +173,16 @@ typedef struct {
     const char* name;
     const char* phsf; /* NULL when absent */
 } pnah_entry_info;
+typedef struct { uint64_t files, dirs, skipped, bytes; double index_ms, gpu_ms, io_ms, total_ms; } pnah_io_stats;
 int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, uint64_t errcap);
+int pnah_open_file(const char* path, pnah_archive** out, char* err, uint64_t errcap);   /* mmap; the handle owns the mapping */
+int pnah_extract_to_dir(pnah_archive* a, const char* out_dir, int device, int workers, uint64_t group_bytes, uint64_t window_bytes,
+                        int io_threads, int verify, pnah_io_stats* stats, int32_t* status /* per file, may be NULL */, char* err,
+                        uint64_t errcap);
+int pnah_create_from_files(uint32_t n, const char* const* names, const char* const* paths, uint8_t compression, int32_t level,
+                           uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf, uint32_t max_chunk_size,
+                           const char* archive_path, int device, int workers, uint64_t group_bytes, int io_threads,
+                           pnah_io_stats* stats, char* err, uint64_t errcap);
 void pnah_close(pnah_archive* a);
 uint32_t pnah_entry_count(pnah_archive* a);
 int pnah_entry_get(pnah_archive* a, uint32_t i, pnah_entry_info* info);

@@ -12,13 +12,22 @@ from . import _ffi
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpna_host.so")
 EXPORTS = ["pnah_open", "pnah_close", "pnah_entry_count", "pnah_entry_get", "pnah_chunk_count", "pnah_set_key", "pnah_prepare",
-           "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound"]
+           "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound",
+           "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files"]
 
 
 class EntryInfo(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("data_kind", C.c_uint8), ("compression", C.c_uint8), ("encryption", C.c_uint8),
                 ("cipher_mode", C.c_uint8), ("n_bodies", C.c_uint32), ("compressed_size", C.c_uint64),
                 ("raw_file_size", C.c_uint64), ("name", C.c_char_p), ("phsf", C.c_char_p)]
+
+
+class IoStats(C.Structure):
+    _fields_ = [("files", C.c_uint64), ("dirs", C.c_uint64), ("skipped", C.c_uint64), ("bytes", C.c_uint64),
+                ("index_ms", C.c_double), ("gpu_ms", C.c_double), ("io_ms", C.c_double), ("total_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 _lib = None
@@ -50,6 +59,12 @@ def lib():
                                   C.c_char_p, u64]
         L.pnah_create_bound.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(u64), C.c_uint8, C.c_uint8, C.c_char_p, u32]
         L.pnah_create_bound.restype = u64
+        L.pnah_open_file.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, u64]
+        L.pnah_extract_to_dir.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, u64, u64, C.c_int, C.c_int, C.POINTER(IoStats),
+                                          C.POINTER(C.c_int32), C.c_char_p, u64]
+        L.pnah_create_from_files.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_uint8, C.c_int32, C.c_uint8, C.c_uint8,
+                                             C.c_char_p, C.c_char_p, u32, C.c_char_p, C.c_int, C.c_int, u64, C.c_int, C.POINTER(IoStats),
+                                             C.c_char_p, u64]
         _lib = L
     return _lib
 
@@ -72,6 +87,33 @@ class HostArchive:
         if rc:
             raise HostError(rc, err.value.decode())
         self.h = h
+
+    @classmethod
+    def open_file(cls, path: str):
+        """Archive over an mmap of `path` (cli/src/utils/mmap.rs:36-45); the handle owns the mapping."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.buf = None
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = self.L.pnah_open_file(os.fsencode(path), C.byref(h), err, 512)
+        if rc:
+            raise HostError(rc, err.value.decode())
+        self.h = h
+        return self
+
+    def extract_to_dir(self, out_dir: str, device=0, workers=3, group_bytes=128 << 20, window_bytes=2 << 30, io_threads=8, verify=True):
+        """`pna extract` data path: GPU decode in pinned windows, files written by io_threads writers.  Returns (stats, statuses)."""
+        self.prepare(device)
+        nf = int(self.L.pnah_file_count(self.h))
+        st = (C.c_int32 * max(nf, 1))()
+        stats = IoStats()
+        err = C.create_string_buffer(512)
+        rc = self.L.pnah_extract_to_dir(self.h, os.fsencode(out_dir), device, workers, group_bytes, window_bytes, io_threads, int(verify),
+                                        C.byref(stats), st, err, 512)
+        if rc:
+            raise HostError(rc, err.value.decode())
+        return stats.as_dict(), list(st)[:nf]
 
     def close(self):
         if getattr(self, "h", None):
@@ -173,3 +215,21 @@ def create_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, 
     if rc:
         raise HostError(rc, err.value.decode())
     return out[:olen.value]
+
+
+def create_from_files(names_and_paths, archive_path, compression=0, level=-1, encryption=0, cipher_mode=1, key=None, phsf=None,
+                      max_chunk_size=0, device=0, workers=4, group_bytes=256 << 20, io_threads=8):
+    """`pna create` data path: files read into pinned memory by io_threads readers, one GPU encode pass, archive written to
+    `archive_path`.  names_and_paths: list of (entry name, file path).  Returns the stats dict."""
+    L = lib()
+    n = len(names_and_paths)
+    names = (C.c_char_p * max(n, 1))(*[a.encode() for a, _ in names_and_paths])
+    paths = (C.c_char_p * max(n, 1))(*[os.fsencode(b) for _, b in names_and_paths])
+    stats = IoStats()
+    err = C.create_string_buffer(512)
+    rc = L.pnah_create_from_files(n, names, paths, compression, level, encryption, cipher_mode, key or bytes(32), (phsf or "").encode(),
+                                  max_chunk_size, os.fsencode(archive_path), device, workers, group_bytes, io_threads, C.byref(stats),
+                                  err, 512)
+    if rc:
+        raise HostError(rc, err.value.decode())
+    return stats.as_dict()

@@ -3,6 +3,11 @@
 // Entry bytes are never touched by the CPU here; see the header for the reference file:line each piece follows.
 #include "../../include/pna_host.hpp"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -10,7 +15,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <mutex>
+#include <random>
+#include <set>
 #include <thread>
 
 namespace pna {
@@ -371,15 +379,25 @@ void Archive::prepare(const ReadOptions& opt, int device) {
 void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                             uint64_t group_bytes, bool verify) {
     if (!prepared_) prepare(opt, device);
-    const size_t n = refs_.size();
+    crc_next_chunk_ = 0;
+    extract_range(opt, out, offsets, status, device, workers, group_bytes, verify, 0, refs_.size());
+}
+
+// Files [first, last) of files(): file i lands at out + (offsets[i] - offsets[first]).  Windows must be taken in order
+// when verify is set: every call checks the chunks between the previous window's last entry and its own.
+void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
+                            uint64_t group_bytes, bool verify, size_t first, size_t last) {
+    if (!prepared_) prepare(opt, device);
+    const size_t n = last;
+    const uint64_t o0 = first < refs_.size() ? offsets[first] : 0;
     // groups of consecutive files of the same owner, cut when the compressed bytes reach group_bytes.  The first groups
     // ramp up (1/4, 1/2 of the size): the pipeline's first download starts that much earlier.
     struct Group { size_t lo, hi; };
     std::vector<Group> groups;
     {
-        size_t lo = 0;
+        size_t lo = first;
         uint64_t acc = 0;
-        for (size_t i = 0; i < n; i++) {
+        for (size_t i = first; i < n; i++) {
             const EntryInfo& e = refs_[i].owner ? inner_[refs_[i].owner - 1].entries[refs_[i].entry] : entries_[refs_[i].entry];
             const uint64_t limit = groups.size() == 0 ? group_bytes / 4 : groups.size() == 1 ? group_bytes / 2 : group_bytes;
             const bool cut = i > lo && (refs_[i].owner != refs_[lo].owner || acc >= limit);
@@ -391,16 +409,19 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
     // chunk ranges of the top-level archive covered by each top-level group (contiguous, together all chunks)
     std::vector<std::pair<uint32_t, uint32_t>> crange(groups.size(), {0, 0});
     if (verify) {
-        int first_top = -1, last_top = -1;
-        for (size_t g = 0; g < groups.size(); g++) if (refs_[groups[g].lo].owner == 0) { if (first_top < 0) first_top = (int)g; last_top = (int)g; }
-        uint32_t prev_end = 0;
+        int64_t last_top_ref = -1;                 // the archive's last top-level FILE: its group also covers the trailing chunks
+        for (size_t i = refs_.size(); i-- > 0;) if (refs_[i].owner == 0) { last_top_ref = (int64_t)i; break; }
+        uint32_t prev_end = crc_next_chunk_;
         for (size_t g = 0; g < groups.size(); g++) {
             if (refs_[groups[g].lo].owner != 0) continue;
-            const uint32_t end = (int)g == last_top ? (uint32_t)chunks_.size() : entries_[refs_[groups[g].hi - 1].entry].chunk_end;
-            crange[g] = {(int)g == first_top ? 0u : prev_end, end};
+            const bool closes = (int64_t)groups[g].lo <= last_top_ref && last_top_ref < (int64_t)groups[g].hi;
+            const uint32_t end = closes ? (uint32_t)chunks_.size() : entries_[refs_[groups[g].hi - 1].entry].chunk_end;
+            crange[g] = {prev_end, end};
             prev_end = end;
         }
-        if (first_top < 0 && !chunks_.empty()) {   // no top-level FILE entry at all: verify the archive's chunks in one call
+        crc_next_chunk_ = prev_end;
+        if (last_top_ref < 0 && crc_next_chunk_ == 0 && !chunks_.empty()) {   // no top-level FILE entry at all: verify the archive's chunks in one call
+            crc_next_chunk_ = (uint32_t)chunks_.size();
             CtxLease L(device);
             std::vector<uint64_t> off(chunks_.size()), len(chunks_.size());
             std::vector<uint32_t> crc(chunks_.size());
@@ -452,7 +473,7 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
             uint64_t at = 0;
             if (e.compressed_size > cap) { status[i] = PNA_E_NOSPACE; continue; }
             for (const pna_span& b : e.bodies) {
-                src.push_back((uint64_t)(b.ptr - in.bytes.data())); len.push_back(b.len); dst.push_back(out + offsets[i] + at);
+                src.push_back((uint64_t)(b.ptr - in.bytes.data())); len.push_back(b.len); dst.push_back(out + (offsets[i] - o0) + at);
                 at += b.len;
             }
             status[i] = PNA_OK;
@@ -472,7 +493,7 @@ void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t
             S.pre[k] = files_[G.lo + k].status ? files_[G.lo + k].status : fill_desc(e, opt, S.descs[k]);
             if (S.pre[k] != PNA_OK) { memset(&S.descs[k], 0, sizeof S.descs[k]); S.descs[k].raw_size_hint = 0; }
             else S.descs[k].raw_size_hint = files_[G.lo + k].size;
-            S.bufs[k] = pna_buf{out + offsets[G.lo + k], offsets[G.lo + k + 1] - offsets[G.lo + k], 0};
+            S.bufs[k] = pna_buf{out + (offsets[G.lo + k] - o0), offsets[G.lo + k + 1] - offsets[G.lo + k], 0};
         }
         S.top = refs_[G.lo].owner == 0;
         const auto t0 = std::chrono::steady_clock::now();
@@ -808,12 +829,212 @@ std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, 
     return out;
 }
 
+// ---------------------------------------------------------------------------------------------- file-system side
+std::string sanitize_entry_name(const std::string& name) {
+    std::string out;
+    size_t i = 0;
+    while (i <= name.size()) {
+        size_t j = name.find('/', i);
+        if (j == std::string::npos) j = name.size();
+        const std::string c = name.substr(i, j - i);
+        if (!c.empty() && c != "." && c != "..") { if (!out.empty()) out += '/'; out += c; }
+        i = j + 1;
+    }
+    return out;
+}
+static void mkdirs(const std::string& path) {   // mkdir -p
+    for (size_t i = 1; i <= path.size(); i++)
+        if (i == path.size() || path[i] == '/') {
+            const std::string d = path.substr(0, i);
+            if (mkdir(d.c_str(), 0755) != 0 && errno != EEXIST) throw Error(PNA_E_INTERNAL, "mkdir " + d + ": " + strerror(errno));
+        }
+}
+struct DirCache {   // directories already made (many files share few parents)
+    std::mutex mu;
+    std::set<std::string> made;
+    void ensure_parent(const std::string& file) {
+        const size_t k = file.rfind('/');
+        if (k == std::string::npos || k == 0) return;
+        const std::string d = file.substr(0, k);
+        { std::lock_guard<std::mutex> g(mu); if (made.count(d)) return; }
+        mkdirs(d);
+        std::lock_guard<std::mutex> g(mu);
+        made.insert(d);
+    }
+};
+static void write_whole(const std::string& path, const uint8_t* p, uint64_t n) {
+    const int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) throw Error(PNA_E_INTERNAL, "open " + path + ": " + strerror(errno));
+    uint64_t done = 0;
+    while (done < n) {
+        const ssize_t w = write(fd, p + done, (size_t)std::min<uint64_t>(n - done, (uint64_t)1 << 30));
+        if (w < 0) { if (errno == EINTR) continue; const std::string m = strerror(errno); close(fd); throw Error(PNA_E_INTERNAL, "write " + path + ": " + m); }
+        done += (uint64_t)w;
+    }
+    close(fd);
+}
+template <class F>
+static void parallel_for(size_t n, int threads, F&& f) {   // f(i), first exception rethrown
+    std::atomic<size_t> next{0};
+    std::mutex mu;
+    std::string msg;
+    int kind = 0;
+    auto work = [&]() {
+        try { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; f(i); } }
+        catch (const Error& e) { std::lock_guard<std::mutex> g(mu); if (msg.empty()) { msg = e.what(); kind = e.kind ? e.kind : PNA_E_INTERNAL; } next.store(n); }
+    };
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(threads, 1), n));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (kind) throw Error(kind, msg);
+}
+static double ms_between(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+}
+
+IoStats extract_to_dir(Archive& a, const ReadOptions& opt, const std::string& out_dir, int device, int workers, uint64_t group_bytes,
+                       uint64_t window_bytes, int io_threads, bool verify, int32_t* status) {
+    IoStats st;
+    const auto t_begin = std::chrono::steady_clock::now();
+    a.prepare(opt, device);
+    st.index_ms = ms_between(t_begin, std::chrono::steady_clock::now());   // solid streams are decoded here too
+    mkdirs(out_dir);
+    DirCache dirs;
+    for (const EntryInfo& e : a.entries()) {
+        if (e.kind != 0) continue;
+        if (e.data_kind == (uint8_t)DataKind::Directory) {
+            const std::string rel = sanitize_entry_name(e.name);
+            if (!rel.empty()) { mkdirs(out_dir + "/" + rel); st.dirs++; }
+        } else if (e.data_kind != (uint8_t)DataKind::File) st.skipped++;   // links: metadata work, not on the data path
+    }
+    const std::vector<FileOut>& files = a.files();
+    const size_t n = files.size();
+    std::vector<uint64_t> offsets(n + 1, 0);
+    for (size_t i = 0; i < n; i++) offsets[i + 1] = offsets[i] + ((files[i].status ? 0 : files[i].size) + 15) / 16 * 16;
+    std::vector<int32_t> stv(n, 0);
+    // windows of whole files
+    std::vector<std::pair<size_t, size_t>> windows;
+    uint64_t biggest = 0;
+    for (size_t lo = 0; lo < n;) {
+        size_t hi = lo + 1;
+        while (hi < n && offsets[hi + 1] - offsets[lo] <= window_bytes) hi++;
+        windows.push_back({lo, hi});
+        biggest = std::max(biggest, offsets[hi] - offsets[lo]);
+        lo = hi;
+    }
+    CtxLease L(device);
+    uint8_t* pinned[2] = {nullptr, nullptr};
+    std::mutex io_mu;
+    std::future<void> writing[2];
+    struct Free { pna_ctx* c; uint8_t** p; ~Free() { for (int k = 0; k < 2; k++) if (p[k]) pna_cuda_host_free(c, p[k]); } } free_guard{L.ctx, pinned};
+    for (int k = 0; k < 2 && (size_t)k < windows.size(); k++) {
+        pinned[k] = (uint8_t*)pna_cuda_host_alloc(L.ctx, biggest + 64);
+        if (!pinned[k]) throw Error(PNA_E_OOM, "pinned window buffer");
+    }
+    a.restart_verify();
+    for (size_t w = 0; w < windows.size(); w++) {
+        const int b = (int)(w & 1);
+        if (writing[b].valid()) writing[b].get();   // this buffer's previous window is on disk
+        const size_t lo = windows[w].first, hi = windows[w].second;
+        const auto t0 = std::chrono::steady_clock::now();
+        a.extract_range(opt, pinned[b], offsets.data(), stv.data(), device, workers, group_bytes, verify, lo, hi);
+        st.gpu_ms += ms_between(t0, std::chrono::steady_clock::now());
+        uint8_t* base = pinned[b];
+        writing[b] = std::async(std::launch::async, [&, lo, hi, base]() {
+            const auto t1 = std::chrono::steady_clock::now();
+            parallel_for(hi - lo, io_threads, [&](size_t k) {
+                const size_t i = lo + k;
+                if (stv[i] != PNA_OK || files[i].status) return;
+                const std::string rel = sanitize_entry_name(files[i].name);
+                if (rel.empty()) return;
+                const std::string path = out_dir + "/" + rel;
+                dirs.ensure_parent(path);
+                write_whole(path, base + (offsets[i] - offsets[lo]), files[i].size);
+            });
+            const double dt = ms_between(t1, std::chrono::steady_clock::now());
+            std::lock_guard<std::mutex> g(io_mu);
+            st.io_ms += dt;                                           // write time of the windows (overlaps the next window's gpu_ms)
+        });
+    }
+    for (auto& f : writing) if (f.valid()) f.get();
+    for (size_t i = 0; i < n; i++) {
+        const int32_t s = files[i].status ? files[i].status : stv[i];
+        if (status) status[i] = s;
+        if (s == PNA_OK) { st.files++; st.bytes += files[i].size; } else st.skipped++;
+    }
+    st.total_ms = ms_between(t_begin, std::chrono::steady_clock::now());
+    return st;
+}
+
+IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>& name_and_path, const WriteOptions& opt,
+                          uint32_t max_chunk_size, const std::string& archive_path, int device, int workers, uint64_t group_bytes,
+                          int io_threads) {
+    IoStats st;
+    const auto t_begin = std::chrono::steady_clock::now();
+    const size_t n = name_and_path.size();
+    std::vector<uint64_t> sizes(n), offs(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+        struct stat sb;
+        if (stat(name_and_path[i].second.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) throw Error(PNA_E_INVALID_INPUT, "not a regular file: " + name_and_path[i].second);
+        sizes[i] = (uint64_t)sb.st_size;
+        offs[i + 1] = offs[i] + (sizes[i] + 15) / 16 * 16;
+    }
+    CtxLease L(device);
+    uint8_t* plain = (uint8_t*)pna_cuda_host_alloc(L.ctx, offs[n] + 64);
+    if (!plain) throw Error(PNA_E_OOM, "pinned plaintext buffer");
+    uint8_t* arch = nullptr;
+    struct Free { pna_ctx* c; uint8_t*& a; uint8_t*& b; ~Free() { if (a) pna_cuda_host_free(c, a); if (b) pna_cuda_host_free(c, b); } } free_guard{L.ctx, plain, arch};
+    // core.rs:889-913: small files are read whole; here every file is, by io_threads readers, into pinned memory
+    parallel_for(n, io_threads, [&](size_t i) {
+        const int fd = open(name_and_path[i].second.c_str(), O_RDONLY);
+        if (fd < 0) throw Error(PNA_E_INTERNAL, "open " + name_and_path[i].second + ": " + strerror(errno));
+        uint64_t done = 0;
+        while (done < sizes[i]) {
+            const ssize_t r = read(fd, plain + offs[i] + done, (size_t)std::min<uint64_t>(sizes[i] - done, (uint64_t)1 << 30));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) { close(fd); throw Error(PNA_E_UNEXPECTED_EOF, "short read: " + name_and_path[i].second); }
+            done += (uint64_t)r;
+        }
+        close(fd);
+    });
+    const auto t_read = std::chrono::steady_clock::now();
+    st.io_ms = ms_between(t_begin, t_read);
+    std::vector<FileEntryBuilder> files(n);
+    std::random_device rd;
+    uint64_t bound = 8 + 20 + 12;
+    for (size_t i = 0; i < n; i++) {
+        files[i].name = name_and_path[i].first;
+        files[i].data = pna_span{plain + offs[i], sizes[i]};
+        for (int k = 0; k < 16; k += 4) { const uint32_t r = rd(); memcpy(files[i].iv + k, &r, 4); }   // entry/write.rs:108-111: random IV per entry
+        pna_encode_desc d;
+        memset(&d, 0, sizeof d);
+        d.plain.len = sizes[i]; d.compression = opt.compression; d.encryption = opt.encryption;
+        bound += entry_frame_bound(files[i].name, pna_cuda_encode_bound(&d), opt.phsf, opt.encryption != 0, max_chunk_size);
+        st.bytes += sizes[i];
+    }
+    arch = (uint8_t*)pna_cuda_host_alloc(L.ctx, bound + 64);
+    if (!arch) throw Error(PNA_E_OOM, "pinned archive buffer");
+    const uint64_t alen = create_archive_into(files, opt, max_chunk_size, device, workers, group_bytes, arch, bound);
+    const auto t_gpu = std::chrono::steady_clock::now();
+    st.gpu_ms = ms_between(t_read, t_gpu);
+    write_whole(archive_path, arch, alen);
+    st.io_ms += ms_between(t_gpu, std::chrono::steady_clock::now());
+    st.files = n;
+    st.total_ms = ms_between(t_begin, std::chrono::steady_clock::now());
+    return st;
+}
+
 }  // namespace pna
 
 // ---------------------------------------------------------------------------------------------- flat C view
 struct pnah_archive {
     pna::Archive a;
     pna::ReadOptions opt;
+    void* map = nullptr;     // mmap of the archive file when opened by path
+    size_t map_len = 0;
+    ~pnah_archive() { if (map) munmap(map, map_len); }
 };
 static int fail(const pna::Error& e, char* err, uint64_t cap) {
     if (err && cap) { strncpy(err, e.what(), cap - 1); err[cap - 1] = 0; }
@@ -828,6 +1049,51 @@ int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, u
     } catch (const pna::Error& e) { *out = nullptr; return fail(e, err, errcap); }
 }
 void pnah_close(pnah_archive* a) { delete a; }
+int pnah_open_file(const char* path, pnah_archive** out, char* err, uint64_t errcap) {
+    *out = nullptr;
+    try {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) throw pna::Error(PNA_E_INTERNAL, std::string("open ") + path + ": " + strerror(errno));
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) { close(fd); throw pna::Error(PNA_E_INTERNAL, "fstat failed"); }
+        void* m = sb.st_size ? mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;   // utils/mmap.rs:36-45
+        close(fd);
+        if (sb.st_size && m == MAP_FAILED) throw pna::Error(PNA_E_OOM, "mmap failed");
+        pnah_archive* h = nullptr;
+        try { h = new pnah_archive{pna::Archive::read_header_from_slice((const uint8_t*)m, (size_t)sb.st_size), {}}; }
+        catch (...) { if (m) munmap(m, (size_t)sb.st_size); throw; }
+        h->map = m; h->map_len = (size_t)sb.st_size;
+        *out = h;
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
+static void put_stats(const pna::IoStats& s, pnah_io_stats* o) {
+    if (!o) return;
+    o->files = s.files; o->dirs = s.dirs; o->skipped = s.skipped; o->bytes = s.bytes;
+    o->index_ms = s.index_ms; o->gpu_ms = s.gpu_ms; o->io_ms = s.io_ms; o->total_ms = s.total_ms;
+}
+int pnah_extract_to_dir(pnah_archive* a, const char* out_dir, int device, int workers, uint64_t group_bytes, uint64_t window_bytes,
+                        int io_threads, int verify, pnah_io_stats* stats, int32_t* status, char* err, uint64_t errcap) {
+    try {
+        put_stats(pna::extract_to_dir(a->a, a->opt, out_dir, device, workers, group_bytes, window_bytes, io_threads, verify != 0, status), stats);
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
+int pnah_create_from_files(uint32_t n, const char* const* names, const char* const* paths, uint8_t compression, int32_t level,
+                           uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf, uint32_t max_chunk_size,
+                           const char* archive_path, int device, int workers, uint64_t group_bytes, int io_threads,
+                           pnah_io_stats* stats, char* err, uint64_t errcap) {
+    try {
+        std::vector<std::pair<std::string, std::string>> np(n);
+        for (uint32_t i = 0; i < n; i++) np[i] = {names[i], paths[i]};
+        pna::WriteOptions opt;
+        opt.compression = compression; opt.level = level; opt.encryption = encryption; opt.cipher_mode = cipher_mode;
+        if (key) memcpy(opt.key, key, 32);
+        if (phsf) opt.phsf = phsf;
+        put_stats(pna::create_from_files(np, opt, max_chunk_size, archive_path, device, workers, group_bytes, io_threads), stats);
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
 uint32_t pnah_entry_count(pnah_archive* a) { return (uint32_t)a->a.entries().size(); }
 uint32_t pnah_chunk_count(pnah_archive* a) { return (uint32_t)a->a.chunks().size(); }
 int pnah_entry_get(pnah_archive* a, uint32_t i, pnah_entry_info* info) {

@@ -181,3 +181,54 @@ def test_create_with_cpp_host_is_reference_readable(host, pna, ctx, oracle, comp
         a.set_key(opts.phsf, opts.key)
     back = a.read_all(workers=2, group_bytes=300_000)
     assert [(n, d) for n, _, d in back] == files and all(s == 0 for _, s, _ in back)
+
+
+@pytest.mark.gpu
+def test_extract_to_dir_and_create_from_files(host, pna, ctx, oracle, golden, tmp_path):
+    """The file-system side of the path (cli/src/command/extract.rs:868-1019, core.rs:889-913): golden archives extracted to
+    a directory through an mmap equal the reference's raw files; a directory packed by create_from_files is read back by the
+    oracle's restatement of the reference reader and by extract_to_dir again (cli/tests/cli/encrypt.rs round trip shape).
+    Small windows force several decode / write rounds."""
+    for name in ("zstd.pna", "deflate.pna", "zstd_aes_ctr.pna", "solid_zstd.pna", "zstd_keep_all.pna"):
+        info = golden["archives"][name]
+        a = host.HostArchive.open_file(os.path.join(golden["dir"], info["file"]))
+        for phsf, key in info["keys"].items():
+            a.set_key(phsf, bytes.fromhex(key))
+        out = tmp_path / name
+        stats, st = a.extract_to_dir(str(out), window_bytes=1 << 20, io_threads=4)
+        a.close()
+        files = [e for e in info["entries"]]
+        assert st == [0] * len(files) and stats["files"] == len(files), name
+        for e in files:
+            p = out / host_sanitize(e["name"])
+            d = p.read_bytes()
+            assert len(d) == e["size"] and hashlib.sha256(d).hexdigest() == e["sha256"], (name, e["name"])
+    # create from a directory tree, encrypted, then read it back both ways
+    src = tmp_path / "src"
+    want = {}
+    for i, n in enumerate([0, 1, 5000, 70_000, 300_000, 1_200_000] * 3):
+        rel = f"tree/d{i % 3}/f{i:02d}.bin"
+        (src / rel).parent.mkdir(parents=True, exist_ok=True)
+        (src / rel).write_bytes(corpus.make_file(900 + i, n))
+        want[rel] = corpus.make_file(900 + i, n)
+    opts = pna.WriteOptions(compression=2, encryption=1, cipher_mode=1, password=b"pw", kdf_params={"i": 1000})
+    arch = tmp_path / "made.pna"
+    stats = host.create_from_files([(rel, str(src / rel)) for rel in want], str(arch), compression=2, level=3, encryption=1, cipher_mode=1,
+                                   key=opts.key, phsf=opts.phsf, group_bytes=1 << 20, io_threads=4)
+    assert stats["files"] == len(want) and stats["bytes"] == sum(len(v) for v in want.values())
+    got = dict(oracle.extract_all(arch.read_bytes(), b"pw", _keys={opts.phsf: opts.key}))
+    assert got == want
+    b = host.HostArchive.open_file(str(arch))
+    b.set_key(opts.phsf, opts.key)
+    out2 = tmp_path / "back"
+    stats2, st2 = b.extract_to_dir(str(out2), window_bytes=1 << 20)
+    b.close()
+    assert st2 == [0] * len(want)
+    for rel, data in want.items():
+        assert (out2 / rel).read_bytes() == data
+    # entry names are sanitised like lib/src/entry/name.rs:148 (only normal components survive)
+    assert host_sanitize("../../etc//./passwd") == "etc/passwd" and host_sanitize("/abs/x") == "abs/x"
+
+
+def host_sanitize(name):
+    return "/".join(c for c in name.split("/") if c not in ("", ".", ".."))
