@@ -830,6 +830,41 @@ std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, 
 }
 
 // ---------------------------------------------------------------------------------------------- file-system side
+// Pinned host buffers are expensive to make (cudaHostAlloc pins at a few GB/s): the windows and staging buffers of the
+// file paths are kept for the life of the process and handed out again (best fit, at most 1.5x oversize).
+struct PinnedPool {
+    struct Blk { uint8_t* p; uint64_t bytes; };
+    std::mutex mu;
+    std::vector<Blk> free_list;
+    uint8_t* get(pna_ctx* ctx, uint64_t bytes, uint64_t* got) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_list.size(); i++)
+                if (free_list[i].bytes >= bytes && free_list[i].bytes <= bytes + bytes / 2 + ((uint64_t)64 << 20) &&
+                    (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+            if (best >= 0) { Blk b = free_list[best]; free_list.erase(free_list.begin() + best); *got = b.bytes; return b.p; }
+        }
+        *got = bytes;
+        return (uint8_t*)pna_cuda_host_alloc(ctx, bytes);
+    }
+    void put(pna_ctx* ctx, uint8_t* p, uint64_t bytes) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (free_list.size() >= 6) { pna_cuda_host_free(ctx, free_list.front().p); free_list.erase(free_list.begin()); }
+        free_list.push_back({p, bytes});
+    }
+};
+static PinnedPool g_pinned;
+struct PinnedBuf {   // RAII lease
+    pna_ctx* ctx;
+    uint8_t* p = nullptr;
+    uint64_t bytes = 0;
+    PinnedBuf(pna_ctx* c, uint64_t n) : ctx(c) { p = g_pinned.get(c, n, &bytes); }
+    ~PinnedBuf() { g_pinned.put(ctx, p, bytes); }
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+};
 std::string sanitize_entry_name(const std::string& name) {
     std::string out;
     size_t i = 0;
@@ -925,14 +960,11 @@ IoStats extract_to_dir(Archive& a, const ReadOptions& opt, const std::string& ou
         lo = hi;
     }
     CtxLease L(device);
-    uint8_t* pinned[2] = {nullptr, nullptr};
+    PinnedBuf win0(L.ctx, biggest + 64), win1(L.ctx, windows.size() > 1 ? biggest + 64 : 64);
+    if (!win0.p || !win1.p) throw Error(PNA_E_OOM, "pinned window buffer");
+    uint8_t* pinned[2] = {win0.p, win1.p};
     std::mutex io_mu;
     std::future<void> writing[2];
-    struct Free { pna_ctx* c; uint8_t** p; ~Free() { for (int k = 0; k < 2; k++) if (p[k]) pna_cuda_host_free(c, p[k]); } } free_guard{L.ctx, pinned};
-    for (int k = 0; k < 2 && (size_t)k < windows.size(); k++) {
-        pinned[k] = (uint8_t*)pna_cuda_host_alloc(L.ctx, biggest + 64);
-        if (!pinned[k]) throw Error(PNA_E_OOM, "pinned window buffer");
-    }
     a.restart_verify();
     for (size_t w = 0; w < windows.size(); w++) {
         const int b = (int)(w & 1);
@@ -982,10 +1014,10 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
         offs[i + 1] = offs[i] + (sizes[i] + 15) / 16 * 16;
     }
     CtxLease L(device);
-    uint8_t* plain = (uint8_t*)pna_cuda_host_alloc(L.ctx, offs[n] + 64);
+    PinnedBuf plain_buf(L.ctx, offs[n] + 64);
+    uint8_t* const plain = plain_buf.p;
     if (!plain) throw Error(PNA_E_OOM, "pinned plaintext buffer");
-    uint8_t* arch = nullptr;
-    struct Free { pna_ctx* c; uint8_t*& a; uint8_t*& b; ~Free() { if (a) pna_cuda_host_free(c, a); if (b) pna_cuda_host_free(c, b); } } free_guard{L.ctx, plain, arch};
+    const auto t_lease = std::chrono::steady_clock::now();
     // core.rs:889-913: small files are read whole; here every file is, by io_threads readers, into pinned memory
     parallel_for(n, io_threads, [&](size_t i) {
         const int fd = open(name_and_path[i].second.c_str(), O_RDONLY);
@@ -1001,6 +1033,7 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
     });
     const auto t_read = std::chrono::steady_clock::now();
     st.io_ms = ms_between(t_begin, t_read);
+    if (getenv("PNA_HOST_TRACE")) fprintf(stderr, "[pna_host] create_from_files: stat+pinned lease %.1f ms, read %.1f ms\n", ms_between(t_begin, t_lease), ms_between(t_lease, t_read));
     std::vector<FileEntryBuilder> files(n);
     std::random_device rd;
     uint64_t bound = 8 + 20 + 12;
@@ -1014,12 +1047,29 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
         bound += entry_frame_bound(files[i].name, pna_cuda_encode_bound(&d), opt.phsf, opt.encryption != 0, max_chunk_size);
         st.bytes += sizes[i];
     }
-    arch = (uint8_t*)pna_cuda_host_alloc(L.ctx, bound + 64);
+    PinnedBuf arch_buf(L.ctx, bound + 64);
+    uint8_t* const arch = arch_buf.p;
     if (!arch) throw Error(PNA_E_OOM, "pinned archive buffer");
     const uint64_t alen = create_archive_into(files, opt, max_chunk_size, device, workers, group_bytes, arch, bound);
     const auto t_gpu = std::chrono::steady_clock::now();
     st.gpu_ms = ms_between(t_read, t_gpu);
-    write_whole(archive_path, arch, alen);
+    {   // the archive file, written by io_threads writers (pwrite of 64 MiB pieces)
+        const int fd = open(archive_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) throw Error(PNA_E_INTERNAL, "open " + archive_path + ": " + strerror(errno));
+        const uint64_t piece = (uint64_t)64 << 20, np = (alen + piece - 1) / piece;
+        try {
+            parallel_for((size_t)np, io_threads, [&](size_t k) {
+                uint64_t o = k * piece;
+                const uint64_t end = std::min<uint64_t>(alen, o + piece);
+                while (o < end) {
+                    const ssize_t w = pwrite(fd, arch + o, (size_t)(end - o), (off_t)o);
+                    if (w < 0) { if (errno == EINTR) continue; throw Error(PNA_E_INTERNAL, "write " + archive_path + ": " + strerror(errno)); }
+                    o += (uint64_t)w;
+                }
+            });
+        } catch (...) { close(fd); throw; }
+        close(fd);
+    }
     st.io_ms += ms_between(t_gpu, std::chrono::steady_clock::now());
     st.files = n;
     st.total_ms = ms_between(t_begin, std::chrono::steady_clock::now());
