@@ -102,8 +102,11 @@ __device__ __forceinline__ void fill_codes(Code* ix, uint32_t n, uint32_t code) 
         uint32_t* p32 = reinterpret_cast<uint32_t*>(ix);
         for (uint32_t q = 0; q + 2 <= n; q += 2) { *p32++ = pair; pair += 0x00020002u; }
         if (n & 1) ix[n - 1] = (Code)(code + n - 1);
-    } else {
-        for (uint32_t q = 0; q < n; q++) ix[q] = (Code)(code + q);
+    } else {   // 32-bit codes: two per 64-bit store once ix is 8-byte aligned
+        if (n && (reinterpret_cast<uintptr_t>(ix) & 4)) { *ix++ = (Code)code; code++; n--; }
+        uint2* p64 = reinterpret_cast<uint2*>(ix);
+        for (uint32_t q = 0; q + 2 <= n; q += 2) { *p64++ = make_uint2(code + q, code + q + 1); }
+        if (n & 1) ix[n - 1] = (Code)(code + n - 1);
     }
 }
 
