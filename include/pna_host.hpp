@@ -109,7 +109,12 @@ private:
     struct FileRef { uint32_t owner; uint32_t entry; };   // owner: 0 = top-level archive, k+1 = inner archive of solid k
     // inner archive of a solid entry: host copy for the index pass, and the decode plan whose output (the same bytes)
     // stays resident in HBM for the inner chunk CRC check and for range copies of STORE entries
-    struct Inner { std::vector<uint8_t> bytes; std::vector<RawChunk> chunks; std::vector<EntryInfo> entries; std::vector<pna_span> body_pool; std::shared_ptr<pna_plan> plan; };
+    struct Inner {
+        std::shared_ptr<uint8_t> mem;   // the decoded stream on the host (pinned, from the process-wide pool)
+        uint64_t len = 0;
+        const uint8_t* data() const { return mem.get(); }
+        std::vector<RawChunk> chunks; std::vector<EntryInfo> entries; std::vector<pna_span> body_pool; std::shared_ptr<pna_plan> plan;
+    };
     const uint8_t* buf_ = nullptr;
     size_t len_ = 0;
     uint32_t archive_number_ = 0;

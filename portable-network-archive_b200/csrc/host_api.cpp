@@ -35,6 +35,32 @@ struct Slots {
 };
 struct SlotGuard { Slots& s; explicit SlotGuard(Slots& x) : s(x) { s.acquire(); } ~SlotGuard() { s.release(); } };
 
+// Pinned host buffers are expensive to make (cudaHostAlloc pins at a few GB/s): the windows and staging buffers of the
+// file paths are kept for the life of the process and handed out again (best fit, at most 1.5x oversize).
+struct PinnedPool {
+    struct Blk { uint8_t* p; uint64_t bytes; };
+    std::mutex mu;
+    std::vector<Blk> free_list;
+    uint8_t* get(pna_ctx* ctx, uint64_t bytes, uint64_t* got) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_list.size(); i++)
+                if (free_list[i].bytes >= bytes && free_list[i].bytes <= bytes + bytes / 2 + ((uint64_t)64 << 20) &&
+                    (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+            if (best >= 0) { Blk b = free_list[best]; free_list.erase(free_list.begin() + best); *got = b.bytes; return b.p; }
+        }
+        *got = bytes;
+        return (uint8_t*)pna_cuda_host_alloc(ctx, bytes);
+    }
+    void put(pna_ctx* ctx, uint8_t* p, uint64_t bytes) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (free_list.size() >= 6) { pna_cuda_host_free(ctx, free_list.front().p); free_list.erase(free_list.begin()); }
+        free_list.push_back({p, bytes});
+    }
+};
+static PinnedPool g_pinned;
 static const uint8_t SIGNATURE[8] = {0x89, 'P', 'N', 'A', 0x0D, 0x0A, 0x1A, 0x0A};
 static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 static inline void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
@@ -318,12 +344,18 @@ void Archive::prepare(const ReadOptions& opt, int device) {
         uint64_t dec_len = 0;
         ck(L.ctx, pna_cuda_decode_plan_lengths(plan, &dec_len, &st), "solid lengths");
         if (st != PNA_OK) throw Error(st, "solid entry: decode failed");
-        in.bytes.resize(dec_len + 16);
-        pna_buf ob{in.bytes.data(), dec_len, 0};
+        {   // host copy for the index pass: a pinned buffer from the pool (true DMA, no zero fill)
+            pna_ctx* const pctx = L.ctx;
+            uint64_t got = 0;
+            uint8_t* p = g_pinned.get(pctx, dec_len + 64, &got);
+            if (!p) throw Error(PNA_E_OOM, "pinned buffer for the solid stream");
+            in.mem = std::shared_ptr<uint8_t>(p, [pctx, got](uint8_t* q) { g_pinned.put(pctx, q, got); });
+        }
+        pna_buf ob{in.mem.get(), dec_len, 0};
         ck(L.ctx, pna_cuda_decode_plan_fetch(plan, &ob, &st), "solid fetch");
         if (st != PNA_OK) throw Error(st, "solid entry: decode failed");
-        in.bytes.resize(ob.len);
-        index_chunks(in.bytes.data(), in.bytes.size(), 0, in.chunks);       // entry.rs:401-423: chunks, CRC checked as read
+        in.len = ob.len;
+        index_chunks(in.data(), in.len, 0, in.chunks);       // entry.rs:401-423: chunks, CRC checked as read
         if (!in.chunks.empty()) {                                           // ... on the copy that is still in HBM
             std::vector<uint64_t> off(in.chunks.size()), len(in.chunks.size());
             std::vector<uint32_t> crc(in.chunks.size());
@@ -332,7 +364,7 @@ void Archive::prepare(const ReadOptions& opt, int device) {
             for (size_t c = 0; c < in.chunks.size(); c++)
                 if (crc[c] != in.chunks[c].crc) throw Error(PNA_E_INVALID_DATA, "broken chunk (inside solid entry)");
         }
-        group_entries(in.bytes.data(), in.chunks, in.entries, in.body_pool);
+        group_entries(in.data(), in.chunks, in.entries, in.body_pool);
         inner_.push_back(std::move(in));
     }
     // 2. FILE entries in archive order
@@ -473,7 +505,7 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
             uint64_t at = 0;
             if (e.compressed_size > cap) { status[i] = PNA_E_NOSPACE; continue; }
             for (const pna_span& b : e.bodies) {
-                src.push_back((uint64_t)(b.ptr - in.bytes.data())); len.push_back(b.len); dst.push_back(out + (offsets[i] - o0) + at);
+                src.push_back((uint64_t)(b.ptr - in.data())); len.push_back(b.len); dst.push_back(out + (offsets[i] - o0) + at);
                 at += b.len;
             }
             status[i] = PNA_OK;
@@ -830,32 +862,6 @@ std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, 
 }
 
 // ---------------------------------------------------------------------------------------------- file-system side
-// Pinned host buffers are expensive to make (cudaHostAlloc pins at a few GB/s): the windows and staging buffers of the
-// file paths are kept for the life of the process and handed out again (best fit, at most 1.5x oversize).
-struct PinnedPool {
-    struct Blk { uint8_t* p; uint64_t bytes; };
-    std::mutex mu;
-    std::vector<Blk> free_list;
-    uint8_t* get(pna_ctx* ctx, uint64_t bytes, uint64_t* got) {
-        {
-            std::lock_guard<std::mutex> g(mu);
-            int best = -1;
-            for (int i = 0; i < (int)free_list.size(); i++)
-                if (free_list[i].bytes >= bytes && free_list[i].bytes <= bytes + bytes / 2 + ((uint64_t)64 << 20) &&
-                    (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
-            if (best >= 0) { Blk b = free_list[best]; free_list.erase(free_list.begin() + best); *got = b.bytes; return b.p; }
-        }
-        *got = bytes;
-        return (uint8_t*)pna_cuda_host_alloc(ctx, bytes);
-    }
-    void put(pna_ctx* ctx, uint8_t* p, uint64_t bytes) {
-        if (!p) return;
-        std::lock_guard<std::mutex> g(mu);
-        if (free_list.size() >= 6) { pna_cuda_host_free(ctx, free_list.front().p); free_list.erase(free_list.begin()); }
-        free_list.push_back({p, bytes});
-    }
-};
-static PinnedPool g_pinned;
 struct PinnedBuf {   // RAII lease
     pna_ctx* ctx;
     uint8_t* p = nullptr;
