@@ -59,8 +59,17 @@ struct DevCache {
     std::vector<Blk> free_list;
     std::map<void*, std::pair<size_t, int>> live;
     cudaError_t alloc(void** out, size_t bytes) {
+        // size classes: 4 KiB steps below 64 KiB, 1 MiB up to 1 MiB, then quarter-octave steps (1, 1.25, 1.5, 1.75 x 2^k):
+        // batches of similar shape ask for the SAME sizes, so a released arena is found again instead of a fresh cudaMalloc
+        // (which stalls the calling worker behind every kernel in flight)
         if (bytes < ((size_t)64 << 10)) bytes = (bytes + 4095) & ~(size_t)4095;
-        else bytes = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        else if (bytes <= ((size_t)1 << 20)) bytes = (size_t)1 << 20;
+        else {
+            size_t k = 20;
+            while (((size_t)2 << k) <= bytes) k++;          // 2^k <= bytes < 2^(k+1)
+            const size_t step = ((size_t)1 << k) / 4;
+            bytes = (bytes + step - 1) / step * step;
+        }
         int dev = 0;
         cudaGetDevice(&dev);
         {
