@@ -38,7 +38,7 @@ enum {
     PNA_E_INVALID_DATA = 1,   /* "broken chunk" format/chunk.rs:18; bad PKCS#7 cipher/block/read.rs:101; corrupt zstd */
     PNA_E_UNEXPECTED_EOF = 2, /* partial CBC block block/read.rs:90; stream shorter than IV entry/read.rs:80; truncated zstd frame */
     PNA_E_INVALID_INPUT = 3,  /* "corrupt deflate stream" (flate2 zio); bad key length stream/read.rs:27 */
-    PNA_E_UNSUPPORTED = 4,    /* xz / GCM / unknown codes entry/read.rs:152-163,184-187 */
+    PNA_E_UNSUPPORTED = 4,    /* xz / unknown codes entry/read.rs:152-163,184-187 */
     PNA_E_NOSPACE = 5,        /* out.cap too small; out.len = required size (two-pass sizing contract) */
     PNA_E_OOM = 6,            /* util/io.rs:19 */
     PNA_E_INTERNAL = 7,
@@ -59,7 +59,9 @@ typedef struct { uint8_t* ptr; uint64_t cap; uint64_t len; } pna_buf; /* caller-
 
 /* One entry's data stream: the FDAT (or SDAT) bodies in order.  The 16-byte IV is the stream prefix when
  * encryption != 0 and may straddle bodies (lib/src/entry/read.rs:79-103; chunk boundaries are arbitrary,
- * lib/src/chunk/types.rs:315-320). */
+ * lib/src/chunk/types.rs:315-320).  cipher_mode == PNA_CIPHER_GCM: the prefix is the 75-byte stream header followed by
+ * { ciphertext || tag } segments (lib/src/cipher/gcm.rs:206-290), and `key` is the per-stream key from
+ * pna_cuda_gcm_stream_key; a tag that does not verify, or a malformed / truncated layout, is PNA_E_INVALID_DATA. */
 typedef struct {
     const pna_span* bodies;
     uint32_t n_bodies;
@@ -149,6 +151,20 @@ int pna_cuda_encode_plan_fetch(pna_plan* plan, pna_buf* out, uint32_t* fdat_crc_
 
 /* stage names of an encode plan for pna_cuda_plan_stage_ms (first 5 entries: lz_match, block_write, layout, cipher, crc) */
 const char* pna_cuda_encode_stage_name(uint32_t stage);
+
+/* ---- GCM STREAM key schedule (cipher mode 2; host only, once per entry like the password KDF) ---- */
+/* decrypt_reader's GCM branch (lib/src/entry/read.rs:105-139) up to the cipher construction: parses the 75-byte stream header
+ * (= the first bytes of the data stream, lib/src/cipher/aead.rs:92-150), checks the key confirmation against k_master
+ * (aead.rs:162-164, :115-121) and derives the per-stream key HKDF-SHA-256(k_master, salt, entry context) (aead.rs:166-208) that
+ * goes into pna_decode_desc.key / pna_encode_desc.key of a cipher_mode == PNA_CIPHER_GCM entry.  header_type = "FHED" or "SHED",
+ * header_data / phsf = the Data fields of those chunks.  PNA_E_INVALID_DATA: short or out-of-range header, or key mismatch
+ * (every AeadError maps to io::ErrorKind::InvalidData, lib/src/error.rs:67-74). */
+int32_t pna_cuda_gcm_stream_key(const uint8_t k_master[32], const uint8_t* stream_header, uint64_t stream_header_len,
+                                const uint8_t header_type[4], const uint8_t* header_data, uint64_t header_len,
+                                const uint8_t* phsf, uint64_t phsf_len, uint8_t out_key[32]);
+/* writer side (lib/src/entry/write.rs:81-106): salt(32) || nonce_prefix(7) || segment_size (BE) || key confirmation(32) */
+int32_t pna_cuda_gcm_stream_header(const uint8_t k_master[32], const uint8_t salt[32], const uint8_t nonce_prefix[7],
+                                   uint32_t segment_size, uint8_t out_header[75]);
 
 /* ---- block-cipher primitives (test hooks for the KATs in lib/src/cipher.rs:256-292) ---- */
 /* ECB over n 16-byte blocks with the same key schedule the stream kernels use. */

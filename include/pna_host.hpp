@@ -64,6 +64,8 @@ struct EntryInfo {       // NormalEntry (kind 0) or SolidEntry (kind 1) as the i
         const pna_span* end() const { return p + n; }
     } bodies;
     uint32_t chunk_begin = 0, chunk_end = 0; // chunk index range [begin, end) incl. FHED..FEND
+    const uint8_t* header_data = nullptr;    // Data field of the FHED / SHED chunk (GCM binds it into the stream key, aead.rs:166)
+    uint32_t header_len = 0;
 };
 
 class ReadOptions {      // options.rs:1344; keys: PHSF string -> derived 32-byte key (KeyCache, options.rs:79)

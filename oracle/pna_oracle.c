@@ -11,6 +11,7 @@
  *                        (ctr 0.10.1 Ctr128BE: keystream block i = E_K(IV +128 i), big endian)
  *   CBC decrypt/encrypt  lib/src/cipher/block/read.rs:31-116, write.rs:48-124 (cbc 0.2.1 + PKCS#7)
  *   IV prefix            lib/src/entry/read.rs:79-103, lib/src/entry/write.rs:46-50
+ *   GCM STREAM segments  lib/src/cipher/gcm.rs:44-63,206-290, lib/src/cipher/aead.rs:92-150,210-217 (aes-gcm 0.11 == SP 800-38D)
  *   decompress           lib/src/entry/read.rs:171-190 (zstd::Decoder::with_buffer -> libzstd streaming,
  *                        flate2::bufread::ZlibDecoder -> one zlib stream)
  *   compress             lib/src/entry/write.rs:251-265 (ZstdEncoder level, no pledged size; ZlibEncoder)
@@ -208,6 +209,144 @@ int pna_oracle_ecb(int encryption, int encrypt, const uint8_t key[32], const uin
     int rc = blk_init(&b, encryption, key, encrypt);
     if (rc) return rc;
     blk_do(&b, in, out, n & ~(size_t)15);
+    blk_free(&b);
+    return ORA_OK;
+}
+
+/* ------------------------------------------------------------------ GCM STREAM (cipher mode 2) */
+/* lib/src/cipher/gcm.rs:206-290 (segment reader), :44-63 (segment writer), lib/src/cipher/aead.rs:92-150,210-217
+ * (stream header layout, segment nonce).  aes-gcm 0.11 `AesGcm<C, U12>` is standard GCM (NIST SP 800-38D) over a
+ * 128-bit block cipher with a 96-bit nonce, no AAD, 16-byte detached tag: restated here over the ECB primitive
+ * (so Camellia works too); gcm_ghash_mul is SP 800-38D Algorithm 1, bit by bit.  tests/test_oracle.py checks the
+ * restatement against OpenSSL's EVP_aes_256_gcm and against the reference's GCM fixtures. */
+enum { GCM_HDR = 75, GCM_TAG = 16, GCM_MAX_SEG = 67108864 };
+static void gcm_ghash_mul(uint8_t x[16], const uint8_t h[16]) { /* x <- x * h */
+    uint8_t z[16] = {0}, v[16];
+    memcpy(v, h, 16);
+    for (int i = 0; i < 128; i++) {
+        if ((x[i >> 3] >> (7 - (i & 7))) & 1) for (int k = 0; k < 16; k++) z[k] ^= v[k];
+        int lsb = v[15] & 1;
+        for (int k = 15; k > 0; k--) v[k] = (uint8_t)((v[k] >> 1) | (v[k - 1] << 7));
+        v[0] >>= 1;
+        if (lsb) v[0] ^= 0xE1;
+    }
+    memcpy(x, z, 16);
+}
+/* one segment, both directions: out = in ^ CTR keystream (inc32 from J0+1); tag over the CIPHERTEXT */
+static void gcm_segment(blk_t* b, const uint8_t h[16], const uint8_t nonce[12], const uint8_t* in, size_t n, uint8_t* out,
+                        int in_is_ciphertext, uint8_t tag[16]) {
+    uint8_t j0[16], ek0[16], y[16] = {0}, ctr[16], ks[16];
+    memcpy(j0, nonce, 12); j0[12] = j0[13] = j0[14] = 0; j0[15] = 1;
+    blk_do(b, j0, ek0, 16);
+    memcpy(ctr, j0, 16);
+    for (size_t off = 0; off < n; off += 16) {
+        size_t k = n - off < 16 ? n - off : 16;
+        uint32_t c = ((uint32_t)ctr[12] << 24 | (uint32_t)ctr[13] << 16 | (uint32_t)ctr[14] << 8 | ctr[15]) + 1u; /* inc32 */
+        ctr[12] = (uint8_t)(c >> 24); ctr[13] = (uint8_t)(c >> 16); ctr[14] = (uint8_t)(c >> 8); ctr[15] = (uint8_t)c;
+        blk_do(b, ctr, ks, 16);
+        uint8_t cblk[16] = {0};
+        for (size_t i = 0; i < k; i++) {
+            uint8_t o = in[off + i] ^ ks[i];
+            cblk[i] = in_is_ciphertext ? in[off + i] : o;
+            out[off + i] = o;
+        }
+        for (int i = 0; i < 16; i++) y[i] ^= cblk[i];
+        gcm_ghash_mul(y, h);
+    }
+    uint64_t bits = (uint64_t)n * 8;
+    for (int i = 0; i < 8; i++) y[15 - i] ^= (uint8_t)(bits >> (8 * i)); /* len(A)=0 || len(C) */
+    gcm_ghash_mul(y, h);
+    for (int i = 0; i < 16; i++) tag[i] = y[i] ^ ek0[i];
+}
+static void gcm_nonce(const uint8_t prefix[7], uint32_t counter, int is_final, uint8_t nonce[12]) { /* aead.rs:210 */
+    memcpy(nonce, prefix, 7);
+    nonce[7] = (uint8_t)(counter >> 24); nonce[8] = (uint8_t)(counter >> 16); nonce[9] = (uint8_t)(counter >> 8);
+    nonce[10] = (uint8_t)counter; nonce[11] = is_final ? 1 : 0;
+}
+/* stream = header(75) || { ciphertext(<= segment_size) || tag(16) }...; key = the derived STREAM key.
+ * Only tag-verified plaintext counts: on any error *out_len = bytes of the verified segments before it. */
+int pna_oracle_gcm_decrypt_stream(int encryption, const uint8_t key[32], const uint8_t* stream, size_t n, uint8_t* out,
+                                  size_t* out_len) {
+    *out_len = 0;
+    if (n < GCM_HDR) return ORA_INVALID_DATA;                /* "datastream shorter than the stream header" read.rs:108 */
+    const uint32_t seg = (uint32_t)stream[39] << 24 | (uint32_t)stream[40] << 16 | (uint32_t)stream[41] << 8 | stream[42];
+    if (seg == 0 || seg > GCM_MAX_SEG) return ORA_INVALID_DATA; /* "segment size out of range" aead.rs:141 */
+    blk_t b = {0};
+    int rc = blk_init(&b, encryption, key, 1);
+    if (rc) return rc;
+    uint8_t h[16], zero[16] = {0};
+    blk_do(&b, zero, h, 16);
+    const uint8_t* p = stream + GCM_HDR;
+    size_t rest = n - GCM_HDR, opos = 0;
+    for (uint32_t i = 0;; i++) {
+        size_t take = rest < (size_t)seg + GCM_TAG ? rest : (size_t)seg + GCM_TAG;
+        int is_final = take == rest;                          /* look-ahead byte absent  gcm.rs:233-235 */
+        if (take < GCM_TAG) { rc = ORA_INVALID_DATA; break; } /* malformed (i == 0) or truncation  gcm.rs:249-258 */
+        uint8_t nonce[12], tag[16];
+        gcm_nonce(stream + 32, i, is_final, nonce);
+        gcm_segment(&b, h, nonce, p, take - GCM_TAG, out + opos, 1, tag);
+        uint8_t diff = 0;
+        for (int k = 0; k < 16; k++) diff |= (uint8_t)(tag[k] ^ p[take - GCM_TAG + k]);
+        if (diff) { rc = ORA_INVALID_DATA; break; }           /* AuthenticationFailure  gcm.rs:283 */
+        opos += take - GCM_TAG; p += take; rest -= take;
+        if (is_final) break;
+        if (i == 0xFFFFFFFFu) { rc = ORA_INVALID_DATA; break; }
+    }
+    blk_free(&b);
+    *out_len = opos;
+    return rc;
+}
+/* GcmEncryptWriter: full segments are flushed when more data follows, finish() always emits a final one. */
+size_t pna_oracle_gcm_encrypt_bound(size_t n, uint32_t seg) { return GCM_HDR + n + (n / seg + 1) * (size_t)GCM_TAG; }
+int pna_oracle_gcm_encrypt_stream(int encryption, const uint8_t key[32], const uint8_t header[75], const uint8_t* plain,
+                                  size_t n, uint8_t* out, size_t* out_len) {
+    *out_len = 0;
+    const uint32_t seg = (uint32_t)header[39] << 24 | (uint32_t)header[40] << 16 | (uint32_t)header[41] << 8 | header[42];
+    if (seg == 0 || seg > GCM_MAX_SEG) return ORA_INVALID_INPUT;
+    blk_t b = {0};
+    int rc = blk_init(&b, encryption, key, 1);
+    if (rc) return rc;
+    uint8_t h[16], zero[16] = {0};
+    blk_do(&b, zero, h, 16);
+    memcpy(out, header, GCM_HDR);
+    size_t opos = GCM_HDR, ipos = 0;
+    for (uint32_t i = 0;; i++) {
+        size_t take = n - ipos < seg ? n - ipos : seg;
+        int is_final = ipos + take == n;
+        uint8_t nonce[12];
+        gcm_nonce(header + 32, i, is_final, nonce);
+        gcm_segment(&b, h, nonce, plain + ipos, take, out + opos, 0, out + opos + take);
+        opos += take + GCM_TAG; ipos += take;
+        if (is_final) break;
+    }
+    blk_free(&b);
+    *out_len = opos;
+    return ORA_OK;
+}
+/* OpenSSL's own AES-256-GCM of one message (check of the restatement above; AES only) */
+int pna_oracle_gcm_openssl(const uint8_t key[32], const uint8_t nonce[12], const uint8_t* in, size_t n, uint8_t* out,
+                           uint8_t tag[16]) {
+    EVP_CIPHER_CTX* c = EVP_CIPHER_CTX_new();
+    if (!c) return ORA_OOM;
+    int ol = 0, rc = ORA_OK;
+    if (EVP_EncryptInit_ex(c, EVP_aes_256_gcm(), NULL, NULL, NULL) != 1 ||
+        EVP_CIPHER_CTX_ctrl(c, EVP_CTRL_GCM_SET_IVLEN, 12, NULL) != 1 ||
+        EVP_EncryptInit_ex(c, NULL, NULL, key, nonce) != 1) rc = ORA_INTERNAL;
+    if (rc == ORA_OK && n && EVP_EncryptUpdate(c, out, &ol, in, (int)n) != 1) rc = ORA_INTERNAL;
+    if (rc == ORA_OK && EVP_EncryptFinal_ex(c, out + ol, &ol) != 1) rc = ORA_INTERNAL;
+    if (rc == ORA_OK && EVP_CIPHER_CTX_ctrl(c, EVP_CTRL_GCM_GET_TAG, 16, tag) != 1) rc = ORA_INTERNAL;
+    EVP_CIPHER_CTX_free(c);
+    return rc;
+}
+/* one restated segment, exposed for that check */
+int pna_oracle_gcm_segment(int encryption, const uint8_t key[32], const uint8_t nonce[12], const uint8_t* in, size_t n,
+                           uint8_t* out, uint8_t tag[16]) {
+    blk_t b = {0};
+    int rc = blk_init(&b, encryption, key, 1);
+    if (rc) return rc;
+    uint8_t h[16], zero[16] = {0};
+    blk_do(&b, zero, h, 16);
+    gcm_segment(&b, h, nonce, in, n, out, 0, tag);
     blk_free(&b);
     return ORA_OK;
 }
@@ -418,7 +557,16 @@ int pna_oracle_decode_stream(const uint8_t* stream, size_t n, int compression, i
     if (compression != 0 && compression != 1 && compression != 2) return ORA_UNSUPPORTED;
     if (encryption == 0) return pna_oracle_decompress(compression, stream, n, out, cap, out_len);
     if (encryption != 1 && encryption != 2) return ORA_UNSUPPORTED;
-    if (cipher_mode != 0 && cipher_mode != 1) return ORA_UNSUPPORTED; /* GCM=2: outside the hot path */
+    if (cipher_mode != 0 && cipher_mode != 1 && cipher_mode != 2) return ORA_UNSUPPORTED;
+    if (cipher_mode == 2) {                                           /* GCM STREAM: key = derived stream key */
+        uint8_t* t2 = (uint8_t*)malloc(n ? n : 1);
+        if (!t2) return ORA_OOM;
+        size_t clen2 = 0;
+        int rc2 = pna_oracle_gcm_decrypt_stream(encryption, key, stream, n, t2, &clen2);
+        if (rc2 == ORA_OK) rc2 = pna_oracle_decompress(compression, t2, clen2, out, cap, out_len);
+        free(t2);
+        return rc2;
+    }
     if (n < 16) return ORA_UNEXPECTED_EOF;                            /* read_exact(iv) entry/read.rs:80 */
     uint8_t* tmp = (uint8_t*)malloc(n ? n : 1);
     if (!tmp) return ORA_OOM;

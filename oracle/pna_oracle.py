@@ -81,6 +81,15 @@ def lib():
         L.pna_oracle_decode_batch_mt.argtypes = [C.POINTER(Job), C.c_uint32, C.c_int, C.c_int, C.c_void_p]
         L.pna_oracle_encode_batch_mt.argtypes = [C.POINTER(EncJob), C.c_uint32, C.c_int, C.c_void_p]
         L.pna_oracle_zstd_version.restype = C.c_uint
+        L.pna_oracle_gcm_decrypt_stream.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p,
+                                                    C.POINTER(C.c_size_t)]
+        L.pna_oracle_gcm_encrypt_bound.restype = C.c_size_t
+        L.pna_oracle_gcm_encrypt_bound.argtypes = [C.c_size_t, C.c_uint32]
+        L.pna_oracle_gcm_encrypt_stream.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p,
+                                                    C.POINTER(C.c_size_t)]
+        L.pna_oracle_gcm_openssl.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p]
+        L.pna_oracle_gcm_segment.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p,
+                                             C.c_char_p]
         _lib = L
     return _lib
 
@@ -198,6 +207,71 @@ def encode_stream(plain: bytes, compression: int, level: int, encryption: int, c
                                         cap, C.byref(n))
     if rc:
         raise OracleError(rc, "encode_stream")
+    return out.raw[:n.value]
+
+
+# ----------------------------------------------------------------------------- GCM STREAM (cipher mode 2)
+GCM_HEADER_LEN = 75
+GCM_TAG_LEN = 16
+GCM_DEFAULT_SEGMENT = 1 << 20
+
+
+def hkdf_sha256(ikm: bytes, salt: bytes, info: bytes) -> bytes:
+    """aead.rs:152-158: RFC 5869 extract + one expand block (32 bytes out).  hkdf 0.12: an empty salt is HashLen zeros."""
+    import hashlib, hmac
+    prk = hmac.new(salt if salt else bytes(32), ikm, hashlib.sha256).digest()
+    return hmac.new(prk, info + b"\x01", hashlib.sha256).digest()
+
+
+def gcm_key_confirmation(k_master: bytes) -> bytes:
+    """aead.rs:162-164"""
+    return hkdf_sha256(k_master, b"", b"PNA-KC-v1")
+
+
+def gcm_stream_header(salt: bytes, nonce_prefix: bytes, segment_size: int, k_master: bytes) -> bytes:
+    """aead.rs:124-132 to_bytes: salt(32) || nonce_prefix(7) || segment_size(u32 BE) || key_confirmation(32)"""
+    assert len(salt) == 32 and len(nonce_prefix) == 7
+    return salt + nonce_prefix + struct.pack(">I", segment_size) + gcm_key_confirmation(k_master)
+
+
+def gcm_derive_stream_key(k_master: bytes, header: bytes, header_type: bytes, header_data: bytes, phsf: bytes) -> bytes:
+    """aead.rs:166-208 entry_context + derive_stream_key; entry/read.rs:105-139 order of checks.
+    Raises INVALID_DATA for a malformed header or a key-confirmation mismatch (AeadError -> InvalidData, error.rs:67)."""
+    import hashlib
+    if len(header) < GCM_HEADER_LEN:
+        raise OracleError(INVALID_DATA, "datastream shorter than the stream header")
+    header = header[:GCM_HEADER_LEN]
+    (seg,) = struct.unpack_from(">I", header, 39)
+    if seg == 0 or seg > 67108864:
+        raise OracleError(INVALID_DATA, "segment size out of range")
+    if len(k_master) != 32:
+        raise OracleError(INVALID_DATA, "K_master is not 32 bytes")
+    if gcm_key_confirmation(k_master) != header[43:75]:
+        raise OracleError(INVALID_DATA, "key mismatch")
+    ctx = (b"PNA-STREAM-v1" + hashlib.sha256(header_type + header_data).digest() + hashlib.sha256(phsf).digest()
+           + header[32:39] + header[39:43])
+    assert len(ctx) == 88
+    return hkdf_sha256(k_master, header[:32], ctx)
+
+
+def gcm_decrypt_stream(encryption: int, k_stream: bytes, stream: bytes) -> bytes:
+    out = C.create_string_buffer(len(stream) or 1)
+    n = C.c_size_t(0)
+    rc = lib().pna_oracle_gcm_decrypt_stream(encryption, k_stream, stream, len(stream), out, C.byref(n))
+    if rc:
+        raise OracleError(rc, "gcm_decrypt_stream")
+    return out.raw[:n.value]
+
+
+def gcm_encrypt_stream(encryption: int, k_stream: bytes, header: bytes, plain: bytes) -> bytes:
+    """GcmEncryptWriter (gcm.rs:44-90): header || { ciphertext || tag } per segment, the last one flagged final."""
+    (seg,) = struct.unpack_from(">I", header, 39)
+    cap = lib().pna_oracle_gcm_encrypt_bound(len(plain), seg)
+    out = C.create_string_buffer(cap)
+    n = C.c_size_t(0)
+    rc = lib().pna_oracle_gcm_encrypt_stream(encryption, k_stream, header, plain, len(plain), out, C.byref(n))
+    if rc:
+        raise OracleError(rc, "gcm_encrypt_stream")
     return out.raw[:n.value]
 
 
@@ -321,6 +395,9 @@ def extract_all(buf: bytes, password: bytes | None = None, _keys=None):
             if e.phsf not in keys:
                 keys[e.phsf] = derive_key(e.phsf, password)
             key = keys[e.phsf]
+        if e.encryption and e.cipher_mode == 2:
+            key = gcm_derive_stream_key(key, e.stream[:GCM_HEADER_LEN], b"SHED" if e.solid else b"FHED", e.header,
+                                        e.phsf.encode())
         if e.solid:
             inner = decode_stream(e.stream, e.compression, e.encryption, e.cipher_mode, key)
             for ie in parse_entries(read_chunks(inner, 0, True)):

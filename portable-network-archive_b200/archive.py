@@ -15,6 +15,7 @@ encrypted by libpna_cuda.so.
 from __future__ import annotations
 
 import base64
+import ctypes as C
 import hashlib
 import os
 import struct
@@ -176,6 +177,29 @@ def index_archive(buf: np.ndarray, pos: int = 0, end: int | None = None):
     return out
 
 
+GCM_STREAM_HEADER_LEN = 75      # aead.rs:15
+GCM_DEFAULT_SEGMENT_SIZE = 1 << 20  # aead.rs:18
+
+
+def gcm_stream_key(k_master: bytes, stream_header: bytes, header_type: bytes, header_data: bytes, phsf: bytes) -> bytes:
+    """Per-stream key of a GCM entry (aead.rs:166-208) through the library's host-side key schedule."""
+    out = C.create_string_buffer(32)
+    rc = _ffi.lib().pna_cuda_gcm_stream_key(k_master, stream_header, len(stream_header), header_type, header_data,
+                                            len(header_data), phsf, len(phsf), out)
+    if rc != _ffi.OK:
+        raise PnaError(rc, "malformed AEAD datastream header or key mismatch")
+    return out.raw
+
+
+def gcm_stream_header(k_master: bytes, salt: bytes, nonce_prefix: bytes, segment_size: int = GCM_DEFAULT_SEGMENT_SIZE) -> bytes:
+    """salt || nonce_prefix || segment_size || key confirmation (aead.rs:124-132, entry/write.rs:81-99)."""
+    out = C.create_string_buffer(GCM_STREAM_HEADER_LEN)
+    rc = _ffi.lib().pna_cuda_gcm_stream_header(k_master, salt, nonce_prefix, segment_size, out)
+    if rc != _ffi.OK:
+        raise PnaError(rc, "bad GCM stream parameters")
+    return out.raw
+
+
 class _EntryBase:
     def __init__(self, archive_buf, chunks):
         self._buf = archive_buf
@@ -186,11 +210,23 @@ class _EntryBase:
     def _body(self, ch: RawChunk) -> np.ndarray:
         return self._buf[ch.off:ch.off + ch.length]
 
+    def _stream_prefix(self, n: int) -> bytes:
+        out = bytearray()
+        for b in self.bodies:
+            if len(out) >= n:
+                break
+            out += bytes(b[:n - len(out)])
+        return bytes(out)
+
     def _desc(self, options: ReadOptions | None):
         key = None
         if self.encryption not in (Encryption.NO,) and self.encryption in (Encryption.AES, Encryption.CAMELLIA) \
-                and self.cipher_mode in (CipherMode.CBC, CipherMode.CTR):
+                and self.cipher_mode in (CipherMode.CBC, CipherMode.CTR, CipherMode.GCM):
             key = (options or ReadOptions()).key_for(self.phsf)
+            if self.cipher_mode == CipherMode.GCM:
+                # decrypt_reader's GCM branch (entry/read.rs:105-139): header checks, key confirmation, stream key
+                key = gcm_stream_key(key, self._stream_prefix(GCM_STREAM_HEADER_LEN), self.chunks[0].ty, self.header_bytes,
+                                     self.phsf.encode("utf-8"))
         return {"bodies": self.bodies, "compression": self.compression, "encryption": self.encryption,
                 "cipher_mode": self.cipher_mode, "key": key, "raw_size_hint": getattr(self, "raw_file_size", None)}
 

@@ -18,6 +18,8 @@
 
 #include "../../include/pna_cuda.h"
 #include "kernels_crc_cipher.cuh"
+#include "kernels_gcm.cuh"
+#include "aead_host.hpp"
 #include "kernels_inflate.cuh"
 #include "kernels_zstd.cuh"
 #include "kernels_encode.cuh"
@@ -199,6 +201,16 @@ struct pna_plan {
     std::vector<DevKeys> h_keys;
     std::vector<CipherTile> h_tiles[5];   // 0 gather, 1 aes-ctr, 2 aes-cbc, 3 camellia-ctr, 4 camellia-cbc
     std::vector<uint32_t> h_store, h_deflate;
+    // GCM STREAM (cipher mode 2): segments, 16 KiB warp tiles (AES tiles first, then Camellia), one power table per entry
+    std::vector<gcm::GcmSeg> h_gcm_segs;
+    std::vector<gcm::GcmTile> h_gcm_tiles;
+    std::vector<gcm::GcmKeyRef> h_gcm_refs;
+    uint32_t n_gcm_tiles_aes = 0;
+    DevArr<gcm::GcmSeg> d_gcm_segs;
+    DevArr<gcm::GcmTile> d_gcm_tiles;
+    DevArr<gcm::GcmKeyRef> d_gcm_refs;
+    DevArr<gcm::GcmPow> d_gcm_pows;
+    DevArr<gcm::G128> d_gcm_partial;
     std::vector<inf::InfStream> h_inf;          // deflate streams of the two-stage path (tokens -> LZ -> Adler)
     std::vector<uint32_t> h_deflate_big;        // streams of 2 GiB and more: one-thread-per-stream kernel
     std::vector<zs::ZEntry> h_ze;
@@ -244,6 +256,7 @@ struct pna_plan {
         if (ev_ready) for (auto& e : ev) { if (ctx) ctx->ev_pool.push_back(e); else cudaEventDestroy(e); }
         d_buf.release(); d_out.release(); d_lits.release(); d_entries.release(); d_entries_init.release();
         d_segs.release(); d_keys.release();
+        d_gcm_segs.release(); d_gcm_tiles.release(); d_gcm_refs.release(); d_gcm_pows.release(); d_gcm_partial.release();
         for (auto& t : d_tiles) t.release();
         d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
@@ -300,6 +313,10 @@ extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
     ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(decrypt_tiles_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(ecb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(gcm::gcm_tiles_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gcm::gcm_tiles_smem<1>()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(gcm::gcm_tiles_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gcm::gcm_tiles_smem<2>()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(gcm::gcm_tiles_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gcm::gcm_tiles_smem<1>()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(gcm::gcm_tiles_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gcm::gcm_tiles_smem<2>()) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inf::TOKEN_SMEM_BYTES) == cudaSuccess;
@@ -447,6 +464,8 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
     std::map<std::array<uint8_t, 33>, int> key_ids;
     uint64_t comp_extra = 0;   // bytes needed in the comp region (decrypted / gathered streams)
     std::vector<uint8_t> needs_copy(n, 0);
+    std::vector<gcm::GcmSeg> gcm_walk;            // segments in entry order
+    std::map<uint32_t, uint64_t> gcm_len;         // entry -> ciphertext bytes without header and tags
     for (uint32_t i = 0; i < n; i++) {
         const pna_decode_desc& d = descs[i];
         EntryRec& e = P->h_entries[i];
@@ -469,8 +488,44 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
             e.status = ST_UNSUPPORTED;
         else if (d.encryption != PNA_ENCRYPTION_NO && d.encryption != PNA_ENCRYPTION_AES && d.encryption != PNA_ENCRYPTION_CAMELLIA)
             e.status = ST_UNSUPPORTED;
-        else if (d.encryption != 0 && d.cipher_mode != PNA_CIPHER_CBC && d.cipher_mode != PNA_CIPHER_CTR)
+        else if (d.encryption != 0 && d.cipher_mode != PNA_CIPHER_CBC && d.cipher_mode != PNA_CIPHER_CTR && d.cipher_mode != PNA_CIPHER_GCM)
             e.status = ST_UNSUPPORTED;
+        else if (d.encryption != 0 && d.cipher_mode == PNA_CIPHER_GCM) {
+            // stream header + segment walk (entry/read.rs:105-118, aead.rs:134-148, gcm.rs:206-262); every layout violation
+            // is an AeadError == InvalidData (error.rs:67-74)
+            uint8_t hdr[gcm::GCM_HEADER_LEN];
+            uint64_t got = 0;
+            for (uint32_t b = 0; b < d.n_bodies && got < sizeof hdr; b++) {
+                const uint64_t k = std::min<uint64_t>(d.bodies[b].len, sizeof hdr - got);
+                if (k) memcpy(hdr + got, d.bodies[b].ptr, k);
+                got += k;
+            }
+            const uint32_t seg = got == sizeof hdr ? ((uint32_t)hdr[39] << 24 | (uint32_t)hdr[40] << 16 | (uint32_t)hdr[41] << 8 | hdr[42]) : 0;
+            if (got < sizeof hdr || seg == 0 || seg > gcm::GCM_MAX_SEGMENT) e.status = ST_INVALID_DATA;
+            else {
+                const size_t seg0 = gcm_walk.size();
+                uint64_t rest = pos - sizeof hdr, at = sizeof hdr, plain = 0;
+                for (uint64_t i = 0;; i++) {
+                    const uint64_t take = std::min<uint64_t>(rest, (uint64_t)seg + gcm::GCM_TAG_LEN);
+                    const bool is_final = take == rest;
+                    if (take < gcm::GCM_TAG_LEN || i > 0xFFFFFFFFull) { e.status = ST_INVALID_DATA; break; }   // malformed / truncated
+                    gcm::GcmSeg g;
+                    memset(&g, 0, sizeof g);
+                    uint8_t nonce[12];
+                    memcpy(nonce, hdr + 32, 7);
+                    nonce[7] = (uint8_t)(i >> 24); nonce[8] = (uint8_t)(i >> 16); nonce[9] = (uint8_t)(i >> 8); nonce[10] = (uint8_t)i;
+                    nonce[11] = is_final ? 1 : 0;   // aead.rs:210-217
+                    memcpy(g.nonce, nonce, 12);
+                    g.entry = (uint32_t)(&e - P->h_entries.data());
+                    g.ct_pos = at; g.ct_len = take - gcm::GCM_TAG_LEN; g.out_off = plain;
+                    gcm_walk.push_back(g);
+                    plain += g.ct_len; at += take; rest -= take;
+                    if (is_final) break;
+                }
+                if (e.status != ST_OK) gcm_walk.resize(seg0);
+                else gcm_len[(uint32_t)(&e - P->h_entries.data())] = plain;
+            }
+        }
         else if (d.encryption != 0 && pos < 16)
             e.status = ST_UNEXPECTED_EOF;   // read_exact(iv)
         else if (d.encryption != 0 && d.cipher_mode == PNA_CIPHER_CBC && ((pos - 16) < 16 || (pos - 16) % 16))
@@ -495,7 +550,7 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
                 P->h_keys.push_back(dk);
             }
             e.key_idx = it->second;
-            e.comp_len = pos - 16;   // CBC: rewritten by the kernel after unpadding
+            e.comp_len = d.cipher_mode == PNA_CIPHER_GCM ? gcm_len[i] : pos - 16;   // CBC: rewritten by the kernel after unpadding
             needs_copy[i] = 1;
         } else {
             e.comp_len = pos;
@@ -527,6 +582,7 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
             e.comp_off = cur;
             cur += align_up(e.comp_len, 16) + 16;
             const uint64_t nb = (e.comp_len + 15) / 16;
+            if (e.encryption && e.cipher_mode == PNA_CIPHER_GCM) continue;   // tiled per segment below
             std::vector<CipherTile>& tv = P->h_tiles[variant_of(e)];
             for (uint64_t b0 = 0; b0 < nb; b0 += CIPHER_TILE_BLOCKS)
                 tv.push_back({i, (uint32_t)std::min<uint64_t>(CIPHER_TILE_BLOCKS, nb - b0), b0});
@@ -535,6 +591,29 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
         }
     }
     P->buf_bytes = cur + 256;
+    if (!gcm_walk.empty()) {
+        // AES segments first, then Camellia (one kernel each); the first tile of a segment is the short one
+        std::map<uint32_t, uint32_t> pow_of;
+        for (int pass = 1; pass <= 2; pass++) {
+            for (const gcm::GcmSeg& w : gcm_walk) {
+                if (P->h_entries[w.entry].encryption != pass) continue;
+                gcm::GcmSeg g = w;
+                auto it = pow_of.find(g.entry);
+                if (it == pow_of.end()) { it = pow_of.emplace(g.entry, (uint32_t)P->h_gcm_refs.size()).first; P->h_gcm_refs.push_back({g.entry}); }
+                g.pow_idx = it->second;
+                const uint64_t nb = (g.ct_len + 15) / 16;
+                g.first_tile = (uint32_t)P->h_gcm_tiles.size();
+                const uint32_t sidx = (uint32_t)P->h_gcm_segs.size();
+                uint64_t b0 = 0;
+                const uint64_t head = nb % gcm::GCM_TILE_BLOCKS;
+                if (head) { P->h_gcm_tiles.push_back({sidx, (uint32_t)head, 0}); b0 = head; }
+                for (; b0 < nb; b0 += gcm::GCM_TILE_BLOCKS) P->h_gcm_tiles.push_back({sidx, gcm::GCM_TILE_BLOCKS, b0});
+                g.n_tiles = (uint32_t)P->h_gcm_tiles.size() - g.first_tile;
+                P->h_gcm_segs.push_back(g);
+            }
+            if (pass == 1) P->n_gcm_tiles_aes = (uint32_t)P->h_gcm_tiles.size();
+        }
+    }
     // decode lists
     bool all_caps = true;
     for (uint32_t i = 0; i < n; i++) {
@@ -566,6 +645,15 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
     if (!P->h_deflate.empty()) {
         CK(P->d_deflate.reserve(P->h_deflate.size()));
         CK(cudaMemcpyAsync(P->d_deflate.p, P->h_deflate.data(), P->h_deflate.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!P->h_gcm_segs.empty()) {
+        CK(P->d_gcm_segs.reserve(P->h_gcm_segs.size())); CK(P->d_gcm_tiles.reserve(P->h_gcm_tiles.size() + 1));
+        CK(P->d_gcm_refs.reserve(P->h_gcm_refs.size())); CK(P->d_gcm_pows.reserve(P->h_gcm_refs.size()));
+        CK(P->d_gcm_partial.reserve(P->h_gcm_tiles.size() + 1));
+        CK(cudaMemcpyAsync(P->d_gcm_segs.p, P->h_gcm_segs.data(), P->h_gcm_segs.size() * sizeof(gcm::GcmSeg), cudaMemcpyHostToDevice, ctx->stream));
+        if (!P->h_gcm_tiles.empty())
+            CK(cudaMemcpyAsync(P->d_gcm_tiles.p, P->h_gcm_tiles.data(), P->h_gcm_tiles.size() * sizeof(gcm::GcmTile), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->d_gcm_refs.p, P->h_gcm_refs.data(), P->h_gcm_refs.size() * sizeof(gcm::GcmKeyRef), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (P->n_crc) {
         const size_t nt = P->h_crc_tiles.size();
@@ -666,6 +754,29 @@ static int launch_cipher(pna_plan* P) {
             case 4: decrypt_tiles_kernel<2, 0><<<grid, 256, cam_smem, ctx->stream>>>(ARGS); break;
         }
 #undef ARGS
+        LAUNCHED();
+    }
+    if (!P->h_gcm_segs.empty()) {
+        const uint32_t nk = (uint32_t)P->h_gcm_refs.size(), ns = (uint32_t)P->h_gcm_segs.size();
+        const uint32_t nt = (uint32_t)P->h_gcm_tiles.size(), na = P->n_gcm_tiles_aes;
+        gcm::gcm_setup_kernel<<<(nk + 127) / 128, 128, 0, ctx->stream>>>(P->d_gcm_refs.p, nk, P->d_entries.p, P->d_keys.p, ctx->d_aes, ctx->d_cam,
+                                                                         P->d_gcm_pows.p);
+        LAUNCHED();
+        const uint32_t cap = (uint32_t)ctx->sm_count * 3;
+        if (na) {
+            gcm::gcm_tiles_kernel<1, true><<<std::min<uint32_t>((na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+                                             gcm::gcm_tiles_smem<1>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_gcm_segs.p,
+                P->d_gcm_tiles.p, na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, nullptr, nullptr, P->d_gcm_partial.p);
+            LAUNCHED();
+        }
+        if (nt > na) {
+            gcm::gcm_tiles_kernel<2, true><<<std::min<uint32_t>((nt - na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+                                             gcm::gcm_tiles_smem<2>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_gcm_segs.p,
+                P->d_gcm_tiles.p + na, nt - na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, nullptr, nullptr, P->d_gcm_partial.p + na);
+            LAUNCHED();
+        }
+        gcm::gcm_finish_kernel<true><<<(ns + 127) / 128, 128, 0, ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_gcm_segs.p, ns, P->d_keys.p,
+                                                                                P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, P->d_gcm_partial.p, nullptr);
         LAUNCHED();
     }
     return PNA_OK;
@@ -1148,6 +1259,34 @@ extern "C" int pna_cuda_decode_batch(pna_ctx* ctx, const pna_decode_desc* descs,
 
 // ------------------------------------------------------------------------------------------------
 // block-cipher test hook
+// GCM STREAM key schedule, host only (entry/read.rs:105-139 order of checks; aead.rs:134-208)
+extern "C" int32_t pna_cuda_gcm_stream_key(const uint8_t k_master[32], const uint8_t* stream_header, uint64_t stream_header_len,
+                                           const uint8_t header_type[4], const uint8_t* header_data, uint64_t header_len,
+                                           const uint8_t* phsf, uint64_t phsf_len, uint8_t out_key[32]) {
+    if (!k_master || !header_type || !out_key || (!stream_header && stream_header_len) || (!header_data && header_len) || (!phsf && phsf_len))
+        return PNA_E_BAD_ARG;
+    if (stream_header_len < aead::STREAM_HEADER_LEN) return PNA_E_INVALID_DATA;   // "datastream shorter than the stream header"
+    const uint32_t seg = (uint32_t)stream_header[39] << 24 | (uint32_t)stream_header[40] << 16 | (uint32_t)stream_header[41] << 8 | stream_header[42];
+    if (seg == 0 || seg > gcm::GCM_MAX_SEGMENT) return PNA_E_INVALID_DATA;       // "segment size out of range"
+    uint8_t kc[32], diff = 0;
+    aead::key_confirmation(k_master, kc);
+    for (int i = 0; i < 32; i++) diff |= (uint8_t)(kc[i] ^ stream_header[43 + i]);
+    if (diff) return PNA_E_INVALID_DATA;                                         // AeadError::KeyMismatch
+    aead::derive_stream_key(k_master, stream_header, header_type, header_data, header_len, phsf, phsf_len, out_key);
+    return PNA_OK;
+}
+extern "C" int32_t pna_cuda_gcm_stream_header(const uint8_t k_master[32], const uint8_t salt[32], const uint8_t nonce_prefix[7],
+                                              uint32_t segment_size, uint8_t out_header[75]) {
+    if (!k_master || !salt || !nonce_prefix || !out_header) return PNA_E_BAD_ARG;
+    if (segment_size == 0 || segment_size > gcm::GCM_MAX_SEGMENT) return PNA_E_INVALID_INPUT;
+    memcpy(out_header, salt, 32);
+    memcpy(out_header + 32, nonce_prefix, 7);
+    out_header[39] = (uint8_t)(segment_size >> 24); out_header[40] = (uint8_t)(segment_size >> 16);
+    out_header[41] = (uint8_t)(segment_size >> 8); out_header[42] = (uint8_t)segment_size;
+    aead::key_confirmation(k_master, out_header + 43);
+    return PNA_OK;
+}
+
 extern "C" int pna_cuda_ecb(pna_ctx* ctx, int encryption, int encrypt, const uint8_t key[32], const uint8_t* in, uint64_t n_bytes,
                             uint8_t* out) {
     if (!ctx || !key || (!in && n_bytes) || (!out && n_bytes)) return PNA_E_BAD_ARG;

@@ -190,6 +190,7 @@ static void group_range(const uint8_t* buf, const std::vector<RawChunk>& ch, siz
         e.kind = solid ? 1 : 0;
         e.chunk_begin = (uint32_t)i;
         const uint8_t* h = buf + c.off;
+        e.header_data = h; e.header_len = c.len;
         if (normal) {
             if (c.len < 6) throw Error(PNA_E_INVALID_DATA, "entry header too short");
             if (h[0] != 0 || h[1] != 0) throw Error(PNA_E_UNSUPPORTED, "entry version is not supported");
@@ -306,7 +307,7 @@ Archive Archive::read_header_from_slice(const uint8_t* buf, size_t len) {
 
 static bool cipher_supported(const EntryInfo& e) {
     return (e.encryption == PNA_ENCRYPTION_AES || e.encryption == PNA_ENCRYPTION_CAMELLIA) &&
-           (e.cipher_mode == PNA_CIPHER_CBC || e.cipher_mode == PNA_CIPHER_CTR);
+           (e.cipher_mode == PNA_CIPHER_CBC || e.cipher_mode == PNA_CIPHER_CTR || e.cipher_mode == PNA_CIPHER_GCM);
 }
 // decrypt_reader's key path (entry/read.rs:45-78): returns false with a per-entry status when the key is unavailable
 static int32_t fill_desc(const EntryInfo& e, const ReadOptions& opt, pna_decode_desc& d) {
@@ -320,6 +321,19 @@ static int32_t fill_desc(const EntryInfo& e, const ReadOptions& opt, pna_decode_
         auto it = opt.keys.find(e.phsf());
         if (it == opt.keys.end()) return PNA_E_INVALID_INPUT;
         memcpy(d.key, it->second.data(), 32);
+        if (e.cipher_mode == PNA_CIPHER_GCM) {
+            // GCM branch of decrypt_reader (entry/read.rs:105-139): stream header, key confirmation, per-stream key
+            uint8_t hdr[75];
+            uint64_t got = 0;
+            for (const pna_span& b : e.bodies) {
+                if (got >= sizeof hdr) break;
+                const uint64_t k = std::min<uint64_t>(b.len, sizeof hdr - got);
+                if (k) memcpy(hdr + got, b.ptr, k);
+                got += k;
+            }
+            return pna_cuda_gcm_stream_key(it->second.data(), hdr, got, (const uint8_t*)(e.kind == 1 ? "SHED" : "FHED"), e.header_data,
+                                           e.header_len, (const uint8_t*)e.phsf().data(), e.phsf().size(), d.key);
+        }
     }
     return PNA_OK;
 }

@@ -1,0 +1,176 @@
+"""GCM STREAM cipher mode (cipher mode 2; lib/src/cipher/gcm.rs, lib/src/cipher/aead.rs).
+
+CPU tier: the oracle's restated GCM against OpenSSL's AES-256-GCM, the reference's HKDF known answer (aead.rs tests,
+K_STREAM_FHED), and the library's host-side key schedule (no GPU work).  GPU tier: the decode seam against the oracle.
+"""
+import ctypes as C
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import corpus
+
+# aead.rs tests: SALT, PREFIX, SEGMENT_SIZE, K_MASTER, HEADER_DATA, PHSF_DATA -> K_STREAM_FHED
+KAT_SALT, KAT_PREFIX, KAT_SEG = bytes([0x42]) * 32, bytes([0x5A]) * 7, 0x01020304
+KAT_K_STREAM_FHED = bytes.fromhex("b88e2edc07538bdd2b9afff57fb0d3433a1f4498d22a5911507e6827590fadb5")
+
+
+def test_oracle_gcm_segment_equals_openssl(oracle):
+    key, nonce = os.urandom(32), os.urandom(12)
+    for n in (0, 1, 15, 16, 17, 255, 4096, 70001):
+        data = os.urandom(n)
+        o1, t1 = C.create_string_buffer(n or 1), C.create_string_buffer(16)
+        o2, t2 = C.create_string_buffer(n or 1), C.create_string_buffer(16)
+        assert oracle.lib().pna_oracle_gcm_openssl(key, nonce, data, n, o1, t1) == 0
+        assert oracle.lib().pna_oracle_gcm_segment(1, key, nonce, data, n, o2, t2) == 0
+        assert o1.raw[:n] == o2.raw[:n] and t1.raw == t2.raw
+
+
+def test_oracle_hkdf_known_answer(oracle):
+    """aead.rs tests: derive_stream_key(K_MASTER, header, FHED, "header", "phsf") == K_STREAM_FHED (external RFC 5869 vector)."""
+    ctx = (b"PNA-STREAM-v1" + hashlib.sha256(b"FHED" + b"header").digest() + hashlib.sha256(b"phsf").digest() + KAT_PREFIX
+           + struct.pack(">I", KAT_SEG))
+    assert oracle.hkdf_sha256(b"master_key", KAT_SALT, ctx) == KAT_K_STREAM_FHED
+
+
+def test_library_key_schedule_matches_oracle(oracle, pna):
+    """pna_cuda_gcm_stream_key / _header are host code: same answers as the oracle's hashlib/hmac restatement."""
+    mod = __import__("importlib").import_module("portable-network-archive_b200.archive")
+    for _ in range(8):
+        km, salt, prefix = os.urandom(32), os.urandom(32), os.urandom(7)
+        seg = int.from_bytes(os.urandom(3), "big") + 1
+        hdr = mod.gcm_stream_header(km, salt, prefix, seg)
+        assert hdr == oracle.gcm_stream_header(salt, prefix, seg, km)
+        hd, ph = os.urandom(int.from_bytes(os.urandom(1), "big") + 6), os.urandom(70)
+        for ty in (b"FHED", b"SHED"):
+            assert mod.gcm_stream_key(km, hdr, ty, hd, ph) == oracle.gcm_derive_stream_key(km, hdr, ty, hd, ph)
+        with pytest.raises(pna.PnaError) as ei:                       # wrong password -> KeyMismatch (InvalidData)
+            mod.gcm_stream_key(os.urandom(32), hdr, b"FHED", hd, ph)
+        assert ei.value.kind == pna.E_INVALID_DATA
+        bad = hdr[:39] + struct.pack(">I", 0) + hdr[43:]
+        with pytest.raises(pna.PnaError):                             # segment size out of range (aead.rs:141)
+            mod.gcm_stream_key(km, bad, b"FHED", hd, ph)
+        with pytest.raises(pna.PnaError):
+            mod.gcm_stream_key(km, hdr[:74], b"FHED", hd, ph)         # shorter than the stream header
+
+
+def test_oracle_gcm_stream_round_trip_and_layout(oracle):
+    """gcm.rs tests: empty plaintext = one tag-only segment; an exact multiple of the segment size ends on a FULL final segment."""
+    key = os.urandom(32)
+    for enc in (1, 2):
+        hdr = os.urandom(39) + struct.pack(">I", 4) + os.urandom(32)
+        assert len(oracle.gcm_encrypt_stream(enc, key, hdr, b"")) == 75 + 16
+        assert len(oracle.gcm_encrypt_stream(enc, key, hdr, b"abcd")) == 75 + 4 + 16
+        assert len(oracle.gcm_encrypt_stream(enc, key, hdr, b"abcde")) == 75 + 2 * 16 + 5
+        for n in (0, 1, 4, 5, 8, 9, 1000):
+            p = os.urandom(n)
+            s = oracle.gcm_encrypt_stream(enc, key, hdr, p)
+            assert oracle.gcm_decrypt_stream(enc, key, s) == p
+            if n > 4:   # dropping the final segment leaves a non-final one at the end: its nonce flag no longer matches
+                cut = s[:75 + 4 + 16]
+                with pytest.raises(oracle.OracleError):
+                    oracle.gcm_decrypt_stream(enc, key, cut)
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU tier
+def _gcm_entry(oracle, plain, comp, enc, seg, key, split=None, hint=True):
+    hdr = os.urandom(39) + struct.pack(">I", seg) + os.urandom(32)   # the key confirmation belongs to the key schedule, not to this seam
+    body = oracle.compress(comp, plain) if comp else plain
+    stream = oracle.gcm_encrypt_stream(enc, key, hdr, body)
+    if split is None:
+        bodies = [stream]
+    else:
+        cuts = sorted(set(min(c, len(stream)) for c in split))
+        bodies = [stream[a:b] for a, b in zip([0] + cuts, cuts + [len(stream)])]
+    return {"bodies": bodies, "compression": comp, "encryption": enc, "cipher_mode": 2, "key": key,
+            "raw_size_hint": len(plain) if hint else None}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("enc", [1, 2])
+def test_gcm_decode_cross_product(ctx, oracle, enc):
+    """Segment sizes around the tile (16 KiB) and block (16 B) boundaries x payload sizes incl. empty and exact multiples."""
+    entries, want = [], []
+    k = 0
+    for seg in (1, 5, 16, 100, 4096, 16384, 16400, 50000, 1 << 20):
+        for n in (0, 1, 15, 16, 17, 4096, 16384, 16385, 50000, 100000, 300000):
+            if seg < 16 and n > 300:
+                continue
+            for comp in (0, 2):
+                key = os.urandom(32)    # stream keys are per entry (aead.rs:188)
+                plain = corpus.make_file(7000 + k, n)
+                k += 1
+                split = None if k % 3 else [40, 75, 76, 75 + seg, 75 + seg + 16, 75 + seg + 17, 99999]
+                entries.append(_gcm_entry(oracle, plain, comp, enc, seg, key, split, hint=(k % 2 == 0)))
+                want.append(plain)
+    outs, st, lens = ctx.decode_batch(entries)
+    assert st == [0] * len(entries)
+    for o, w in zip(outs, want):
+        assert o.tobytes() == w
+
+
+@pytest.mark.gpu
+def test_gcm_multi_tile_segments_and_mixed_batch(ctx, oracle):
+    """1 MiB segments (64 tiles chained with H^1024), 4 MiB entries, AES and Camellia and CTR entries in one batch."""
+    entries, want = [], []
+    for i, (enc, mode) in enumerate([(1, 2), (2, 2), (1, 1), (1, 2), (2, 0), (2, 2)]):
+        key = os.urandom(32)
+        plain = corpus.make_file(9000 + i, (4 << 20) + 123 * i)
+        if mode == 2:
+            entries.append(_gcm_entry(oracle, plain, 2 if i % 2 else 0, enc, 1 << 20, key))
+        else:
+            s = oracle.encode_stream(plain, 2, -1, enc, mode, key, os.urandom(16))
+            entries.append({"bodies": [s], "compression": 2, "encryption": enc, "cipher_mode": mode, "key": key,
+                            "raw_size_hint": len(plain)})
+        want.append(plain)
+    outs, st, lens = ctx.decode_batch(entries)
+    assert st == [0] * len(entries)
+    for o, w in zip(outs, want):
+        assert hashlib.sha256(o.tobytes()).digest() == hashlib.sha256(w).digest()
+
+
+@pytest.mark.gpu
+def test_gcm_error_classes(ctx, oracle, pna):
+    """Every AEAD failure is InvalidData (error.rs:67-74): tampering, truncation, layout violations."""
+    key = os.urandom(32)
+    plain = corpus.make_file(5, 40000)
+    good = _gcm_entry(oracle, plain, 0, 1, 16384, key)
+    s = bytes(good["bodies"][0])
+    seg_len = 16384 + 16
+
+    def flip(pos):
+        b = bytearray(s)
+        b[pos] ^= 1
+        return bytes(b)
+
+    cases = [
+        ([s], 0),
+        ([flip(75 + 100)], pna.E_INVALID_DATA),                   # ciphertext bit           gcm.rs:283
+        ([flip(75 + seg_len - 1)], pna.E_INVALID_DATA),           # tag bit of segment 0
+        ([flip(len(s) - 1)], pna.E_INVALID_DATA),                 # tag bit of the final segment
+        ([flip(33)], pna.E_INVALID_DATA),                         # nonce prefix in the header
+        ([s[:75 + 2 * seg_len]], pna.E_INVALID_DATA),             # final segment dropped: flag mismatch on the new last one
+        ([s[:75 + 2 * seg_len + 5]], pna.E_INVALID_DATA),         # 5-byte tail after verified segments: truncation  gcm.rs:254
+        ([s[:len(s) - 3]], pna.E_INVALID_DATA),                   # final segment cut short
+        ([s[:60]], pna.E_INVALID_DATA),                           # shorter than the stream header  entry/read.rs:108
+        ([s[:75]], pna.E_INVALID_DATA),                           # no segment at all          gcm.rs:250
+        ([s[:75 + 9]], pna.E_INVALID_DATA),                       # shorter than one empty final segment
+        ([s[:39] + bytes(4) + s[43:]], pna.E_INVALID_DATA),       # segment size 0             aead.rs:141
+        ([s[:39] + struct.pack(">I", (64 << 20) + 1) + s[43:]], pna.E_INVALID_DATA),
+        ([s + s[75:]], pna.E_INVALID_DATA),                       # bytes after the final segment: it is no longer final
+    ]
+    entries = [dict(good, bodies=b) for b, _ in cases]
+    outs, st, lens = ctx.decode_batch(entries)
+    for (b, want), got, o in zip(cases, st, outs):
+        assert got == want, (len(b[0]), got, want)
+        try:
+            ref = oracle.gcm_decrypt_stream(1, key, b[0])
+            assert want == 0 and o.tobytes() == ref
+        except oracle.OracleError as e:
+            assert want == e.status
+    wrong = dict(good, key=os.urandom(32))
+    _, st, _ = ctx.decode_batch([wrong, good])
+    assert st[0] == pna.E_INVALID_DATA and st[1] == 0

@@ -130,7 +130,7 @@ def test_decode_error_classes(ctx, oracle, pna):
         (dict(good, bodies=[s[:16]]), pna.E_UNEXPECTED_EOF),                   # no first block       block/read.rs:36
         (dict(good, key=os.urandom(32)), None),                               # wrong key: bad pad or corrupt zstd
         (dict(good, compression=4), pna.E_UNSUPPORTED),                        # xz
-        (dict(good, cipher_mode=2), pna.E_UNSUPPORTED),                        # GCM
+        (dict(good, cipher_mode=3), pna.E_UNSUPPORTED),                        # reserved cipher mode  entry/read.rs:152
         (dict(good, encryption=7), pna.E_UNSUPPORTED),
     ]
     z = _mk(oracle, plain, 2, 0, 0, key)
