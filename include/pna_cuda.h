@@ -70,14 +70,20 @@ typedef struct {
     uint64_t raw_size_hint;                             /* fSIZ (lib/src/entry.rs:817) or UINT64_MAX */
 } pna_decode_desc;
 
-/* One entry to build: plaintext in, IV || cipher(compress(plain)) out (lib/src/entry/write.rs:268-273). */
+/* One entry to build: plaintext in, IV || cipher(compress(plain)) out (lib/src/entry/write.rs:268-273; the prefix chunk is
+ * split off by the caller: builder.rs:62-69). */
 typedef struct {
     pna_span plain;
     uint8_t compression, encryption, cipher_mode, _pad;
     int32_t level;          /* <0: reference default (zstd 3 compress/zstandard.rs:46, deflate 6 compress/deflate.rs:89) */
     uint8_t key[32];
-    uint8_t iv[16];         /* caller-drawn (lib/src/entry/write.rs:108-111, random.rs:8) */
+    uint8_t iv[16];         /* caller-drawn (lib/src/entry/write.rs:108-111, random.rs:8); unused by GCM */
     uint32_t max_chunk_size; /* FDAT body cap for CRC emission; 0 = u32::MAX - one body (lib/src/util/io.rs:24-33) */
+    /* cipher_mode == PNA_CIPHER_GCM only: the 75-byte stream header (pna_cuda_gcm_stream_header; salt and nonce prefix
+     * caller-drawn, lib/src/entry/write.rs:81-99) -- it becomes the stream prefix where CBC/CTR put the IV -- and `key` is the
+     * per-stream key (pna_cuda_gcm_stream_key).  Output: header || { ciphertext(segment_size) || tag(16) }..., the last segment
+     * flagged final (lib/src/cipher/gcm.rs:44-90). */
+    const uint8_t* stream_header;
 } pna_encode_desc;
 
 /* ---- context ---- */

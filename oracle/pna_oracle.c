@@ -258,6 +258,31 @@ static void gcm_segment(blk_t* b, const uint8_t h[16], const uint8_t nonce[12], 
     gcm_ghash_mul(y, h);
     for (int i = 0; i < 16; i++) tag[i] = y[i] ^ ek0[i];
 }
+/* AES segments go through OpenSSL's AES-256-GCM (AES-NI + PCLMUL: what the CPU baseline should time, like the aes-gcm crate's
+ * hardware back ends); Camellia has no OpenSSL GCM and uses the restatement.  tests/test_gcm.py checks one against the other. */
+static int gcm_segment_aes_evp(const uint8_t key[32], const uint8_t nonce[12], const uint8_t* in, size_t n, uint8_t* out, int decrypt,
+                               uint8_t tag[16]) {
+    EVP_CIPHER_CTX* c = EVP_CIPHER_CTX_new();
+    if (!c) return ORA_OOM;
+    int ol = 0, rc = ORA_OK;
+    if (EVP_CipherInit_ex(c, EVP_aes_256_gcm(), NULL, NULL, NULL, !decrypt) != 1 ||
+        EVP_CIPHER_CTX_ctrl(c, EVP_CTRL_GCM_SET_IVLEN, 12, NULL) != 1 ||
+        EVP_CipherInit_ex(c, NULL, NULL, key, nonce, !decrypt) != 1) rc = ORA_INTERNAL;
+    size_t done = 0;
+    while (rc == ORA_OK && done < n) {
+        int k = n - done > (1u << 30) ? (1 << 30) : (int)(n - done);
+        if (EVP_CipherUpdate(c, out + done, &ol, in + done, k) != 1) rc = ORA_INTERNAL;
+        done += (size_t)k;
+    }
+    if (rc == ORA_OK && decrypt) {
+        if (EVP_CIPHER_CTX_ctrl(c, EVP_CTRL_GCM_SET_TAG, 16, tag) != 1) rc = ORA_INTERNAL;
+        else if (EVP_CipherFinal_ex(c, out + n, &ol) != 1) rc = ORA_INVALID_DATA;   /* tag mismatch */
+    } else if (rc == ORA_OK) {
+        if (EVP_CipherFinal_ex(c, out + n, &ol) != 1 || EVP_CIPHER_CTX_ctrl(c, EVP_CTRL_GCM_GET_TAG, 16, tag) != 1) rc = ORA_INTERNAL;
+    }
+    EVP_CIPHER_CTX_free(c);
+    return rc;
+}
 static void gcm_nonce(const uint8_t prefix[7], uint32_t counter, int is_final, uint8_t nonce[12]) { /* aead.rs:210 */
     memcpy(nonce, prefix, 7);
     nonce[7] = (uint8_t)(counter >> 24); nonce[8] = (uint8_t)(counter >> 16); nonce[9] = (uint8_t)(counter >> 8);
@@ -284,10 +309,16 @@ int pna_oracle_gcm_decrypt_stream(int encryption, const uint8_t key[32], const u
         if (take < GCM_TAG) { rc = ORA_INVALID_DATA; break; } /* malformed (i == 0) or truncation  gcm.rs:249-258 */
         uint8_t nonce[12], tag[16];
         gcm_nonce(stream + 32, i, is_final, nonce);
-        gcm_segment(&b, h, nonce, p, take - GCM_TAG, out + opos, 1, tag);
-        uint8_t diff = 0;
-        for (int k = 0; k < 16; k++) diff |= (uint8_t)(tag[k] ^ p[take - GCM_TAG + k]);
-        if (diff) { rc = ORA_INVALID_DATA; break; }           /* AuthenticationFailure  gcm.rs:283 */
+        if (encryption == 1) {
+            memcpy(tag, p + take - GCM_TAG, 16);
+            rc = gcm_segment_aes_evp(key, nonce, p, take - GCM_TAG, out + opos, 1, tag);
+            if (rc) break;
+        } else {
+            gcm_segment(&b, h, nonce, p, take - GCM_TAG, out + opos, 1, tag);
+            uint8_t diff = 0;
+            for (int k = 0; k < 16; k++) diff |= (uint8_t)(tag[k] ^ p[take - GCM_TAG + k]);
+            if (diff) { rc = ORA_INVALID_DATA; break; }       /* AuthenticationFailure  gcm.rs:283 */
+        }
         opos += take - GCM_TAG; p += take; rest -= take;
         if (is_final) break;
         if (i == 0xFFFFFFFFu) { rc = ORA_INVALID_DATA; break; }
@@ -315,7 +346,12 @@ int pna_oracle_gcm_encrypt_stream(int encryption, const uint8_t key[32], const u
         int is_final = ipos + take == n;
         uint8_t nonce[12];
         gcm_nonce(header + 32, i, is_final, nonce);
-        gcm_segment(&b, h, nonce, plain + ipos, take, out + opos, 0, out + opos + take);
+        if (encryption == 1) {
+            uint8_t tg[16];
+            int r2 = gcm_segment_aes_evp(key, nonce, plain + ipos, take, out + opos, 0, tg);
+            if (r2) { blk_free(&b); return r2; }
+            memcpy(out + opos + take, tg, 16);
+        } else gcm_segment(&b, h, nonce, plain + ipos, take, out + opos, 0, out + opos + take);
         opos += take + GCM_TAG; ipos += take;
         if (is_final) break;
     }

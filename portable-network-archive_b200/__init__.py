@@ -295,6 +295,11 @@ class Context:
             C.memmove(d.key, e.get("key") or bytes(32), 32)
             C.memmove(d.iv, e.get("iv") or bytes(16), 16)
             d.max_chunk_size = e.get("max_chunk_size", 0)
+            sh = e.get("stream_header")     # GCM: the 75-byte stream header (archive.gcm_stream_header)
+            if sh is not None:
+                hb = C.create_string_buffer(bytes(sh), len(sh))
+                keep.append(hb)
+                d.stream_header = C.cast(hb, C.c_void_p)
         return descs, keep
 
     def encode_plan(self, entries) -> "EncodePlan":

@@ -41,7 +41,7 @@ class DecodeDesc(C.Structure):
 class EncodeDesc(C.Structure):
     _fields_ = [("plain", Span), ("compression", C.c_uint8), ("encryption", C.c_uint8), ("cipher_mode", C.c_uint8),
                 ("_pad", C.c_uint8), ("level", C.c_int32), ("key", C.c_uint8 * 32), ("iv", C.c_uint8 * 16),
-                ("max_chunk_size", C.c_uint32)]
+                ("max_chunk_size", C.c_uint32), ("stream_header", C.c_void_p)]
 
 
 class PnaCudaError(RuntimeError):

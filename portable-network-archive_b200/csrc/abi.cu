@@ -517,7 +517,7 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
                     nonce[11] = is_final ? 1 : 0;   // aead.rs:210-217
                     memcpy(g.nonce, nonce, 12);
                     g.entry = (uint32_t)(&e - P->h_entries.data());
-                    g.ct_pos = at; g.ct_len = take - gcm::GCM_TAG_LEN; g.out_off = plain;
+                    g.ct_pos = at; g.ct_len = take - gcm::GCM_TAG_LEN; g.dst_off = plain;   // + comp_off once that is known
                     gcm_walk.push_back(g);
                     plain += g.ct_len; at += take; rest -= take;
                     if (is_final) break;
@@ -598,9 +598,16 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
             for (const gcm::GcmSeg& w : gcm_walk) {
                 if (P->h_entries[w.entry].encryption != pass) continue;
                 gcm::GcmSeg g = w;
+                const EntryRec& ge = P->h_entries[g.entry];
                 auto it = pow_of.find(g.entry);
-                if (it == pow_of.end()) { it = pow_of.emplace(g.entry, (uint32_t)P->h_gcm_refs.size()).first; P->h_gcm_refs.push_back({g.entry}); }
+                if (it == pow_of.end()) {
+                    it = pow_of.emplace(g.entry, (uint32_t)P->h_gcm_refs.size()).first;
+                    P->h_gcm_refs.push_back({ge.key_idx, (uint32_t)ge.encryption});
+                }
                 g.pow_idx = it->second;
+                g.key_idx = ge.key_idx; g.enc = ge.encryption;
+                g.src_seg_begin = ge.seg_begin; g.src_n_segs = ge.n_segs; g.src_len = ge.stream_len;
+                g.dst_off += ge.comp_off;
                 const uint64_t nb = (g.ct_len + 15) / 16;
                 g.first_tile = (uint32_t)P->h_gcm_tiles.size();
                 const uint32_t sidx = (uint32_t)P->h_gcm_segs.size();
@@ -759,20 +766,19 @@ static int launch_cipher(pna_plan* P) {
     if (!P->h_gcm_segs.empty()) {
         const uint32_t nk = (uint32_t)P->h_gcm_refs.size(), ns = (uint32_t)P->h_gcm_segs.size();
         const uint32_t nt = (uint32_t)P->h_gcm_tiles.size(), na = P->n_gcm_tiles_aes;
-        gcm::gcm_setup_kernel<<<(nk + 127) / 128, 128, 0, ctx->stream>>>(P->d_gcm_refs.p, nk, P->d_entries.p, P->d_keys.p, ctx->d_aes, ctx->d_cam,
-                                                                         P->d_gcm_pows.p);
+        gcm::gcm_setup_kernel<<<(nk + 127) / 128, 128, 0, ctx->stream>>>(P->d_gcm_refs.p, nk, P->d_keys.p, ctx->d_aes, ctx->d_cam, P->d_gcm_pows.p);
         LAUNCHED();
         const uint32_t cap = (uint32_t)ctx->sm_count * 3;
         if (na) {
             gcm::gcm_tiles_kernel<1, true><<<std::min<uint32_t>((na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
-                                             gcm::gcm_tiles_smem<1>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_gcm_segs.p,
-                P->d_gcm_tiles.p, na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, nullptr, nullptr, P->d_gcm_partial.p);
+                                             gcm::gcm_tiles_smem<1>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_buf.p, P->d_gcm_segs.p,
+                P->d_gcm_tiles.p, na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, P->d_gcm_partial.p);
             LAUNCHED();
         }
         if (nt > na) {
             gcm::gcm_tiles_kernel<2, true><<<std::min<uint32_t>((nt - na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
-                                             gcm::gcm_tiles_smem<2>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_gcm_segs.p,
-                P->d_gcm_tiles.p + na, nt - na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, nullptr, nullptr, P->d_gcm_partial.p + na);
+                                             gcm::gcm_tiles_smem<2>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_buf.p, P->d_gcm_segs.p,
+                P->d_gcm_tiles.p + na, nt - na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, P->d_gcm_partial.p + na);
             LAUNCHED();
         }
         gcm::gcm_finish_kernel<true><<<(ns + 127) / 128, 128, 0, ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_entries.p, P->d_gcm_segs.p, ns, P->d_keys.p,

@@ -26,6 +26,16 @@ struct EncodePlan {
     DevArr<CrcTile> d_crc_tiles;
     DevArr<EncTables> d_tables;
     uint32_t fdat_init = 0;
+    // GCM STREAM: segment / tile slots from the compressed-length bounds (AES slots first, then Camellia)
+    std::vector<GcmSlot> h_gcm_slots;
+    std::vector<gcm::GcmKeyRef> h_gcm_refs;
+    uint32_t n_gcm_tiles = 0, n_gcm_tiles_aes = 0;
+    DevArr<GcmSlot> d_gcm_slots;
+    DevArr<gcm::GcmKeyRef> d_gcm_refs;
+    DevArr<gcm::GcmSeg> d_gcm_segs;
+    DevArr<gcm::GcmTile> d_gcm_tiles;
+    DevArr<gcm::GcmPow> d_gcm_pows;
+    DevArr<gcm::G128> d_gcm_partial;
 };
 void destroy(EncodePlan* p) { delete p; }
 bool init_attributes() {
@@ -48,14 +58,28 @@ static uint64_t enc_comp_bound(uint8_t compression, uint64_t len) {
     if (compression == PNA_COMPRESSION_DEFLATE) return len + 5 * enc_nsegs(len) + 8;
     return len;
 }
+static bool enc_is_gcm(const pna_encode_desc& d) { return d.encryption != 0 && d.cipher_mode == PNA_CIPHER_GCM; }
+static uint32_t enc_gcm_seg_size(const pna_encode_desc& d) {   // 0: no / invalid header
+    if (!d.stream_header) return 0;
+    const uint8_t* h = d.stream_header;
+    const uint32_t s = (uint32_t)h[39] << 24 | (uint32_t)h[40] << 16 | (uint32_t)h[41] << 8 | h[42];
+    return s <= gcm::GCM_MAX_SEGMENT ? s : 0;
+}
+// stream prefix that the caller splits off as its own chunk(s): IV (CBC/CTR) or stream header (GCM)  builder.rs:62-69
+static uint64_t enc_prefix_len(const pna_encode_desc& d) { return d.encryption ? (enc_is_gcm(d) ? gcm::GCM_HEADER_LEN : 16) : 0; }
 extern "C" uint64_t pna_cuda_encode_bound(const pna_encode_desc* d) {
     if (!d) return 0;
-    return enc_comp_bound(d->compression, d->plain.len) + (d->encryption ? 32 : 0);
+    const uint64_t cb = enc_comp_bound(d->compression, d->plain.len);
+    if (enc_is_gcm(*d)) {
+        const uint32_t seg = enc_gcm_seg_size(*d);
+        return gcm::GCM_HEADER_LEN + cb + (seg ? cb / seg + 1 : 1) * (uint64_t)gcm::GCM_TAG_LEN;
+    }
+    return cb + (d->encryption ? 32 : 0);
 }
 extern "C" uint64_t pna_cuda_encode_crc_count(const pna_encode_desc* d) {
     if (!d) return 0;
     const uint64_t cap = d->max_chunk_size ? d->max_chunk_size : 0xFFFFFFFFull;
-    const uint64_t body = pna_cuda_encode_bound(d) - (d->encryption ? 16 : 0);
+    const uint64_t body = pna_cuda_encode_bound(d) - enc_prefix_len(*d);
     return (body + cap - 1) / cap + 1;
 }
 
@@ -81,9 +105,12 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
             e.status = ST_UNSUPPORTED;   // xz: entry/write.rs:264 has it, this path does not
         else if (d.encryption != PNA_ENCRYPTION_NO && d.encryption != PNA_ENCRYPTION_AES && d.encryption != PNA_ENCRYPTION_CAMELLIA)
             e.status = ST_UNSUPPORTED;
-        else if (d.encryption != 0 && d.cipher_mode != PNA_CIPHER_CBC && d.cipher_mode != PNA_CIPHER_CTR)
+        else if (d.encryption != 0 && d.cipher_mode != PNA_CIPHER_CBC && d.cipher_mode != PNA_CIPHER_CTR && d.cipher_mode != PNA_CIPHER_GCM)
             e.status = ST_UNSUPPORTED;
+        else if (enc_is_gcm(d) && enc_gcm_seg_size(d) == 0)
+            e.status = ST_INVALID_INPUT;   // no stream header / segment size out of range (SegmentSize::new, aead.rs:83-88)
         if (e.status != ST_OK) continue;
+        if (enc_is_gcm(d)) { e.gcm_seg_size = enc_gcm_seg_size(d); memcpy(e.gcm_hdr, d.stream_header, gcm::GCM_HEADER_LEN); }
         if (d.compression != PNA_COMPRESSION_NO) { e.seg_begin = (uint32_t)nsegs_total; e.n_segs = (uint32_t)enc_nsegs(d.plain.len); nsegs_total += e.n_segs; }
         if (d.encryption) {
             std::array<uint8_t, 33> k;
@@ -136,13 +163,15 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
             s.adler = e.compression == PNA_COMPRESSION_DEFLATE;
         }
         piece_cur += 3 + 3 * (uint64_t)e.n_segs;
-        const uint64_t bound = enc_comp_bound(e.compression, e.plain_len) + (e.encryption ? 32 : 0);
+        const uint64_t bound = pna_cuda_encode_bound(&d);
         e.out_cap = bound;
         out_cur += align_up(bound, 16) + 16;
         // cipher work from the bound: CTR / none tiles, CBC list
         const uint64_t cb = enc_comp_bound(e.compression, e.plain_len);
         if (e.encryption && e.cipher_mode == PNA_CIPHER_CBC) E->h_cbc[e.encryption - 1].push_back(i);
-        else {
+        else if (e.encryption && e.cipher_mode == PNA_CIPHER_GCM) {
+            // slots are laid out below (AES first, then Camellia)
+        } else {
             std::vector<CipherTile>& tv = E->h_tiles[e.encryption];
             const uint64_t nb = (cb + 15) / 16;
             uint64_t b0 = 0;
@@ -152,7 +181,7 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
             } while (b0 < nb);
         }
         // FDAT bodies after the IV (the IV is its own chunk, lib/src/entry/builder.rs:62-69)
-        const uint64_t iv_len = e.encryption ? 16 : 0, mcs = E->crc_body_size[i];
+        const uint64_t iv_len = enc_prefix_len(d), mcs = E->crc_body_size[i];
         const uint64_t nbody = (bound - iv_len + mcs - 1) / mcs + 1;
         for (uint64_t b = 0; b < nbody; b++) {
             E->h_crc_first.push_back((uint32_t)E->h_crc_src.size());
@@ -166,6 +195,24 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
             } while (l && o < bound + 16);
         }
         crc_bodies += nbody;
+    }
+    for (uint32_t pass = 1; pass <= 2; pass++) {
+        for (uint32_t i = 0; i < n; i++) {
+            EncEntry& e = E->h_entries[i];
+            if (e.status != ST_OK || e.encryption != pass || e.cipher_mode != PNA_CIPHER_GCM) continue;
+            const uint64_t cb = enc_comp_bound(e.compression, e.plain_len), S = e.gcm_seg_size;
+            const uint64_t max_segs = cb / S + 1;
+            const uint64_t tps = ((S + 15) / 16 + gcm::GCM_TILE_BLOCKS - 1) / gcm::GCM_TILE_BLOCKS;
+            if (E->h_gcm_slots.size() + max_segs > 0x7FFFFFF0ull || (uint64_t)E->n_gcm_tiles + max_segs * tps > 0x7FFFFFF0ull) return PNA_E_OOM;
+            e.gcm_slot_begin = (uint32_t)E->h_gcm_slots.size();
+            e.gcm_tile_begin = E->n_gcm_tiles;
+            e.gcm_tiles_per_seg = (uint32_t)tps;
+            e.gcm_pow_idx = (uint32_t)E->h_gcm_refs.size();
+            E->h_gcm_refs.push_back({e.key_idx, (uint32_t)e.encryption});
+            for (uint64_t j = 0; j < max_segs; j++) E->h_gcm_slots.push_back({i, (uint32_t)j});
+            E->n_gcm_tiles += (uint32_t)(max_segs * tps);
+        }
+        if (pass == 1) E->n_gcm_tiles_aes = E->n_gcm_tiles;
     }
     E->n_pieces = piece_cur;
     E->out_bytes = out_cur;
@@ -194,6 +241,13 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
         if (E->h_cbc[v].empty()) continue;
         CK(E->d_cbc[v].reserve(E->h_cbc[v].size()));
         CK(cudaMemcpyAsync(E->d_cbc[v].p, E->h_cbc[v].data(), E->h_cbc[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!E->h_gcm_slots.empty()) {
+        const size_t ns = E->h_gcm_slots.size();
+        CK(E->d_gcm_slots.reserve(ns)); CK(E->d_gcm_segs.reserve(ns)); CK(E->d_gcm_refs.reserve(E->h_gcm_refs.size()));
+        CK(E->d_gcm_pows.reserve(E->h_gcm_refs.size())); CK(E->d_gcm_tiles.reserve(E->n_gcm_tiles + 1)); CK(E->d_gcm_partial.reserve(E->n_gcm_tiles + 1));
+        CK(cudaMemcpyAsync(E->d_gcm_slots.p, E->h_gcm_slots.data(), ns * sizeof(enc::GcmSlot), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(E->d_gcm_refs.p, E->h_gcm_refs.data(), E->h_gcm_refs.size() * sizeof(gcm::GcmKeyRef), cudaMemcpyHostToDevice, ctx->stream));
     }
     const size_t nt = E->h_crc_src.size(), nb = E->h_crc_first.size();
     if (nt) {
@@ -260,6 +314,29 @@ static int encode_launch_all(pna_plan* P) {
         if (v == 0) enc::cbc_encrypt_kernel<1><<<(nc + 63) / 64, 64, aes_smem, ctx->stream>>>(ARGS);
         else enc::cbc_encrypt_kernel<2><<<(nc + 63) / 64, 64, cam_smem, ctx->stream>>>(ARGS);
 #undef ARGS
+        LAUNCHED();
+    }
+    if (!E->h_gcm_slots.empty()) {
+        const uint32_t ns = (uint32_t)E->h_gcm_slots.size(), nk = (uint32_t)E->h_gcm_refs.size(), ntl = E->n_gcm_tiles, na = E->n_gcm_tiles_aes;
+        enc::gcm_enc_slots_kernel<<<(ns + 127) / 128, 128, 0, ctx->stream>>>(E->d_gcm_slots.p, ns, E->d_entries.p, E->d_gcm_segs.p, E->d_gcm_tiles.p, E->d_out.p);
+        LAUNCHED();
+        gcm::gcm_setup_kernel<<<(nk + 127) / 128, 128, 0, ctx->stream>>>(E->d_gcm_refs.p, nk, E->d_keys.p, ctx->d_aes, ctx->d_cam, E->d_gcm_pows.p);
+        LAUNCHED();
+        const uint32_t cap = (uint32_t)ctx->sm_count * 3;
+        if (na) {
+            gcm::gcm_tiles_kernel<1, false><<<std::min<uint32_t>((na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+                                              gcm::gcm_tiles_smem<1>(), ctx->stream>>>(E->d_work.p, E->d_pieces.p, E->d_out.p, E->d_gcm_segs.p,
+                E->d_gcm_tiles.p, na, E->d_keys.p, E->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, E->d_gcm_partial.p);
+            LAUNCHED();
+        }
+        if (ntl > na) {
+            gcm::gcm_tiles_kernel<2, false><<<std::min<uint32_t>((ntl - na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+                                              gcm::gcm_tiles_smem<2>(), ctx->stream>>>(E->d_work.p, E->d_pieces.p, E->d_out.p, E->d_gcm_segs.p,
+                E->d_gcm_tiles.p + na, ntl - na, E->d_keys.p, E->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, E->d_gcm_partial.p + na);
+            LAUNCHED();
+        }
+        gcm::gcm_finish_kernel<false><<<(ns + 127) / 128, 128, 0, ctx->stream>>>(E->d_work.p, E->d_pieces.p, nullptr, E->d_gcm_segs.p, ns, E->d_keys.p,
+                                                                                 E->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, E->d_gcm_partial.p, E->d_out.p);
         LAUNCHED();
     }
     STAGE(4);
@@ -344,7 +421,7 @@ extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* f
         if (st == ST_OK) {
             if (len) CK(cudaMemcpyAsync(out[i].ptr, E->d_out.p + e.out_off, len, cudaMemcpyDeviceToHost, ctx->stream));
             stream_bytes += len;
-            const uint64_t iv_len = e.encryption ? 16 : 0, mcs = E->crc_body_size[i];
+            const uint64_t iv_len = e.encryption ? (e.cipher_mode == PNA_CIPHER_GCM ? gcm::GCM_HEADER_LEN : 16) : 0, mcs = E->crc_body_size[i];
             nbody = (uint32_t)((len - iv_len + mcs - 1) / mcs);
             if (fdat_crc_out)
                 for (uint32_t b = 0; b < nbody; b++) fdat_crc_out[crc_pos + b] = crcs[E->crc_body_begin[i] + b];

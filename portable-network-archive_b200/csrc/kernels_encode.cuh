@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "encode_core.cuh"
 #include "kernels_crc_cipher.cuh"
+#include "kernels_gcm.cuh"
 
 namespace pna {
 namespace enc {
@@ -45,6 +46,9 @@ struct EncEntry {
     int32_t status;
     uint8_t compression, encryption, cipher_mode, _pad;
     uint8_t iv[16];
+    // GCM STREAM (cipher mode 2): segment size, this entry's ranges in the plan's segment / tile slot tables, stream header
+    uint32_t gcm_seg_size, gcm_slot_begin, gcm_tile_begin, gcm_tiles_per_seg, gcm_pow_idx;
+    uint8_t gcm_hdr[76];
 };
 
 constexpr int ENC_WARPS = 9;          // 9 warps x 8 KB of hash table per CTA, 3 CTAs per SM: 27 segments in flight per SM
@@ -290,6 +294,10 @@ __global__ void enc_layout_kernel(uint8_t* __restrict__ work, const SegRec* __re
     e.n_pieces = np;
     e.comp_len = pos;
     const uint64_t hdr = e.encryption ? 16 : 0;
+    if (e.encryption && e.cipher_mode == 2) {   // header || { segment || tag }: full segments while data follows, then a final one (gcm.rs:44-90)
+        const uint64_t S = e.gcm_seg_size, nseg = pos ? (pos + S - 1) / S : 1;
+        e.out_len = gcm::GCM_HEADER_LEN + pos + nseg * gcm::GCM_TAG_LEN;
+    } else
     e.out_len = e.encryption && e.cipher_mode == 0 ? hdr + (pos / 16 + 1) * 16 : hdr + pos;
     if (e.out_len > e.out_cap) { e.status = ST_NOSPACE; }
 }
@@ -419,6 +427,45 @@ __global__ void crc_clip_kernel(const CrcTileSrc* __restrict__ src, uint32_t n, 
     t.len = (uint32_t)len;
     t.span = s.span;
     tiles[i] = t;
+}
+
+// GCM: the segment / tile tables are sized from the compressed-length BOUND on the host; once the produced length is known
+// every slot is filled in (or marked unused) here, and slot 0 of an entry puts the stream header in front of its output.
+struct GcmSlot { uint32_t entry, j; };
+__global__ void gcm_enc_slots_kernel(const GcmSlot* __restrict__ slots, uint32_t n, const EncEntry* __restrict__ entries,
+                                     gcm::GcmSeg* __restrict__ gsegs, gcm::GcmTile* __restrict__ tiles, uint8_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GcmSlot sl = slots[i];
+    const EncEntry& e = entries[sl.entry];
+    const uint64_t S = e.gcm_seg_size;
+    const uint32_t tps = e.gcm_tiles_per_seg, t0 = e.gcm_tile_begin + sl.j * tps;
+    const uint64_t nseg = e.status != ST_OK ? 0 : e.comp_len ? (e.comp_len + S - 1) / S : 1;
+    gcm::GcmSeg g;
+    memset(&g, 0, sizeof g);
+    uint32_t used = 0;
+    if (sl.j >= nseg) g.ct_len = gcm::GCM_SEG_UNUSED;
+    else {
+        g.entry = sl.entry; g.pow_idx = e.gcm_pow_idx; g.key_idx = e.key_idx; g.enc = e.encryption;
+        uint8_t nonce[12];
+        for (int k = 0; k < 7; k++) nonce[k] = e.gcm_hdr[32 + k];
+        nonce[7] = (uint8_t)(sl.j >> 24); nonce[8] = (uint8_t)(sl.j >> 16); nonce[9] = (uint8_t)(sl.j >> 8); nonce[10] = (uint8_t)sl.j;
+        nonce[11] = sl.j + 1 == nseg ? 1 : 0;   // aead.rs:210-217
+        for (int k = 0; k < 3; k++) g.nonce[k] = load_le32(nonce + 4 * k);
+        g.src_seg_begin = e.piece_begin; g.src_n_segs = e.n_pieces; g.src_len = e.comp_len;
+        g.ct_pos = (uint64_t)sl.j * S;
+        g.ct_len = e.comp_len - g.ct_pos < S ? e.comp_len - g.ct_pos : S;
+        g.dst_off = e.out_off + gcm::GCM_HEADER_LEN + (uint64_t)sl.j * (S + gcm::GCM_TAG_LEN);
+        g.first_tile = t0;
+        const uint64_t nb = (g.ct_len + 15) / 16, head = nb % gcm::GCM_TILE_BLOCKS;
+        uint64_t b0 = 0;
+        if (head) { tiles[t0 + used++] = gcm::GcmTile{i, (uint32_t)head, 0}; b0 = head; }
+        for (; b0 < nb; b0 += gcm::GCM_TILE_BLOCKS) tiles[t0 + used++] = gcm::GcmTile{i, gcm::GCM_TILE_BLOCKS, b0};
+        g.n_tiles = used;
+        if (sl.j == 0) for (uint32_t k = 0; k < gcm::GCM_HEADER_LEN; k++) out[e.out_off + k] = e.gcm_hdr[k];
+    }
+    for (uint32_t t = used; t < tps; t++) tiles[t0 + t] = gcm::GcmTile{i, 0, 0};
+    gsegs[i] = g;
 }
 
 // host-side plan state (encode_host.cuh)

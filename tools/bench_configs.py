@@ -31,6 +31,10 @@ def _small(i_n):
     return corpus.make_file(10_000_000 + i, n)
 
 
+def _big(i):
+    return corpus.make_file(20_000_000 + i, 4 << 20)
+
+
 def oracle_encode(files, comp, level, enc, mode, key, threads, seed=7):
     import pna_oracle as O
     L = O.lib()
@@ -130,6 +134,7 @@ def main():
     ap.add_argument("--cfg5-files", type=int, default=32)
     ap.add_argument("--cfg1-files", type=int, default=2500)
     ap.add_argument("--io-files", type=int, default=256)
+    ap.add_argument("--gcm-files", type=int, default=256)
     ap.add_argument("--only", default="")
     ap.add_argument("--workers", type=int, default=2)
     ap.add_argument("--group-mib", type=int, default=64)
@@ -254,6 +259,63 @@ def main():
                               "path": "files on tmpfs -> pinned -> GPU zstd+AES-CTR -> archive file; archive file (mmap) -> GPU -> pinned windows -> files"}), flush=True)
         finally:
             shutil.rmtree(root, ignore_errors=True)
+
+    if args.only in ("", "gcm"):
+        # cfg2's entry shape under the GCM STREAM cipher mode: 4 MiB files, zstd 3 + AES-256-GCM, 1 MiB segments, one stream key
+        # per entry (aead.rs:188).  Kernel-only through one plan (stage times from CUDA events) and the CPU port beside it.
+        import pna_oracle as O
+        from concurrent.futures import ThreadPoolExecutor
+        n = args.gcm_files
+        with mp.get_context("fork").Pool(min(ncpu, 64)) as pool:
+            files = pool.map(_big, list(range(n)), chunksize=4)
+        keys = [bytes(np.random.Generator(np.random.PCG64(900 + i)).bytes(32)) for i in range(n)]
+
+        def enc_one(i):
+            hdr = bytes(np.random.Generator(np.random.PCG64(500 + i)).bytes(39)) + struct.pack(">I", 1 << 20) + bytes(32)
+            return O.gcm_encrypt_stream(1, keys[i], hdr, O.compress(2, files[i], 3))
+        with ThreadPoolExecutor(ncpu) as ex:
+            streams = list(ex.map(enc_one, range(n)))
+        U, Cb = sum(len(f) for f in files), sum(len(x) for x in streams)
+        img = ctx.pinned(Cb)
+        ents, pos = [], 0
+        for i, x in enumerate(streams):
+            img[pos:pos + len(x)] = np.frombuffer(x, dtype=np.uint8)
+            ents.append({"bodies": [img[pos:pos + len(x)]], "compression": 2, "encryption": 1, "cipher_mode": 2, "key": keys[i],
+                         "raw_size_hint": len(files[i])})
+            pos += len(x)
+        plan = ctx.decode_plan(ents)
+        for _ in range(4):
+            plan.run()
+        stage = plan.stage_ms()               # CUDA events of the last run, on the library's stream
+        dt = sum(stage.values()) * 1e-3
+        outs, st, _ = plan.fetch([len(f) for f in files])
+        assert list(st) == [0] * n
+        for k in range(0, n, max(1, n // 16)):
+            assert outs[k].tobytes() == files[k]
+        plan.close()
+        L = O.lib()
+        jobs = (O.Job * n)()
+        keep = []
+        for j in range(n):
+            o = C.create_string_buffer(len(files[j]))
+            keep.append(o)
+            jobs[j].stream = C.cast(C.c_char_p(streams[j]), C.c_void_p)
+            jobs[j].len = len(streams[j])
+            jobs[j].compression, jobs[j].encryption, jobs[j].cipher_mode = 2, 1, 2
+            C.memmove(jobs[j].key, keys[j], 32)
+            jobs[j].out = C.cast(o, C.c_void_p)
+            jobs[j].cap = len(files[j])
+        crc = (C.c_uint32 * n)()
+        L.pna_oracle_decode_batch_mt(jobs, n, ncpu, 1, crc)
+        t0 = time.perf_counter()
+        L.pna_oracle_decode_batch_mt(jobs, n, ncpu, 1, crc)
+        cpu_dt = time.perf_counter() - t0
+        assert all(jobs[j].status == 0 for j in range(n))
+        print(json.dumps({"config": "gcm", "files": n, "plain_bytes": U, "stream_bytes": Cb, "codec": "zstd-3 + aes-256-gcm (1 MiB segments)",
+                          "kernel_only_GBps": U / dt / 1e9, "kernel_only_ms": dt * 1e3, "stage_ms": stage,
+                          "gcm_stage_GBps_of_ciphertext": Cb / (stage.get("cipher", 0) * 1e-3 + 1e-12) / 1e9,
+                          "cpu_baseline_GBps": U / cpu_dt / 1e9, "cpu_cores": ncpu, "cpu_kind": "port (OpenSSL AES-256-GCM + libzstd)"}), flush=True)
+        del files, streams, img
 
     if args.only in ("", "cfg1"):
         n = args.cfg1_files
