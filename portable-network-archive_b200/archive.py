@@ -120,8 +120,9 @@ class WriteOptions:
     The KDF runs once per options object (options.rs:1239-1274)."""
 
     def __init__(self, compression=Compression.NO, level=-1, encryption=Encryption.NO, cipher_mode=CipherMode.CTR,
-                 password=None, hash_algorithm="pbkdf2-sha256", kdf_params=None, salt=None):
+                 password=None, hash_algorithm="pbkdf2-sha256", kdf_params=None, salt=None, segment_size=1 << 20):
         self.compression, self.level = compression, level
+        self.segment_size = segment_size     # GCM datastream segment size (options.rs:1200); unused by CBC/CTR
         self.encryption, self.cipher_mode = encryption, cipher_mode
         self.password = password.encode() if isinstance(password, str) else password
         self.phsf, self.key = None, None
@@ -484,6 +485,18 @@ class Archive:
         return bytes(out)
 
 
+def _cipher_fields(o: "WriteOptions", head_ty: bytes, header: bytes, iv) -> tuple[dict, int]:
+    """to_hashed (entry/write.rs:75-125): what the encode seam needs for this entry's cipher and the length of the stream
+    prefix that becomes its own chunk (builder.rs:62-69) -- the IV for CBC/CTR, the stream header for GCM, whose per-stream
+    key is bound to the header chunk (aead.rs:166-208)."""
+    if o.encryption == Encryption.NO:
+        return {"key": None, "iv": None}, 0
+    if o.cipher_mode == CipherMode.GCM:
+        sh = gcm_stream_header(o.key, os.urandom(32), os.urandom(7), o.segment_size)
+        return {"key": gcm_stream_key(o.key, sh, head_ty, header, o.phsf.encode()), "iv": None, "stream_header": sh}, GCM_STREAM_HEADER_LEN
+    return {"key": o.key, "iv": iv}, 16
+
+
 class BuiltEntry:
     """A NormalEntry / SolidEntry ready to be written: header, metadata chunks, PHSF and data bodies."""
 
@@ -535,10 +548,15 @@ class FileEntryBuilder:
     def plain(self) -> bytes:
         return b"".join(self._parts)
 
+    def header_bytes(self) -> bytes:
+        o = self.options
+        return bytes([0, 0, self.data_kind, o.compression, o.encryption, o.cipher_mode]) + self.name.encode()
+
     def _encode_desc(self, max_chunk_size=0):
         o = self.options
-        return {"plain": self.plain(), "compression": o.compression, "level": o.level, "encryption": o.encryption,
-                "cipher_mode": o.cipher_mode, "key": o.key, "iv": self.iv, "max_chunk_size": max_chunk_size}
+        fields, self._prefix_len = _cipher_fields(o, ChunkType.FHED, self.header_bytes(), self.iv)
+        return dict({"plain": self.plain(), "compression": o.compression, "level": o.level, "encryption": o.encryption,
+                     "cipher_mode": o.cipher_mode, "max_chunk_size": max_chunk_size}, **fields)
 
     def build(self, ctx=None, max_chunk_size: int = 0) -> BuiltEntry:
         return EntryBuilder.build_many([self], ctx, max_chunk_size)[0]
@@ -557,10 +575,10 @@ class EntryBuilder:
             if code != _ffi.OK:
                 raise PnaError(code, f"{b.name}: encode failed")
             o = b.options
-            header = bytes([0, 0, b.data_kind, o.compression, o.encryption, o.cipher_mode]) + b.name.encode()
+            header = b.header_bytes()
             size = len(b.plain())
             extra = [(ChunkType.fSIZ, size.to_bytes(16, "big").lstrip(b"\0"))]   # entry.rs:901-903 minimal BE
-            iv_len = 16 if o.encryption != Encryption.NO else 0
+            iv_len = b._prefix_len
             # encode kernels return CRCs for the bodies after the IV when max_chunk_size matches the writer's
             out.append(BuiltEntry(ChunkType.FHED, header, extra, o.phsf, ChunkType.FDAT, bytes(s), ChunkType.FEND,
                                   c if len(c) else None, iv_len))
@@ -596,13 +614,12 @@ class SolidEntryBuilder:
         for ty, data, crc in a._pending:
             inner += struct.pack(">I", len(data)) + ty + bytes(data) + struct.pack(">I", crc)
         o = self.options
-        streams, _, st = self._ctx.encode_batch([{"plain": bytes(inner), "compression": o.compression, "level": o.level,
-                                                  "encryption": o.encryption, "cipher_mode": o.cipher_mode,
-                                                  "key": o.key, "iv": self.iv}])
+        header = bytes([0, 0, o.compression, o.encryption, o.cipher_mode])
+        fields, iv_len = _cipher_fields(o, ChunkType.SHED, header, self.iv)
+        streams, _, st = self._ctx.encode_batch([dict({"plain": bytes(inner), "compression": o.compression, "level": o.level,
+                                                       "encryption": o.encryption, "cipher_mode": o.cipher_mode}, **fields)])
         if st[0] != _ffi.OK:
             raise PnaError(st[0], "solid encode failed")
-        header = bytes([0, 0, o.compression, o.encryption, o.cipher_mode])
-        iv_len = 16 if o.encryption != Encryption.NO else 0
         be = BuiltEntry(ChunkType.SHED, header, [], o.phsf, ChunkType.SDAT, bytes(streams[0]), ChunkType.SEND, None, iv_len)
         be._sdat = sdat_size
         return be
