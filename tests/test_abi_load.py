@@ -35,7 +35,7 @@ def test_struct_layout(pna):
     from importlib import import_module
     ffi = import_module("portable-network-archive_b200._ffi")
     assert C.sizeof(ffi.Span) == 16 and C.sizeof(ffi.Buf) == 24
-    assert C.sizeof(ffi.DecodeDesc) == 8 + 4 + 4 + 32 + 8 and C.sizeof(ffi.EncodeDesc) == 16 + 4 + 4 + 32 + 16 + 4 + 4
+    assert C.sizeof(ffi.DecodeDesc) == 8 + 4 + 4 + 32 + 8 and C.sizeof(ffi.EncodeDesc) == 16 + 4 + 4 + 32 + 16 + 4 + 4 + 8   # + stream_header pointer (GCM)
 
 
 def test_index_pass_on_golden(pna, golden):
