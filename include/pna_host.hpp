@@ -135,11 +135,15 @@ struct WriteOptions {    // options.rs:1035
     int32_t level = -1;
     uint8_t key[32] = {0};
     std::string phsf;    // recorded in the PHSF chunk when encryption != 0
+    uint32_t segment_size = 1u << 20;   // GCM datastream segment size (options.rs:1200); unused by CBC/CTR
 };
 struct FileEntryBuilder {   // builder/file.rs:41: plaintext is borrowed until Archive::create returns
     std::string name;
     pna_span data{nullptr, 0};
     uint8_t iv[16] = {0};   // caller-drawn (entry/write.rs:108-111)
+    // GCM: salt and nonce prefix of the stream header (entry/write.rs:81-85); drawn by the writer when left all-zero
+    uint8_t gcm_salt[32] = {0};
+    uint8_t gcm_nonce_prefix[7] = {0};
 };
 // Archive::write_header + add_entry per file + finalize, with one GPU encode batch per worker group.
 std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,

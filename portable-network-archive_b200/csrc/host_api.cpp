@@ -622,7 +622,21 @@ static inline void wr_be32(uint8_t* p, uint32_t x) { p[0] = x >> 24; p[1] = x >>
 static uint64_t entry_frame_bound(const std::string& name, uint64_t stream_bound, const std::string& phsf, bool enc, uint32_t mcs) {
     const uint64_t cap = mcs ? mcs : 0xFFFFFFFFull;
     const uint64_t nbody = stream_bound / cap + 2;
-    return 12 + 6 + name.size() + 12 + 16 + (enc ? 12 + phsf.size() + 12 + 16 : 0) + nbody * 12 + stream_bound + 12;
+    // prefix chunk: 16 (IV) or 75 (GCM stream header); the GCM tags of callers that sized the stream for CBC/CTR fit in the
+    // last term for segments of 64 KiB and more
+    return 12 + 6 + name.size() + 12 + 16 + (enc ? 12 + phsf.size() + 12 + 75 : 0) + nbody * 12 + stream_bound + 12 + (enc ? 64 + (stream_bound >> 12) : 0);
+}
+
+// upper bound of one entry's data stream under `opt` (GCM: header + one tag per segment)
+static uint64_t stream_bound_of(uint64_t plain_len, const WriteOptions& opt) {
+    pna_encode_desc d;
+    memset(&d, 0, sizeof d);
+    uint8_t hdr[75] = {0};
+    hdr[39] = (uint8_t)(opt.segment_size >> 24); hdr[40] = (uint8_t)(opt.segment_size >> 16);
+    hdr[41] = (uint8_t)(opt.segment_size >> 8); hdr[42] = (uint8_t)opt.segment_size;
+    d.plain.len = plain_len; d.compression = opt.compression; d.encryption = opt.encryption; d.cipher_mode = opt.cipher_mode;
+    d.stream_header = hdr;
+    return pna_cuda_encode_bound(&d);
 }
 
 // Archive::write_header + add_entry per file + finalize (archive/write.rs:92,368,545; wire order entry.rs:895-912), written
@@ -643,7 +657,12 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
         if (lo < n) groups.push_back({lo, n});
     }
     const bool enc = opt.encryption != PNA_ENCRYPTION_NO;
-    const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull, iv_len = enc ? 16 : 0;
+    const bool gcm = enc && opt.cipher_mode == PNA_CIPHER_GCM;
+    const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull, iv_len = enc ? (gcm ? 75 : 16) : 0;   // stream prefix = its own chunk
+    // GCM (entry/write.rs:75-106): per entry a stream header (salt, nonce prefix, segment size, key confirmation) and a stream key
+    // bound to the entry's FHED chunk -- host work, once per entry, through the library's key schedule
+    std::vector<std::array<uint8_t, 75>> gcm_hdr(gcm ? n : 0);
+    std::vector<std::array<uint8_t, 32>> gcm_key(gcm ? n : 0);
     if (cap < 8 + 20 + 12) throw Error(PNA_E_NOSPACE, "archive buffer too small");
     memcpy(out, SIGNATURE, 8);
     // ---- metadata chunks (type || data, contiguous) of EVERY entry plus AHED / AEND, CRCs in one GPU batch up front: the
@@ -672,6 +691,27 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
         add_meta("fSIZ", sz + skip, (uint32_t)(8 - skip));
         if (enc) {
             add_meta("PHSF", (const uint8_t*)opt.phsf.data(), (uint32_t)opt.phsf.size());
+            if (gcm) {
+                uint8_t salt[32], prefix[7];
+                memcpy(salt, f.gcm_salt, 32); memcpy(prefix, f.gcm_nonce_prefix, 7);
+                bool drawn = false;
+                for (uint8_t b : salt) drawn = drawn || b;
+                if (!drawn) {
+                    static thread_local std::random_device rd;
+                    for (int k = 0; k < 32; k += 4) { const uint32_t r = rd(); memcpy(salt + k, &r, 4); }
+                    const uint32_t r0 = rd(), r1 = rd();
+                    memcpy(prefix, &r0, 4); memcpy(prefix + 4, &r1, 3);
+                }
+                int32_t rc = pna_cuda_gcm_stream_header(opt.key, salt, prefix, opt.segment_size, gcm_hdr[i].data());
+                if (rc == PNA_OK) {
+                    std::vector<uint8_t> hd(h6, h6 + 6);
+                    hd.insert(hd.end(), f.name.begin(), f.name.end());
+                    rc = pna_cuda_gcm_stream_key(opt.key, gcm_hdr[i].data(), 75, (const uint8_t*)"FHED", hd.data(), hd.size(),
+                                                 (const uint8_t*)opt.phsf.data(), opt.phsf.size(), gcm_key[i].data());
+                }
+                if (rc != PNA_OK) throw Error(rc, f.name + ": GCM stream parameters");
+                add_meta("FDAT", gcm_hdr[i].data(), 75);                // the stream header is its own chunk, like the IV
+            } else
             add_meta("FDAT", f.iv, 16);                                 // the IV is its own chunk (builder.rs:62-69)
         }
         add_meta("FEND", nullptr, 0);
@@ -725,6 +765,7 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
             d.plain = f.data;
             d.compression = opt.compression; d.encryption = opt.encryption; d.cipher_mode = opt.cipher_mode; d.level = opt.level;
             memcpy(d.key, opt.key, 32); memcpy(d.iv, f.iv, 16);
+            if (gcm) { memcpy(d.key, gcm_key[G.lo + k].data(), 32); d.stream_header = gcm_hdr[G.lo + k].data(); }
             d.max_chunk_size = max_chunk_size;
             S.crc_total += pna_cuda_encode_crc_count(&d);
         }
@@ -868,7 +909,7 @@ std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, 
         pna_encode_desc d;
         memset(&d, 0, sizeof d);
         d.plain.len = f.data.len; d.compression = opt.compression; d.encryption = opt.encryption;
-        bound += entry_frame_bound(f.name, pna_cuda_encode_bound(&d), opt.phsf, opt.encryption != 0, max_chunk_size);
+        bound += entry_frame_bound(f.name, stream_bound_of(f.data.len, opt), opt.phsf, opt.encryption != 0, max_chunk_size);
     }
     std::vector<uint8_t> out(bound);
     out.resize(create_archive_into(files, opt, max_chunk_size, device, workers, group_bytes, out.data(), out.size()));
@@ -1064,7 +1105,7 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
         pna_encode_desc d;
         memset(&d, 0, sizeof d);
         d.plain.len = sizes[i]; d.compression = opt.compression; d.encryption = opt.encryption;
-        bound += entry_frame_bound(files[i].name, pna_cuda_encode_bound(&d), opt.phsf, opt.encryption != 0, max_chunk_size);
+        bound += entry_frame_bound(files[i].name, stream_bound_of(sizes[i], opt), opt.phsf, opt.encryption != 0, max_chunk_size);
         st.bytes += sizes[i];
     }
     PinnedBuf arch_buf(L.ctx, bound + 64);

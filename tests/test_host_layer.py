@@ -166,7 +166,7 @@ def test_broken_chunk_detected_by_cpp_host(host, pna, ctx, golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("comp,enc,mode", [(2, 1, 1), (1, 2, 0), (0, 0, 0), (2, 0, 0)])
+@pytest.mark.parametrize("comp,enc,mode", [(2, 1, 1), (1, 2, 0), (0, 0, 0), (2, 0, 0), (2, 1, 2), (1, 2, 2)])
 def test_create_with_cpp_host_is_reference_readable(host, pna, ctx, oracle, comp, enc, mode):
     """create path end to end (FileEntryBuilder -> add_entry -> finalize in C++): the oracle's restatement of the reference
     reader must list and extract the same files; then our own C++ reader too (cli/tests/cli/encrypt.rs round trip)."""
@@ -189,7 +189,8 @@ def test_extract_to_dir_and_create_from_files(host, pna, ctx, oracle, golden, tm
     a directory through an mmap equal the reference's raw files; a directory packed by create_from_files is read back by the
     oracle's restatement of the reference reader and by extract_to_dir again (cli/tests/cli/encrypt.rs round trip shape).
     Small windows force several decode / write rounds."""
-    for name in ("zstd.pna", "deflate.pna", "zstd_aes_ctr.pna", "solid_zstd.pna", "zstd_keep_all.pna"):
+    for name in ("zstd.pna", "deflate.pna", "zstd_aes_ctr.pna", "solid_zstd.pna", "zstd_keep_all.pna", "zstd_camellia_gcm.pna",
+                 "solid_zstd_aes_gcm.pna"):
         info = golden["archives"][name]
         a = host.HostArchive.open_file(os.path.join(golden["dir"], info["file"]))
         for phsf, key in info["keys"].items():
