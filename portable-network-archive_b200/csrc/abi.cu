@@ -225,6 +225,8 @@ struct pna_plan {
     DevArr<uint32_t> d_deflate, d_seq_order, d_lit_order, d_counts, d_lz_order;
     DevArr<zs::SeqRec> d_seqs;
     DevArr<zs::ZEntry> d_ze;
+    DevArr<zs::LzUnit> d_lz_units;   // one per frame
+    uint32_t n_lz_units = 0;
     DevArr<zs::ZBlock> d_blocks;
     DevArr<uint64_t> d_lit_base, d_seq_base;
     DevArr<inf::InfStream> d_inf;
@@ -258,7 +260,7 @@ struct pna_plan {
         d_segs.release(); d_keys.release();
         d_gcm_segs.release(); d_gcm_tiles.release(); d_gcm_refs.release(); d_gcm_pows.release(); d_gcm_partial.release();
         for (auto& t : d_tiles) t.release();
-        d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_ze.release(); d_blocks.release();
+        d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_lz_units.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
         d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release();
         if (enc) enc::destroy(enc);
@@ -837,8 +839,8 @@ static int launch_zstd_prefix(pna_plan* P) {
     LAUNCHED();
     return PNA_OK;
 }
-static int launch_zstd_lz_on(pna_plan* P, const zs::ZEntry* ze, const uint32_t* order, uint32_t nz, const zs::ZBlock* blocks,
-                             const uint8_t* lits, const zs::SeqRec* seqs) {
+static int launch_zstd_lz_on(pna_plan* P, const zs::ZEntry* ze, const uint32_t* order, const zs::LzUnit* units, uint32_t nz,
+                             const zs::ZBlock* blocks, const uint8_t* lits, const zs::SeqRec* seqs) {
     pna_ctx* ctx = P->ctx;
     if (!nz) return PNA_OK;
     // one CTA per entry, longest streams first.  Fewer entries than half the SMs (a solid archive is ONE frame): the
@@ -846,10 +848,10 @@ static int launch_zstd_lz_on(pna_plan* P, const zs::ZEntry* ze, const uint32_t* 
     const char* force = getenv("PNA_LZ_VARIANT");
     const bool big = force ? force[0] == 'b' : nz * 2 <= (uint32_t)ctx->sm_count;
     if (big)
-        zs::zstd_lz_kernel<zs::LzBig><<<nz, zs::LzBig::T, zs::LzBig::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, ze, order, nz, blocks, lits,
+        zs::zstd_lz_kernel<zs::LzBig><<<nz, zs::LzBig::T, zs::LzBig::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, ze, order, units, nz, blocks, lits,
                                                                                             seqs, P->d_out.p);
     else
-        zs::zstd_lz_kernel<zs::LzSmall><<<nz, zs::LzSmall::T, zs::LzSmall::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, ze, order, nz, blocks,
+        zs::zstd_lz_kernel<zs::LzSmall><<<nz, zs::LzSmall::T, zs::LzSmall::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, ze, order, units, nz, blocks,
                                                                                                 lits, seqs, P->d_out.p);
     LAUNCHED();
     return PNA_OK;
@@ -876,7 +878,7 @@ static int launch_inflate(pna_plan* P, int size_only) {
         inf::inflate_tokens_kernel<<<(ni + inf::TOKEN_CTA - 1) / inf::TOKEN_CTA, inf::TOKEN_CTA, inf::TOKEN_SMEM_BYTES, ctx->stream>>>(
             P->d_buf.p, P->d_entries.p, P->d_inf.p, ni, P->d_inf_lits.p, P->d_inf_recs.p, P->d_inf_blocks.p, P->d_inf_ze.p, P->d_inf_tr.p, 0);
         LAUNCHED();
-        int rc = launch_zstd_lz_on(P, P->d_inf_ze.p, nullptr, ni, P->d_inf_blocks.p, P->d_inf_lits.p, P->d_inf_recs.p);
+        int rc = launch_zstd_lz_on(P, P->d_inf_ze.p, nullptr, nullptr, ni, P->d_inf_blocks.p, P->d_inf_lits.p, P->d_inf_recs.p);
         if (rc) return rc;
         inf::inflate_adler_kernel<<<(ni + 7) / 8, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_inf.p, P->d_inf_tr.p, ni, P->d_out.p);
         LAUNCHED();
@@ -889,7 +891,7 @@ static int launch_inflate(pna_plan* P, int size_only) {
     return PNA_OK;
 }
 static int launch_zstd_lz(pna_plan* P) {
-    return launch_zstd_lz_on(P, P->d_ze.p, P->d_lz_order.p, (uint32_t)P->h_ze.size(), P->d_blocks.p, P->d_lits.p, P->d_seqs.p);
+    return launch_zstd_lz_on(P, P->d_ze.p, P->d_lz_order.p, P->d_lz_units.p, P->n_lz_units, P->d_blocks.p, P->d_lits.p, P->d_seqs.p);
 }
 static int launch_store(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
@@ -918,8 +920,6 @@ static int decode_prepare(pna_plan* P) {
         for (uint32_t i = 0; i < nz; i++) lz_order[i] = i;
         std::stable_sort(lz_order.begin(), lz_order.end(), [&](uint32_t a, uint32_t b) {
             return P->h_entries[P->h_ze[a].entry].comp_len > P->h_entries[P->h_ze[b].entry].comp_len; });
-        CK(P->d_lz_order.reserve(nz));
-        CK(cudaMemcpyAsync(P->d_lz_order.p, lz_order.data(), nz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = launch_zstd_front(P, true))) return rc;
         CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -933,13 +933,23 @@ static int decode_prepare(pna_plan* P) {
         if ((rc = launch_zstd_front(P, false))) return rc;
         CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        uint64_t lit = 0, seq = 0;
+        uint64_t lit = 0, seq = 0, nu = 0;
         std::vector<uint64_t> lb(P->n, 0), sb(P->n, 0);
         for (auto& z : P->h_ze) {
             z.lit_base = lit; z.seq_base = seq;
             lb[z.entry] = lit; sb[z.entry] = seq;
             lit += z.lit_total; seq += z.seq_total;
+            z.unit_begin = (uint32_t)nu; nu += z.n_frames;
         }
+        if (nu > 0xFFFFFFF0ull) return PNA_E_OOM;
+        // LZ units = frames; dispatched entry by entry in the longest-stream-first order, an entry's frames in stream order
+        P->n_lz_units = (uint32_t)nu;
+        std::vector<uint32_t> unit_order;
+        unit_order.reserve(nu);
+        for (uint32_t zi : lz_order)
+            for (uint32_t f = 0; f < P->h_ze[zi].n_frames; f++) unit_order.push_back(P->h_ze[zi].unit_begin + f);
+        CK(P->d_lz_order.reserve(nu + 1)); CK(P->d_lz_units.reserve(nu + 1));
+        if (nu) CK(cudaMemcpyAsync(P->d_lz_order.p, unit_order.data(), nu * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         P->lit_total = lit; P->seq_total = seq;
         CK(P->d_lits.reserve(lit + 256));
         CK(P->d_seqs.reserve(seq + 32));
@@ -947,7 +957,9 @@ static int decode_prepare(pna_plan* P) {
         CK(cudaMemcpyAsync(P->d_lit_base.p, lb.data(), P->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(P->d_seq_base.p, sb.data(), P->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // lb/sb are locals
+        zs::zstd_units_kernel<<<(nz + 127) / 128, 128, 0, ctx->stream>>>(P->d_ze.p, nz, P->d_blocks.p, P->d_lz_units.p);
+        LAUNCHED();
+        CK(cudaStreamSynchronize(ctx->stream));   // lb/sb/unit_order are locals
     }
     if (P->need_sizing) {
         // exact sizes: zstd from the entropy+prefix stages, deflate from a count-only pass, store = comp_len

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(TOKEN_CTA) inflate_tokens_kernel(const uint8_t
     EntryRec& e = entries[s.entry];
     if (in_range && !size_only) {
         zs::ZEntry z;
-        z.entry = s.entry; z.blk_begin = i; z.blk_count = 0; z._pad = 0;
+        z.entry = s.entry; z.blk_begin = i; z.blk_count = 0; z.n_frames = 1; z.unit_begin = 0; z._pad = 0;
         z.lit_base = s.lit_off; z.seq_base = s.rec_off; z.lit_total = 0; z.seq_total = 0;
         ze[i] = z;
     }

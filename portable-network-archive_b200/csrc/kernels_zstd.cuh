@@ -58,11 +58,13 @@ __global__ void zstd_resolve_kernel(EntryRec* entries, ZEntry* ze, uint32_t nz, 
     if (i >= nz) return;
     ZEntry z = ze[i];
     uint64_t lit = 0, seq = 0;
+    uint32_t nf = 0;
     if (entries[z.entry].status == ST_OK) {
         int32_t st = resolve_sources(blocks, z.blk_begin, z.blk_count);
         set_status(entries, z.entry, st);
         for (uint32_t k = z.blk_begin; k < z.blk_begin + z.blk_count; k++) {
             ZBlock& b = blocks[k];
+            nf += b.first_in_frame;
             b.lit_off = lit;   // relative to the entry's bases
             b.seq_off = seq;
             if (b.type == BT_COMPRESSED) {
@@ -73,6 +75,19 @@ __global__ void zstd_resolve_kernel(EntryRec* entries, ZEntry* ze, uint32_t nz, 
     }
     ze[i].lit_total = lit;
     ze[i].seq_total = seq;
+    ze[i].n_frames = nf;
+}
+// LZ units of every entry: one per frame, in stream order, at the entry's slots (ZEntry.unit_begin from the host)
+__global__ void zstd_units_kernel(const ZEntry* __restrict__ ze, uint32_t nz, const ZBlock* __restrict__ blocks, LzUnit* __restrict__ units) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nz) return;
+    const ZEntry z = ze[i];
+    const uint32_t u = z.unit_begin;
+    uint32_t made = 0;
+    for (uint32_t k = z.blk_begin; k < z.blk_begin + z.blk_count; k++) {
+        if (blocks[k].first_in_frame && made < z.n_frames) { units[u + made] = LzUnit{i, k, 0u, 0u}; made++; }
+        if (made) units[u + made - 1].blk_count++;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,12 +36,18 @@ struct ZEntry {          // per zstd entry, device resident
     uint32_t entry;      // index into EntryRec[]
     uint32_t blk_begin;  // first ZBlock
     uint32_t blk_count;
-    uint32_t _pad;
+    uint32_t n_frames;   // device-written by zstd_resolve: frames that own at least one block
     uint64_t lit_base;   // literal arena base of this entry
     uint64_t seq_base;   // sequence array base
     uint64_t lit_total;  // device-written by zstd_resolve
     uint64_t seq_total;
+    uint32_t unit_begin; // first LzUnit of this entry (host prefix sum of n_frames)
+    uint32_t _pad;
 };
+// One unit of the LZ stage = one FRAME: matches never reach across a frame start, so the frames of a stream that is a
+// concatenation of frames (what this library's own writer emits for long entries, and any multi-frame zstd stream) are
+// executed by different CTAs.  A reference-written entry is one frame = one unit.
+struct LzUnit { uint32_t ze, blk_begin, blk_count, _pad; };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -113,6 +119,7 @@ __device__ __forceinline__ void fill_codes(Code* ix, uint32_t n, uint32_t code) 
 template <class C>
 __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* __restrict__ buf, EntryRec* entries,
                                                                const ZEntry* __restrict__ ze, const uint32_t* __restrict__ order,
+                                                               const LzUnit* __restrict__ units /* null: one unit per ZEntry */,
                                                                uint32_t nz, const ZBlock* __restrict__ blocks,
                                                                const uint8_t* __restrict__ lits, const SeqRec* __restrict__ seqs,
                                                                uint8_t* out) {
@@ -130,17 +137,24 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
     uint32_t* const wstop = misc + 16;
 
     if (blockIdx.x >= nz) return;
-    const ZEntry z = ze[order ? order[blockIdx.x] : blockIdx.x];
+    const uint32_t ui = order ? order[blockIdx.x] : blockIdx.x;
+    const LzUnit unit = units ? units[ui] : LzUnit{ui, 0u, 0u, 0u};
+    const ZEntry z = ze[unit.ze];
+    const uint32_t blk_first = units ? unit.blk_begin : z.blk_begin, blk_n = units ? unit.blk_count : z.blk_count;
     EntryRec& er = entries[z.entry];
     if (er.status != ST_OK) return;
     if (er.out_len > er.out_cap) { if (tid == 0) atomicCAS(&er.status, ST_OK, ST_NOSPACE); return; }
     // Positions are 32-bit and relative to the start of the CURRENT block (oblk = its place in HBM); they are rebased
     // at every block, so the window start and the flush mark may be negative.  oblk + bpos and oblk + flushed stay
     // multiples of 16 in the (16-byte aligned) entry.
-    uint8_t* oblk = out + er.out_off;
-    int32_t bpos = 0;       // position of win[0]
-    int32_t cur = 0;        // position of the next output byte
-    int32_t flushed = 0;    // HBM holds everything below
+    // A unit that is not the first frame of its entry starts at any byte: the window then begins `skip` bytes before it (at
+    // the 16-byte boundary below), and those bytes -- another CTA's -- are never written.
+    const uint64_t unit_off = (units && blk_n) ? blocks[blk_first].out_off : 0;
+    uint32_t skip = (uint32_t)(unit_off & 15u);
+    uint8_t* oblk = out + er.out_off + (unit_off - skip);
+    int32_t bpos = 0;             // position of win[0]
+    int32_t cur = (int32_t)skip;  // position of the next output byte
+    int32_t flushed = 0;          // HBM holds everything below
 
     // ---- whole-CTA helpers; every one is called under uniform control flow
     // finished 512-byte rows -> HBM (rows distributed over the warps).  force: also the 16-byte groups and the byte
@@ -152,9 +166,11 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
             uint8_t* const g = oblk + (int64_t)flushed;
             for (uint32_t r = warp; r < nrows; r += C::W) {
                 const uint4 v = *reinterpret_cast<const uint4*>(win + w0 + (r << 9) + 16 * lane);
-                *reinterpret_cast<uint4*>(g + (r << 9) + 16 * lane) = v;
+                if (skip && r == 0 && lane == 0) { for (uint32_t q = skip; q < 16; q++) g[q] = win[w0 + q]; }
+                else *reinterpret_cast<uint4*>(g + (r << 9) + 16 * lane) = v;
             }
             flushed += (int32_t)(nrows << 9);
+            skip = 0;
         }
         if (force && flushed < cur) {
             const uint32_t n = (uint32_t)(cur - flushed);   // < 512
@@ -163,11 +179,13 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
                 uint8_t* const g = oblk + (int64_t)flushed;
                 if (16u * lane + 16u <= n) {
                     const uint4 v = *reinterpret_cast<const uint4*>(win + w0 + 16 * lane);
-                    *reinterpret_cast<uint4*>(g + 16 * lane) = v;
+                    if (skip && lane == 0) { for (uint32_t q = skip; q < 16; q++) g[q] = win[w0 + q]; }
+                    else *reinterpret_cast<uint4*>(g + 16 * lane) = v;
                 }
                 const uint32_t full = n & ~15u;
-                if (full + lane < n) g[full + lane] = win[w0 + full + lane];
+                if (full + lane < n && full + lane >= (full ? 0u : skip)) g[full + lane] = win[w0 + full + lane];
             }
+            if (n & ~15u) skip = 0;
             flushed += (int32_t)(n & ~15u);
         }
     };
@@ -243,7 +261,7 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
     };
 
     int32_t fail = ST_OK;
-    for (uint32_t k = z.blk_begin; k < z.blk_begin + z.blk_count && fail == ST_OK; k++) {
+    for (uint32_t k = blk_first; k < blk_first + blk_n && fail == ST_OK; k++) {
         const ZBlock& b = blocks[k];
         // the prefix pass laid the blocks out back to back: this block starts where the previous one ended.  Rebase.
         oblk += cur; bpos -= cur; flushed -= cur; cur = 0;

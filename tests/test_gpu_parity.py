@@ -406,3 +406,45 @@ def test_inflate_token_path_errors(ctx, oracle, pna):
     assert outs[2].tobytes() == want_cut
     outs, st, lens = ctx.decode_batch(ents[:1], caps=[1000])
     assert st == [pna.E_NOSPACE] and int(lens[0]) == len(plain)
+
+
+@pytest.mark.gpu
+def test_zstd_multi_frame_streams_run_one_lz_unit_per_frame(ctx, oracle):
+    """A stream that is a concatenation of frames (zstd::Decoder reads them all, entry/read.rs:181; what this library's own
+    writer emits for long entries): every frame is its own unit of the LZ stage and starts at any byte of the output.  Frame
+    sizes around the 16-byte row and the 512-byte flush granularity, empty frames, a skippable frame, many frames per entry."""
+    import struct
+    rnd = random.Random(11)
+    entries, want = [], []
+    shapes = [[1, 1, 1], [17, 1000, 5], [70_000, 200_000, 3, 0, 131_072], [511, 513, 15, 16, 1_000_000],
+              [rnd.randrange(1, 3000) for _ in range(200)], [0, 0, 7], [300_000] * 6]
+    for si, sizes in enumerate(shapes):
+        for enc, mode in ((0, 0), (1, 1)):
+            parts = [corpus.make_file(4000 + 31 * si + j, n) for j, n in enumerate(sizes)]
+            frames = [oracle.compress(2, p, 3) for p in parts]
+            if si == 2:
+                frames.insert(2, struct.pack("<II", 0x184D2A53, 5) + b"hello")     # skippable frame between data frames
+            body = b"".join(frames)
+            key = os.urandom(32)
+            if enc:
+                iv = os.urandom(16)
+                body = iv + oracle.ctr(enc, key, iv, body)
+            plain = b"".join(parts)
+            assert oracle.decode_stream(body, 2, enc, mode, key) == plain           # the reference pipeline agrees
+            entries.append({"bodies": [body], "compression": 2, "encryption": enc, "cipher_mode": mode, "key": key,
+                            "raw_size_hint": len(plain) if si % 2 else None})
+            want.append(plain)
+    outs, st, lens = ctx.decode_batch(entries)
+    assert st == [0] * len(entries)
+    for o, w in zip(outs, want):
+        assert o.tobytes() == w
+    # a corrupt later frame fails the entry, not its neighbours
+    bad = bytearray(entries[6]["bodies"][0])
+    bad[len(bad) - 40] ^= 0x55
+    outs, st, _ = ctx.decode_batch([entries[0], dict(entries[6], bodies=[bytes(bad)]), entries[2]])
+    assert st[0] == 0 and st[2] == 0 and outs[0].tobytes() == want[0] and outs[2].tobytes() == want[2]
+    try:   # no frame checksum: libzstd may accept the flipped byte; then both must produce the same bytes
+        ref = oracle.decode_stream(bytes(bad), 2, 0, 0, None)
+        assert st[1] == 0 and outs[1].tobytes() == ref
+    except oracle.OracleError:
+        assert st[1] != 0
