@@ -54,7 +54,7 @@ using pna::enc::EncEntry;
 static uint64_t enc_nsegs(uint64_t len) { return (len + enc::SEG - 1) / enc::SEG; }
 // upper bound of the compressed stream (before IV / padding): raw-block / stored-block fallbacks bound every segment
 static uint64_t enc_comp_bound(uint8_t compression, uint64_t len) {
-    if (compression == PNA_COMPRESSION_ZSTD) return len + 3 * enc_nsegs(len) + 9;
+    if (compression == PNA_COMPRESSION_ZSTD) return len + 3 * enc_nsegs(len) + 9 + 6 * (enc_nsegs(len) / enc::FRAME_SEGS + 1);
     if (compression == PNA_COMPRESSION_DEFLATE) return len + 5 * enc_nsegs(len) + 8;
     return len;
 }
@@ -159,10 +159,10 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
             s.seq_off = (uint64_t)(e.seg_begin + k) * enc::SEG_SEQ_MAX;
             s.len = (uint32_t)std::min<uint64_t>(enc::SEG, e.plain_len - (uint64_t)k * enc::SEG);
             s.entry = i;
-            s.last = k + 1 == e.n_segs;
+            s.last = k + 1 == e.n_segs || (e.compression == PNA_COMPRESSION_ZSTD && (k + 1) % enc::FRAME_SEGS == 0);   // Last_Block of its frame
             s.adler = e.compression == PNA_COMPRESSION_DEFLATE;
         }
-        piece_cur += 3 + 3 * (uint64_t)e.n_segs;
+        piece_cur += 4 + 3 * (uint64_t)e.n_segs + e.n_segs / enc::FRAME_SEGS;
         const uint64_t bound = pna_cuda_encode_bound(&d);
         e.out_cap = bound;
         out_cur += align_up(bound, 16) + 16;

@@ -32,6 +32,10 @@ struct SegRec {            // one segment (host fills the first group, kernels t
     uint64_t adler_a, adler_b;     // sum of bytes, sum of (len - k) * byte_k
 };
 constexpr uint32_t TMP_HEAD = 16;
+// zstd: a new FRAME every FRAME_SEGS segments (1 MiB of input).  Blocks never reference earlier blocks here, so the split costs
+// 6 bytes per MiB and nothing else; a reader that executes matches frame by frame (ours: one LZ unit per frame) gets
+// parallelism inside long entries and solid streams, and zstd::Decoder reads concatenated frames (lib/src/entry/read.rs:181).
+constexpr uint32_t FRAME_SEGS = 32;
 constexpr uint32_t TMP_SEG = TMP_HEAD + SEG + SEG / 8 + 112;   // 36992: head + worst fixed-Huffman body, multiple of 16
 
 struct EncEntry {
@@ -266,9 +270,9 @@ __global__ void enc_layout_kernel(uint8_t* __restrict__ work, const SegRec* __re
     else if (e.compression == 2) {
         h[0] = 0x28; h[1] = 0xB5; h[2] = 0x2F; h[3] = 0xFD; h[4] = 0x00; h[5] = 0x38;
         if (e.n_segs == 0) { zstd_block_header(1, 0, 0, h + 6); add(e.hdr_off, 9); }
-        else add(e.hdr_off, 6);
         for (uint32_t k = e.seg_begin; k < e.seg_begin + e.n_segs; k++) {
             const SegRec& s = segs[k];
+            if ((k - e.seg_begin) % FRAME_SEGS == 0) add(e.hdr_off, 6);   // frame header (the same six bytes every time)
             add(s.tmp_off, s.head_len);
             if (s.raw) add(s.plain_off, s.len);
             else { add(s.litp_off, s.litp_len); add(s.tmp_off + TMP_HEAD + s.tail_off, s.tail_len); }
