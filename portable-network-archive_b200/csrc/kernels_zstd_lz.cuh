@@ -138,39 +138,58 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
 
     if (blockIdx.x >= nz) return;
     const uint32_t ui = order ? order[blockIdx.x] : blockIdx.x;
-    const LzUnit unit = units ? units[ui] : LzUnit{ui, 0u, 0u, 0u};
-    const ZEntry z = ze[unit.ze];
-    const uint32_t blk_first = units ? unit.blk_begin : z.blk_begin, blk_n = units ? unit.blk_count : z.blk_count;
-    EntryRec& er = entries[z.entry];
+    uint32_t zi = ui, blk_first = 0, blk_end = 0;
+    if (units) { const LzUnit unit = units[ui]; zi = unit.ze; blk_first = unit.blk_begin; blk_end = unit.blk_begin + unit.blk_count; }
+    const ZEntry* const zp = ze + zi;
+    if (!units) { blk_first = zp->blk_begin; blk_end = blk_first + zp->blk_count; }
+    EntryRec& er = entries[zp->entry];
     if (er.status != ST_OK) return;
     if (er.out_len > er.out_cap) { if (tid == 0) atomicCAS(&er.status, ST_OK, ST_NOSPACE); return; }
     // Positions are 32-bit and relative to the start of the CURRENT block (oblk = its place in HBM); they are rebased
     // at every block, so the window start and the flush mark may be negative.  oblk + bpos and oblk + flushed stay
     // multiples of 16 in the (16-byte aligned) entry.
     // A unit that is not the first frame of its entry starts at any byte: the window then begins `skip` bytes before it (at
-    // the 16-byte boundary below), and those bytes -- another CTA's -- are never written.
-    const uint64_t unit_off = (units && blk_n) ? blocks[blk_first].out_off : 0;
-    uint32_t skip = (uint32_t)(unit_off & 15u);
-    uint8_t* oblk = out + er.out_off + (unit_off - skip);
-    int32_t bpos = 0;             // position of win[0]
-    int32_t cur = (int32_t)skip;  // position of the next output byte
-    int32_t flushed = 0;          // HBM holds everything below
+    // the 16-byte boundary below), and those bytes -- another CTA's -- must never be written.  The regular flushes start
+    // behind that first 16-byte group; its own bytes go out once, bytewise, from warp 0 in the first flush after the group is
+    // complete (far matches read HBM, so it cannot wait long) or at the end of a unit shorter than that.
+    // The pending mark lives in shared memory (misc[3]): the kernel has no register to spare.
+    const uint64_t unit_off = (units && blk_end > blk_first) ? blocks[blk_first].out_off : 0;
+    const uint32_t skip0 = (uint32_t)(unit_off & 15u);
+    uint8_t* oblk = out + er.out_off + (unit_off - skip0);
+    int32_t bpos = 0;                         // position of win[0]
+    int32_t cur = (int32_t)skip0;             // position of the next output byte
+    int32_t flushed = skip0 ? 16 : 0;         // HBM holds everything below (bar the pending head group)
+    if (tid == 0) misc[3] = skip0;
+    __syncthreads();
+    // win[0] <-> oblk + bpos as long as the window has not slid
+    auto flush_head = [&](bool at_end) {
+        if (warp == 0) {
+            const uint32_t a = misc[3];
+            __syncwarp();
+            const uint32_t have = (uint32_t)(cur - bpos);
+            if (a && (at_end || have >= 16u)) {
+                const uint32_t top = have < 16u ? have : 16u;
+                if (lane >= a && lane < top) (oblk + (int64_t)bpos)[lane] = win[lane];
+                if (lane == 0) misc[3] = 0;
+            }
+        }
+    };
 
     // ---- whole-CTA helpers; every one is called under uniform control flow
     // finished 512-byte rows -> HBM (rows distributed over the warps).  force: also the 16-byte groups and the byte
     // tail below cur (rewritten later with the same values).  Callers guarantee the window bytes are visible.
     auto flush = [&](bool force) {
+        if (force) flush_head(true);
         if (flushed + 512 <= cur) {
             const uint32_t nrows = (uint32_t)((cur - flushed) >> 9);
             const uint32_t w0 = (uint32_t)(flushed - bpos);
+            if (w0 == 16u) flush_head(false);   // the first row flush of a unit with a pending head group starts here (others: no-op)
             uint8_t* const g = oblk + (int64_t)flushed;
             for (uint32_t r = warp; r < nrows; r += C::W) {
                 const uint4 v = *reinterpret_cast<const uint4*>(win + w0 + (r << 9) + 16 * lane);
-                if (skip && r == 0 && lane == 0) { for (uint32_t q = skip; q < 16; q++) g[q] = win[w0 + q]; }
-                else *reinterpret_cast<uint4*>(g + (r << 9) + 16 * lane) = v;
+                *reinterpret_cast<uint4*>(g + (r << 9) + 16 * lane) = v;
             }
             flushed += (int32_t)(nrows << 9);
-            skip = 0;
         }
         if (force && flushed < cur) {
             const uint32_t n = (uint32_t)(cur - flushed);   // < 512
@@ -179,13 +198,11 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
                 uint8_t* const g = oblk + (int64_t)flushed;
                 if (16u * lane + 16u <= n) {
                     const uint4 v = *reinterpret_cast<const uint4*>(win + w0 + 16 * lane);
-                    if (skip && lane == 0) { for (uint32_t q = skip; q < 16; q++) g[q] = win[w0 + q]; }
-                    else *reinterpret_cast<uint4*>(g + 16 * lane) = v;
+                    *reinterpret_cast<uint4*>(g + 16 * lane) = v;
                 }
                 const uint32_t full = n & ~15u;
-                if (full + lane < n && full + lane >= (full ? 0u : skip)) g[full + lane] = win[w0 + full + lane];
+                if (full + lane < n) g[full + lane] = win[w0 + full + lane];
             }
-            if (n & ~15u) skip = 0;
             flushed += (int32_t)(n & ~15u);
         }
     };
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
     };
 
     int32_t fail = ST_OK;
-    for (uint32_t k = blk_first; k < blk_first + blk_n && fail == ST_OK; k++) {
+    for (uint32_t k = blk_first; k < blk_end && fail == ST_OK; k++) {
         const ZBlock& b = blocks[k];
         // the prefix pass laid the blocks out back to back: this block starts where the previous one ended.  Rebase.
         oblk += cur; bpos -= cur; flushed -= cur; cur = 0;
@@ -271,9 +288,9 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
         uint32_t lstride = 1;
         if (b.lit_type == LT_RAW) lit = buf + b.src + b.lit_pos;
         else if (b.lit_type == LT_RLE) { lit = buf + b.src + b.lit_pos; lstride = 0; }
-        else lit = lits + z.lit_base + b.lit_off;
+        else lit = lits + zp->lit_base + b.lit_off;
         const uint32_t lit_regen = b.lit_regen, nseq = b.nseq;
-        const SeqRec* sq = seqs + z.seq_base + b.seq_off;
+        const SeqRec* sq = seqs + zp->seq_base + b.seq_off;
         const uint32_t rep_in[3] = {b.rep_in[0], b.rep_in[1], b.rep_in[2]};
         const uint64_t fd64 = b.out_off - b.frame_out;                // bytes of this frame before the block
         const uint32_t frame_dist = fd64 < 0x7FFFFFFFull ? (uint32_t)fd64 : 0x7FFFFFFFu;   // offsets beyond 2^31 are corrupt anyway
