@@ -26,7 +26,7 @@
  *   flate2 1.1.9/miniz_oxide   -> zlib 1.3 inflate()/deflate() (same RFC 1950/1951 format; encode
  *                                 bytes differ from miniz_oxide, decode is a unique function)
  *
- * Parity is PINNED: tests/test_oracle_fixtures.py checks this file against the reference's own
+ * Parity is PINNED: tests/test_oracle.py and tests/test_gcm.py check this file against the reference's own
  * golden archives (resources/test/*.pna vs resources/test/raw) and the KATs in
  * lib/src/format/chunk.rs:31, lib/src/io.rs:179, lib/src/cipher.rs:256-292.
  */

@@ -245,3 +245,82 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
     if (compression != 2) { const uint32_t ad = (a2 << 16) | a1; out[o++] = ad >> 24; out[o++] = ad >> 16; out[o++] = ad >> 8; out[o++] = ad; }
     return o;
 }
+
+// ---- GCM STREAM: the tile algorithm of kernels_gcm.cuh with the lanes looped on the host (gcm_core.cuh is the same code)
+#include "../../portable-network-archive_b200/csrc/gcm_core.cuh"
+#include "../../portable-network-archive_b200/csrc/aead_host.hpp"
+// one segment: CTR from J0+1 and the tag, GHASH evaluated tile by tile exactly like gcm_tiles_kernel / gcm_finish_kernel
+// (first tile short, lane l takes blocks l, l+32, ... with H^32, 5-level lane tree, tiles chained with H^1024)
+extern "C" int hc_gcm_segment(int encryption, const uint8_t* key, const uint8_t* nonce12, const uint8_t* ct, uint64_t n, uint8_t* plain,
+                              uint8_t* tag) {
+    init();
+    using namespace pna::gcm;
+    const uint32_t last4[16] = PNA_GCM_LAST4;
+    AesKey AK; CamelliaKey CK;
+    if (encryption == 1) aes256_expand_key(&g_aes, key, &AK); else camellia256_expand_key(&g_cam, key, &CK);
+    auto E = [&](uint32_t s[4]) {
+        if (encryption == 1) aes256_encrypt_block(s, AK.rk, TabView{g_aes.te0, 1, 0});
+        else camellia256_crypt_block(s, CK.ek, &g_cam.sp_hi[0][0], &g_cam.sp_lo[0][0]);
+    };
+    uint32_t h[4] = {0, 0, 0, 0};
+    E(h);
+    GcmPow P;
+    make_powers(from_le_words(h[0], h[1], h[2], h[3]), &P);
+    uint32_t nw[3];
+    memcpy(nw, nonce12, 12);
+    const uint64_t nb = (n + 15) / 16, head = nb % 1024;
+    G128 y = G128{{0, 0, 0, 0}};
+    bool first_tile = true;
+    for (uint64_t b0 = 0; b0 < nb;) {
+        const uint32_t m = (b0 == 0 && head) ? (uint32_t)head : 1024u, pad = 1024u - m;
+        G128 lanes[32];
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            G128 yl = G128{{0, 0, 0, 0}};
+            for (uint32_t k = pad >> 5; k < 32; k++) {
+                const uint32_t r = k * 32 + lane;
+                yl = mul_table(yl, P.t[GCM_POW_STRIDE].e, last4);
+                if (r < pad) continue;
+                const uint64_t bi = b0 + (r - pad), off = bi * 16;
+                const uint32_t have = (uint32_t)(n - off >= 16 ? 16 : n - off);
+                uint32_t c[4] = {0, 0, 0, 0};
+                memcpy(c, ct + off, have);
+                uint32_t o[4] = {nw[0], nw[1], nw[2], bswap32((uint32_t)bi + 2u)};
+                E(o);
+                for (int q = 0; q < 4; q++) o[q] ^= c[q];
+                memcpy(plain + off, o, have);
+                gxor(yl, from_le_words(c[0], c[1], c[2], c[3]));
+            }
+            lanes[lane] = yl;
+        }
+        for (int l = 0; l < 5; l++) {
+            G128 nx[32];
+            for (uint32_t lane = 0; lane < 32; lane++) {
+                G128 a = lanes[lane], b = lanes[lane ^ (1u << l)];
+                if (!((lane >> l) & 1)) a = mul_table(a, P.t[l].e, last4); else b = mul_table(b, P.t[l].e, last4);
+                gxor(a, b);
+                nx[lane] = a;
+            }
+            memcpy(lanes, nx, sizeof nx);
+        }
+        const G128 part = mul_table(lanes[0], P.t[0].e, last4);
+        if (!first_tile) y = mul_table(y, P.t[GCM_POW_TILE].e, last4);
+        gxor(y, part);
+        first_tile = false;
+        b0 += m;
+    }
+    const uint64_t bits = n * 8;
+    y.w[1] ^= (uint32_t)(bits >> 32); y.w[0] ^= (uint32_t)bits;
+    y = mul_table(y, P.t[0].e, last4);
+    uint32_t j0[4] = {nw[0], nw[1], nw[2], bswap32(1u)};
+    E(j0);
+    uint32_t t[4];
+    to_le_words(y, t);
+    for (int q = 0; q < 4; q++) t[q] ^= j0[q];
+    memcpy(tag, t, 16);
+    return 0;
+}
+extern "C" void hc_hkdf_sha256(const uint8_t* ikm, uint64_t n_ikm, const uint8_t* salt, uint64_t n_salt, const uint8_t* info, uint64_t n_info,
+                               uint8_t* okm) {
+    pna::aead::hkdf_sha256(ikm, n_ikm, salt, n_salt, info, n_info, okm);
+}
+extern "C" void hc_sha256(const uint8_t* d, uint64_t n, uint8_t* out) { pna::aead::sha256(d, n, nullptr, 0, out); }

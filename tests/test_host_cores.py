@@ -155,3 +155,30 @@ def test_encode_writers_decode_with_reference_codecs(hc, oracle, comp):
         assert oracle.decompress(comp, out.raw[:n]) == d, (comp, len(d))
         if len(d) > 50000 and d[:4] != os.urandom(4) and len(set(d[:1000])) < 200:
             assert n < len(d)
+
+
+def test_gcm_tile_algorithm_and_key_schedule(hc, oracle):
+    """kernels_gcm.cuh's evaluation order (lane-strided Horner with H^32, lane tree, tiles chained with H^1024, short tile first)
+    run with the lanes looped on the host == the oracle's bit-by-bit GCM (SP 800-38D) for both ciphers; SHA-256 / HKDF of
+    aead_host.hpp == hashlib / RFC 5869."""
+    import hashlib
+    hc.hc_gcm_segment.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p]
+    for enc in (1, 2):
+        for n in (0, 1, 15, 16, 17, 511, 512, 16 * 1024, 16 * 1024 + 1, 16 * 1025, 40000, 3 * 16384 + 5):
+            key, nonce, ct = os.urandom(32), os.urandom(12), os.urandom(n)
+            plain, tag = C.create_string_buffer(n or 1), C.create_string_buffer(16)
+            hc.hc_gcm_segment(enc, key, nonce, ct, n, plain, tag)
+            ref_ct, ref_tag = C.create_string_buffer(n or 1), C.create_string_buffer(16)
+            # the oracle encrypts: feed it our plaintext, it must reproduce the ciphertext and the tag
+            assert oracle.lib().pna_oracle_gcm_segment(enc, key, nonce, plain.raw[:n], n, ref_ct, ref_tag) == 0
+            assert ref_ct.raw[:n] == ct and ref_tag.raw == tag.raw, (enc, n)
+    hc.hc_sha256.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]
+    hc.hc_hkdf_sha256.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p]
+    for n in (0, 1, 55, 56, 63, 64, 65, 119, 120, 1000):
+        d, out = os.urandom(n), C.create_string_buffer(32)
+        hc.hc_sha256(d, n, out)
+        assert out.raw == hashlib.sha256(d).digest()
+    for ns in (0, 16, 32, 80):
+        ikm, salt, info, out = os.urandom(32), os.urandom(ns), os.urandom(88), C.create_string_buffer(32)
+        hc.hc_hkdf_sha256(ikm, 32, salt, ns, info, 88, out)
+        assert out.raw == oracle.hkdf_sha256(ikm, salt, info)
