@@ -151,10 +151,11 @@ class WriteOptions:
 
 # ------------------------------------------------------------------------------------ index pass
 class RawChunk:
-    __slots__ = ("ty", "off", "length", "crc")
+    __slots__ = ("ty", "off", "length", "crc", "buf")
 
-    def __init__(self, ty, off, length, crc):
+    def __init__(self, ty, off, length, crc, buf=None):
         self.ty, self.off, self.length, self.crc = ty, off, length, crc   # off = offset of the data field
+        self.buf = buf      # the part this chunk lives in when an archive is read from several parts (else the entry's buffer)
 
 
 def index_archive(buf: np.ndarray, pos: int = 0, end: int | None = None):
@@ -209,7 +210,8 @@ class _EntryBase:
         self.bodies = []          # numpy views of the FDAT/SDAT bodies, in order
 
     def _body(self, ch: RawChunk) -> np.ndarray:
-        return self._buf[ch.off:ch.off + ch.length]
+        buf = ch.buf if ch.buf is not None else self._buf
+        return buf[ch.off:ch.off + ch.length]
 
     def _stream_prefix(self, n: int) -> bytes:
         out = bytearray()
@@ -388,6 +390,44 @@ class Archive:
             _verify(a._ctx, buf, a._chunks)
         return a
 
+    @classmethod
+    def read_multipart(cls, parts, ctx=None, verify: bool = True) -> "Archive":
+        """A split archive (archive/read.rs:105-165 read_next_archive; writer archive/split_parts.rs): every part is a complete
+        chunk stream signature + AHED(archive_number = part index) ... [ANXT] AEND, and an entry's chunks -- its FDAT stream
+        included -- simply continue in the next part.  Parts are indexed and CRC-checked one by one; the entry iterator then
+        runs over the concatenated chunk list without the archive-level chunks."""
+        from . import default_context
+        a = cls()
+        a._ctx = ctx or default_context()
+        a._chunks = []
+        a._multipart = True
+        for k, data in enumerate(parts):
+            buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+            if buf.size < 8 or bytes(buf[:8]) != SIGNATURE:
+                raise PnaError(_ffi.E_INVALID_DATA, "it is not PNA")
+            chunks = index_archive(buf, 8)
+            if not chunks or chunks[0].ty != ChunkType.AHED or chunks[0].length != 8:
+                raise PnaError(_ffi.E_INVALID_DATA, "expected `AHED` chunk")
+            ah = bytes(buf[chunks[0].off:chunks[0].off + 8])
+            if int.from_bytes(ah[4:8], "big") != k:
+                raise PnaError(_ffi.E_INVALID_DATA, f"part {k} carries archive number {int.from_bytes(ah[4:8], 'big')}")
+            if k == 0:
+                a._buf, a.major, a.minor, a.archive_number = buf, ah[0], ah[1], 0
+            if verify:
+                _verify(a._ctx, buf, chunks)
+            if chunks[-1].ty != ChunkType.AEND:
+                raise PnaError(_ffi.E_UNEXPECTED_EOF, "part without `AEND`")
+            has_next = any(c.ty == ChunkType.ANXT for c in chunks)
+            if has_next != (k + 1 < len(parts)):
+                raise PnaError(_ffi.E_UNEXPECTED_EOF if has_next else _ffi.E_INVALID_DATA,
+                               "next part missing" if has_next else "part does not announce a next archive (`ANXT`)")
+            for c in chunks:
+                if c.ty in (ChunkType.AHED, ChunkType.ANXT, ChunkType.AEND):
+                    continue
+                c.buf = buf
+                a._chunks.append(c)
+        return a
+
     def entries(self):
         """Entries iterator: NormalEntry | SolidEntry in archive order."""
         return _group(self._buf, self._chunks, self._ctx)
@@ -419,6 +459,8 @@ class Archive:
         """The whole extract hot path as ONE device plan: CRC check of every chunk of the archive (seam 1) fused
         with decrypt+decompress of every FILE entry (seam 2) over a single upload of the archive bytes.
         Returns (plan, entries); plan.run(); plan.fetch(sizes)."""
+        if getattr(self, "_multipart", False):
+            raise PnaError(_ffi.E_UNSUPPORTED, "extract_plan works on one contiguous archive buffer; use read_all for split archives")
         ents = [e for e in self.entries() if isinstance(e, NormalEntry) and e.data_kind == DataKind.FILE]
         owner = {}
         for i, e in enumerate(ents):

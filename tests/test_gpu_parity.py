@@ -448,3 +448,18 @@ def test_zstd_multi_frame_streams_run_one_lz_unit_per_frame(ctx, oracle):
         assert st[1] == 0 and outs[1].tobytes() == ref
     except oracle.OracleError:
         assert st[1] != 0
+
+
+@pytest.mark.gpu
+def test_multipart_archive_api(ctx, pna, golden):
+    """extract_multipart_compatibility.rs:36 through the archive API: Archive over both parts, one entry whose FDAT stream
+    continues in part 2; wrong part order / missing part are errors (archive/read.rs:118)."""
+    p1 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part1.pna"), dtype=np.uint8)
+    p2 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part2.pna"), dtype=np.uint8)
+    want = open(os.path.join(golden["dir"], "ref", "multipart_test.txt"), "rb").read()
+    got = list(pna.Archive.read_multipart([p1, p2], ctx).read_all())
+    assert len(got) == 1 and got[0][1] == want
+    with pytest.raises(pna.PnaError):
+        pna.Archive.read_multipart([p2, p1], ctx)
+    with pytest.raises(pna.PnaError):
+        pna.Archive.read_multipart([p1], ctx)
