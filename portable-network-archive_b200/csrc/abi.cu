@@ -227,6 +227,7 @@ struct pna_plan {
     DevArr<zs::ZEntry> d_ze;
     DevArr<zs::LzUnit> d_lz_units;   // one per frame
     uint32_t n_lz_units = 0;
+    uint64_t lz_avg_unit_comp = 0;   // compressed bytes per unit, for the choice of the LZ kernel variant
     DevArr<zs::ZBlock> d_blocks;
     DevArr<uint64_t> d_lit_base, d_seq_base;
     DevArr<inf::InfStream> d_inf;
@@ -843,10 +844,13 @@ static int launch_zstd_lz_on(pna_plan* P, const zs::ZEntry* ze, const uint32_t* 
                              const zs::ZBlock* blocks, const uint8_t* lits, const zs::SeqRec* seqs) {
     pna_ctx* ctx = P->ctx;
     if (!nz) return PNA_OK;
-    // one CTA per entry, longest streams first.  Fewer entries than half the SMs (a solid archive is ONE frame): the
-    // 16-warp variant with the 128 KiB window; otherwise 4 warps per entry, 7 entries per SM.
+    // one CTA per unit (frame), longest streams first.  Fewer units than half the SMs (a reference-written solid archive is ONE
+    // frame): the 16-warp variant with the 128 KiB window; otherwise 4 warps per unit, 7 units per SM.  In between -- up to four
+    // waves of large units (measured on 4 MiB entries: 16 warps x 1 unit per SM beat 4 warps x 7 up to ~600 units; 256 entries
+    // 10.7 -> 5.8 ms) -- the 16-warp variant too, because a unit is serial and more warps per unit is the only parallelism left.
     const char* force = getenv("PNA_LZ_VARIANT");
-    const bool big = force ? force[0] == 'b' : nz * 2 <= (uint32_t)ctx->sm_count;
+    const bool big = force ? force[0] == 'b'
+                           : nz * 2 <= (uint32_t)ctx->sm_count || (units && nz <= 4u * (uint32_t)ctx->sm_count && P->lz_avg_unit_comp >= (256u << 10));
     if (big)
         zs::zstd_lz_kernel<zs::LzBig><<<nz, zs::LzBig::T, zs::LzBig::BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, ze, order, units, nz, blocks, lits,
                                                                                             seqs, P->d_out.p);
@@ -944,6 +948,11 @@ static int decode_prepare(pna_plan* P) {
         if (nu > 0xFFFFFFF0ull) return PNA_E_OOM;
         // LZ units = frames; dispatched entry by entry in the longest-stream-first order, an entry's frames in stream order
         P->n_lz_units = (uint32_t)nu;
+        {
+            uint64_t zc = 0;
+            for (const auto& z : P->h_ze) zc += P->h_entries[z.entry].comp_len;
+            P->lz_avg_unit_comp = nu ? zc / nu : 0;
+        }
         std::vector<uint32_t> unit_order;
         unit_order.reserve(nu);
         for (uint32_t zi : lz_order)
