@@ -773,13 +773,13 @@ static int launch_cipher(pna_plan* P) {
         LAUNCHED();
         const uint32_t cap = (uint32_t)ctx->sm_count * 3;
         if (na) {
-            gcm::gcm_tiles_kernel<1, true><<<std::min<uint32_t>((na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+            gcm::gcm_tiles_kernel<1, true><<<std::min<uint32_t>((na + gcm::gcm_tile_warps<1>() - 1) / gcm::gcm_tile_warps<1>(), (uint32_t)ctx->sm_count), gcm::gcm_tile_warps<1>() * 32,
                                              gcm::gcm_tiles_smem<1>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_buf.p, P->d_gcm_segs.p,
                 P->d_gcm_tiles.p, na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, P->d_gcm_partial.p);
             LAUNCHED();
         }
         if (nt > na) {
-            gcm::gcm_tiles_kernel<2, true><<<std::min<uint32_t>((nt - na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+            gcm::gcm_tiles_kernel<2, true><<<std::min<uint32_t>((nt - na + gcm::gcm_tile_warps<2>() - 1) / gcm::gcm_tile_warps<2>(), cap), gcm::gcm_tile_warps<2>() * 32,
                                              gcm::gcm_tiles_smem<2>(), ctx->stream>>>(P->d_buf.p, P->d_segs.p, P->d_buf.p, P->d_gcm_segs.p,
                 P->d_gcm_tiles.p + na, nt - na, P->d_keys.p, P->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, P->d_gcm_partial.p + na);
             LAUNCHED();

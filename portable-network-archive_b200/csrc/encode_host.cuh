@@ -324,13 +324,13 @@ static int encode_launch_all(pna_plan* P) {
         LAUNCHED();
         const uint32_t cap = (uint32_t)ctx->sm_count * 3;
         if (na) {
-            gcm::gcm_tiles_kernel<1, false><<<std::min<uint32_t>((na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+            gcm::gcm_tiles_kernel<1, false><<<std::min<uint32_t>((na + gcm::gcm_tile_warps<1>() - 1) / gcm::gcm_tile_warps<1>(), (uint32_t)ctx->sm_count), gcm::gcm_tile_warps<1>() * 32,
                                               gcm::gcm_tiles_smem<1>(), ctx->stream>>>(E->d_work.p, E->d_pieces.p, E->d_out.p, E->d_gcm_segs.p,
                 E->d_gcm_tiles.p, na, E->d_keys.p, E->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, E->d_gcm_partial.p);
             LAUNCHED();
         }
         if (ntl > na) {
-            gcm::gcm_tiles_kernel<2, false><<<std::min<uint32_t>((ntl - na + gcm::GCM_TILE_WARPS - 1) / gcm::GCM_TILE_WARPS, cap), gcm::GCM_TILE_WARPS * 32,
+            gcm::gcm_tiles_kernel<2, false><<<std::min<uint32_t>((ntl - na + gcm::gcm_tile_warps<2>() - 1) / gcm::gcm_tile_warps<2>(), cap), gcm::gcm_tile_warps<2>() * 32,
                                               gcm::gcm_tiles_smem<2>(), ctx->stream>>>(E->d_work.p, E->d_pieces.p, E->d_out.p, E->d_gcm_segs.p,
                 E->d_gcm_tiles.p + na, ntl - na, E->d_keys.p, E->d_gcm_pows.p, ctx->d_aes, ctx->d_cam, E->d_gcm_partial.p + na);
             LAUNCHED();

@@ -73,12 +73,15 @@ struct GcmWarpState {   // per-warp shared memory
     uint32_t rk32[60];
     uint64_t rk64[34];
 };
-constexpr int GCM_TILE_WARPS = 8;
+// AES: the four rotations of Te0 as four lane-replicated tables (128 KB, no rotate per lookup -- two thirds of this kernel's
+// instructions are AES) and 32 warps in ONE CTA per SM, like the CTR kernel; Camellia: 16 KB of SP tables, 8 warps, 3 CTAs per SM.
 template <int ENC>
-constexpr int gcm_tiles_smem() { return (ENC == 1 ? 256 * 32 * 4 : 2 * 2048 * 4) + GCM_TILE_WARPS * (int)sizeof(GcmWarpState) + 64; }
+constexpr int gcm_tile_warps() { return ENC == 1 ? 32 : 8; }
+template <int ENC>
+constexpr int gcm_tiles_smem() { return (ENC == 1 ? 4 * 256 * 32 * 4 : 2 * 2048 * 4) + gcm_tile_warps<ENC>() * (int)sizeof(GcmWarpState) + 64; }
 
 template <int ENC, bool DECRYPT>
-__global__ void __launch_bounds__(GCM_TILE_WARPS * 32) gcm_tiles_kernel(const uint8_t* __restrict__ src, const Segment* __restrict__ segs,
+__global__ void __launch_bounds__(gcm_tile_warps<ENC>() * 32) gcm_tiles_kernel(const uint8_t* __restrict__ src, const Segment* __restrict__ segs,
                                                                        uint8_t* __restrict__ dst_base,
                                                                        const GcmSeg* __restrict__ gsegs, const GcmTile* __restrict__ tiles,
                                                                        uint32_t n_tiles, const DevKeys* __restrict__ keys,
@@ -87,10 +90,11 @@ __global__ void __launch_bounds__(GCM_TILE_WARPS * 32) gcm_tiles_kernel(const ui
                                                                        G128* __restrict__ partial) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* s_tab = smem;
-    constexpr int TAB_WORDS = ENC == 1 ? 256 * 32 : 2 * 2048;
+    constexpr int TAB_WORDS = ENC == 1 ? 4 * 256 * 32 : 2 * 2048;
+    constexpr int GCM_TILE_WARPS = ENC == 1 ? 32 : 8;
     GcmWarpState* ws_all = reinterpret_cast<GcmWarpState*>(smem + TAB_WORDS);
     uint32_t* s_last4 = reinterpret_cast<uint32_t*>(ws_all + GCM_TILE_WARPS);
-    if (ENC == 1) { for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_tab[i] = aes->te0[i >> 5]; }
+    if (ENC == 1) { for (int i = threadIdx.x; i < 4 * 256 * 32; i += blockDim.x) s_tab[i] = rotl32(aes->te0[(i >> 5) & 255], 8 * (i >> 13)); }   // [k][x*32 + lane]
     else for (int i = threadIdx.x; i < 2048; i += blockDim.x) { s_tab[i] = (&cam->sp_hi[0][0])[i]; s_tab[2048 + i] = (&cam->sp_lo[0][0])[i]; }
     if (threadIdx.x < 16) { const uint32_t l4[16] = PNA_GCM_LAST4; s_last4[threadIdx.x] = l4[threadIdx.x]; }
     __syncthreads();
@@ -135,8 +139,10 @@ __global__ void __launch_bounds__(GCM_TILE_WARPS * 32) gcm_tiles_kernel(const ui
                 }
             }
             uint32_t o[4] = {sg.nonce[0], sg.nonce[1], sg.nonce[2], bswap32((uint32_t)bi + 2u)};   // inc32 from J0 + 1
-            if (ENC == 1) aes256_encrypt_block(o, ws.rk32, tv);
-            else camellia256_crypt_block(o, ws.rk64, s_tab, s_tab + 2048);
+            if (ENC == 1) {
+                const TabView t1{s_tab + 8192, 32, lane}, t2{s_tab + 16384, 32, lane}, t3{s_tab + 24576, 32, lane};
+                aes256_encrypt_block4(o, ws.rk32, tv, t1, t2, t3);
+            } else camellia256_crypt_block(o, ws.rk64, s_tab, s_tab + 2048);
             o[0] ^= c[0]; o[1] ^= c[1]; o[2] ^= c[2]; o[3] ^= c[3];
             if (!DECRYPT && have < 16) {   // the hash sees the ciphertext zero-padded
                 const uint32_t keep = have * 8;
