@@ -281,3 +281,37 @@ def test_gcm_solid_archive_round_trip(ctx, pna, oracle):
     assert dict(oracle.extract_all(blob, b"pw")) == files
     ar = pna.Archive.read_header(np.frombuffer(blob, dtype=np.uint8), ctx)
     assert {e.name: d for e, d in ar.read_all(pna.ReadOptions.with_password(b"pw"))} == files
+
+
+def test_encode_bound_counts_header_and_tags(pna):
+    """pna_cuda_encode_bound / _crc_count are host arithmetic: a GCM stream is header(75) + payload + one tag per segment
+    (at least one: the empty final segment, gcm.rs tests `empty_plaintext_emits_single_tag_only_segment`)."""
+    import importlib
+    ffi = importlib.import_module("portable-network-archive_b200._ffi")
+    L = ffi.lib()
+    for n, seg in [(0, 1 << 20), (1, 1 << 20), (1 << 20, 1 << 20), ((1 << 20) + 1, 1 << 20), (5 << 20, 65536), (1000, 16)]:
+        d = ffi.EncodeDesc()
+        hdr = C.create_string_buffer(bytes(39) + struct.pack(">I", seg) + bytes(32), 75)
+        d.plain.len, d.compression, d.encryption, d.cipher_mode = n, 0, 1, 2
+        d.stream_header = C.cast(hdr, C.c_void_p)
+        bound = L.pna_cuda_encode_bound(C.byref(d))
+        exact = 75 + n + 16 * max(1, -(-n // seg))          # store: the payload is the plaintext itself
+        assert exact <= bound <= exact + 16, (n, seg, bound, exact)
+        d.max_chunk_size = 1000
+        assert L.pna_cuda_encode_crc_count(C.byref(d)) >= -(-(exact - 75) // 1000)
+
+
+def test_multipart_index_without_gpu(golden):
+    """Archive.read_multipart's part walk is host logic: the reference's two-part fixture yields ONE entry whose FDAT stream
+    spans both parts; part order and completeness are checked (archive/read.rs:105-165)."""
+    import importlib
+    mod = importlib.import_module("portable-network-archive_b200.archive")
+    p1 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part1.pna"), dtype=np.uint8)
+    p2 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part2.pna"), dtype=np.uint8)
+    a = mod.Archive.read_multipart([p1, p2], ctx=object(), verify=False)
+    es = list(a.entries())
+    assert len(es) == 1 and es[0].name == "multipart_test.txt" and len(es[0].bodies) == 2
+    assert {id(ch.buf) for ch in es[0].chunks} == {id(p1), id(p2)}
+    for bad in ([p2, p1], [p1], [p1, p1]):
+        with pytest.raises(mod.PnaError):
+            mod.Archive.read_multipart(bad, ctx=object(), verify=False)
