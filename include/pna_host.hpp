@@ -148,6 +148,11 @@ struct FileEntryBuilder {   // builder/file.rs:41: plaintext is borrowed until A
 // Archive::write_header + add_entry per file + finalize, with one GPU encode batch per worker group.
 std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
                                     int device, int workers, uint64_t group_bytes);
+// Solid mode (lib/src/archive/write.rs:438-471): all files as STORE entries inside ONE compressed (+ encrypted) stream, SDAT bodies of
+// max_chunk_size.  Returns the archive length; create_solid_archive_bound sizes `out`.
+uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
+                                   uint8_t* out, uint64_t cap);
+uint64_t create_solid_archive_bound(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size);
 // Same, written straight into a caller buffer (pinned memory makes the stream copies true DMA); returns the archive length.
 uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
                              int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap);
@@ -205,6 +210,11 @@ int pnah_file_get(pnah_archive* a, uint32_t i, const char** name, uint64_t* size
 int pnah_file_sizes(pnah_archive* a, uint64_t* sizes, int32_t* status /* may be NULL */);   /* bulk form of pnah_file_get */
 int pnah_extract_files(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                        uint64_t group_bytes, int verify, char* err, uint64_t errcap);
+uint64_t pnah_create_solid_bound(uint32_t n, const char* const* names, const uint64_t* lens, uint8_t compression, uint8_t encryption,
+                                 uint8_t cipher_mode, const char* phsf, uint32_t max_chunk_size);
+int pnah_create_solid(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, uint8_t compression, int32_t level,
+                      uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf, uint32_t max_chunk_size, int device,
+                      uint8_t* out, uint64_t cap, uint64_t* out_len, char* err, uint64_t errcap);
 int pnah_create(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs,
                 uint8_t compression, int32_t level, uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf,
                 uint32_t max_chunk_size, int device, int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap, uint64_t* out_len,

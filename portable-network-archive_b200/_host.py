@@ -12,7 +12,7 @@ from . import _ffi
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpna_host.so")
 EXPORTS = ["pnah_open", "pnah_close", "pnah_entry_count", "pnah_entry_get", "pnah_chunk_count", "pnah_set_key", "pnah_prepare",
-           "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound",
+           "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound", "pnah_create_solid", "pnah_create_solid_bound",
            "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files"]
 
 
@@ -59,6 +59,10 @@ def lib():
                                   C.c_char_p, u64]
         L.pnah_create_bound.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(u64), C.c_uint8, C.c_uint8, C.c_char_p, u32]
         L.pnah_create_bound.restype = u64
+        L.pnah_create_solid_bound.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(u64), C.c_uint8, C.c_uint8, C.c_uint8, C.c_char_p, u32]
+        L.pnah_create_solid_bound.restype = u64
+        L.pnah_create_solid.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(u64), C.c_uint8, C.c_int32, C.c_uint8, C.c_uint8,
+                                        C.c_char_p, C.c_char_p, u32, C.c_int, vp, u64, C.POINTER(u64), C.c_char_p, u64]
         L.pnah_open_file.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, u64]
         L.pnah_extract_to_dir.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, u64, u64, C.c_int, C.c_int, C.POINTER(IoStats),
                                           C.POINTER(C.c_int32), C.c_char_p, u64]
@@ -212,6 +216,28 @@ def create_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, 
     err = C.create_string_buffer(512)
     rc = L.pnah_create(n, names, ptrs, lens, ivs, compression, level, encryption, cipher_mode, key or bytes(32), (phsf or "").encode(),
                        max_chunk_size, device, workers, group_bytes, out.ctypes.data, out.size, C.byref(olen), err, 512)
+    if rc:
+        raise HostError(rc, err.value.decode())
+    return out[:olen.value]
+
+
+def create_solid_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, key=None, phsf=None, max_chunk_size=32 * 1024,
+                         device=0, out=None):
+    """Solid mode (archive/write.rs:438-471): every file a STORE entry inside one compressed (+ encrypted) stream of SDAT bodies.
+    files: list of (name, bytes-like).  Returns the archive bytes."""
+    L = lib()
+    n = len(files)
+    arrs = [f[1] if isinstance(f[1], np.ndarray) else np.frombuffer(f[1], dtype=np.uint8) for f in files]
+    names = (C.c_char_p * max(n, 1))(*[f[0].encode() for f in files])
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+    lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrs])
+    bound = int(L.pnah_create_solid_bound(n, names, lens, compression, encryption, cipher_mode, (phsf or "").encode(), max_chunk_size))
+    if out is None:
+        out = np.empty(bound, dtype=np.uint8)
+    olen = C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    rc = L.pnah_create_solid(n, names, ptrs, lens, compression, level, encryption, cipher_mode, key or bytes(32), (phsf or "").encode(),
+                             max_chunk_size, device, out.ctypes.data, out.size, C.byref(olen), err, 512)
     if rc:
         raise HostError(rc, err.value.decode())
     return out[:olen.value]

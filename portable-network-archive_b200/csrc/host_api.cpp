@@ -926,6 +926,131 @@ struct PinnedBuf {   // RAII lease
     PinnedBuf(const PinnedBuf&) = delete;
     PinnedBuf& operator=(const PinnedBuf&) = delete;
 };
+
+// ---------------------------------------------------------------------------------------------- solid create
+// Archive::write_solid_header + add_entry... + finalize (lib/src/archive/write.rs:438-471, lib/src/entry/builder/solid.rs:68-320):
+// the inner entries are written STORE, chunk by chunk, into ONE stream that is compressed + encrypted as a whole and cut into
+// SDAT bodies (wire order lib/src/entry.rs:471-483).  Inner chunk CRCs, the encode and the outer chunk CRCs are three GPU calls.
+// The stream this library writes is one zstd frame per MiB, so the solid entry decodes frame-parallel (DESIGN "Frame-parallel streams").
+uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
+                                   uint8_t* out, uint64_t cap) {
+    const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull;
+    const bool enc = opt.encryption != PNA_ENCRYPTION_NO, gcm = enc && opt.cipher_mode == PNA_CIPHER_GCM;
+    CtxLease L(device);
+    // ---- inner archive stream: FHED, fSIZ, FDAT..., FEND per file
+    uint64_t inner_len = 0;
+    std::vector<uint64_t> at(files.size());
+    for (size_t i = 0; i < files.size(); i++) {
+        at[i] = inner_len;
+        const uint64_t D = files[i].data.len, nb = (D + mcs - 1) / mcs;
+        inner_len += (12 + 6 + files[i].name.size()) + (12 + 8) + nb * 12 + D + 12;
+    }
+    PinnedBuf inner_buf(L.ctx, inner_len + 64);
+    uint8_t* const inner = inner_buf.p;
+    if (!inner) throw Error(PNA_E_OOM, "pinned inner stream");
+    std::vector<pna_span> spans;
+    std::vector<uint64_t> crc_at;
+    uint64_t w = 0;
+    auto put = [&](const char* ty, const uint8_t* data, uint64_t len) {
+        wr_be32(inner + w, (uint32_t)len); memcpy(inner + w + 4, ty, 4);
+        if (len) memcpy(inner + w + 8, data, len);
+        spans.push_back({inner + w + 4, len + 4});
+        crc_at.push_back(w + 8 + len);
+        w += 12 + len;
+    };
+    for (size_t i = 0; i < files.size(); i++) {
+        const FileEntryBuilder& f = files[i];
+        std::vector<uint8_t> h = {0, 0, (uint8_t)DataKind::File, 0, 0, 0};
+        h.insert(h.end(), f.name.begin(), f.name.end());
+        put("FHED", h.data(), h.size());
+        uint8_t sz[8];
+        for (int b = 0; b < 8; b++) sz[b] = (uint8_t)(f.data.len >> (8 * (7 - b)));
+        int skip = 0;
+        while (skip < 8 && sz[skip] == 0) skip++;
+        put("fSIZ", sz + skip, (uint64_t)(8 - skip));
+        for (uint64_t o = 0; o < f.data.len; o += mcs) put("FDAT", f.data.ptr + o, std::min<uint64_t>(mcs, f.data.len - o));
+        put("FEND", nullptr, 0);
+    }
+    inner_len = w;
+    {
+        std::vector<uint32_t> crcs(spans.size());
+        for (size_t b0 = 0; b0 < spans.size(); b0 += 1u << 20) {   // batches of a million chunks
+            const uint32_t m = (uint32_t)std::min<size_t>(1u << 20, spans.size() - b0);
+            ck(L.ctx, pna_cuda_crc32(L.ctx, spans.data() + b0, m, crcs.data() + b0), "inner chunk crc");
+        }
+        for (size_t k = 0; k < spans.size(); k++) wr_be32(inner + crc_at[k], crcs[k]);
+    }
+    // ---- encode the inner stream as one entry
+    const uint8_t shed[5] = {0, 0, opt.compression, opt.encryption, opt.cipher_mode};
+    pna_encode_desc d;
+    memset(&d, 0, sizeof d);
+    d.plain = pna_span{inner, inner_len};
+    d.compression = opt.compression; d.encryption = opt.encryption; d.cipher_mode = opt.cipher_mode; d.level = opt.level;
+    memcpy(d.key, opt.key, 32);
+    uint8_t gcm_hdr[75], gcm_key[32];
+    static thread_local std::random_device rd;
+    if (gcm) {
+        uint8_t salt[32], prefix[8];
+        for (int k = 0; k < 32; k += 4) { const uint32_t r = rd(); memcpy(salt + k, &r, 4); }
+        for (int k = 0; k < 8; k += 4) { const uint32_t r = rd(); memcpy(prefix + k, &r, 4); }
+        int32_t rc = pna_cuda_gcm_stream_header(opt.key, salt, prefix, opt.segment_size, gcm_hdr);
+        if (rc == PNA_OK)
+            rc = pna_cuda_gcm_stream_key(opt.key, gcm_hdr, 75, (const uint8_t*)"SHED", shed, 5, (const uint8_t*)opt.phsf.data(), opt.phsf.size(), gcm_key);
+        if (rc != PNA_OK) throw Error(rc, "GCM stream parameters");
+        memcpy(d.key, gcm_key, 32);
+        d.stream_header = gcm_hdr;
+    } else if (enc) {
+        for (int k = 0; k < 16; k += 4) { const uint32_t r = rd(); memcpy(d.iv + k, &r, 4); }   // entry/write.rs:108-111
+    }
+    const uint64_t sbound = pna_cuda_encode_bound(&d);
+    PinnedBuf stream_buf(L.ctx, sbound + 64);
+    if (!stream_buf.p) throw Error(PNA_E_OOM, "pinned stream buffer");
+    pna_buf ob{stream_buf.p, sbound, 0};
+    int32_t st = 0;
+    ck(L.ctx, pna_cuda_encode_batch(L.ctx, &d, 1, &ob, nullptr, nullptr, &st), "solid encode");
+    if (st != PNA_OK) throw Error(st, "solid encode failed");
+    // ---- frame: signature, AHED, SHED, [PHSF], SDAT(prefix), SDAT..., SEND, AEND
+    const uint64_t prefix_len = enc ? (gcm ? 75 : 16) : 0, D = ob.len - prefix_len, nbody = (D + mcs - 1) / mcs;
+    const uint64_t need = 8 + 20 + (12 + 5) + (enc ? 12 + opt.phsf.size() + 12 + prefix_len : 0) + nbody * 12 + D + 12 + 12;
+    if (need > cap) throw Error(PNA_E_NOSPACE, "archive buffer too small");
+    memcpy(out, SIGNATURE, 8);
+    uint64_t o = 8;
+    std::vector<pna_span> ospans;
+    std::vector<uint64_t> ocrc_at;
+    auto oput = [&](const char* ty, const uint8_t* data, uint64_t len) {
+        wr_be32(out + o, (uint32_t)len); memcpy(out + o + 4, ty, 4);
+        if (len) memcpy(out + o + 8, data, len);
+        ospans.push_back({out + o + 4, len + 4});
+        ocrc_at.push_back(o + 8 + len);
+        o += 12 + len;
+    };
+    const uint8_t ahed8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    oput("AHED", ahed8, 8);
+    oput("SHED", shed, 5);
+    if (enc) {
+        oput("PHSF", (const uint8_t*)opt.phsf.data(), opt.phsf.size());
+        oput("SDAT", stream_buf.p, prefix_len);                      // IV / stream header: its own chunk (builder.rs:62-69)
+    }
+    for (uint64_t b = 0; b < nbody; b++) oput("SDAT", stream_buf.p + prefix_len + b * mcs, std::min<uint64_t>(mcs, D - b * mcs));
+    oput("SEND", nullptr, 0);
+    oput("AEND", nullptr, 0);
+    {
+        std::vector<uint32_t> crcs(ospans.size());
+        for (size_t b0 = 0; b0 < ospans.size(); b0 += 1u << 20) {
+            const uint32_t m = (uint32_t)std::min<size_t>(1u << 20, ospans.size() - b0);
+            ck(L.ctx, pna_cuda_crc32(L.ctx, ospans.data() + b0, m, crcs.data() + b0), "outer chunk crc");
+        }
+        for (size_t k = 0; k < ospans.size(); k++) wr_be32(out + ocrc_at[k], crcs[k]);
+    }
+    return o;
+}
+uint64_t create_solid_archive_bound(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size) {
+    const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull;
+    uint64_t inner = 0;
+    for (const auto& f : files) inner += (12 + 6 + f.name.size()) + (12 + 8) + ((f.data.len + mcs - 1) / mcs) * 12 + f.data.len + 12;
+    const uint64_t sb = stream_bound_of(inner, opt);
+    return 8 + 20 + 17 + 12 + opt.phsf.size() + 12 + 75 + (sb / mcs + 2) * 12 + sb + 24 + 64;
+}
 std::string sanitize_entry_name(const std::string& name) {
     std::string out;
     size_t i = 0;
@@ -1245,6 +1370,29 @@ uint64_t pnah_create_bound(uint32_t n, const char* const* names, const uint64_t*
         t += pna::entry_frame_bound(names[i], pna_cuda_encode_bound(&d), phsf ? phsf : "", encryption != 0, max_chunk_size);
     }
     return t;
+}
+uint64_t pnah_create_solid_bound(uint32_t n, const char* const* names, const uint64_t* lens, uint8_t compression, uint8_t encryption,
+                                 uint8_t cipher_mode, const char* phsf, uint32_t max_chunk_size) {
+    std::vector<pna::FileEntryBuilder> files(n);
+    for (uint32_t i = 0; i < n; i++) { files[i].name = names[i]; files[i].data = pna_span{nullptr, lens[i]}; }
+    pna::WriteOptions opt;
+    opt.compression = compression; opt.encryption = encryption; opt.cipher_mode = cipher_mode;
+    if (phsf) opt.phsf = phsf;
+    return pna::create_solid_archive_bound(files, opt, max_chunk_size);
+}
+int pnah_create_solid(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, uint8_t compression, int32_t level,
+                      uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf, uint32_t max_chunk_size, int device,
+                      uint8_t* out, uint64_t cap, uint64_t* out_len, char* err, uint64_t errcap) {
+    try {
+        std::vector<pna::FileEntryBuilder> files(n);
+        for (uint32_t i = 0; i < n; i++) { files[i].name = names[i]; files[i].data = pna_span{data[i], lens[i]}; }
+        pna::WriteOptions opt;
+        opt.compression = compression; opt.level = level; opt.encryption = encryption; opt.cipher_mode = cipher_mode;
+        if (key) memcpy(opt.key, key, 32);
+        if (phsf) opt.phsf = phsf;
+        *out_len = pna::create_solid_archive_into(files, opt, max_chunk_size, device, out, cap);
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
 }
 int pnah_create(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs,
                 uint8_t compression, int32_t level, uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf,

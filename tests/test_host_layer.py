@@ -233,3 +233,21 @@ def test_extract_to_dir_and_create_from_files(host, pna, ctx, oracle, golden, tm
 
 def host_sanitize(name):
     return "/".join(c for c in name.split("/") if c not in ("", ".", ".."))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("comp,enc,mode", [(2, 0, 0), (2, 1, 1), (2, 2, 2), (1, 1, 0), (0, 0, 0)])
+def test_create_solid_with_cpp_host_is_reference_readable(host, pna, ctx, oracle, comp, enc, mode):
+    """Solid create in C++ (write_solid_header -> add_entry -> finalize, archive/write.rs:438-471): the oracle's restatement of the
+    reference reader (SolidEntry::entries, inner chunk CRCs included) and our own C++ reader extract the same files
+    (cli/tests/cli/solid_mode.rs round trip shape)."""
+    opts = pna.WriteOptions(compression=comp, encryption=enc, cipher_mode=mode, password=b"pw", kdf_params={"i": 1000})
+    files = [(f"solid/f{i:03d}.bin", corpus.make_file(700 + i, n)) for i, n in enumerate([0, 1, 100, 70_000, 1_400_000, 33_000, 2_500_000])]
+    blob = host.create_solid_archive(files, compression=comp, encryption=enc, cipher_mode=mode, key=opts.key, phsf=opts.phsf,
+                                     max_chunk_size=32 * 1024)
+    assert list(oracle.extract_all(blob.tobytes(), b"pw")) == files
+    a = host.HostArchive(blob)
+    if enc:
+        a.set_key(opts.phsf, opts.key)
+    back = a.read_all(workers=2, group_bytes=300_000)
+    assert [(n, d) for n, _, d in back] == files and all(s == 0 for _, s, _ in back)
