@@ -932,6 +932,10 @@ struct PinnedBuf {   // RAII lease
 // the inner entries are written STORE, chunk by chunk, into ONE stream that is compressed + encrypted as a whole and cut into
 // SDAT bodies (wire order lib/src/entry.rs:471-483).  Inner chunk CRCs, the encode and the outer chunk CRCs are three GPU calls.
 // The stream this library writes is one zstd frame per MiB, so the solid entry decodes frame-parallel (DESIGN "Frame-parallel streams").
+// max_chunk_size cuts the SDAT bodies; an inner entry's data stays in FDAT chunks as large as the format allows (the inner entries are
+// built before they are added, lib/src/entry/builder/solid.rs: their chunking is independent of the solid stream's), which also keeps
+// the reader's inner CRC checks and range copies few and large.
+static constexpr uint64_t INNER_FDAT = 0x40000000ull;
 uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
                                    uint8_t* out, uint64_t cap) {
     const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull;
@@ -942,7 +946,7 @@ uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, c
     std::vector<uint64_t> at(files.size());
     for (size_t i = 0; i < files.size(); i++) {
         at[i] = inner_len;
-        const uint64_t D = files[i].data.len, nb = (D + mcs - 1) / mcs;
+        const uint64_t D = files[i].data.len, nb = (D + INNER_FDAT - 1) / INNER_FDAT;
         inner_len += (12 + 6 + files[i].name.size()) + (12 + 8) + nb * 12 + D + 12;
     }
     PinnedBuf inner_buf(L.ctx, inner_len + 64);
@@ -968,7 +972,7 @@ uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, c
         int skip = 0;
         while (skip < 8 && sz[skip] == 0) skip++;
         put("fSIZ", sz + skip, (uint64_t)(8 - skip));
-        for (uint64_t o = 0; o < f.data.len; o += mcs) put("FDAT", f.data.ptr + o, std::min<uint64_t>(mcs, f.data.len - o));
+        for (uint64_t o = 0; o < f.data.len; o += INNER_FDAT) put("FDAT", f.data.ptr + o, std::min<uint64_t>(INNER_FDAT, f.data.len - o));
         put("FEND", nullptr, 0);
     }
     inner_len = w;
@@ -1047,7 +1051,7 @@ uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, c
 uint64_t create_solid_archive_bound(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size) {
     const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull;
     uint64_t inner = 0;
-    for (const auto& f : files) inner += (12 + 6 + f.name.size()) + (12 + 8) + ((f.data.len + mcs - 1) / mcs) * 12 + f.data.len + 12;
+    for (const auto& f : files) inner += (12 + 6 + f.name.size()) + (12 + 8) + ((f.data.len + INNER_FDAT - 1) / INNER_FDAT) * 12 + f.data.len + 12;
     const uint64_t sb = stream_bound_of(inner, opt);
     return 8 + 20 + 17 + 12 + opt.phsf.size() + 12 + 75 + (sb / mcs + 2) * 12 + sb + 24 + 64;
 }
