@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--cfg1-files", type=int, default=2500)
     ap.add_argument("--io-files", type=int, default=256)
     ap.add_argument("--gcm-files", type=int, default=256)
+    ap.add_argument("--own-files", type=int, default=256)
     ap.add_argument("--only", default="")
     ap.add_argument("--workers", type=int, default=2)
     ap.add_argument("--group-mib", type=int, default=64)
@@ -382,6 +383,43 @@ def main():
                           "create_kernel_only_GBps": U / (sum(c_stage.values()) * 1e-3) / 1e9, "create_stage_ms": c_stage,
                           "create_gcm_stage_GBps_of_ciphertext": c_gpu / (c_stage.get("cipher", 0) * 1e-3 + 1e-12) / 1e9}), flush=True)
         del files, streams, img
+
+    if args.only in ("", "own"):
+        # an archive WRITTEN BY THIS LIBRARY (cfg2's shape: 4 MiB files, zstd + AES-256-CTR; 32 KiB blocks, one frame per MiB) read back:
+        # kernel-only through one plan and end to end through the C++ host layer
+        import torch
+        n = args.own_files
+        with mp.get_context("fork").Pool(min(ncpu, 64)) as pool:
+            files = pool.map(_big, list(range(n)), chunksize=4)
+        U = sum(len(f) for f in files)
+        pl = ctx.pinned(U)
+        views, pos = [], 0
+        for f in files:
+            pl[pos:pos + len(f)] = np.frombuffer(f, dtype=np.uint8)
+            views.append(pl[pos:pos + len(f)])
+            pos += len(f)
+        oopts = pna.WriteOptions(compression=2, encryption=1, cipher_mode=1, password=b"pw", kdf_params={"i": 1000})
+        arch = ctx.pinned(int(U * 1.05) + (8 << 20))
+        blob = host.create_archive([(f"own/{i:05d}.bin", v) for i, v in enumerate(views)], compression=2, level=3, encryption=1, cipher_mode=1,
+                                   key=oopts.key, phsf=oopts.phsf, max_chunk_size=0, device=0, workers=4, group_bytes=256 << 20, out=arch)
+        torch.cuda.synchronize()
+        a = pna.Archive.read_header(blob, ctx, verify=False)
+        ro = pna.ReadOptions.with_password(b"pw")
+        ro._keys[oopts.phsf] = oopts.key
+        plan, ents = a.extract_plan(ro)
+        for _ in range(4):
+            plan.run()
+        stage = plan.stage_ms()
+        cnt = plan.counts()
+        outs, st, _ = plan.fetch([len(f) for f in files])
+        assert list(st) == [0] * n and all(outs[k].tobytes() == files[k] for k in range(0, n, max(1, n // 16)))
+        plan.close()
+        edt, _, eout, eoffs, est, _ = timed_extract(host, ctx, blob, oopts.phsf, oopts.key, U, n, workers=args.workers, group_mib=args.group_mib)
+        assert est == [0] * n
+        print(json.dumps({"config": "own", "files": n, "plain_bytes": U, "archive_bytes": int(blob.size), "codec": "this library's zstd writer + aes-256-ctr",
+                          "kernel_only_GBps": U / (sum(stage.values()) * 1e-3) / 1e9, "kernel_only_ms": sum(stage.values()), "stage_ms": stage,
+                          "counts": cnt, "extract_e2e_GBps": U / edt / 1e9, "extract_e2e_ms": edt * 1e3}), flush=True)
+        del files, pl, arch
 
     if args.only in ("", "cfg1"):
         n = args.cfg1_files
