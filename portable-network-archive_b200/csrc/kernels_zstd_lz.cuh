@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
                 if (lane >= a && lane < top) (oblk + (int64_t)bpos)[lane] = win[lane];
                 if (lane == 0) misc[3] = 0;
             }
+            __syncwarp();   // a second call in the same flush must see the cleared mark
         }
     };
 
