@@ -955,9 +955,12 @@ uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, c
     std::vector<pna_span> spans;
     std::vector<uint64_t> crc_at;
     uint64_t w = 0;
-    auto put = [&](const char* ty, const uint8_t* data, uint64_t len) {
+    // bodies of a MiB and more are copied afterwards by a few threads (the copy is the host-side cost of solid mode)
+    std::vector<uint64_t> big_dst, big_len;
+    std::vector<const uint8_t*> big_src;
+    auto put = [&](const char* ty, const uint8_t* data, uint64_t copy_len, uint64_t len) {
         wr_be32(inner + w, (uint32_t)len); memcpy(inner + w + 4, ty, 4);
-        if (len) memcpy(inner + w + 8, data, len);
+        if (copy_len) memcpy(inner + w + 8, data, copy_len);
         spans.push_back({inner + w + 4, len + 4});
         crc_at.push_back(w + 8 + len);
         w += 12 + len;
@@ -966,16 +969,29 @@ uint64_t create_solid_archive_into(const std::vector<FileEntryBuilder>& files, c
         const FileEntryBuilder& f = files[i];
         std::vector<uint8_t> h = {0, 0, (uint8_t)DataKind::File, 0, 0, 0};
         h.insert(h.end(), f.name.begin(), f.name.end());
-        put("FHED", h.data(), h.size());
+        put("FHED", h.data(), h.size(), h.size());
         uint8_t sz[8];
         for (int b = 0; b < 8; b++) sz[b] = (uint8_t)(f.data.len >> (8 * (7 - b)));
         int skip = 0;
         while (skip < 8 && sz[skip] == 0) skip++;
-        put("fSIZ", sz + skip, (uint64_t)(8 - skip));
-        for (uint64_t o = 0; o < f.data.len; o += INNER_FDAT) put("FDAT", f.data.ptr + o, std::min<uint64_t>(INNER_FDAT, f.data.len - o));
-        put("FEND", nullptr, 0);
+        put("fSIZ", sz + skip, (uint64_t)(8 - skip), (uint64_t)(8 - skip));
+        for (uint64_t o = 0; o < f.data.len; o += INNER_FDAT) {
+            const uint64_t len = std::min<uint64_t>(INNER_FDAT, f.data.len - o);
+            if (len >= (1u << 20)) { big_dst.push_back(w + 8); big_src.push_back(f.data.ptr + o); big_len.push_back(len); put("FDAT", nullptr, 0, len); }
+            else put("FDAT", f.data.ptr + o, len, len);
+        }
+        put("FEND", nullptr, 0, 0);
     }
     inner_len = w;
+    if (!big_dst.empty()) {
+        std::atomic<size_t> next{0};
+        auto copier = [&]() { for (size_t k; (k = next.fetch_add(1)) < big_dst.size();) memcpy(inner + big_dst[k], big_src[k], big_len[k]); };
+        const int nt = (int)std::min<size_t>(8, big_dst.size());
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(copier);
+        copier();
+        for (auto& t : th) t.join();
+    }
     {
         std::vector<uint32_t> crcs(spans.size());
         for (size_t b0 = 0; b0 < spans.size(); b0 += 1u << 20) {   // batches of a million chunks
