@@ -17,6 +17,7 @@
 #include <cstring>
 #include <future>
 #include <mutex>
+#include <functional>
 #include <random>
 #include <set>
 #include <thread>
@@ -642,8 +643,12 @@ static uint64_t stream_bound_of(uint64_t plain_len, const WriteOptions& opt) {
 // Archive::write_header + add_entry per file + finalize (archive/write.rs:92,368,545; wire order entry.rs:895-912), written
 // straight into `out`: every worker encodes one group of files on its own pna_ctx, learns the produced stream lengths,
 // takes its place behind the previous group, and lets the GPU copy the streams to their final position (D2H).
-uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
-                             int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap) {
+// on_region (optional): called by the worker that completed a group with the byte range of the archive that is final now
+// (groups are contiguous and cover everything between the archive header and AEND) -- lets a caller write the file while later
+// groups are still being encoded.
+static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
+                                       int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap,
+                                       const std::function<void(uint64_t, uint64_t)>* on_region) {
     const size_t n = files.size();
     struct Group { size_t lo, hi; };
     std::vector<Group> groups;
@@ -858,6 +863,7 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
             put_meta(k * metas_per_entry + metas_per_entry - 1);   // FEND
             cpos += ncrc[k];
         }
+        if (on_region) (*on_region)(my_base, entry_pos[m]);
         if (trace) fprintf(stderr, "[pna_host] create group %zu (%u files): plan_create/H2D %.1f-%.1f, lengths(wait) %.1f-%.1f, fetch/D2H %.1f-%.1f, frames -%.1f ms\n",
                            g, m, S.t_issue0, S.t_issue1, tr2, tr3, tr4, tr5, ms_now());
     };
@@ -900,6 +906,11 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
         wr_be32(out + end, 0); memcpy(out + end + 4, meta.data() + re.off, 4); wr_be32(out + end + 8, mcrc[n * metas_per_entry + 1]);
     }
     return end + 12;
+}
+
+uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
+                             int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap) {
+    return create_archive_regions(files, opt, max_chunk_size, device, workers, group_bytes, out, cap, nullptr);
 }
 
 std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
@@ -1256,27 +1267,29 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
     PinnedBuf arch_buf(L.ctx, bound + 64);
     uint8_t* const arch = arch_buf.p;
     if (!arch) throw Error(PNA_E_OOM, "pinned archive buffer");
-    const uint64_t alen = create_archive_into(files, opt, max_chunk_size, device, workers, group_bytes, arch, bound);
+    // the archive file is written WHILE later groups are encoded: every worker writes the group it has just completed (its next
+    // group's kernels are already running on its other context); the header and AEND follow at the end
+    const int fd = open(archive_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) throw Error(PNA_E_INTERNAL, "open " + archive_path + ": " + strerror(errno));
+    auto write_range = [&](uint64_t o, uint64_t len) {
+        const uint64_t end = o + len;
+        while (o < end) {
+            const ssize_t w = pwrite(fd, arch + o, (size_t)(end - o), (off_t)o);
+            if (w < 0) { if (errno == EINTR) continue; throw Error(PNA_E_INTERNAL, "write " + archive_path + ": " + strerror(errno)); }
+            o += (uint64_t)w;
+        }
+    };
+    const std::function<void(uint64_t, uint64_t)> on_region = write_range;
+    uint64_t alen = 0;
+    try {
+        alen = create_archive_regions(files, opt, max_chunk_size, device, workers, group_bytes, arch, bound, &on_region);
+        write_range(0, 8 + 20);
+        write_range(alen - 12, 12);
+    } catch (...) { close(fd); throw; }
+    close(fd);
+    (void)io_threads;
     const auto t_gpu = std::chrono::steady_clock::now();
-    st.gpu_ms = ms_between(t_read, t_gpu);
-    {   // the archive file, written by io_threads writers (pwrite of 64 MiB pieces)
-        const int fd = open(archive_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (fd < 0) throw Error(PNA_E_INTERNAL, "open " + archive_path + ": " + strerror(errno));
-        const uint64_t piece = (uint64_t)64 << 20, np = (alen + piece - 1) / piece;
-        try {
-            parallel_for((size_t)np, io_threads, [&](size_t k) {
-                uint64_t o = k * piece;
-                const uint64_t end = std::min<uint64_t>(alen, o + piece);
-                while (o < end) {
-                    const ssize_t w = pwrite(fd, arch + o, (size_t)(end - o), (off_t)o);
-                    if (w < 0) { if (errno == EINTR) continue; throw Error(PNA_E_INTERNAL, "write " + archive_path + ": " + strerror(errno)); }
-                    o += (uint64_t)w;
-                }
-            });
-        } catch (...) { close(fd); throw; }
-        close(fd);
-    }
-    st.io_ms += ms_between(t_gpu, std::chrono::steady_clock::now());
+    st.gpu_ms = ms_between(t_read, t_gpu);   // encode with the file writes riding on it
     st.files = n;
     st.total_ms = ms_between(t_begin, std::chrono::steady_clock::now());
     return st;
