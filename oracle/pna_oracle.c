@@ -27,7 +27,7 @@
  *                                 bytes differ from miniz_oxide, decode is a unique function)
  *
  * Parity is PINNED: tests/test_oracle.py and tests/test_gcm.py check this file against the reference's own
- * golden archives (resources/test/*.pna vs resources/test/raw) and the KATs in
+ * golden archives (resources/test/NAME.pna vs resources/test/raw) and the KATs in
  * lib/src/format/chunk.rs:31, lib/src/io.rs:179, lib/src/cipher.rs:256-292.
  */
 #define _GNU_SOURCE
