@@ -89,6 +89,12 @@ public:
     Archive(const Archive&) = delete;
     Archive& operator=(const Archive&) = delete;
     static Archive read_header_from_slice(const uint8_t* buf, size_t len);
+    // Split archive (archive/read.rs:105-165 read_next_archive; writer archive/split_parts.rs): part k is a complete chunk
+    // stream with archive_number k that ends ... [ANXT] AEND, and an entry's chunks simply continue in the next part.  The
+    // parts are joined into one chunk stream the Archive owns (every chunk frame of every part verbatim, stored CRCs
+    // included: the entry chunks in order, then AEND, the other parts' archive-level chunks behind it), so the CRC check
+    // and the entry groups run as for a single archive.
+    static Archive read_multipart(const pna_span* parts, size_t n_parts);
     const std::vector<RawChunk>& chunks() const { return chunks_; }
     const std::vector<EntryInfo>& entries() const { return entries_; }
     uint32_t archive_number() const { return archive_number_; }
@@ -119,6 +125,7 @@ private:
     };
     const uint8_t* buf_ = nullptr;
     size_t len_ = 0;
+    std::shared_ptr<uint8_t> joined_;          // read_multipart: the joined chunk stream buf_ points into
     uint32_t archive_number_ = 0;
     std::vector<RawChunk> chunks_;
     std::vector<EntryInfo> entries_;
@@ -191,6 +198,7 @@ typedef struct {
 } pnah_entry_info;
 typedef struct { uint64_t files, dirs, skipped, bytes; double index_ms, gpu_ms, io_ms, total_ms; } pnah_io_stats;
 int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, uint64_t errcap);
+int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, pnah_archive** out, char* err, uint64_t errcap);   /* split archive: parts in order; the handle owns a joined copy */
 int pnah_open_file(const char* path, pnah_archive** out, char* err, uint64_t errcap);   /* mmap; the handle owns the mapping */
 int pnah_extract_to_dir(pnah_archive* a, const char* out_dir, int device, int workers, uint64_t group_bytes, uint64_t window_bytes,
                         int io_threads, int verify, pnah_io_stats* stats, int32_t* status /* per file, may be NULL */, char* err,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpna_host.so")
 EXPORTS = ["pnah_open", "pnah_close", "pnah_entry_count", "pnah_entry_get", "pnah_chunk_count", "pnah_set_key", "pnah_prepare",
            "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound", "pnah_create_solid", "pnah_create_solid_bound",
-           "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files"]
+           "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files", "pnah_open_multipart"]
 
 
 class EntryInfo(C.Structure):
@@ -64,6 +64,7 @@ def lib():
         L.pnah_create_solid.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(u64), C.c_uint8, C.c_int32, C.c_uint8, C.c_uint8,
                                         C.c_char_p, C.c_char_p, u32, C.c_int, vp, u64, C.POINTER(u64), C.c_char_p, u64]
         L.pnah_open_file.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, u64]
+        L.pnah_open_multipart.argtypes = [C.POINTER(vp), C.POINTER(u64), u32, C.POINTER(vp), C.c_char_p, u64]
         L.pnah_extract_to_dir.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, u64, u64, C.c_int, C.c_int, C.POINTER(IoStats),
                                           C.POINTER(C.c_int32), C.c_char_p, u64]
         L.pnah_create_from_files.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_uint8, C.c_int32, C.c_uint8, C.c_uint8,
@@ -91,6 +92,23 @@ class HostArchive:
         if rc:
             raise HostError(rc, err.value.decode())
         self.h = h
+
+    @classmethod
+    def open_multipart(cls, parts):
+        """Split archive (archive/read.rs:105-165): `parts` in order, bytes-like or uint8 arrays; the handle owns a joined copy."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        bufs = [p if isinstance(p, np.ndarray) else np.frombuffer(p, dtype=np.uint8) for p in parts]
+        self.buf = None
+        ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        lens = (C.c_uint64 * len(bufs))(*[b.size for b in bufs])
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = self.L.pnah_open_multipart(ptrs, lens, len(bufs), C.byref(h), err, 512)
+        if rc:
+            raise HostError(rc, err.value.decode())
+        self.h = h
+        return self
 
     @classmethod
     def open_file(cls, path: str):

@@ -306,6 +306,45 @@ Archive Archive::read_header_from_slice(const uint8_t* buf, size_t len) {
     return a;
 }
 
+Archive Archive::read_multipart(const pna_span* parts, size_t n_parts) {
+    if (n_parts == 0) throw Error(PNA_E_INVALID_INPUT, "no archive part given");
+    std::vector<std::vector<RawChunk>> lists(n_parts);
+    uint64_t total = 8;
+    for (size_t k = 0; k < n_parts; k++) {
+        const uint8_t* b = parts[k].ptr;
+        const size_t len = (size_t)parts[k].len;
+        if (len < 8 || memcmp(b, SIGNATURE, 8) != 0) throw Error(PNA_E_INVALID_DATA, "it is not PNA");
+        std::vector<RawChunk>& ch = lists[k];
+        index_chunks(b, len, 8, ch);
+        if (ch.empty() || !ty_is(ch[0], "AHED") || ch[0].len != 8) throw Error(PNA_E_INVALID_DATA, "expected `AHED` chunk");
+        if (b[ch[0].off] != 0) throw Error(PNA_E_UNSUPPORTED, "archive version is not supported");
+        if (be32(b + ch[0].off + 4) != (uint32_t)k) throw Error(PNA_E_INVALID_DATA, "part " + std::to_string(k) + " carries archive number " + std::to_string(be32(b + ch[0].off + 4)));
+        if (ty32(ch.back()) != T_AEND) throw Error(PNA_E_UNEXPECTED_EOF, "part without `AEND`");
+        bool has_next = false;
+        for (const RawChunk& c : ch) { has_next |= ty32(c) == T_ANXT; total += 12 + (uint64_t)c.len; }
+        if (has_next && k + 1 == n_parts) throw Error(PNA_E_UNEXPECTED_EOF, "next part missing");
+        if (!has_next && k + 1 < n_parts) throw Error(PNA_E_INVALID_DATA, "part does not announce a next archive (`ANXT`)");
+    }
+    std::shared_ptr<uint8_t> mem(new uint8_t[total], std::default_delete<uint8_t[]>());
+    uint8_t* w = mem.get();
+    memcpy(w, SIGNATURE, 8); w += 8;
+    auto put = [&](size_t k, const RawChunk& c) { memcpy(w, parts[k].ptr + c.off - 8, 12 + (size_t)c.len); w += 12 + (size_t)c.len; };
+    auto archive_level = [](const RawChunk& c) { const uint32_t t = ty32(c); return t == T_AEND || t == T_ANXT || t == ty32("AHED"); };
+    put(0, lists[0][0]);
+    for (size_t k = 0; k < n_parts; k++)
+        for (const RawChunk& c : lists[k]) if (!archive_level(c)) put(k, c);
+    put(n_parts - 1, lists[n_parts - 1].back());
+    for (size_t k = 0; k < n_parts; k++)              // behind AEND: indexed and CRC-checked, never grouped
+        for (size_t i = 0; i < lists[k].size(); i++) {
+            const RawChunk& c = lists[k][i];
+            const bool placed = (k == 0 && i == 0) || (k + 1 == n_parts && i + 1 == lists[k].size());
+            if (archive_level(c) && !placed) put(k, c);
+        }
+    Archive a = read_header_from_slice(mem.get(), (size_t)total);
+    a.joined_ = std::move(mem);
+    return a;
+}
+
 static bool cipher_supported(const EntryInfo& e) {
     return (e.encryption == PNA_ENCRYPTION_AES || e.encryption == PNA_ENCRYPTION_CAMELLIA) &&
            (e.cipher_mode == PNA_CIPHER_CBC || e.cipher_mode == PNA_CIPHER_CTR || e.cipher_mode == PNA_CIPHER_GCM);
@@ -1316,6 +1355,15 @@ int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, u
         *out = h;
         return PNA_OK;
     } catch (const pna::Error& e) { *out = nullptr; return fail(e, err, errcap); }
+}
+int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, pnah_archive** out, char* err, uint64_t errcap) {
+    *out = nullptr;
+    try {
+        std::vector<pna_span> sp(n_parts);
+        for (uint32_t k = 0; k < n_parts; k++) sp[k] = pna_span{parts[k], lens[k]};
+        *out = new pnah_archive{pna::Archive::read_multipart(sp.data(), sp.size()), {}};
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
 }
 void pnah_close(pnah_archive* a) { delete a; }
 int pnah_open_file(const char* path, pnah_archive** out, char* err, uint64_t errcap) {

@@ -251,3 +251,84 @@ def test_create_solid_with_cpp_host_is_reference_readable(host, pna, ctx, oracle
         a.set_key(opts.phsf, opts.key)
     back = a.read_all(workers=2, group_bytes=300_000)
     assert [(n, d) for n, _, d in back] == files and all(s == 0 for _, s, _ in back)
+
+
+# ---------------------------------------------------------------------------------------------- split archives (C++ reader)
+def _frame(ty: bytes, data: bytes = b"") -> bytes:
+    import struct
+    import zlib
+    return struct.pack(">I", len(data)) + ty + data + struct.pack(">I", zlib.crc32(ty + data))
+
+
+def _split_at_chunks(buf: np.ndarray, n_parts: int):
+    """What archive/split_parts.rs produces when no chunk has to be cut: part k = signature, AHED(archive_number k), a run of
+    the archive's chunks, [ANXT], AEND.  The cuts fall between ANY two chunks, so entries and their FDAT streams straddle parts."""
+    raw = buf.tobytes()
+    pos, frames = 8, []
+    while pos < len(raw):
+        ln = int.from_bytes(raw[pos:pos + 4], "big")
+        frames.append(raw[pos:pos + 12 + ln])
+        pos += 12 + ln
+    ahed, body = frames[0], frames[1:-1]
+    assert ahed[4:8] == b"AHED" and frames[-1][4:8] == b"AEND"
+    per = -(-len(body) // n_parts)
+    parts = []
+    for k in range(n_parts):
+        head = _frame(b"AHED", ahed[8:12] + k.to_bytes(4, "big"))
+        tail = (_frame(b"ANXT") if k + 1 < n_parts else b"") + _frame(b"AEND")
+        parts.append(np.frombuffer(raw[:8] + head + b"".join(body[k * per:(k + 1) * per]) + tail, dtype=np.uint8))
+    return parts
+
+
+def test_cpp_multipart_index(host, pna, golden):
+    """archive/read.rs:105-165: the reference's two-part fixture is ONE entry with two FDAT bodies; part order, a missing
+    part and a part behind the last one are errors.  Every chunk of every part stays in the index (CRC-checked later)."""
+    p1 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part1.pna"), dtype=np.uint8)
+    p2 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part2.pna"), dtype=np.uint8)
+    a = host.HostArchive.open_multipart([p1, p2])
+    es = a.entries()
+    assert len(es) == 1 and es[0]["name"] == "multipart_test.txt" and es[0]["n_bodies"] == 2
+    mod = importlib.import_module("portable-network-archive_b200.archive")
+    assert a.n_chunks == len(mod.index_archive(p1, 8)) + len(mod.index_archive(p2, 8))
+    for bad, kind in (([p2, p1], pna.E_INVALID_DATA), ([p1], pna.E_UNEXPECTED_EOF), ([p1, p2, p2], pna.E_INVALID_DATA),
+                      ([p1, p2[:-5]], pna.E_UNEXPECTED_EOF), ([], pna.E_INVALID_INPUT)):
+        with pytest.raises(host.HostError) as ei:
+            host.HostArchive.open_multipart(bad)
+        assert ei.value.kind == kind
+    # a fixture cut into three parts between arbitrary chunks groups into the same entries as the single archive
+    info = golden["archives"]["zstd_aes_ctr.pna"]
+    buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+    one = host.HostArchive(buf).entries()
+    three = host.HostArchive.open_multipart(_split_at_chunks(buf, 3)).entries()
+    assert [(e["name"], e["compressed_size"], e["n_bodies"]) for e in one] == [(e["name"], e["compressed_size"], e["n_bodies"]) for e in three]
+
+
+@pytest.mark.gpu
+def test_cpp_multipart_extract(host, pna, ctx, golden):
+    """extract_multipart_compatibility.rs:36 through the C++ host layer, plus golden archives re-split into 2..4 parts."""
+    p1 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part1.pna"), dtype=np.uint8)
+    p2 = np.fromfile(os.path.join(golden["dir"], "ref", "multipart.part2.pna"), dtype=np.uint8)
+    want = open(os.path.join(golden["dir"], "ref", "multipart_test.txt"), "rb").read()
+    got = host.HostArchive.open_multipart([p1, p2]).read_all()
+    assert [(n, s) for n, s, _ in got] == [("multipart_test.txt", 0)] and got[0][2] == want
+    for name, n_parts in (("zstd.pna", 2), ("zstd_aes_ctr.pna", 3), ("deflate.pna", 4), ("solid_zstd.pna", 2), ("zstd_camellia_cbc.pna", 3)):
+        info = golden["archives"][name]
+        buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+        a = host.HostArchive.open_multipart(_split_at_chunks(buf, n_parts))
+        for phsf, key in info["keys"].items():
+            a.set_key(phsf, bytes.fromhex(key))
+        got = a.read_all(workers=2, group_bytes=20_000)
+        assert [n for n, _, _ in got] == [e["name"] for e in info["entries"]], name
+        for (n, st, d), e in zip(got, info["entries"]):
+            assert st == 0 and len(d) == e["size"] and hashlib.sha256(d).hexdigest() == e["sha256"], (name, n)
+    # a flipped bit in a later part's archive-level chunk (its AHED) is an archive error, in an entry chunk an entry error
+    buf = np.fromfile(os.path.join(golden["dir"], golden["archives"]["zstd.pna"]["file"]), dtype=np.uint8)
+    parts = [p.copy() for p in _split_at_chunks(buf, 2)]
+    parts[1][8 + 8 + 1] ^= 1      # minor version byte of part 2's AHED: framing intact, CRC wrong
+    with pytest.raises(host.HostError) as ei:
+        host.HostArchive.open_multipart(parts).extract_files()
+    assert ei.value.kind == pna.E_INVALID_DATA
+    parts = [p.copy() for p in _split_at_chunks(buf, 2)]
+    parts[1][len(parts[1]) // 2] ^= 0x40
+    out, offs, st = host.HostArchive.open_multipart(parts).extract_files()
+    assert st.count(pna.E_INVALID_DATA) >= 1 and st.count(0) >= 1
