@@ -164,6 +164,14 @@ uint64_t create_solid_archive_bound(const std::vector<FileEntryBuilder>& files, 
 uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
                              int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap);
 
+// Split writer (lib/src/archive/split_parts.rs:90-188 SplitParts::{new, put_chunk, put_stream, roll_over}): a finished archive is cut
+// into parts of at most max_part_bytes.  Part k = signature, AHED(0, 0, k), chunks, [ANXT], AEND; a chunk that fits the part's
+// remaining budget is copied verbatim, FDAT / SDAT chunks that do not are re-cut at the budget boundary (their new CRCs, like those
+// of the new AHED / ANXT / AEND chunks, come from ONE pna_cuda_crc32 batch over the laid-out parts), other chunks move to the next
+// part.  Errors as the reference: InvalidInput below MIN_SPLIT_PART_BYTES (64) or when a non-stream chunk exceeds a part.
+constexpr uint64_t MIN_SPLIT_PART_BYTES = 64;
+std::vector<std::vector<uint8_t>> split_archive(const uint8_t* archive, size_t len, uint64_t max_part_bytes, int device);
+
 // ---- the file-system side of the path (SURVEY 8f "next", item 1): the CLI's extract / create data flow around the kernels
 struct IoStats {
     uint64_t files = 0, dirs = 0, skipped = 0, bytes = 0;   // skipped: links and other non-file kinds, entries that failed
@@ -199,6 +207,10 @@ typedef struct {
 typedef struct { uint64_t files, dirs, skipped, bytes; double index_ms, gpu_ms, io_ms, total_ms; } pnah_io_stats;
 int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, uint64_t errcap);
 int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, pnah_archive** out, char* err, uint64_t errcap);   /* split archive: parts in order; the handle owns a joined copy */
+/* split writer: parts are written back to back into out (cap bytes), their lengths into part_lens (max_parts slots).  PNA_E_NOSPACE
+ * when either is too small; *total and *n_parts always carry what is needed. */
+int pnah_split(const uint8_t* archive, uint64_t len, uint64_t max_part_bytes, int device, uint8_t* out, uint64_t cap, uint64_t* total,
+               uint64_t* part_lens, uint32_t max_parts, uint32_t* n_parts, char* err, uint64_t errcap);
 int pnah_open_file(const char* path, pnah_archive** out, char* err, uint64_t errcap);   /* mmap; the handle owns the mapping */
 int pnah_extract_to_dir(pnah_archive* a, const char* out_dir, int device, int workers, uint64_t group_bytes, uint64_t window_bytes,
                         int io_threads, int verify, pnah_io_stats* stats, int32_t* status /* per file, may be NULL */, char* err,

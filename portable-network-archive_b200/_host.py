@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpna_host.so")
 EXPORTS = ["pnah_open", "pnah_close", "pnah_entry_count", "pnah_entry_get", "pnah_chunk_count", "pnah_set_key", "pnah_prepare",
            "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound", "pnah_create_solid", "pnah_create_solid_bound",
-           "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files", "pnah_open_multipart"]
+           "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files", "pnah_open_multipart", "pnah_split"]
 
 
 class EntryInfo(C.Structure):
@@ -64,6 +64,7 @@ def lib():
         L.pnah_create_solid.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(u64), C.c_uint8, C.c_int32, C.c_uint8, C.c_uint8,
                                         C.c_char_p, C.c_char_p, u32, C.c_int, vp, u64, C.POINTER(u64), C.c_char_p, u64]
         L.pnah_open_file.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, u64]
+        L.pnah_split.argtypes = [vp, u64, u64, C.c_int, vp, u64, C.POINTER(u64), C.POINTER(u64), u32, C.POINTER(u32), C.c_char_p, u64]
         L.pnah_open_multipart.argtypes = [C.POINTER(vp), C.POINTER(u64), u32, C.POINTER(vp), C.c_char_p, u64]
         L.pnah_extract_to_dir.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, u64, u64, C.c_int, C.c_int, C.POINTER(IoStats),
                                           C.POINTER(C.c_int32), C.c_char_p, u64]
@@ -214,6 +215,29 @@ class HostArchive:
         for i, (name, size, _) in enumerate(self.files()):
             res.append((name, st[i], out[int(offs[i]):int(offs[i]) + size].tobytes() if st[i] == 0 else None))
         return res
+
+
+def split_archive(archive, max_part_bytes: int, device=0):
+    """Split writer (lib/src/archive/split_parts.rs): a finished archive cut into parts of at most max_part_bytes.  Returns the
+    parts as uint8 arrays."""
+    L = lib()
+    buf = archive if isinstance(archive, np.ndarray) else np.frombuffer(archive, dtype=np.uint8)
+    err = C.create_string_buffer(512)
+    total, n_parts = C.c_uint64(0), C.c_uint32(0)
+    out, lens = np.empty(0, dtype=np.uint8), (C.c_uint64 * 1)()
+    for _ in range(2):
+        rc = L.pnah_split(buf.ctypes.data, buf.size, max_part_bytes, device, out.ctypes.data, out.size, C.byref(total), lens, len(lens),
+                          C.byref(n_parts), err, 512)
+        if rc != _ffi.E_NOSPACE:
+            break
+        out, lens = np.empty(total.value, dtype=np.uint8), (C.c_uint64 * n_parts.value)()
+    if rc:
+        raise HostError(rc, err.value.decode())
+    parts, at = [], 0
+    for k in range(n_parts.value):
+        parts.append(out[at:at + lens[k]])
+        at += lens[k]
+    return parts
 
 
 def create_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, key=None, phsf=None, ivs=None, max_chunk_size=0,

@@ -1334,6 +1334,83 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
     return st;
 }
 
+// ---- split writer (archive/split_parts.rs)
+std::vector<std::vector<uint8_t>> split_archive(const uint8_t* archive, size_t len, uint64_t max_part_bytes, int device) {
+    if (max_part_bytes < MIN_SPLIT_PART_BYTES)       // split_parts.rs:91-96
+        throw Error(PNA_E_INVALID_INPUT, "max_part_bytes must be at least " + std::to_string(MIN_SPLIT_PART_BYTES) + " bytes");
+    if (len < 8 || memcmp(archive, SIGNATURE, 8) != 0) throw Error(PNA_E_INVALID_DATA, "it is not PNA");
+    std::vector<RawChunk> ch;
+    index_chunks(archive, len, 8, ch);
+    if (ch.empty() || !ty_is(ch[0], "AHED")) throw Error(PNA_E_INVALID_DATA, "expected `AHED` chunk");
+    size_t end = ch.size();
+    for (size_t i = 0; i < ch.size(); i++) if (ty32(ch[i]) == T_AEND || ty32(ch[i]) == T_ANXT) { end = i; break; }
+    if (end == ch.size()) throw Error(PNA_E_UNEXPECTED_EOF, "archive without `AEND`");
+    const uint64_t MINC = 12, budget = max_part_bytes - 52;   // signature 8 + AHED 20 + ANXT 12 + AEND 12
+    std::vector<std::vector<uint8_t>> parts;
+    struct Fix { uint32_t part; uint64_t at, n; };   // freshly framed chunk: type||data at parts[part][at .. at+n), CRC behind it
+    std::vector<Fix> fixes;
+    uint64_t remaining = 0;
+    auto frame = [&](const char* ty, const uint8_t* data, uint32_t n) {
+        std::vector<uint8_t>& p = parts.back();
+        put_be32(p, n);
+        fixes.push_back({(uint32_t)parts.size() - 1, p.size(), (uint64_t)n + 4});
+        p.insert(p.end(), ty, ty + 4);
+        p.insert(p.end(), data, data + n);
+        put_be32(p, 0);
+    };
+    auto open_part = [&]() {
+        if (parts.size() > 0xFFFFFFFFull) throw Error(PNA_E_INVALID_INPUT, "too many archive parts");
+        const uint32_t k = (uint32_t)parts.size();
+        parts.emplace_back();
+        parts.back().reserve((size_t)std::min<uint64_t>(max_part_bytes, len + 64));
+        parts.back().insert(parts.back().end(), SIGNATURE, SIGNATURE + 8);
+        const uint8_t h[8] = {0, 0, 0, 0, (uint8_t)(k >> 24), (uint8_t)(k >> 16), (uint8_t)(k >> 8), (uint8_t)k};
+        frame("AHED", h, 8);
+        remaining = budget;
+    };
+    auto roll_over = [&]() { frame("ANXT", nullptr, 0); frame("AEND", nullptr, 0); open_part(); };
+    auto verbatim = [&](const RawChunk& c) {
+        parts.back().insert(parts.back().end(), archive + c.off - 8, archive + c.off + c.len + 4);
+        remaining -= MINC + c.len;
+    };
+    auto does_not_fit = [&](uint64_t n) {
+        return Error(PNA_E_INVALID_INPUT, "a " + std::to_string(n) + " byte chunk does not fit within the maximum part size of " + std::to_string(max_part_bytes) + " bytes");
+    };
+    open_part();
+    for (size_t i = 1; i < end; i++) {
+        const RawChunk& c = ch[i];
+        const uint64_t clen = MINC + c.len;
+        const bool stream = ty32(c) == T_FDAT || ty32(c) == T_SDAT;
+        if (clen <= remaining) { verbatim(c); continue; }
+        if (!stream) {
+            if (clen > budget) throw does_not_fit(clen);
+            roll_over(); verbatim(c); continue;
+        }
+        if (clen <= budget && remaining <= MINC) { roll_over(); verbatim(c); continue; }
+        const uint8_t* data = archive + c.off;
+        uint64_t left = c.len;
+        for (;;) {   // put_stream
+            if (MINC + left <= remaining) { frame(c.ty, data, (uint32_t)left); remaining -= MINC + left; break; }
+            if (remaining > MINC) {
+                const uint64_t take = remaining - MINC;
+                frame(c.ty, data, (uint32_t)take);
+                remaining -= MINC + take; data += take; left -= take;
+            } else if (budget <= MINC) throw does_not_fit(MINC + left);
+            roll_over();
+        }
+    }
+    frame("AEND", nullptr, 0);
+    std::vector<pna_span> spans(fixes.size());
+    std::vector<uint32_t> crc(fixes.size());
+    for (size_t f = 0; f < fixes.size(); f++) spans[f] = pna_span{parts[fixes[f].part].data() + fixes[f].at, fixes[f].n};
+    {
+        CtxLease L(device);
+        ck(L.ctx, pna_cuda_crc32(L.ctx, spans.data(), (uint32_t)spans.size(), crc.data()), "split writer: chunk CRCs");
+    }
+    for (size_t f = 0; f < fixes.size(); f++) wr_be32(parts[fixes[f].part].data() + fixes[f].at + fixes[f].n, crc[f]);
+    return parts;
+}
+
 }  // namespace pna
 
 // ---------------------------------------------------------------------------------------------- flat C view
@@ -1366,6 +1443,18 @@ int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint3
     } catch (const pna::Error& e) { return fail(e, err, errcap); }
 }
 void pnah_close(pnah_archive* a) { delete a; }
+int pnah_split(const uint8_t* archive, uint64_t len, uint64_t max_part_bytes, int device, uint8_t* out, uint64_t cap, uint64_t* total,
+               uint64_t* part_lens, uint32_t max_parts, uint32_t* n_parts, char* err, uint64_t errcap) {
+    try {
+        const std::vector<std::vector<uint8_t>> parts = pna::split_archive(archive, (size_t)len, max_part_bytes, device);
+        uint64_t sum = 0;
+        for (const auto& p : parts) sum += p.size();
+        *total = sum; *n_parts = (uint32_t)parts.size();
+        if (sum > cap || parts.size() > max_parts) return PNA_E_NOSPACE;
+        for (size_t k = 0; k < parts.size(); k++) { memcpy(out, parts[k].data(), parts[k].size()); out += parts[k].size(); part_lens[k] = parts[k].size(); }
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
 int pnah_open_file(const char* path, pnah_archive** out, char* err, uint64_t errcap) {
     *out = nullptr;
     try {

@@ -332,3 +332,104 @@ def test_cpp_multipart_extract(host, pna, ctx, golden):
     parts[1][len(parts[1]) // 2] ^= 0x40
     out, offs, st = host.HostArchive.open_multipart(parts).extract_files()
     assert st.count(pna.E_INVALID_DATA) >= 1 and st.count(0) >= 1
+
+
+# ---------------------------------------------------------------------------------------------- split writer
+def _split_parts_restated(raw: bytes, max_part_bytes: int):
+    """lib/src/archive/split_parts.rs:90-188 restated (SplitParts::new / put_chunk / put_stream / roll_over / finalize), CRCs by
+    zlib: the checker for pna::split_archive."""
+    if max_part_bytes < 64:
+        raise ValueError("max_part_bytes")
+    budget = max_part_bytes - 52
+    parts, st = [], {"remaining": 0}
+
+    def open_part():
+        parts.append(bytearray(raw[:8] + _frame(b"AHED", bytes(4) + len(parts).to_bytes(4, "big"))))
+        st["remaining"] = budget
+
+    def roll_over():
+        parts[-1] += _frame(b"ANXT") + _frame(b"AEND")
+        open_part()
+
+    def write(ty, data):
+        parts[-1] += _frame(ty, data)
+        st["remaining"] -= 12 + len(data)
+
+    open_part()
+    pos = 8
+    first = True
+    while pos < len(raw):
+        ln = int.from_bytes(raw[pos:pos + 4], "big")
+        ty, data = raw[pos + 4:pos + 8], raw[pos + 8:pos + 8 + ln]
+        pos += 12 + ln
+        if first:
+            first = False
+            continue                  # the source AHED: every part gets its own
+        if ty == b"AEND":
+            break
+        clen = 12 + ln
+        if clen <= st["remaining"]:
+            write(ty, data)
+        elif ty not in (b"FDAT", b"SDAT"):
+            if clen > budget:
+                raise ValueError("does not fit")
+            roll_over()
+            write(ty, data)
+        elif clen <= budget and st["remaining"] <= 12:
+            roll_over()
+            write(ty, data)
+        else:
+            while True:
+                if 12 + len(data) <= st["remaining"]:
+                    write(ty, data)
+                    break
+                if st["remaining"] > 12:
+                    take = st["remaining"] - 12
+                    write(ty, data[:take])
+                    data = data[take:]
+                elif budget <= 12:
+                    raise ValueError("does not fit")
+                roll_over()
+    parts[-1] += _frame(b"AEND")
+    return [bytes(p) for p in parts]
+
+
+def test_split_writer_rejects_before_any_gpu_work(host, pna, golden):
+    """split_parts.rs:91-96 (below MIN_SPLIT_PART_BYTES) and :148-150 (a non-stream chunk larger than a part): InvalidInput."""
+    buf = np.fromfile(os.path.join(golden["dir"], golden["archives"]["zstd.pna"]["file"]), dtype=np.uint8)
+    for size in (0, 63, 64, 65):         # at 64/65 the budget (12/13 bytes) cannot hold the first FHED chunk
+        with pytest.raises(host.HostError) as ei:
+            host.split_archive(buf, size)
+        assert ei.value.kind == pna.E_INVALID_INPUT, size
+    with pytest.raises(host.HostError) as ei:
+        host.split_archive(buf[:7], 1000)
+    assert ei.value.kind == pna.E_INVALID_DATA
+
+
+@pytest.mark.gpu
+def test_split_writer_matches_restated_reference_and_reads_back(host, pna, ctx, golden):
+    """Byte-exact parts against the restated SplitParts at part sizes from the reference's own tests (172 = ROLLOVER_PART_MAX,
+    split_parts.rs:374) up to one larger than the archive; every split reads back through the multi-part reader."""
+    for name in ("zstd.pna", "zstd_aes_ctr.pna", "solid_zstd.pna", "deflate.pna"):
+        info = golden["archives"][name]
+        buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+        raw = buf.tobytes()
+        for size in (172, 173, 257, 1000, 4096, 50_000, len(raw) + 100):
+            try:
+                want = _split_parts_restated(raw, size)
+            except ValueError:
+                with pytest.raises(host.HostError) as ei:
+                    host.split_archive(buf, size)
+                assert ei.value.kind == pna.E_INVALID_INPUT
+                continue
+            got = host.split_archive(buf, size)
+            assert [p.tobytes() for p in got] == want, (name, size)
+            assert all(p.size <= size for p in got)
+            if size in (172, 4096, len(raw) + 100) or name == "solid_zstd.pna":
+                a = host.HostArchive.open_multipart(got)
+                for phsf, key in info["keys"].items():
+                    a.set_key(phsf, bytes.fromhex(key))
+                res = a.read_all(workers=2, group_bytes=20_000)
+                assert [n for n, _, _ in res] == [e["name"] for e in info["entries"]], (name, size)
+                for (n, st, d), e in zip(res, info["entries"]):
+                    assert st == 0 and hashlib.sha256(d).hexdigest() == e["sha256"], (name, size, n)
