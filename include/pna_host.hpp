@@ -171,6 +171,10 @@ uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const W
 // part.  Errors as the reference: InvalidInput below MIN_SPLIT_PART_BYTES (64) or when a non-stream chunk exceeds a part.
 constexpr uint64_t MIN_SPLIT_PART_BYTES = 64;
 std::vector<std::vector<uint8_t>> split_archive(const uint8_t* archive, size_t len, uint64_t max_part_bytes, int device);
+// Same, parts written back to back into out (copies by several threads); part_lens always receives the layout, the return value is
+// the total length.  When out is null, cap too small or there are more than max_parts parts, nothing is written (sizing call).
+uint64_t split_archive_into(const uint8_t* archive, size_t len, uint64_t max_part_bytes, int device, uint8_t* out, uint64_t cap,
+                            std::vector<uint64_t>& part_lens, uint64_t max_parts = UINT64_MAX);
 
 // ---- the file-system side of the path (SURVEY 8f "next", item 1): the CLI's extract / create data flow around the kernels
 struct IoStats {

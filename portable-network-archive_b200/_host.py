@@ -224,7 +224,8 @@ def split_archive(archive, max_part_bytes: int, device=0):
     buf = archive if isinstance(archive, np.ndarray) else np.frombuffer(archive, dtype=np.uint8)
     err = C.create_string_buffer(512)
     total, n_parts = C.c_uint64(0), C.c_uint32(0)
-    out, lens = np.empty(0, dtype=np.uint8), (C.c_uint64 * 1)()
+    guess = buf.size // max(1, max_part_bytes - 52) + 2            # one call when the guess holds, a sizing pass otherwise
+    out, lens = np.empty(buf.size + 128 * guess, dtype=np.uint8), (C.c_uint64 * (2 * guess))()
     for _ in range(2):
         rc = L.pnah_split(buf.ctypes.data, buf.size, max_part_bytes, device, out.ctypes.data, out.size, C.byref(total), lens, len(lens),
                           C.byref(n_parts), err, 512)

@@ -306,6 +306,8 @@ Archive Archive::read_header_from_slice(const uint8_t* buf, size_t len) {
     return a;
 }
 
+struct JoinCopy { uint8_t* dst; const uint8_t* src; uint64_t n; };
+static void join_copy(const std::vector<JoinCopy>& copies);   // several threads; defined with the split writer
 Archive Archive::read_multipart(const pna_span* parts, size_t n_parts) {
     if (n_parts == 0) throw Error(PNA_E_INVALID_INPUT, "no archive part given");
     std::vector<std::vector<RawChunk>> lists(n_parts);
@@ -328,7 +330,14 @@ Archive Archive::read_multipart(const pna_span* parts, size_t n_parts) {
     std::shared_ptr<uint8_t> mem(new uint8_t[total], std::default_delete<uint8_t[]>());
     uint8_t* w = mem.get();
     memcpy(w, SIGNATURE, 8); w += 8;
-    auto put = [&](size_t k, const RawChunk& c) { memcpy(w, parts[k].ptr + c.off - 8, 12 + (size_t)c.len); w += 12 + (size_t)c.len; };
+    std::vector<JoinCopy> copies;          // runs of consecutive source frames; copied by several threads below
+    auto put = [&](size_t k, const RawChunk& c) {
+        const uint8_t* src = parts[k].ptr + c.off - 8;
+        const uint64_t n = 12 + (uint64_t)c.len;
+        if (!copies.empty() && copies.back().src + copies.back().n == src) copies.back().n += n;
+        else copies.push_back({w, src, n});
+        w += n;
+    };
     auto archive_level = [](const RawChunk& c) { const uint32_t t = ty32(c); return t == T_AEND || t == T_ANXT || t == ty32("AHED"); };
     put(0, lists[0][0]);
     for (size_t k = 0; k < n_parts; k++)
@@ -340,6 +349,7 @@ Archive Archive::read_multipart(const pna_span* parts, size_t n_parts) {
             const bool placed = (k == 0 && i == 0) || (k + 1 == n_parts && i + 1 == lists[k].size());
             if (archive_level(c) && !placed) put(k, c);
         }
+    join_copy(copies);
     Archive a = read_header_from_slice(mem.get(), (size_t)total);
     a.joined_ = std::move(mem);
     return a;
@@ -1335,7 +1345,27 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
 }
 
 // ---- split writer (archive/split_parts.rs)
-std::vector<std::vector<uint8_t>> split_archive(const uint8_t* archive, size_t len, uint64_t max_part_bytes, int device) {
+namespace {
+struct CopyTask { uint8_t* dst; const uint8_t* src; uint64_t n; };
+// large copies into fresh (untouched) memory are page-fault bound on one thread: pieces of 4 MiB over up to 8 threads
+void parallel_copy(const std::vector<CopyTask>& tasks) {
+    std::vector<CopyTask> pieces;
+    uint64_t total = 0;
+    for (const CopyTask& t : tasks)
+        for (uint64_t o = 0; o < t.n; o += (uint64_t)4 << 20) { pieces.push_back({t.dst + o, t.src + o, std::min<uint64_t>((uint64_t)4 << 20, t.n - o)}); total += pieces.back().n; }
+    const unsigned nt = total < ((uint64_t)16 << 20) ? 1u : std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    std::atomic<size_t> next{0};
+    auto work = [&]() { for (size_t i; (i = next.fetch_add(1)) < pieces.size();) memcpy(pieces[i].dst, pieces[i].src, (size_t)pieces[i].n); };
+    std::vector<std::thread> th;
+    for (unsigned k = 1; k < nt; k++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+// one step of the layout: a run of source frames copied verbatim, or one freshly framed chunk (length, type, data, CRC to come)
+struct SplitOp { uint32_t part; bool fresh; char ty[4]; uint64_t src, n, dst; };   // src: offset in the archive (UINT64_MAX: data made here)
+struct SplitPlan { std::vector<SplitOp> ops; std::vector<uint64_t> part_len; };
+
+SplitPlan split_layout(const uint8_t* archive, size_t len, uint64_t max_part_bytes) {
     if (max_part_bytes < MIN_SPLIT_PART_BYTES)       // split_parts.rs:91-96
         throw Error(PNA_E_INVALID_INPUT, "max_part_bytes must be at least " + std::to_string(MIN_SPLIT_PART_BYTES) + " bytes");
     if (len < 8 || memcmp(archive, SIGNATURE, 8) != 0) throw Error(PNA_E_INVALID_DATA, "it is not PNA");
@@ -1346,32 +1376,28 @@ std::vector<std::vector<uint8_t>> split_archive(const uint8_t* archive, size_t l
     for (size_t i = 0; i < ch.size(); i++) if (ty32(ch[i]) == T_AEND || ty32(ch[i]) == T_ANXT) { end = i; break; }
     if (end == ch.size()) throw Error(PNA_E_UNEXPECTED_EOF, "archive without `AEND`");
     const uint64_t MINC = 12, budget = max_part_bytes - 52;   // signature 8 + AHED 20 + ANXT 12 + AEND 12
-    std::vector<std::vector<uint8_t>> parts;
-    struct Fix { uint32_t part; uint64_t at, n; };   // freshly framed chunk: type||data at parts[part][at .. at+n), CRC behind it
-    std::vector<Fix> fixes;
+    SplitPlan P;
     uint64_t remaining = 0;
-    auto frame = [&](const char* ty, const uint8_t* data, uint32_t n) {
-        std::vector<uint8_t>& p = parts.back();
-        put_be32(p, n);
-        fixes.push_back({(uint32_t)parts.size() - 1, p.size(), (uint64_t)n + 4});
-        p.insert(p.end(), ty, ty + 4);
-        p.insert(p.end(), data, data + n);
-        put_be32(p, 0);
+    auto fresh = [&](const char* ty, uint64_t src, uint64_t n) {
+        SplitOp o{(uint32_t)P.part_len.size() - 1, true, {ty[0], ty[1], ty[2], ty[3]}, src, n, P.part_len.back()};
+        P.ops.push_back(o);
+        P.part_len.back() += MINC + n;
     };
     auto open_part = [&]() {
-        if (parts.size() > 0xFFFFFFFFull) throw Error(PNA_E_INVALID_INPUT, "too many archive parts");
-        const uint32_t k = (uint32_t)parts.size();
-        parts.emplace_back();
-        parts.back().reserve((size_t)std::min<uint64_t>(max_part_bytes, len + 64));
-        parts.back().insert(parts.back().end(), SIGNATURE, SIGNATURE + 8);
-        const uint8_t h[8] = {0, 0, 0, 0, (uint8_t)(k >> 24), (uint8_t)(k >> 16), (uint8_t)(k >> 8), (uint8_t)k};
-        frame("AHED", h, 8);
+        if (P.part_len.size() > 0xFFFFFFFFull) throw Error(PNA_E_INVALID_INPUT, "too many archive parts");
+        P.part_len.push_back(8);
+        fresh("AHED", UINT64_MAX, 8);
         remaining = budget;
     };
-    auto roll_over = [&]() { frame("ANXT", nullptr, 0); frame("AEND", nullptr, 0); open_part(); };
+    auto roll_over = [&]() { fresh("ANXT", UINT64_MAX, 0); fresh("AEND", UINT64_MAX, 0); open_part(); };
     auto verbatim = [&](const RawChunk& c) {
-        parts.back().insert(parts.back().end(), archive + c.off - 8, archive + c.off + c.len + 4);
-        remaining -= MINC + c.len;
+        const uint32_t part = (uint32_t)P.part_len.size() - 1;
+        const uint64_t n = MINC + c.len;
+        SplitOp* last = P.ops.empty() ? nullptr : &P.ops.back();
+        if (last && !last->fresh && last->part == part && last->src + last->n == c.off - 8) last->n += n;
+        else P.ops.push_back(SplitOp{part, false, {0, 0, 0, 0}, c.off - 8, n, P.part_len.back()});
+        P.part_len.back() += n;
+        remaining -= n;
     };
     auto does_not_fit = [&](uint64_t n) {
         return Error(PNA_E_INVALID_INPUT, "a " + std::to_string(n) + " byte chunk does not fit within the maximum part size of " + std::to_string(max_part_bytes) + " bytes");
@@ -1381,34 +1407,76 @@ std::vector<std::vector<uint8_t>> split_archive(const uint8_t* archive, size_t l
         const RawChunk& c = ch[i];
         const uint64_t clen = MINC + c.len;
         const bool stream = ty32(c) == T_FDAT || ty32(c) == T_SDAT;
-        if (clen <= remaining) { verbatim(c); continue; }
+        if (clen <= remaining) { verbatim(c); continue; }                       // put_chunk, split_parts.rs:140-163
         if (!stream) {
             if (clen > budget) throw does_not_fit(clen);
             roll_over(); verbatim(c); continue;
         }
         if (clen <= budget && remaining <= MINC) { roll_over(); verbatim(c); continue; }
-        const uint8_t* data = archive + c.off;
-        uint64_t left = c.len;
-        for (;;) {   // put_stream
-            if (MINC + left <= remaining) { frame(c.ty, data, (uint32_t)left); remaining -= MINC + left; break; }
+        uint64_t at = c.off, left = c.len;
+        for (;;) {                                                              // put_stream, split_parts.rs:165-188
+            if (MINC + left <= remaining) { fresh(c.ty, at, left); remaining -= MINC + left; break; }
             if (remaining > MINC) {
                 const uint64_t take = remaining - MINC;
-                frame(c.ty, data, (uint32_t)take);
-                remaining -= MINC + take; data += take; left -= take;
+                fresh(c.ty, at, take);
+                remaining -= MINC + take; at += take; left -= take;
             } else if (budget <= MINC) throw does_not_fit(MINC + left);
             roll_over();
         }
     }
-    frame("AEND", nullptr, 0);
-    std::vector<pna_span> spans(fixes.size());
-    std::vector<uint32_t> crc(fixes.size());
-    for (size_t f = 0; f < fixes.size(); f++) spans[f] = pna_span{parts[fixes[f].part].data() + fixes[f].at, fixes[f].n};
+    fresh("AEND", UINT64_MAX, 0);
+    return P;
+}
+
+// lays the parts out at out[k] (part_len[k] bytes each): copies by several threads, fresh CRCs from one pna_cuda_crc32 batch
+void split_write(const uint8_t* archive, const SplitPlan& P, uint8_t* const* out, int device) {
+    std::vector<CopyTask> copies;
+    std::vector<pna_span> spans;
+    for (size_t k = 0; k < P.part_len.size(); k++) memcpy(out[k], SIGNATURE, 8);
+    for (const SplitOp& o : P.ops) {
+        uint8_t* d = out[o.part] + o.dst;
+        if (!o.fresh) { copies.push_back({d, archive + o.src, o.n}); continue; }
+        wr_be32(d, (uint32_t)o.n);
+        memcpy(d + 4, o.ty, 4);
+        if (o.src != UINT64_MAX) copies.push_back({d + 8, archive + o.src, o.n});
+        else if (o.n == 8) { memset(d + 8, 0, 4); wr_be32(d + 12, o.part); }     // ArchiveHeader::new(0, 0, archive_number)
+        spans.push_back(pna_span{d + 4, o.n + 4});
+    }
+    parallel_copy(copies);
+    std::vector<uint32_t> crc(spans.size());
     {
         CtxLease L(device);
         ck(L.ctx, pna_cuda_crc32(L.ctx, spans.data(), (uint32_t)spans.size(), crc.data()), "split writer: chunk CRCs");
     }
-    for (size_t f = 0; f < fixes.size(); f++) wr_be32(parts[fixes[f].part].data() + fixes[f].at + fixes[f].n, crc[f]);
+    for (size_t f = 0; f < spans.size(); f++) wr_be32(const_cast<uint8_t*>(spans[f].ptr) + spans[f].len, crc[f]);
+}
+}  // namespace
+static void join_copy(const std::vector<JoinCopy>& copies) {
+    std::vector<CopyTask> t;
+    for (const JoinCopy& c : copies) t.push_back({c.dst, c.src, c.n});
+    parallel_copy(t);
+}
+
+std::vector<std::vector<uint8_t>> split_archive(const uint8_t* archive, size_t len, uint64_t max_part_bytes, int device) {
+    const SplitPlan P = split_layout(archive, len, max_part_bytes);
+    std::vector<std::vector<uint8_t>> parts(P.part_len.size());
+    std::vector<uint8_t*> ptr(parts.size());
+    for (size_t k = 0; k < parts.size(); k++) { parts[k].resize((size_t)P.part_len[k]); ptr[k] = parts[k].data(); }
+    split_write(archive, P, ptr.data(), device);
     return parts;
+}
+uint64_t split_archive_into(const uint8_t* archive, size_t len, uint64_t max_part_bytes, int device, uint8_t* out, uint64_t cap,
+                            std::vector<uint64_t>& part_lens, uint64_t max_parts) {
+    const SplitPlan P = split_layout(archive, len, max_part_bytes);
+    part_lens = P.part_len;
+    uint64_t total = 0;
+    for (uint64_t n : P.part_len) total += n;
+    if (total > cap || !out || P.part_len.size() > max_parts) return total;    // sizing: nothing copied, no GPU work
+    std::vector<uint8_t*> ptr(P.part_len.size());
+    uint64_t at = 0;
+    for (size_t k = 0; k < ptr.size(); k++) { ptr[k] = out + at; at += P.part_len[k]; }
+    split_write(archive, P, ptr.data(), device);
+    return total;
 }
 
 }  // namespace pna
@@ -1446,12 +1514,11 @@ void pnah_close(pnah_archive* a) { delete a; }
 int pnah_split(const uint8_t* archive, uint64_t len, uint64_t max_part_bytes, int device, uint8_t* out, uint64_t cap, uint64_t* total,
                uint64_t* part_lens, uint32_t max_parts, uint32_t* n_parts, char* err, uint64_t errcap) {
     try {
-        const std::vector<std::vector<uint8_t>> parts = pna::split_archive(archive, (size_t)len, max_part_bytes, device);
-        uint64_t sum = 0;
-        for (const auto& p : parts) sum += p.size();
-        *total = sum; *n_parts = (uint32_t)parts.size();
-        if (sum > cap || parts.size() > max_parts) return PNA_E_NOSPACE;
-        for (size_t k = 0; k < parts.size(); k++) { memcpy(out, parts[k].data(), parts[k].size()); out += parts[k].size(); part_lens[k] = parts[k].size(); }
+        std::vector<uint64_t> lens;
+        *total = pna::split_archive_into(archive, (size_t)len, max_part_bytes, device, out, cap, lens, max_parts);
+        *n_parts = (uint32_t)lens.size();
+        if (*total > cap || !out || lens.size() > max_parts) return PNA_E_NOSPACE;
+        for (size_t k = 0; k < lens.size(); k++) part_lens[k] = lens[k];
         return PNA_OK;
     } catch (const pna::Error& e) { return fail(e, err, errcap); }
 }

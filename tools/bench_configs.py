@@ -419,6 +419,25 @@ def main():
         print(json.dumps({"config": "own", "files": n, "plain_bytes": U, "archive_bytes": int(blob.size), "codec": "this library's zstd writer + aes-256-ctr",
                           "kernel_only_GBps": U / (sum(stage.values()) * 1e-3) / 1e9, "kernel_only_ms": sum(stage.values()), "stage_ms": stage,
                           "counts": cnt, "extract_e2e_GBps": U / edt / 1e9, "extract_e2e_ms": edt * 1e3}), flush=True)
+        # the same archive as a split archive (split_parts.rs writer, read.rs:105-165 reader): 64 MiB parts
+        t0 = time.perf_counter()
+        parts = host.split_archive(blob, 64 << 20)
+        t_split = time.perf_counter() - t0
+        mts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            hm = host.HostArchive.open_multipart(parts)
+            t_join = time.perf_counter() - t0
+            hm.set_key(oopts.phsf, oopts.key)
+            _, moffs, mst = hm.extract_files(out=eout, device=0, workers=args.workers, group_bytes=args.group_mib << 20, verify=True)
+            torch.cuda.synchronize()
+            mts.append(time.perf_counter() - t0)
+            hm.close()
+        assert mst == [0] * n and all(eout[int(moffs[k]):int(moffs[k]) + len(files[k])].tobytes() == files[k] for k in range(0, n, max(1, n // 16)))
+        print(json.dumps({"config": "own_split", "parts": len(parts), "part_bytes": 64 << 20, "split_ms": t_split * 1e3,
+                          "split_GBps": int(blob.size) / t_split / 1e9, "join_ms": t_join * 1e3, "extract_e2e_ms": min(mts[1:]) * 1e3,
+                          "extract_e2e_GBps": U / min(mts[1:]) / 1e9, "note": "split: host copy + one GPU CRC batch of the re-cut chunks; "
+                          "read: parts joined into one owned chunk stream (pageable memory), then the single-archive path"}), flush=True)
         del files, pl, arch
 
     if args.only in ("", "cfg1"):
