@@ -94,7 +94,8 @@ public:
     // parts are joined into one chunk stream the Archive owns (every chunk frame of every part verbatim, stored CRCs
     // included: the entry chunks in order, then AEND, the other parts' archive-level chunks behind it), so the CRC check
     // and the entry groups run as for a single archive.
-    static Archive read_multipart(const pna_span* parts, size_t n_parts);
+    // pinned_device >= 0: the joined stream is leased from the pinned pool of that device's contexts (DMA uploads); -1: pageable.
+    static Archive read_multipart(const pna_span* parts, size_t n_parts, int pinned_device = -1);
     const std::vector<RawChunk>& chunks() const { return chunks_; }
     const std::vector<EntryInfo>& entries() const { return entries_; }
     uint32_t archive_number() const { return archive_number_; }
@@ -210,7 +211,8 @@ typedef struct {
 } pnah_entry_info;
 typedef struct { uint64_t files, dirs, skipped, bytes; double index_ms, gpu_ms, io_ms, total_ms; } pnah_io_stats;
 int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, uint64_t errcap);
-int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, pnah_archive** out, char* err, uint64_t errcap);   /* split archive: parts in order; the handle owns a joined copy */
+int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, int pinned_device /* -1: pageable */,
+                        pnah_archive** out, char* err, uint64_t errcap);   /* split archive: parts in order; the handle owns a joined copy */
 /* split writer: parts are written back to back into out (cap bytes), their lengths into part_lens (max_parts slots).  PNA_E_NOSPACE
  * when either is too small; *total and *n_parts always carry what is needed. */
 int pnah_split(const uint8_t* archive, uint64_t len, uint64_t max_part_bytes, int device, uint8_t* out, uint64_t cap, uint64_t* total,

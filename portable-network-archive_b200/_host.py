@@ -65,7 +65,7 @@ def lib():
                                         C.c_char_p, C.c_char_p, u32, C.c_int, vp, u64, C.POINTER(u64), C.c_char_p, u64]
         L.pnah_open_file.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, u64]
         L.pnah_split.argtypes = [vp, u64, u64, C.c_int, vp, u64, C.POINTER(u64), C.POINTER(u64), u32, C.POINTER(u32), C.c_char_p, u64]
-        L.pnah_open_multipart.argtypes = [C.POINTER(vp), C.POINTER(u64), u32, C.POINTER(vp), C.c_char_p, u64]
+        L.pnah_open_multipart.argtypes = [C.POINTER(vp), C.POINTER(u64), u32, C.c_int, C.POINTER(vp), C.c_char_p, u64]
         L.pnah_extract_to_dir.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, u64, u64, C.c_int, C.c_int, C.POINTER(IoStats),
                                           C.POINTER(C.c_int32), C.c_char_p, u64]
         L.pnah_create_from_files.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_uint8, C.c_int32, C.c_uint8, C.c_uint8,
@@ -95,8 +95,9 @@ class HostArchive:
         self.h = h
 
     @classmethod
-    def open_multipart(cls, parts):
-        """Split archive (archive/read.rs:105-165): `parts` in order, bytes-like or uint8 arrays; the handle owns a joined copy."""
+    def open_multipart(cls, parts, pinned_device=-1):
+        """Split archive (archive/read.rs:105-165): `parts` in order, bytes-like or uint8 arrays; the handle owns a joined copy
+        (pinned_device >= 0: in pinned memory of that device's pool, so uploads are DMA)."""
         self = cls.__new__(cls)
         self.L = lib()
         bufs = [p if isinstance(p, np.ndarray) else np.frombuffer(p, dtype=np.uint8) for p in parts]
@@ -105,7 +106,7 @@ class HostArchive:
         lens = (C.c_uint64 * len(bufs))(*[b.size for b in bufs])
         h = C.c_void_p()
         err = C.create_string_buffer(512)
-        rc = self.L.pnah_open_multipart(ptrs, lens, len(bufs), C.byref(h), err, 512)
+        rc = self.L.pnah_open_multipart(ptrs, lens, len(bufs), pinned_device, C.byref(h), err, 512)
         if rc:
             raise HostError(rc, err.value.decode())
         self.h = h

@@ -308,7 +308,7 @@ Archive Archive::read_header_from_slice(const uint8_t* buf, size_t len) {
 
 struct JoinCopy { uint8_t* dst; const uint8_t* src; uint64_t n; };
 static void join_copy(const std::vector<JoinCopy>& copies);   // several threads; defined with the split writer
-Archive Archive::read_multipart(const pna_span* parts, size_t n_parts) {
+Archive Archive::read_multipart(const pna_span* parts, size_t n_parts, int pinned_device) {
     if (n_parts == 0) throw Error(PNA_E_INVALID_INPUT, "no archive part given");
     std::vector<std::vector<RawChunk>> lists(n_parts);
     uint64_t total = 8;
@@ -327,7 +327,15 @@ Archive Archive::read_multipart(const pna_span* parts, size_t n_parts) {
         if (has_next && k + 1 == n_parts) throw Error(PNA_E_UNEXPECTED_EOF, "next part missing");
         if (!has_next && k + 1 < n_parts) throw Error(PNA_E_INVALID_DATA, "part does not announce a next archive (`ANXT`)");
     }
-    std::shared_ptr<uint8_t> mem(new uint8_t[total], std::default_delete<uint8_t[]>());
+    std::shared_ptr<uint8_t> mem;
+    if (pinned_device >= 0) {              // joined stream in pinned memory from the process-wide pool: its upload is true DMA
+        CtxLease L(pinned_device);
+        pna_ctx* const pctx = L.ctx;
+        uint64_t got = 0;
+        uint8_t* p = g_pinned.get(pctx, total, &got);
+        if (!p) throw Error(PNA_E_OOM, "pinned buffer for the joined parts");
+        mem = std::shared_ptr<uint8_t>(p, [pctx, got](uint8_t* q) { g_pinned.put(pctx, q, got); });
+    } else mem = std::shared_ptr<uint8_t>(new uint8_t[total], std::default_delete<uint8_t[]>());
     uint8_t* w = mem.get();
     memcpy(w, SIGNATURE, 8); w += 8;
     std::vector<JoinCopy> copies;          // runs of consecutive source frames; copied by several threads below
@@ -1501,12 +1509,12 @@ int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, u
         return PNA_OK;
     } catch (const pna::Error& e) { *out = nullptr; return fail(e, err, errcap); }
 }
-int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, pnah_archive** out, char* err, uint64_t errcap) {
+int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, int pinned_device, pnah_archive** out, char* err, uint64_t errcap) {
     *out = nullptr;
     try {
         std::vector<pna_span> sp(n_parts);
         for (uint32_t k = 0; k < n_parts; k++) sp[k] = pna_span{parts[k], lens[k]};
-        *out = new pnah_archive{pna::Archive::read_multipart(sp.data(), sp.size()), {}};
+        *out = new pnah_archive{pna::Archive::read_multipart(sp.data(), sp.size(), pinned_device), {}};
         return PNA_OK;
     } catch (const pna::Error& e) { return fail(e, err, errcap); }
 }

@@ -426,7 +426,7 @@ def main():
         mts = []
         for _ in range(3):
             t0 = time.perf_counter()
-            hm = host.HostArchive.open_multipart(parts)
+            hm = host.HostArchive.open_multipart(parts, pinned_device=0)
             t_join = time.perf_counter() - t0
             hm.set_key(oopts.phsf, oopts.key)
             _, moffs, mst = hm.extract_files(out=eout, device=0, workers=args.workers, group_bytes=args.group_mib << 20, verify=True)
@@ -437,7 +437,7 @@ def main():
         print(json.dumps({"config": "own_split", "parts": len(parts), "part_bytes": 64 << 20, "split_ms": t_split * 1e3,
                           "split_GBps": int(blob.size) / t_split / 1e9, "join_ms": t_join * 1e3, "extract_e2e_ms": min(mts[1:]) * 1e3,
                           "extract_e2e_GBps": U / min(mts[1:]) / 1e9, "note": "split: host copy + one GPU CRC batch of the re-cut chunks; "
-                          "read: parts joined into one owned chunk stream (pageable memory), then the single-archive path"}), flush=True)
+                          "read: parts joined into one owned chunk stream (pinned pool), then the single-archive path"}), flush=True)
         del files, pl, arch
 
     if args.only in ("", "cfg1"):
