@@ -214,7 +214,8 @@ int pnah_open(const uint8_t* buf, uint64_t len, pnah_archive** out, char* err, u
 int pnah_open_multipart(const uint8_t* const* parts, const uint64_t* lens, uint32_t n_parts, int pinned_device /* -1: pageable */,
                         pnah_archive** out, char* err, uint64_t errcap);   /* split archive: parts in order; the handle owns a joined copy */
 /* split writer: parts are written back to back into out (cap bytes), their lengths into part_lens (max_parts slots).  PNA_E_NOSPACE
- * when either is too small; *total and *n_parts always carry what is needed. */
+ * when either is too small (or out is NULL: sizing call, no copy and no GPU work); *total, *n_parts and the first max_parts part_lens
+ * always carry the layout. */
 int pnah_split(const uint8_t* archive, uint64_t len, uint64_t max_part_bytes, int device, uint8_t* out, uint64_t cap, uint64_t* total,
                uint64_t* part_lens, uint32_t max_parts, uint32_t* n_parts, char* err, uint64_t errcap);
 int pnah_open_file(const char* path, pnah_archive** out, char* err, uint64_t errcap);   /* mmap; the handle owns the mapping */

@@ -242,6 +242,19 @@ def split_archive(archive, max_part_bytes: int, device=0):
     return parts
 
 
+def split_layout(archive, max_part_bytes: int, max_parts: int = 1 << 16):
+    """Part lengths the split writer would produce (sizing call of pnah_split: budget arithmetic only, no copy, no GPU work)."""
+    L = lib()
+    buf = archive if isinstance(archive, np.ndarray) else np.frombuffer(archive, dtype=np.uint8)
+    err = C.create_string_buffer(512)
+    total, n_parts = C.c_uint64(0), C.c_uint32(0)
+    lens = (C.c_uint64 * max_parts)()
+    rc = L.pnah_split(buf.ctypes.data, buf.size, max_part_bytes, 0, None, 0, C.byref(total), lens, max_parts, C.byref(n_parts), err, 512)
+    if rc != _ffi.E_NOSPACE:
+        raise HostError(rc, err.value.decode())
+    return [int(lens[k]) for k in range(min(n_parts.value, max_parts))], int(total.value)
+
+
 def create_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, key=None, phsf=None, ivs=None, max_chunk_size=0,
                    device=0, workers=3, group_bytes=256 << 20, out=None):
     """files: list of (name, bytes-like).  Returns the archive bytes (numpy view of `out` when given)."""

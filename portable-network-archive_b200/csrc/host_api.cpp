@@ -1525,8 +1525,8 @@ int pnah_split(const uint8_t* archive, uint64_t len, uint64_t max_part_bytes, in
         std::vector<uint64_t> lens;
         *total = pna::split_archive_into(archive, (size_t)len, max_part_bytes, device, out, cap, lens, max_parts);
         *n_parts = (uint32_t)lens.size();
+        for (size_t k = 0; k < lens.size() && k < max_parts; k++) part_lens[k] = lens[k];   // the layout, also on a sizing call
         if (*total > cap || !out || lens.size() > max_parts) return PNA_E_NOSPACE;
-        for (size_t k = 0; k < lens.size(); k++) part_lens[k] = lens[k];
         return PNA_OK;
     } catch (const pna::Error& e) { return fail(e, err, errcap); }
 }

@@ -433,3 +433,23 @@ def test_split_writer_matches_restated_reference_and_reads_back(host, pna, ctx, 
                 assert [n for n, _, _ in res] == [e["name"] for e in info["entries"]], (name, size)
                 for (n, st, d), e in zip(res, info["entries"]):
                     assert st == 0 and hashlib.sha256(d).hexdigest() == e["sha256"], (name, size, n)
+
+
+def test_split_layout_matches_restated_reference_without_gpu(host, pna, golden):
+    """The budget arithmetic of SplitParts (split_parts.rs:140-188) is host logic: part count and every part length equal the
+    restated writer's, on every single-archive fixture and a sweep of part sizes (sizing call: no copy, no GPU work)."""
+    for name, info in golden["archives"].items():
+        if name.startswith("multipart"):
+            continue
+        buf = np.fromfile(os.path.join(golden["dir"], info["file"]), dtype=np.uint8)
+        raw = buf.tobytes()
+        for size in (100, 172, 173, 200, 511, 4096, 65_536, len(raw) + 52, len(raw) + 1000):
+            try:
+                want = [len(p) for p in _split_parts_restated(raw, size)]
+            except ValueError:
+                with pytest.raises(host.HostError) as ei:
+                    host.split_layout(buf, size)
+                assert ei.value.kind == pna.E_INVALID_INPUT, (name, size)
+                continue
+            lens, total = host.split_layout(buf, size)
+            assert lens == want and total == sum(want), (name, size)
