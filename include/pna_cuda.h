@@ -19,8 +19,10 @@
  * pna_cuda_host_alloc() memory.
  * Errors: the function return is a context-level error (bad argument, CUDA failure); per-entry
  * results are in status[] and map 1:1 to the reference's io::ErrorKind classes (see enum).
- * Threading: a pna_ctx serialises batch calls internally; use one ctx per host thread / per GPU for
- * concurrency (entries shard by entry across GPUs; the path has no collective).
+ * Threading: a single-device pna_ctx serialises batch calls internally; use one ctx per host thread for concurrency.
+ * Multi-GPU: a pna_ctx created over several devices shards every batch call by entry across them (greedy
+ * longest-processing-time on stream bytes, one host thread per GPU; entries are independent, the path has no collective
+ * and no peer traffic -- the reference's counterpart is the per-entry task fan-out of cli/src/command/extract.rs:868-1019).
  * There is NO CPU fallback: every entry point fails with PNA_E_CUDA when no sm_100 device is usable.
  */
 #ifndef PNA_CUDA_H
@@ -51,7 +53,7 @@ enum { PNA_COMPRESSION_NO = 0, PNA_COMPRESSION_DEFLATE = 1, PNA_COMPRESSION_ZSTD
 enum { PNA_ENCRYPTION_NO = 0, PNA_ENCRYPTION_AES = 1, PNA_ENCRYPTION_CAMELLIA = 2 };
 enum { PNA_CIPHER_CBC = 0, PNA_CIPHER_CTR = 1, PNA_CIPHER_GCM = 2 };
 
-typedef struct pna_ctx pna_ctx;   /* one device: streams, device arenas, pinned staging */
+typedef struct pna_ctx pna_ctx;   /* one or several devices: streams, device arenas, pinned staging */
 typedef struct pna_plan pna_plan; /* a batch resident in HBM (used for kernel-only timing and re-runs) */
 
 typedef struct { const uint8_t* ptr; uint64_t len; } pna_span;        /* borrowed host memory */
@@ -67,7 +69,11 @@ typedef struct {
     uint32_t n_bodies;
     uint8_t compression, encryption, cipher_mode, _pad; /* FHED bytes [3],[4],[5] / SHED [2],[3],[4] */
     uint8_t key[32];                                    /* KDF output (host side, lib/src/hash.rs:45); ignored if encryption==0 */
-    uint64_t raw_size_hint;                             /* fSIZ (lib/src/entry.rs:817) or UINT64_MAX */
+    uint64_t raw_size_hint;                             /* fSIZ (lib/src/entry.rs:817) or UINT64_MAX.  A HINT: untrusted archive
+                                                         * input the reference never sizes anything from.  Values no stream of
+                                                         * this length can decode to (pna_cuda_decode_size_bound) are ignored and
+                                                         * the exact sizing pass runs instead; the decoded length always comes
+                                                         * back in pna_buf.len / pna_cuda_decode_plan_lengths. */
 } pna_decode_desc;
 
 /* One entry to build: plaintext in, IV || cipher(compress(plain)) out (lib/src/entry/write.rs:268-273; the prefix chunk is
@@ -87,14 +93,19 @@ typedef struct {
 } pna_encode_desc;
 
 /* ---- context ---- */
-int pna_cuda_init(pna_ctx** out, int device_id);
+/* device_ids: the CUDA devices this context owns (distinct, each an sm_100 part); NULL = devices 0 .. n_devices-1
+ * (n_devices == 0: every visible device).  One device: an ordinary context.  Several: every batch / plan call below is
+ * sharded by entry across them and results come back in caller order. */
+int pna_cuda_init(pna_ctx** out, const int* device_ids, int n_devices);
+int pna_cuda_device_count(pna_ctx* ctx);          /* devices owned by the context */
+int pna_cuda_device_id(pna_ctx* ctx, int i);      /* CUDA ordinal of the i-th, -1 when out of range */
 void pna_cuda_destroy(pna_ctx* ctx);
 const char* pna_cuda_strerror(int32_t status);
 const char* pna_cuda_last_error(pna_ctx* ctx);   /* text of the last context-level failure */
 /* pinned host memory for end-to-end paths (cudaHostAlloc); pageable buffers are accepted everywhere too */
 void* pna_cuda_host_alloc(pna_ctx* ctx, uint64_t bytes);
 void pna_cuda_host_free(pna_ctx* ctx, void* p);
-/* the CUDA stream every kernel of this ctx is launched on (cudaStream_t), for CUDA-event timing by callers */
+/* the CUDA stream every kernel of this ctx (its first device) is launched on (cudaStream_t), for CUDA-event timing by callers */
 void* pna_cuda_stream(pna_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py "gpu_launches") */
 uint64_t pna_cuda_launch_count(pna_ctx* ctx);
@@ -107,6 +118,11 @@ int pna_cuda_crc32_image(pna_ctx* ctx, const uint8_t* image, uint64_t image_len,
                          const uint64_t* span_len, uint32_t n, uint32_t* crc_out);
 
 /* ---- seam 2: decode ---- */
+/* largest size a compressed stream of stream_len bytes can decode to (zstd: 128 KiB per 4 bytes, deflate: 1032x, store: 1x) */
+uint64_t pna_cuda_decode_size_bound(uint8_t compression, uint64_t stream_len);
+/* 1 when the library lays the output out from this fSIZ value, 0 when it ignores it and sizes the entry exactly (beyond the
+ * bound above, or above 1 GiB and more than 256x the stream): host layers apply the same rule before they size buffers */
+int pna_cuda_size_hint_trusted(uint8_t compression, uint64_t stream_len, uint64_t hint);
 int pna_cuda_decode_batch(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_buf* out, int32_t* status);
 /* staged form: upload once, run the kernels any number of times on HBM-resident input, fetch once */
 int pna_cuda_decode_plan_create(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_plan** plan);
@@ -116,6 +132,14 @@ int pna_cuda_decode_plan_create(pna_ctx* ctx, const pna_decode_desc* descs, uint
  * lib/src/format/chunk.rs:16-21) before it is decoded; pna_cuda_plan_crc_results returns all computed CRCs. */
 int pna_cuda_decode_plan_create_crc(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const pna_span* crc_spans,
                                     const uint32_t* crc_expect, const int32_t* crc_entry, uint32_t n_spans, pna_plan** plan);
+/* Same again for callers whose spans and bodies all lie inside ONE host allocation [image, image + image_len) -- an
+ * archive buffer or mapping.  Only then may the library bridge the few bytes of chunk framing between neighbouring spans
+ * and upload whole ranges in one copy (a million small files must not mean a million copies); without the declaration
+ * (the two calls above) every span is copied on its own, because the gap between two independent allocations is not the
+ * caller's memory.  crc_spans may be NULL with n_spans == 0 (no CRC check, e.g. after the caller verified the archive). */
+int pna_cuda_decode_plan_create_in_image(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint8_t* image,
+                                         uint64_t image_len, const pna_span* crc_spans, const uint32_t* crc_expect,
+                                         const int32_t* crc_entry, uint32_t n_spans, pna_plan** plan);
 int pna_cuda_plan_crc_results(pna_plan* plan, uint32_t* crc_out, uint32_t* n_broken);
 int pna_cuda_decode_plan_run(pna_plan* plan);                 /* asynchronous on pna_cuda_stream(ctx) after first call */
 int pna_cuda_decode_plan_fetch(pna_plan* plan, pna_buf* out, int32_t* status);

@@ -106,12 +106,20 @@ public:
     const std::vector<FileOut>& files() const { return files_; }
     // Extract all FILE entries into out[offsets[i] .. offsets[i+1]) (offsets from files()[i].size, caller-computed).
     // verify: chunk CRCs of the whole archive are checked on the GPU, fused with the decode batches.
+    // After the call files()[i].size is the DECODED length of every file that came out (fSIZ is only a hint: a smaller real
+    // length is reported here; a larger one fails that file with PNA_E_NOSPACE and leaves the required length in size).
     void extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                        uint64_t group_bytes, bool verify);
+    // Same over several GPUs of the box (the partition by entry of the reference's CLI, cli/src/command/extract.rs:868-1019):
+    // entry groups go to `workers` threads per device from one shared queue; no collective, no peer traffic.
+    void extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, const std::vector<int>& devices,
+                       int workers_per_device, uint64_t group_bytes, bool verify);
     // Same for the files [first, last) only (file i lands at out + offsets[i] - offsets[first]): windows of a large archive.
     // With verify, windows must be taken in archive order (each call checks the chunks up to its last entry).
     void extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                        uint64_t group_bytes, bool verify, size_t first, size_t last);
+    void extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, const std::vector<int>& devices,
+                       int workers_per_device, uint64_t group_bytes, bool verify, size_t first, size_t last);
     void restart_verify() { crc_next_chunk_ = 0; }
 
 private:
@@ -148,10 +156,20 @@ struct WriteOptions {    // options.rs:1035
 struct FileEntryBuilder {   // builder/file.rs:41: plaintext is borrowed until Archive::create returns
     std::string name;
     pna_span data{nullptr, 0};
-    uint8_t iv[16] = {0};   // caller-drawn (entry/write.rs:108-111)
-    // GCM: salt and nonce prefix of the stream header (entry/write.rs:81-85); drawn by the writer when left all-zero
+    // CBC / CTR IV.  The reference's writer draws a fresh one per entry (entry/write.rs:108-111, random.rs:8) and so does
+    // this one, from the OS CSPRNG, unless the caller supplies its own with set_iv (tests that pin ciphertext bytes).
+    uint8_t iv[16] = {0};
+    bool iv_set = false;
+    void set_iv(const uint8_t v[16]) { for (int i = 0; i < 16; i++) iv[i] = v[i]; iv_set = true; }
+    // GCM: salt and nonce prefix of the stream header (entry/write.rs:81-85); drawn by the writer unless set_gcm_params was called
     uint8_t gcm_salt[32] = {0};
     uint8_t gcm_nonce_prefix[7] = {0};
+    bool gcm_params_set = false;
+    void set_gcm_params(const uint8_t salt[32], const uint8_t prefix[7]) {
+        for (int i = 0; i < 32; i++) gcm_salt[i] = salt[i];
+        for (int i = 0; i < 7; i++) gcm_nonce_prefix[i] = prefix[i];
+        gcm_params_set = true;
+    }
 };
 // Archive::write_header + add_entry per file + finalize, with one GPU encode batch per worker group.
 std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
@@ -164,6 +182,9 @@ uint64_t create_solid_archive_bound(const std::vector<FileEntryBuilder>& files, 
 // Same, written straight into a caller buffer (pinned memory makes the stream copies true DMA); returns the archive length.
 uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
                              int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap);
+// Same over several GPUs: file groups go to `workers` threads per device from one shared queue (entries are independent).
+uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
+                             const std::vector<int>& devices, int workers_per_device, uint64_t group_bytes, uint8_t* out, uint64_t cap);
 
 // Split writer (lib/src/archive/split_parts.rs:90-188 SplitParts::{new, put_chunk, put_stream, roll_over}): a finished archive is cut
 // into parts of at most max_part_bytes.  Part k = signature, AHED(0, 0, k), chunks, [ANXT], AEND; a chunk that fits the part's
@@ -237,6 +258,17 @@ int pnah_file_get(pnah_archive* a, uint32_t i, const char** name, uint64_t* size
 int pnah_file_sizes(pnah_archive* a, uint64_t* sizes, int32_t* status /* may be NULL */);   /* bulk form of pnah_file_get */
 int pnah_extract_files(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                        uint64_t group_bytes, int verify, char* err, uint64_t errcap);
+/* files [first, last) only; file i lands at out + offsets[i] - offsets[first] (windows of a large archive; a second take of a file
+ * that failed with PNA_E_NOSPACE because its fSIZ understated it -- pnah_file_get then reports the required size) */
+int pnah_extract_range(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers, uint64_t group_bytes,
+                       int verify, uint64_t first, uint64_t last, char* err, uint64_t errcap);
+/* over several GPUs of the box: entries are partitioned by entry (a shared queue of entry groups), no collective */
+int pnah_extract_files_on(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, const int* devices, uint32_t n_devices,
+                          int workers_per_device, uint64_t group_bytes, int verify, char* err, uint64_t errcap);
+int pnah_create_on(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs /* NULL: drawn */,
+                   uint8_t compression, int32_t level, uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf,
+                   uint32_t max_chunk_size, const int* devices, uint32_t n_devices, int workers_per_device, uint64_t group_bytes, uint8_t* out,
+                   uint64_t cap, uint64_t* out_len, char* err, uint64_t errcap);
 uint64_t pnah_create_solid_bound(uint32_t n, const char* const* names, const uint64_t* lens, uint8_t compression, uint8_t encryption,
                                  uint8_t cipher_mode, const char* phsf, uint32_t max_chunk_size);
 int pnah_create_solid(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, uint8_t compression, int32_t level,

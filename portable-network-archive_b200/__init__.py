@@ -52,6 +52,13 @@ class DecodePlan:
         self.ctx._ck(self.ctx.L.pna_cuda_decode_plan_fetch(self.h, bufs, st), "decode_plan_fetch")
         return [o[:bufs[i].len] if st[i] == OK else o[:0] for i, o in enumerate(outs)], list(st), [b.len for b in bufs]
 
+    def lengths(self):
+        """(decoded length, status) of every entry after run(): E_NOSPACE + the required length when its size hint was too small."""
+        lens = (C.c_uint64 * max(self.n, 1))()
+        st = (C.c_int32 * max(self.n, 1))()
+        self.ctx._ck(self.ctx.L.pna_cuda_decode_plan_lengths(self.h, lens, st), "decode_plan_lengths")
+        return [int(x) for x in lens][:self.n], list(st)[:self.n]
+
     def fetch_into(self, bufs, st):
         self.ctx._ck(self.ctx.L.pna_cuda_decode_plan_fetch(self.h, bufs, st), "decode_plan_fetch")
 
@@ -144,16 +151,21 @@ class EncodePlan:
 
 
 class Context:
-    """One GPU (pna_ctx).  Entries shard across GPUs by entry: use one Context per device/rank."""
+    """A pna_ctx over one GPU (`device`) or several (`devices=[...]`): with several, every batch / plan call is sharded by
+    entry across them inside the library (no collective; entries are independent).  One process per GPU (one Context per
+    rank) works just as well -- bench.py does that, because the driver launches it with torchrun."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
         self.L = _ffi.lib()
         h = C.c_void_p()
-        rc = self.L.pna_cuda_init(C.byref(h), device)
+        ids = [int(device)] if devices is None else [int(d) for d in devices]
+        arr = (C.c_int * len(ids))(*ids)
+        rc = self.L.pna_cuda_init(C.byref(h), arr, len(ids))
         if rc != OK:
             raise PnaCudaError(rc, "pna_cuda_init failed: no usable sm_100 device (there is no CPU fallback)")
         self.h = h
-        self.device = device
+        self.device = ids[0]
+        self.devices = ids
 
     def close(self):
         if getattr(self, "h", None):

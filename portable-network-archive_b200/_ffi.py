@@ -14,7 +14,8 @@ OK, E_INVALID_DATA, E_UNEXPECTED_EOF, E_INVALID_INPUT, E_UNSUPPORTED, E_NOSPACE,
 UINT64_MAX = (1 << 64) - 1
 
 EXPORTS = [
-    "pna_cuda_init", "pna_cuda_destroy", "pna_cuda_strerror", "pna_cuda_last_error", "pna_cuda_host_alloc",
+    "pna_cuda_init", "pna_cuda_device_count", "pna_cuda_device_id", "pna_cuda_decode_size_bound", "pna_cuda_size_hint_trusted",
+    "pna_cuda_decode_plan_create_in_image", "pna_cuda_destroy", "pna_cuda_strerror", "pna_cuda_last_error", "pna_cuda_host_alloc",
     "pna_cuda_host_free", "pna_cuda_stream", "pna_cuda_launch_count", "pna_cuda_crc32", "pna_cuda_crc32_image",
     "pna_cuda_decode_batch", "pna_cuda_decode_plan_create", "pna_cuda_decode_plan_create_crc", "pna_cuda_plan_crc_results", "pna_cuda_decode_plan_run", "pna_cuda_decode_plan_fetch",
     "pna_cuda_decode_plan_lengths", "pna_cuda_decode_plan_crc32_out", "pna_cuda_decode_plan_fetch_ranges",
@@ -62,7 +63,13 @@ def lib():
         raise PnaCudaError(E_CUDA, f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = C.CDLL(LIB_PATH)
     vp, u32, u64, i32p = C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_int32)
-    L.pna_cuda_init.argtypes = [C.POINTER(vp), C.c_int]
+    L.pna_cuda_init.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.pna_cuda_device_count.argtypes = [vp]
+    L.pna_cuda_device_id.argtypes = [vp, C.c_int]
+    L.pna_cuda_decode_size_bound.argtypes = [C.c_uint8, u64]
+    L.pna_cuda_decode_size_bound.restype = u64
+    L.pna_cuda_size_hint_trusted.argtypes = [C.c_uint8, u64, u64]
+    L.pna_cuda_decode_plan_create_in_image.argtypes = [vp, C.POINTER(DecodeDesc), u32, vp, u64, C.POINTER(Span), C.POINTER(u32), i32p, u32, C.POINTER(vp)]
     L.pna_cuda_destroy.argtypes = [vp]
     L.pna_cuda_destroy.restype = None
     L.pna_cuda_strerror.argtypes = [C.c_int32]
@@ -85,6 +92,7 @@ def lib():
     L.pna_cuda_plan_crc_results.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.pna_cuda_decode_plan_run.argtypes = [vp]
     L.pna_cuda_decode_plan_fetch.argtypes = [vp, C.POINTER(Buf), i32p]
+    L.pna_cuda_decode_plan_lengths.argtypes = [vp, C.POINTER(u64), i32p]
     L.pna_cuda_plan_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.pna_cuda_encode_stage_name.restype = C.c_char_p
     L.pna_cuda_encode_stage_name.argtypes = [u32]

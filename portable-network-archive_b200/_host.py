@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpna_host.so")
 EXPORTS = ["pnah_open", "pnah_close", "pnah_entry_count", "pnah_entry_get", "pnah_chunk_count", "pnah_set_key", "pnah_prepare",
            "pnah_file_count", "pnah_file_get", "pnah_file_sizes", "pnah_extract_files", "pnah_create", "pnah_create_bound", "pnah_create_solid", "pnah_create_solid_bound",
-           "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files", "pnah_open_multipart", "pnah_split"]
+           "pnah_open_file", "pnah_extract_to_dir", "pnah_create_from_files", "pnah_open_multipart", "pnah_split",
+           "pnah_extract_range", "pnah_extract_files_on", "pnah_create_on"]
 
 
 class EntryInfo(C.Structure):
@@ -54,6 +55,12 @@ def lib():
         L.pnah_file_get.argtypes = [vp, u32, C.POINTER(C.c_char_p), C.POINTER(u64)]
         L.pnah_file_sizes.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_int32)]
         L.pnah_extract_files.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(C.c_int32), C.c_int, C.c_int, u64, C.c_int, C.c_char_p, u64]
+        L.pnah_extract_range.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(C.c_int32), C.c_int, C.c_int, u64, C.c_int, u64, u64, C.c_char_p, u64]
+        L.pnah_extract_files_on.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(C.c_int32), C.POINTER(C.c_int), u32, C.c_int, u64, C.c_int,
+                                            C.c_char_p, u64]
+        L.pnah_create_on.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(u64), C.c_char_p, C.c_uint8, C.c_int32,
+                                     C.c_uint8, C.c_uint8, C.c_char_p, C.c_char_p, u32, C.POINTER(C.c_int), u32, C.c_int, u64, vp, u64,
+                                     C.POINTER(u64), C.c_char_p, u64]
         L.pnah_create.argtypes = [u32, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(u64), C.c_char_p, C.c_uint8, C.c_int32,
                                   C.c_uint8, C.c_uint8, C.c_char_p, C.c_char_p, u32, C.c_int, C.c_int, u64, vp, u64, C.POINTER(u64),
                                   C.c_char_p, u64]
@@ -192,28 +199,58 @@ class HostArchive:
             out.append((name.value.decode(), int(size.value), st))
         return out
 
-    def extract_files(self, out: np.ndarray | None = None, device=0, workers=3, group_bytes=256 << 20, verify=True):
-        """Returns (out buffer, offsets, statuses).  `out`: optional (pinned) uint8 array of sum(sizes) bytes."""
-        self.prepare(device)
+    def extract_files(self, out: np.ndarray | None = None, device=0, workers=3, group_bytes=256 << 20, verify=True, devices=None):
+        """Returns (out buffer, offsets, statuses).  `out`: optional (pinned) uint8 array of sum(sizes) bytes.
+        devices: list of GPUs to partition the entries over (workers threads each); default: the single `device`."""
+        self.prepare(device if devices is None else devices[0])
         nf = int(self.L.pnah_file_count(self.h))
         sizes = np.zeros(max(nf, 1), dtype=np.uint64)
         self.L.pnah_file_sizes(self.h, sizes.ctypes.data_as(C.POINTER(C.c_uint64)), None)
         offs = np.zeros(nf + 1, dtype=np.uint64)
-        offs[1:] = np.cumsum((sizes[:nf] + np.uint64(15)) // np.uint64(16) * np.uint64(16), dtype=np.uint64)
+        total = 0
+        for i in range(nf):   # checked sum: sizes are derived from untrusted archive fields
+            total += (int(sizes[i]) + 15) // 16 * 16
+            if total >= 1 << 60:
+                raise HostError(_ffi.E_OOM, "decoded sizes overflow the buffer layout")
+            offs[i + 1] = total
         if out is None:
-            out = np.empty(int(offs[-1]) + 16, dtype=np.uint8)
+            out = np.empty(total + 16, dtype=np.uint8)
+        elif out.size < total:
+            raise HostError(_ffi.E_NOSPACE, f"output buffer of {out.size} bytes, {total} needed")
         st = (C.c_int32 * max(nf, 1))()
         err = C.create_string_buffer(512)
-        rc = self.L.pnah_extract_files(self.h, out.ctypes.data, offs.ctypes.data_as(C.POINTER(C.c_uint64)), st, device, workers,
-                                       group_bytes, int(verify), err, 512)
+        if devices is None:
+            rc = self.L.pnah_extract_files(self.h, out.ctypes.data, offs.ctypes.data_as(C.POINTER(C.c_uint64)), st, device, workers,
+                                           group_bytes, int(verify), err, 512)
+        else:
+            dv = (C.c_int * len(devices))(*devices)
+            rc = self.L.pnah_extract_files_on(self.h, out.ctypes.data, offs.ctypes.data_as(C.POINTER(C.c_uint64)), st, dv, len(devices),
+                                              workers, group_bytes, int(verify), err, 512)
         if rc:
             raise HostError(rc, err.value.decode())
         return out, offs, list(st)[:nf]
 
     def read_all(self, **kw):
+        """[(name, status, bytes | None)] of every FILE entry.  The length of each result is the DECODED length the stream
+        produced (files() after the extraction), not the archive's fSIZ hint; an entry that decodes to more than its hint said
+        (PNA_E_NOSPACE on the first pass) is taken again on its own with the length the first pass reported."""
         out, offs, st = self.extract_files(**kw)
+        files = self.files()
         res = []
-        for i, (name, size, _) in enumerate(self.files()):
+        for i, (name, size, _) in enumerate(files):
+            if st[i] == _ffi.E_NOSPACE:
+                one = np.empty((size + 15) // 16 * 16 + 16, dtype=np.uint8)
+                off2 = np.zeros(len(files) + 1, dtype=np.uint64)
+                off2[i + 1] = (size + 15) // 16 * 16
+                st2 = (C.c_int32 * len(files))()
+                err = C.create_string_buffer(512)
+                rc = self.L.pnah_extract_range(self.h, one.ctypes.data, off2.ctypes.data_as(C.POINTER(C.c_uint64)), st2, kw.get("device", 0), 1,
+                                               kw.get("group_bytes", 256 << 20), 0, i, i + 1, err, 512)
+                if rc:
+                    raise HostError(rc, err.value.decode())
+                size2 = self.files()[i][1]
+                res.append((name, st2[i], one[:size2].tobytes() if st2[i] == 0 else None))
+                continue
             res.append((name, st[i], out[int(offs[i]):int(offs[i]) + size].tobytes() if st[i] == 0 else None))
         return res
 
@@ -256,23 +293,28 @@ def split_layout(archive, max_part_bytes: int, max_parts: int = 1 << 16):
 
 
 def create_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, key=None, phsf=None, ivs=None, max_chunk_size=0,
-                   device=0, workers=3, group_bytes=256 << 20, out=None):
-    """files: list of (name, bytes-like).  Returns the archive bytes (numpy view of `out` when given)."""
+                   device=0, workers=3, group_bytes=256 << 20, out=None, devices=None):
+    """files: list of (name, bytes-like).  Returns the archive bytes (numpy view of `out` when given).
+    ivs: 16 bytes per file, or None: the writer draws a fresh IV per entry from the OS (entry/write.rs:108-111).
+    devices: list of GPUs to partition the files over (`workers` threads each); default: the single `device`."""
     L = lib()
     n = len(files)
     arrs = [f[1] if isinstance(f[1], np.ndarray) else np.frombuffer(f[1], dtype=np.uint8) for f in files]
     names = (C.c_char_p * max(n, 1))(*[f[0].encode() for f in files])
     ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
     lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrs])
-    if ivs is None and encryption:
-        ivs = os.urandom(16 * n)
     bound = int(L.pnah_create_bound(n, names, lens, compression, encryption, (phsf or "").encode(), max_chunk_size))
     if out is None:
         out = np.empty(bound, dtype=np.uint8)
     olen = C.c_uint64(0)
     err = C.create_string_buffer(512)
-    rc = L.pnah_create(n, names, ptrs, lens, ivs, compression, level, encryption, cipher_mode, key or bytes(32), (phsf or "").encode(),
-                       max_chunk_size, device, workers, group_bytes, out.ctypes.data, out.size, C.byref(olen), err, 512)
+    if devices is None:
+        rc = L.pnah_create(n, names, ptrs, lens, ivs, compression, level, encryption, cipher_mode, key or bytes(32), (phsf or "").encode(),
+                           max_chunk_size, device, workers, group_bytes, out.ctypes.data, out.size, C.byref(olen), err, 512)
+    else:
+        dv = (C.c_int * len(devices))(*devices)
+        rc = L.pnah_create_on(n, names, ptrs, lens, ivs, compression, level, encryption, cipher_mode, key or bytes(32), (phsf or "").encode(),
+                              max_chunk_size, dv, len(devices), workers, group_bytes, out.ctypes.data, out.size, C.byref(olen), err, 512)
     if rc:
         raise HostError(rc, err.value.decode())
     return out[:olen.value]

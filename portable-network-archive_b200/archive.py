@@ -307,6 +307,8 @@ class SolidEntry(_EntryBase):
                 self.bodies.append(self._body(ch))
             elif ch.ty == ChunkType.PHSF:
                 self.phsf = bytes(self._body(ch)).decode("utf-8")
+            elif ch.ty[0:1].isupper():   # unknown critical chunk, entry.rs:716
+                raise PnaError(_ffi.E_INVALID_DATA, f"unknown critical chunk type: {ch.ty!r}")
 
     def entries(self, options: ReadOptions | None = None, ctx=None):
         """SolidEntry::entries (entry.rs:567): decode the solid stream on the GPU, then re-parse the inner
@@ -339,6 +341,10 @@ def _group(buf, chunks, ctx):
     """next_raw_item (archive/read.rs:46-73): gather chunks up to FEND / SEND."""
     cur, kind = None, None
     for ch in chunks:
+        if ch.ty == ChunkType.AEND:   # archive/read.rs:58: end of this archive -- nothing behind it is an entry
+            return
+        if ch.ty == ChunkType.ANXT:   # archive/read.rs:57: only flags that another part follows
+            continue
         if cur is None:
             if ch.ty == ChunkType.FHED:
                 cur, kind = [ch], "F"

@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pna_cuda.h"
@@ -28,9 +29,13 @@ using namespace pna;
 
 // ------------------------------------------------------------------------------------------------
 struct pna_ctx {
+    // A context over several devices (pna_cuda_init with n_devices > 1) is a dispatcher: `devs` holds one single-device
+    // context per GPU and every batch call shards its entries across them (multi_host.cuh).  Single-device contexts have no devs.
+    std::vector<pna_ctx*> devs;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaEvent_t sync_ev = nullptr;   // blocking-sync event: waits sleep instead of spinning (many contexts per box share the host cores)
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
@@ -43,6 +48,11 @@ struct pna_ctx {
     bool fail(const char* what, cudaError_t e) {
         err = std::string(what) + ": " + cudaGetErrorString(e);
         return false;
+    }
+    // wait for everything queued on the stream; the calling thread sleeps (cudaEventBlockingSync)
+    cudaError_t sync() {
+        cudaError_t e = cudaEventRecord(sync_ev, stream);
+        return e == cudaSuccess ? cudaEventSynchronize(sync_ev) : e;
     }
 };
 
@@ -141,6 +151,56 @@ struct DevArr {   // growable device array (never shrinks); returned to the cach
 
 static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+namespace pna { namespace multi {
+// LPT: heaviest entries first onto the least loaded device; each device keeps its entries in caller order
+static std::vector<std::vector<uint32_t>> shard(const std::vector<uint64_t>& weight, size_t n_dev) {
+    std::vector<uint32_t> order(weight.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+    std::vector<uint64_t> load(n_dev, 0);
+    std::vector<std::vector<uint32_t>> part(n_dev);
+    for (uint32_t i : order) {
+        size_t best = 0;
+        for (size_t d = 1; d < n_dev; d++) if (load[d] < load[best]) best = d;
+        part[best].push_back(i);
+        load[best] += weight[i] + 1;
+    }
+    for (auto& p : part) std::sort(p.begin(), p.end());
+    return part;
+}
+// f(d) on one host thread per device; the first non-zero return code wins
+template <class F>
+static int for_devices(size_t n_dev, F&& f) {
+    std::vector<int> rc(n_dev, PNA_OK);
+    std::vector<std::thread> th;
+    for (size_t d = 1; d < n_dev; d++) th.emplace_back([&, d]() { rc[d] = f(d); });
+    rc[0] = f(0);
+    for (auto& t : th) t.join();
+    for (int r : rc) if (r != PNA_OK) return r;
+    return PNA_OK;
+}
+static void carry_error(pna_ctx* root) {
+    for (pna_ctx* c : root->devs) if (!c->err.empty()) { root->err = "device " + std::to_string(c->device) + ": " + c->err; return; }
+}
+
+static int crc32(pna_ctx* root, const pna_span* spans, uint32_t n, uint32_t* crc_out);
+static int decode_plan_create(pna_ctx* root, const pna_decode_desc* descs, uint32_t n, const uint8_t* image, uint64_t image_len,
+                              const pna_span* crc_spans, const uint32_t* crc_expect, const int32_t* crc_entry, uint32_t n_spans, bool with_crc,
+                              pna_plan** plan);
+static int decode_plan_run(pna_plan* P);
+static int decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* status);
+static int decode_plan_lengths(pna_plan* P, uint64_t* out_len, int32_t* status);
+static int plan_crc_results(pna_plan* P, uint32_t* crc_out, uint32_t* n_broken);
+static void plan_destroy(pna_plan* P);
+static int encode_plan_create(pna_ctx* root, const pna_encode_desc* descs, uint32_t n, pna_plan** plan);
+static int encode_plan_run(pna_plan* P);
+static int encode_plan_lengths(pna_plan* P, uint64_t* out_len, int32_t* status);
+static int encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status);
+static int route(pna_plan* P, uint32_t entry, pna_plan** sub, uint32_t* local);
+static void sum_stats(pna_plan* P, uint64_t* a, uint64_t* b, uint64_t* c, bool counts);
+static int stage_ms(pna_plan* P, float* ms, uint32_t cap);
+}}
+
 // ------------------------------------------------------------------------------------------------
 // Host span -> device image staging with range coalescing: spans that lie close together in host
 // memory (e.g. the FDAT bodies of one mmap'd archive) travel in one cudaMemcpyAsync.
@@ -149,6 +209,11 @@ struct Stager {
     std::vector<Range> ranges;
     uint64_t total = 0;
     static constexpr uint64_t GAP = 64 * 1024;
+    // Gaps between spans are carried along only inside a host range the caller DECLARED as one allocation (the archive
+    // image of pna_cuda_decode_plan_create_in_image): bytes between independent allocations are not the caller's to read.
+    const uint8_t* image = nullptr;
+    uint64_t image_len = 0;
+    bool inside(const uint8_t* p, uint64_t len) const { return image && p >= image && len <= image_len && (uint64_t)(p - image) <= image_len - len; }
     bool sealed = false;   // after the CRC spans were registered: later spans first try to resolve inside a range
     // returns the device offset of the span
     uint64_t add(const uint8_t* p, uint64_t len) {
@@ -168,7 +233,8 @@ struct Stager {
         if (!ranges.empty()) {
             Range& r = ranges.back();
             const uint8_t* end = r.host + r.len;
-            if (p >= r.host && p <= end + GAP) {
+            const bool bridge = inside(r.host, r.len) && inside(p, len);
+            if (p >= r.host && p <= end + (bridge ? GAP : 0)) {
                 uint64_t off = r.dev_off + (uint64_t)(p - r.host);
                 if (p + len > end) { r.len = (uint64_t)(p + len - r.host); total = r.dev_off + r.len; }
                 return off;
@@ -188,8 +254,11 @@ struct Stager {
 constexpr int PNA_N_STAGES = 9;
 static const char* const PNA_STAGE_NAMES[PNA_N_STAGES] = {"crc", "cipher", "zstd_scan", "zstd_seq", "zstd_lit", "zstd_prefix", "zstd_lz", "inflate", "store"};
 
+namespace pna { namespace multi { struct Plan; } }
 // ------------------------------------------------------------------------------------------------
 struct pna_plan {
+    pna::multi::Plan* multi = nullptr;   // set: a plan of a multi-device context (multi_host.cuh); everything below is unused then
+    std::vector<uint64_t> h_crc_count_bound;
     pna_ctx* ctx = nullptr;
     int kind = 0;   // 0 decode, 1 encode
     uint32_t n = 0;
@@ -285,12 +354,34 @@ extern "C" const char* pna_cuda_strerror(int32_t s) {
     }
 }
 
-extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
-    if (!out) return PNA_E_BAD_ARG;
+static int ctx_create_single(pna_ctx** out, int device_id);
+extern "C" int pna_cuda_init(pna_ctx** out, const int* device_ids, int n_devices) {
+    if (!out || n_devices < 0) return PNA_E_BAD_ARG;
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return PNA_E_CUDA;   // no fallback: fail loudly
-    if (device_id < 0 || device_id >= count) return PNA_E_BAD_ARG;
+    std::vector<int> ids;
+    if (device_ids) ids.assign(device_ids, device_ids + n_devices);
+    else for (int d = 0; d < (n_devices ? n_devices : count); d++) ids.push_back(d);   // NULL: the first n (0: all visible) devices
+    if (ids.empty()) return PNA_E_BAD_ARG;
+    for (size_t i = 0; i < ids.size(); i++) {
+        if (ids[i] < 0 || ids[i] >= count) return PNA_E_BAD_ARG;
+        for (size_t j = 0; j < i; j++) if (ids[j] == ids[i]) return PNA_E_BAD_ARG;
+    }
+    if (ids.size() == 1) return ctx_create_single(out, ids[0]);
+    pna_ctx* root = new pna_ctx();
+    root->device = ids[0];
+    for (int d : ids) {
+        pna_ctx* c = nullptr;
+        const int rc = ctx_create_single(&c, d);
+        if (rc != PNA_OK) { for (pna_ctx* q : root->devs) pna_cuda_destroy(q); delete root; return rc; }
+        root->devs.push_back(c);
+    }
+    root->sm_count = root->devs[0]->sm_count;
+    *out = root;
+    return PNA_OK;
+}
+static int ctx_create_single(pna_ctx** out, int device_id) {
     pna_ctx* ctx = new pna_ctx();
     ctx->device = device_id;
     if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return PNA_E_CUDA; }
@@ -298,6 +389,7 @@ extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
     if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess || prop.major < 10) { delete ctx; return PNA_E_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PNA_E_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return PNA_E_CUDA; }
     CrcConsts* hc = new CrcConsts();
     crc_make_consts(hc);
     aes_make_tables(&ctx->h_aes);
@@ -335,8 +427,10 @@ extern "C" int pna_cuda_init(pna_ctx** out, int device_id) {
 
 extern "C" void pna_cuda_destroy(pna_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->devs.empty()) { for (pna_ctx* c : ctx->devs) pna_cuda_destroy(c); delete ctx; return; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     g_dev_cache.trim(ctx->device);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
@@ -349,12 +443,22 @@ extern "C" void* pna_cuda_host_alloc(pna_ctx* ctx, uint64_t bytes) {
     if (!ctx) return nullptr;
     cudaSetDevice(ctx->device);
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;   // pinned for every device of the process
     return p;
 }
 extern "C" void pna_cuda_host_free(pna_ctx* ctx, void* p) { if (p) cudaFreeHost(p); }
-extern "C" void* pna_cuda_stream(pna_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-extern "C" uint64_t pna_cuda_launch_count(pna_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int pna_cuda_device_count(pna_ctx* ctx) { return !ctx ? 0 : ctx->devs.empty() ? 1 : (int)ctx->devs.size(); }
+extern "C" int pna_cuda_device_id(pna_ctx* ctx, int i) {
+    if (!ctx || i < 0 || i >= pna_cuda_device_count(ctx)) return -1;
+    return ctx->devs.empty() ? ctx->device : ctx->devs[i]->device;
+}
+extern "C" void* pna_cuda_stream(pna_ctx* ctx) { return !ctx ? nullptr : ctx->devs.empty() ? (void*)ctx->stream : (void*)ctx->devs[0]->stream; }
+extern "C" uint64_t pna_cuda_launch_count(pna_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (pna_ctx* c : ctx->devs) n += c->launches;
+    return n;
+}
 
 // ------------------------------------------------------------------------------------------------
 // seam 1: CRC
@@ -390,7 +494,7 @@ static int crc_run(pna_ctx* ctx, const uint8_t* d_img, const std::vector<uint64_
         ctx->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess ||
             (e = cudaMemcpyAsync(crc_out, d_crc.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
-            (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+            (e = ctx->sync()) != cudaSuccess) {
             ctx->fail("crc run", e); rc = PNA_E_CUDA; break;
         }
     } while (0);
@@ -401,6 +505,7 @@ static int crc_run(pna_ctx* ctx, const uint8_t* d_img, const std::vector<uint64_
 extern "C" int pna_cuda_crc32(pna_ctx* ctx, const pna_span* spans, uint32_t n, uint32_t* crc_out) {
     if (!ctx || (!spans && n) || (!crc_out && n)) return PNA_E_BAD_ARG;
     if (n == 0) return PNA_OK;
+    if (!ctx->devs.empty()) return multi::crc32(ctx, spans, n, crc_out);
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     Stager st;
@@ -410,7 +515,7 @@ extern "C" int pna_cuda_crc32(pna_ctx* ctx, const pna_span* spans, uint32_t n, u
     CK(d_img.reserve(st.total + 64));
     int rc = st.upload(ctx, d_img.p);
     if (rc == PNA_OK) rc = crc_run(ctx, d_img.p, off, len.data(), n, crc_out);
-    cudaStreamSynchronize(ctx->stream);
+    ctx->sync();
     d_img.release();
     return rc;
 }
@@ -421,6 +526,11 @@ extern "C" int pna_cuda_crc32_image(pna_ctx* ctx, const uint8_t* image, uint64_t
     if (n == 0) return PNA_OK;
     for (uint32_t i = 0; i < n; i++)
         if (span_off[i] > image_len || span_len[i] > image_len - span_off[i]) return PNA_E_BAD_ARG;
+    if (!ctx->devs.empty()) {
+        std::vector<pna_span> sp(n);
+        for (uint32_t i = 0; i < n; i++) sp[i] = {image + span_off[i], span_len[i]};
+        return multi::crc32(ctx, sp.data(), n, crc_out);
+    }
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     DevArr<uint8_t> d_img;
@@ -430,7 +540,7 @@ extern "C" int pna_cuda_crc32_image(pna_ctx* ctx, const uint8_t* image, uint64_t
     if (e != cudaSuccess) { ctx->fail("image upload", e); rc = PNA_E_CUDA; }
     std::vector<uint64_t> off(span_off, span_off + n);
     if (rc == PNA_OK) rc = crc_run(ctx, d_img.p, off, span_len, n, crc_out);
-    cudaStreamSynchronize(ctx->stream);
+    ctx->sync();
     d_img.release();
     return rc;
 }
@@ -442,15 +552,31 @@ static int variant_of(const EntryRec& e) {
     return (e.encryption == 1 ? 1 : 3) + (e.cipher_mode == 1 ? 0 : 1);
 }
 
-struct CrcReq { const pna_span* spans; const uint32_t* expect; const int32_t* entry_of; uint32_t n; };
+// Upper bound of what a compressed stream of `comp_len` bytes can decode to: zstd emits at most one 128 KiB block per 4
+// stream bytes (RLE block: 3-byte header + 1 byte), deflate at most 1032 bytes per stream byte, store is the identity.
+static uint64_t decode_size_bound(uint8_t compression, uint64_t comp_len) {
+    if (compression == PNA_COMPRESSION_ZSTD) return comp_len > ((uint64_t)1 << 44) ? UINT64_MAX / 2 : (comp_len / 3 + 2) * 131072ull;
+    if (compression == PNA_COMPRESSION_DEFLATE) return comp_len > ((uint64_t)1 << 50) ? UINT64_MAX / 2 : comp_len * 1032ull + 1024;
+    return comp_len;
+}
+extern "C" uint64_t pna_cuda_decode_size_bound(uint8_t compression, uint64_t stream_len) { return decode_size_bound(compression, stream_len); }
+// whether a size hint (fSIZ) is used to lay out the output, or ignored in favour of the exact sizing pass
+static bool size_hint_trusted(uint8_t compression, uint64_t comp_len, uint64_t hint) {
+    if (hint == UINT64_MAX || hint > decode_size_bound(compression, comp_len)) return false;
+    return !(hint > ((uint64_t)1 << 30) && hint / 256 > comp_len);   // huge both absolutely and relative to the stream
+}
+extern "C" int pna_cuda_size_hint_trusted(uint8_t compression, uint64_t stream_len, uint64_t hint) { return size_hint_trusted(compression, stream_len, hint) ? 1 : 0; }
+struct CrcReq { const pna_span* spans; const uint32_t* expect; const int32_t* entry_of; uint32_t n; const uint8_t* image; uint64_t image_len; };
 static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint64_t* caps, const CrcReq* crc,
                              pna_plan* P) {
     P->ctx = ctx; P->kind = 0; P->n = n;
     P->h_entries.resize(n);
     Stager st;
+    if (crc) { st.image = crc->image; st.image_len = crc->image_len; }
     // chunk spans (type||data) first: they start 4 bytes before the bodies, so bodies fall into the same ranges
     // when both are registered in address order; spans and bodies may also interleave arbitrarily.
     std::vector<uint64_t> crc_off;
+    if (crc && crc->n && !crc->spans) return PNA_E_BAD_ARG;
     if (crc && crc->n) {
         // merge-register spans and bodies in ascending host address order so that ranges coalesce
         P->n_crc = crc->n;
@@ -629,6 +755,12 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
     for (uint32_t i = 0; i < n; i++) {
         EntryRec& e = P->h_entries[i];
         uint64_t cap = caps ? caps[i] : descs[i].raw_size_hint;
+        // fSIZ is untrusted input (the reference never sizes anything from it: its readers are stream-driven).  No stream of
+        // comp_len bytes can decode to more than `bound`, so a larger capacity is clamped (a caller's buffer) or, for a mere
+        // hint, ignored in favour of the exact sizing pass; so is a hint that is huge both absolutely and relative to the stream.
+        const uint64_t bound = decode_size_bound(e.compression, e.comp_len);
+        if (caps) { if (cap != UINT64_MAX && cap > bound) cap = bound; }
+        else if (!size_hint_trusted(e.compression, e.comp_len, cap)) cap = UINT64_MAX;
         e.out_cap = cap;
         if (e.status != ST_OK) { e.out_cap = 0; continue; }
         if (cap == UINT64_MAX) all_caps = false;
@@ -674,7 +806,7 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
         CK(cudaMemcpyAsync(P->d_crc_expect.p, P->h_crc_expect.data(), P->n_crc * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(P->d_crc_entry.p, P->h_crc_entry.data(), P->n_crc * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));   // the borrowed host spans may go away after this call
+    CK(ctx->sync());   // the borrowed host spans may go away after this call
     return PNA_OK;
 }
 
@@ -684,7 +816,10 @@ static int decode_layout_out(pna_plan* P) {
     uint64_t cur = 0;
     for (EntryRec& e : P->h_entries) {
         e.out_off = cur;
-        if (e.status == ST_OK && e.out_cap != UINT64_MAX) cur += align_up(e.out_cap, 16);
+        if (e.status == ST_OK && e.out_cap != UINT64_MAX) {
+            if (e.out_cap > ((uint64_t)1 << 60) || cur > ((uint64_t)1 << 60)) return PNA_E_OOM;   // checked: no wrap of the layout
+            cur += align_up(e.out_cap, 16);
+        }
     }
     P->out_bytes = cur;
     CK(P->d_out.reserve(cur + 256));
@@ -874,7 +1009,7 @@ static int launch_inflate(pna_plan* P, int size_only) {
         inf::inflate_tokens_kernel<<<(nd + inf::TOKEN_CTA - 1) / inf::TOKEN_CTA, inf::TOKEN_CTA, inf::TOKEN_SMEM_BYTES, ctx->stream>>>(
             P->d_buf.p, P->d_entries.p, P->d_inf.p, nd, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
         LAUNCHED();
-        CK(cudaStreamSynchronize(ctx->stream));   // `all` is a local
+        CK(ctx->sync());   // `all` is a local
         return PNA_OK;
     }
     const uint32_t ni = (uint32_t)P->h_inf.size(), nb = (uint32_t)P->h_deflate_big.size();
@@ -926,7 +1061,7 @@ static int decode_prepare(pna_plan* P) {
             return P->h_entries[P->h_ze[a].entry].comp_len > P->h_entries[P->h_ze[b].entry].comp_len; });
         if ((rc = launch_zstd_front(P, true))) return rc;
         CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ctx->sync());
         uint64_t nb = 0;
         for (auto& z : P->h_ze) { z.blk_begin = (uint32_t)nb; nb += z.blk_count; }
         if (nb > 0xFFFFFFF0ull) return PNA_E_OOM;
@@ -936,7 +1071,7 @@ static int decode_prepare(pna_plan* P) {
         CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = launch_zstd_front(P, false))) return rc;
         CK(cudaMemcpyAsync(P->h_ze.data(), P->d_ze.p, nz * sizeof(zs::ZEntry), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ctx->sync());
         uint64_t lit = 0, seq = 0, nu = 0;
         std::vector<uint64_t> lb(P->n, 0), sb(P->n, 0);
         for (auto& z : P->h_ze) {
@@ -968,7 +1103,7 @@ static int decode_prepare(pna_plan* P) {
         CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
         zs::zstd_units_kernel<<<(nz + 127) / 128, 128, 0, ctx->stream>>>(P->d_ze.p, nz, P->d_blocks.p, P->d_lz_units.p);
         LAUNCHED();
-        CK(cudaStreamSynchronize(ctx->stream));   // lb/sb/unit_order are locals
+        CK(ctx->sync());   // lb/sb/unit_order are locals
     }
     if (P->need_sizing) {
         // exact sizes: zstd from the entropy+prefix stages, deflate from a count-only pass, store = comp_len
@@ -979,7 +1114,7 @@ static int decode_prepare(pna_plan* P) {
         P->sized_entropy = true;
         std::vector<EntryRec> dev(P->n);
         CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ctx->sync());
         for (uint32_t i = 0; i < P->n; i++) {
             EntryRec& e = P->h_entries[i];
             if (e.status != ST_OK || e.out_cap != UINT64_MAX) continue;
@@ -989,7 +1124,7 @@ static int decode_prepare(pna_plan* P) {
         }
     }
     if ((rc = decode_layout_out(P))) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     P->prepared = true;
     return PNA_OK;
 }
@@ -1037,7 +1172,7 @@ static int decode_launch_all(pna_plan* P, bool fresh) {
         CK(cudaMemcpyAsync(P->d_layout.p, oc.data(), oc.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         set_layout_kernel<<<(P->n + 127) / 128, 128, 0, ctx->stream>>>(P->d_entries.p, P->d_layout.p, P->n);
         LAUNCHED();
-        CK(cudaStreamSynchronize(ctx->stream));   // oc is a local
+        CK(ctx->sync());   // oc is a local
         STAGE(0); STAGE(1); STAGE(2); STAGE(3);
         if (!P->sized_entropy) {
             if ((rc = launch_zstd_seq(P))) return rc;
@@ -1063,6 +1198,9 @@ static int decode_plan_create_ex(pna_ctx* ctx, const pna_decode_desc* descs, uin
                                  pna_plan** plan) {
     if (!ctx || !plan || (!descs && n)) return PNA_E_BAD_ARG;
     *plan = nullptr;
+    if (!ctx->devs.empty())   // (caps only come from pna_cuda_decode_batch, which shards before it gets here)
+        return multi::decode_plan_create(ctx, descs, n, crc ? crc->image : nullptr, crc ? crc->image_len : 0, crc ? crc->spans : nullptr,
+                                         crc ? crc->expect : nullptr, crc ? crc->entry_of : nullptr, crc ? crc->n : 0, crc != nullptr, plan);
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     pna_plan* P = new pna_plan();
@@ -1079,11 +1217,21 @@ extern "C" int pna_cuda_decode_plan_create_crc(pna_ctx* ctx, const pna_decode_de
                                                pna_plan** plan) {
     if (n_spans && (!crc_spans || !crc_expect || !crc_entry)) return PNA_E_BAD_ARG;
     for (uint32_t i = 0; i < n_spans; i++) if (crc_entry[i] >= (int64_t)n) return PNA_E_BAD_ARG;
-    CrcReq rq{crc_spans, crc_expect, crc_entry, n_spans};
+    CrcReq rq{crc_spans, crc_expect, crc_entry, n_spans, nullptr, 0};
+    return decode_plan_create_ex(ctx, descs, n, nullptr, &rq, plan);
+}
+extern "C" int pna_cuda_decode_plan_create_in_image(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, const uint8_t* image,
+                                                    uint64_t image_len, const pna_span* crc_spans, const uint32_t* crc_expect,
+                                                    const int32_t* crc_entry, uint32_t n_spans, pna_plan** plan) {
+    if (n_spans && (!crc_spans || !crc_expect || !crc_entry)) return PNA_E_BAD_ARG;
+    if (!image && image_len) return PNA_E_BAD_ARG;
+    for (uint32_t i = 0; i < n_spans; i++) if (crc_entry[i] >= (int64_t)n) return PNA_E_BAD_ARG;
+    CrcReq rq{crc_spans, crc_expect, crc_entry, n_spans, image, image_len};
     return decode_plan_create_ex(ctx, descs, n, nullptr, &rq, plan);
 }
 extern "C" int pna_cuda_plan_crc_results(pna_plan* P, uint32_t* crc_out, uint32_t* n_broken) {
     if (!P) return PNA_E_BAD_ARG;
+    if (P->multi) return multi::plan_crc_results(P, crc_out, n_broken);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -1091,11 +1239,12 @@ extern "C" int pna_cuda_plan_crc_results(pna_plan* P, uint32_t* crc_out, uint32_
     if (!P->n_crc || !P->prepared) return PNA_OK;
     if (crc_out) CK(cudaMemcpyAsync(crc_out, P->d_crc_val.p, P->n_crc * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (n_broken) CK(cudaMemcpyAsync(n_broken, P->d_crc_broken.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     return PNA_OK;
 }
 extern "C" int pna_cuda_decode_plan_run(pna_plan* P) {
     if (!P || P->kind != 0) return PNA_E_BAD_ARG;
+    if (P->multi) return multi::decode_plan_run(P);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -1109,6 +1258,7 @@ extern "C" int pna_cuda_decode_plan_run(pna_plan* P) {
 }
 extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* status) {
     if (!P || P->kind != 0 || ((!out || !status) && P->n)) return PNA_E_BAD_ARG;
+    if (P->multi) return multi::decode_plan_fetch(P, out, status);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -1116,7 +1266,7 @@ extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* st
     if (!P->prepared) return PNA_E_BAD_ARG;
     std::vector<EntryRec> dev(P->n);
     CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     uint64_t plain = 0;
     // D2H: entries whose host buffers mirror the device layout (same distance between starts, inside the previous
     // buffer's capacity) travel in ONE cudaMemcpyAsync -- a million small files must not mean a million copies
@@ -1161,11 +1311,12 @@ extern "C" int pna_cuda_decode_plan_fetch(pna_plan* P, pna_buf* out, int32_t* st
         if (rc) return rc;
     }
     P->plain_bytes = plain;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     return PNA_OK;
 }
 extern "C" int pna_cuda_decode_plan_lengths(pna_plan* P, uint64_t* out_len, int32_t* status) {
     if (!P || P->kind != 0 || ((!out_len || !status) && P->n)) return PNA_E_BAD_ARG;
+    if (P->multi) return multi::decode_plan_lengths(P, out_len, status);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -1173,7 +1324,7 @@ extern "C" int pna_cuda_decode_plan_lengths(pna_plan* P, uint64_t* out_len, int3
     if (!P->prepared) return PNA_E_BAD_ARG;
     std::vector<EntryRec> dev(P->n);
     CK(cudaMemcpyAsync(dev.data(), P->d_entries.p, P->n * sizeof(EntryRec), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     P->h_out_len.assign(P->n, 0);
     for (uint32_t i = 0; i < P->n; i++) {
         const EntryRec& e = dev[i];
@@ -1196,6 +1347,11 @@ static int plan_entry_out(pna_plan* P, uint32_t entry, const uint8_t** base, uin
 }
 extern "C" int pna_cuda_decode_plan_crc32_out(pna_plan* P, uint32_t entry, const uint64_t* span_off, const uint64_t* span_len,
                                               uint32_t n, uint32_t* crc_out) {
+    if (P && P->multi) {
+        pna_plan* sub = nullptr; uint32_t loc = 0;
+        const int r = multi::route(P, entry, &sub, &loc);
+        return r ? r : pna_cuda_decode_plan_crc32_out(sub, loc, span_off, span_len, n, crc_out);
+    }
     const uint8_t* base = nullptr;
     uint64_t len = 0;
     int rc = plan_entry_out(P, entry, &base, &len);
@@ -1211,6 +1367,11 @@ extern "C" int pna_cuda_decode_plan_crc32_out(pna_plan* P, uint32_t entry, const
 }
 extern "C" int pna_cuda_decode_plan_fetch_ranges(pna_plan* P, uint32_t entry, const uint64_t* src_off, const uint64_t* len,
                                                  uint8_t* const* dst, uint32_t n) {
+    if (P && P->multi) {
+        pna_plan* sub = nullptr; uint32_t loc = 0;
+        const int r = multi::route(P, entry, &sub, &loc);
+        return r ? r : pna_cuda_decode_plan_fetch_ranges(sub, loc, src_off, len, dst, n);
+    }
     const uint8_t* base = nullptr;
     uint64_t total = 0;
     int rc = plan_entry_out(P, entry, &base, &total);
@@ -1231,11 +1392,12 @@ extern "C" int pna_cuda_decode_plan_fetch_ranges(pna_plan* P, uint32_t entry, co
         run_src = src_off[i]; run_len = len[i]; run_dst = dst[i];
     }
     if (run_len) CK(cudaMemcpyAsync(run_dst, base + run_src, run_len, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     return PNA_OK;
 }
 extern "C" int pna_cuda_plan_stats(pna_plan* P, uint64_t* stream_bytes, uint64_t* plain_bytes, uint64_t* launches_per_run) {
     if (!P) return PNA_E_BAD_ARG;
+    if (P->multi) { multi::sum_stats(P, stream_bytes, plain_bytes, launches_per_run, false); return PNA_OK; }
     if (stream_bytes) *stream_bytes = P->stream_bytes;
     if (plain_bytes) *plain_bytes = P->plain_bytes;
     if (launches_per_run) *launches_per_run = P->launches_per_run;
@@ -1243,6 +1405,7 @@ extern "C" int pna_cuda_plan_stats(pna_plan* P, uint64_t* stream_bytes, uint64_t
 }
 extern "C" int pna_cuda_plan_counts(pna_plan* P, uint64_t* n_blocks, uint64_t* n_sequences, uint64_t* literal_bytes) {
     if (!P) return PNA_E_BAD_ARG;
+    if (P->multi) { multi::sum_stats(P, n_blocks, n_sequences, literal_bytes, true); return PNA_OK; }
     if (n_blocks) *n_blocks = P->n_blocks;
     if (n_sequences) *n_sequences = P->seq_total;
     if (literal_bytes) *literal_bytes = P->lit_total;
@@ -1250,6 +1413,7 @@ extern "C" int pna_cuda_plan_counts(pna_plan* P, uint64_t* n_blocks, uint64_t* n
 }
 extern "C" int pna_cuda_plan_stage_ms(pna_plan* P, float* ms, uint32_t cap) {
     if (!P) return -1;
+    if (P->multi) return multi::stage_ms(P, ms, cap);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!P->ev_recorded) return 0;
@@ -1264,15 +1428,34 @@ extern "C" int pna_cuda_plan_stage_ms(pna_plan* P, float* ms, uint32_t cap) {
 extern "C" const char* pna_cuda_stage_name(uint32_t i) { return i < (uint32_t)PNA_N_STAGES ? PNA_STAGE_NAMES[i] : ""; }
 extern "C" void pna_cuda_plan_destroy(pna_plan* P) {
     if (!P) return;
+    if (P->multi) { multi::plan_destroy(P); return; }
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    ctx->sync();
     delete P;
 }
 extern "C" int pna_cuda_decode_batch(pna_ctx* ctx, const pna_decode_desc* descs, uint32_t n, pna_buf* out, int32_t* status) {
     if (!ctx || ((!descs || !out || !status) && n)) return PNA_E_BAD_ARG;
     if (n == 0) return PNA_OK;
+    if (!ctx->devs.empty()) {   // shard by entry, one ordinary batch per device
+        std::vector<uint64_t> w(n);
+        for (uint32_t i = 0; i < n; i++) { uint64_t b = 0; for (uint32_t k = 0; k < descs[i].n_bodies; k++) b += descs[i].bodies[k].len; w[i] = b; }
+        const auto part = multi::shard(w, ctx->devs.size());
+        const int rc = multi::for_devices(ctx->devs.size(), [&](size_t d) -> int {
+            const auto& idx = part[d];
+            if (idx.empty()) return PNA_OK;
+            std::vector<pna_decode_desc> dd(idx.size());
+            std::vector<pna_buf> bb(idx.size());
+            std::vector<int32_t> st(idx.size());
+            for (size_t k = 0; k < idx.size(); k++) { dd[k] = descs[idx[k]]; bb[k] = out[idx[k]]; }
+            const int r = pna_cuda_decode_batch(ctx->devs[d], dd.data(), (uint32_t)dd.size(), bb.data(), st.data());
+            if (r == PNA_OK) for (size_t k = 0; k < idx.size(); k++) { out[idx[k]].len = bb[k].len; status[idx[k]] = st[k]; }
+            return r;
+        });
+        if (rc) multi::carry_error(ctx);
+        return rc;
+    }
     std::vector<uint64_t> caps(n);
     for (uint32_t i = 0; i < n; i++) caps[i] = out[i].cap;
     pna_plan* P = nullptr;
@@ -1318,6 +1501,7 @@ extern "C" int pna_cuda_ecb(pna_ctx* ctx, int encryption, int encrypt, const uin
                             uint8_t* out) {
     if (!ctx || !key || (!in && n_bytes) || (!out && n_bytes)) return PNA_E_BAD_ARG;
     if (encryption != 1 && encryption != 2) return PNA_E_BAD_ARG;
+    if (!ctx->devs.empty()) return pna_cuda_ecb(ctx->devs[0], encryption, encrypt, key, in, n_bytes, out);
     const uint64_t nb = n_bytes / 16;
     if (!nb) return PNA_OK;
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -1345,7 +1529,7 @@ extern "C" int pna_cuda_ecb(pna_ctx* ctx, int encryption, int encrypt, const uin
         ctx->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess ||
             (e = cudaMemcpyAsync(out, d_out.p, nb * 16, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
-            (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+            (e = ctx->sync()) != cudaSuccess) {
             ctx->fail("ecb run", e); rc = PNA_E_CUDA;
         }
     }
@@ -1356,3 +1540,4 @@ extern "C" int pna_cuda_ecb(pna_ctx* ctx, int encryption, int encrypt, const uin
 // ------------------------------------------------------------------------------------------------
 // seam 3: encode -- implemented in encode_host.cuh on top of kernels_encode.cuh
 #include "encode_host.cuh"
+#include "multi_host.cuh"

@@ -49,6 +49,52 @@ PNA_HD uint32_t bswap32(uint32_t v) {
     return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
 }
 
+
+// ---- asynchronous global -> shared copies (cp.async = LDGSTS).  Under the test-only SIMT emulator (tests/emu,
+// PNA_EMU) the copy happens at issue time.
+#if defined(__CUDACC__) || defined(PNA_EMU)
+PNA_D void cp_async16(void* smem_dst, const void* gsrc) {
+#if defined(PNA_EMU)
+    memcpy(smem_dst, gsrc, 16);
+#else
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+#endif
+}
+PNA_D void cp_async8(void* smem_dst, const void* gsrc) {
+#if defined(PNA_EMU)
+    memcpy(smem_dst, gsrc, 8);
+#else
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+#endif
+}
+PNA_D void cp_async_commit() {
+#if !defined(PNA_EMU)
+    asm volatile("cp.async.commit_group;");
+#endif
+}
+PNA_D void cp_async_wait_all() {
+#if !defined(PNA_EMU)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+PNA_D void cp_async_wait_1() {
+#if !defined(PNA_EMU)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+PNA_D uint32_t ldcg32(const uint32_t* p) {
+#if defined(PNA_EMU)
+    return *p;
+#else
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#endif
+}
+#endif
+
 // One data stream (= one entry) as the kernels see it.  Host fills it (abi.cu); layout is shared.
 struct Segment {        // one FDAT/SDAT body inside the uploaded image
     uint64_t img_off;   // byte offset in the device image

@@ -58,7 +58,7 @@ inline void crc_make_consts(CrcConsts* C) {
         t0[i] = c;
     }
     // U_k for k = 0..511, keep the 20 we need
-    static uint32_t cur[256];
+    uint32_t cur[256];   // (not static: contexts are created concurrently by the host layer's worker threads)
     for (int i = 0; i < 256; i++) cur[i] = t0[i];
     for (int k = 0; k < 512; k++) {
         int slot = k < 16 ? k : (k >= 508 ? 16 + (k - 508) : -1);

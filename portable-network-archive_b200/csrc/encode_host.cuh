@@ -229,8 +229,9 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
     CK(cudaMemcpyAsync(E->d_entries_init.p, E->h_entries.data(), n * sizeof(EncEntry), cudaMemcpyHostToDevice, ctx->stream));
     if (nsegs_total) CK(cudaMemcpyAsync(E->d_segs.p, E->h_segs.data(), nsegs_total * sizeof(enc::SegRec), cudaMemcpyHostToDevice, ctx->stream));
     if (!E->h_keys.empty()) CK(cudaMemcpyAsync(E->d_keys.p, E->h_keys.data(), E->h_keys.size() * sizeof(DevKeys), cudaMemcpyHostToDevice, ctx->stream));
-    static enc::EncTables h_tables; static bool h_tables_init = false;
-    if (!h_tables_init) { enc::make_enc_tables(&h_tables); h_tables_init = true; }
+    static enc::EncTables h_tables;
+    static std::once_flag h_tables_once;   // plans are built concurrently by the host layer's worker threads
+    std::call_once(h_tables_once, []() { enc::make_enc_tables(&h_tables); });
     CK(cudaMemcpyAsync(E->d_tables.p, &h_tables, sizeof h_tables, cudaMemcpyHostToDevice, ctx->stream));
     for (int v = 0; v < 3; v++) {
         if (E->h_tiles[v].empty()) continue;
@@ -262,7 +263,7 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
         for (int k = 0; k < 4; k++) { c ^= ty[k]; for (int b = 0; b < 8; b++) c = (c >> 1) ^ (CRC_POLY & (0u - (c & 1u))); }
         E->fdat_init = c;
     }
-    CK(cudaStreamSynchronize(ctx->stream));   // the borrowed plaintext may go away after this call
+    CK(ctx->sync());   // the borrowed plaintext may go away after this call
     for (uint32_t i = 0; i < n; i++) P->plain_bytes += descs[i].plain.len;
     return PNA_OK;
 }
@@ -366,6 +367,7 @@ extern "C" const char* pna_cuda_encode_stage_name(uint32_t i) {
 extern "C" int pna_cuda_encode_plan_create(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_plan** plan) {
     if (!ctx || !plan || (!descs && n)) return PNA_E_BAD_ARG;
     *plan = nullptr;
+    if (!ctx->devs.empty()) return multi::encode_plan_create(ctx, descs, n, plan);
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     pna_plan* P = new pna_plan();
@@ -376,6 +378,7 @@ extern "C" int pna_cuda_encode_plan_create(pna_ctx* ctx, const pna_encode_desc* 
 }
 extern "C" int pna_cuda_encode_plan_run(pna_plan* P) {
     if (!P || P->kind != 1) return PNA_E_BAD_ARG;
+    if (P->multi) return multi::encode_plan_run(P);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -384,6 +387,7 @@ extern "C" int pna_cuda_encode_plan_run(pna_plan* P) {
 }
 extern "C" int pna_cuda_encode_plan_lengths(pna_plan* P, uint64_t* out_len, int32_t* status) {
     if (!P || P->kind != 1 || ((!out_len || !status) && P->n)) return PNA_E_BAD_ARG;
+    if (P->multi) return multi::encode_plan_lengths(P, out_len, status);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -391,12 +395,13 @@ extern "C" int pna_cuda_encode_plan_lengths(pna_plan* P, uint64_t* out_len, int3
     if (!P->prepared) return PNA_E_BAD_ARG;
     std::vector<EncEntry> dev(P->n);
     CK(cudaMemcpyAsync(dev.data(), P->enc->d_entries.p, P->n * sizeof(EncEntry), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     for (uint32_t i = 0; i < P->n; i++) { status[i] = dev[i].status; out_len[i] = dev[i].status == ST_OK ? dev[i].out_len : 0; }
     return PNA_OK;
 }
 extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status) {
     if (!P || P->kind != 1 || ((!out || !status) && P->n)) return PNA_E_BAD_ARG;
+    if (P->multi) return multi::encode_plan_fetch(P, out, fdat_crc_out, crc_count_out, status);
     pna_ctx* ctx = P->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     CK(cudaSetDevice(ctx->device));
@@ -408,7 +413,7 @@ extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* f
     CK(cudaMemcpyAsync(dev.data(), E->d_entries.p, P->n * sizeof(EncEntry), cudaMemcpyDeviceToHost, ctx->stream));
     if (fdat_crc_out && !crcs.empty())
         CK(cudaMemcpyAsync(crcs.data(), E->d_crc_val.p, crcs.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     uint64_t stream_bytes = 0, crc_pos = 0;
     for (uint32_t i = 0; i < P->n; i++) {
         const EncEntry& e = dev[i];
@@ -430,7 +435,7 @@ extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* f
         crc_pos += nbody;
     }
     P->stream_bytes = stream_bytes;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->sync());
     return PNA_OK;
 }
 extern "C" int pna_cuda_encode_batch(pna_ctx* ctx, const pna_encode_desc* descs, uint32_t n, pna_buf* out, uint32_t* fdat_crc_out,

@@ -5,6 +5,7 @@
 
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/random.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -79,7 +80,7 @@ struct CtxLease {
             auto& v = g_pool[dev];
             if (!v.empty()) { ctx = v.back(); v.pop_back(); }
         }
-        if (!ctx && pna_cuda_init(&ctx, dev) != PNA_OK) throw Error(PNA_E_CUDA, "pna_cuda_init failed: no usable sm_100 device (there is no CPU fallback)");
+        if (!ctx && pna_cuda_init(&ctx, &dev, 1) != PNA_OK) throw Error(PNA_E_CUDA, "pna_cuda_init failed: no usable sm_100 device (there is no CPU fallback)");
     }
     ~CtxLease() { if (ctx) { std::lock_guard<std::mutex> g(g_pool_mu); g_pool[device].push_back(ctx); } }
 };
@@ -456,8 +457,11 @@ void Archive::prepare(const ReadOptions& opt, int device) {
     for (size_t i = 0; i < refs_.size(); i++) {
         const EntryInfo& e = refs_[i].owner ? inner_[refs_[i].owner - 1].entries[refs_[i].entry] : entries_[refs_[i].entry];
         files_[i].name = e.name;
-        files_[i].size = e.raw_file_size;
-        if (e.raw_file_size == UINT64_MAX) unknown.push_back((uint32_t)i);
+        // fSIZ is untrusted input and only a hint (the reference never sizes anything from it): values the library would
+        // ignore are treated as absent, so the sizing pass below learns the real length
+        const bool trusted = pna_cuda_size_hint_trusted(e.compression, e.compressed_size, e.raw_file_size) != 0;
+        files_[i].size = trusted ? e.raw_file_size : UINT64_MAX;
+        if (!trusted) unknown.push_back((uint32_t)i);
     }
     if (!unknown.empty()) {
         std::vector<pna_decode_desc> descs(unknown.size());
@@ -482,15 +486,29 @@ void Archive::prepare(const ReadOptions& opt, int device) {
 
 void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
                             uint64_t group_bytes, bool verify) {
-    if (!prepared_) prepare(opt, device);
+    extract_files(opt, out, offsets, status, std::vector<int>{device}, workers, group_bytes, verify);
+}
+void Archive::extract_files(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, const std::vector<int>& devices,
+                            int workers, uint64_t group_bytes, bool verify) {
+    if (devices.empty()) throw Error(PNA_E_BAD_ARG, "no device given");
+    if (!prepared_) prepare(opt, devices[0]);
     crc_next_chunk_ = 0;
-    extract_range(opt, out, offsets, status, device, workers, group_bytes, verify, 0, refs_.size());
+    extract_range(opt, out, offsets, status, devices, workers, group_bytes, verify, 0, refs_.size());
+}
+void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
+                            uint64_t group_bytes, bool verify, size_t first, size_t last) {
+    extract_range(opt, out, offsets, status, std::vector<int>{device}, workers, group_bytes, verify, first, last);
 }
 
 // Files [first, last) of files(): file i lands at out + (offsets[i] - offsets[first]).  Windows must be taken in order
 // when verify is set: every call checks the chunks between the previous window's last entry and its own.
-void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers,
-                            uint64_t group_bytes, bool verify, size_t first, size_t last) {
+// Several devices: the entry groups are handed out dynamically (one shared counter) to `workers` threads PER DEVICE, each with its
+// own pair of contexts on that device -- the partition by entry of SURVEY 8e with the load balance of a work queue; uploads take
+// turns per device (every GPU has its own PCIe link).
+void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t* offsets, int32_t* status, const std::vector<int>& devices,
+                            int workers, uint64_t group_bytes, bool verify, size_t first, size_t last) {
+    if (devices.empty()) throw Error(PNA_E_BAD_ARG, "no device given");
+    const int device = devices[0];
     if (!prepared_) prepare(opt, device);
     const size_t n = last;
     const uint64_t o0 = first < refs_.size() ? offsets[first] : 0;
@@ -538,7 +556,8 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
     const auto t_begin = std::chrono::steady_clock::now();
     const bool trace = getenv("PNA_HOST_TRACE") != nullptr;
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - t_begin).count(); };
-    std::mutex err_mu, h2d_mu;
+    std::mutex err_mu;
+    std::vector<std::mutex> h2d_mus(devices.size());
     std::string err_msg;
     int err_kind = 0;
     // One group in flight per context; every worker thread keeps TWO contexts and software-pipelines its groups:
@@ -585,7 +604,7 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
         ck(L.ctx, pna_cuda_decode_plan_fetch_ranges(in.plan.get(), 0, src.data(), len.data(), dst.data(), (uint32_t)src.size()), "solid ranges");
         return true;
     };
-    auto issue = [&](CtxLease& L, Stage& S, size_t g) {
+    auto issue = [&](CtxLease& L, Stage& S, size_t g, std::mutex& h2d_mu) {
         const Group G = groups[g];
         const uint32_t m = (uint32_t)(G.hi - G.lo);
         S.g = g; S.m = m; S.plan = nullptr;
@@ -611,8 +630,13 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
                     const EntryInfo& e = entries_[refs_[G.lo + k].entry];
                     for (uint32_t c = e.chunk_begin; c < e.chunk_end; c++) S.owner[c - c0] = (int32_t)k;
                 }
-                ck(L.ctx, pna_cuda_decode_plan_create_crc(L.ctx, S.descs.data(), m, S.spans.data(), S.expect.data(), S.owner.data(), nc, &S.plan), "plan_create_crc");
-            } else ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, S.descs.data(), m, &S.plan), "plan_create");
+                // spans and bodies all lie inside the archive buffer: declared, so neighbouring ones travel in one copy
+                ck(L.ctx, pna_cuda_decode_plan_create_in_image(L.ctx, S.descs.data(), m, buf_, len_, S.spans.data(), S.expect.data(), S.owner.data(), nc, &S.plan), "plan_create_in_image");
+            } else if (S.top) ck(L.ctx, pna_cuda_decode_plan_create_in_image(L.ctx, S.descs.data(), m, buf_, len_, nullptr, nullptr, nullptr, 0, &S.plan), "plan_create_in_image");
+            else {
+                const Inner& in = inner_[refs_[G.lo].owner - 1];
+                ck(L.ctx, pna_cuda_decode_plan_create_in_image(L.ctx, S.descs.data(), m, in.data(), in.len, nullptr, nullptr, nullptr, 0, &S.plan), "plan_create_in_image");
+            }
         }
         const auto t1 = std::chrono::steady_clock::now();
         const int rc = pna_cuda_decode_plan_run(S.plan);
@@ -642,20 +666,23 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
         for (uint32_t k = 0; k < S.m; k++) {
             status[G.lo + k] = S.pre[k] != PNA_OK ? S.pre[k] : S.st[k];
             if (S.st[k] == PNA_E_INVALID_DATA) any_entry_broken = true;
+            // the decoded length is what the stream says, not what fSIZ said: callers slice / write files()[i].size bytes.
+            // PNA_E_NOSPACE: size becomes the required length, so the caller can take the entry again with room for it.
+            if (S.pre[k] == PNA_OK && (S.st[k] == PNA_OK || S.st[k] == PNA_E_NOSPACE)) files_[G.lo + k].size = S.bufs[k].len;
         }
         if (broken && !any_entry_broken) throw Error(PNA_E_INVALID_DATA, "broken chunk");   // an archive-level / non-file chunk
     };
-    auto work = [&]() {
+    auto work = [&](size_t di) {
         Stage stage[2];
         try {
-            CtxLease L0(device), L1(device);
+            CtxLease L0(devices[di]), L1(devices[di]);
             CtxLease* L[2] = {&L0, &L1};
             int cur = 0;
             bool have_prev = false;
             for (;;) {
                 const size_t g = next.fetch_add(1);
                 if (g >= groups.size()) break;
-                issue(*L[cur], stage[cur], g);
+                issue(*L[cur], stage[cur], g, h2d_mus[di]);
                 if (have_prev) collect(*L[cur ^ 1], stage[cur ^ 1]);
                 have_prev = true;
                 cur ^= 1;
@@ -667,10 +694,10 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
             if (err_msg.empty()) { err_msg = e.what(); err_kind = e.kind; }
         }
     };
-    const int nw = std::max(1, std::min<int>(workers, (int)std::max<size_t>(groups.size(), 1)));
+    const int nw = std::max(1, std::min<int>(workers * (int)devices.size(), (int)std::max<size_t>(groups.size(), 1)));
     std::vector<std::thread> th;
-    for (int w = 1; w < nw; w++) th.emplace_back(work);
-    work();
+    for (int w = 1; w < nw; w++) th.emplace_back(work, (size_t)w % devices.size());
+    work(0);
     for (auto& t : th) t.join();
     if (!err_msg.empty()) throw Error(err_kind, err_msg);
 }
@@ -703,9 +730,20 @@ static uint64_t stream_bound_of(uint64_t plain_len, const WriteOptions& opt) {
 // on_region (optional): called by the worker that completed a group with the byte range of the archive that is final now
 // (groups are contiguous and cover everything between the archive header and AEND) -- lets a caller write the file while later
 // groups are still being encoded.
-static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
-                                       int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap,
+// fresh random bytes for IVs / salts (lib/src/random.rs:8 uses the OS CSPRNG)
+static void os_random(uint8_t* p, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+        const ssize_t k = getrandom(p + got, n - got, 0);
+        if (k <= 0) throw Error(PNA_E_INTERNAL, "getrandom failed");
+        got += (size_t)k;
+    }
+}
+static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
+                                       const std::vector<int>& devices, int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap,
                                        const std::function<void(uint64_t, uint64_t)>* on_region) {
+    if (devices.empty()) throw Error(PNA_E_BAD_ARG, "no device given");
+    const int device = devices[0];
     const size_t n = files.size();
     struct Group { size_t lo, hi; };
     std::vector<Group> groups;
@@ -721,6 +759,18 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
     const bool enc = opt.encryption != PNA_ENCRYPTION_NO;
     const bool gcm = enc && opt.cipher_mode == PNA_CIPHER_GCM;
     const uint64_t mcs = max_chunk_size ? max_chunk_size : 0xFFFFFFFFull, iv_len = enc ? (gcm ? 75 : 16) : 0;   // stream prefix = its own chunk
+    // CBC / CTR: one fresh IV per entry (entry/write.rs:108-111 draws it inside the writer).  A builder without an IV of its own
+    // gets one from the OS here -- never a shared default: under CTR that would reuse the keystream across the archive.
+    std::vector<std::array<uint8_t, 16>> ivs(enc && !gcm ? n : 0);
+    if (enc && !gcm) {
+        std::vector<size_t> need;
+        for (size_t i = 0; i < n; i++) { if (files[i].iv_set) memcpy(ivs[i].data(), files[i].iv, 16); else need.push_back(i); }
+        if (!need.empty()) {
+            std::vector<uint8_t> rnd(16 * need.size());
+            os_random(rnd.data(), rnd.size());
+            for (size_t q = 0; q < need.size(); q++) memcpy(ivs[need[q]].data(), rnd.data() + 16 * q, 16);
+        }
+    }
     // GCM (entry/write.rs:75-106): per entry a stream header (salt, nonce prefix, segment size, key confirmation) and a stream key
     // bound to the entry's FHED chunk -- host work, once per entry, through the library's key schedule
     std::vector<std::array<uint8_t, 75>> gcm_hdr(gcm ? n : 0);
@@ -756,14 +806,7 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
             if (gcm) {
                 uint8_t salt[32], prefix[7];
                 memcpy(salt, f.gcm_salt, 32); memcpy(prefix, f.gcm_nonce_prefix, 7);
-                bool drawn = false;
-                for (uint8_t b : salt) drawn = drawn || b;
-                if (!drawn) {
-                    static thread_local std::random_device rd;
-                    for (int k = 0; k < 32; k += 4) { const uint32_t r = rd(); memcpy(salt + k, &r, 4); }
-                    const uint32_t r0 = rd(), r1 = rd();
-                    memcpy(prefix, &r0, 4); memcpy(prefix + 4, &r1, 3);
-                }
+                if (!f.gcm_params_set) { os_random(salt, 32); os_random(prefix, 7); }
                 int32_t rc = pna_cuda_gcm_stream_header(opt.key, salt, prefix, opt.segment_size, gcm_hdr[i].data());
                 if (rc == PNA_OK) {
                     std::vector<uint8_t> hd(h6, h6 + 6);
@@ -774,7 +817,7 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
                 if (rc != PNA_OK) throw Error(rc, f.name + ": GCM stream parameters");
                 add_meta("FDAT", gcm_hdr[i].data(), 75);                // the stream header is its own chunk, like the IV
             } else
-            add_meta("FDAT", f.iv, 16);                                 // the IV is its own chunk (builder.rs:62-69)
+            add_meta("FDAT", ivs[i].data(), 16);                        // the IV is its own chunk (builder.rs:62-69)
         }
         add_meta("FEND", nullptr, 0);
     }
@@ -793,7 +836,8 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
     std::vector<uint8_t> ready(groups.size() + 1, 0);
     base[0] = 8 + 20; ready[0] = 1;
     std::mutex mu;
-    Slots h2d_slots(2);
+    std::vector<std::unique_ptr<Slots>> h2d_slots;   // uploads take turns per device (each GPU has its own PCIe link)
+    for (size_t d = 0; d < devices.size(); d++) h2d_slots.emplace_back(new Slots(2));
     std::condition_variable cv;
     std::atomic<size_t> next{0};
     std::string err_msg;
@@ -815,7 +859,7 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
         std::vector<pna_encode_desc> descs;
         double t_issue0 = 0, t_issue1 = 0;
     };
-    auto issue = [&](CtxLease& L, Stage& S, size_t g) {
+    auto issue = [&](CtxLease& L, Stage& S, size_t g, Slots& h2d_slot) {
         const Group G = groups[g];
         const uint32_t m = (uint32_t)(G.hi - G.lo);
         S.g = g; S.m = m; S.plan = nullptr; S.crc_total = 0;
@@ -826,13 +870,14 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
             memset(&d, 0, sizeof d);
             d.plain = f.data;
             d.compression = opt.compression; d.encryption = opt.encryption; d.cipher_mode = opt.cipher_mode; d.level = opt.level;
-            memcpy(d.key, opt.key, 32); memcpy(d.iv, f.iv, 16);
+            memcpy(d.key, opt.key, 32);
+            if (!ivs.empty()) memcpy(d.iv, ivs[G.lo + k].data(), 16);
             if (gcm) { memcpy(d.key, gcm_key[G.lo + k].data(), 32); d.stream_header = gcm_hdr[G.lo + k].data(); }
             d.max_chunk_size = max_chunk_size;
             S.crc_total += pna_cuda_encode_crc_count(&d);
         }
         {
-            SlotGuard h2d(h2d_slots);   // uploads take turns: PCIe is the shared resource
+            SlotGuard h2d(h2d_slot);   // uploads take turns: PCIe is the shared resource
             S.t_issue0 = ms_now();
             ck(L.ctx, pna_cuda_encode_plan_create(L.ctx, S.descs.data(), m, &S.plan), "encode_plan_create");
         }
@@ -924,17 +969,17 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
         if (trace) fprintf(stderr, "[pna_host] create group %zu (%u files): plan_create/H2D %.1f-%.1f, lengths(wait) %.1f-%.1f, fetch/D2H %.1f-%.1f, frames -%.1f ms\n",
                            g, m, S.t_issue0, S.t_issue1, tr2, tr3, tr4, tr5, ms_now());
     };
-    auto work = [&]() {
+    auto work = [&](size_t di) {
         Stage stage[2];
         try {
-            CtxLease L0(device), L1(device);
+            CtxLease L0(devices[di]), L1(devices[di]);
             CtxLease* L[2] = {&L0, &L1};
             int cur = 0;
             bool have_prev = false;
             for (;;) {
                 const size_t g = next.fetch_add(1);
                 if (g >= groups.size()) break;
-                issue(*L[cur], stage[cur], g);
+                issue(*L[cur], stage[cur], g, *h2d_slots[di]);
                 if (have_prev) finish(*L[cur ^ 1], stage[cur ^ 1]);
                 have_prev = true;
                 cur ^= 1;
@@ -948,10 +993,10 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
             cv.notify_all();
         }
     };
-    const int nw = std::max(1, std::min<int>(workers, (int)std::max<size_t>(groups.size(), 1)));
+    const int nw = std::max(1, std::min<int>(workers * (int)devices.size(), (int)std::max<size_t>(groups.size(), 1)));
     std::vector<std::thread> th;
-    for (int w = 1; w < nw; w++) th.emplace_back(work);
-    work();
+    for (int w = 1; w < nw; w++) th.emplace_back(work, (size_t)w % devices.size());
+    work(0);
     for (auto& t : th) t.join();
     if (!err_msg.empty()) throw Error(err_kind, err_msg);
     // archive framing: AHED right behind the signature, AEND behind the last group (archive/write.rs:92,545)
@@ -967,7 +1012,11 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
 
 uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size, int device,
                              int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap) {
-    return create_archive_regions(files, opt, max_chunk_size, device, workers, group_bytes, out, cap, nullptr);
+    return create_archive_regions(files, opt, max_chunk_size, std::vector<int>{device}, workers, group_bytes, out, cap, nullptr);
+}
+uint64_t create_archive_into(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
+                             const std::vector<int>& devices, int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap) {
+    return create_archive_regions(files, opt, max_chunk_size, devices, workers, group_bytes, out, cap, nullptr);
 }
 
 std::vector<uint8_t> create_archive(const std::vector<FileEntryBuilder>& files, const WriteOptions& opt, uint32_t max_chunk_size,
@@ -1221,7 +1270,11 @@ IoStats extract_to_dir(Archive& a, const ReadOptions& opt, const std::string& ou
     const std::vector<FileOut>& files = a.files();
     const size_t n = files.size();
     std::vector<uint64_t> offsets(n + 1, 0);
-    for (size_t i = 0; i < n; i++) offsets[i + 1] = offsets[i] + ((files[i].status ? 0 : files[i].size) + 15) / 16 * 16;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t sz = files[i].status ? 0 : files[i].size;
+        if (sz > ((uint64_t)1 << 60) || offsets[i] > ((uint64_t)1 << 60)) throw Error(PNA_E_OOM, "decoded sizes overflow the buffer layout");   // checked sum
+        offsets[i + 1] = offsets[i] + (sz + 15) / 16 * 16;
+    }
     std::vector<int32_t> stv(n, 0);
     // windows of whole files
     std::vector<std::pair<size_t, size_t>> windows;
@@ -1265,6 +1318,22 @@ IoStats extract_to_dir(Archive& a, const ReadOptions& opt, const std::string& ou
         });
     }
     for (auto& f : writing) if (f.valid()) f.get();
+    // files whose stream decodes to MORE than their fSIZ said (the reference extracts them all the same: it never looks at fSIZ):
+    // extract_range left the required length in files()[i].size -- take them again, one by one, with room for it
+    for (size_t i = 0; i < n; i++) {
+        if (stv[i] != PNA_E_NOSPACE || files[i].status) continue;
+        std::vector<uint64_t> off2(n + 1, 0);
+        off2[i + 1] = (files[i].size + 15) / 16 * 16;
+        PinnedBuf one(L.ctx, off2[i + 1] + 64);
+        if (!one.p) throw Error(PNA_E_OOM, "pinned retry buffer");
+        a.extract_range(opt, one.p, off2.data(), stv.data(), device, 1, group_bytes, false, i, i + 1);
+        if (stv[i] != PNA_OK) continue;
+        const std::string rel = sanitize_entry_name(files[i].name);
+        if (rel.empty()) continue;
+        const std::string path = out_dir + "/" + rel;
+        dirs.ensure_parent(path);
+        write_whole(path, one.p, files[i].size);
+    }
     for (size_t i = 0; i < n; i++) {
         const int32_t s = files[i].status ? files[i].status : stv[i];
         if (status) status[i] = s;
@@ -1314,7 +1383,6 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
     for (size_t i = 0; i < n; i++) {
         files[i].name = name_and_path[i].first;
         files[i].data = pna_span{plain + offs[i], sizes[i]};
-        for (int k = 0; k < 16; k += 4) { const uint32_t r = rd(); memcpy(files[i].iv + k, &r, 4); }   // entry/write.rs:108-111: random IV per entry
         pna_encode_desc d;
         memset(&d, 0, sizeof d);
         d.plain.len = sizes[i]; d.compression = opt.compression; d.encryption = opt.encryption;
@@ -1339,7 +1407,7 @@ IoStats create_from_files(const std::vector<std::pair<std::string, std::string>>
     const std::function<void(uint64_t, uint64_t)> on_region = write_range;
     uint64_t alen = 0;
     try {
-        alen = create_archive_regions(files, opt, max_chunk_size, device, workers, group_bytes, arch, bound, &on_region);
+        alen = create_archive_regions(files, opt, max_chunk_size, std::vector<int>{device}, workers, group_bytes, arch, bound, &on_region);
         write_range(0, 8 + 20);
         write_range(alen - 12, 12);
     } catch (...) { close(fd); throw; }
@@ -1639,6 +1707,42 @@ int pnah_create_solid(uint32_t n, const char* const* names, const uint8_t* const
         return PNA_OK;
     } catch (const pna::Error& e) { return fail(e, err, errcap); }
 }
+int pnah_extract_range(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, int device, int workers, uint64_t group_bytes,
+                       int verify, uint64_t first, uint64_t last, char* err, uint64_t errcap) {
+    try {
+        if (first > last || last > a->a.files().size()) throw pna::Error(PNA_E_BAD_ARG, "file range out of bounds");
+        a->a.extract_range(a->opt, out, offsets, status, device, workers, group_bytes, verify != 0, (size_t)first, (size_t)last);
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
+int pnah_extract_files_on(pnah_archive* a, uint8_t* out, const uint64_t* offsets, int32_t* status, const int* devices, uint32_t n_devices,
+                          int workers_per_device, uint64_t group_bytes, int verify, char* err, uint64_t errcap) {
+    try {
+        if (!devices || !n_devices) throw pna::Error(PNA_E_BAD_ARG, "no device given");
+        a->a.extract_files(a->opt, out, offsets, status, std::vector<int>(devices, devices + n_devices), workers_per_device, group_bytes, verify != 0);
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
+int pnah_create_on(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs,
+                   uint8_t compression, int32_t level, uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf,
+                   uint32_t max_chunk_size, const int* devices, uint32_t n_devices, int workers_per_device, uint64_t group_bytes, uint8_t* out,
+                   uint64_t cap, uint64_t* out_len, char* err, uint64_t errcap) {
+    try {
+        if (!devices || !n_devices) throw pna::Error(PNA_E_BAD_ARG, "no device given");
+        std::vector<pna::FileEntryBuilder> files(n);
+        for (uint32_t i = 0; i < n; i++) {
+            files[i].name = names[i];
+            files[i].data = pna_span{data[i], lens[i]};
+            if (ivs) files[i].set_iv(ivs + 16 * (size_t)i);
+        }
+        pna::WriteOptions opt;
+        opt.compression = compression; opt.level = level; opt.encryption = encryption; opt.cipher_mode = cipher_mode;
+        if (key) memcpy(opt.key, key, 32);
+        if (phsf) opt.phsf = phsf;
+        *out_len = pna::create_archive_into(files, opt, max_chunk_size, std::vector<int>(devices, devices + n_devices), workers_per_device, group_bytes, out, cap);
+        return PNA_OK;
+    } catch (const pna::Error& e) { return fail(e, err, errcap); }
+}
 int pnah_create(uint32_t n, const char* const* names, const uint8_t* const* data, const uint64_t* lens, const uint8_t* ivs,
                 uint8_t compression, int32_t level, uint8_t encryption, uint8_t cipher_mode, const uint8_t key[32], const char* phsf,
                 uint32_t max_chunk_size, int device, int workers, uint64_t group_bytes, uint8_t* out, uint64_t cap, uint64_t* out_len,
@@ -1648,7 +1752,7 @@ int pnah_create(uint32_t n, const char* const* names, const uint8_t* const* data
         for (uint32_t i = 0; i < n; i++) {
             files[i].name = names[i];
             files[i].data = pna_span{data[i], lens[i]};
-            if (ivs) memcpy(files[i].iv, ivs + 16 * (size_t)i, 16);
+            if (ivs) files[i].set_iv(ivs + 16 * (size_t)i);   // NULL: the writer draws a fresh IV per entry
         }
         pna::WriteOptions opt;
         opt.compression = compression; opt.level = level; opt.encryption = encryption; opt.cipher_mode = cipher_mode;

@@ -173,10 +173,9 @@ struct RingBitSrc {
     __device__ __forceinline__ void fetch(int32_t g) {
         const uint32_t* src = gbase + 4 * (int64_t)g;
         if (src >= words) {
-            const uint32_t d = (uint32_t)__cvta_generic_to_shared(ring + ((uint32_t)g & 3u) * 4u);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
-            asm volatile("cp.async.commit_group;");
-        } else asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing newer will follow: drain
+            cp_async16(ring + ((uint32_t)g & 3u) * 4u, src);
+            cp_async_commit();
+        } else cp_async_wait_all();   // nothing newer will follow: drain
     }
     __device__ __forceinline__ void init(const uint32_t* w, uint64_t begin, int32_t pos) {
         words = w;
@@ -187,14 +186,14 @@ struct RingBitSrc {
         const int32_t a = (((int32_t)b0 + pos - 1) >> 5) + (int32_t)mis;
         gl = (a >> 2) - 3;
         for (int32_t g = gl + 3; g >= gl; g--) fetch(g);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        cp_async_wait_all();
     }
     __device__ __forceinline__ uint64_t window(int32_t pos) {
         const int32_t top = (int32_t)b0 + pos - 1;
         const int32_t a = (top >> 5) + (int32_t)mis;      // ring word index of the window's top word (>= -2 + mis)
         const uint32_t sh = 31u - ((uint32_t)top & 31u);
         if ((a >> 2) <= gl + 2) { gl--; fetch(gl); }
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        cp_async_wait_1();
         const uint32_t h = ring[(uint32_t)a & 15u], m = ring[(uint32_t)(a - 1) & 15u], l = ring[(uint32_t)(a - 2) & 15u];
         return ((uint64_t)__funnelshift_l(m, h, sh) << 32) | __funnelshift_l(l, m, sh);
     }

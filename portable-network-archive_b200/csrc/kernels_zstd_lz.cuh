@@ -57,19 +57,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     }
     return v;
 }
-__device__ __forceinline__ uint32_t ldcg32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
 constexpr uint32_t LZ_SEQ_MAX = 255;   // ll and ml bound of the parallel path
 constexpr uint32_t LZ_FAR_MAX = 32;    // far matches up to this length are prefetched (9 words)
 

@@ -10,8 +10,31 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 
+def pytest_addoption(parser):
+    # development aid for a box without a GPU: run the kernels' logic under the fiber-based SIMT emulator of
+    # tests/emu (test infrastructure; the package never loads it).  Parity evidence comes from `-m gpu` on a B200 only.
+    parser.addoption("--emu", action="store_true", default=False, help="run -m gpu tests against tests/emu/_gen (SIMT emulator, debugging only)")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow_emu: too large for the SIMT emulator (skipped under --emu)")
+    if config.getoption("--emu"):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+        gen = build_emu.build()
+        ffi = importlib.import_module("portable-network-archive_b200._ffi")
+        host = importlib.import_module("portable-network-archive_b200._host")
+        ffi.LIB_PATH = os.path.join(gen, "libpna_cuda.so")
+        host.LIB_PATH = os.path.join(gen, "libpna_host.so")
+
+
+def pytest_collection_modifyitems(config, items):
+    if config.getoption("--emu"):
+        skip = pytest.mark.skip(reason="too large for the SIMT emulator")
+        for it in items:
+            if "slow_emu" in it.keywords:
+                it.add_marker(skip)
 
 
 @pytest.fixture(scope="session")
