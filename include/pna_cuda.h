@@ -110,6 +110,11 @@ void* pna_cuda_stream(pna_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py "gpu_launches") */
 uint64_t pna_cuda_launch_count(pna_ctx* ctx);
 
+/* Transfer yardstick for end-to-end measurements: pinned -> HBM copy of h2d_bytes and HBM -> pinned copy of d2h_bytes, each
+ * alone and both at once on two streams, timed with CUDA events (milliseconds).  The buffers are the caller's (pinned). */
+int pna_cuda_transfer_probe(pna_ctx* ctx, const uint8_t* h2d_src, uint64_t h2d_bytes, uint8_t* d2h_dst, uint64_t d2h_bytes,
+                            float* h2d_ms, float* d2h_ms, float* both_ms);
+
 /* ---- seam 1: chunk CRC ---- */
 /* crc_out[i] = CRC-32/ISO-HDLC over spans[i] (the caller passes type||data, lib/src/format/chunk.rs:7-12). */
 int pna_cuda_crc32(pna_ctx* ctx, const pna_span* type_and_data, uint32_t n, uint32_t* crc_out);

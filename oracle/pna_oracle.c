@@ -643,6 +643,89 @@ int pna_oracle_encode_stream(const uint8_t* plain, size_t n, int compression, in
     return rc;
 }
 
+/* ------------------------------------------------------------------ folding CRC-32 (PCLMULQDQ) */
+/* The reference's chunk CRC is crc32fast 1.5.0 (lib/src/format/chunk.rs:8-11), whose x86-64 fast path
+ * (crc32fast src/specialized/pclmulqdq.rs) is the carry-less-multiply folding of Gopal, Ozturk, Guilford et al., "Fast CRC
+ * Computation for Generic Polynomials Using PCLMULQDQ Instruction" (Intel white paper, 2009): four 128-bit lanes folded
+ * across 64 bytes per step, then 128 -> 64 -> 32 bits by Barrett reduction.  zlib 1.3's crc32() is a table method several
+ * times slower, so timing the reference's serial CRC thread with it would flatter the GPU; this restatement of the published
+ * method (constants: x^k mod P for the reflected polynomial 0xEDB88320, as tabulated in the paper) is what the CPU baseline
+ * uses.  Pinned on the reference's CRC KATs and against zlib in tests/test_oracle.py. */
+#if defined(__x86_64__)
+#include <immintrin.h>
+#include <cpuid.h>
+__attribute__((target("pclmul,sse4.1")))
+static uint32_t crc32_fold_pclmul(const uint8_t* buf, size_t len, uint32_t state) {   /* len >= 64, len % 16 == 0; raw (pre-inverted) state */
+    const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596, 0x0154442bd4);   /* fold by 512 bits */
+    const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009e, 0x01751997d0);   /* fold by 128 bits */
+    const __m128i k5 = _mm_set_epi64x(0, 0x0163cd6124);
+    const __m128i poly = _mm_set_epi64x(0x01f7011641, 0x01db710641);   /* mu, P */
+    const __m128i mask32 = _mm_setr_epi32(~0, 0, ~0, 0);
+    __m128i x1 = _mm_loadu_si128((const __m128i*)(buf + 0)), x2 = _mm_loadu_si128((const __m128i*)(buf + 16));
+    __m128i x3 = _mm_loadu_si128((const __m128i*)(buf + 32)), x4 = _mm_loadu_si128((const __m128i*)(buf + 48));
+    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)state));
+    buf += 64; len -= 64;
+    while (len >= 64) {
+        __m128i a1 = _mm_clmulepi64_si128(x1, k1k2, 0x00), a2 = _mm_clmulepi64_si128(x2, k1k2, 0x00);
+        __m128i a3 = _mm_clmulepi64_si128(x3, k1k2, 0x00), a4 = _mm_clmulepi64_si128(x4, k1k2, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, k1k2, 0x11); x2 = _mm_clmulepi64_si128(x2, k1k2, 0x11);
+        x3 = _mm_clmulepi64_si128(x3, k1k2, 0x11); x4 = _mm_clmulepi64_si128(x4, k1k2, 0x11);
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, a1), _mm_loadu_si128((const __m128i*)(buf + 0)));
+        x2 = _mm_xor_si128(_mm_xor_si128(x2, a2), _mm_loadu_si128((const __m128i*)(buf + 16)));
+        x3 = _mm_xor_si128(_mm_xor_si128(x3, a3), _mm_loadu_si128((const __m128i*)(buf + 32)));
+        x4 = _mm_xor_si128(_mm_xor_si128(x4, a4), _mm_loadu_si128((const __m128i*)(buf + 48)));
+        buf += 64; len -= 64;
+    }
+    __m128i t;
+    t = _mm_clmulepi64_si128(x1, k3k4, 0x00); x1 = _mm_clmulepi64_si128(x1, k3k4, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), t);
+    t = _mm_clmulepi64_si128(x1, k3k4, 0x00); x1 = _mm_clmulepi64_si128(x1, k3k4, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), t);
+    t = _mm_clmulepi64_si128(x1, k3k4, 0x00); x1 = _mm_clmulepi64_si128(x1, k3k4, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), t);
+    while (len >= 16) {
+        t = _mm_clmulepi64_si128(x1, k3k4, 0x00); x1 = _mm_clmulepi64_si128(x1, k3k4, 0x11);
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, _mm_loadu_si128((const __m128i*)buf)), t);
+        buf += 16; len -= 16;
+    }
+    /* 128 -> 64 bits */
+    x2 = _mm_clmulepi64_si128(x1, k3k4, 0x10);
+    x1 = _mm_xor_si128(_mm_srli_si128(x1, 8), x2);
+    x2 = _mm_srli_si128(x1, 4);
+    x1 = _mm_clmulepi64_si128(_mm_and_si128(x1, mask32), k5, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    /* Barrett reduction to 32 bits */
+    x2 = _mm_clmulepi64_si128(_mm_and_si128(x1, mask32), poly, 0x10);
+    x2 = _mm_clmulepi64_si128(_mm_and_si128(x2, mask32), poly, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+static int have_pclmul(void) {
+    static int cached = -1;
+    if (cached < 0) { unsigned a, b, c, d; cached = __get_cpuid(1, &a, &b, &c, &d) && (c & (1u << 1)) && (c & (1u << 19)); }
+    return cached;
+}
+#else
+static int have_pclmul(void) { return 0; }
+#endif
+int pna_oracle_have_pclmul(void) { return have_pclmul(); }
+/* same contract as zlib's crc32(): running value in, running value out */
+uint32_t pna_oracle_crc32_fold(uint32_t crc, const uint8_t* buf, size_t len) {
+#if defined(__x86_64__)
+    if (have_pclmul() && len >= 64) {
+        const size_t bulk = len & ~(size_t)15;
+        crc = ~crc32_fold_pclmul(buf, bulk, ~crc);
+        buf += bulk; len -= bulk;
+    }
+#endif
+    while (len) { uInt k = len > (1u << 30) ? (1u << 30) : (uInt)len; crc = (uint32_t)crc32(crc, buf, k); buf += k; len -= k; }
+    return crc;
+}
+/* crc_impl: 1 = zlib table CRC, 2 = folding CRC (what crc32fast does on x86-64) */
+static uint32_t chunk_crc_impl(int crc_impl, const char ty[4], const uint8_t* s, size_t l) {
+    uint32_t z = (uint32_t)crc32(0L, (const Bytef*)ty, 4);
+    if (crc_impl == 2) return pna_oracle_crc32_fold(z, s, l);
+    while (l) { uInt k = l > (1u << 30) ? (1u << 30) : (uInt)l; z = (uint32_t)crc32(z, s, k); s += k; l -= k; }
+    return z;
+}
+
 /* ------------------------------------------------------------------ task-per-entry pool (CPU baseline) */
 /* Mirrors the CLI's extract dataflow: ONE thread walks the archive and CRC-checks every chunk
  * (archive/read/slice.rs:42-66 -> bytes.rs:39-75), worker threads decode one entry each
@@ -668,6 +751,7 @@ static void* ora_worker(void* arg) {
     }
     return NULL;
 }
+/* crc_on_caller_thread: 0 = no CRC, 1 = zlib's table CRC, 2 = the folding (PCLMULQDQ) CRC the reference really runs */
 int pna_oracle_decode_batch_mt(ora_job* jobs, uint32_t n, int nthreads, int crc_on_caller_thread,
                                uint32_t* crc_out) {
     ora_pool p = {jobs, n, 0, crc_on_caller_thread};
@@ -677,10 +761,8 @@ int pna_oracle_decode_batch_mt(ora_job* jobs, uint32_t n, int nthreads, int crc_
     for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, ora_worker, &p);
     if (crc_on_caller_thread) /* the serial iterating thread of the reference */
         for (uint32_t i = 0; i < n; i++) {
-            uLong z = crc32(0L, (const Bytef*)"FDAT", 4);
-            const uint8_t* s = jobs[i].stream; size_t l = jobs[i].len;
-            while (l) { uInt k = l > (1u << 30) ? (1u << 30) : (uInt)l; z = crc32(z, s, k); s += k; l -= k; }
-            if (crc_out) crc_out[i] = (uint32_t)z;
+            const uint32_t z = chunk_crc_impl(crc_on_caller_thread, "FDAT", jobs[i].stream, jobs[i].len);
+            if (crc_out) crc_out[i] = z;
         }
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     free(th);
@@ -710,6 +792,8 @@ static void* ora_enc_worker(void* arg) {
     }
     return NULL;
 }
+static int g_encode_crc_impl = 2;   /* the writer's chunk CRC (io.rs:187) is crc32fast too */
+void pna_oracle_set_encode_crc_impl(int impl) { g_encode_crc_impl = impl == 1 ? 1 : 2; }
 int pna_oracle_encode_batch_mt(ora_enc_job* jobs, uint32_t n, int nthreads, uint32_t* crc_out) {
     ora_enc_pool p = {jobs, n, 0};
     if (nthreads < 1) nthreads = 1;
@@ -719,11 +803,6 @@ int pna_oracle_encode_batch_mt(ora_enc_job* jobs, uint32_t n, int nthreads, uint
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     free(th);
     if (crc_out)
-        for (uint32_t i = 0; i < n; i++) {
-            uLong z = crc32(0L, (const Bytef*)"FDAT", 4);
-            const uint8_t* s = jobs[i].out; size_t l = jobs[i].out_len;
-            while (l) { uInt k = l > (1u << 30) ? (1u << 30) : (uInt)l; z = crc32(z, s, k); s += k; l -= k; }
-            crc_out[i] = (uint32_t)z;
-        }
+        for (uint32_t i = 0; i < n; i++) crc_out[i] = chunk_crc_impl(g_encode_crc_impl, "FDAT", jobs[i].out, jobs[i].out_len);
     return ORA_OK;
 }

@@ -191,11 +191,28 @@ class Context:
         return int(self.L.pna_cuda_launch_count(self.h))
 
     def pinned(self, nbytes: int) -> np.ndarray:
-        """Pinned host buffer as a numpy array (freed with the context's process)."""
+        """Pinned host buffer as a numpy array (lives until pinned_free or the end of the process)."""
         p = self.L.pna_cuda_host_alloc(self.h, nbytes)
         if not p:
             raise PnaCudaError(E_OOM, "pna_cuda_host_alloc")
+        if not hasattr(self, "_pinned"):
+            self._pinned = set()
+        self._pinned.add(int(p))
         return np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(p))[:nbytes]
+
+    def pinned_free(self, arr: np.ndarray):
+        """Give a buffer from pinned() back (the caller must drop every view of it)."""
+        p = int(arr.ctypes.data)
+        if p in getattr(self, "_pinned", ()):
+            self._pinned.discard(p)
+            self.L.pna_cuda_host_free(self.h, p)
+
+    def transfer_probe(self, h2d_src: np.ndarray, d2h_dst: np.ndarray):
+        """pinned -> HBM copy of h2d_src and HBM -> pinned copy into d2h_dst: milliseconds alone and both at once (CUDA events)."""
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        self._ck(self.L.pna_cuda_transfer_probe(self.h, h2d_src.ctypes.data, h2d_src.size, d2h_dst.ctypes.data, d2h_dst.size,
+                                                C.byref(a), C.byref(b), C.byref(c)), "transfer_probe")
+        return {"h2d_ms": a.value, "d2h_ms": b.value, "both_ms": c.value}
 
     # ---- seam 1
     def crc32(self, spans) -> np.ndarray:

@@ -15,7 +15,7 @@ UINT64_MAX = (1 << 64) - 1
 
 EXPORTS = [
     "pna_cuda_init", "pna_cuda_device_count", "pna_cuda_device_id", "pna_cuda_decode_size_bound", "pna_cuda_size_hint_trusted",
-    "pna_cuda_decode_plan_create_in_image", "pna_cuda_destroy", "pna_cuda_strerror", "pna_cuda_last_error", "pna_cuda_host_alloc",
+    "pna_cuda_decode_plan_create_in_image", "pna_cuda_transfer_probe", "pna_cuda_destroy", "pna_cuda_strerror", "pna_cuda_last_error", "pna_cuda_host_alloc",
     "pna_cuda_host_free", "pna_cuda_stream", "pna_cuda_launch_count", "pna_cuda_crc32", "pna_cuda_crc32_image",
     "pna_cuda_decode_batch", "pna_cuda_decode_plan_create", "pna_cuda_decode_plan_create_crc", "pna_cuda_plan_crc_results", "pna_cuda_decode_plan_run", "pna_cuda_decode_plan_fetch",
     "pna_cuda_decode_plan_lengths", "pna_cuda_decode_plan_crc32_out", "pna_cuda_decode_plan_fetch_ranges",
@@ -64,6 +64,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, u32, u64, i32p = C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_int32)
     L.pna_cuda_init.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.pna_cuda_transfer_probe.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.pna_cuda_device_count.argtypes = [vp]
     L.pna_cuda_device_id.argtypes = [vp, C.c_int]
     L.pna_cuda_decode_size_bound.argtypes = [C.c_uint8, u64]

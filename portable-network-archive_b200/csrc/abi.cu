@@ -460,6 +460,51 @@ extern "C" uint64_t pna_cuda_launch_count(pna_ctx* ctx) {
     return n;
 }
 
+// Transfer yardstick for end-to-end numbers: the same pinned <-> HBM copies a step makes, timed with CUDA events -- H2D
+// alone, D2H alone, and both directions at once on two streams (what the pipelined host layer does; PCIe is full duplex but
+// the directions are not independent).  Run by every rank at the same time it gives the box's concurrent transfer floor.
+extern "C" int pna_cuda_transfer_probe(pna_ctx* ctx, const uint8_t* h2d_src, uint64_t h2d_bytes, uint8_t* d2h_dst, uint64_t d2h_bytes,
+                                       float* h2d_ms, float* d2h_ms, float* both_ms) {
+    if (!ctx || (!h2d_src && h2d_bytes) || (!d2h_dst && d2h_bytes)) return PNA_E_BAD_ARG;
+    if (!ctx->devs.empty()) ctx = ctx->devs[0];
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    DevArr<uint8_t> d_in, d_out;
+    CK(d_in.reserve(h2d_bytes + 256)); CK(d_out.reserve(d2h_bytes + 256));
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t e[4] = {};
+    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    for (auto& x : e) CK(cudaEventCreate(&x));
+    int rc = PNA_OK;
+    auto ck2 = [&](cudaError_t err) { if (err != cudaSuccess && rc == PNA_OK) { ctx->fail("transfer probe", err); rc = PNA_E_CUDA; } };
+    float t = 0;
+    // warm-up (page tables of the pinned ranges, first-touch of the device arenas)
+    if (h2d_bytes) ck2(cudaMemcpyAsync(d_in.p, h2d_src, h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (d2h_bytes) ck2(cudaMemcpyAsync(d2h_dst, d_out.p, d2h_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ck2(ctx->sync());
+    ck2(cudaEventRecord(e[0], ctx->stream));
+    if (h2d_bytes) ck2(cudaMemcpyAsync(d_in.p, h2d_src, h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ck2(cudaEventRecord(e[1], ctx->stream));
+    if (d2h_bytes) ck2(cudaMemcpyAsync(d2h_dst, d_out.p, d2h_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ck2(cudaEventRecord(e[2], ctx->stream));
+    ck2(ctx->sync());
+    if (rc == PNA_OK) { cudaEventElapsedTime(&t, e[0], e[1]); if (h2d_ms) *h2d_ms = t; cudaEventElapsedTime(&t, e[1], e[2]); if (d2h_ms) *d2h_ms = t; }
+    // both directions at once: s2 starts behind the common start event
+    ck2(cudaEventRecord(e[0], ctx->stream));
+    ck2(cudaStreamWaitEvent(s2, e[0], 0));
+    if (h2d_bytes) ck2(cudaMemcpyAsync(d_in.p, h2d_src, h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (d2h_bytes) ck2(cudaMemcpyAsync(d2h_dst, d_out.p, d2h_bytes, cudaMemcpyDeviceToHost, s2));
+    ck2(cudaEventRecord(e[3], s2));
+    ck2(cudaStreamWaitEvent(ctx->stream, e[3], 0));
+    ck2(cudaEventRecord(e[1], ctx->stream));
+    ck2(ctx->sync());
+    if (rc == PNA_OK) { cudaEventElapsedTime(&t, e[0], e[1]); if (both_ms) *both_ms = t; }
+    for (auto& x : e) cudaEventDestroy(x);
+    cudaStreamDestroy(s2);
+    d_in.release(); d_out.release();
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // seam 1: CRC
 static int crc_run(pna_ctx* ctx, const uint8_t* d_img, const std::vector<uint64_t>& off, const uint64_t* len, uint32_t n,

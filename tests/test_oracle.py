@@ -89,3 +89,25 @@ def test_roundtrip_cross_product(oracle):
             for enc, mode in ((0, 0), (1, 0), (1, 1), (2, 0), (2, 1)):
                 s = oracle.encode_stream(plain, comp, -1, enc, mode, key, os.urandom(16))
                 assert oracle.decode_stream(s, comp, enc, mode, key) == plain
+
+
+def test_folding_crc_matches_zlib_and_reference_kats(oracle):
+    """The CPU baseline's CRC is the PCLMULQDQ folding method crc32fast uses (lib/src/format/chunk.rs:8-11): same values as
+    zlib's table CRC on every length / alignment class, and the reference's known answers (chunk.rs:31, traits.rs:24, io.rs:179)."""
+    import ctypes as C
+    import os
+    import zlib
+    L = oracle.lib()
+    L.pna_oracle_crc32_fold.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t]
+    L.pna_oracle_crc32_fold.restype = C.c_uint32
+    for n in [0, 1, 15, 16, 17, 63, 64, 65, 79, 80, 81, 127, 128, 129, 255, 1000, 4095, 4096, 65537, 1 << 20]:
+        for off in (0, 1, 3, 8, 15):
+            b = os.urandom(n + off)[off:]
+            for init in (0, 0xFFFFFFFF, 0x12345678):
+                assert L.pna_oracle_crc32_fold(init, b, len(b)) == zlib.crc32(b, init), (n, off, init)
+    fdat = zlib.crc32(b"FDAT")
+    assert L.pna_oracle_crc32_fold(fdat, bytes([0xAA, 0xBB, 0xCC, 0xDD]), 4) == 0x47F32B10 == 1207118608
+    assert L.pna_oracle_crc32_fold(fdat, bytes([1, 2, 3]), 3) == 2776590148
+    assert L.pna_oracle_crc32_fold(zlib.crc32(b"AEND"), b"", 0) == 0x6BF6486D
+    big = os.urandom(3 << 20) * 3
+    assert L.pna_oracle_crc32_fold(fdat, big, len(big)) == zlib.crc32(big, fdat)
