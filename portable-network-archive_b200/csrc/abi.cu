@@ -298,6 +298,14 @@ struct pna_plan {
     uint32_t n_lz_units = 0;
     uint64_t lz_avg_unit_comp = 0;   // compressed bytes per unit, for the choice of the LZ kernel variant
     DevArr<zs::ZBlock> d_blocks;
+    DevArr<zs::WalkRec> d_walk;        // block headers as the (serial) frame walk found them
+    // entries decoded block-parallel inside their frames (kernels_zstd_pj.cuh): segments, pointer scratch, round flags
+    std::vector<zs::PjSeg> h_pj_segs;
+    DevArr<zs::PjSeg> d_pj_segs;
+    DevArr<int32_t> d_pj_ptr;
+    DevArr<uint2> d_pj_cpos;
+    DevArr<uint32_t> d_pj_flags;
+    uint32_t pj_max_blocks = 0;
     DevArr<uint64_t> d_lit_base, d_seq_base;
     DevArr<inf::InfStream> d_inf;
     DevArr<uint8_t> d_inf_lits;
@@ -332,6 +340,7 @@ struct pna_plan {
         for (auto& t : d_tiles) t.release();
         d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_lz_units.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
+        d_walk.release(); d_pj_segs.release(); d_pj_ptr.release(); d_pj_cpos.release(); d_pj_flags.release();
         d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release();
         if (enc) enc::destroy(enc);
     }
@@ -980,13 +989,15 @@ static int launch_zstd_front(pna_plan* P, bool with_count) {   // scan .. resolv
         LAUNCHED();
         return PNA_OK;
     }
-    zs::zstd_fill_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
+    zs::zstd_walk_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, nz, P->d_walk.p);
     LAUNCHED();
     if (P->n_blocks) {
+        zs::zstd_fill_kernel<<<(P->n_blocks + 127) / 128, 128, 0, ctx->stream>>>(P->d_entries.p, P->d_walk.p, P->n_blocks, P->d_blocks.p);
+        LAUNCHED();
         zs::zstd_parse_kernel<<<(P->n_blocks + 127) / 128, 128, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_blocks.p, P->n_blocks);
         LAUNCHED();
     }
-    zs::zstd_resolve_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
+    zs::zstd_resolve_kernel<<<(nz + 3) / 4, 128, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);   // warp per entry
     LAUNCHED();
     zs::zstd_order_kernel<<<1, 1024, 0, ctx->stream>>>(P->d_entries.p, P->d_blocks.p, P->n_blocks, P->d_seq_order.p, P->d_lit_order.p,
                                                       P->d_counts.p);
@@ -1016,8 +1027,34 @@ static int launch_zstd_prefix(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
     const uint32_t nz = (uint32_t)P->h_ze.size();
     if (!nz) return PNA_OK;
-    zs::zstd_prefix_kernel<<<(nz + 63) / 64, 64, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);
+    zs::zstd_prefix_kernel<<<(nz + 3) / 4, 128, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, nz, P->d_blocks.p);   // warp per entry
     LAUNCHED();
+    return PNA_OK;
+}
+// Entries taken block-parallel inside their frames: per segment  scan -> expand -> pointer-jumping rounds -> gather.
+// The rounds after the one that found every pointer at a root return at once (flag of the previous round), so the fixed
+// launch sequence needs no host round trip.
+static int launch_zstd_pj(pna_plan* P) {
+    pna_ctx* ctx = P->ctx;
+    const uint32_t ns = (uint32_t)P->h_pj_segs.size();
+    if (!ns) return PNA_OK;
+    CK(cudaMemsetAsync(P->d_pj_flags.p, 0, (size_t)ns * zs::PJ_MAX_ROUNDS * sizeof(uint32_t), ctx->stream));
+    const uint32_t jump_grid = (uint32_t)ctx->sm_count * 8;
+    for (uint32_t s = 0; s < ns; s++) {
+        const uint32_t nb = P->h_pj_segs[s].blk_count;
+        uint32_t* flags = P->d_pj_flags.p + (size_t)s * zs::PJ_MAX_ROUNDS;
+        zs::pj_scan_kernel<<<(nb + 7) / 8, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_seqs.p, P->d_pj_cpos.p);
+        LAUNCHED();
+        zs::pj_expand_kernel<<<dim3(zs::PJ_EXPAND_X, nb), 256, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p,
+                                                                                P->d_lits.p, P->d_seqs.p, P->d_pj_cpos.p, P->d_out.p, P->d_pj_ptr.p);
+        LAUNCHED();
+        for (int r = 0; r < zs::PJ_MAX_ROUNDS; r++) {
+            zs::pj_jump_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p, flags, r);
+            LAUNCHED();
+        }
+        zs::pj_gather_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p, flags, P->d_out.p);
+        LAUNCHED();
+    }
     return PNA_OK;
 }
 static int launch_zstd_lz_on(pna_plan* P, const zs::ZEntry* ze, const uint32_t* order, const zs::LzUnit* units, uint32_t nz,
@@ -1074,8 +1111,10 @@ static int launch_inflate(pna_plan* P, int size_only) {
     }
     return PNA_OK;
 }
+static int launch_zstd_pj(pna_plan* P);
 static int launch_zstd_lz(pna_plan* P) {
-    return launch_zstd_lz_on(P, P->d_ze.p, P->d_lz_order.p, P->d_lz_units.p, P->n_lz_units, P->d_blocks.p, P->d_lits.p, P->d_seqs.p);
+    int rc = launch_zstd_lz_on(P, P->d_ze.p, P->d_lz_order.p, P->d_lz_units.p, P->n_lz_units, P->d_blocks.p, P->d_lits.p, P->d_seqs.p);
+    return rc ? rc : launch_zstd_pj(P);
 }
 static int launch_store(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
@@ -1111,7 +1150,7 @@ static int decode_prepare(pna_plan* P) {
         for (auto& z : P->h_ze) { z.blk_begin = (uint32_t)nb; nb += z.blk_count; }
         if (nb > 0xFFFFFFF0ull) return PNA_E_OOM;
         P->n_blocks = (uint32_t)nb;
-        CK(P->d_blocks.reserve(nb));
+        CK(P->d_blocks.reserve(nb)); CK(P->d_walk.reserve(nb));
         CK(P->d_seq_order.reserve(nb)); CK(P->d_lit_order.reserve(nb)); CK(P->d_counts.reserve(8));
         CK(cudaMemcpyAsync(P->d_ze.p, P->h_ze.data(), nz * sizeof(zs::ZEntry), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = launch_zstd_front(P, false))) return rc;
@@ -1127,18 +1166,50 @@ static int decode_prepare(pna_plan* P) {
         }
         if (nu > 0xFFFFFFF0ull) return PNA_E_OOM;
         // LZ units = frames; dispatched entry by entry in the longest-stream-first order, an entry's frames in stream order
-        P->n_lz_units = (uint32_t)nu;
+        P->n_lz_units = (uint32_t)nu;   // (reduced to the units of the CTA-per-frame kernel below)
         {
             uint64_t zc = 0;
             for (const auto& z : P->h_ze) zc += P->h_entries[z.entry].comp_len;
             P->lz_avg_unit_comp = nu ? zc / nu : 0;
         }
+        // Entries of very many blocks (a reference-written solid archive: ONE frame over every file) leave the CTA-per-frame
+        // kernel with a single busy SM: they are decoded block-parallel by pointer jumping instead (kernels_zstd_pj.cuh), as
+        // long as there are few of them -- with many large entries the frames themselves are the parallelism.
+        const char* pj_env = getenv("PNA_LZ_PJ_MIN_BLOCKS");
+        const uint32_t pj_min = pj_env ? (uint32_t)atoi(pj_env) : 512u;
+        std::vector<uint8_t> is_pj(nz, 0);
+        {
+            uint32_t n_big = 0;
+            for (uint32_t zi = 0; zi < nz; zi++) if (pj_min && P->h_ze[zi].blk_count >= pj_min) n_big++;
+            if (n_big && (n_big <= 16 || pj_env))
+                for (uint32_t zi = 0; zi < nz; zi++) if (P->h_ze[zi].blk_count >= pj_min && P->h_ze[zi].blk_count > 0) is_pj[zi] = 1;
+        }
+        P->h_pj_segs.clear(); P->pj_max_blocks = 0;
+        for (uint32_t zi = 0; zi < nz; zi++) {
+            if (!is_pj[zi]) continue;
+            const auto& z = P->h_ze[zi];
+            for (uint32_t b0 = 0; b0 < z.blk_count; b0 += zs::PJ_SEG_BLOCKS) {
+                const uint32_t nbk = std::min<uint32_t>(zs::PJ_SEG_BLOCKS, z.blk_count - b0);
+                P->h_pj_segs.push_back({zi, z.blk_begin + b0, nbk, 0u});
+                P->pj_max_blocks = std::max(P->pj_max_blocks, nbk);
+            }
+        }
+        if (!P->h_pj_segs.empty()) {
+            CK(P->d_pj_segs.reserve(P->h_pj_segs.size()));
+            CK(cudaMemcpyAsync(P->d_pj_segs.p, P->h_pj_segs.data(), P->h_pj_segs.size() * sizeof(zs::PjSeg), cudaMemcpyHostToDevice, ctx->stream));
+            CK(P->d_pj_ptr.reserve((size_t)P->pj_max_blocks * zs::BLOCK_MAX + 64));
+            CK(P->d_pj_cpos.reserve((size_t)P->pj_max_blocks * zs::PJ_MAX_CHUNKS));
+            CK(P->d_pj_flags.reserve(P->h_pj_segs.size() * zs::PJ_MAX_ROUNDS));
+        }
         std::vector<uint32_t> unit_order;
         unit_order.reserve(nu);
-        for (uint32_t zi : lz_order)
+        for (uint32_t zi : lz_order) {
+            if (is_pj[zi]) continue;
             for (uint32_t f = 0; f < P->h_ze[zi].n_frames; f++) unit_order.push_back(P->h_ze[zi].unit_begin + f);
+        }
         CK(P->d_lz_order.reserve(nu + 1)); CK(P->d_lz_units.reserve(nu + 1));
-        if (nu) CK(cudaMemcpyAsync(P->d_lz_order.p, unit_order.data(), nu * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (!unit_order.empty()) CK(cudaMemcpyAsync(P->d_lz_order.p, unit_order.data(), unit_order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        const uint32_t n_regular_units = (uint32_t)unit_order.size();
         P->lit_total = lit; P->seq_total = seq;
         CK(P->d_lits.reserve(lit + 256));
         CK(P->d_seqs.reserve(seq + 32));
@@ -1149,6 +1220,7 @@ static int decode_prepare(pna_plan* P) {
         zs::zstd_units_kernel<<<(nz + 127) / 128, 128, 0, ctx->stream>>>(P->d_ze.p, nz, P->d_blocks.p, P->d_lz_units.p);
         LAUNCHED();
         CK(ctx->sync());   // lb/sb/unit_order are locals
+        P->n_lz_units = n_regular_units;
     }
     if (P->need_sizing) {
         // exact sizes: zstd from the entropy+prefix stages, deflate from a count-only pass, store = comp_len

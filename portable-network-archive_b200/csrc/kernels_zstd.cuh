@@ -14,6 +14,7 @@
 #include "zstd_core.cuh"
 #include "kernels_crc_cipher.cuh"   // load16_any
 #include "kernels_zstd_lz.cuh"       // ZEntry, zstd_lz_kernel<LzSmall|LzBig>
+#include "kernels_zstd_pj.cuh"       // block-parallel LZ inside one frame (pointer jumping)
 
 namespace pna {
 namespace zs {
@@ -32,18 +33,28 @@ __global__ void zstd_count_kernel(const uint8_t* __restrict__ buf, EntryRec* ent
     set_status(entries, e, st);
     ze[i].blk_count = st == ST_OK && entries[e].status == ST_OK ? nb : 0;
 }
-// Re-walks the frames (the entry table is reset at the start of every run, so the status has to be
-// re-established here too) and records the blocks of entries whose walk succeeded.
-__global__ void zstd_fill_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, const ZEntry* ze, uint32_t nz,
-                                 ZBlock* blocks) {
+// Re-walks the frames (the entry table is reset at the start of every run, so the status has to be re-established here
+// too).  The walk is serial per entry -- a block is found only behind the previous block's header -- so it records 16 bytes
+// per block; zstd_fill_kernel builds the ZBlock records with a thread per block.
+__global__ void zstd_walk_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, const ZEntry* ze, uint32_t nz,
+                                 WalkRec* __restrict__ walk) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nz) return;
     const uint32_t e = ze[i].entry;
     if (entries[e].status != ST_OK) return;
     uint32_t nb = 0;
-    int32_t st = scan_entry(buf, entries[e].comp_off, entries[e].comp_len, e,
-                            ze[i].blk_count ? blocks + ze[i].blk_begin : nullptr, &nb);
+    int32_t st = scan_entry(buf, entries[e].comp_off, entries[e].comp_len, e, nullptr, &nb, walk + ze[i].blk_begin, ze[i].blk_count);
+    if (st == ST_OK && nb != ze[i].blk_count) st = ST_INTERNAL;
     set_status(entries, e, st);
+}
+__global__ void zstd_fill_kernel(const EntryRec* __restrict__ entries, const WalkRec* __restrict__ walk, uint32_t n_blocks, ZBlock* blocks) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    const WalkRec w = walk[i];
+    ZBlock z;
+    zblock_from_walk(w, z);
+    if (entries[w.entry].status != ST_OK) z.status = ST_INTERNAL;   // the walk failed: nothing of this entry is decoded
+    blocks[i] = z;
 }
 __global__ void zstd_parse_kernel(const uint8_t* __restrict__ buf, EntryRec* entries, ZBlock* blocks, uint32_t n_blocks) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,29 +64,64 @@ __global__ void zstd_parse_kernel(const uint8_t* __restrict__ buf, EntryRec* ent
     blocks[i] = b;
     set_status(entries, b.entry, b.status);
 }
-__global__ void zstd_resolve_kernel(EntryRec* entries, ZEntry* ze, uint32_t nz, ZBlock* blocks) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// value of a "last writer wins" variable as lane `lane` sees it (its own write included): the newest writer at or below the
+// lane, else the value carried in from the previous chunk
+__device__ __forceinline__ int32_t last_writer(uint32_t writers, int32_t myval, int32_t carry, uint32_t lane) {
+    const uint32_t m = writers & (0xFFFFFFFFu >> (31u - lane));
+    const int src = m ? 31 - __clz((int)m) : 0;
+    const int32_t v = __shfl_sync(0xFFFFFFFFu, myval, src);
+    return m ? v : carry;
+}
+// Repeat_Mode / treeless sources, literal and sequence offsets, frame count of every entry (zstd_core.cuh resolve_sources,
+// restated as warp scans: ONE WARP per entry, 32 blocks per round -- a solid archive is one entry of tens of thousands of
+// blocks, which a thread per entry would walk for tens of milliseconds).
+__global__ void __launch_bounds__(128) zstd_resolve_kernel(EntryRec* entries, ZEntry* ze, uint32_t nz, ZBlock* blocks) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (i >= nz) return;
-    ZEntry z = ze[i];
+    const ZEntry z = ze[i];
     uint64_t lit = 0, seq = 0;
     uint32_t nf = 0;
     if (entries[z.entry].status == ST_OK) {
-        int32_t st = resolve_sources(blocks, z.blk_begin, z.blk_count);
-        set_status(entries, z.entry, st);
-        for (uint32_t k = z.blk_begin; k < z.blk_begin + z.blk_count; k++) {
-            ZBlock& b = blocks[k];
-            nf += b.first_in_frame;
-            b.lit_off = lit;   // relative to the entry's bases
-            b.seq_off = seq;
-            if (b.type == BT_COMPRESSED) {
-                if (b.lit_type >= LT_COMPRESSED) lit += (b.lit_regen + 15u) & ~15u;
-                seq += b.nseq;
+        int32_t c_huf = -2, c_cur[3] = {-2, -2, -2};
+        bool bad = false;
+        for (uint32_t k0 = z.blk_begin; k0 < z.blk_begin + z.blk_count; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const bool have = k < z.blk_begin + z.blk_count;
+            ZBlock* b = blocks + (have ? k : k0);
+            const bool first = have && b->first_in_frame;
+            const bool comp = have && b->type == BT_COMPRESSED;
+            const bool live = comp && b->status == ST_OK;                  // resolve_sources skips the others
+            const uint32_t lt = b->lit_type, nseq = b->nseq, lit_regen = b->lit_regen;
+            // Huffman tree source
+            {
+                const bool own = live && lt == LT_COMPRESSED;
+                const uint32_t w = __ballot_sync(0xFFFFFFFFu, first || own);
+                const int32_t seen = last_writer(w, own ? (int32_t)k : -2, c_huf, lane);
+                if (live) { if (lt == LT_TREELESS && seen < 0) bad = true; b->huf_src = seen; }
+                c_huf = __shfl_sync(0xFFFFFFFFu, last_writer(w, own ? (int32_t)k : -2, c_huf, 31u), 31);
             }
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const uint32_t mode = b->mode[t];
+                const bool uses = live && nseq != 0;
+                const bool own = uses && mode != SM_REPEAT;
+                const int32_t val = own ? (mode == SM_PREDEF ? -1 : (int32_t)k) : -2;
+                const uint32_t w = __ballot_sync(0xFFFFFFFFu, first || own);
+                const int32_t seen = last_writer(w, val, c_cur[t], lane);
+                if (uses) { if (mode == SM_REPEAT && seen == -2) bad = true; b->tsrc[t] = seen; }
+                c_cur[t] = __shfl_sync(0xFFFFFFFFu, last_writer(w, val, c_cur[t], 31u), 31);
+            }
+            // literal / sequence arena offsets (exclusive sums), relative to the entry's bases
+            const uint32_t lc = (comp && lt >= LT_COMPRESSED) ? ((lit_regen + 15u) & ~15u) : 0u, sc = comp ? nseq : 0u;
+            const uint32_t li = warp_incl_scan(lc, (int)lane), si = warp_incl_scan(sc, (int)lane);
+            if (have) { b->lit_off = lit + li - lc; b->seq_off = seq + si - sc; }
+            lit += __shfl_sync(0xFFFFFFFFu, li, 31);
+            seq += __shfl_sync(0xFFFFFFFFu, si, 31);
+            nf += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, first));
         }
+        if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) set_status(entries, z.entry, ST_INVALID_DATA);
     }
-    ze[i].lit_total = lit;
-    ze[i].seq_total = seq;
-    ze[i].n_frames = nf;
+    if (lane == 0) { ze[i].lit_total = lit; ze[i].seq_total = seq; ze[i].n_frames = nf; }
 }
 // LZ units of every entry: one per frame, in stream order, at the entry's slots (ZEntry.unit_begin from the host)
 __global__ void zstd_units_kernel(const ZEntry* __restrict__ ze, uint32_t nz, const ZBlock* __restrict__ blocks, LzUnit* __restrict__ units) {
@@ -317,15 +363,68 @@ __global__ void __launch_bounds__(32) zstd_lit_kernel(const uint8_t* __restrict_
     }
 }
 
-__global__ void zstd_prefix_kernel(EntryRec* entries, const ZEntry* ze, uint32_t nz, ZBlock* blocks) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// Output offsets, frame starts and the absolute incoming repeat-offset history of every block (zstd_core.cuh prefix_entry):
+// ONE WARP per entry, 32 blocks per round -- positions by warp scans, the history by a register-only walk over the 32
+// blocks' (symbolic) outgoing histories, so that no round waits on memory more than once.
+__global__ void __launch_bounds__(128) zstd_prefix_kernel(EntryRec* entries, const ZEntry* ze, uint32_t nz, ZBlock* blocks) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (i >= nz) return;
     const ZEntry z = ze[i];
     if (entries[z.entry].status != ST_OK) return;
-    uint64_t total = 0;
-    int32_t st = prefix_entry(blocks, z.blk_begin, z.blk_count, 0, &total);   // offsets relative to the entry
-    set_status(entries, z.entry, st);
-    entries[z.entry].out_len = total;
+    uint64_t pos = 0, frame_start = 0;
+    uint32_t rep[3] = {1, 4, 8};
+    int32_t st = ST_OK;
+    for (uint32_t k0 = z.blk_begin; k0 < z.blk_begin + z.blk_count; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool have = k < z.blk_begin + z.blk_count;
+        ZBlock* b = blocks + (have ? k : k0);
+        const bool first = have && b->first_in_frame;
+        const int32_t bst = have ? b->status : ST_OK;
+        const bool ok = have && bst == ST_OK;
+        const uint32_t osz = ok ? b->out_size : 0u;                       // a failed block does not advance (prefix_entry)
+        const bool upd = ok && b->type == BT_COMPRESSED && b->nseq > 0;
+        const uint32_t ro0 = b->rep_out[0], ro1 = b->rep_out[1], ro2 = b->rep_out[2];
+        const uint32_t incl = warp_incl_scan(osz, (int)lane);
+        const uint64_t my_pos = pos + incl - osz;
+        // frame start = position of the newest first_in_frame block at or below this one
+        const uint32_t fw = __ballot_sync(0xFFFFFFFFu, first);
+        const uint32_t fm = fw & (0xFFFFFFFFu >> (31u - lane));
+        const uint32_t fsrc = fm ? 31u - (uint32_t)__clz((int)fm) : 0u;
+        const uint32_t fpos_lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)my_pos, (int)fsrc), fpos_hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(my_pos >> 32), (int)fsrc);
+        const uint64_t my_frame = fm ? (((uint64_t)fpos_hi << 32) | fpos_lo) : frame_start;
+        // repeat-offset history: every lane walks the 32 blocks in registers, lane j keeps what block j sees
+        uint32_t in0 = 0, in1 = 0, in2 = 0;
+        int32_t my_st = bst;
+        for (int j = 0; j < 32; j++) {
+            const bool jf = (fw >> j) & 1u;
+            if (jf) { rep[0] = 1; rep[1] = 4; rep[2] = 8; }
+            if ((int)lane == j) { in0 = rep[0]; in1 = rep[1]; in2 = rep[2]; }
+            const bool ju = __shfl_sync(0xFFFFFFFFu, upd ? 1 : 0, j) != 0;
+            const uint32_t a0 = __shfl_sync(0xFFFFFFFFu, ro0, j), a1 = __shfl_sync(0xFFFFFFFFu, ro1, j), a2 = __shfl_sync(0xFFFFFFFFu, ro2, j);
+            if (ju) {
+                const uint32_t r0 = resolve_rep(a0, rep), r1 = resolve_rep(a1, rep), r2 = resolve_rep(a2, rep);
+                if (!r0 || !r1 || !r2) { if ((int)lane == j) my_st = ST_INVALID_DATA; }
+                else { rep[0] = r0; rep[1] = r1; rep[2] = r2; }
+            }
+        }
+        if (have) {
+            b->out_off = my_pos; b->frame_out = my_frame;
+            b->rep_in[0] = in0; b->rep_in[1] = in1; b->rep_in[2] = in2;
+            if (my_st != bst) b->status = my_st;
+        }
+        // first failure in block order (a failed entry produces no output, so the positions behind it do not matter)
+        const uint32_t badm = __ballot_sync(0xFFFFFFFFu, have && my_st != ST_OK);
+        const int32_t first_bad = __shfl_sync(0xFFFFFFFFu, my_st, badm ? __ffs((int)badm) - 1 : 0);
+        if (badm && st == ST_OK) st = first_bad;
+        pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const int fl = fw ? 31 - __clz((int)fw) : 0;
+        const uint32_t fs_lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)my_pos, fl), fs_hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(my_pos >> 32), fl);
+        if (fw) frame_start = ((uint64_t)fs_hi << 32) | fs_lo;
+    }
+    if (lane == 0) {
+        set_status(entries, z.entry, st);
+        entries[z.entry].out_len = pos;
+    }
 }
 
 }  // namespace zs

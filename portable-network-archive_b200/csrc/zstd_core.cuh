@@ -718,8 +718,27 @@ PNA_HD bool huf_decode_stream_w(const uint32_t* words, const uint8_t* comp, uint
 // ---------------------------------------------------------------------------------------------
 // Frame scan.  Walks the frames and block headers of one entry's compressed stream.  When `blocks`
 // is null only counts.  Returns the entry status; *n_blocks = number of blocks found.
+// One block header as the frame walk records it: the walk is the only inherently serial step (a block's position is
+// known only after every block header in front of it was read), so it writes 16 bytes per block and leaves building the
+// 200-byte ZBlock records to a thread per block (zstd_fill_kernel).
+struct WalkRec {
+    uint64_t src;       // byte offset of the block content inside the comp arena
+    uint32_t entry;
+    uint32_t bits;      // size (bits 0-20) | type << 21 | first_in_frame << 23
+};
+PNA_HD void zblock_from_walk(const WalkRec& w, ZBlock& z) {
+    memset(&z, 0, sizeof z);
+    z.src = w.src;
+    z.entry = w.entry;
+    z.size = w.bits & 0x1FFFFFu;
+    z.type = (uint8_t)((w.bits >> 21) & 3u);
+    z.first_in_frame = (uint8_t)((w.bits >> 23) & 1u);
+    z.out_size = z.type == BT_COMPRESSED ? 0 : z.size;
+    z.tsrc[0] = z.tsrc[1] = z.tsrc[2] = -1;
+    z.huf_src = -1;
+}
 PNA_HD int32_t scan_entry(const uint8_t* comp, uint64_t base, uint64_t len, uint32_t entry, ZBlock* blocks,
-                          uint32_t* n_blocks) {
+                          uint32_t* n_blocks, WalkRec* walk = nullptr, uint32_t walk_cap = 0) {
     uint64_t pos = 0;
     uint32_t nb = 0;
     int32_t st = ST_OK;
@@ -783,6 +802,7 @@ PNA_HD int32_t scan_entry(const uint8_t* comp, uint64_t base, uint64_t len, uint
                 z.huf_src = -1;
                 blocks[nb] = z;
             }
+            if (walk && nb < walk_cap) walk[nb] = WalkRec{base + pos + 3, entry, size | (type << 21) | ((first ? 1u : 0u) << 23)};
             nb++;
             first = false;
             pos += 3 + content;

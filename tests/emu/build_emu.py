@@ -137,7 +137,7 @@ def build(force: bool = False) -> str:
         with open(os.path.join(GEN, name), "w") as o:
             o.write(text)
     opt = os.environ.get("PNA_EMU_OPT", "-O2")
-    subprocess.check_call(["g++", opt, "-g", "-std=c++17", "-shared", "-fPIC", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
+    subprocess.check_call(["g++", *opt.split(), "-g", "-std=c++17", "-shared", "-fPIC", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
                            "-I" + HERE, "-o", lib, os.path.join(GEN, "abi.cpp"), os.path.join(HERE, "emu_switch.S"), "-lpthread"])
     subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-o", host, os.path.join(GEN, "host_api.cpp"), "-L" + GEN,
                            "-lpna_cuda", "-Wl,-rpath,$ORIGIN", "-lpthread"])
