@@ -1007,7 +1007,7 @@ static int launch_zstd_front(pna_plan* P, bool with_count) {   // scan .. resolv
 static int launch_zstd_seq(pna_plan* P) {
     pna_ctx* ctx = P->ctx;
     if (P->h_ze.empty() || !P->n_blocks) return PNA_OK;
-    const uint32_t per_cta = zs::SEQ_LANES * zs::SEQ_WARPS;
+    const uint32_t per_cta = zs::SEQ_SLOTS * zs::SEQ_WARPS;
     const uint32_t grid = std::min<uint32_t>((P->n_blocks + per_cta - 1) / per_cta, (uint32_t)ctx->sm_count);
     zs::zstd_seq_kernel<<<grid, 32 * zs::SEQ_WARPS, zs::SEQ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_blocks.p, P->d_seq_order.p,
                                                                       P->d_counts.p, P->d_seq_base.p, P->d_seqs.p);
@@ -1047,6 +1047,8 @@ static int launch_zstd_pj(pna_plan* P) {
         LAUNCHED();
         zs::pj_expand_kernel<<<dim3(zs::PJ_EXPAND_X, nb), 256, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p,
                                                                                 P->d_lits.p, P->d_seqs.p, P->d_pj_cpos.p, P->d_out.p, P->d_pj_ptr.p);
+        LAUNCHED();
+        zs::pj_chase_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p);
         LAUNCHED();
         for (int r = 0; r < zs::PJ_MAX_ROUNDS; r++) {
             zs::pj_jump_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p, flags, r);

@@ -198,14 +198,18 @@ __global__ void __launch_bounds__(1024) zstd_order_kernel(const EntryRec* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sequence stage: ONE LANE per block.  The FSE chain (table lookup -> bit counts -> next state) is serial
-// per block, so throughput = blocks in flight / chain latency, and blocks in flight = shared memory /
-// table bytes.  16-bit cells (zstd_core.cuh Tab16) make a block's three tables 2.5 KB: 88 blocks fill the
-// SM's 227 KB.  One CTA of 4 warps per SM (one warp per scheduler), 22 active lanes per warp, each warp's
-// 22 tables interleaved by lane; the warps take batches of 22 blocks independently (no CTA barrier).
-constexpr uint32_t SEQ_LANES = 22, SEQ_WARPS = 4;
-constexpr uint32_t SEQ_TAB_BYTES = TAB16_TOTAL * SEQ_LANES * SEQ_WARPS * sizeof(uint16_t);    // 225280
-constexpr uint32_t SEQ_SMEM_BYTES = SEQ_TAB_BYTES + SEQ_LANES * SEQ_WARPS * 64;               // + a 64-byte bitstream ring per active lane
+// Sequence stage.  The FSE chain (table lookup -> bit counts -> next state) is serial per block, so throughput = blocks in
+// flight / chain latency, and blocks in flight = shared memory / table bytes: 16-bit cells (zstd_core.cuh Tab16) make a
+// block's three tables 2.5 KB, 88 blocks fill the SM's 227 KB.  One CTA of 4 warps per SM (one warp per scheduler), 22 table
+// sets per warp, interleaved by set; the warps take batches of 22 blocks independently (no CTA barrier).
+// Measured dead end (round 2, profiles/r2_seq_streams_per_lane.txt): advancing K independent blocks per lane (22 / K lanes
+// active) to fill the empty issue slots takes K times as long -- 9.7 / 17.9 / 25.8 ms for K = 1 / 2 / 3 on the cfg2 shard.
+// The kernel is not waiting on latency that a second chain could fill: with ONE warp per scheduler the integer pipe issues
+// a warp instruction every two cycles at best, the loop runs at 0.27 of a possible 0.5 IPC, and fewer active lanes per warp
+// means more warp instructions for the same sequences.  What would help is fewer instructions per sequence or smaller tables.
+constexpr uint32_t SEQ_SLOTS = 22, SEQ_WARPS = 4;
+constexpr uint32_t SEQ_TAB_BYTES = TAB16_TOTAL * SEQ_SLOTS * SEQ_WARPS * sizeof(uint16_t);    // 225280
+constexpr uint32_t SEQ_SMEM_BYTES = SEQ_TAB_BYTES + SEQ_SLOTS * SEQ_WARPS * 64;               // + a 64-byte bitstream ring per block in flight
 
 // A lane's bitstream through shared memory: 16 words (four 16-byte groups) of the stream around the read position,
 // refilled one group at a time by cp.async two groups before it is needed.  The stream is consumed downwards at
@@ -256,43 +260,36 @@ __global__ void __launch_bounds__(32 * SEQ_WARPS) zstd_seq_kernel(const uint8_t*
     __syncthreads();
     const uint32_t n = counts[0];
     const uint32_t* words = reinterpret_cast<const uint32_t*>(buf);
-    uint16_t* const stab = stab_all + (uint32_t)warp * TAB16_TOTAL * SEQ_LANES;
-    const bool active = (uint32_t)lane < SEQ_LANES;
-    const uint32_t l = active ? (uint32_t)lane : 0u;
-    const Tab16 tll{stab + TAB16_LL * SEQ_LANES + l, SEQ_LANES}, tml{stab + TAB16_ML * SEQ_LANES + l, SEQ_LANES},
-        tof{stab + TAB16_OF * SEQ_LANES + l, SEQ_LANES};
+    uint16_t* const stab = stab_all + (uint32_t)warp * TAB16_TOTAL * SEQ_SLOTS;
+    const bool active = (uint32_t)lane < SEQ_SLOTS;
+    const uint32_t slot = active ? (uint32_t)lane : 0u;
+    const Tab16 tll{stab + TAB16_LL * SEQ_SLOTS + slot, SEQ_SLOTS}, tml{stab + TAB16_ML * SEQ_SLOTS + slot, SEQ_SLOTS},
+        tof{stab + TAB16_OF * SEQ_SLOTS + slot, SEQ_SLOTS};
     for (;;) {
         uint32_t first = 0;
-        if (lane == 0) first = atomicAdd(&counts[2], SEQ_LANES);
+        if (lane == 0) first = atomicAdd(&counts[2], SEQ_SLOTS);
         first = __shfl_sync(0xFFFFFFFFu, first, 0);
         if (first >= n) break;
         const uint32_t k = first + (uint32_t)lane;
         if (active && k < n) {
-            const uint32_t bi = order[k];
-            ZBlock& gb = blocks[bi];
-            ZBlock b;                       // only the fields the decoder reads (the rest of the 200-byte record stays in HBM)
-            b.src = gb.src; b.bs_pos = gb.bs_pos; b.bs_len = gb.bs_len; b.nseq = gb.nseq; b.lit_regen = gb.lit_regen;
-            b.tsrc[0] = gb.tsrc[0]; b.tsrc[1] = gb.tsrc[1]; b.tsrc[2] = gb.tsrc[2];
-            const uint32_t entry = gb.entry;
+            ZBlock& gb = blocks[order[k]];
             int16_t norm[64];
             uint16_t next_of[64];
-            const int l0 = seq_tab16_for(buf, blocks, b, 0, tll, norm, next_of);
-            const int l1 = seq_tab16_for(buf, blocks, b, 1, tof, norm, next_of);
-            const int l2 = seq_tab16_for(buf, blocks, b, 2, tml, norm, next_of);
+            const int l0 = seq_tab16_for(buf, blocks, gb, 0, tll, norm, next_of);
+            const int l1 = seq_tab16_for(buf, blocks, gb, 1, tof, norm, next_of);
+            const int l2 = seq_tab16_for(buf, blocks, gb, 2, tml, norm, next_of);
             int32_t st = ST_INVALID_DATA;
-            uint32_t esc_n = 0, esc_idx[SEQ_ESC_MAX], esc_ll[SEQ_ESC_MAX], esc_ml[SEQ_ESC_MAX];
             if (l0 >= 0 && l1 >= 0 && l2 >= 0) {
-                const uint64_t so = seq_base_of_entry[entry] + gb.seq_off;
-                RingBitSrc src;
-                src.ring = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(stab_all) + SEQ_TAB_BYTES) + ((uint32_t)warp * SEQ_LANES + l) * 16;
-                st = decode_sequences16_from(src, words, buf, b, tll, tof, tml, l0, l1, l2, s_llb, s_mlb, seqs + so, &esc_n, esc_idx, esc_ll, esc_ml);
+                SeqStream<RingBitSrc> s;   // scalars only: lives in registers (no L1 is left beside 225 KB of tables)
+                s.src.ring = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(stab_all) + SEQ_TAB_BYTES) + ((uint32_t)warp * SEQ_SLOTS + slot) * 16;
+                st = s.begin(words, buf, gb, tll, tof, tml, l0, l1, l2, s_llb, s_mlb, seqs + seq_base_of_entry[gb.entry] + gb.seq_off);
+                if (st == ST_OK) {
+                    const uint32_t nseq = s.nseq;
+                    for (uint32_t i = 0; i < nseq; i++) s.step(i);
+                    st = s.end();
+                }
             }
-            if (st == ST_OK) {
-                gb.out_size = b.out_size; gb.lit_used = b.lit_used;
-                gb.rep_out[0] = b.rep_out[0]; gb.rep_out[1] = b.rep_out[1]; gb.rep_out[2] = b.rep_out[2];
-                gb.esc_n = esc_n;
-                for (uint32_t q = 0; q < esc_n && q < (uint32_t)SEQ_ESC_MAX; q++) { gb.esc_idx[q] = esc_idx[q]; gb.esc_ll[q] = esc_ll[q]; gb.esc_ml[q] = esc_ml[q]; }
-            } else { gb.status = st; set_status(entries, entry, st); }
+            if (st != ST_OK) { gb.status = st; set_status(entries, gb.entry, st); }
         }
         __syncwarp();
     }

@@ -10,6 +10,7 @@
 //
 //   pj_scan     warp per block    prefix sums of (literal length, total length) at every 32nd sequence; length checks
 //   pj_expand   warp per 32 sequences: literals go to their final place, match bytes get their pointer (byte parallel)
+//   pj_chase    thread per 4 bytes, one ascending sweep that follows every chain a few hops (resolves almost everything)
 //   pj_jump     thread per 4 bytes, repeated until a round finds every pointer at a root (the launches that follow exit at once)
 //   pj_gather   thread per 4 bytes: every non-root byte copies its root
 //
@@ -58,15 +59,25 @@ __global__ void __launch_bounds__(256) pj_scan_kernel(EntryRec* entries, const Z
     const SeqRec* sq = seqs + zp->seq_base + b.seq_off;
     uint2* cp = cpos + (size_t)bl * PJ_MAX_CHUNKS;
     uint32_t lit = 0, tot = 0;
-    for (uint32_t c0 = 0; c0 < nseq; c0 += 32) {
-        if (lane == 0) cp[c0 >> 5] = make_uint2(lit, tot);
-        uint32_t ll = 0, ml = 0;
-        if (c0 + lane < nseq) pj_seq_lengths(b, sq[c0 + lane], c0 + lane, ll, ml);
-        uint32_t a = ll, t = ll + ml;
+    for (uint32_t c0 = 0; c0 < nseq && tot <= BLOCK_MAX; c0 += 128) {   // four chunks per round: four loads in flight per lane
+        uint32_t a[4], t[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, o); t += __shfl_xor_sync(0xFFFFFFFFu, t, o); }
-        lit += a; tot += t;
-        if (tot > BLOCK_MAX) break;   // corrupt: caught below
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i = c0 + 32u * k + lane;
+            uint32_t ll = 0, ml = 0;
+            if (i < nseq) pj_seq_lengths(b, sq[i], i, ll, ml);
+            a[k] = ll; t[k] = ll + ml;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { a[k] += __shfl_xor_sync(0xFFFFFFFFu, a[k], o); t[k] += __shfl_xor_sync(0xFFFFFFFFu, t[k], o); }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (c0 + 32u * k < nseq && lane == 0) cp[(c0 >> 5) + k] = make_uint2(lit, tot);
+            lit += a[k]; tot += t[k];
+        }
     }
     if (lane == 0) {
         // the same checks the CTA-per-frame kernel makes while it runs: literals not overrun, block size as announced
@@ -120,6 +131,7 @@ __global__ void __launch_bounds__(256) pj_expand_kernel(const uint8_t* __restric
         const uint32_t lstart = base.x + lincl - ll;                     // its first literal
         if (i < nseq && ml) bad = bad || off == 0 || (uint64_t)off > fd64 + start + ll || off > 0x7FFFFFFFu;
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+#pragma unroll 4
         for (uint32_t q0 = 0; q0 < total; q0 += 32) {
             const uint32_t q = q0 + lane;
             // the sequence that holds byte q: the first lane whose inclusive sum exceeds q
@@ -185,6 +197,41 @@ __global__ void __launch_bounds__(256) pj_jump_kernel(const EntryRec* __restrict
         }
     }
     if (open) flags[round] = 1;
+}
+
+// First pass over the pointers: an ascending sweep (every CTA walks its grid-stride positions upwards, so the grid as a whole
+// moves through the segment in windows of gridDim.x KiB) that follows each chain for up to PJ_CHASE_HOPS hops.  Sources are
+// mostly recent bytes (the codec's window), i.e. pointers that this very sweep has just resolved: a typical chain ends at a
+// root after two hops, and ONE pass leaves almost nothing for the doubling rounds that follow.  Any pointer read on the way
+// is valid whether or not another thread has already shortened it (pointers only ever move towards their root).
+constexpr int PJ_CHASE_HOPS = 6;
+__global__ void __launch_bounds__(256) pj_chase_kernel(const EntryRec* __restrict__ entries, const ZEntry* __restrict__ ze,
+                                                       const PjSeg* __restrict__ segs, uint32_t seg_index, const ZBlock* __restrict__ blocks,
+                                                       int32_t* ptr) {
+    const PjSeg sg = segs[seg_index];
+    const ZEntry* zp = ze + sg.ze;
+    const EntryRec& er = entries[zp->entry];
+    if (er.status != ST_OK || er.out_len > er.out_cap) return;
+    const ZBlock& last = blocks[sg.blk_begin + sg.blk_count - 1];
+    const uint32_t n = (uint32_t)(last.out_off + last.out_size - blocks[sg.blk_begin].out_off);
+    for (uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u; i0 < n; i0 += gridDim.x * 1024u) {
+        int32_t v[4];
+        if (i0 + 4 <= n) { const int4 t = *reinterpret_cast<const int4*>(ptr + i0); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else for (int k = 0; k < 4; k++) v[k] = i0 + k < n ? ptr[i0 + k] : -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int32_t p = v[k];
+            if (p < 0 || (uint32_t)p == i0 + k) continue;
+            int32_t r = p;
+            for (int h = 0; h < PJ_CHASE_HOPS; h++) {
+                const int32_t w = ptr[r];
+                if (w == r) break;                 // a literal: r is the root
+                r = w;
+                if (w < 0) break;                  // left the segment: root
+            }
+            if (r != p) ptr[i0 + k] = r;
+        }
+    }
 }
 
 // every byte that is not its own root copies the root's byte

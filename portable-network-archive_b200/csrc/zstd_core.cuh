@@ -469,34 +469,55 @@ struct GlobalBitSrc {
     }
 };
 
+// One block's sequence stream as a stepper, so that a lane can advance several independent streams side by side (the FSE
+// chain of one stream is serial; zstd_seq_kernel interleaves K streams per lane to fill the issue slots its latency leaves).
+// A step is cut in three phases -- call each phase for all of a lane's streams before the next one:
+//   advance(i)  the loop-carried part: cells -> bit counts -> fields of this sequence, next position, next states
+//   fetch()     the NEXT sequence's bit window and table cells are requested
+//   emit(i)     this sequence's values, repeat-offset logic and the store, in the latency shadow of those loads
 template <class Src>
-PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll,
-                                       const Tab16& tof, const Tab16& tml, int lll, int lof, int lml,
-                                       const uint32_t* llb, const uint32_t* mlb, SeqRec* out, uint32_t* esc_n,
-                                       uint32_t* esc_idx, uint32_t* esc_ll, uint32_t* esc_ml) {
-    const uint64_t begin = b.src + b.bs_pos;
-    const uint32_t len = b.bs_len, nseq = b.nseq, lit_regen = b.lit_regen;
-    if (len == 0) return ST_INVALID_DATA;
-    const uint8_t last = comp[begin + len - 1];
-    if (last == 0) return ST_INVALID_DATA;
-    int32_t pos = (int32_t)(len - 1) * 8 + highbit32(last);
-    const uint32_t ulll = (uint32_t)lll, ulof = (uint32_t)lof, ulml = (uint32_t)lml;
-    if (pos < (int32_t)(ulll + ulof + ulml)) return ST_INVALID_DATA;
-    src.init(words, begin, pos);
-    uint64_t W = src.window(pos);
-    uint32_t sll = win_bits(W, 0, ulll), sof = win_bits(W, ulll, ulof), sml = win_bits(W, ulll + ulof, ulml);
-    pos -= (int32_t)(ulll + ulof + ulml);
-    uint32_t rep0 = REP_SYM | (0u << 29), rep1 = REP_SYM | (1u << 29), rep2 = REP_SYM | (2u << 29);
-    uint32_t lit_sum = 0, match_sum = 0;     // < 2^32: nseq < 2^17 values < 2^17 each
-    const uint32_t zll = 1u << lll, zof = 1u << lof, zml = 1u << lml;
-    uint32_t ne = 0;
-    uint32_t err = 0;
-    // Software pipeline: the loop-carried part (cells -> bit counts -> next position / states) comes first, then the
-    // NEXT sequence's window and table cells are requested, and only then this sequence's values, repeat-offset
-    // logic and store run -- in the latency shadow of those loads (one warp per scheduler: nothing else hides it).
-    W = src.window(pos);
-    uint32_t ell = tll.get(sll), eof = tof.get(sof), eml = tml.get(sml);
-    for (uint32_t i = 0; i < nseq; i++) {
+struct SeqStream {
+    Src src;
+    Tab16 tll, tof, tml;
+    const uint32_t *llb, *mlb;
+    SeqRec* out;
+    uint32_t ulll, ulof, ulml, zll, zof, zml, nseq, lit_regen;
+    uint32_t sll, sof, sml, ell, eof, eml;
+    int32_t pos;
+    uint64_t W;
+    uint32_t rep0, rep1, rep2, lit_sum, match_sum, ne, err;
+    ZBlock* blk;   // the block's record: escapes (rare) and results go straight there -- the struct holds scalars only, so that
+                   // a lane's streams live in registers (an array member would pin them to local memory, which the sequence
+                   // kernel's shared-memory carve-out leaves without L1)
+    // fields of the sequence between advance() and emit()
+    uint32_t f_ofx, f_x, f_cof, f_xll, f_pll, f_pml;
+
+    // everything in front of the loop; ST_OK or the status the block fails with
+    PNA_HD int32_t begin(const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll_, const Tab16& tof_, const Tab16& tml_,
+                         int lll, int lof, int lml, const uint32_t* llb_, const uint32_t* mlb_, SeqRec* out_) {
+        tll = tll_; tof = tof_; tml = tml_; llb = llb_; mlb = mlb_; out = out_; blk = &b;
+        const uint64_t begin_at = b.src + b.bs_pos;
+        const uint32_t len = b.bs_len;
+        nseq = b.nseq; lit_regen = b.lit_regen;
+        if (len == 0) return ST_INVALID_DATA;
+        const uint8_t last = comp[begin_at + len - 1];
+        if (last == 0) return ST_INVALID_DATA;
+        pos = (int32_t)(len - 1) * 8 + highbit32(last);
+        ulll = (uint32_t)lll; ulof = (uint32_t)lof; ulml = (uint32_t)lml;
+        if (pos < (int32_t)(ulll + ulof + ulml)) return ST_INVALID_DATA;
+        src.init(words, begin_at, pos);
+        W = src.window(pos);
+        sll = win_bits(W, 0, ulll); sof = win_bits(W, ulll, ulof); sml = win_bits(W, ulll + ulof, ulml);
+        pos -= (int32_t)(ulll + ulof + ulml);
+        rep0 = REP_SYM | (0u << 29); rep1 = REP_SYM | (1u << 29); rep2 = REP_SYM | (2u << 29);
+        lit_sum = 0; match_sum = 0;            // < 2^32: nseq < 2^17 values < 2^17 each
+        zll = 1u << lll; zof = 1u << lof; zml = 1u << lml;
+        ne = 0; err = 0;
+        W = src.window(pos);
+        ell = tll.get(sll); eof = tof.get(sof); eml = tml.get(sml);
+        return ST_OK;
+    }
+    PNA_HD void advance(uint32_t i) {
         const uint32_t cll = ell >> 10, cof = eof >> 10, cml = eml >> 10;
         const uint32_t pll = llb[cll], pml = mlb[cml];       // baseline | extra bits << 24 (seq_pack_base)
         const uint32_t xll = pll >> 24, xml = pml >> 24;
@@ -506,8 +527,8 @@ PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const ui
         const uint32_t xb = cof + xml + xll;                 // value bits: offset, match length, literal length
         const bool more = i + 1 < nseq;
         const uint32_t nbs = more ? nbl + nbm + nbo : 0u;    // the last sequence updates no state
-        const uint32_t ofx = win_bits(W, 0, cof);
-        const uint32_t x = win_bits(W, cof, xml + xll);
+        f_ofx = win_bits(W, 0, cof);
+        f_x = win_bits(W, cof, xml + xll);
         uint32_t y;
         if (xb + nbs <= 64u) y = win_bits(W, xb, nbs);
         else {   // > 64 bits in one sequence (offset codes > 22 with long length codes): second window for the states
@@ -520,14 +541,17 @@ PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const ui
         sll = more ? ((nsl << nbl) - zll) + (y >> (nbm + nbo)) : 0u;
         sml = more ? ((nsm << nbm) - zml) + ((y >> nbo) & ((1u << nbm) - 1u)) : 0u;
         sof = more ? ((nso << nbo) - zof) + (y & ((1u << nbo) - 1u)) : 0u;
-        // ---- the next sequence's loads (after the last sequence: position 0 / state 0, valid and unused)
+        f_cof = cof; f_xll = xll; f_pll = pll; f_pml = pml;
+    }
+    PNA_HD void fetch() {   // (after the last sequence: position 0 / state 0, valid and unused)
         W = src.window(pos);
         ell = tll.get(sll); eof = tof.get(sof); eml = tml.get(sml);
-        // ---- this sequence's values
-        const uint32_t mlx = x >> xll, llx = x & ((1u << xll) - 1u);
-        const uint32_t ofv = (1u << cof) + ofx;
-        const uint32_t ml = (pml & 0xFFFFFFu) + mlx;
-        const uint32_t ll = (pll & 0xFFFFFFu) + llx;
+    }
+    PNA_HD void emit(uint32_t i) {
+        const uint32_t mlx = f_x >> f_xll, llx = f_x & ((1u << f_xll) - 1u);
+        const uint32_t ofv = (1u << f_cof) + f_ofx;
+        const uint32_t ml = (f_pml & 0xFFFFFFu) + mlx;
+        const uint32_t ll = (f_pll & 0xFFFFFFu) + llx;
         // repeat-offset logic (RFC 8878 3.1.1.5), branch-free; offsets may be symbolic (REP_SYM) in the block's incoming history
         const bool is_new = ofv > 3;
         const uint32_t idx = ofv - 1 + (ll == 0 ? 1u : 0u);                     // meaningful when !is_new: 0..3
@@ -545,7 +569,7 @@ PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const ui
         r.y = ll | (ml << 16);
         if ((ll | ml) >= SEQ_ESC) {                          // cheap superset of "a length does not fit 16 bits" (rare)
             if (ll >= SEQ_ESC || ml >= SEQ_ESC) {
-                if (ne < (uint32_t)SEQ_ESC_MAX) { esc_idx[ne] = i; esc_ll[ne] = ll; esc_ml[ne] = ml; }
+                if (ne < (uint32_t)SEQ_ESC_MAX) { blk->esc_idx[ne] = i; blk->esc_ll[ne] = ll; blk->esc_ml[ne] = ml; }
                 else err |= 1u;                              // > 4 such sequences cannot fit a 128 KiB block
                 ne++;
             }
@@ -554,15 +578,38 @@ PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const ui
         out[i] = r;
         lit_sum += ll; match_sum += ml;
     }
-    if (err || pos != 0) return ST_INVALID_DATA;
-    if (lit_sum > lit_regen) return ST_INVALID_DATA;
-    const uint64_t outsz = (uint64_t)lit_regen + match_sum;
-    if (outsz > BLOCK_MAX) return ST_INVALID_DATA;
-    b.out_size = (uint32_t)outsz;
-    b.lit_used = lit_sum;
-    b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
-    *esc_n = ne;
-    return ST_OK;
+    PNA_HD void step(uint32_t i) { advance(i); fetch(); emit(i); }
+    // after the last sequence: final checks, block totals, outgoing history, escapes
+    PNA_HD int32_t end() {
+        if (err || pos != 0) return ST_INVALID_DATA;
+        if (lit_sum > lit_regen) return ST_INVALID_DATA;
+        const uint64_t outsz = (uint64_t)lit_regen + match_sum;
+        if (outsz > BLOCK_MAX) return ST_INVALID_DATA;
+        ZBlock& b = *blk;
+        b.out_size = (uint32_t)outsz;
+        b.lit_used = lit_sum;
+        b.rep_out[0] = rep0; b.rep_out[1] = rep1; b.rep_out[2] = rep2;
+        b.esc_n = ne;
+        return ST_OK;
+    }
+};
+
+template <class Src>
+PNA_HD int32_t decode_sequences16_from(Src& src, const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll,
+                                       const Tab16& tof, const Tab16& tml, int lll, int lof, int lml,
+                                       const uint32_t* llb, const uint32_t* mlb, SeqRec* out, uint32_t* esc_n,
+                                       uint32_t* esc_idx, uint32_t* esc_ll, uint32_t* esc_ml) {
+    SeqStream<Src> st;
+    st.src = src;
+    const int32_t rc = st.begin(words, comp, b, tll, tof, tml, lll, lof, lml, llb, mlb, out);
+    if (rc != ST_OK) return rc;
+    for (uint32_t i = 0; i < st.nseq; i++) st.step(i);
+    const int32_t rc2 = st.end();
+    if (rc2 == ST_OK) {
+        *esc_n = b.esc_n;
+        for (uint32_t q = 0; q < b.esc_n && q < (uint32_t)SEQ_ESC_MAX; q++) { esc_idx[q] = b.esc_idx[q]; esc_ll[q] = b.esc_ll[q]; esc_ml[q] = b.esc_ml[q]; }
+    }
+    return rc2;
 }
 PNA_HD int32_t decode_sequences16(const uint32_t* words, const uint8_t* comp, ZBlock& b, const Tab16& tll,
                                   const Tab16& tof, const Tab16& tml, int lll, int lof, int lml,
