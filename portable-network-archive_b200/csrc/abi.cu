@@ -305,6 +305,8 @@ struct pna_plan {
     DevArr<int32_t> d_pj_ptr;
     DevArr<uint2> d_pj_cpos;
     DevArr<uint32_t> d_pj_flags;
+    DevArr<uint8_t> d_pj_tiles;        // one byte per 1024 pointers, two copies (ping-pong between rounds)
+    uint64_t pj_tile_stride = 0;
     uint32_t pj_max_blocks = 0;
     DevArr<uint64_t> d_lit_base, d_seq_base;
     DevArr<inf::InfStream> d_inf;
@@ -340,7 +342,7 @@ struct pna_plan {
         for (auto& t : d_tiles) t.release();
         d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_lz_units.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
-        d_walk.release(); d_pj_segs.release(); d_pj_ptr.release(); d_pj_cpos.release(); d_pj_flags.release();
+        d_walk.release(); d_pj_segs.release(); d_pj_ptr.release(); d_pj_cpos.release(); d_pj_flags.release(); d_pj_tiles.release();
         d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release();
         if (enc) enc::destroy(enc);
     }
@@ -1048,10 +1050,12 @@ static int launch_zstd_pj(pna_plan* P) {
         zs::pj_expand_kernel<<<dim3(zs::PJ_EXPAND_X, nb), 256, 0, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p,
                                                                                 P->d_lits.p, P->d_seqs.p, P->d_pj_cpos.p, P->d_out.p, P->d_pj_ptr.p);
         LAUNCHED();
-        zs::pj_chase_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p);
+        uint8_t* tiles[2] = {P->d_pj_tiles.p, P->d_pj_tiles.p + P->pj_tile_stride};
+        zs::pj_chase_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p, tiles[0]);
         LAUNCHED();
         for (int r = 0; r < zs::PJ_MAX_ROUNDS; r++) {
-            zs::pj_jump_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p, flags, r);
+            zs::pj_jump_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p, flags, r,
+                                                                   tiles[r & 1], tiles[(r + 1) & 1]);
             LAUNCHED();
         }
         zs::pj_gather_kernel<<<jump_grid, 256, 0, ctx->stream>>>(P->d_entries.p, P->d_ze.p, P->d_pj_segs.p, s, P->d_blocks.p, P->d_pj_ptr.p, flags, P->d_out.p);
@@ -1202,6 +1206,8 @@ static int decode_prepare(pna_plan* P) {
             CK(P->d_pj_ptr.reserve((size_t)P->pj_max_blocks * zs::BLOCK_MAX + 64));
             CK(P->d_pj_cpos.reserve((size_t)P->pj_max_blocks * zs::PJ_MAX_CHUNKS));
             CK(P->d_pj_flags.reserve(P->h_pj_segs.size() * zs::PJ_MAX_ROUNDS));
+            P->pj_tile_stride = align_up((uint64_t)P->pj_max_blocks * zs::BLOCK_MAX / 1024 + 64, 256);
+            CK(P->d_pj_tiles.reserve(2 * P->pj_tile_stride));
         }
         std::vector<uint32_t> unit_order;
         unit_order.reserve(nu);

@@ -411,7 +411,9 @@ void Archive::prepare(const ReadOptions& opt, int device) {
         if (st != PNA_OK) throw Error(st, "solid entry: key unavailable");
         d.raw_size_hint = UINT64_MAX;                                       // solid streams carry no size: the plan sizes itself
         pna_plan* plan = nullptr;
-        ck(L.ctx, pna_cuda_decode_plan_create(L.ctx, &d, 1, &plan), "solid plan");
+        // the SDAT bodies all lie inside the archive buffer: declared, so the tens of thousands of 32 KiB bodies of a large solid
+        // entry travel in a few copies instead of one cudaMemcpyAsync each
+        ck(L.ctx, pna_cuda_decode_plan_create_in_image(L.ctx, &d, 1, buf_, len_, nullptr, nullptr, nullptr, 0, &plan), "solid plan");
         in.plan = std::shared_ptr<pna_plan>(plan, [](pna_plan* p) { pna_cuda_plan_destroy(p); });
         ck(L.ctx, pna_cuda_decode_plan_run(plan), "solid decode");
         uint64_t dec_len = 0;
