@@ -10,6 +10,16 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 
+# The reference links zstd 1.5.7 (Cargo.lock: zstd-sys 2.0.14+zstd.1.5.7); the system libzstd of this image is 1.5.5, the
+# same image also carries 1.5.7 inside pillow.libs.  The oracle uses 1.5.7 when it is there (accept / reject behaviour on
+# malformed streams differs between the two: 1.5.6 started to reject non-zero reserved bits of the sequence modes byte).
+for _d in [p for p in sys.path if p.endswith("site-packages")] + [os.path.join(sys.prefix, "lib", "python%d.%d" % sys.version_info[:2], "site-packages")]:
+    _c = [f for f in (os.listdir(os.path.join(_d, "pillow.libs")) if os.path.isdir(os.path.join(_d, "pillow.libs")) else []) if f.startswith("libzstd") and "1.5.7" in f]
+    if _c:
+        os.environ.setdefault("PNA_ORACLE_LIBZSTD", os.path.join(_d, "pillow.libs", _c[0]))
+        break
+
+
 def pytest_addoption(parser):
     # development aid for a box without a GPU: run the kernels' logic under the fiber-based SIMT emulator of
     # tests/emu (test infrastructure; the package never loads it).  Parity evidence comes from `-m gpu` on a B200 only.

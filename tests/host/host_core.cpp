@@ -54,7 +54,7 @@ extern "C" uint32_t hc_crc_span(const uint8_t* img, uint64_t S, uint64_t E) {
 // ---- zstd: the kernels' phases run serially on the host (scan -> parse -> resolve -> entropy -> prefix -> LZ)
 #include "../../portable-network-archive_b200/csrc/zstd_core.cuh"
 #include <vector>
-extern "C" { int hc_site = 0; }
+extern "C" { int hc_site = 0; int hc_site_value() { return hc_site; } }
 extern "C" int hc_zstd_decode(const uint8_t* in, uint64_t len, uint8_t* out, uint64_t cap, uint64_t* out_len,
                               uint32_t* stats /* [nblocks, nseq, nlit] optional */) {
     using namespace pna::zs;

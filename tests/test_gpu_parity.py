@@ -180,7 +180,7 @@ def test_zstd_corruption_never_crashes_and_matches_when_accepted(ctx, oracle):
     plain = corpus.make_file(8, 60_000)
     c = oracle.compress(2, plain, 3)
     entries, refs = [], []
-    for _ in range(200):
+    for _ in range(400):
         b = bytearray(c)
         b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
         entries.append({"bodies": [bytes(b)], "compression": 2, "raw_size_hint": None})
@@ -189,13 +189,20 @@ def test_zstd_corruption_never_crashes_and_matches_when_accepted(ctx, oracle):
         except oracle.OracleError:
             refs.append(None)
     outs, st, _ = ctx.decode_batch(entries, caps=[len(plain) + 4096] * len(entries))
-    disagree = 0
+    # Against libzstd 1.5.7 (the reference's version; tests/conftest.py points the oracle at it) the only accept / reject
+    # difference is the documented one: a Huffman literal stream that over-reads its bitstream -- libzstd's BMI2 fast path
+    # emits garbage there, its portable path and the GPU decoder answer InvalidData (tests/test_host_cores.py pins the class).
+    is_157 = oracle.lib().pna_oracle_zstd_version() >= 10507
+    ours_only_rejects = 0
     for o, s, r in zip(outs, st, refs):
         if s == 0 and r is not None:
             assert o.tobytes() == r
-        elif (s == 0) != (r is not None):
-            disagree += 1
-    assert disagree <= 6
+        elif s == 0:
+            assert not is_157, "accepted a stream libzstd 1.5.7 rejects"
+        elif r is not None:
+            assert s == 1 or not is_157
+            ours_only_rejects += 1
+    assert ours_only_rejects <= (3 if is_157 else 6)
 
 
 # ------------------------------------------------------------------------------------------- golden archives

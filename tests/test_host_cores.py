@@ -83,11 +83,17 @@ def test_zstd_core_golden(hc, oracle, golden):
 
 
 def test_zstd_core_corruption_agrees_with_libzstd(hc, oracle):
+    """Single-bit corruptions of a level-3 frame: same bytes when both decoders accept, and the ONLY accept/reject difference
+    against libzstd 1.5.7 (the reference's version) is the one documented in DESIGN.md: a Huffman literal stream that over-reads
+    its bitstream.  libzstd's BMI2 fast path (x86-64 only) validates just the produced length there and emits garbage literals,
+    its portable path and this decoder answer corruption_detected / InvalidData -- so we may reject what libzstd-on-this-CPU
+    accepts, never the other way round, and rarely (measured 6 of 3000 flips, all of that class)."""
     rnd = random.Random(9)
     d = corpus.make_file(5, 60000)
     c = oracle.compress(2, d, 3)
-    disagree = 0
-    for _ in range(300):
+    is_157 = oracle.lib().pna_oracle_zstd_version() >= 10507
+    ours_only_rejects = 0
+    for _ in range(1000):
         b = bytearray(c)
         b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
         st, o = _dec(hc.hc_zstd_decode, bytes(b), len(d) + 4096)
@@ -98,9 +104,13 @@ def test_zstd_core_corruption_agrees_with_libzstd(hc, oracle):
             rst, ref = ex.status, None
         if st == 0 and rst == 0:
             assert o == ref           # both accept: bytes must be identical
-        elif (st == 0) != (rst == 0):
-            disagree += 1             # libzstd versions differ on a few malformed-but-decodable streams
-    assert disagree <= 6
+        elif st == 0:
+            assert not is_157, "accepted a stream libzstd 1.5.7 rejects"
+        elif rst == 0:
+            ours_only_rejects += 1
+            if is_157:
+                assert st == 1 and hc.hc_site_value() == 10, "a rejection outside the documented Huffman over-read class"
+    assert ours_only_rejects <= (10 if is_157 else 20)
 
 
 def test_inflate_core(hc, oracle, golden):
