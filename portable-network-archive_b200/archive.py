@@ -508,8 +508,15 @@ class Archive:
     def _emit(self, ty: bytes, data, crc: int | None = None):
         self._pending.append((ty, data, crc))
 
-    def add_entry(self, entry: "BuiltEntry"):
-        """Archive::add_entry (archive/write.rs:368) -> write_chunks_to (entry.rs:895-912)."""
+    def add_entry(self, entry):
+        """Archive::add_entry (archive/write.rs:368) -> write_chunks_to (entry.rs:895-912).  A freshly built entry brings
+        the CRCs of its data chunks from the encode kernels; an entry READ from another archive (NormalEntry / SolidEntry) is
+        re-serialised chunk by chunk in its wire order, every CRC recomputed by the finalize batch -- what makes
+        lib/tests/copy_entries.rs:15-21 byte exact."""
+        if isinstance(entry, _EntryBase):
+            for ch in entry.chunks:
+                self._emit(ch.ty, bytes(entry._body(ch)), None)
+            return
         for ty, data, crc in entry.chunks(self.max_chunk_size):
             self._emit(ty, data, crc)
 
