@@ -93,7 +93,12 @@ __device__ __forceinline__ void fill_codes(Code* ix, uint32_t n, uint32_t code) 
         if (n && (reinterpret_cast<uintptr_t>(ix) & 2)) { *ix++ = (Code)code; code++; n--; }
         uint32_t pair = code | ((code + 1) << 16);         // no carry between the halves: codes stay below 2^16
         uint32_t* p32 = reinterpret_cast<uint32_t*>(ix);
-        for (uint32_t q = 0; q + 2 <= n; q += 2) { *p32++ = pair; pair += 0x00020002u; }
+        uint32_t q = 0;
+        if (n >= 2 && (reinterpret_cast<uintptr_t>(p32) & 4)) { *p32++ = pair; pair += 0x00020002u; q = 2; }   // up to 8-byte alignment
+        uint2* p64 = reinterpret_cast<uint2*>(p32);
+        for (; q + 4 <= n; q += 4) { *p64++ = make_uint2(pair, pair + 0x00020002u); pair += 0x00040004u; }      // four codes per store
+        p32 = reinterpret_cast<uint32_t*>(p64);
+        if (q + 2 <= n) { *p32 = pair; }
         if (n & 1) ix[n - 1] = (Code)(code + n - 1);
     } else {   // 32-bit codes: two per 64-bit store once ix is 8-byte aligned
         if (n && (reinterpret_cast<uintptr_t>(ix) & 4)) { *ix++ = (Code)code; code++; n--; }
@@ -517,16 +522,20 @@ __global__ void __launch_bounds__(C::T, C::CTAS) zstd_lz_kernel(const uint8_t* _
                         if (4 * G + 2 < g0 || 4 * G + 2 >= lim) c2 = self + 2;
                         if (4 * G + 3 < g0 || 4 * G + 3 >= lim) c3 = self + 3;
                     }
+                    // The chase reads codes that other threads may be replacing at the same moment (path compression below):
+                    // both sides use VOLATILE accesses of the code's own size, so a reader gets the old or the new code, never a
+                    // torn one, and either leads to the same byte (codes strictly decrease along a chain).
+                    volatile Code* const vidx = idx;
                     while (!((c0 & c1 & c2 & c3) & FL)) {
-                        if (!(c0 & FL)) c0 = idx[c0];
-                        if (!(c1 & FL)) c1 = idx[c1];
-                        if (!(c2 & FL)) c2 = idx[c2];
-                        if (!(c3 & FL)) c3 = idx[c3];
+                        if (!(c0 & FL)) c0 = vidx[c0];
+                        if (!(c1 & FL)) c1 = vidx[c1];
+                        if (!(c2 & FL)) c2 = vidx[c2];
+                        if (!(c3 & FL)) c3 = vidx[c3];
                     }
-                    // path compression: later bytes of the step that chase into these stop after one hop (a racing reader
-                    // sees the old or the new code; both lead to the same byte)
-                    if constexpr (sizeof(Code) == 2) *reinterpret_cast<uint2*>(idx + 4 * G) = make_uint2(c0 | (c1 << 16), c2 | (c3 << 16));
-                    else *reinterpret_cast<uint4*>(idx + 4 * G) = make_uint4(c0, c1, c2, c3);
+#ifndef PNA_LZ_NO_PATH_COMPRESSION
+                    // path compression: later bytes of the step that chase into these stop after one hop
+                    vidx[4 * G + 0] = (Code)c0; vidx[4 * G + 1] = (Code)c1; vidx[4 * G + 2] = (Code)c2; vidx[4 * G + 3] = (Code)c3;
+#endif
                     const uint32_t v0 = lz_smem[c0 & M], v1 = lz_smem[c1 & M], v2 = lz_smem[c2 & M], v3 = lz_smem[c3 & M];
                     *reinterpret_cast<uint32_t*>(win + a0 + 4 * G) = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
                 }
