@@ -1,0 +1,362 @@
+// lzma_core.cuh -- .xz container + LZMA2 decode of ONE stream by one thread (PNA_HD: the same code runs in xz_decode_kernel
+// and, compiled with g++, in the CPU test tier).  Reference: decompress_reader's XZ arm, lib/src/entry/read.rs:183
+// (liblzma_rs bufread::XzDecoder::new = one .xz stream, integrity check verified); writer lib/src/compress/xz.rs.
+//
+// The format is bit-serial through an adaptive range coder (every decoded bit updates the probability the next bit of the
+// same context is decoded with), so the parallelism is ACROSS streams: one lane per entry, probabilities (28 KB per stream at
+// the format's lc + lp <= 4 limit) in a per-stream global arena, the dictionary is the output itself.  Restated from the
+// public format descriptions (xz-file-format-1.1.0, the LZMA SDK's lzma-specification.txt).
+#pragma once
+#include "common.cuh"
+
+namespace pna {
+namespace xz {
+
+constexpr uint32_t LZMA_PROBS_FIXED = 12 * 16 + 12 * 4 + 12 * 16 + 4 * 64 + 115 + 16 + 2 * (2 + 16 * 8 + 16 * 8 + 256);   // everything but literals
+constexpr uint32_t LZMA_PROBS_MAX = LZMA_PROBS_FIXED + (0x300u << 4);                                                         // lc + lp <= 4
+constexpr uint32_t PROB_INIT = 1024;
+
+struct Probs {   // offsets into the per-stream probability arena
+    static constexpr uint32_t IS_MATCH = 0, IS_REP = IS_MATCH + 12 * 16, IS_REP_G0 = IS_REP + 12, IS_REP_G1 = IS_REP_G0 + 12,
+                              IS_REP_G2 = IS_REP_G1 + 12, IS_REP0_LONG = IS_REP_G2 + 12, POS_SLOT = IS_REP0_LONG + 12 * 16,
+                              POS_SPECIAL = POS_SLOT + 4 * 64, POS_ALIGN = POS_SPECIAL + 115, LEN_MATCH = POS_ALIGN + 16,
+                              LEN_REP = LEN_MATCH + (2 + 16 * 8 + 16 * 8 + 256), LITERAL = LEN_REP + (2 + 16 * 8 + 16 * 8 + 256);
+    static_assert(LITERAL == LZMA_PROBS_FIXED, "layout");
+};
+
+struct RangeDec {
+    uint32_t range, code;
+    const uint8_t* p;
+    const uint8_t* end;
+    bool overrun;
+    PNA_HD void normalize() {
+        if (range < (1u << 24)) {
+            range <<= 8;
+            uint32_t b = 0;
+            if (p < end) b = *p++; else overrun = true;
+            code = (code << 8) | b;
+        }
+    }
+    PNA_HD uint32_t bit(uint16_t* prob) {
+        normalize();
+        const uint32_t v = *prob, bound = (range >> 11) * v;
+        if (code < bound) { range = bound; *prob = (uint16_t)(v + ((2048u - v) >> 5)); return 0; }
+        range -= bound; code -= bound; *prob = (uint16_t)(v - (v >> 5));
+        return 1;
+    }
+    PNA_HD uint32_t tree(uint16_t* probs, int nbits) {
+        uint32_t m = 1;
+        for (int i = 0; i < nbits; i++) m = (m << 1) | bit(probs + m);
+        return m - (1u << nbits);
+    }
+    PNA_HD uint32_t tree_reverse(uint16_t* probs, int nbits) {
+        uint32_t m = 1, sym = 0;
+        for (int i = 0; i < nbits; i++) { const uint32_t b = bit(probs + m); m = (m << 1) | b; sym |= b << i; }
+        return sym;
+    }
+    PNA_HD uint32_t direct(int nbits) {
+        uint32_t r = 0;
+        for (int i = 0; i < nbits; i++) {
+            normalize();
+            range >>= 1;
+            code -= range;
+            const uint32_t t = 0u - (code >> 31);
+            code += range & t;
+            r = (r << 1) + (t + 1);
+        }
+        return r;
+    }
+};
+
+PNA_HD uint32_t len_decode(RangeDec& rc, uint16_t* lc, uint32_t pos_state) {
+    if (!rc.bit(lc + 0)) return 2 + rc.tree(lc + 2 + pos_state * 8, 3);
+    if (!rc.bit(lc + 1)) return 10 + rc.tree(lc + 2 + 16 * 8 + pos_state * 8, 3);
+    return 18 + rc.tree(lc + 2 + 2 * 16 * 8, 8);
+}
+
+struct LzmaState {
+    uint32_t state, rep0, rep1, rep2, rep3, lc, lp, pb;
+    bool need_props, need_dict_reset;
+};
+
+// One LZMA chunk: `usize` bytes into out[pos ..), from exactly `csize` compressed bytes.  dict_start = first byte the
+// dictionary reaches back to (bytes since the last dictionary reset).  Returns ST_OK / ST_INVALID_DATA.
+PNA_HD int32_t lzma_chunk(LzmaState& S, uint16_t* probs, const uint8_t* in, uint32_t csize, uint8_t* out, uint64_t pos, uint32_t usize,
+                          uint64_t dict_start) {
+    if (csize < 5 || in[0] != 0) return ST_INVALID_DATA;
+    RangeDec rc;
+    rc.range = 0xFFFFFFFFu;
+    rc.code = ((uint32_t)in[1] << 24) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 8) | in[4];
+    rc.p = in + 5; rc.end = in + csize; rc.overrun = false;
+    const uint64_t end = pos + usize;
+    const uint32_t pb_mask = (1u << S.pb) - 1u, lp_mask = (1u << S.lp) - 1u;
+    uint32_t state = S.state, rep0 = S.rep0, rep1 = S.rep1, rep2 = S.rep2, rep3 = S.rep3;
+    while (pos < end) {
+        const uint32_t pos_state = (uint32_t)(pos - dict_start) & pb_mask;
+        if (!rc.bit(probs + Probs::IS_MATCH + state * 16 + pos_state)) {
+            const uint32_t prev = pos > dict_start ? out[pos - 1] : 0u;
+            uint16_t* lp = probs + Probs::LITERAL + 0x300u * ((((uint32_t)(pos - dict_start) & lp_mask) << S.lc) + (prev >> (8 - S.lc)));
+            uint32_t sym = 1;
+            if (state < 7) {
+                do sym = (sym << 1) | rc.bit(lp + sym); while (sym < 0x100);
+            } else {
+                if ((uint64_t)rep0 >= pos - dict_start) return ST_INVALID_DATA;
+                uint32_t match_byte = out[pos - rep0 - 1], offs = 0x100;
+                do {
+                    match_byte <<= 1;
+                    const uint32_t match_bit = match_byte & offs;
+                    const uint32_t b = rc.bit(lp + offs + match_bit + sym);
+                    sym = (sym << 1) | b;
+                    offs &= b ? match_bit : ~match_bit;
+                } while (sym < 0x100);
+            }
+            out[pos++] = (uint8_t)sym;
+            state = state < 4 ? 0 : state < 10 ? state - 3 : state - 6;
+            if (rc.overrun) return ST_INVALID_DATA;
+            continue;
+        }
+        uint32_t len;
+        if (!rc.bit(probs + Probs::IS_REP + state)) {
+            rep3 = rep2; rep2 = rep1; rep1 = rep0;
+            len = len_decode(rc, probs + Probs::LEN_MATCH, pos_state);
+            state = state < 7 ? 7 : 10;
+            const uint32_t dist_state = len < 6 ? len - 2 : 3;
+            const uint32_t slot = rc.tree(probs + Probs::POS_SLOT + dist_state * 64, 6);
+            if (slot < 4) rep0 = slot;
+            else {
+                const int nb = (int)(slot >> 1) - 1;
+                rep0 = (2u | (slot & 1u)) << nb;
+                if (slot < 14) rep0 += rc.tree_reverse(probs + Probs::POS_SPECIAL + rep0 - slot - 1, nb);
+                else { rep0 += rc.direct(nb - 4) << 4; rep0 += rc.tree_reverse(probs + Probs::POS_ALIGN, 4); }
+            }
+            if (rep0 == 0xFFFFFFFFu) return ST_INVALID_DATA;   // end-of-payload marker: not allowed inside LZMA2
+        } else {
+            if (!rc.bit(probs + Probs::IS_REP_G0 + state)) {
+                if (!rc.bit(probs + Probs::IS_REP0_LONG + state * 16 + pos_state)) {
+                    if ((uint64_t)rep0 >= pos - dict_start) return ST_INVALID_DATA;
+                    state = state < 7 ? 9 : 11;
+                    out[pos] = out[pos - rep0 - 1];
+                    pos++;
+                    if (rc.overrun) return ST_INVALID_DATA;
+                    continue;
+                }
+            } else {
+                uint32_t dist;
+                if (!rc.bit(probs + Probs::IS_REP_G1 + state)) dist = rep1;
+                else {
+                    if (!rc.bit(probs + Probs::IS_REP_G2 + state)) dist = rep2;
+                    else { dist = rep3; rep3 = rep2; }
+                    rep2 = rep1;
+                }
+                rep1 = rep0; rep0 = dist;
+            }
+            len = len_decode(rc, probs + Probs::LEN_REP, pos_state);
+            state = state < 7 ? 8 : 11;
+        }
+        if (rc.overrun || (uint64_t)rep0 >= pos - dict_start || len > end - pos) return ST_INVALID_DATA;
+        const uint64_t src = pos - rep0 - 1;
+        for (uint32_t i = 0; i < len; i++) out[pos + i] = out[src + i];
+        pos += len;
+    }
+    rc.normalize();
+    if (rc.overrun || rc.p != rc.end || rc.code != 0) return ST_INVALID_DATA;   // the chunk must end exactly here, coder flushed
+    S.state = state; S.rep0 = rep0; S.rep1 = rep1; S.rep2 = rep2; S.rep3 = rep3;
+    return ST_OK;
+}
+
+PNA_HD void lzma_reset_probs(uint16_t* probs, uint32_t lc, uint32_t lp) {
+    const uint32_t n = LZMA_PROBS_FIXED + (0x300u << (lc + lp));
+    for (uint32_t i = 0; i < n; i++) probs[i] = (uint16_t)PROB_INIT;
+}
+
+// multibyte integer of the .xz format (up to 9 bytes, 63 bits); returns bytes consumed, 0 on error
+PNA_HD uint32_t xz_vli(const uint8_t* p, uint64_t avail, uint64_t* v) {
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < 9 && i < avail; i++) {
+        const uint8_t b = p[i];
+        r |= (uint64_t)(b & 0x7F) << (7 * i);
+        if (!(b & 0x80)) { if (b == 0 && i > 0) return 0; *v = r; return i + 1; }
+    }
+    return 0;
+}
+PNA_HD uint32_t xz_crc32(const uint8_t* p, uint64_t n) {   // small header fields only
+    uint32_t c = 0xFFFFFFFFu;
+    for (uint64_t i = 0; i < n; i++) {
+        c ^= p[i];
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+    }
+    return ~c;
+}
+// CRC-64/XZ (ECMA-182 reflected) of the decoded bytes: nibble table, 16 entries built on the fly
+PNA_HD uint64_t xz_crc64(const uint8_t* p, uint64_t n) {
+    uint64_t t[16];
+    for (uint32_t i = 0; i < 16; i++) {
+        uint64_t c = i;
+        for (int k = 0; k < 4; k++) c = (c >> 1) ^ (0xC96C5795D7870F42ull & (0ull - (c & 1ull)));
+        t[i] = c;
+    }
+    uint64_t c = ~0ull;
+    for (uint64_t i = 0; i < n; i++) {
+        c ^= p[i];
+        c = (c >> 4) ^ t[c & 15];
+        c = (c >> 4) ^ t[c & 15];
+    }
+    return ~c;
+}
+
+// Decoded size of the FIRST .xz stream of [in, in + n) from its index (for the sizing pass); ST_OK or the failure class.
+// The stream's end is found by walking the blocks' headers and the index (sizes are recorded there), never by decoding.
+PNA_HD int32_t xz_stream_size(const uint8_t* in, uint64_t n, uint64_t* out_len) {
+    *out_len = 0;
+    if (n < 12) return ST_UNEXPECTED_EOF;
+    if (!(in[0] == 0xFD && in[1] == '7' && in[2] == 'z' && in[3] == 'X' && in[4] == 'Z' && in[5] == 0)) return ST_INVALID_DATA;
+    // Sizes are not in front of the data unless the encoder put them into the block header; the index behind the blocks has
+    // them.  Walk: block header -> (compressed size unknown without decoding) ... so use the footer when the stream is the whole
+    // input (what the reference writes: one stream per entry), else fail over to "unknown".
+    if (n < 24 || (n & 3)) return ST_UNEXPECTED_EOF;
+    const uint8_t* f = in + n - 12;
+    if (!(f[10] == 'Y' && f[11] == 'Z')) return ST_UNEXPECTED_EOF;       // truncated (or trailing bytes): the decode pass decides
+    const uint64_t isize = ((uint64_t)(load_le32(f + 4)) + 1) * 4;
+    if (isize + 24 > n) return ST_INVALID_DATA;
+    const uint8_t* ix = f - isize;
+    if (ix[0] != 0) return ST_INVALID_DATA;
+    uint64_t nrec = 0, at = 1, total = 0;
+    uint32_t k = xz_vli(ix + at, isize - at, &nrec);
+    if (!k) return ST_INVALID_DATA;
+    at += k;
+    for (uint64_t r = 0; r < nrec; r++) {
+        uint64_t us = 0, un = 0;
+        k = xz_vli(ix + at, isize - at, &us); if (!k) return ST_INVALID_DATA; at += k;
+        k = xz_vli(ix + at, isize - at, &un); if (!k) return ST_INVALID_DATA; at += k;
+        total += un;
+        if (total > ((uint64_t)1 << 62)) return ST_INVALID_DATA;
+    }
+    *out_len = total;
+    return ST_OK;
+}
+
+// Decode the first .xz stream of [in, in + n) into out[0, cap).  probs: LZMA_PROBS_MAX entries of scratch.
+// ST_OK (*out_len = decoded bytes), ST_NOSPACE (*out_len = bytes needed when the index tells, else cap + 1),
+// ST_UNEXPECTED_EOF (input ends inside the stream: liblzma_rs "premature eof"), ST_INVALID_DATA (everything liblzma calls
+// LZMA_DATA_ERROR / LZMA_FORMAT_ERROR), ST_UNSUPPORTED (filters other than LZMA2, unknown check types: LZMA_OPTIONS_ERROR).
+PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, uint16_t* probs) {
+    *out_len = 0;
+    if (n < 12) return ST_UNEXPECTED_EOF;
+    if (!(in[0] == 0xFD && in[1] == '7' && in[2] == 'z' && in[3] == 'X' && in[4] == 'Z' && in[5] == 0)) return ST_INVALID_DATA;
+    if (in[6] != 0 || (in[7] & 0xF0)) return ST_UNSUPPORTED;
+    if (xz_crc32(in + 6, 2) != load_le32(in + 8)) return ST_INVALID_DATA;
+    const uint32_t check = in[7] & 15;
+    const uint32_t check_size = check == 0 ? 0 : check == 1 ? 4 : check == 4 ? 8 : check == 10 ? 32 : 0xFFFFFFFFu;
+    if (check_size == 0xFFFFFFFFu) return ST_UNSUPPORTED;
+    uint64_t pos = 12, op = 0;
+    uint64_t n_blocks = 0;
+    for (;;) {
+        if (pos >= n) return ST_UNEXPECTED_EOF;
+        if (in[pos] == 0) break;                                            // index indicator
+        // ---- block header
+        const uint64_t hsize = ((uint64_t)in[pos] + 1) * 4;
+        if (pos + hsize > n) return ST_UNEXPECTED_EOF;
+        if (xz_crc32(in + pos, hsize - 4) != load_le32(in + pos + hsize - 4)) return ST_INVALID_DATA;
+        const uint8_t bflags = in[pos + 1];
+        if (bflags & 0x3C) return ST_UNSUPPORTED;
+        if ((bflags & 3) != 0) return ST_UNSUPPORTED;                       // exactly one filter: LZMA2 (what the reference writes)
+        uint64_t at = pos + 2, hend = pos + hsize - 4, csz = ~0ull, usz = ~0ull;
+        uint32_t k;
+        if (bflags & 0x40) { k = xz_vli(in + at, hend - at, &csz); if (!k) return ST_INVALID_DATA; at += k; }
+        if (bflags & 0x80) { k = xz_vli(in + at, hend - at, &usz); if (!k) return ST_INVALID_DATA; at += k; }
+        uint64_t fid = 0, psz = 0;
+        k = xz_vli(in + at, hend - at, &fid); if (!k) return ST_INVALID_DATA; at += k;
+        k = xz_vli(in + at, hend - at, &psz); if (!k) return ST_INVALID_DATA; at += k;
+        if (fid != 0x21 || psz != 1 || at >= hend) return ST_UNSUPPORTED;
+        if (in[at] > 40) return ST_UNSUPPORTED;                             // dictionary size code
+        at += 1;
+        for (; at < hend; at++) if (in[at] != 0) return ST_UNSUPPORTED;     // header padding must be zero
+        pos += hsize;
+        // ---- LZMA2 chunks
+        const uint64_t block_in = pos, block_out = op;
+        LzmaState S;
+        S.state = 0; S.rep0 = S.rep1 = S.rep2 = S.rep3 = 0; S.lc = 3; S.lp = 0; S.pb = 2;
+        S.need_props = true; S.need_dict_reset = true;
+        uint64_t dict_start = op;
+        for (;;) {
+            if (pos >= n) return ST_UNEXPECTED_EOF;
+            const uint8_t ctl = in[pos++];
+            if (ctl == 0) break;
+            if (ctl == 1 || ctl >= 0xE0) { S.need_dict_reset = false; S.need_props = true; dict_start = op; }
+            else if (S.need_dict_reset) return ST_INVALID_DATA;
+            if (ctl >= 0x80) {
+                if (pos + 4 > n) return ST_UNEXPECTED_EOF;
+                const uint32_t usize = (((uint32_t)(ctl & 0x1F) << 16) | ((uint32_t)in[pos] << 8) | in[pos + 1]) + 1;
+                const uint32_t csize = (((uint32_t)in[pos + 2] << 8) | in[pos + 3]) + 1;
+                pos += 4;
+                const uint32_t mode = (ctl >> 5) & 3;
+                if (mode >= 2) {
+                    if (pos >= n) return ST_UNEXPECTED_EOF;
+                    uint32_t props = in[pos++];
+                    if (props > (4 * 5 + 4) * 9 + 8) return ST_INVALID_DATA;
+                    S.pb = props / 45; props -= S.pb * 45;
+                    S.lp = props / 9; S.lc = props - S.lp * 9;
+                    if (S.lc + S.lp > 4) return ST_INVALID_DATA;
+                    S.need_props = false;
+                } else if (S.need_props) return ST_INVALID_DATA;
+                if (mode >= 1) { lzma_reset_probs(probs, S.lc, S.lp); S.state = 0; S.rep0 = S.rep1 = S.rep2 = S.rep3 = 0; }
+                if (pos + csize > n) return ST_UNEXPECTED_EOF;
+                if (op + usize > cap) { uint64_t need = 0; if (xz_stream_size(in, n, &need) == ST_OK) *out_len = need; else *out_len = cap + 1; return ST_NOSPACE; }
+                const int32_t st = lzma_chunk(S, probs, in + pos, csize, out, op, usize, dict_start);
+                if (st != ST_OK) return st;
+                pos += csize; op += usize;
+            } else if (ctl == 1 || ctl == 2) {
+                if (pos + 2 > n) return ST_UNEXPECTED_EOF;
+                const uint32_t usize = (((uint32_t)in[pos] << 8) | in[pos + 1]) + 1;
+                pos += 2;
+                if (pos + usize > n) return ST_UNEXPECTED_EOF;
+                if (op + usize > cap) { uint64_t need = 0; if (xz_stream_size(in, n, &need) == ST_OK) *out_len = need; else *out_len = cap + 1; return ST_NOSPACE; }
+                for (uint32_t i = 0; i < usize; i++) out[op + i] = in[pos + i];
+                pos += usize; op += usize;
+            } else return ST_INVALID_DATA;
+        }
+        if (csz != ~0ull && csz != pos - block_in) return ST_INVALID_DATA;
+        if (usz != ~0ull && usz != op - block_out) return ST_INVALID_DATA;
+        // ---- block padding + check
+        while ((pos - block_in) & 3) { if (pos >= n) return ST_UNEXPECTED_EOF; if (in[pos++] != 0) return ST_INVALID_DATA; }
+        if (pos + check_size > n) return ST_UNEXPECTED_EOF;
+        if (check == 1) { if (xz_crc32(out + block_out, op - block_out) != load_le32(in + pos)) return ST_INVALID_DATA; }
+        else if (check == 4) {
+            const uint64_t want = (uint64_t)load_le32(in + pos) | ((uint64_t)load_le32(in + pos + 4) << 32);
+            if (xz_crc64(out + block_out, op - block_out) != want) return ST_INVALID_DATA;
+        }   // SHA-256 (check 10) is carried but not verified here; none: nothing to verify
+        pos += check_size;
+        n_blocks++;
+    }
+    // ---- index + footer: present, consistent with what was decoded
+    {
+        const uint64_t ix = pos;
+        uint64_t nrec = 0, total = 0;
+        uint64_t at = ix + 1;
+        uint32_t k = xz_vli(in + at, n - at, &nrec);
+        if (!k) return at >= n ? ST_UNEXPECTED_EOF : ST_INVALID_DATA;
+        at += k;
+        if (nrec != n_blocks) return ST_INVALID_DATA;
+        for (uint64_t r = 0; r < nrec; r++) {
+            uint64_t us = 0, un = 0;
+            k = xz_vli(in + at, at < n ? n - at : 0, &us); if (!k) return at >= n ? ST_UNEXPECTED_EOF : ST_INVALID_DATA; at += k;
+            k = xz_vli(in + at, at < n ? n - at : 0, &un); if (!k) return at >= n ? ST_UNEXPECTED_EOF : ST_INVALID_DATA; at += k;
+            total += un;
+        }
+        if (total != op) return ST_INVALID_DATA;
+        while ((at - ix) & 3) { if (at >= n) return ST_UNEXPECTED_EOF; if (in[at++] != 0) return ST_INVALID_DATA; }
+        if (at + 4 > n) return ST_UNEXPECTED_EOF;
+        if (xz_crc32(in + ix, at - ix) != load_le32(in + at)) return ST_INVALID_DATA;
+        at += 4;
+        if (at + 12 > n) return ST_UNEXPECTED_EOF;
+        const uint8_t* f = in + at;
+        if (xz_crc32(f + 4, 6) != load_le32(f)) return ST_INVALID_DATA;
+        if (((uint64_t)load_le32(f + 4) + 1) * 4 != at - ix) return ST_INVALID_DATA;
+        if (f[8] != in[6] || f[9] != in[7] || f[10] != 'Y' || f[11] != 'Z') return ST_INVALID_DATA;
+    }
+    *out_len = op;
+    return ST_OK;
+}
+
+}  // namespace xz
+}  // namespace pna

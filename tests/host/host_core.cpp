@@ -324,3 +324,11 @@ extern "C" void hc_hkdf_sha256(const uint8_t* ikm, uint64_t n_ikm, const uint8_t
     pna::aead::hkdf_sha256(ikm, n_ikm, salt, n_salt, info, n_info, okm);
 }
 extern "C" void hc_sha256(const uint8_t* d, uint64_t n, uint8_t* out) { pna::aead::sha256(d, n, nullptr, 0, out); }
+
+// ---- xz: the .xz container + LZMA2 decoder the kernel runs one lane per stream
+#include "../../portable-network-archive_b200/csrc/lzma_core.cuh"
+extern "C" int hc_xz_decode(const uint8_t* in, uint64_t len, uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* /*stats*/) {
+    std::vector<uint16_t> probs(pna::xz::LZMA_PROBS_MAX);
+    return pna::xz::xz_decode(in, len, out, cap, out_len, probs.data());
+}
+extern "C" int hc_xz_size(const uint8_t* in, uint64_t len, uint64_t* out_len) { return pna::xz::xz_stream_size(in, len, out_len); }

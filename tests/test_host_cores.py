@@ -20,6 +20,8 @@ def hc(built):
     L.hc_zstd_decode.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
     L.hc_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.hc_ecb.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p]
+    L.hc_xz_decode.argtypes = L.hc_zstd_decode.argtypes
+    L.hc_xz_size.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     return L
 
 
@@ -192,3 +194,52 @@ def test_gcm_tile_algorithm_and_key_schedule(hc, oracle):
         ikm, salt, info, out = os.urandom(32), os.urandom(ns), os.urandom(88), C.create_string_buffer(32)
         hc.hc_hkdf_sha256(ikm, 32, salt, ns, info, 88, out)
         assert out.raw == oracle.hkdf_sha256(ikm, salt, info)
+
+
+def test_xz_core(hc, golden, oracle):
+    """.xz container + LZMA2 (decompress_reader's XZ arm, lib/src/entry/read.rs:183) against liblzma itself (Python's lzma module
+    is the C library the reference links through liblzma-sys): presets, check types, filters' property sets, uncompressed
+    chunks, sizing, truncation and corruption classes, and the reference's xz fixtures."""
+    import lzma
+    rnd = random.Random(3)
+    cases = [b"", b"a", b"hello xz " * 3, corpus.make_file(1, 5000), corpus.make_file(2, 300_000), os.urandom(70_000),
+             bytes(200_000), corpus.make_file(3, 2_500_000)]
+    for d in cases:
+        for preset, check in ((6, lzma.CHECK_CRC64), (0, lzma.CHECK_CRC32), (9 | lzma.PRESET_EXTREME, lzma.CHECK_NONE), (3, lzma.CHECK_SHA256)):
+            c = lzma.compress(d, format=lzma.FORMAT_XZ, check=check, preset=preset)
+            st, o = _dec(hc.hc_xz_decode, c, len(d))
+            assert st == 0 and o == d, (len(d), preset, check, st)
+            n = C.c_uint64(0)
+            assert hc.hc_xz_size(c, len(c), C.byref(n)) == 0 and n.value == len(d)
+            if d:
+                assert _dec(hc.hc_xz_decode, c, len(d) - 1) == (5, len(d))          # NOSPACE + the length from the index
+    # other literal / position context settings than the presets use
+    d = corpus.make_file(9, 120_000)
+    for lc, lp, pb in ((0, 0, 0), (4, 0, 2), (0, 4, 4), (2, 2, 1), (3, 1, 3)):
+        flt = [{"id": lzma.FILTER_LZMA2, "preset": 4, "lc": lc, "lp": lp, "pb": pb, "dict_size": 1 << 16}]
+        c = lzma.compress(d, format=lzma.FORMAT_XZ, filters=flt)
+        assert _dec(hc.hc_xz_decode, c, len(d)) == (0, d), (lc, lp, pb)
+    # truncation -> UnexpectedEof ("premature eof"), bit flips -> InvalidData or, when liblzma still accepts, the same bytes
+    c = lzma.compress(d, preset=6)
+    for cut in (0, 5, 11, 12, 13, 30, len(c) // 2, len(c) - 13, len(c) - 1):
+        assert _dec(hc.hc_xz_decode, c[:cut], len(d))[0] == 2, cut
+    for _ in range(300):
+        b = bytearray(c)
+        b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        st, o = _dec(hc.hc_xz_decode, bytes(b), len(d) + 4096)
+        try:
+            ref = lzma.LZMADecompressor(format=lzma.FORMAT_XZ).decompress(bytes(b))
+            ok = True
+        except lzma.LZMAError:
+            ok = False
+        assert (st == 0) == ok, (st, ok)
+        if ok:
+            assert o == ref
+    # the reference's own xz fixtures
+    for name in ("xz.pna", "solid_xz.pna"):
+        if name not in golden["archives"]:
+            continue
+        buf = open(os.path.join(golden["dir"], golden["archives"][name]["file"]), "rb").read()
+        for e in oracle.read_archive(buf):
+            ref = lzma.decompress(e.stream)
+            assert _dec(hc.hc_xz_decode, e.stream, len(ref)) == (0, ref), (name, e.name)
