@@ -40,7 +40,7 @@ enum {
     PNA_E_INVALID_DATA = 1,   /* "broken chunk" format/chunk.rs:18; bad PKCS#7 cipher/block/read.rs:101; corrupt zstd */
     PNA_E_UNEXPECTED_EOF = 2, /* partial CBC block block/read.rs:90; stream shorter than IV entry/read.rs:80; truncated zstd frame */
     PNA_E_INVALID_INPUT = 3,  /* "corrupt deflate stream" (flate2 zio); bad key length stream/read.rs:27 */
-    PNA_E_UNSUPPORTED = 4,    /* xz / unknown codes entry/read.rs:152-163,184-187 */
+    PNA_E_UNSUPPORTED = 4,    /* unknown codes entry/read.rs:152-163,184-187; xz on the ENCODE side */
     PNA_E_NOSPACE = 5,        /* out.cap too small; out.len = required size (two-pass sizing contract) */
     PNA_E_OOM = 6,            /* util/io.rs:19 */
     PNA_E_INTERNAL = 7,

@@ -152,7 +152,28 @@ def ecb(encryption: int, encrypt: bool, key: bytes, data: bytes) -> bytes:
     return out.raw[:len(data) & ~15]
 
 
+def _xz_decompress(data: bytes, cap: int | None = None) -> bytes:
+    """Compression::XZ (entry/read.rs:182: liblzma::bufread::XzDecoder::new -- ONE stream, whatever follows it is not read).
+    Python's lzma module is liblzma, the C library the reference links through liblzma-sys, so this arm is the reference's own
+    decoder rather than a restatement.  Error classes as liblzma-rs maps them: a stream that ends early is "premature eof"
+    (UnexpectedEof), LZMA_OPTIONS_ERROR is Unsupported, every other liblzma error InvalidData."""
+    import lzma
+    d = lzma.LZMADecompressor(format=lzma.FORMAT_XZ)
+    try:
+        out = d.decompress(data)
+    except lzma.LZMAError as e:
+        msg = str(e).lower()
+        raise OracleError(UNSUPPORTED if ("unsupported" in msg or "invalid or unsupported options" in msg) else INVALID_DATA, f"xz: {e}")
+    if not d.eof:
+        raise OracleError(UNEXPECTED_EOF, "xz: premature eof")
+    if cap is not None and len(out) > cap:
+        raise OracleError(NOSPACE, "xz")
+    return out
+
+
 def decompress(compression: int, data: bytes, cap: int | None = None) -> bytes:
+    if compression == 4:
+        return _xz_decompress(data, cap)
     n = C.c_size_t(0)
     if cap is None:
         rc = lib().pna_oracle_decompress(compression, data, len(data), None, 0, C.byref(n))
@@ -180,6 +201,8 @@ def decode_stream(stream: bytes, compression: int, encryption: int, cipher_mode:
                   cap: int | None = None) -> bytes:
     """NormalEntry::reader (entry.rs:1150) over the concatenated FDAT bodies."""
     key = key or bytes(32)
+    if compression == 4:   # decrypt through the C oracle (as a stored stream), then liblzma
+        return _xz_decompress(decode_stream(stream, 0, encryption, cipher_mode, key), cap)
     n = C.c_size_t(0)
     if cap is None:
         rc = lib().pna_oracle_decode_stream(stream, len(stream), compression, encryption, cipher_mode, key, None, 0,
@@ -200,6 +223,10 @@ def encode_stream(plain: bytes, compression: int, level: int, encryption: int, c
     """FileEntryBuilder data_writer (builder.rs:45) -> IV || cipher(compress(plain))."""
     key = key or bytes(32)
     iv = iv or bytes(16)
+    if compression == 4:   # XzEncoder::new(writer, level) (entry/write.rs:263): liblzma's easy encoder, CRC64 check; default preset 6
+        import lzma
+        return encode_stream(lzma.compress(plain, format=lzma.FORMAT_XZ, preset=6 if level < 0 else level), 0, -1, encryption,
+                             cipher_mode, key, iv)
     cap = lib().pna_oracle_encode_bound(compression, len(plain))
     out = C.create_string_buffer(cap)
     n = C.c_size_t(0)

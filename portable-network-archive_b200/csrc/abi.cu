@@ -22,6 +22,7 @@
 #include "kernels_gcm.cuh"
 #include "aead_host.hpp"
 #include "kernels_inflate.cuh"
+#include "kernels_xz.cuh"
 #include "kernels_zstd.cuh"
 #include "kernels_encode.cuh"
 
@@ -269,7 +270,7 @@ struct pna_plan {
     std::vector<Segment> h_segs;
     std::vector<DevKeys> h_keys;
     std::vector<CipherTile> h_tiles[5];   // 0 gather, 1 aes-ctr, 2 aes-cbc, 3 camellia-ctr, 4 camellia-cbc
-    std::vector<uint32_t> h_store, h_deflate;
+    std::vector<uint32_t> h_store, h_deflate, h_xz;
     // GCM STREAM (cipher mode 2): segments, 16 KiB warp tiles (AES tiles first, then Camellia), one power table per entry
     std::vector<gcm::GcmSeg> h_gcm_segs;
     std::vector<gcm::GcmTile> h_gcm_tiles;
@@ -310,6 +311,7 @@ struct pna_plan {
     uint32_t pj_max_blocks = 0;
     DevArr<uint64_t> d_lit_base, d_seq_base;
     DevArr<inf::InfStream> d_inf;
+    DevArr<uint32_t> d_xz;
     DevArr<uint8_t> d_inf_lits;
     DevArr<zs::SeqRec> d_inf_recs;
     DevArr<zs::ZBlock> d_inf_blocks;
@@ -343,7 +345,7 @@ struct pna_plan {
         d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_lz_units.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
         d_walk.release(); d_pj_segs.release(); d_pj_ptr.release(); d_pj_cpos.release(); d_pj_flags.release(); d_pj_tiles.release();
-        d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release();
+        d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release(); d_xz.release();
         if (enc) enc::destroy(enc);
     }
 };
@@ -425,6 +427,7 @@ static int ctx_create_single(pna_ctx** out, int device_id) {
     ok = ok && cudaFuncSetAttribute(gcm::gcm_tiles_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gcm::gcm_tiles_smem<2>()) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(xz::xz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz::XZ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inf::TOKEN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::SEQ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LIT_SMEM_BYTES) == cudaSuccess;
@@ -613,6 +616,7 @@ static int variant_of(const EntryRec& e) {
 static uint64_t decode_size_bound(uint8_t compression, uint64_t comp_len) {
     if (compression == PNA_COMPRESSION_ZSTD) return comp_len > ((uint64_t)1 << 44) ? UINT64_MAX / 2 : (comp_len / 3 + 2) * 131072ull;
     if (compression == PNA_COMPRESSION_DEFLATE) return comp_len > ((uint64_t)1 << 50) ? UINT64_MAX / 2 : comp_len * 1032ull + 1024;
+    if (compression == PNA_COMPRESSION_XZ) return comp_len > ((uint64_t)1 << 40) ? UINT64_MAX / 2 : (comp_len / 6 + 1) * (2ull << 20);   // LZMA2 chunk: <= 2 MiB from >= 6 bytes
     return comp_len;
 }
 extern "C" uint64_t pna_cuda_decode_size_bound(uint8_t compression, uint64_t stream_len) { return decode_size_bound(compression, stream_len); }
@@ -669,7 +673,8 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
         e.stream_len = pos;
         P->stream_bytes += pos;
         // host-side validation == the reference's dispatch (entry/read.rs:59-190)
-        if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD)
+        if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD &&
+            d.compression != PNA_COMPRESSION_XZ)
             e.status = ST_UNSUPPORTED;
         else if (d.encryption != PNA_ENCRYPTION_NO && d.encryption != PNA_ENCRYPTION_AES && d.encryption != PNA_ENCRYPTION_CAMELLIA)
             e.status = ST_UNSUPPORTED;
@@ -822,10 +827,12 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
         if (cap == UINT64_MAX) all_caps = false;
         if (e.compression == PNA_COMPRESSION_NO) P->h_store.push_back(i);
         else if (e.compression == PNA_COMPRESSION_DEFLATE) P->h_deflate.push_back(i);
+        else if (e.compression == PNA_COMPRESSION_XZ) P->h_xz.push_back(i);
         else { zs::ZEntry z; memset(&z, 0, sizeof z); z.entry = i; P->h_ze.push_back(z); }
     }
     P->need_sizing = !all_caps;
     std::stable_sort(P->h_deflate.begin(), P->h_deflate.end(), [&](uint32_t a, uint32_t b) { return P->h_entries[a].comp_len > P->h_entries[b].comp_len; });
+    std::stable_sort(P->h_xz.begin(), P->h_xz.end(), [&](uint32_t a, uint32_t b) { return P->h_entries[a].comp_len > P->h_entries[b].comp_len; });
     // device arrays + upload
     CK(P->d_buf.reserve(P->buf_bytes));
     CK(P->d_entries.reserve(n)); CK(P->d_entries_init.reserve(n));
@@ -843,6 +850,10 @@ static int decode_plan_build(pna_ctx* ctx, const pna_decode_desc* descs, uint32_
     if (!P->h_deflate.empty()) {
         CK(P->d_deflate.reserve(P->h_deflate.size()));
         CK(cudaMemcpyAsync(P->d_deflate.p, P->h_deflate.data(), P->h_deflate.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!P->h_xz.empty()) {
+        CK(P->d_xz.reserve(P->h_xz.size()));
+        CK(cudaMemcpyAsync(P->d_xz.p, P->h_xz.data(), P->h_xz.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (!P->h_gcm_segs.empty()) {
         CK(P->d_gcm_segs.reserve(P->h_gcm_segs.size())); CK(P->d_gcm_tiles.reserve(P->h_gcm_tiles.size() + 1));
@@ -1087,6 +1098,11 @@ static int launch_zstd_lz_on(pna_plan* P, const zs::ZEntry* ze, const uint32_t* 
 // Otherwise: tokens -> LZ -> Adler for the two-stage streams, the bits-to-bytes kernel for the >= 2 GiB ones.
 static int launch_inflate(pna_plan* P, int size_only) {
     pna_ctx* ctx = P->ctx;
+    const uint32_t nx = (uint32_t)P->h_xz.size();
+    if (nx) {   // xz: a warp per stream (kernels_xz.cuh); sizing reads the chunk headers only
+        xz::xz_decode_kernel<<<nx, 32, xz::XZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_xz.p, nx, P->d_out.p, size_only);
+        LAUNCHED();
+    }
     if (size_only) {
         const uint32_t nd = (uint32_t)P->h_deflate.size();
         if (!nd) return PNA_OK;

@@ -91,10 +91,10 @@ PNA_HD int32_t lzma_chunk(LzmaState& S, uint16_t* probs, const uint8_t* in, uint
     const uint64_t end = pos + usize;
     const uint32_t pb_mask = (1u << S.pb) - 1u, lp_mask = (1u << S.lp) - 1u;
     uint32_t state = S.state, rep0 = S.rep0, rep1 = S.rep1, rep2 = S.rep2, rep3 = S.rep3;
+    uint32_t prev = pos > dict_start ? out[pos - 1] : 0u;   // the byte before pos, carried in a register (one global load less per literal)
     while (pos < end) {
         const uint32_t pos_state = (uint32_t)(pos - dict_start) & pb_mask;
         if (!rc.bit(probs + Probs::IS_MATCH + state * 16 + pos_state)) {
-            const uint32_t prev = pos > dict_start ? out[pos - 1] : 0u;
             uint16_t* lp = probs + Probs::LITERAL + 0x300u * ((((uint32_t)(pos - dict_start) & lp_mask) << S.lc) + (prev >> (8 - S.lc)));
             uint32_t sym = 1;
             if (state < 7) {
@@ -111,6 +111,7 @@ PNA_HD int32_t lzma_chunk(LzmaState& S, uint16_t* probs, const uint8_t* in, uint
                 } while (sym < 0x100);
             }
             out[pos++] = (uint8_t)sym;
+            prev = sym & 0xFFu;
             state = state < 4 ? 0 : state < 10 ? state - 3 : state - 6;
             if (rc.overrun) return ST_INVALID_DATA;
             continue;
@@ -135,8 +136,8 @@ PNA_HD int32_t lzma_chunk(LzmaState& S, uint16_t* probs, const uint8_t* in, uint
                 if (!rc.bit(probs + Probs::IS_REP0_LONG + state * 16 + pos_state)) {
                     if ((uint64_t)rep0 >= pos - dict_start) return ST_INVALID_DATA;
                     state = state < 7 ? 9 : 11;
-                    out[pos] = out[pos - rep0 - 1];
-                    pos++;
+                    prev = out[pos - rep0 - 1];
+                    out[pos++] = (uint8_t)prev;
                     if (rc.overrun) return ST_INVALID_DATA;
                     continue;
                 }
@@ -155,7 +156,7 @@ PNA_HD int32_t lzma_chunk(LzmaState& S, uint16_t* probs, const uint8_t* in, uint
         }
         if (rc.overrun || (uint64_t)rep0 >= pos - dict_start || len > end - pos) return ST_INVALID_DATA;
         const uint64_t src = pos - rep0 - 1;
-        for (uint32_t i = 0; i < len; i++) out[pos + i] = out[src + i];
+        for (uint32_t i = 0; i < len; i++) { prev = out[src + i]; out[pos + i] = (uint8_t)prev; }
         pos += len;
     }
     rc.normalize();
@@ -204,39 +205,50 @@ PNA_HD uint64_t xz_crc64(const uint8_t* p, uint64_t n) {
     return ~c;
 }
 
-// Decoded size of the FIRST .xz stream of [in, in + n) from its index (for the sizing pass); ST_OK or the failure class.
-// The stream's end is found by walking the blocks' headers and the index (sizes are recorded there), never by decoding.
+// Decoded size of the FIRST .xz stream of [in, in + n) for the sizing pass: the sum of the LZMA2 chunk headers' uncompressed
+// sizes, found by walking block and chunk headers (each chunk header carries both of its sizes) -- no entropy decoding, and
+// nothing read from the index, which is only checked against what was decoded.  A stream that ends early or goes wrong yields
+// the bytes of the chunks seen so far: the decode pass, given that much room, then stops at the same place and reports why.
 PNA_HD int32_t xz_stream_size(const uint8_t* in, uint64_t n, uint64_t* out_len) {
     *out_len = 0;
     if (n < 12) return ST_UNEXPECTED_EOF;
-    if (!(in[0] == 0xFD && in[1] == '7' && in[2] == 'z' && in[3] == 'X' && in[4] == 'Z' && in[5] == 0)) return ST_INVALID_DATA;
-    // Sizes are not in front of the data unless the encoder put them into the block header; the index behind the blocks has
-    // them.  Walk: block header -> (compressed size unknown without decoding) ... so use the footer when the stream is the whole
-    // input (what the reference writes: one stream per entry), else fail over to "unknown".
-    if (n < 24 || (n & 3)) return ST_UNEXPECTED_EOF;
-    const uint8_t* f = in + n - 12;
-    if (!(f[10] == 'Y' && f[11] == 'Z')) return ST_UNEXPECTED_EOF;       // truncated (or trailing bytes): the decode pass decides
-    const uint64_t isize = ((uint64_t)(load_le32(f + 4)) + 1) * 4;
-    if (isize + 24 > n) return ST_INVALID_DATA;
-    const uint8_t* ix = f - isize;
-    if (ix[0] != 0) return ST_INVALID_DATA;
-    uint64_t nrec = 0, at = 1, total = 0;
-    uint32_t k = xz_vli(ix + at, isize - at, &nrec);
-    if (!k) return ST_INVALID_DATA;
-    at += k;
-    for (uint64_t r = 0; r < nrec; r++) {
-        uint64_t us = 0, un = 0;
-        k = xz_vli(ix + at, isize - at, &us); if (!k) return ST_INVALID_DATA; at += k;
-        k = xz_vli(ix + at, isize - at, &un); if (!k) return ST_INVALID_DATA; at += k;
-        total += un;
-        if (total > ((uint64_t)1 << 62)) return ST_INVALID_DATA;
+    const uint32_t check = in[7] & 15;
+    const uint32_t check_size = check == 0 ? 0 : check == 1 ? 4 : check == 4 ? 8 : check == 10 ? 32 : 0;
+    uint64_t pos = 12, total = 0;
+    for (;;) {
+        if (pos >= n || in[pos] == 0) break;                                // index (or the end of what is there)
+        const uint64_t hsize = ((uint64_t)in[pos] + 1) * 4;
+        if (pos + hsize > n) break;
+        const uint64_t block_in = pos + hsize;
+        pos = block_in;
+        for (;;) {
+            if (pos >= n) { *out_len = total; return ST_OK; }
+            const uint8_t ctl = in[pos++];
+            if (ctl == 0) break;
+            if (ctl >= 0x80) {
+                if (pos + 4 > n) { *out_len = total; return ST_OK; }
+                const uint32_t usize = (((uint32_t)(ctl & 0x1F) << 16) | ((uint32_t)in[pos] << 8) | in[pos + 1]) + 1;
+                const uint32_t csize = (((uint32_t)in[pos + 2] << 8) | in[pos + 3]) + 1;
+                pos += 4 + (((ctl >> 5) & 3) >= 2 ? 1 : 0);
+                if (pos + csize > n) { *out_len = total; return ST_OK; }    // the decode pass fails before it writes this chunk
+                pos += csize; total += usize;
+            } else if (ctl <= 2) {
+                if (pos + 2 > n) { *out_len = total; return ST_OK; }
+                const uint32_t usize = (((uint32_t)in[pos] << 8) | in[pos + 1]) + 1;
+                pos += 2;
+                if (pos + usize > n) { *out_len = total; return ST_OK; }
+                pos += usize; total += usize;
+            } else { *out_len = total; return ST_OK; }                      // invalid control byte: decode reports it
+        }
+        pos += (4 - ((pos - block_in) & 3)) & 3;
+        pos += check_size;
     }
     *out_len = total;
     return ST_OK;
 }
 
 // Decode the first .xz stream of [in, in + n) into out[0, cap).  probs: LZMA_PROBS_MAX entries of scratch.
-// ST_OK (*out_len = decoded bytes), ST_NOSPACE (*out_len = bytes needed when the index tells, else cap + 1),
+// ST_OK (*out_len = decoded bytes), ST_NOSPACE (*out_len = bytes needed, from the chunk headers),
 // ST_UNEXPECTED_EOF (input ends inside the stream: liblzma_rs "premature eof"), ST_INVALID_DATA (everything liblzma calls
 // LZMA_DATA_ERROR / LZMA_FORMAT_ERROR), ST_UNSUPPORTED (filters other than LZMA2, unknown check types: LZMA_OPTIONS_ERROR).
 PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, uint16_t* probs) {
@@ -301,7 +313,7 @@ PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t c
                 } else if (S.need_props) return ST_INVALID_DATA;
                 if (mode >= 1) { lzma_reset_probs(probs, S.lc, S.lp); S.state = 0; S.rep0 = S.rep1 = S.rep2 = S.rep3 = 0; }
                 if (pos + csize > n) return ST_UNEXPECTED_EOF;
-                if (op + usize > cap) { uint64_t need = 0; if (xz_stream_size(in, n, &need) == ST_OK) *out_len = need; else *out_len = cap + 1; return ST_NOSPACE; }
+                if (op + usize > cap) { xz_stream_size(in, n, out_len); if (*out_len <= cap) *out_len = cap + 1; return ST_NOSPACE; }
                 const int32_t st = lzma_chunk(S, probs, in + pos, csize, out, op, usize, dict_start);
                 if (st != ST_OK) return st;
                 pos += csize; op += usize;
@@ -310,7 +322,7 @@ PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t c
                 const uint32_t usize = (((uint32_t)in[pos] << 8) | in[pos + 1]) + 1;
                 pos += 2;
                 if (pos + usize > n) return ST_UNEXPECTED_EOF;
-                if (op + usize > cap) { uint64_t need = 0; if (xz_stream_size(in, n, &need) == ST_OK) *out_len = need; else *out_len = cap + 1; return ST_NOSPACE; }
+                if (op + usize > cap) { xz_stream_size(in, n, out_len); if (*out_len <= cap) *out_len = cap + 1; return ST_NOSPACE; }
                 for (uint32_t i = 0; i < usize; i++) out[op + i] = in[pos + i];
                 pos += usize; op += usize;
             } else return ST_INVALID_DATA;

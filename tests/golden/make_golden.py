@@ -16,7 +16,7 @@ FIXTURES = ["deflate.pna", "zstd.pna", "zstd_aes_ctr.pna", "zstd_aes_cbc.pna", "
             "solid_deflate.pna", "solid_zstd_aes_ctr.pna", "solid_zstd_aes_cbc.pna", "solid_zstd_camellia_ctr.pna",
             "solid_zstd_camellia_cbc.pna", "solid_zstd_keep_all.pna", "empty.pna", "multipart.part1.pna",
             "multipart.part2.pna", "zstd_aes_gcm.pna", "zstd_camellia_gcm.pna", "solid_zstd_aes_gcm.pna",
-            "solid_zstd_camellia_gcm.pna", "xz.pna", "0.33.0/zstd_keep_all.pna", "zstd_keep_fflags.pna"]
+            "solid_zstd_camellia_gcm.pna", "xz.pna", "solid_xz.pna", "0.33.0/zstd_keep_all.pna", "zstd_keep_fflags.pna"]
 PASSWORD = b"password"
 
 

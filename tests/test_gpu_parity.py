@@ -103,6 +103,44 @@ def test_decode_cross_product(ctx, oracle, comp):
     assert st == [0] * len(entries) and all(o.tobytes() == w for o, w in zip(outs, want))
 
 
+def test_xz_decode(ctx, oracle):
+    """decompress_reader's XZ arm (entry/read.rs:182) against liblzma (the oracle's xz arm IS liblzma): every cipher, sizes from
+    empty to several LZMA2 chunks, presets 0/6/9, with and without size hints, split across FDAT bodies; error classes."""
+    import lzma
+    key = os.urandom(32)
+    entries, want = [], []
+    for i, n in enumerate([0, 1, 17, 1000, 70_000, 300_000, 2_300_000]):
+        for j, (enc, mode) in enumerate(CIPHERS):
+            plain = corpus.make_file(400 + i, n)
+            entries.append(_mk(oracle, plain, 4, enc, mode, key, hint=((i + j) % 2 == 0), level=(0, 6, 9)[(i + j) % 3],
+                               split=None if j % 2 else [5, 30, 1000]))
+            want.append(plain)
+    # incompressible data (uncompressed LZMA2 chunks) and a highly compressible run (long matches, many repeats)
+    for plain in (os.urandom(200_000), bytes(3_000_000), b"abcdefg" * 100_000):
+        entries.append(_mk(oracle, plain, 4, 0, 0, key, hint=False))
+        want.append(plain)
+    outs, st, lens = ctx.decode_batch(entries)
+    assert st == [0] * len(entries)
+    assert [int(x) for x in lens] == [len(w) for w in want]
+    for o, w in zip(outs, want):
+        assert o.tobytes() == w
+    # error classes: truncation = UnexpectedEof ("premature eof"), corruption = InvalidData, too small a capacity = NoSpace
+    plain = corpus.make_file(7, 50_000)
+    c = lzma.compress(plain, preset=6)
+    mk = lambda b: {"bodies": [b], "compression": 4, "encryption": 0, "cipher_mode": 0, "key": key, "raw_size_hint": None}
+    bad = bytearray(c); bad[len(c) // 2] ^= 0x10
+    badcheck = bytearray(c); badcheck[-30] ^= 1
+    cases = [mk(c[:len(c) // 2]), mk(c[:-1]), mk(bytes(bad)), mk(bytes(badcheck)), mk(b"\xFD7zXZ"), mk(c)]
+    outs, st, lens = ctx.decode_batch(cases)
+    for case, s_ in zip(cases[:-1], st[:-1]):
+        with pytest.raises(oracle.OracleError) as ei:
+            oracle.decompress(4, bytes(case["bodies"][0]))
+        assert s_ == ei.value.status, (s_, ei.value.status)
+    assert st[-1] == 0 and outs[-1].tobytes() == plain
+    outs, st, lens = ctx.decode_batch([mk(c)], caps=[len(plain) - 1])
+    assert st == [5] and int(lens[0]) == len(plain)
+
+
 def test_decode_adversarial_chunk_splits(ctx, oracle):
     """IV and cipher blocks straddling FDAT boundaries; 1-byte and 16-byte chunks (util/io.rs:24-33,
     archive.rs:969 chunk_split_one_byte, fixture solid_zstd_aes_cbc.pna with 16-byte SDATs)."""
@@ -129,7 +167,8 @@ def test_decode_error_classes(ctx, oracle, pna):
         (dict(good, bodies=[s[:16 + 24]]), pna.E_UNEXPECTED_EOF),              # partial CBC block     block/read.rs:90
         (dict(good, bodies=[s[:16]]), pna.E_UNEXPECTED_EOF),                   # no first block       block/read.rs:36
         (dict(good, key=os.urandom(32)), None),                               # wrong key: bad pad or corrupt zstd
-        (dict(good, compression=4), pna.E_UNSUPPORTED),                        # xz
+        (dict(good, compression=4), pna.E_INVALID_DATA),                       # the xz arm over a zstd stream: no .xz magic
+        (dict(good, compression=3), pna.E_UNSUPPORTED),                        # unassigned compression code
         (dict(good, cipher_mode=3), pna.E_UNSUPPORTED),                        # reserved cipher mode  entry/read.rs:152
         (dict(good, encryption=7), pna.E_UNSUPPORTED),
     ]

@@ -212,7 +212,7 @@ def test_xz_core(hc, golden, oracle):
             n = C.c_uint64(0)
             assert hc.hc_xz_size(c, len(c), C.byref(n)) == 0 and n.value == len(d)
             if d:
-                assert _dec(hc.hc_xz_decode, c, len(d) - 1) == (5, len(d))          # NOSPACE + the length from the index
+                assert _dec(hc.hc_xz_decode, c, len(d) - 1) == (5, len(d))          # NOSPACE + the length from the chunk headers
     # other literal / position context settings than the presets use
     d = corpus.make_file(9, 120_000)
     for lc, lp, pb in ((0, 0, 0), (4, 0, 2), (0, 4, 4), (2, 2, 1), (3, 1, 3)):
@@ -223,6 +223,16 @@ def test_xz_core(hc, golden, oracle):
     c = lzma.compress(d, preset=6)
     for cut in (0, 5, 11, 12, 13, 30, len(c) // 2, len(c) - 13, len(c) - 1):
         assert _dec(hc.hc_xz_decode, c[:cut], len(d))[0] == 2, cut
+        # the two-pass product path: the sizing walk never fails a stream the decode pass could still classify, and the room
+        # it asks for is enough for the decode pass to get to the real reason
+        n = C.c_uint64(0)
+        hc.hc_xz_size(c[:cut], cut, C.byref(n))
+        assert n.value <= len(d) and _dec(hc.hc_xz_decode, c[:cut], n.value)[0] == 2, cut
+    big = corpus.make_file(4, 5_000_000)                       # several LZMA2 chunks (2 MiB each at most), two blocks
+    cb = lzma.compress(big[:3_000_000], preset=1)
+    n = C.c_uint64(0)
+    assert hc.hc_xz_size(cb, len(cb), C.byref(n)) == 0 and n.value == 3_000_000
+    assert _dec(hc.hc_xz_decode, cb, 1000) == (5, 3_000_000)
     for _ in range(300):
         b = bytearray(c)
         b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
