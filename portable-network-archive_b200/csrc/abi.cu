@@ -427,6 +427,7 @@ static int ctx_create_single(pna_ctx** out, int device_id) {
     ok = ok && cudaFuncSetAttribute(gcm::gcm_tiles_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gcm::gcm_tiles_smem<2>()) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(crc_tiles_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_WIDE_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(xz::xz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz::XZ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inf::TOKEN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::SEQ_SMEM_BYTES) == cudaSuccess;
@@ -545,9 +546,7 @@ static int crc_run(pna_ctx* ctx, const uint8_t* d_img, const std::vector<uint64_
             (e = cudaMemcpyAsync(d_first.p, first.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
             ctx->fail("crc upload", e); rc = PNA_E_CUDA; break;
         }
-        const uint32_t warps_per_cta = 8;
-        uint32_t grid = std::min<uint32_t>((nt + warps_per_cta - 1) / warps_per_cta, (uint32_t)ctx->sm_count * 8);
-        crc_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, d_tiles.p, nt, ctx->d_crc, d_raw.p);
+        launch_crc_tiles(ctx->stream, ctx->sm_count, d_img, d_tiles.p, nt, ctx->d_crc, d_raw.p);
         ctx->launches++;
         crc_combine_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_tiles.p, d_raw.p, d_first.p, n, nt, ctx->d_crc, d_crc.p);
         ctx->launches++;
@@ -938,8 +937,7 @@ static int launch_crc(pna_plan* P) {
     if (!P->n_crc) return PNA_OK;
     const uint32_t nt = (uint32_t)P->h_crc_tiles.size();
     CK(cudaMemsetAsync(P->d_crc_broken.p, 0, sizeof(uint32_t), ctx->stream));
-    const uint32_t grid = std::min<uint32_t>((nt + 7) / 8, (uint32_t)ctx->sm_count * 8);
-    crc_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(P->d_buf.p, P->d_crc_tiles.p, nt, ctx->d_crc, P->d_crc_raw.p);
+    launch_crc_tiles(ctx->stream, ctx->sm_count, P->d_buf.p, P->d_crc_tiles.p, nt, ctx->d_crc, P->d_crc_raw.p);
     LAUNCHED();
     crc_combine_kernel<<<(P->n_crc + 127) / 128, 128, 0, ctx->stream>>>(P->d_crc_tiles.p, P->d_crc_raw.p, P->d_crc_first.p, P->n_crc, nt,
                                                                        ctx->d_crc, P->d_crc_val.p);

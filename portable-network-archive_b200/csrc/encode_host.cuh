@@ -345,8 +345,7 @@ static int encode_launch_all(pna_plan* P) {
     if (nt) {
         enc::crc_clip_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(E->d_crc_src.p, nt, E->d_entries.p, E->d_crc_tiles.p);
         LAUNCHED();
-        const uint32_t grid = std::min<uint32_t>((nt + 7) / 8, (uint32_t)ctx->sm_count * 8);
-        crc_tiles_kernel<<<grid, 256, 0, ctx->stream>>>(E->d_out.p, E->d_crc_tiles.p, nt, ctx->d_crc, E->d_crc_raw.p);
+        launch_crc_tiles(ctx->stream, ctx->sm_count, E->d_out.p, E->d_crc_tiles.p, nt, ctx->d_crc, E->d_crc_raw.p);
         LAUNCHED();
         crc_combine_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(E->d_crc_tiles.p, E->d_crc_raw.p, E->d_crc_first.p, nb, nt, ctx->d_crc,
                                                                      E->d_crc_val.p, E->fdat_init);

@@ -55,6 +55,90 @@ __global__ void __launch_bounds__(256) crc_tiles_kernel(const uint8_t* __restric
     }
 }
 
+// The same tiles for batches large enough to fill the GPU: 1024 threads per CTA, one CTA per SM, and the four hot tables
+// LANE-PRIVATE in shared memory ([table][byte][lane], 128 KB): lane l only ever touches bank l, so the 32 lookups of a warp
+// instruction never conflict (the 1 KB tables of crc_tiles_kernel cost 3.1 wavefronts per lookup: random bytes, 32 lanes, 32
+// banks).  The recurrence is also cheaper: a lane keeps FOUR registers, one per word of its 16-byte column, in the basis where
+// a step is  s_j <- F(s_j ^ w_j),  F = "feed four bytes, then 508 zeros" -- four lookups per word, sixteen per 16 bytes (the
+// 20-table form spends four more on advancing a separate state).  The last row is not advanced: s_j ^ w_j is the lane's
+// 16-byte column remainder input, folded once per tile with the ordinary sixteen tables (from L1), then the lane constant,
+// the XOR tree and the pad correction exactly as above.
+constexpr int CRC_WIDE_THREADS = 1024;
+constexpr int CRC_WIDE_SMEM = 4 * 256 * 32 * 4;
+__global__ void __launch_bounds__(CRC_WIDE_THREADS, 1) crc_tiles_wide_kernel(const uint8_t* __restrict__ img, const CrcTile* __restrict__ tiles,
+                                                                             uint32_t n_tiles, const CrcConsts* __restrict__ C,
+                                                                             uint32_t* __restrict__ raw) {
+    extern __shared__ uint32_t s_priv[];   // [k][b][lane] = U_{508+k}[b]
+    for (int i = threadIdx.x; i < 4 * 256 * 32; i += blockDim.x) s_priv[i] = C->U[16 + (i >> 13)][(i >> 5) & 255];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t* const tl0 = s_priv + lane;   // + 32 * byte + 8192 * table
+    const uint32_t* const U = &C->U[0][0];
+    const uint32_t warps_per_cta = blockDim.x >> 5;
+    // s ^ w advanced by 512 bytes: byte 0 of the word is the oldest (table U_511), byte 3 the newest (U_508)
+    auto step = [&](uint32_t v) -> uint32_t {
+        return tl0[3 * 8192 + ((v & 0xFFu) << 5)] ^ tl0[2 * 8192 + ((v >> 3) & 0x1FE0u)] ^ tl0[1 * 8192 + ((v >> 11) & 0x1FE0u)] ^
+               tl0[0 * 8192 + ((v >> 19) & 0x1FE0u)];
+    };
+    for (uint32_t t = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); t < n_tiles; t += gridDim.x * warps_per_cta) {
+        const CrcTile tl = tiles[t];
+        const uint64_t S = tl.begin, E = tl.begin + tl.len;
+        const uint64_t A = (E + 15) & ~(uint64_t)15;
+        const uint32_t rows = (uint32_t)(((A - (S & ~(uint64_t)15)) + 511) / 512);
+        uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int64_t a = (int64_t)A - (int64_t)rows * 512 + 16 * lane;   // oldest row first
+        auto load_row = [&](int64_t at, uint32_t w[4]) {
+            w[0] = w[1] = w[2] = w[3] = 0;
+            if (at + 16 > (int64_t)S && at < (int64_t)E && at >= 0) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + at));
+                w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+                crc_mask_chunk((uint64_t)at, S, E, w);
+            }
+        };
+        uint32_t r = 0;
+        // rows strictly inside the tile need no masking: four loads in flight per lane
+        for (; r + 4 < rows; r += 4, a += 2048) {
+            uint32_t w[4][4];
+            if (r == 0) load_row(a, w[0]);
+            else { const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + a)); w[0][0] = q.x; w[0][1] = q.y; w[0][2] = q.z; w[0][3] = q.w; }
+#pragma unroll
+            for (int k = 1; k < 4; k++) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + a + 512 * k));
+                w[k][0] = q.x; w[k][1] = q.y; w[k][2] = q.z; w[k][3] = q.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { s0 = step(s0 ^ w[k][0]); s1 = step(s1 ^ w[k][1]); s2 = step(s2 ^ w[k][2]); s3 = step(s3 ^ w[k][3]); }
+        }
+        for (; r + 1 < rows; r++, a += 512) {
+            uint32_t w[4];
+            load_row(a, w);
+            s0 = step(s0 ^ w[0]); s1 = step(s1 ^ w[1]); s2 = step(s2 ^ w[2]); s3 = step(s3 ^ w[3]);
+        }
+        uint32_t x = 0;
+        if (rows) {
+            uint32_t w[4];
+            load_row(a, w);
+            x = crc_fold_row(0u, s0 ^ w[0], s1 ^ w[1], s2 ^ w[2], s3 ^ w[3], U);   // the column as 16 bytes, no advance
+        }
+        x = crc_multmodp(x, C->lane_k[lane]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0) raw[t] = crc_multmodp(x, C->inv_z[(16 - (E & 15)) & 15]);
+    }
+}
+// tiles of a batch: the wide kernel once there is enough work to pay for its table fill on every SM
+static inline void launch_crc_tiles(cudaStream_t stream, int sm_count, const uint8_t* img, const CrcTile* tiles, uint32_t nt, const CrcConsts* C,
+                                    uint32_t* raw) {
+    if (nt >= 512u) {   // every SM takes part; warps per CTA follow the work (4 .. 32)
+        const uint32_t warps = std::min<uint32_t>(32u, std::max<uint32_t>(4u, (nt + (uint32_t)sm_count - 1) / (uint32_t)sm_count));
+        const uint32_t grid = std::min<uint32_t>((nt + warps - 1) / warps, (uint32_t)sm_count);
+        crc_tiles_wide_kernel<<<grid, 32 * warps, CRC_WIDE_SMEM, stream>>>(img, tiles, nt, C, raw);
+    } else {
+        const uint32_t grid = std::min<uint32_t>((nt + 7) / 8, (uint32_t)sm_count * 8);
+        crc_tiles_kernel<<<grid, 256, 0, stream>>>(img, tiles, nt, C, raw);
+    }
+}
+
 // combine the tiles of each span: acc <- acc * x^(8 len) ^ raw ; crc = ~acc
 __global__ void crc_combine_kernel(const CrcTile* __restrict__ tiles, const uint32_t* __restrict__ raw,
                                    const uint32_t* __restrict__ span_first_tile, uint32_t n_spans, uint32_t n_tiles,

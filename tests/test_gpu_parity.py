@@ -32,6 +32,26 @@ def test_crc_ragged_spans(ctx, oracle):
     assert int(got[5]) == oracle.crc32(spans[5])
 
 
+def test_crc_wide_kernel_every_shape(ctx):
+    """Batches of >= 512 tiles take crc_tiles_wide_kernel (lane-private tables, four-word columns): every start alignment x
+    lengths around the 16-byte column, the 512-byte row, the 4-row unroll and the 64 KiB tile, plus multi-tile spans."""
+    img = np.frombuffer(np.random.default_rng(5).bytes(1_500_000), dtype=np.uint8)
+    offs, lens = [], []
+    for a in range(0, 48):
+        for n in (0, 1, 3, 4, 15, 16, 17, 496, 511, 512, 513, 1024, 1535, 2047, 2048, 2049, 2560, 4096 + a, 65535, 65536, 65537, 200_000 + 7 * a):
+            offs.append(777 + a)
+            lens.append(n)
+    assert len(offs) >= 512
+    got = ctx.crc32_image(img, offs, lens)
+    want = [zlib.crc32(img[o:o + n].tobytes()) for o, n in zip(offs, lens)]
+    assert [int(x) for x in got] == want
+    # all-ones / all-zero data (masking of the rows outside a span must not depend on the bytes there)
+    for fill in (0x00, 0xFF):
+        blk = np.full(300_000, fill, dtype=np.uint8)
+        got = ctx.crc32_image(blk, offs[:600], [min(n, 250_000) for n in lens[:600]])
+        assert [int(x) for x in got] == [zlib.crc32(blk[o:o + min(n, 250_000)].tobytes()) for o, n in zip(offs[:600], lens[:600])]
+
+
 def test_crc_image_every_alignment(ctx):
     img = np.frombuffer(os.urandom(200_000), dtype=np.uint8)
     offs, lens = [], []
