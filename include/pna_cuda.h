@@ -81,7 +81,11 @@ typedef struct {
 typedef struct {
     pna_span plain;
     uint8_t compression, encryption, cipher_mode, _pad;
-    int32_t level;          /* <0: reference default (zstd 3 compress/zstandard.rs:46, deflate 6 compress/deflate.rs:89) */
+    int32_t level;          /* <0: reference default (zstd 3 compress/zstandard.rs:46, deflate 6 compress/deflate.rs:89).
+                             * Selects the encoder setting: zstd 1-2 / deflate 1-3 fast (greedy parse, Predefined FSE tables);
+                             * zstd 3-5 / deflate 4-6 default (per-block FSE tables chosen by cost); zstd >= 6 / deflate 7-9
+                             * high (lazy parse); deflate 0 stored blocks.  Sizes differ from the reference's at the same
+                             * level (another encoder); every setting decodes with the reference's codecs. */
     uint8_t key[32];
     uint8_t iv[16];         /* caller-drawn (lib/src/entry/write.rs:108-111, random.rs:8); unused by GCM */
     uint32_t max_chunk_size; /* FDAT body cap for CRC emission; 0 = u32::MAX - one body (lib/src/util/io.rs:24-33) */

@@ -42,10 +42,10 @@ struct EncTables {
     uint8_t ml_code[128];   // (ml - 3) < 128 -> code
 };
 
-inline void fse_build_ctab(FseCTab* T, int kind) {
-    const int log = kind == 1 ? 5 : 6, n = kind == 0 ? 36 : kind == 1 ? 29 : 53, size = 1 << log;
-    int16_t norm[56];
-    for (int s = 0; s < n; s++) norm[s] = (int16_t)zs::predef_norm(kind, s);
+// FSE compression table from normalised counts (sum = 1 << log, -1 = "less than one"), libzstd FSE_buildCTable semantics.
+// log <= 6, n <= 56.
+PNA_HD void fse_build_ctab_norm(FseCTab* T, const int16_t* norm, int n, int log) {
+    const int size = 1 << log;
     uint32_t cumul[57];
     uint8_t sym_of[64];
     int high = size - 1;
@@ -76,6 +76,93 @@ inline void fse_build_ctab(FseCTab* T, int kind) {
         }
     }
     T->log = (uint32_t)log;
+}
+inline void fse_build_ctab(FseCTab* T, int kind) {
+    const int log = kind == 1 ? 5 : 6, n = kind == 0 ? 36 : kind == 1 ? 29 : 53;
+    int16_t norm[56];
+    for (int s = 0; s < n; s++) norm[s] = (int16_t)zs::predef_norm(kind, s);
+    fse_build_ctab_norm(T, norm, n, log);
+}
+// the table of an RLE-mode symbol: zero bits per symbol, state 0 (libzstd FSE_buildCTable_rle)
+PNA_HD void fse_build_ctab_rle(FseCTab* T, uint32_t sym) {
+    T->state[0] = 0; T->state[1] = 0;
+    T->dnb[sym] = 0; T->dfs[sym] = 0;
+    T->log = 0;
+}
+
+// ---- per-block ("FSE_Compressed_Mode") tables.  Blocks are written by one thread each, so everything here is small and
+// serial: a histogram of the block's codes, counts normalised to 2^6 (every present symbol gets at least 1; the rounding
+// remainder goes to / comes from the most frequent symbols), the table description (RFC 8878 4.1.1), and an integer cost
+// model (1/256 bit units) that decides between Predefined, RLE and FSE_Compressed per table.
+constexpr int FSE_DYN_LOG = 6;
+// 256 * log2(n) for 1 <= n <= 64, piecewise linear in the mantissa (never above the true value by more than it is below: the
+// error, <= 0.09 bit, only tilts close decisions)
+PNA_HD uint32_t log2_256(uint32_t n) {
+    const uint32_t hb = (uint32_t)highbit32(n);
+    return (hb << 8) + (((n << 8) >> hb) - 256u);
+}
+// bits * 256 to code `count` symbols each of probability norm / 2^log
+PNA_HD uint32_t fse_cost256(uint32_t count, int norm, int log) { return count * (((uint32_t)log << 8) - log2_256((uint32_t)(norm < 1 ? 1 : norm))); }
+
+// counts[0..n) (sum = total >= 1, at most 64 non-zero) -> norm[0..n) with sum 2^FSE_DYN_LOG; returns the number of present symbols
+PNA_HD int fse_normalize64(const uint16_t* counts, int n, uint32_t total, int16_t* norm) {
+    const int size = 1 << FSE_DYN_LOG;
+    int sum = 0, present = 0;
+    for (int s = 0; s < n; s++) {
+        int v = 0;
+        if (counts[s]) {
+            v = (int)(((uint64_t)counts[s] * (uint32_t)size + total / 2) / total);
+            if (v < 1) v = 1;
+            present++;
+        }
+        norm[s] = (int16_t)v;
+        sum += v;
+    }
+    while (sum != size) {   // a few rounds: rounding leaves at most one unit per present symbol
+        int big = 0;
+        for (int s = 1; s < n; s++) if (norm[s] > norm[big]) big = s;
+        if (sum < size) { norm[big] = (int16_t)(norm[big] + (size - sum)); break; }
+        const int excess = sum - size, can = norm[big] - 1;
+        if (can <= 0) break;   // cannot happen: at most 53 present symbols of weight 1 in a table of 64
+        int take = can / 2 > 1 ? can / 2 : 1;   // a large excess is spread over several symbols
+        if (take > excess) take = excess;
+        norm[big] = (int16_t)(norm[big] - take);
+        sum -= take;
+    }
+    return present;
+}
+// FSE table description; returns the byte count (< 56: 53 symbols of at most 7 bits, plus zero-run flags)
+PNA_HD uint32_t fse_write_ncount(const int16_t* norm, int n, uint8_t* dst) {
+    int last = n - 1;
+    while (last > 0 && norm[last] == 0) last--;
+    const int alphabet = last + 1, log = FSE_DYN_LOG;
+    uint64_t acc = (uint64_t)(log - 5);
+    uint32_t nb = 4, bytes = 0;
+    int remaining = (1 << log) + 1, threshold = 1 << log, bits = log + 1, sym = 0;
+    bool prev0 = false;
+    auto flush = [&]() { while (nb >= 8) { dst[bytes++] = (uint8_t)acc; acc >>= 8; nb -= 8; } };
+    while (sym < alphabet && remaining > 1) {
+        if (prev0) {
+            int start = sym;
+            while (sym < alphabet && norm[sym] == 0) sym++;
+            while (sym >= start + 3) { start += 3; acc |= (uint64_t)3 << nb; nb += 2; flush(); }
+            acc |= (uint64_t)(sym - start) << nb; nb += 2;
+            flush();
+        }
+        int count = norm[sym++];
+        const int mx = (2 * threshold - 1) - remaining;
+        remaining -= count < 0 ? -count : count;
+        count++;
+        if (count >= threshold) count += mx;
+        acc |= (uint64_t)(uint32_t)count << nb;
+        nb += (uint32_t)bits;
+        if (count < mx) nb--;
+        prev0 = count == 1;
+        while (remaining < threshold) { bits--; threshold >>= 1; }
+        flush();
+    }
+    if (nb) { dst[bytes++] = (uint8_t)acc; }
+    return bytes;
 }
 inline void make_enc_tables(EncTables* E) {
     fse_build_ctab(&E->ll, 0); fse_build_ctab(&E->of, 1); fse_build_ctab(&E->ml, 2);
@@ -164,22 +251,67 @@ PNA_HD void zstd_assign_repcodes(Seq* seqs, uint32_t nseq) {
     }
 }
 
-// Sequences section of one block (nseq >= 1): Number_of_Sequences, mode byte 0 (predefined x3), FSE bitstream.
+// Sequences section of one block (nseq >= 1): Number_of_Sequences, Symbol_Compression_Modes, table descriptions, FSE bitstream.
 // seqs[i].off is a distance, or SEQ_REPCODE | Offset_Value where zstd_assign_repcodes chose a repeat offset.
+// dyn: choose per table between Predefined, RLE and FSE_Compressed (a table fitted to this block) by estimated cost; else all
+// three Predefined (the fast setting).
 // dst must be 4-byte aligned, cap bytes.  Returns (offset of first byte << 24) | length, or 0xFFFFFFFF when the
 // section would not fit cap (the caller then emits the segment as a Raw_Block).
-PNA_HD uint32_t zstd_write_sequences(const EncTables& E, const Seq* seqs, uint32_t nseq, uint8_t* dst, uint32_t cap) {
-    // header is written after the bitstream at its front; bitstream starts 4-byte aligned at dst + 4
+constexpr uint32_t SEQ_HDR_ROOM = 208;   // Number_of_Sequences (3) + modes (1) + three table descriptions (< 64 each), multiple of 4
+PNA_HD uint32_t zstd_write_sequences(const EncTables& E, const Seq* seqs, uint32_t nseq, uint8_t* dst, uint32_t cap, bool dyn = false) {
+    if (cap < SEQ_HDR_ROOM + 64) return 0xFFFFFFFFu;
+    // ---- tables
+    FseCTab dtab[3];
+    const FseCTab* tab[3] = {&E.ll, &E.of, &E.ml};
+    uint8_t desc[3][64];
+    uint32_t desc_n[3] = {0, 0, 0}, mode[3] = {0, 0, 0};
+    if (dyn && nseq >= 48) {
+        uint16_t cnt[3][56];
+        for (int t = 0; t < 3; t++) for (int k = 0; k < 56; k++) cnt[t][k] = 0;
+        for (uint32_t i = 0; i < nseq; i++) {
+            const Seq q = seqs[i];
+            const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = (q.off & SEQ_REPCODE) ? (q.off & 3u) : q.off + 3u;
+            cnt[0][ll_code_of(E, ll)]++; cnt[1][(uint32_t)highbit32(ob)]++; cnt[2][ml_code_of(E, mlb)]++;
+        }
+        for (int t = 0; t < 3; t++) {
+            const int n = t == 0 ? 36 : t == 1 ? 29 : 53, plog = t == 1 ? 5 : 6;
+            int16_t norm[56];
+            int only = -1;
+            uint32_t pre = 0;
+            bool pre_ok = true;
+            for (int k = 0; k < n; k++) {
+                if (!cnt[t][k]) continue;
+                if (cnt[t][k] == nseq) only = k;
+                pre += fse_cost256(cnt[t][k], zs::predef_norm(t, k), plog);
+            }
+            for (int k = n; k < 56; k++) if (cnt[t][k]) pre_ok = false;   // (offset codes above 28 cannot occur with 32 KiB segments)
+            if (only >= 0) { mode[t] = 1; desc[t][0] = (uint8_t)only; desc_n[t] = 1; fse_build_ctab_rle(&dtab[t], (uint32_t)only); tab[t] = &dtab[t]; continue; }
+            fse_normalize64(cnt[t], n, nseq, norm);
+            uint32_t fit = 0;
+            for (int k = 0; k < n; k++) if (cnt[t][k]) fit += fse_cost256(cnt[t][k], norm[k], FSE_DYN_LOG);
+            const uint32_t dn = fse_write_ncount(norm, n, desc[t]);
+            if (!pre_ok || fit + (dn << 11) < pre) {   // description bytes * 8 bits * 256
+                mode[t] = 2; desc_n[t] = dn;
+                fse_build_ctab_norm(&dtab[t], norm, n, FSE_DYN_LOG);
+                tab[t] = &dtab[t];
+            }
+        }
+    }
+    const FseCTab& TL = *tab[0];
+    const FseCTab& TO = *tab[1];
+    const FseCTab& TM = *tab[2];
+    // header is written after the bitstream at its front; bitstream starts 4-byte aligned at dst + SEQ_HDR_ROOM
     BitOut b;
-    b.init(dst + 4);
+    b.init(dst + SEQ_HDR_ROOM);
+    const uint32_t room = cap - SEQ_HDR_ROOM;
     FseCState sll, sof, sml;
     {
         const Seq q = seqs[nseq - 1];
         const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = (q.off & SEQ_REPCODE) ? (q.off & 3u) : q.off + 3u;
         const uint32_t cl = ll_code_of(E, ll), cm = ml_code_of(E, mlb), co = (uint32_t)highbit32(ob);
-        fse_init_state(sml, E.ml, cm);
-        fse_init_state(sof, E.of, co);
-        fse_init_state(sll, E.ll, cl);
+        fse_init_state(sml, TM, cm);
+        fse_init_state(sof, TO, co);
+        fse_init_state(sll, TL, cl);
         b.add(ll, (uint32_t)zs::ll_bits((int)cl));
         b.add(mlb, (uint32_t)zs::ml_bits((int)cm));
         b.add(ob, co);
@@ -188,29 +320,32 @@ PNA_HD uint32_t zstd_write_sequences(const EncTables& E, const Seq* seqs, uint32
         const Seq q = seqs[i];
         const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = (q.off & SEQ_REPCODE) ? (q.off & 3u) : q.off + 3u;
         const uint32_t cl = ll_code_of(E, ll), cm = ml_code_of(E, mlb), co = (uint32_t)highbit32(ob);
-        fse_encode(b, sof, E.of, co);
-        fse_encode(b, sml, E.ml, cm);
-        fse_encode(b, sll, E.ll, cl);
+        fse_encode(b, sof, TO, co);
+        fse_encode(b, sml, TM, cm);
+        fse_encode(b, sll, TL, cl);
         b.add(ll, (uint32_t)zs::ll_bits((int)cl));
         b.add(mlb, (uint32_t)zs::ml_bits((int)cm));
         b.add(ob, co);
-        if (b.bytes + 32 > cap) return 0xFFFFFFFFu;
+        if (b.bytes + 32 > room) return 0xFFFFFFFFu;
     }
-    if (b.bytes + 32 > cap) return 0xFFFFFFFFu;
-    b.add(sml.v, E.ml.log);
-    b.add(sof.v, E.of.log);
-    b.add(sll.v, E.ll.log);
+    if (b.bytes + 32 > room) return 0xFFFFFFFFu;
+    b.add(sml.v, TM.log);
+    b.add(sof.v, TO.log);
+    b.add(sll.v, TL.log);
     b.add(1, 1);
     const uint32_t bs = b.finish();
-    // Number_of_Sequences (1-3 bytes) + modes byte, right-aligned against the bitstream
+    // Number_of_Sequences (1-3 bytes) + modes byte + table descriptions (LL, OF, ML), right-aligned against the bitstream
     uint8_t h[4];
     uint32_t hn;
     if (nseq < 128) { h[0] = (uint8_t)nseq; hn = 1; }
     else if (nseq < 0x7F00) { h[0] = (uint8_t)((nseq >> 8) + 0x80); h[1] = (uint8_t)nseq; hn = 2; }
     else { h[0] = 0xFF; h[1] = (uint8_t)(nseq - 0x7F00); h[2] = (uint8_t)((nseq - 0x7F00) >> 8); hn = 3; }
-    h[hn++] = 0;   // Symbol_Compression_Modes: predefined LL / OF / ML
-    for (uint32_t k = 0; k < hn; k++) dst[4 - hn + k] = h[k];
-    return (4 - hn) << 24 | (hn + bs);   // high byte: offset of the first valid byte inside dst
+    h[hn++] = (uint8_t)((mode[0] << 6) | (mode[1] << 4) | (mode[2] << 2));   // Symbol_Compression_Modes
+    const uint32_t total_h = hn + desc_n[0] + desc_n[1] + desc_n[2];
+    uint8_t* w = dst + SEQ_HDR_ROOM - total_h;
+    for (uint32_t k = 0; k < hn; k++) *w++ = h[k];
+    for (int t = 0; t < 3; t++) for (uint32_t k = 0; k < desc_n[t]; k++) *w++ = desc[t][k];
+    return (SEQ_HDR_ROOM - total_h) << 24 | (total_h + bs);   // high byte: offset of the first valid byte inside dst
 }
 
 // Raw_Literals section header for `n` literal bytes; returns header length (1..3)

@@ -99,6 +99,7 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
         e.plain_off = plain_total; e.plain_len = d.plain.len;
         plain_total += align_up(d.plain.len, 16) + 16;
         e.compression = d.compression; e.encryption = d.encryption; e.cipher_mode = d.cipher_mode;
+        e.effort = (uint8_t)enc::enc_effort(d.compression, d.level);
         memcpy(e.iv, d.iv, 16);
         e.key_idx = -1;
         if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD)
@@ -161,6 +162,7 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
             s.entry = i;
             s.last = k + 1 == e.n_segs || (e.compression == PNA_COMPRESSION_ZSTD && (k + 1) % enc::FRAME_SEGS == 0);   // Last_Block of its frame
             s.adler = e.compression == PNA_COMPRESSION_DEFLATE;
+            s.effort = e.effort;
         }
         piece_cur += 4 + 3 * (uint64_t)e.n_segs + e.n_segs / enc::FRAME_SEGS;
         const uint64_t bound = pna_cuda_encode_bound(&d);

@@ -28,9 +28,20 @@ struct SegRec {            // one segment (host fills the first group, kernels t
     uint32_t head_len, raw;        // raw: pieces = head + plain; else head + literals + tail (zstd) / body (deflate)
     uint32_t tail_off, tail_len;   // inside the body
     uint64_t litp_off;             // literal payload of a compressed zstd block: the literal arena (raw) or the body (Huffman)
-    uint32_t litp_len, _pad2;
+    uint32_t litp_len, effort;     // effort: the entry's (enc_effort)
     uint64_t adler_a, adler_b;     // sum of bytes, sum of (len - k) * byte_k
 };
+// The `level` of the reference's writers (zstd 1..22, default 3: compress/zstandard.rs:46; deflate 0..9, default 6:
+// compress/deflate.rs:89) selects one of this encoder's settings:
+//   0 fast     greedy parse, Predefined FSE tables                      zstd 1-2, deflate 1-3
+//   1 default  greedy parse, per-block FSE tables chosen by cost        zstd 3-5 (and < 0 / 0 = default), deflate 4-6 (and < 0)
+//   2 high     lazy parse (one position of look-ahead) + per-block FSE  zstd >= 6, deflate 7-9
+//   3 stored   deflate level 0: stored blocks only
+inline uint32_t enc_effort(uint8_t compression, int32_t level) {
+    if (compression == 2) return level <= 0 ? 1u : level <= 2 ? 0u : level <= 5 ? 1u : 2u;
+    if (compression == 1) return level < 0 ? 1u : level == 0 ? 3u : level <= 3 ? 0u : level <= 6 ? 1u : 2u;
+    return 1u;
+}
 constexpr uint32_t TMP_HEAD = 16;
 // zstd: a new FRAME every FRAME_SEGS segments (1 MiB of input).  Blocks never reference earlier blocks here, so the split costs
 // 6 bytes per MiB and nothing else; a reader that executes matches frame by frame (ours: one LZ unit per frame) gets
@@ -48,7 +59,7 @@ struct EncEntry {
     uint32_t n_pieces;             // device written
     int32_t key_idx;
     int32_t status;
-    uint8_t compression, encryption, cipher_mode, _pad;
+    uint8_t compression, encryption, cipher_mode, effort;   // effort: enc_effort(compression, level)
     uint8_t iv[16];
     // GCM STREAM (cipher mode 2): segment size, this entry's ranges in the plan's segment / tile slot tables, stream header
     uint32_t gcm_seg_size, gcm_slot_begin, gcm_tile_begin, gcm_tiles_per_seg, gcm_pow_idx;
@@ -159,6 +170,12 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
             if (lw >= MIN_MATCH && lw >= ltb) { best = lw; boff = p - cw; }
             else if (ltb >= MIN_MATCH) { best = ltb; boff = p - ct; }
         }
+        // lazy matching (high effort): a match gives way to a strictly longer one that starts at the next position -- its first
+        // byte becomes a literal.  (Lane 31 cannot see its successor and stays greedy.)
+        if (sr.effort >= 2u) {
+            const uint32_t nb = __shfl_down_sync(0xFFFFFFFFu, best, 1);
+            if (lane < 31 && best && nb > best) best = 0;
+        }
         // ---- greedy parse of the step: orbit of `carry` under p -> p + (match ? len : 1), by pointer doubling
         uint32_t J = (uint32_t)lane + (best ? best : 1u);
         bool M = (uint32_t)lane >= carry;                      // no match anywhere in the step: everything from carry on is a literal
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
         bool fits = true;
         if (nseq) {
             zstd_assign_repcodes(sq, nseq);
-            const uint32_t r = zstd_write_sequences(T, sq, nseq, body + sbase, TMP_SEG - TMP_HEAD - sbase);
+            const uint32_t r = zstd_write_sequences(T, sq, nseq, body + sbase, TMP_SEG - TMP_HEAD - sbase, sr.effort >= 1u);
             if (r == 0xFFFFFFFFu) fits = false;
             soff = r >> 24; ssz = r & 0xFFFFFFu;
         } else body[sbase] = 0;
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
         }
     } else {
         const uint32_t sz = deflate_write_segment(sq, nseq, work + sr.lit_off, nlit, last != 0, body);
-        if (sz >= len + 5) {
+        if (sz >= len + 5 || sr.effort == 3u) {   // effort 3: deflate level 0 = stored blocks
             head[0] = (uint8_t)(last ? 1 : 0); head[1] = (uint8_t)len; head[2] = (uint8_t)(len >> 8);
             head[3] = (uint8_t)~len; head[4] = (uint8_t)(~len >> 8);
             sr.head_len = 5; sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0;

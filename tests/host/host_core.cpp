@@ -174,6 +174,8 @@ extern "C" int hc_inflate(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t 
 // warp-synchronous matcher of kernels_encode.cuh); output must decode with libzstd / zlib (checked in Python)
 #include "../../portable-network-archive_b200/csrc/encode_core.cuh"
 static pna::enc::EncTables g_enc; static bool g_enc_init = false;
+static int g_enc_dyn = 1;   // per-block FSE tables (the default effort) or predefined ones (the fast setting)
+extern "C" void hc_set_enc_dyn(int v) { g_enc_dyn = v; }
 static void greedy_segment(const uint8_t* d, uint32_t len, std::vector<pna::enc::Seq>& seqs, std::vector<uint8_t>& lits) {
     using namespace pna::enc;
     std::vector<int32_t> head(1 << 13, -1);
@@ -220,7 +222,7 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
         uint8_t* t4 = tmp.data() + ((4 - ((uintptr_t)tmp.data() & 3)) & 3);
         if (compression == 2) {
             uint32_t ssz = 1, soff = 0;
-            if (!seqs.empty()) { zstd_assign_repcodes(seqs.data(), (uint32_t)seqs.size()); uint32_t r = zstd_write_sequences(g_enc, seqs.data(), (uint32_t)seqs.size(), t4, 2 * SEG); soff = r >> 24; ssz = r & 0xFFFFFF; }
+            if (!seqs.empty()) { zstd_assign_repcodes(seqs.data(), (uint32_t)seqs.size()); uint32_t r = zstd_write_sequences(g_enc, seqs.data(), (uint32_t)seqs.size(), t4, 2 * SEG, g_enc_dyn != 0); soff = r >> 24; ssz = r & 0xFFFFFF; }
             else { t4[0] = 0; }
             uint8_t lh[5]; uint32_t lhn = 0;
             std::vector<uint8_t> cl(lits.size() + 64);
@@ -332,3 +334,64 @@ extern "C" int hc_xz_decode(const uint8_t* in, uint64_t len, uint8_t* out, uint6
     return pna::xz::xz_decode(in, len, out, cap, out_len, probs.data());
 }
 extern "C" int hc_xz_size(const uint8_t* in, uint64_t len, uint64_t* out_len) { return pna::xz::xz_stream_size(in, len, out_len); }
+
+// ---- development aid: where do an encoded stream's bytes go?  stats[0..5] = literals, sequences, bytes of the literal
+// sections, bytes of the sequence sections, empirical-entropy bytes of the (ll, ml, of) codes + extra bits per block, and
+// the extra bits alone (what a per-block FSE table could reach at best, table headers not counted)
+#include <cmath>
+extern "C" void hc_encode_stats(const uint8_t* in, uint64_t len, double* stats) {
+    using namespace pna::enc;
+    if (!g_enc_init) { make_enc_tables(&g_enc); g_enc_init = true; }
+    for (int i = 0; i < 24; i++) stats[i] = 0;
+    const uint64_t nseg = (len + SEG - 1) / SEG;
+    for (uint64_t s = 0; s < nseg; s++) {
+        const uint8_t* d = in + s * SEG;
+        const uint32_t n = (uint32_t)(len - s * SEG < SEG ? len - s * SEG : SEG);
+        std::vector<Seq> seqs; std::vector<uint8_t> lits;
+        greedy_segment(d, n, seqs, lits);
+        stats[0] += lits.size(); stats[1] += seqs.size();
+        std::vector<uint8_t> tmp(2 * SEG + 64), cl(lits.size() + 64);
+        uint8_t* t4 = tmp.data() + ((4 - ((uintptr_t)tmp.data() & 3)) & 3);
+        uint8_t lh[5]; uint32_t lhn = 0;
+        const uint32_t clit = zstd_write_literals(lits.data(), (uint32_t)lits.size(), cl.data(), lh, &lhn);
+        stats[2] += lhn + (clit ? clit : lits.size());
+        if (seqs.empty()) continue;
+        zstd_assign_repcodes(seqs.data(), (uint32_t)seqs.size());
+        const uint32_t r = zstd_write_sequences(g_enc, seqs.data(), (uint32_t)seqs.size(), t4, 2 * SEG, g_enc_dyn != 0);
+        stats[3] += r & 0xFFFFFF;
+        double hl[36] = {0}, hm[53] = {0}, ho[32] = {0}, extra = 0;
+        for (const Seq& q : seqs) {
+            const uint32_t ll = q.llml & 0xFFFFu, mlb = (q.llml >> 16) - 3u, ob = (q.off & SEQ_REPCODE) ? (q.off & 3u) : q.off + 3u;
+            const uint32_t c1 = ll_code_of(g_enc, ll), c2 = ml_code_of(g_enc, mlb), c3 = (uint32_t)pna::highbit32(ob);
+            hl[c1]++; hm[c2]++; ho[c3]++;
+            extra += pna::zs::ll_bits((int)c1) + pna::zs::ml_bits((int)c2) + c3;
+        }
+        double bits = extra;
+        const double N = (double)seqs.size();
+        for (double c : hl) if (c > 0) bits += -c * std::log2(c / N);
+        for (double c : hm) if (c > 0) bits += -c * std::log2(c / N);
+        for (double c : ho) if (c > 0) bits += -c * std::log2(c / N);
+        stats[4] += bits / 8; stats[5] += extra / 8;
+        // cost with counts normalised to 2^L (every present symbol >= 1), L = 5..9 -> stats[8 + L]
+        for (int L = 5; L <= 9; L++) {
+            double tb = extra;
+            for (int t = 0; t < 3; t++) {
+                double* h = t == 0 ? hl : t == 1 ? hm : ho;
+                const int ns = t == 0 ? 36 : t == 1 ? 53 : 32;
+                int norm[64]; int sum = 0, big = 0;
+                const int size = 1 << L;
+                int present = 0;
+                for (int k = 0; k < ns; k++) if (h[k] > 0) present++;
+                if (present > size) { tb += 1e9; continue; }
+                for (int k = 0; k < ns; k++) { norm[k] = h[k] > 0 ? std::max(1, (int)std::lround(h[k] * size / N)) : 0; sum += norm[k]; if (norm[k] > norm[big]) big = k; }
+                while (sum != size) {
+                    big = 0; for (int k = 0; k < ns; k++) if (norm[k] > norm[big]) big = k;
+                    if (sum > size) { norm[big]--; sum--; } else { norm[big]++; sum++; }
+                }
+                for (int k = 0; k < ns; k++) if (h[k] > 0) tb += -h[k] * std::log2((double)norm[k] / size);
+                tb += 8 * (4 + present * 0.8);   // rough header: ~6 bits per present symbol
+            }
+            stats[8 + L] += tb / 8;
+        }
+    }
+}

@@ -87,6 +87,39 @@ def test_ratio_reported_against_reference_level(ctx, oracle):
         assert st == [0] and len(s) / ref < limit
 
 
+def test_level_selects_the_encoder_setting(ctx, oracle):
+    """`level` (WriteOptions -> compress/zstandard.rs:46, compress/deflate.rs:89) is honoured: fast (zstd 1-2 / deflate 1-3:
+    greedy + Predefined tables), default (per-block FSE tables), high (zstd >= 6 / deflate 7-9: lazy parse), deflate 0 = stored.
+    Every setting decodes with the reference codecs; sizes are ordered on compressible data; all kinds of input survive."""
+    p = corpus.make_file(6, 1 << 20)
+    for comp, levels in ((2, (1, 3, -1, 9, 19)), (1, (0, 1, 6, -1, 9))):
+        ents = [{"plain": p, "compression": comp, "level": lv} for lv in levels]
+        streams, _, st = ctx.encode_batch(ents)
+        assert st == [0] * len(ents)
+        sizes = {lv: len(s) for lv, s in zip(levels, streams)}
+        for s in streams:
+            assert oracle.decompress(comp, s.tobytes()) == p
+        print(f"compression={comp} sizes by level: {sizes}")
+        if comp == 2:
+            assert sizes[3] == sizes[-1] and sizes[9] == sizes[19]
+            assert sizes[3] < 0.97 * sizes[1]            # per-block FSE tables: several per cent on this corpus
+            assert sizes[9] < sizes[3]                   # lazy parse helps on text-like data
+        else:
+            assert sizes[0] > len(p) and sizes[6] == sizes[-1] and sizes[9] <= sizes[6] <= sizes[1]
+    # per-block tables over every kind of block: RLE-mode tables (one repeated sequence shape), tiny blocks (stay Predefined),
+    # incompressible data, all levels
+    kinds = [bytes(200_000), (b"abcdefgh" * 30_000), os.urandom(70_000), corpus.make_file(8, 47), corpus.make_file(9, 3000),
+             b"".join(bytes([i & 255]) * (1 + i % 7) for i in range(40_000)), corpus.make_file(10, 700_000)]
+    ents = [{"plain": k, "compression": 2, "level": lv} for k in kinds for lv in (1, 3, 9)]
+    streams, _, st = ctx.encode_batch(ents)
+    assert st == [0] * len(ents)
+    for e, s in zip(ents, streams):
+        assert oracle.decompress(2, s.tobytes()) == e["plain"]
+    back, st2, _ = ctx.decode_batch([{"bodies": [s], "compression": 2, "encryption": 0, "cipher_mode": 0, "key": None, "raw_size_hint": None}
+                                     for s in streams])
+    assert st2 == [0] * len(ents) and all(b.tobytes() == e["plain"] for b, e in zip(back, ents))
+
+
 def test_many_small_entries_and_builder_api(ctx, pna, oracle):
     """create path through the host mirror (FileEntryBuilder -> Archive.add_entry -> finalize), read back by the
     oracle's restatement of the reference reader: container framing, chunk CRCs, PHSF, fSIZ, entries."""
