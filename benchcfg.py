@@ -67,7 +67,7 @@ def cfg1(pna, host, ctx, corpus_np, threads, scale, workers):
     state = {}
 
     def create():
-        state["blob"] = host.create_archive(list(zip(names, views)), compression=2, level=3, max_chunk_size=0, device=ctx.device, workers=2,
+        state["blob"] = host.create_archive((names, plain, offs), compression=2, level=3, max_chunk_size=0, device=ctx.device, workers=2,
                                             group_bytes=256 << 20, out=arch)
     c_dt, _ = _timed(create, 2)
     blob = state["blob"]

@@ -187,6 +187,12 @@ int pna_cuda_encode_plan_run(pna_plan* plan);
 int pna_cuda_encode_plan_lengths(pna_plan* plan, uint64_t* out_len, int32_t* status);
 int pna_cuda_encode_plan_fetch(pna_plan* plan, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out,
                                int32_t* status);
+/* The same, for a caller that owns one contiguous `region` into which every out[i] points (an archive being assembled, the
+ * chunk frames between the streams still to be written): when the streams are many, small and close together they come down
+ * in ONE copy of the span they cover, laid out on the device first -- the bytes of that span BETWEEN the streams are
+ * unspecified afterwards.  Falls back to one copy per stream whenever that does not apply.  region == NULL: plain fetch. */
+int pna_cuda_encode_plan_fetch_region(pna_plan* plan, pna_buf* out, uint8_t* region, uint64_t region_len, uint32_t* fdat_crc_out,
+                                      uint32_t* crc_count_out, int32_t* status);
 
 /* stage names of an encode plan for pna_cuda_plan_stage_ms (first 5 entries: lz_match, block_write, layout, cipher, crc) */
 const char* pna_cuda_encode_stage_name(uint32_t stage);

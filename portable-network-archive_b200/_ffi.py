@@ -21,6 +21,7 @@ EXPORTS = [
     "pna_cuda_decode_plan_lengths", "pna_cuda_decode_plan_crc32_out", "pna_cuda_decode_plan_fetch_ranges",
     "pna_cuda_plan_stats", "pna_cuda_plan_counts", "pna_cuda_plan_stage_ms", "pna_cuda_stage_name", "pna_cuda_encode_stage_name", "pna_cuda_plan_destroy", "pna_cuda_encode_bound", "pna_cuda_encode_crc_count",
     "pna_cuda_encode_batch", "pna_cuda_encode_plan_create", "pna_cuda_encode_plan_run", "pna_cuda_encode_plan_lengths", "pna_cuda_encode_plan_fetch",
+    "pna_cuda_encode_plan_fetch_region",
     "pna_cuda_ecb", "pna_cuda_gcm_stream_key", "pna_cuda_gcm_stream_header",
 ]
 
@@ -112,6 +113,7 @@ def lib():
     L.pna_cuda_encode_plan_run.argtypes = [vp]
     L.pna_cuda_encode_plan_lengths.argtypes = [vp, C.POINTER(u64), i32p]
     L.pna_cuda_encode_plan_fetch.argtypes = [vp, C.POINTER(Buf), C.POINTER(u32), C.POINTER(u32), i32p]
+    L.pna_cuda_encode_plan_fetch_region.argtypes = [vp, C.POINTER(Buf), vp, u64, C.POINTER(u32), C.POINTER(u32), i32p]
     L.pna_cuda_ecb.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, vp, u64, vp]
     L.pna_cuda_gcm_stream_key.argtypes = [C.c_char_p, C.c_char_p, u64, C.c_char_p, C.c_char_p, u64, C.c_char_p, u64, C.c_char_p]
     L.pna_cuda_gcm_stream_key.restype = C.c_int32

@@ -294,15 +294,27 @@ def split_layout(archive, max_part_bytes: int, max_parts: int = 1 << 16):
 
 def create_archive(files, compression=0, level=-1, encryption=0, cipher_mode=1, key=None, phsf=None, ivs=None, max_chunk_size=0,
                    device=0, workers=3, group_bytes=256 << 20, out=None, devices=None):
-    """files: list of (name, bytes-like).  Returns the archive bytes (numpy view of `out` when given).
+    """files: list of (name, bytes-like), or the packed form (names, uint8 buffer, offsets[n + 1]).  Returns the archive bytes (numpy view of `out` when given).
     ivs: 16 bytes per file, or None: the writer draws a fresh IV per entry from the OS (entry/write.rs:108-111).
     devices: list of GPUs to partition the files over (`workers` threads each); default: the single `device`."""
     L = lib()
-    n = len(files)
-    arrs = [f[1] if isinstance(f[1], np.ndarray) else np.frombuffer(f[1], dtype=np.uint8) for f in files]
-    names = (C.c_char_p * max(n, 1))(*[f[0].encode() for f in files])
-    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
-    lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrs])
+    if isinstance(files, tuple) and len(files) == 3:
+        # packed form (names, buffer, offsets[n + 1]): file i is buffer[offsets[i]:offsets[i + 1]] -- no per-file Python objects
+        fnames, fbuf, foffs = files
+        n = len(fnames)
+        foffs = np.ascontiguousarray(foffs, dtype=np.uint64)
+        assert foffs.size == n + 1 and int(foffs[-1]) <= fbuf.size
+        names = (C.c_char_p * max(n, 1))(*[x.encode() for x in fnames])
+        lens_np = np.ascontiguousarray(np.diff(foffs), dtype=np.uint64)
+        ptrs_np = np.ascontiguousarray(foffs[:-1] + np.uint64(fbuf.ctypes.data), dtype=np.uint64)
+        ptrs = (C.c_void_p * max(n, 1)).from_buffer(ptrs_np) if n else (C.c_void_p * 1)()
+        lens = (C.c_uint64 * max(n, 1)).from_buffer(lens_np) if n else (C.c_uint64 * 1)()
+    else:
+        n = len(files)
+        arrs = [f[1] if isinstance(f[1], np.ndarray) else np.frombuffer(f[1], dtype=np.uint8) for f in files]
+        names = (C.c_char_p * max(n, 1))(*[f[0].encode() for f in files])
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+        lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrs])
     bound = int(L.pnah_create_bound(n, names, lens, compression, encryption, (phsf or "").encode(), max_chunk_size))
     if out is None:
         out = np.empty(bound, dtype=np.uint8)
@@ -325,11 +337,23 @@ def create_solid_archive(files, compression=0, level=-1, encryption=0, cipher_mo
     """Solid mode (archive/write.rs:438-471): every file a STORE entry inside one compressed (+ encrypted) stream of SDAT bodies.
     files: list of (name, bytes-like).  Returns the archive bytes."""
     L = lib()
-    n = len(files)
-    arrs = [f[1] if isinstance(f[1], np.ndarray) else np.frombuffer(f[1], dtype=np.uint8) for f in files]
-    names = (C.c_char_p * max(n, 1))(*[f[0].encode() for f in files])
-    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
-    lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrs])
+    if isinstance(files, tuple) and len(files) == 3:
+        # packed form (names, buffer, offsets[n + 1]): file i is buffer[offsets[i]:offsets[i + 1]] -- no per-file Python objects
+        fnames, fbuf, foffs = files
+        n = len(fnames)
+        foffs = np.ascontiguousarray(foffs, dtype=np.uint64)
+        assert foffs.size == n + 1 and int(foffs[-1]) <= fbuf.size
+        names = (C.c_char_p * max(n, 1))(*[x.encode() for x in fnames])
+        lens_np = np.ascontiguousarray(np.diff(foffs), dtype=np.uint64)
+        ptrs_np = np.ascontiguousarray(foffs[:-1] + np.uint64(fbuf.ctypes.data), dtype=np.uint64)
+        ptrs = (C.c_void_p * max(n, 1)).from_buffer(ptrs_np) if n else (C.c_void_p * 1)()
+        lens = (C.c_uint64 * max(n, 1)).from_buffer(lens_np) if n else (C.c_uint64 * 1)()
+    else:
+        n = len(files)
+        arrs = [f[1] if isinstance(f[1], np.ndarray) else np.frombuffer(f[1], dtype=np.uint8) for f in files]
+        names = (C.c_char_p * max(n, 1))(*[f[0].encode() for f in files])
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+        lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrs])
     bound = int(L.pnah_create_solid_bound(n, names, lens, compression, encryption, cipher_mode, (phsf or "").encode(), max_chunk_size))
     if out is None:
         out = np.empty(bound, dtype=np.uint8)

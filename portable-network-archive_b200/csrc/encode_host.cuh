@@ -25,6 +25,8 @@ struct EncodePlan {
     DevArr<CrcTileSrc> d_crc_src;
     DevArr<CrcTile> d_crc_tiles;
     DevArr<EncTables> d_tables;
+    DevArr<uint8_t> d_stage;                  // coalesced transfers: many small adjacent host spans travel as one copy
+    DevArr<CopyJob> d_stage_jobs;
     uint32_t fdat_init = 0;
     // GCM STREAM: segment / tile slots from the compressed-length bounds (AES slots first, then Camellia)
     std::vector<GcmSlot> h_gcm_slots;
@@ -225,9 +227,51 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
     CK(E->d_entries.reserve(n)); CK(E->d_entries_init.reserve(n));
     CK(E->d_segs.reserve(nsegs_total)); CK(E->d_seqs.reserve(E->seq_total + 8)); CK(E->d_pieces.reserve(piece_cur + 1));
     CK(E->d_keys.reserve(E->h_keys.size())); CK(E->d_tables.reserve(1));
-    for (uint32_t i = 0; i < n; i++)
-        if (descs[i].plain.len && E->h_entries[i].status == ST_OK)
-            CK(cudaMemcpyAsync(E->d_work.p + E->h_entries[i].plain_off, descs[i].plain.ptr, descs[i].plain.len, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        // Upload of the plaintext.  A cudaMemcpyAsync costs the host 5-10 us whatever its size, which is what a group of
+        // thousands of small files is made of -- so runs of entries whose host spans are exactly adjacent (files packed into one
+        // buffer, the common case) travel as ONE copy into a staging buffer and are scattered to their padded places by a kernel.
+        constexpr uint64_t SMALL = 1 << 20, PIECE = 32 << 10;
+        std::vector<CopyJob> jobs;
+        struct Run { uint32_t lo, hi; uint64_t stage_off, bytes; };
+        std::vector<Run> runs;
+        uint64_t stage_bytes = 0;
+        for (uint32_t i = 0; i < n;) {
+            uint32_t j = i;
+            uint64_t bytes = 0;
+            auto ok = [&](uint32_t k) { return descs[k].plain.len && descs[k].plain.len < SMALL && E->h_entries[k].status == ST_OK; };
+            if (ok(i)) {
+                bytes = descs[i].plain.len;
+                j = i + 1;
+                while (j < n && ok(j) && descs[j - 1].plain.ptr + descs[j - 1].plain.len == descs[j].plain.ptr) { bytes += descs[j].plain.len; j++; }
+            }
+            if (j - i >= 4) { runs.push_back({i, j, stage_bytes, bytes}); stage_bytes += align_up(bytes, 256); i = j; continue; }
+            const uint32_t end = j > i ? j : i + 1;
+            for (uint32_t k = i; k < end; k++)
+                if (descs[k].plain.len && E->h_entries[k].status == ST_OK)
+                    CK(cudaMemcpyAsync(E->d_work.p + E->h_entries[k].plain_off, descs[k].plain.ptr, descs[k].plain.len, cudaMemcpyHostToDevice, ctx->stream));
+            i = end;
+        }
+        if (!runs.empty()) {
+            CK(E->d_stage.reserve(stage_bytes + 256));
+            for (const Run& r : runs) {
+                CK(cudaMemcpyAsync(E->d_stage.p + r.stage_off, descs[r.lo].plain.ptr, r.bytes, cudaMemcpyHostToDevice, ctx->stream));
+                uint64_t at = r.stage_off;
+                for (uint32_t k = r.lo; k < r.hi; k++) {
+                    for (uint64_t o = 0; o < descs[k].plain.len; o += PIECE)
+                        jobs.push_back({E->h_entries[k].plain_off + o, at + o, std::min<uint64_t>(PIECE, descs[k].plain.len - o)});
+                    at += descs[k].plain.len;
+                }
+            }
+            CK(E->d_stage_jobs.reserve(jobs.size()));
+            CK(cudaMemcpyAsync(E->d_stage_jobs.p, jobs.data(), jobs.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
+            const uint32_t grid = std::min<uint32_t>(((uint32_t)jobs.size() + 7) / 8, (uint32_t)ctx->sm_count * 8);
+            copy_jobs_kernel<<<grid, 256, 0, ctx->stream>>>(E->d_work.p, E->d_stage.p, E->d_stage_jobs.p, (uint32_t)jobs.size());
+            LAUNCHED();
+            CK(ctx->sync());   // `jobs` is a local; the staging buffer goes back to the cache
+            E->d_stage.release();
+        }
+    }
     CK(cudaMemcpyAsync(E->d_entries_init.p, E->h_entries.data(), n * sizeof(EncEntry), cudaMemcpyHostToDevice, ctx->stream));
     if (nsegs_total) CK(cudaMemcpyAsync(E->d_segs.p, E->h_segs.data(), nsegs_total * sizeof(enc::SegRec), cudaMemcpyHostToDevice, ctx->stream));
     if (!E->h_keys.empty()) CK(cudaMemcpyAsync(E->d_keys.p, E->h_keys.data(), E->h_keys.size() * sizeof(DevKeys), cudaMemcpyHostToDevice, ctx->stream));
@@ -400,7 +444,18 @@ extern "C" int pna_cuda_encode_plan_lengths(pna_plan* P, uint64_t* out_len, int3
     for (uint32_t i = 0; i < P->n; i++) { status[i] = dev[i].status; out_len[i] = dev[i].status == ST_OK ? dev[i].out_len : 0; }
     return PNA_OK;
 }
+static int encode_plan_fetch_impl(pna_plan* P, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status, uint8_t* region,
+                                  uint64_t region_len);
 extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status) {
+    return encode_plan_fetch_impl(P, out, fdat_crc_out, crc_count_out, status, nullptr, 0);
+}
+extern "C" int pna_cuda_encode_plan_fetch_region(pna_plan* P, pna_buf* out, uint8_t* region, uint64_t region_len, uint32_t* fdat_crc_out,
+                                                 uint32_t* crc_count_out, int32_t* status) {
+    if (!region && region_len) return PNA_E_BAD_ARG;
+    return encode_plan_fetch_impl(P, out, fdat_crc_out, crc_count_out, status, region, region_len);
+}
+static int encode_plan_fetch_impl(pna_plan* P, pna_buf* out, uint32_t* fdat_crc_out, uint32_t* crc_count_out, int32_t* status, uint8_t* region,
+                                  uint64_t region_len) {
     if (!P || P->kind != 1 || ((!out || !status) && P->n)) return PNA_E_BAD_ARG;
     if (P->multi) return multi::encode_plan_fetch(P, out, fdat_crc_out, crc_count_out, status);
     pna_ctx* ctx = P->ctx;
@@ -416,6 +471,43 @@ extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* f
         CK(cudaMemcpyAsync(crcs.data(), E->d_crc_val.p, crcs.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx->sync());
     uint64_t stream_bytes = 0, crc_pos = 0;
+    // The caller owns `region` entirely and every stream lands inside it: when the streams are many and close together (a
+    // group of small files on their way into an archive, frames between them), the device lays them out as they will lie
+    // in the region and ONE copy brings the whole span down; what lies between the streams is unspecified afterwards.
+    bool staged = false;
+    if (region && P->n >= 16) {
+        const uint8_t* lo = nullptr; const uint8_t* hi = nullptr;
+        uint64_t total = 0;
+        bool fits = true;
+        for (uint32_t i = 0; i < P->n; i++) {
+            const EncEntry& e = dev[i];
+            if (e.status != ST_OK || e.out_len == 0) continue;
+            if (e.out_len > out[i].cap) continue;   // reported below as NOSPACE, not copied
+            if (out[i].ptr < region || out[i].ptr + e.out_len > region + region_len) { fits = false; break; }
+            if (!lo || out[i].ptr < lo) lo = out[i].ptr;
+            if (!hi || out[i].ptr + e.out_len > hi) hi = out[i].ptr + e.out_len;
+            total += e.out_len;
+        }
+        const uint64_t span = lo ? (uint64_t)(hi - lo) : 0;
+        if (fits && lo && total / P->n < (1u << 20) && span <= total + total / 4 + 4096) {
+            constexpr uint64_t PIECE = 32 << 10;
+            std::vector<CopyJob> jobs;
+            for (uint32_t i = 0; i < P->n; i++) {
+                const EncEntry& e = dev[i];
+                if (e.status != ST_OK || e.out_len == 0 || e.out_len > out[i].cap) continue;
+                for (uint64_t o = 0; o < e.out_len; o += PIECE)
+                    jobs.push_back({(uint64_t)(out[i].ptr - lo) + o, e.out_off + o, std::min<uint64_t>(PIECE, e.out_len - o)});
+            }
+            CK(E->d_stage.reserve(span + 256)); CK(E->d_stage_jobs.reserve(jobs.size()));
+            CK(cudaMemcpyAsync(E->d_stage_jobs.p, jobs.data(), jobs.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
+            const uint32_t grid = std::min<uint32_t>(((uint32_t)jobs.size() + 7) / 8, (uint32_t)ctx->sm_count * 8);
+            copy_jobs_kernel<<<grid, 256, 0, ctx->stream>>>(E->d_stage.p, E->d_out.p, E->d_stage_jobs.p, (uint32_t)jobs.size());
+            LAUNCHED();
+            CK(cudaMemcpyAsync(const_cast<uint8_t*>(lo), E->d_stage.p, span, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(ctx->sync());   // `jobs` is a local
+            staged = true;
+        }
+    }
     for (uint32_t i = 0; i < P->n; i++) {
         const EncEntry& e = dev[i];
         int32_t st = e.status;
@@ -425,7 +517,7 @@ extern "C" int pna_cuda_encode_plan_fetch(pna_plan* P, pna_buf* out, uint32_t* f
         status[i] = st;
         uint32_t nbody = 0;
         if (st == ST_OK) {
-            if (len) CK(cudaMemcpyAsync(out[i].ptr, E->d_out.p + e.out_off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            if (len && !staged) CK(cudaMemcpyAsync(out[i].ptr, E->d_out.p + e.out_off, len, cudaMemcpyDeviceToHost, ctx->stream));
             stream_bytes += len;
             const uint64_t iv_len = e.encryption ? (e.cipher_mode == PNA_CIPHER_GCM ? gcm::GCM_HEADER_LEN : 16) : 0, mcs = E->crc_body_size[i];
             nbody = (uint32_t)((len - iv_len + mcs - 1) / mcs);

@@ -936,7 +936,7 @@ static uint64_t create_archive_regions(const std::vector<FileEntryBuilder>& file
         }
         std::vector<uint32_t> crcs(S.crc_total + 1), ncrc(m, 0);
         const double tr4 = ms_now();
-        ck(L.ctx, pna_cuda_encode_plan_fetch(S.plan, bufs.data(), crcs.data(), ncrc.data(), st.data()), "encode_plan_fetch");
+        ck(L.ctx, pna_cuda_encode_plan_fetch_region(S.plan, bufs.data(), out + my_base, entry_pos[m], crcs.data(), ncrc.data(), st.data()), "encode_plan_fetch");
         const double tr5 = ms_now();
         size_t cpos = 0;
         for (uint32_t k = 0; k < m; k++) {

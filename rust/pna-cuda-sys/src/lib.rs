@@ -135,6 +135,7 @@ extern "C" {
     pub fn pna_cuda_encode_plan_run(plan: *mut pna_plan) -> c_int;
     pub fn pna_cuda_encode_plan_lengths(plan: *mut pna_plan, out_len: *mut u64, status: *mut i32) -> c_int;
     pub fn pna_cuda_encode_plan_fetch(plan: *mut pna_plan, out: *mut pna_buf, fdat_crc_out: *mut u32, crc_count_out: *mut u32, status: *mut i32) -> c_int;
+    pub fn pna_cuda_encode_plan_fetch_region(plan: *mut pna_plan, out: *mut pna_buf, region: *mut u8, region_len: u64, fdat_crc_out: *mut u32, crc_count_out: *mut u32, status: *mut i32) -> c_int;
     pub fn pna_cuda_encode_stage_name(stage: u32) -> *const c_char;
     pub fn pna_cuda_gcm_stream_key(k_master: *const u8, stream_header: *const u8, stream_header_len: u64, header_type: *const u8, header_data: *const u8, header_len: u64, phsf: *const u8, phsf_len: u64, out_key: *mut u8) -> i32;
     pub fn pna_cuda_gcm_stream_header(k_master: *const u8, salt: *const u8, nonce_prefix: *const u8, segment_size: u32, out_header: *mut u8) -> i32;

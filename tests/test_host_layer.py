@@ -23,7 +23,7 @@ def test_host_exports_match_header(host):
     hdr = open(os.path.join(ROOT, "include", "pna_host.hpp")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(pnah_\w+)\s*\(", hdr))
-    lib = C.CDLL(os.path.join(ROOT, "portable-network-archive_b200", "libpna_host.so"))
+    lib = C.CDLL(host.LIB_PATH)   # the in-tree build (under --emu: the emulator build -- two libraries of one soname cannot share a process)
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(host.EXPORTS)
@@ -181,6 +181,31 @@ def test_create_with_cpp_host_is_reference_readable(host, pna, ctx, oracle, comp
         a.set_key(opts.phsf, opts.key)
     back = a.read_all(workers=2, group_bytes=300_000)
     assert [(n, d) for n, _, d in back] == files and all(s == 0 for _, s, _ in back)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("comp,enc,mode,mcs", [(2, 0, 0, 0), (2, 1, 1, 0), (1, 2, 0, 0), (0, 0, 0, 0), (2, 0, 0, 50_000)])
+def test_create_from_packed_small_files_uses_coalesced_transfers(host, pna, ctx, oracle, comp, enc, mode, mcs):
+    """BASELINE config 1's shape in small: many small files that are slices of ONE buffer.  Their plaintext goes up as one copy
+    per run of adjacent files (scattered on the device), their streams come down as one copy per group into the archive region
+    (pna_cuda_encode_plan_fetch_region) -- the archive must be what the reference reader expects, byte for byte of content."""
+    sizes = [3000, 1, 70_000, 0, 0, 12_345, 999_999, 16, 15, 17, 2_000_000, 400, 500, 600, 700, 131_072, 32_768, 32_769] + [1000 + 37 * i for i in range(60)]
+    total = sum(sizes)
+    plain = ctx.pinned(total)
+    plain[:] = np.frombuffer(corpus.make_file(77, total), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    views = [plain[int(offs[i]):int(offs[i + 1])] for i in range(len(sizes))]
+    files = [(f"p/{i:03d}", v) for i, v in enumerate(views)]
+    opts = pna.WriteOptions(compression=comp, encryption=enc, cipher_mode=mode, password=b"pw", kdf_params={"i": 1000})
+    out = ctx.pinned(int(total * 1.1) + (1 << 20))
+    for form in (files, ([n for n, _ in files], plain, offs)):     # list of (name, view) and the packed (names, buffer, offsets) form
+        blob = host.create_archive(form, compression=comp, encryption=enc, cipher_mode=mode, key=opts.key, phsf=opts.phsf,
+                                   max_chunk_size=mcs, workers=2, group_bytes=1 << 20, out=out)
+        got = list(oracle.extract_all(blob.tobytes(), b"pw"))
+        assert [n for n, _ in got] == [n for n, _ in files]
+        assert all(d == v.tobytes() for (_, d), v in zip(got, views))
+    ctx.pinned_free(out)
+    ctx.pinned_free(plain)
 
 
 @pytest.mark.gpu
