@@ -623,7 +623,10 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
         S.top = refs_[G.lo].owner == 0;
         const auto t0 = std::chrono::steady_clock::now();
         {
-            std::lock_guard<std::mutex> h2d(h2d_mu);   // one upload at a time: PCIe is the shared resource
+            // one upload at a time: PCIe is the shared resource -- unless the group is thousands of small entries, whose plan
+            // construction is host work (descriptors, chunk spans, CRC tiles) that dwarfs the upload: those build in parallel
+            std::unique_lock<std::mutex> h2d(h2d_mu, std::defer_lock);
+            if (m <= 2048) h2d.lock();
             if (verify && S.top && crange[g].second > crange[g].first) {
                 const uint32_t c0 = crange[g].first, c1 = crange[g].second, nc = c1 - c0;
                 S.spans.resize(nc); S.expect.resize(nc); S.owner.assign(nc, -1);

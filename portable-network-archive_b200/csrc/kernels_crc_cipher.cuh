@@ -5,6 +5,7 @@
 // tile tables, tables are staged into shared memory once per CTA.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "crc32_core.cuh"
 #include "cipher_core.cuh"
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(CRC_WIDE_THREADS, 1) crc_tiles_wide_kernel(con
 // tiles of a batch: the wide kernel once there is enough work to pay for its table fill on every SM
 static inline void launch_crc_tiles(cudaStream_t stream, int sm_count, const uint8_t* img, const CrcTile* tiles, uint32_t nt, const CrcConsts* C,
                                     uint32_t* raw) {
-    if (nt >= 512u) {   // every SM takes part; warps per CTA follow the work (4 .. 32)
+    static const uint32_t wide_min = [] { const char* e = getenv("PNA_CRC_WIDE_MIN"); return e ? (uint32_t)strtoul(e, nullptr, 10) : 512u; }();
+    if (nt >= wide_min) {   // every SM takes part; warps per CTA follow the work (4 .. 32)
         const uint32_t warps = std::min<uint32_t>(32u, std::max<uint32_t>(4u, (nt + (uint32_t)sm_count - 1) / (uint32_t)sm_count));
         const uint32_t grid = std::min<uint32_t>((nt + warps - 1) / warps, (uint32_t)sm_count);
         crc_tiles_wide_kernel<<<grid, 32 * warps, CRC_WIDE_SMEM, stream>>>(img, tiles, nt, C, raw);
