@@ -527,31 +527,193 @@ PNA_HD void deflate_dist_sym(uint32_t dist, uint32_t* sym, uint32_t* xb, uint32_
     *sym = 2 * hb + ((d >> eb) & 1);
     *xb = eb; *xv = d & ((1u << eb) - 1u);
 }
-// One segment as a fixed-Huffman block (+ sync marker unless final).  lits = the segment's literal bytes in
-// order, n_lit_total of them (sequence literal runs first, the rest trail).  dst 4-byte aligned, room for
-// 9/8 * len + 16.  Returns bytes written.
+// Length-limited Huffman code lengths for count[0..n) (n <= NMAX): len_of[s] = 0 for absent symbols.  Two-queue merge over
+// the present symbols sorted by count, then miniz's length-limit repair (fold the too-long codes into the limit, pay the
+// Kraft excess back by splitting the longest code below it).  Returns the number of present symbols (0 and 1: no code built).
+template <int NMAX>
+PNA_HD uint32_t huff_lengths(const uint32_t* count, uint32_t stride, uint32_t n, uint32_t maxbits, uint8_t* len_of) {
+    uint16_t order[NMAX];
+    uint32_t m = 0;
+    for (uint32_t s = 0; s < n; s++) {
+        len_of[s] = 0;
+        if (count[s * stride]) order[m++] = (uint16_t)s;
+    }
+    // ascending by count: shell sort (an insertion sort moves ~m^2/4 keys -- ten thousand steps for a literal alphabet)
+    {
+        const uint32_t gaps[6] = {132, 57, 23, 10, 4, 1};
+        for (int gi = 0; gi < 6; gi++) {
+            const uint32_t gap = gaps[gi];
+            for (uint32_t i = gap; i < m; i++) {
+                const uint16_t v = order[i];
+                const uint32_t cv = count[v * stride];
+                uint32_t k = i;
+                while (k >= gap && count[order[k - gap] * stride] > cv) { order[k] = order[k - gap]; k -= gap; }
+                order[k] = v;
+            }
+        }
+    }
+    if (m < 2) return m;
+    uint32_t wt[2 * NMAX];       // weights while the tree is built, depths afterwards
+    uint16_t parent[2 * NMAX];
+    for (uint32_t k = 0; k < m; k++) wt[k] = count[order[k] * stride];
+    uint32_t li = 0, ni = m, no = m;
+    for (uint32_t k = 0; k + 1 < m; k++) {
+        uint32_t pick[2];
+        for (int q = 0; q < 2; q++) {
+            if (li < m && (ni >= no || wt[li] <= wt[ni])) pick[q] = li++;
+            else pick[q] = ni++;
+        }
+        wt[no] = wt[pick[0]] + wt[pick[1]];
+        parent[pick[0]] = (uint16_t)no; parent[pick[1]] = (uint16_t)no;
+        no++;
+    }
+    wt[no - 1] = 0;
+    for (uint32_t k = no - 1; k-- > 0;) wt[k] = wt[parent[k]] + 1;
+    uint32_t num[34];
+    for (uint32_t l = 0; l < 34; l++) num[l] = 0;
+    for (uint32_t k = 0; k < m; k++) num[wt[k] > 32 ? 32 : wt[k]]++;
+    for (uint32_t l = maxbits + 1; l < 33; l++) { num[maxbits] += num[l]; num[l] = 0; }
+    uint32_t total = 0;
+    for (uint32_t l = maxbits; l > 0; l--) total += num[l] << (maxbits - l);
+    while (total != (1u << maxbits)) {
+        num[maxbits]--;
+        for (uint32_t l = maxbits - 1; l > 0; l--)
+            if (num[l]) { num[l]--; num[l + 1] += 2; break; }
+        total--;
+    }
+    uint32_t k = m;
+    for (uint32_t l = 1; l <= maxbits; l++)
+        for (uint32_t c = 0; c < num[l]; c++) len_of[order[--k]] = (uint8_t)l;
+    return m;
+}
+// canonical deflate codes (RFC 1951 3.2.2) for len_of[0..n), bit-reversed for the LSB-first writer: code | nbits << 16
+PNA_HD void deflate_codes(const uint8_t* len_of, uint32_t n, uint32_t* code_of, uint32_t stride = 1) {
+    uint32_t bl_count[16], next[16];
+    for (int l = 0; l < 16; l++) bl_count[l] = 0;
+    for (uint32_t s = 0; s < n; s++) bl_count[len_of[s]]++;
+    bl_count[0] = 0;
+    uint32_t code = 0;
+    next[0] = 0;
+    for (int l = 1; l < 16; l++) { code = (code + bl_count[l - 1]) << 1; next[l] = code; }
+    for (uint32_t s = 0; s < n; s++) {
+        const uint32_t l = len_of[s];
+        code_of[s * stride] = l ? (rev_bits_n(next[l]++, (int)l) | (l << 16)) : 0u;
+    }
+}
+
+// One segment as ONE deflate block (+ sync marker unless final): dynamic Huffman when `dyn` and it is smaller by the exact bit
+// count, else fixed Huffman.  lits = the segment's literal bytes in order, n_lit_total of them (sequence literal runs first, the
+// rest trail).  dst 4-byte aligned, room for 9/8 * len + 16.  Returns bytes written.
+// ws: DEFLATE_WS 32-bit slots spaced `stride` words apart -- first the histograms, then the code tables: they are touched once or
+// twice per literal (the kernel passes a thread-local array with stride 1; the stride exists for table layouts shared by a CTA).
+constexpr uint32_t DEFLATE_WS = 286 + 30;
 PNA_HD uint32_t deflate_write_segment(const Seq* seqs, uint32_t nseq, const uint8_t* lits, uint32_t n_lit_total, bool final_seg,
-                                      uint8_t* dst) {
+                                      uint8_t* dst, bool dyn, uint32_t* ws, uint32_t stride) {
     BitOut b;
     b.init(dst);
-    b.add((final_seg ? 1u : 0u) | (1u << 1), 3);   // BFINAL, BTYPE=01
+    uint32_t* const ll_code = ws;
+    uint32_t* const d_code = ws + 286 * stride;
+    bool use_dyn = false;
+    if (dyn) {
+        // ---- histograms
+        uint32_t* const cl = ll_code;   // counts first, codes later
+        uint32_t* const cd = d_code;
+        for (uint32_t s = 0; s < DEFLATE_WS; s++) ws[s * stride] = 0;
+        uint64_t extra = 0;
+        for (uint32_t i = 0; i < n_lit_total; i++) cl[lits[i] * stride]++;
+        for (uint32_t i = 0; i < nseq; i++) {
+            uint32_t sym, xb, xv;
+            deflate_len_sym(seqs[i].llml >> 16, &sym, &xb, &xv);
+            cl[sym * stride]++; extra += xb;
+            deflate_dist_sym(seqs[i].off, &sym, &xb, &xv);
+            cd[sym * stride]++; extra += xb;
+        }
+        cl[256 * stride] = 1;
+        {   // at least two distance codes, as zlib's deflate writes them (readers that reject a lone / absent distance code)
+            uint32_t nd = 0;
+            for (uint32_t s = 0; s < 30; s++) nd += cd[s * stride] != 0;
+            if (nd < 2) { if (!cd[0]) cd[0] = 1; else cd[stride] = 1; if (nd == 0) cd[stride] = 1; }
+        }
+        uint8_t lens[286 + 30];
+        huff_lengths<286>(cl, stride, 286, 15, lens);
+        huff_lengths<30>(cd, stride, 30, 15, lens + 286);
+        uint32_t nl = 286, nd = 30;
+        while (nl > 257 && lens[nl - 1] == 0) nl--;
+        while (nd > 1 && lens[286 + nd - 1] == 0) nd--;
+        // ---- the two length sets as one run-length coded sequence over the code-length alphabet
+        uint8_t seq_len[286 + 30];
+        for (uint32_t i = 0; i < nl; i++) seq_len[i] = lens[i];
+        for (uint32_t i = 0; i < nd; i++) seq_len[nl + i] = lens[286 + i];
+        const uint32_t ntot = nl + nd;
+        uint16_t tok[286 + 30];      // symbol | extra value << 8
+        uint32_t ntok = 0;
+        uint32_t ccl[19];
+        for (int s = 0; s < 19; s++) ccl[s] = 0;
+        for (uint32_t i = 0; i < ntot;) {
+            const uint32_t v = seq_len[i];
+            uint32_t run = 1;
+            while (i + run < ntot && seq_len[i + run] == v) run++;
+            if (v == 0 && run >= 3) {
+                const uint32_t r = run > 138 ? 138 : run;
+                if (r <= 10) { tok[ntok++] = (uint16_t)(17 | ((r - 3) << 8)); ccl[17]++; }
+                else { tok[ntok++] = (uint16_t)(18 | ((r - 11) << 8)); ccl[18]++; }
+                i += r;
+            } else if (v != 0 && run >= 4) {
+                tok[ntok++] = (uint16_t)v; ccl[v]++;
+                const uint32_t r = run - 1 > 6 ? 6 : run - 1;
+                tok[ntok++] = (uint16_t)(16 | ((r - 3) << 8)); ccl[16]++;
+                i += 1 + r;
+            } else { tok[ntok++] = (uint16_t)v; ccl[v]++; i++; }
+        }
+        uint8_t cl_len[19];
+        const uint32_t mcl = huff_lengths<19>(ccl, 1, 19, 7, cl_len);
+        const uint8_t ord[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        uint32_t ncl = 19;
+        while (ncl > 4 && cl_len[ord[ncl - 1]] == 0) ncl--;
+        // ---- exact sizes of both forms
+        uint64_t bits_dyn = 3 + 5 + 5 + 4 + 3ull * ncl + extra, bits_fix = 3 + extra;
+        for (uint32_t t = 0; t < ntok; t++) { const uint32_t sy = tok[t] & 0xFF; bits_dyn += cl_len[sy] + (sy == 16 ? 2 : sy == 17 ? 3 : sy == 18 ? 7 : 0); }
+        for (uint32_t s = 0; s < 286; s++) { const uint64_t c = cl[s * stride]; bits_dyn += c * lens[s]; bits_fix += c * (fixed_litlen(s) >> 16); }
+        for (uint32_t s = 0; s < 30; s++) { const uint64_t c = cd[s * stride]; bits_dyn += c * lens[286 + s]; bits_fix += c * 5u; }
+        // (the forced extra distance code is counted in both and never emitted: an upper bound, equal for the comparison)
+        use_dyn = mcl >= 2 && bits_dyn < bits_fix;   // (fewer than two code-length symbols cannot happen: EOB has a length, absent symbols have none)
+        if (use_dyn) {
+            uint32_t cl_code[19];
+            deflate_codes(cl_len, 19, cl_code);
+            deflate_codes(lens, 286, ll_code, stride);
+            deflate_codes(lens + 286, 30, d_code, stride);
+            b.add((final_seg ? 1u : 0u) | (2u << 1), 3);   // BFINAL, BTYPE=10
+            b.add(nl - 257, 5); b.add(nd - 1, 5); b.add(ncl - 4, 4);
+            for (uint32_t k = 0; k < ncl; k++) b.add(cl_len[ord[k]], 3);
+            for (uint32_t t = 0; t < ntok; t++) {
+                const uint32_t sy = tok[t] & 0xFF, xv = tok[t] >> 8;
+                b.add(cl_code[sy] & 0xFFFFu, cl_code[sy] >> 16);
+                if (sy == 16) b.add(xv, 2); else if (sy == 17) b.add(xv, 3); else if (sy == 18) b.add(xv, 7);
+            }
+        }
+    }
+    if (!use_dyn) {
+        b.add((final_seg ? 1u : 0u) | (1u << 1), 3);   // BFINAL, BTYPE=01
+        for (uint32_t s = 0; s < 286; s++) ll_code[s * stride] = fixed_litlen(s);
+        for (uint32_t s = 0; s < 30; s++) d_code[s * stride] = rev_bits_n(s, 5) | (5u << 16);
+    }
     uint32_t lp = 0;
     for (uint32_t i = 0; i < nseq; i++) {
         const Seq q = seqs[i];
         const uint32_t ll = q.llml & 0xFFFFu, ml = q.llml >> 16;
-        for (uint32_t k = 0; k < ll; k++) { const uint32_t c = fixed_litlen(lits[lp + k]); b.add(c & 0xFFFFu, c >> 16); }
+        for (uint32_t k = 0; k < ll; k++) { const uint32_t c = ll_code[lits[lp + k] * stride]; b.add(c & 0xFFFFu, c >> 16); }
         lp += ll;
         uint32_t sym, xb, xv;
         deflate_len_sym(ml, &sym, &xb, &xv);
-        const uint32_t c = fixed_litlen(sym);
+        const uint32_t c = ll_code[sym * stride];
         b.add(c & 0xFFFFu, c >> 16);
         b.add(xv, xb);
         deflate_dist_sym(q.off, &sym, &xb, &xv);
-        b.add(rev_bits_n(sym, 5), 5);
+        { const uint32_t dc = d_code[sym * stride]; b.add(dc & 0xFFFFu, dc >> 16); }
         b.add(xv, xb);
     }
-    for (; lp < n_lit_total; lp++) { const uint32_t c = fixed_litlen(lits[lp]); b.add(c & 0xFFFFu, c >> 16); }
-    { const uint32_t c = fixed_litlen(256); b.add(c & 0xFFFFu, c >> 16); }
+    for (; lp < n_lit_total; lp++) { const uint32_t c = ll_code[lits[lp] * stride]; b.add(c & 0xFFFFu, c >> 16); }
+    { const uint32_t c = ll_code[256 * stride]; b.add(c & 0xFFFFu, c >> 16); }
     if (!final_seg) {
         b.add(0, 3);                               // empty stored block, not final
         if (b.n & 7) b.add(0, 8 - (b.n & 7));      // to the byte boundary

@@ -333,8 +333,9 @@ static int encode_launch_all(pna_plan* P) {
             E->d_work.p, E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p);
         LAUNCHED();
         STAGE(1);
-        enc::enc_block_kernel<<<(nsegs + 127) / 128, 128, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p,
-                                                                           E->d_entries.p);
+        enc::enc_block_kernel<<<(nsegs + enc::ENC_BLOCK_THREADS - 1) / enc::ENC_BLOCK_THREADS, enc::ENC_BLOCK_THREADS,
+                                0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p,
+                                                                                                 E->d_entries.p);
         LAUNCHED();
     }
     else STAGE(1);

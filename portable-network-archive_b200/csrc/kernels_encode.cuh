@@ -33,8 +33,8 @@ struct SegRec {            // one segment (host fills the first group, kernels t
 };
 // The `level` of the reference's writers (zstd 1..22, default 3: compress/zstandard.rs:46; deflate 0..9, default 6:
 // compress/deflate.rs:89) selects one of this encoder's settings:
-//   0 fast     greedy parse, Predefined FSE tables                      zstd 1-2, deflate 1-3
-//   1 default  greedy parse, per-block FSE tables chosen by cost        zstd 3-5 (and < 0 / 0 = default), deflate 4-6 (and < 0)
+//   0 fast     greedy parse, Predefined FSE tables / fixed Huffman        zstd 1-2, deflate 1-3
+//   1 default  greedy parse, per-block FSE tables / dynamic Huffman, chosen by cost   zstd 3-5 (and < 0 / 0 = default), deflate 4-6 (and < 0)
 //   2 high     lazy parse (one position of look-ahead) + per-block FSE  zstd >= 6, deflate 7-9
 //   3 stored   deflate level 0: stored blocks only
 inline uint32_t enc_effort(uint8_t compression, int32_t level) {
@@ -42,6 +42,7 @@ inline uint32_t enc_effort(uint8_t compression, int32_t level) {
     if (compression == 1) return level < 0 ? 1u : level == 0 ? 3u : level <= 3 ? 0u : level <= 6 ? 1u : 2u;
     return 1u;
 }
+constexpr uint32_t ENC_BLOCK_THREADS = 128;
 constexpr uint32_t TMP_HEAD = 16;
 // zstd: a new FRAME every FRAME_SEGS segments (1 MiB of input).  Blocks never reference earlier blocks here, so the split costs
 // 6 bytes per MiB and nothing else; a reader that executes matches frame by frame (ours: one LZ unit per frame) gets
@@ -262,7 +263,11 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
             sr.litp_len = lpay;
         }
     } else {
-        const uint32_t sz = deflate_write_segment(sq, nseq, work + sr.lit_off, nlit, last != 0, body);
+        // The writer's histogram / code tables (316 words) stay in the thread's local memory.  Shared memory was measured and is
+        // slower here: 158 KB of tables per 128 threads leave one CTA per SM, and this lane-per-segment kernel lives on warps
+        // in flight (block_write for 4 GiB: local 80 ms, shared rows 114 ms, fixed Huffman 21 ms).
+        uint32_t ws_local[DEFLATE_WS];
+        const uint32_t sz = deflate_write_segment(sq, nseq, work + sr.lit_off, nlit, last != 0, body, sr.effort >= 1u && sr.effort != 3u, ws_local, 1);
         if (sz >= len + 5 || sr.effort == 3u) {   // effort 3: deflate level 0 = stored blocks
             head[0] = (uint8_t)(last ? 1 : 0); head[1] = (uint8_t)len; head[2] = (uint8_t)(len >> 8);
             head[3] = (uint8_t)~len; head[4] = (uint8_t)(~len >> 8);

@@ -237,7 +237,8 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
                 memcpy(out + o, t4 + soff, ssz); o += ssz;
             }
         } else {
-            uint32_t sz = deflate_write_segment(seqs.data(), (uint32_t)seqs.size(), lits.data(), (uint32_t)lits.size(), last, t4);
+            uint32_t ws[DEFLATE_WS];
+            uint32_t sz = deflate_write_segment(seqs.data(), (uint32_t)seqs.size(), lits.data(), (uint32_t)lits.size(), last, t4, g_enc_dyn != 0, ws, 1);
             if (sz >= n + 5) {   // stored block
                 out[o++] = last ? 1 : 0; out[o++] = (uint8_t)n; out[o++] = (uint8_t)(n >> 8); out[o++] = (uint8_t)~n; out[o++] = (uint8_t)(~n >> 8);
                 memcpy(out + o, d, n); o += n;
