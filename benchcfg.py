@@ -108,7 +108,7 @@ def cfg3(pna, host, ctx, corpus_np, threads, scale, workers):
     opts = pna.WriteOptions(compression=1, encryption=2, cipher_mode=0, password=b"pw", kdf_params={"i": 1000})
     streams, s_offs, enc_dt = benchlib.oracle_encode(corpus_np, offs, 1, 6, 2, 0, KEY, threads)
     buf = benchlib.frame_archive(streams, s_offs, sizes, bytes([0, 0, 0, 1, 2, 0]), opts.phsf, 16, "s/%07d", ctx.pinned, threads)
-    dt, t_index, out, xoffs, st = _extract_e2e(host, ctx, buf, opts.phsf, n, U, max(2, workers), 64)
+    dt, t_index, out, xoffs, st = _extract_e2e(host, ctx, buf, opts.phsf, n, U, max(2, workers), 64, reps=3)
     assert st == [0] * n
     for k in range(0, n, max(1, n // 256)):
         assert out[int(xoffs[k]):int(xoffs[k]) + int(sizes[k])].tobytes() == corpus_np[offs[k]:offs[k + 1]].tobytes()

@@ -22,6 +22,7 @@
 #include <random>
 #include <set>
 #include <thread>
+#include <sched.h>
 
 namespace pna {
 
@@ -97,6 +98,12 @@ static inline bool ty_letters(uint32_t t) {   // every byte an ASCII letter (chu
     const uint32_t low = t & 0x1F1F1F1Fu;
     return (t & 0xC0C0C0C0u) == 0x40404040u && !((low - 0x01010101u) & 0x80808080u) && !((0x1A1A1A1Au - low) & 0x80808080u);
 }
+// threads this process may use: its affinity mask (a rank pinned to a slice of the box must not plan for all of it)
+static unsigned usable_cpus() {
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) { const int n = CPU_COUNT(&set); if (n > 0) return (unsigned)n; }
+    return std::max(1u, std::thread::hardware_concurrency());
+}
 // serial walk from `pos` until `stop` (the first chunk that starts at or behind it is not taken); returns where it stopped
 static size_t walk_chunks(const uint8_t* buf, size_t len, size_t pos, size_t stop, std::vector<RawChunk>& out, bool speculative, bool* broken) {
     while (pos < len && pos < stop) {
@@ -123,7 +130,7 @@ static size_t walk_chunks(const uint8_t* buf, size_t len, size_t pos, size_t sto
 // lands EXACTLY on that offset -- then the result is what the serial walk produces -- and re-walked serially otherwise.
 static void index_chunks(const uint8_t* buf, size_t len, size_t pos, std::vector<RawChunk>& out) {
     const size_t span = len > pos ? len - pos : 0;
-    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    unsigned nt = std::min(16u, std::max(1u, usable_cpus()));
     if (span < ((size_t)32 << 20) || getenv("PNA_INDEX_SERIAL")) nt = 1;
     if (nt == 1) {
         out.reserve(std::min<size_t>(len / 256 + 16, (size_t)1 << 24));
@@ -236,7 +243,7 @@ static void group_entries(const uint8_t* buf, const std::vector<RawChunk>& ch, s
     const size_t nc = ch.size();
     size_t limit = nc;
     for (size_t i = 0; i < nc; i++) { const uint32_t t = ty32(ch[i]); if (t == T_AEND || t == T_ANXT) { limit = i; break; } }
-    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    unsigned nt = std::min(16u, std::max(1u, usable_cpus()));
     if (limit < 65536 || getenv("PNA_INDEX_SERIAL")) nt = 1;
     // range starts: the first entry header at or behind k * limit / nt.  An entry header can only be cut off from its
     // chunks by a range start that lies INSIDE the entry, so starts are moved forward to the next header that follows an

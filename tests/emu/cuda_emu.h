@@ -423,6 +423,10 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) {
 }
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+typedef int cudaMemPool_t;
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 1 };
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = 0; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = aligned_alloc(4096, (n + 4095) & ~(size_t)4095); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaHostAlloc(p, n, 0); }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
@@ -438,6 +442,7 @@ static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n)
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new emu_stream_t{emu::cur_device()}; return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, 0); }
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
