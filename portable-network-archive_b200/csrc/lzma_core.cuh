@@ -156,7 +156,19 @@ PNA_HD int32_t lzma_chunk(LzmaState& S, uint16_t* probs, const uint8_t* in, uint
         }
         if (rc.overrun || (uint64_t)rep0 >= pos - dict_start || len > end - pos) return ST_INVALID_DATA;
         const uint64_t src = pos - rep0 - 1;
-        for (uint32_t i = 0; i < len; i++) { prev = out[src + i]; out[pos + i] = (uint8_t)prev; }
+        if (rep0 + 1u >= len) {
+            // source and destination do not overlap: four loads in flight per round (a thread's dependent byte loads are an
+            // L2 round trip each -- the copy loop is where a lane of the GPU kernel spends its time)
+            uint32_t i = 0;
+            for (; i + 4 <= len; i += 4) {
+                const uint8_t b0 = out[src + i], b1 = out[src + i + 1], b2 = out[src + i + 2], b3 = out[src + i + 3];
+                out[pos + i] = b0; out[pos + i + 1] = b1; out[pos + i + 2] = b2; out[pos + i + 3] = b3;
+                prev = b3;
+            }
+            for (; i < len; i++) { prev = out[src + i]; out[pos + i] = (uint8_t)prev; }
+        } else {
+            for (uint32_t i = 0; i < len; i++) { prev = out[src + i]; out[pos + i] = (uint8_t)prev; }
+        }
         pos += len;
     }
     rc.normalize();
