@@ -32,8 +32,8 @@ struct Seq { uint32_t off; uint32_t llml; };   // ll | ml << 16 (ll <= 32768, ml
 // FSE compression tables of the three predefined distributions (libzstd FSE_buildCTable semantics)
 struct FseCTab {
     uint16_t state[64];     // tableU16
-    int32_t dfs[56];        // deltaFindState per symbol
-    uint32_t dnb[56];       // deltaNbBits per symbol
+    struct Sym { uint32_t dnb; int32_t dfs; };   // deltaNbBits, deltaFindState: one 8-byte load per symbol (the per-block tables sit in
+    Sym sym[56];                                   // local memory, where every scattered load is a sector)
     uint32_t log;
 };
 struct EncTables {
@@ -65,13 +65,13 @@ PNA_HD void fse_build_ctab_norm(FseCTab* T, const int16_t* norm, int n, int log)
     for (int u = 0; u < size; u++) { int s = sym_of[u]; T->state[cumul[s]++] = (uint16_t)(size + u); }
     int total = 0;
     for (int s = 0; s < n; s++) {
-        if (norm[s] == 0) { T->dnb[s] = ((uint32_t)(log + 1) << 16) - (1u << log); T->dfs[s] = 0; }
-        else if (norm[s] == -1 || norm[s] == 1) { T->dnb[s] = ((uint32_t)log << 16) - (1u << log); T->dfs[s] = total - 1; total++; }
+        if (norm[s] == 0) { T->sym[s].dnb = ((uint32_t)(log + 1) << 16) - (1u << log); T->sym[s].dfs = 0; }
+        else if (norm[s] == -1 || norm[s] == 1) { T->sym[s].dnb = ((uint32_t)log << 16) - (1u << log); T->sym[s].dfs = total - 1; total++; }
         else {
             const uint32_t max_bits = (uint32_t)log - (uint32_t)highbit32((uint32_t)norm[s] - 1);
             const uint32_t min_state_plus = (uint32_t)norm[s] << max_bits;
-            T->dnb[s] = (max_bits << 16) - min_state_plus;
-            T->dfs[s] = total - norm[s];
+            T->sym[s].dnb = (max_bits << 16) - min_state_plus;
+            T->sym[s].dfs = total - norm[s];
             total += norm[s];
         }
     }
@@ -86,7 +86,7 @@ inline void fse_build_ctab(FseCTab* T, int kind) {
 // the table of an RLE-mode symbol: zero bits per symbol, state 0 (libzstd FSE_buildCTable_rle)
 PNA_HD void fse_build_ctab_rle(FseCTab* T, uint32_t sym) {
     T->state[0] = 0; T->state[1] = 0;
-    T->dnb[sym] = 0; T->dfs[sym] = 0;
+    T->sym[sym].dnb = 0; T->sym[sym].dfs = 0;
     T->log = 0;
 }
 
@@ -205,14 +205,16 @@ struct BitOut {
 
 struct FseCState { uint32_t v; };
 PNA_HD void fse_init_state(FseCState& s, const FseCTab& t, uint32_t sym) {
-    const uint32_t nb = (t.dnb[sym] + (1u << 15)) >> 16;
-    const uint32_t value = (nb << 16) - t.dnb[sym];
-    s.v = t.state[(value >> nb) + (uint32_t)t.dfs[sym]];
+    const FseCTab::Sym e = t.sym[sym];
+    const uint32_t nb = (e.dnb + (1u << 15)) >> 16;
+    const uint32_t value = (nb << 16) - e.dnb;
+    s.v = t.state[(value >> nb) + (uint32_t)e.dfs];
 }
 PNA_HD void fse_encode(BitOut& b, FseCState& s, const FseCTab& t, uint32_t sym) {
-    const uint32_t nb = (s.v + t.dnb[sym]) >> 16;
+    const FseCTab::Sym e = t.sym[sym];
+    const uint32_t nb = (s.v + e.dnb) >> 16;
     b.add(s.v, nb);
-    s.v = t.state[(int32_t)(s.v >> nb) + t.dfs[sym]];
+    s.v = t.state[(int32_t)(s.v >> nb) + e.dfs];
 }
 
 PNA_HD uint32_t ll_code_of(const EncTables& E, uint32_t ll) { return ll < 64 ? E.ll_code[ll] : (uint32_t)highbit32(ll) + 19u; }
