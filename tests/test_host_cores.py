@@ -169,6 +169,43 @@ def test_encode_writers_decode_with_reference_codecs(hc, oracle, comp):
             assert n < len(d)
 
 
+@pytest.mark.parametrize("comp", [1, 2])
+def test_block_writers_table_choices_decode_with_reference_codecs(hc, oracle, comp):
+    """The per-block table machinery of the writers (encode_core.cuh): zstd Predefined / RLE / FSE_Compressed per table with the
+    RFC 8878 4.1.1 description, deflate dynamic-Huffman blocks with run-length coded code lengths -- against libzstd / zlib on
+    inputs that push each choice: skewed and flat symbol statistics, one repeated sequence shape (RLE tables), tiny blocks
+    (Predefined), alphabets that exhaust the code-length limit, and both settings of the fast/default switch."""
+    hc.hc_encode.restype = C.c_uint64
+    hc.hc_encode.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p]
+    rnd = random.Random(40 + comp)
+    fib = [1, 1]
+    while len(fib) < 40:
+        fib.append(fib[-1] + fib[-2])
+    cases = [
+        b"".join(bytes([i & 255]) * (1 + i % 7) for i in range(30_000)),                     # many short runs: RLE-ish length codes
+        (b"abcdefgh" * 5000) + os.urandom(3000) + (b"0123456789" * 4000),                    # one sequence shape, then noise, then another
+        bytes(rnd.choice(b"ab") for _ in range(90_000)),                                     # two literals only
+        bytes(min(255, int(rnd.expovariate(0.05))) for _ in range(120_000)),                 # geometric literal statistics
+        b"".join(bytes([k]) * min(fib[k], 4000) for k in range(30)) * 2,                     # Fibonacci counts: the length limit is hit
+        bytes(range(256)) * 150 + corpus.make_file(21, 50_000),                              # flat alphabet next to text
+        corpus.make_file(22, 47), corpus.make_file(23, 700), corpus.make_file(24, 33_000), corpus.make_file(25, 400_000),
+        bytes(rnd.randrange(256) if rnd.random() < 0.1 else 65 for _ in range(80_000)),      # one dominant literal
+    ]
+    sizes = {}
+    for dyn in (1, 0):
+        hc.hc_set_enc_dyn(dyn)
+        for k, d in enumerate(cases):
+            out = C.create_string_buffer(len(d) + len(d) // 4 + 1024)
+            n = hc.hc_encode(comp, d, len(d), out)
+            assert oracle.decompress(comp, out.raw[:n]) == d, (comp, dyn, k, len(d))
+            sizes[(dyn, k)] = n
+    hc.hc_set_enc_dyn(1)
+    # fitted tables are only taken when the cost model says so: never worse than the fixed ones by more than the model's slack
+    for k in range(len(cases)):
+        assert sizes[(1, k)] <= sizes[(0, k)] + 16 + sizes[(0, k)] // 200, (comp, k, sizes[(1, k)], sizes[(0, k)])
+    assert sum(sizes[(1, k)] for k in range(len(cases))) < 0.95 * sum(sizes[(0, k)] for k in range(len(cases)))
+
+
 def test_gcm_tile_algorithm_and_key_schedule(hc, oracle):
     """kernels_gcm.cuh's evaluation order (lane-strided Horner with H^32, lane tree, tiles chained with H^1024, short tile first)
     run with the lanes looped on the host == the oracle's bit-by-bit GCM (SP 800-38D) for both ciphers; SHA-256 / HKDF of
