@@ -684,22 +684,22 @@ void Archive::extract_range(const ReadOptions& opt, uint8_t* out, const uint64_t
         }
         if (broken && !any_entry_broken) throw Error(PNA_E_INVALID_DATA, "broken chunk");   // an archive-level / non-file chunk
     };
+    // groups in flight per worker: `depth` contexts in a ring -- issue(g) ... collect(g - depth + 1)  (PNA_PIPE_DEPTH, default 2)
+    static const int depth = [] { const char* e = getenv("PNA_PIPE_DEPTH"); const int d = e ? atoi(e) : 2; return d < 2 ? 2 : d > 4 ? 4 : d; }();
     auto work = [&](size_t di) {
-        Stage stage[2];
+        std::vector<Stage> stage((size_t)depth);
         try {
-            CtxLease L0(devices[di]), L1(devices[di]);
-            CtxLease* L[2] = {&L0, &L1};
-            int cur = 0;
-            bool have_prev = false;
+            std::vector<std::unique_ptr<CtxLease>> L;
+            for (int k = 0; k < depth; k++) L.emplace_back(new CtxLease(devices[di]));
+            size_t issued = 0, collected = 0;
             for (;;) {
                 const size_t g = next.fetch_add(1);
                 if (g >= groups.size()) break;
-                issue(*L[cur], stage[cur], g, h2d_mus[di]);
-                if (have_prev) collect(*L[cur ^ 1], stage[cur ^ 1]);
-                have_prev = true;
-                cur ^= 1;
+                issue(*L[issued % depth], stage[issued % depth], g, h2d_mus[di]);
+                issued++;
+                if (issued - collected >= (size_t)depth) { collect(*L[collected % depth], stage[collected % depth]); collected++; }
             }
-            if (have_prev) collect(*L[cur ^ 1], stage[cur ^ 1]);
+            for (; collected < issued; collected++) collect(*L[collected % depth], stage[collected % depth]);
         } catch (const Error& e) {
             for (auto& S : stage) if (S.plan) { pna_cuda_plan_destroy(S.plan); S.plan = nullptr; }
             std::lock_guard<std::mutex> g(err_mu);
