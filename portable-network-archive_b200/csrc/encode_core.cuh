@@ -532,9 +532,22 @@ PNA_HD void deflate_dist_sym(uint32_t dist, uint32_t* sym, uint32_t* xb, uint32_
 // Length-limited Huffman code lengths for count[0..n) (n <= NMAX): len_of[s] = 0 for absent symbols.  Two-queue merge over
 // the present symbols sorted by count, then miniz's length-limit repair (fold the too-long codes into the limit, pay the
 // Kraft excess back by splitting the longest code below it).  Returns the number of present symbols (0 and 1: no code built).
+// Scratch of the builder, owned by the CALLER as part of ONE object (DeflateScratch below).  The helpers of the deflate writer
+// declare no arrays of their own, on purpose: with per-helper arrays inlined into one lane-per-segment frame, nvcc 12.9 (sm_100a,
+// -O3 and -O1) let the frame slots of a later helper overlap an array of the caller that was still live -- the run-length tokens
+// came back holding the sort order of the code-length alphabet -- so that unrelated edits (a table stride, an unrolled loop) made
+// every dynamic-Huffman header corrupt on the GPU while the same source is clean under ASan / UBSan on the host, on the emulator,
+// and under memcheck / racecheck / initcheck.  One enclosing object is one stack slot: nothing to merge.
+struct HuffScratch {
+    uint16_t order[286];
+    uint32_t wt[2 * 286];       // weights while the tree is built, depths afterwards
+    uint16_t parent[2 * 286];
+    uint32_t num[34];
+};
 template <int NMAX>
-PNA_HD uint32_t huff_lengths(const uint32_t* count, uint32_t stride, uint32_t n, uint32_t maxbits, uint8_t* len_of) {
-    uint16_t order[NMAX];
+PNA_HD uint32_t huff_lengths(const uint32_t* count, uint32_t stride, uint32_t n, uint32_t maxbits, uint8_t* len_of, HuffScratch& hs) {
+    static_assert(NMAX <= 286, "scratch is sized for the literal/length alphabet");
+    uint16_t* const order = hs.order;
     uint32_t m = 0;
     for (uint32_t s = 0; s < n; s++) {
         len_of[s] = 0;
@@ -542,9 +555,8 @@ PNA_HD uint32_t huff_lengths(const uint32_t* count, uint32_t stride, uint32_t n,
     }
     // ascending by count: shell sort (an insertion sort moves ~m^2/4 keys -- ten thousand steps for a literal alphabet)
     {
-        const uint32_t gaps[6] = {132, 57, 23, 10, 4, 1};
         for (int gi = 0; gi < 6; gi++) {
-            const uint32_t gap = gaps[gi];
+            const uint32_t gap = gi == 0 ? 132u : gi == 1 ? 57u : gi == 2 ? 23u : gi == 3 ? 10u : gi == 4 ? 4u : 1u;
             for (uint32_t i = gap; i < m; i++) {
                 const uint16_t v = order[i];
                 const uint32_t cv = count[v * stride];
@@ -555,8 +567,8 @@ PNA_HD uint32_t huff_lengths(const uint32_t* count, uint32_t stride, uint32_t n,
         }
     }
     if (m < 2) return m;
-    uint32_t wt[2 * NMAX];       // weights while the tree is built, depths afterwards
-    uint16_t parent[2 * NMAX];
+    uint32_t* const wt = hs.wt;
+    uint16_t* const parent = hs.parent;
     for (uint32_t k = 0; k < m; k++) wt[k] = count[order[k] * stride];
     uint32_t li = 0, ni = m, no = m;
     for (uint32_t k = 0; k + 1 < m; k++) {
@@ -571,7 +583,7 @@ PNA_HD uint32_t huff_lengths(const uint32_t* count, uint32_t stride, uint32_t n,
     }
     wt[no - 1] = 0;
     for (uint32_t k = no - 1; k-- > 0;) wt[k] = wt[parent[k]] + 1;
-    uint32_t num[34];
+    uint32_t* const num = hs.num;
     for (uint32_t l = 0; l < 34; l++) num[l] = 0;
     for (uint32_t k = 0; k < m; k++) num[wt[k] > 32 ? 32 : wt[k]]++;
     for (uint32_t l = maxbits + 1; l < 33; l++) { num[maxbits] += num[l]; num[l] = 0; }
@@ -589,8 +601,7 @@ PNA_HD uint32_t huff_lengths(const uint32_t* count, uint32_t stride, uint32_t n,
     return m;
 }
 // canonical deflate codes (RFC 1951 3.2.2) for len_of[0..n), bit-reversed for the LSB-first writer: code | nbits << 16
-PNA_HD void deflate_codes(const uint8_t* len_of, uint32_t n, uint32_t* code_of, uint32_t stride = 1) {
-    uint32_t bl_count[16], next[16];
+PNA_HD void deflate_codes(const uint8_t* len_of, uint32_t n, uint32_t* code_of, uint32_t stride, uint32_t* bl_count /*[16]*/, uint32_t* next /*[16]*/) {
     for (int l = 0; l < 16; l++) bl_count[l] = 0;
     for (uint32_t s = 0; s < n; s++) bl_count[len_of[s]]++;
     bl_count[0] = 0;
@@ -609,8 +620,18 @@ PNA_HD void deflate_codes(const uint8_t* len_of, uint32_t n, uint32_t* code_of, 
 // ws: DEFLATE_WS 32-bit slots spaced `stride` words apart -- first the histograms, then the code tables: they are touched once or
 // twice per literal (the kernel passes a thread-local array with stride 1; the stride exists for table layouts shared by a CTA).
 constexpr uint32_t DEFLATE_WS = 286 + 30;
+struct DeflateScratch {   // every array of the writer and its helpers, as ONE object (see HuffScratch)
+    HuffScratch huff;
+    uint8_t lens[286 + 30];
+    uint8_t seq_len[286 + 30];
+    uint16_t tok[286 + 30];      // symbol | extra value << 8
+    uint32_t ccl[19];
+    uint8_t cl_len[20];
+    uint32_t cl_code[19];
+    uint32_t bl_count[16], next[16];
+};
 PNA_HD uint32_t deflate_write_segment(const Seq* seqs, uint32_t nseq, const uint8_t* lits, uint32_t n_lit_total, bool final_seg,
-                                      uint8_t* dst, bool dyn, uint32_t* ws, uint32_t stride) {
+                                      uint8_t* dst, bool dyn, uint32_t* ws, uint32_t stride, DeflateScratch& sc) {
     BitOut b;
     b.init(dst);
     uint32_t* const ll_code = ws;
@@ -636,20 +657,20 @@ PNA_HD uint32_t deflate_write_segment(const Seq* seqs, uint32_t nseq, const uint
             for (uint32_t s = 0; s < 30; s++) nd += cd[s * stride] != 0;
             if (nd < 2) { if (!cd[0]) cd[0] = 1; else cd[stride] = 1; if (nd == 0) cd[stride] = 1; }
         }
-        uint8_t lens[286 + 30];
-        huff_lengths<286>(cl, stride, 286, 15, lens);
-        huff_lengths<30>(cd, stride, 30, 15, lens + 286);
+        uint8_t* const lens = sc.lens;
+        huff_lengths<286>(cl, stride, 286, 15, lens, sc.huff);
+        huff_lengths<30>(cd, stride, 30, 15, lens + 286, sc.huff);
         uint32_t nl = 286, nd = 30;
         while (nl > 257 && lens[nl - 1] == 0) nl--;
         while (nd > 1 && lens[286 + nd - 1] == 0) nd--;
         // ---- the two length sets as one run-length coded sequence over the code-length alphabet
-        uint8_t seq_len[286 + 30];
+        uint8_t* const seq_len = sc.seq_len;
         for (uint32_t i = 0; i < nl; i++) seq_len[i] = lens[i];
         for (uint32_t i = 0; i < nd; i++) seq_len[nl + i] = lens[286 + i];
         const uint32_t ntot = nl + nd;
-        uint16_t tok[286 + 30];      // symbol | extra value << 8
+        uint16_t* const tok = sc.tok;
         uint32_t ntok = 0;
-        uint32_t ccl[19];
+        uint32_t* const ccl = sc.ccl;
         for (int s = 0; s < 19; s++) ccl[s] = 0;
         for (uint32_t i = 0; i < ntot;) {
             const uint32_t v = seq_len[i];
@@ -667,11 +688,16 @@ PNA_HD uint32_t deflate_write_segment(const Seq* seqs, uint32_t nseq, const uint
                 i += 1 + r;
             } else { tok[ntok++] = (uint16_t)v; ccl[v]++; i++; }
         }
-        uint8_t cl_len[19];
-        const uint32_t mcl = huff_lengths<19>(ccl, 1, 19, 7, cl_len);
-        const uint8_t ord[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        uint8_t* const cl_len = sc.cl_len;
+        const uint32_t mcl = huff_lengths<19>(ccl, 1, 19, 7, cl_len, sc.huff);
+        // order of the code-length code lengths in the header (RFC 1951 3.2.7), packed five bits per entry: no local table
+        auto ord = [](uint32_t k) -> uint32_t {
+            const uint64_t lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
+            const uint64_t hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+            return (uint32_t)((k < 12 ? lo >> (5 * k) : hi >> (5 * (k - 12))) & 31u);
+        };
         uint32_t ncl = 19;
-        while (ncl > 4 && cl_len[ord[ncl - 1]] == 0) ncl--;
+        while (ncl > 4 && cl_len[ord(ncl - 1)] == 0) ncl--;
         // ---- exact sizes of both forms
         uint64_t bits_dyn = 3 + 5 + 5 + 4 + 3ull * ncl + extra, bits_fix = 3 + extra;
         for (uint32_t t = 0; t < ntok; t++) { const uint32_t sy = tok[t] & 0xFF; bits_dyn += cl_len[sy] + (sy == 16 ? 2 : sy == 17 ? 3 : sy == 18 ? 7 : 0); }
@@ -680,13 +706,13 @@ PNA_HD uint32_t deflate_write_segment(const Seq* seqs, uint32_t nseq, const uint
         // (the forced extra distance code is counted in both and never emitted: an upper bound, equal for the comparison)
         use_dyn = mcl >= 2 && bits_dyn < bits_fix;   // (fewer than two code-length symbols cannot happen: EOB has a length, absent symbols have none)
         if (use_dyn) {
-            uint32_t cl_code[19];
-            deflate_codes(cl_len, 19, cl_code);
-            deflate_codes(lens, 286, ll_code, stride);
-            deflate_codes(lens + 286, 30, d_code, stride);
+            uint32_t* const cl_code = sc.cl_code;
+            deflate_codes(cl_len, 19, cl_code, 1, sc.bl_count, sc.next);
+            deflate_codes(lens, 286, ll_code, stride, sc.bl_count, sc.next);
+            deflate_codes(lens + 286, 30, d_code, stride, sc.bl_count, sc.next);
             b.add((final_seg ? 1u : 0u) | (2u << 1), 3);   // BFINAL, BTYPE=10
             b.add(nl - 257, 5); b.add(nd - 1, 5); b.add(ncl - 4, 4);
-            for (uint32_t k = 0; k < ncl; k++) b.add(cl_len[ord[k]], 3);
+            for (uint32_t k = 0; k < ncl; k++) b.add(cl_len[ord(k)], 3);
             for (uint32_t t = 0; t < ntok; t++) {
                 const uint32_t sy = tok[t] & 0xFF, xv = tok[t] >> 8;
                 b.add(cl_code[sy] & 0xFFFFu, cl_code[sy] >> 16);

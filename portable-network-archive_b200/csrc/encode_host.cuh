@@ -28,6 +28,7 @@ struct EncodePlan {
     DevArr<uint8_t> d_stage;                  // coalesced transfers: many small adjacent host spans travel as one copy
     DevArr<CopyJob> d_stage_jobs;
     uint32_t fdat_init = 0;
+    bool has_zstd = false, has_deflate = false;   // which block writers the batch needs
     // GCM STREAM: segment / tile slots from the compressed-length bounds (AES slots first, then Camellia)
     std::vector<GcmSlot> h_gcm_slots;
     std::vector<gcm::GcmKeyRef> h_gcm_refs;
@@ -102,6 +103,8 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
         plain_total += align_up(d.plain.len, 16) + 16;
         e.compression = d.compression; e.encryption = d.encryption; e.cipher_mode = d.cipher_mode;
         e.effort = (uint8_t)enc::enc_effort(d.compression, d.level);
+        if (d.compression == PNA_COMPRESSION_ZSTD) E->has_zstd = true;
+        if (d.compression == PNA_COMPRESSION_DEFLATE) E->has_deflate = true;
         memcpy(e.iv, d.iv, 16);
         e.key_idx = -1;
         if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD)
@@ -333,10 +336,15 @@ static int encode_launch_all(pna_plan* P) {
             E->d_work.p, E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p);
         LAUNCHED();
         STAGE(1);
-        enc::enc_block_kernel<<<(nsegs + enc::ENC_BLOCK_THREADS - 1) / enc::ENC_BLOCK_THREADS, enc::ENC_BLOCK_THREADS,
-                                0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p,
-                                                                                                 E->d_entries.p);
-        LAUNCHED();
+        const uint32_t bgrid = (nsegs + enc::ENC_BLOCK_THREADS - 1) / enc::ENC_BLOCK_THREADS;
+        if (E->has_zstd) {
+            enc::enc_block_kernel<2><<<bgrid, enc::ENC_BLOCK_THREADS, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p, E->d_entries.p);
+            LAUNCHED();
+        }
+        if (E->has_deflate) {
+            enc::enc_block_kernel<1><<<bgrid, enc::ENC_BLOCK_THREADS, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p, E->d_entries.p);
+            LAUNCHED();
+        }
     }
     else STAGE(1);
     STAGE(2);

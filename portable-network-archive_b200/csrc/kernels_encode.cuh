@@ -221,6 +221,9 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) lz_match_kernel(const uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------------
+// COMP: the codec this instantiation writes (2 zstd, 1 deflate); segments of the other codec are left to the other launch.  Two
+// kernels because the deflate writer carries 6 KB of Huffman scratch and 80 registers: the zstd writer should not pay for them.
+template <int COMP>
 __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ work, SegRec* __restrict__ segs, uint32_t nsegs,
                                                         Seq* __restrict__ seqs, const EncTables* __restrict__ tables,
                                                         const EncEntry* __restrict__ entries) {
@@ -235,7 +238,8 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
     uint8_t* const head = work + sr.tmp_off;
     uint8_t* const body = head + TMP_HEAD;
     Seq* sq = seqs + sr.seq_off;
-    if (entries[sr.entry].compression == 2) {
+    if (entries[sr.entry].compression != COMP) return;
+    if (COMP == 2) {
         // literals section first (Huffman-compressed into the body when that is smaller, else raw = the literal arena as it
         // is), the sequences section behind it on the next 4-byte boundary
         uint8_t lh[5];
@@ -267,7 +271,8 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
         // slower here: 158 KB of tables per 128 threads leave one CTA per SM, and this lane-per-segment kernel lives on warps
         // in flight (block_write for 4 GiB: local 80 ms, shared rows 114 ms, fixed Huffman 21 ms).
         uint32_t ws_local[DEFLATE_WS];
-        const uint32_t sz = deflate_write_segment(sq, nseq, work + sr.lit_off, nlit, last != 0, body, sr.effort >= 1u && sr.effort != 3u, ws_local, 1);
+        DeflateScratch scratch;
+        const uint32_t sz = deflate_write_segment(sq, nseq, work + sr.lit_off, nlit, last != 0, body, sr.effort >= 1u && sr.effort != 3u, ws_local, 1, scratch);
         if (sz >= len + 5 || sr.effort == 3u) {   // effort 3: deflate level 0 = stored blocks
             head[0] = (uint8_t)(last ? 1 : 0); head[1] = (uint8_t)len; head[2] = (uint8_t)(len >> 8);
             head[3] = (uint8_t)~len; head[4] = (uint8_t)(~len >> 8);

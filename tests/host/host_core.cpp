@@ -238,7 +238,8 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
             }
         } else {
             uint32_t ws[DEFLATE_WS];
-            uint32_t sz = deflate_write_segment(seqs.data(), (uint32_t)seqs.size(), lits.data(), (uint32_t)lits.size(), last, t4, g_enc_dyn != 0, ws, 1);
+            DeflateScratch scratch;
+            uint32_t sz = deflate_write_segment(seqs.data(), (uint32_t)seqs.size(), lits.data(), (uint32_t)lits.size(), last, t4, g_enc_dyn != 0, ws, 1, scratch);
             if (sz >= n + 5) {   // stored block
                 out[o++] = last ? 1 : 0; out[o++] = (uint8_t)n; out[o++] = (uint8_t)(n >> 8); out[o++] = (uint8_t)~n; out[o++] = (uint8_t)(~n >> 8);
                 memcpy(out + o, d, n); o += n;
