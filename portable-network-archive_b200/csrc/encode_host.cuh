@@ -28,7 +28,7 @@ struct EncodePlan {
     DevArr<uint8_t> d_stage;                  // coalesced transfers: many small adjacent host spans travel as one copy
     DevArr<CopyJob> d_stage_jobs;
     uint32_t fdat_init = 0;
-    bool has_zstd = false, has_deflate = false;   // which block writers the batch needs
+    bool has_zstd = false, has_deflate = false, has_xz = false;   // which block writers the batch needs
     // GCM STREAM: segment / tile slots from the compressed-length bounds (AES slots first, then Camellia)
     std::vector<GcmSlot> h_gcm_slots;
     std::vector<gcm::GcmKeyRef> h_gcm_refs;
@@ -44,6 +44,7 @@ void destroy(EncodePlan* p) { delete p; }
 bool init_attributes() {
     const int aes_smem = 256 * 32 * 4, cam_smem = 2 * 2048 * 4;
     return cudaFuncSetAttribute(lz_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(xz_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XZ_ENC_SMEM_BYTES) == cudaSuccess &&
            cudaFuncSetAttribute(encrypt_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_CTR_SMEM) == cudaSuccess &&
            cudaFuncSetAttribute(encrypt_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess &&
            cudaFuncSetAttribute(cbc_encrypt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess &&
@@ -59,6 +60,7 @@ static uint64_t enc_nsegs(uint64_t len) { return (len + enc::SEG - 1) / enc::SEG
 static uint64_t enc_comp_bound(uint8_t compression, uint64_t len) {
     if (compression == PNA_COMPRESSION_ZSTD) return len + 3 * enc_nsegs(len) + 9 + 6 * (enc_nsegs(len) / enc::FRAME_SEGS + 1);
     if (compression == PNA_COMPRESSION_DEFLATE) return len + 5 * enc_nsegs(len) + 8;
+    if (compression == PNA_COMPRESSION_XZ) return len + 3 * enc_nsegs(len) + 24 + 48;   // uncompressed chunks + container
     return len;
 }
 static bool enc_is_gcm(const pna_encode_desc& d) { return d.encryption != 0 && d.cipher_mode == PNA_CIPHER_GCM; }
@@ -105,10 +107,12 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
         e.effort = (uint8_t)enc::enc_effort(d.compression, d.level);
         if (d.compression == PNA_COMPRESSION_ZSTD) E->has_zstd = true;
         if (d.compression == PNA_COMPRESSION_DEFLATE) E->has_deflate = true;
+        if (d.compression == PNA_COMPRESSION_XZ) E->has_xz = true;
         memcpy(e.iv, d.iv, 16);
         e.key_idx = -1;
-        if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD)
-            e.status = ST_UNSUPPORTED;   // xz: entry/write.rs:264 has it, this path does not
+        if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD &&
+            d.compression != PNA_COMPRESSION_XZ)
+            e.status = ST_UNSUPPORTED;
         else if (d.encryption != PNA_ENCRYPTION_NO && d.encryption != PNA_ENCRYPTION_AES && d.encryption != PNA_ENCRYPTION_CAMELLIA)
             e.status = ST_UNSUPPORTED;
         else if (d.encryption != 0 && d.cipher_mode != PNA_CIPHER_CBC && d.cipher_mode != PNA_CIPHER_CTR && d.cipher_mode != PNA_CIPHER_GCM)
@@ -143,14 +147,14 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
     const uint64_t lit_base = align_up(plain_total, 256);
     const uint64_t tmp_base = lit_base + align_up(plain_total, 256);
     const uint64_t hdr_base = tmp_base + nsegs_total * enc::TMP_SEG;
-    E->work_bytes = hdr_base + (uint64_t)n * 32 + 256;
+    E->work_bytes = hdr_base + (uint64_t)n * xz::XZ_HDR_SCRATCH + 256;
     E->h_segs.resize(nsegs_total);
     uint64_t out_cur = 0, piece_cur = 0, crc_bodies = 0;
     E->crc_body_begin.resize(n); E->crc_body_size.resize(n);
     for (uint32_t i = 0; i < n; i++) {
         EncEntry& e = E->h_entries[i];
         const pna_encode_desc& d = descs[i];
-        e.hdr_off = hdr_base + (uint64_t)i * 32;
+        e.hdr_off = hdr_base + (uint64_t)i * xz::XZ_HDR_SCRATCH;
         e.piece_begin = piece_cur;
         e.out_off = out_cur;
         E->crc_body_begin[i] = (uint32_t)crc_bodies;
@@ -343,6 +347,11 @@ static int encode_launch_all(pna_plan* P) {
         }
         if (E->has_deflate) {
             enc::enc_block_kernel<1><<<bgrid, enc::ENC_BLOCK_THREADS, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p, E->d_entries.p);
+            LAUNCHED();
+        }
+        if (E->has_xz) {
+            enc::xz_encode_kernel<<<(nsegs + enc::XZ_ENC_WARPS - 1) / enc::XZ_ENC_WARPS, 32 * enc::XZ_ENC_WARPS, enc::XZ_ENC_SMEM_BYTES, ctx->stream>>>(
+                E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_entries.p);
             LAUNCHED();
         }
     }

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include "common.cuh"
 #include "encode_core.cuh"
+#include "lzma_enc_core.cuh"
 #include "kernels_crc_cipher.cuh"
 #include "kernels_gcm.cuh"
 
@@ -40,6 +41,7 @@ struct SegRec {            // one segment (host fills the first group, kernels t
 inline uint32_t enc_effort(uint8_t compression, int32_t level) {
     if (compression == 2) return level <= 0 ? 1u : level <= 2 ? 0u : level <= 5 ? 1u : 2u;
     if (compression == 1) return level < 0 ? 1u : level == 0 ? 3u : level <= 3 ? 0u : level <= 6 ? 1u : 2u;
+    if (compression == 4) return level >= 0 && level <= 3 ? 1u : 2u;   // xz 0..9, default 6 (compress/xz.rs:10-16): presets >= 4 parse lazily
     return 1u;
 }
 constexpr uint32_t ENC_BLOCK_THREADS = 128;
@@ -53,7 +55,7 @@ constexpr uint32_t TMP_SEG = TMP_HEAD + SEG + SEG / 8 + 112;   // 36992: head + 
 struct EncEntry {
     uint64_t plain_off, plain_len;
     uint64_t piece_begin;          // first Segment of this entry's piece list
-    uint64_t hdr_off;              // 32 bytes of scratch in the work arena: frame header at +0, trailer at +16
+    uint64_t hdr_off;              // XZ_HDR_SCRATCH bytes in the work arena: frame header at +0, trailer at +16 (xz: +24)
     uint64_t out_off, out_cap;
     uint64_t comp_len, out_len;    // device written
     uint32_t seg_begin, n_segs;
@@ -282,6 +284,44 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
 }
 
 // ------------------------------------------------------------------------------------------------
+// xz: a warp per segment.  All lanes reset the segment's probability arena (16 KB of shared memory: the dependent
+// load-compare-update chain per coded bit runs at shared-memory latency) and take the CRC-32 of a 1 KiB slice each; lane 0 then
+// runs the range coder over the segment's parse (lzma_enc_core.cuh) and writes the LZMA2 chunk header.  Segments are independent
+// chunks, so a 4 MiB file is 128 coders in flight; 12 segments per SM.
+constexpr int XZ_ENC_WARPS = 4;
+constexpr uint32_t XZ_ENC_PROB_BYTES = (xz::ENC_PROBS * 2u + 15u) & ~15u;
+constexpr uint32_t XZ_ENC_SMEM_BYTES = XZ_ENC_PROB_BYTES * XZ_ENC_WARPS;
+__global__ void __launch_bounds__(32 * XZ_ENC_WARPS) xz_encode_kernel(uint8_t* __restrict__ work, SegRec* __restrict__ segs, uint32_t nsegs,
+                                                                      const Seq* __restrict__ seqs, const EncEntry* __restrict__ entries) {
+    extern __shared__ __align__(16) uint8_t xz_enc_smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t s = blockIdx.x * XZ_ENC_WARPS + w;
+    if (s >= nsegs) return;
+    SegRec& sr = segs[s];
+    if (entries[sr.entry].compression != 4) return;
+    uint16_t* const probs = reinterpret_cast<uint16_t*>(xz_enc_smem_raw + w * XZ_ENC_PROB_BYTES);
+    for (uint32_t i = lane; i < xz::ENC_PROBS; i += 32) probs[i] = (uint16_t)xz::PROB_INIT;
+    const uint32_t len = sr.len;
+    const uint8_t* const d = work + sr.plain_off;
+    const uint32_t lo = lane * (SEG / 32), nl = lo >= len ? 0u : (len - lo < SEG / 32 ? len - lo : SEG / 32);
+    const uint32_t my_crc = nl ? xz::crc_slice(d + lo, nl) : 0u;
+    const uint32_t my_pow = xz::crc_xpow_bytes(nl);
+    uint32_t crc = 0;
+    for (int l = 0; l < 32; l++) {
+        const uint32_t c = __shfl_sync(0xFFFFFFFFu, my_crc, l), pw = __shfl_sync(0xFFFFFFFFu, my_pow, l);
+        crc = xz::crc_concat(crc, c, pw);
+    }
+    __syncwarp();
+    if (lane) return;
+    uint8_t* const head = work + sr.tmp_off;
+    const uint32_t cap = len > 4 ? len - 4 : 0u;   // a compressed chunk must save its three extra header bytes
+    const uint32_t cs = cap ? xz::lzma_encode_segment(d, len, seqs + sr.seq_off, sr.nseq, probs, head + TMP_HEAD, cap) : 0xFFFFFFFFu;
+    if (cs == 0xFFFFFFFFu) { sr.head_len = xz::lzma2_chunk_header(head, len, 0); sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0; }
+    else { sr.head_len = xz::lzma2_chunk_header(head, len, cs); sr.raw = 0; sr.tail_off = 0; sr.tail_len = cs; }
+    sr.adler_a = crc;
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void enc_layout_kernel(uint8_t* __restrict__ work, const SegRec* __restrict__ segs, EncEntry* __restrict__ entries,
                                   uint32_t n, Segment* __restrict__ pieces) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,6 +344,21 @@ __global__ void enc_layout_kernel(uint8_t* __restrict__ work, const SegRec* __re
             if (s.raw) add(s.plain_off, s.len);
             else { add(s.litp_off, s.litp_len); add(s.tmp_off + TMP_HEAD + s.tail_off, s.tail_len); }
         }
+    } else if (e.compression == 4) {
+        // .xz container around the segments' LZMA2 chunks (lzma_enc_core.cuh): front at +0, back at +24 of the entry's scratch
+        const bool empty = e.n_segs == 0;
+        add(e.hdr_off, xz::xz_write_front(h, empty));
+        uint64_t chunk_bytes = 0;
+        uint32_t crc = 0;
+        const uint32_t pow_seg = xz::crc_xpow_bytes(SEG);
+        for (uint32_t k = e.seg_begin; k < e.seg_begin + e.n_segs; k++) {
+            const SegRec& s = segs[k];
+            add(s.tmp_off, s.head_len);
+            if (s.raw) add(s.plain_off, s.len); else add(s.tmp_off + TMP_HEAD, s.tail_len);
+            chunk_bytes += s.head_len + (s.raw ? s.len : s.tail_len);
+            crc = xz::crc_concat(crc, (uint32_t)s.adler_a, s.len == SEG ? pow_seg : xz::crc_xpow_bytes(s.len));
+        }
+        add(e.hdr_off + 24, xz::xz_write_back(h + 24, empty, chunk_bytes, e.plain_len, crc));
     } else {
         h[0] = 0x78; h[1] = 0x9C;
         if (e.n_segs == 0) { h[2] = 0x03; h[3] = 0x00; add(e.hdr_off, 4); }

@@ -1,0 +1,247 @@
+// lzma_enc_core.cuh -- the XZ arm of the create seam: Compress::XZ -> liblzma's XzEncoder around the entry's writer
+// (lib/src/entry/write.rs:263, lib/src/compress.rs:29; level: lib/src/compress/xz.rs:6-47).  PNA_HD: the same code runs in
+// xz_encode_kernel and, compiled with g++, in the CPU test tier.
+//
+// LZMA adapts one probability per coded bit, so a stream is serial -- but LZMA2 cuts a stream into chunks that may reset the
+// coder state and the dictionary, and that is where the parallelism comes from: every 32 KiB segment of the matcher
+// (lz_match_kernel: the sequences never reach outside their segment) becomes ONE chunk with control byte 0xE0 (dictionary
+// reset, state reset, new properties) or, when the range coder does not shrink it, 0x01 (uncompressed, dictionary reset).
+// Chunks are therefore independent in both directions: segments are encoded by different warps, and a reader may decode them
+// in parallel.  Container (xz-file-format-1.1.0): stream header, ONE block (LZMA2 filter, 64 KiB dictionary, no size fields),
+// its chunks, end marker, padding, CRC32 check, index with one record, stream footer.  liblzma's encoder would write CRC64
+// as the check; every .xz reader accepts CRC32, and this path already owns a CRC-32 engine.
+#pragma once
+#include "lzma_core.cuh"
+#include "encode_core.cuh"
+#include "crc32_core.cuh"
+
+namespace pna {
+namespace xz {
+
+constexpr uint32_t ENC_LC = 3, ENC_LP = 0, ENC_PB = 2;                     // liblzma's defaults for every preset
+constexpr uint32_t ENC_PROPS = (ENC_PB * 5 + ENC_LP) * 9 + ENC_LC;         // 0x5D
+constexpr uint32_t ENC_PROBS = LZMA_PROBS_FIXED + (0x300u << (ENC_LC + ENC_LP));
+constexpr uint8_t ENC_DICT_CODE = 8;                                       // 64 KiB: distances stay below the 32 KiB segment
+constexpr uint32_t XZ_HDR_SCRATCH = 96;                                    // per entry: 24 bytes in front, <= 47 behind
+
+struct RangeEnc {
+    uint64_t low;
+    uint32_t range, cache, cache_size;
+    uint8_t* p;
+    uint8_t* end;
+    bool over;
+    PNA_HD void init(uint8_t* dst, uint8_t* e) { low = 0; range = 0xFFFFFFFFu; cache = 0; cache_size = 1; p = dst; end = e; over = false; }
+    PNA_HD void put(uint32_t b) { if (p < end) *p++ = (uint8_t)b; else over = true; }
+    PNA_HD void shift_low() {
+        if ((uint32_t)low < 0xFF000000u || (uint32_t)(low >> 32) != 0) {
+            const uint32_t carry = (uint32_t)(low >> 32);
+            uint32_t c = cache;
+            do { put(c + carry); c = 0xFF; } while (--cache_size);
+            cache = ((uint32_t)low >> 24) & 0xFFu;
+        }
+        cache_size++;
+        low = (uint64_t)((uint32_t)low << 8);
+    }
+    PNA_HD void bit(uint16_t* prob, uint32_t b) {
+        const uint32_t v = *prob, bound = (range >> 11) * v;
+        if (!b) { range = bound; *prob = (uint16_t)(v + ((2048u - v) >> 5)); }
+        else { low += bound; range -= bound; *prob = (uint16_t)(v - (v >> 5)); }
+        if (range < (1u << 24)) { range <<= 8; shift_low(); }
+    }
+    PNA_HD void tree(uint16_t* probs, int nbits, uint32_t v) {
+        uint32_t m = 1;
+        for (int i = nbits - 1; i >= 0; i--) { const uint32_t b = (v >> i) & 1u; bit(probs + m, b); m = (m << 1) | b; }
+    }
+    PNA_HD void tree_reverse(uint16_t* probs, int nbits, uint32_t v) {
+        uint32_t m = 1;
+        for (int i = 0; i < nbits; i++) { const uint32_t b = (v >> i) & 1u; bit(probs + m, b); m = (m << 1) | b; }
+    }
+    PNA_HD void direct(uint32_t v, int nbits) {
+        for (int i = nbits - 1; i >= 0; i--) {
+            range >>= 1;
+            if ((v >> i) & 1u) low += range;
+            if (range < (1u << 24)) { range <<= 8; shift_low(); }
+        }
+    }
+    PNA_HD void flush() { for (int i = 0; i < 5; i++) shift_low(); }
+};
+
+PNA_HD void len_encode(RangeEnc& rc, uint16_t* lc, uint32_t pos_state, uint32_t len) {
+    const uint32_t l = len - 2;
+    if (l < 8) { rc.bit(lc + 0, 0); rc.tree(lc + 2 + pos_state * 8, 3, l); }
+    else if (l < 16) { rc.bit(lc + 0, 1); rc.bit(lc + 1, 0); rc.tree(lc + 2 + 16 * 8 + pos_state * 8, 3, l - 8); }
+    else { rc.bit(lc + 0, 1); rc.bit(lc + 1, 1); rc.tree(lc + 2 + 2 * 16 * 8, 8, l - 16); }
+}
+
+// One segment d[0, len) with its parse (sequences: ll literals, then a match of ml bytes at distance off) as ONE LZMA chunk
+// payload into dst[0, cap): fresh state, fresh probabilities (the caller has set probs[0, ENC_PROBS) to PROB_INIT), positions
+// counted from 0 -- exactly what a reader sees after control byte 0xE0.  Returns the payload size, or 0xFFFFFFFF when it does
+// not fit into cap.  Matches are coded as repeats when their distance is one of the last four (the parse does not look for
+// them; structured data produces them by itself), else as a new distance.
+PNA_HD uint32_t lzma_encode_segment(const uint8_t* d, uint32_t len, const enc::Seq* sq, uint32_t nseq, uint16_t* probs, uint8_t* dst, uint32_t cap) {
+    RangeEnc rc;
+    rc.init(dst, dst + cap);
+    const uint32_t pb_mask = (1u << ENC_PB) - 1u, lp_mask = (1u << ENC_LP) - 1u;
+    uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0, pos = 0, prev = 0;
+    auto literal = [&]() {
+        const uint32_t byte = d[pos];
+        rc.bit(probs + Probs::IS_MATCH + state * 16 + (pos & pb_mask), 0);
+        uint16_t* lp = probs + Probs::LITERAL + 0x300u * (((pos & lp_mask) << ENC_LC) + (prev >> (8 - ENC_LC)));
+        uint32_t sym = 1;
+        if (state < 7) {
+            for (int i = 7; i >= 0; i--) { const uint32_t b = (byte >> i) & 1u; rc.bit(lp + sym, b); sym = (sym << 1) | b; }
+        } else {
+            uint32_t match_byte = d[pos - rep0 - 1], offs = 0x100;
+            for (int i = 7; i >= 0; i--) {
+                match_byte <<= 1;
+                const uint32_t match_bit = match_byte & offs, b = (byte >> i) & 1u;
+                rc.bit(lp + offs + match_bit + sym, b);
+                sym = (sym << 1) | b;
+                offs &= b ? match_bit : ~match_bit;
+            }
+        }
+        prev = byte;
+        pos++;
+        state = state < 4 ? 0 : state < 10 ? state - 3 : state - 6;
+    };
+    for (uint32_t s = 0; s < nseq && !rc.over; s++) {
+        const uint32_t ll = sq[s].llml & 0xFFFFu, ml = sq[s].llml >> 16, dist = sq[s].off - 1u;
+        for (uint32_t k = 0; k < ll && !rc.over; k++) literal();
+        const uint32_t pos_state = pos & pb_mask;
+        rc.bit(probs + Probs::IS_MATCH + state * 16 + pos_state, 1);
+        if (dist == rep0 || dist == rep1 || dist == rep2 || dist == rep3) {
+            rc.bit(probs + Probs::IS_REP + state, 1);
+            if (dist == rep0) {
+                rc.bit(probs + Probs::IS_REP_G0 + state, 0);
+                rc.bit(probs + Probs::IS_REP0_LONG + state * 16 + pos_state, 1);
+            } else {
+                rc.bit(probs + Probs::IS_REP_G0 + state, 1);
+                if (dist == rep1) rc.bit(probs + Probs::IS_REP_G1 + state, 0);
+                else {
+                    rc.bit(probs + Probs::IS_REP_G1 + state, 1);
+                    if (dist == rep2) rc.bit(probs + Probs::IS_REP_G2 + state, 0);
+                    else { rc.bit(probs + Probs::IS_REP_G2 + state, 1); rep3 = rep2; }
+                    rep2 = rep1;
+                }
+                rep1 = rep0; rep0 = dist;
+            }
+            len_encode(rc, probs + Probs::LEN_REP, pos_state, ml);
+            state = state < 7 ? 8 : 11;
+        } else {
+            rc.bit(probs + Probs::IS_REP + state, 0);
+            len_encode(rc, probs + Probs::LEN_MATCH, pos_state, ml);
+            state = state < 7 ? 7 : 10;
+            rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = dist;
+            const uint32_t dist_state = ml < 6 ? ml - 2 : 3;
+            uint32_t slot = dist;
+            if (dist >= 4) {
+                uint32_t n = 31;
+                while (!(dist >> n)) n--;
+                slot = 2 * n + ((dist >> (n - 1)) & 1u);
+            }
+            rc.tree(probs + Probs::POS_SLOT + dist_state * 64, 6, slot);
+            if (slot >= 4) {
+                const int nb = (int)(slot >> 1) - 1;
+                const uint32_t base = (2u | (slot & 1u)) << nb, rem = dist - base;
+                if (slot < 14) rc.tree_reverse(probs + Probs::POS_SPECIAL + base - slot - 1, nb, rem);
+                else { rc.direct(rem >> 4, nb - 4); rc.tree_reverse(probs + Probs::POS_ALIGN, 4, rem & 15u); }
+            }
+        }
+        pos += ml;
+        prev = d[pos - 1];
+    }
+    while (pos < len && !rc.over) literal();
+    rc.flush();
+    return rc.over ? 0xFFFFFFFFu : (uint32_t)(rc.p - dst);
+}
+
+// LZMA2 chunk header for a segment: compressed (6 bytes) or uncompressed (3 bytes).  Returns its length.
+PNA_HD uint32_t lzma2_chunk_header(uint8_t* h, uint32_t usize, uint32_t csize /* 0: uncompressed chunk */) {
+    const uint32_t u = usize - 1;
+    if (!csize) { h[0] = 0x01; h[1] = (uint8_t)(u >> 8); h[2] = (uint8_t)u; return 3; }
+    const uint32_t c = csize - 1;
+    h[0] = (uint8_t)(0xE0u | (u >> 16)); h[1] = (uint8_t)(u >> 8); h[2] = (uint8_t)u;
+    h[3] = (uint8_t)(c >> 8); h[4] = (uint8_t)c; h[5] = (uint8_t)ENC_PROPS;
+    return 6;
+}
+
+// x^(8n) mod P (reflected): appending n bytes to a message multiplies its CRC by this
+PNA_HD uint32_t crc_xpow_bytes(uint64_t n) {
+    uint32_t p = 0x80000000u, sq = 0x00800000u;   // x^0, x^8
+    while (n) {
+        if (n & 1) p = crc_multmodp(sq, p);
+        sq = crc_multmodp(sq, sq);
+        n >>= 1;
+    }
+    return p;
+}
+// crc(A || B) from crc(A), crc(B), |B| (finalised values; zlib's crc32_combine identity)
+PNA_HD uint32_t crc_concat(uint32_t crc_a, uint32_t crc_b, uint32_t xpow_b) { return crc_multmodp(xpow_b, crc_a) ^ crc_b; }
+// plain CRC-32 of a slice, four bytes per step, no tables (a lane's 1 KiB share of a segment)
+PNA_HD uint32_t crc_slice(const uint8_t* p, uint32_t n) {
+    uint32_t c = 0xFFFFFFFFu, i = 0;
+    for (; i + 4 <= n; i += 4) {
+        c ^= (uint32_t)p[i] | (uint32_t)p[i + 1] << 8 | (uint32_t)p[i + 2] << 16 | (uint32_t)p[i + 3] << 24;
+        for (int k = 0; k < 32; k++) c = (c >> 1) ^ (CRC_POLY & (0u - (c & 1u)));
+    }
+    for (; i < n; i++) {
+        c ^= p[i];
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (CRC_POLY & (0u - (c & 1u)));
+    }
+    return ~c;
+}
+
+PNA_HD uint32_t xz_put_vli(uint8_t* p, uint64_t v) {
+    uint32_t k = 0;
+    while (v >= 0x80) { p[k++] = (uint8_t)(v | 0x80); v >>= 7; }
+    p[k++] = (uint8_t)v;
+    return k;
+}
+PNA_HD void xz_put_le32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+// Everything of the container in front of the chunks: stream header (12 bytes) and, unless the stream is empty, the block header
+// (12 bytes).  Returns the length.
+PNA_HD uint32_t xz_write_front(uint8_t* h, bool empty) {
+    h[0] = 0xFD; h[1] = '7'; h[2] = 'z'; h[3] = 'X'; h[4] = 'Z'; h[5] = 0;
+    h[6] = 0x00; h[7] = 0x01;                                  // stream flags: check = CRC32
+    xz_put_le32(h + 8, xz_crc32(h + 6, 2));
+    if (empty) return 12;
+    h[12] = 0x02;                                              // header size (12 bytes)
+    h[13] = 0x00;                                              // one filter, no size fields
+    h[14] = 0x21; h[15] = 0x01; h[16] = ENC_DICT_CODE;         // LZMA2, one property byte
+    h[17] = h[18] = h[19] = 0;
+    xz_put_le32(h + 20, xz_crc32(h + 12, 8));
+    return 24;
+}
+// Everything behind the chunks: end marker, block padding, check, index, footer (no block at all for an empty stream, as
+// liblzma writes it).  chunk_bytes: all chunk headers + payloads.  Returns the length (<= 47).
+PNA_HD uint32_t xz_write_back(uint8_t* t, bool empty, uint64_t chunk_bytes, uint64_t plain_len, uint32_t crc) {
+    uint32_t k = 0;
+    if (!empty) {
+        t[k++] = 0x00;                                         // LZMA2 end marker
+        const uint64_t csz = chunk_bytes + 1;
+        for (uint64_t q = csz; q & 3; q++) t[k++] = 0;
+        xz_put_le32(t + k, crc); k += 4;
+        const uint32_t ix = k;
+        t[k++] = 0x00; t[k++] = 0x01;
+        k += xz_put_vli(t + k, 12 + csz + 4);                  // unpadded size: header + data + check
+        k += xz_put_vli(t + k, plain_len);
+        while ((k - ix) & 3) t[k++] = 0;
+        xz_put_le32(t + k, xz_crc32(t + ix, k - ix)); k += 4;
+        uint8_t* f = t + k;
+        xz_put_le32(f + 4, (k - ix) / 4 - 1);
+        f[8] = 0x00; f[9] = 0x01; f[10] = 'Y'; f[11] = 'Z';
+        xz_put_le32(f, xz_crc32(f + 4, 6));
+        return k + 12;
+    }
+    t[0] = 0x00; t[1] = 0x00; t[2] = 0; t[3] = 0;
+    xz_put_le32(t + 4, xz_crc32(t, 4));
+    uint8_t* f = t + 8;
+    xz_put_le32(f + 4, 8 / 4 - 1);
+    f[8] = 0x00; f[9] = 0x01; f[10] = 'Y'; f[11] = 'Z';
+    xz_put_le32(f, xz_crc32(f + 4, 6));
+    return 20;
+}
+
+}  // namespace xz
+}  // namespace pna

@@ -173,6 +173,7 @@ extern "C" int hc_inflate(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t 
 // ---- encode: the PNA_HD bitstream writers driven by a plain greedy matcher (test-side stand-in for the
 // warp-synchronous matcher of kernels_encode.cuh); output must decode with libzstd / zlib (checked in Python)
 #include "../../portable-network-archive_b200/csrc/encode_core.cuh"
+#include "../../portable-network-archive_b200/csrc/lzma_enc_core.cuh"
 static pna::enc::EncTables g_enc; static bool g_enc_init = false;
 static int g_enc_dyn = 1;   // per-block FSE tables (the default effort) or predefined ones (the fast setting)
 extern "C" void hc_set_enc_dyn(int v) { g_enc_dyn = v; }
@@ -202,6 +203,35 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
     if (!g_enc_init) { make_enc_tables(&g_enc); g_enc_init = true; }
     uint64_t o = 0;
     const uint64_t nseg = len ? (len + SEG - 1) / SEG : 0;
+    if (compression == 4) {   // xz: the segment writer + container pieces of lzma_enc_core.cuh, stitched the way the kernels do
+        using namespace pna::xz;
+        o = xz_write_front(out, nseg == 0);
+        uint64_t chunk_bytes = 0;
+        uint32_t crc = 0;
+        std::vector<uint16_t> probs(ENC_PROBS);
+        for (uint64_t s = 0; s < nseg; s++) {
+            const uint8_t* d = in + s * SEG;
+            const uint32_t n = (uint32_t)(len - s * SEG < SEG ? len - s * SEG : SEG);
+            std::vector<Seq> seqs; std::vector<uint8_t> lits;
+            greedy_segment(d, n, seqs, lits);
+            for (auto& q : probs) q = (uint16_t)PROB_INIT;
+            std::vector<uint8_t> body(SEG + 64);
+            const uint32_t cap = n > 4 ? n - 4 : 0;
+            const uint32_t cs = cap ? lzma_encode_segment(d, n, seqs.data(), (uint32_t)seqs.size(), probs.data(), body.data(), cap) : 0xFFFFFFFFu;
+            uint32_t hl;
+            if (cs == 0xFFFFFFFFu) { hl = lzma2_chunk_header(out + o, n, 0); o += hl; memcpy(out + o, d, n); o += n; chunk_bytes += hl + n; }
+            else { hl = lzma2_chunk_header(out + o, n, cs); o += hl; memcpy(out + o, body.data(), cs); o += cs; chunk_bytes += hl + cs; }
+            // lanes' slices combined the way xz_encode_kernel does
+            uint32_t sc = 0;
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t lo = l * 1024, nl = lo >= n ? 0 : (n - lo < 1024 ? n - lo : 1024);
+                if (nl) sc = crc_concat(sc, crc_slice(d + lo, nl), crc_xpow_bytes(nl));
+            }
+            crc = crc_concat(crc, sc, crc_xpow_bytes(n));
+        }
+        o += xz_write_back(out + o, nseg == 0, chunk_bytes, len, crc);
+        return o;
+    }
     if (compression == 2) {
         const uint8_t fh[6] = {0x28, 0xB5, 0x2F, 0xFD, 0x00, 0x38};
         memcpy(out, fh, 6); o = 6;

@@ -26,7 +26,7 @@ def _plain(i, n):
     return (b"abcdefgh" * (n // 8 + 1))[:n]                # short period
 
 
-@pytest.mark.parametrize("comp", [0, 1, 2])
+@pytest.mark.parametrize("comp", [0, 1, 2, 4])
 def test_encode_cross_product_reference_readable(ctx, oracle, comp):
     key = os.urandom(32)
     entries, plains = [], []
@@ -141,3 +141,65 @@ def test_many_small_entries_and_builder_api(ctx, pna, oracle):
     ar = pna.Archive.read_header(np.frombuffer(blob, dtype=np.uint8), ctx)
     back = {e.name: d for e, d in ar.read_all(pna.ReadOptions.with_password(b"pw"))}
     assert back == files
+
+
+def test_xz_encode_chunks_levels_and_container(ctx, pna, oracle):
+    """Compress::XZ on the create side (entry/write.rs:263): every stream is ONE .xz stream that liblzma (the reference's own
+    decoder) reads back; one LZMA2 chunk per 32 KiB segment, each resetting dictionary and state (0xE0 / 0x01), CRC32 check;
+    the empty input is liblzma's zero-block stream; the archive built from it is read by the reference reader."""
+    import lzma
+    kinds = [b"", b"a", bytes(200_000), (b"abcdefgh" * 30_000), os.urandom(70_000), corpus.make_file(8, 47), corpus.make_file(9, 3000),
+             b"".join(bytes([i & 255]) * (1 + i % 7) for i in range(40_000)), corpus.make_file(10, 700_000),
+             corpus.make_file(11, 40_000) + os.urandom(40_000) + corpus.make_file(12, 40_000)]     # mixed: both chunk kinds in one stream
+    ents = [{"plain": k, "compression": 4, "level": lv} for k in kinds for lv in (0, 6, 9)]
+    streams, _, st = ctx.encode_batch(ents)
+    assert st == [0] * len(ents)
+    for e, s in zip(ents, streams):
+        s = s.tobytes()
+        assert lzma.decompress(s, format=lzma.FORMAT_XZ) == e["plain"]
+        assert s[:8] == b"\xfd7zXZ\x00\x00\x01" and s[-2:] == b"YZ"       # stream flags: CRC32
+        if not e["plain"]:
+            assert len(s) == 32
+            continue
+        # walk the block: header (12 bytes), then one chunk per segment
+        at, n_chunks, total = 24, 0, 0
+        while s[at] != 0:
+            ctl = s[at]
+            assert ctl == 0x01 or (ctl & 0xE0) == 0xE0, hex(ctl)
+            if ctl == 0x01:
+                u = ((s[at + 1] << 8) | s[at + 2]) + 1
+                at += 3 + u
+            else:
+                u = (((ctl & 0x1F) << 16) | (s[at + 1] << 8) | s[at + 2]) + 1
+                c = ((s[at + 3] << 8) | s[at + 4]) + 1
+                assert s[at + 5] == 0x5D and c + 3 < u
+                at += 6 + c
+            assert u <= 32768
+            n_chunks += 1; total += u
+        assert total == len(e["plain"]) and n_chunks == (len(e["plain"]) + 32767) // 32768
+    big = corpus.make_file(10, 700_000)
+    sizes = {lv: len(s) for e, s in zip(ents, streams) for lv in [e["level"]] if e["plain"] == big}
+    ref = len(lzma.compress(big, preset=6))
+    print(f"xz sizes by level {sizes}, liblzma preset 6: {ref}")
+    assert sizes[9] == sizes[6] <= sizes[0] and sizes[6] < 1.5 * ref
+    # our own decoder reads it (GPU -> GPU), also encrypted
+    key = os.urandom(32)
+    ents2 = [{"plain": k, "compression": 4, "level": -1, "encryption": 1, "cipher_mode": 1, "key": key, "iv": os.urandom(16)} for k in kinds]
+    streams2, _, st = ctx.encode_batch(ents2)
+    assert st == [0] * len(ents2)
+    back, st2, _ = ctx.decode_batch([{"bodies": [s], "compression": 4, "encryption": 1, "cipher_mode": 1, "key": key, "raw_size_hint": None}
+                                     for s in streams2])
+    assert st2 == [0] * len(kinds) and all(b.tobytes() == k for b, k in zip(back, kinds))
+    # through the host mirror: an xz archive the reference reader extracts
+    opts = pna.WriteOptions(compression=4, encryption=2, cipher_mode=0, password=b"pw", kdf_params={"i": 1000})
+    files = {f"x/f{i}": k for i, k in enumerate(kinds)}
+    builders = []
+    for name, data in files.items():
+        b = pna.FileEntryBuilder.new_with_options(name, opts)
+        b.write(data)
+        builders.append(b)
+    a = pna.Archive.write_header(ctx)
+    for be in pna.EntryBuilder.build_many(builders, ctx):
+        a.add_entry(be)
+    blob = a.finalize()
+    assert dict(oracle.extract_all(blob, b"pw")) == files

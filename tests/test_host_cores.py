@@ -169,6 +169,41 @@ def test_encode_writers_decode_with_reference_codecs(hc, oracle, comp):
             assert n < len(d)
 
 
+def test_xz_writer_core_decodes_with_liblzma(hc):
+    """lzma_enc_core.cuh (range encoder, literal / match / repeat coding, LZMA2 chunk headers, the .xz container with its three
+    small CRC32s and the sliced CRC32 check) against liblzma, the decoder the reference links (entry/read.rs:182): every size
+    around the segment boundary, both chunk kinds, repeats, the empty stream."""
+    import lzma
+    hc.hc_encode.restype = C.c_uint64
+    hc.hc_encode.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p]
+    rnd = random.Random(4)
+    cases = [b"", b"a", b"ab", b"abcd" * 3, bytes(5), bytes(70000), os.urandom(40000), corpus.make_file(7, 200000),
+             corpus.make_file(8, 32767), corpus.make_file(8, 32768), corpus.make_file(9, 32769), b"xyz" * 30000,
+             bytes(rnd.randrange(4) for _ in range(100000)), corpus.make_file(10, 50000) + os.urandom(50000) + corpus.make_file(11, 50000),
+             b"".join(bytes([i & 255]) * (1 + i % 7) for i in range(30_000)),
+             b"".join((b"<row id=%d>" % (i % 10)) + bytes(rnd.randrange(256) for _ in range(3)) + b"</row>\n" for i in range(8000))]
+    tot_in = tot_out = 0
+    for d in cases:
+        out = C.create_string_buffer(len(d) + len(d) // 1000 + 4096)
+        n = hc.hc_encode(4, d, len(d), out)
+        s = out.raw[:n]
+        dec = lzma.LZMADecompressor(format=lzma.FORMAT_XZ)
+        assert dec.decompress(s) == d and dec.eof and not dec.unused_data, len(d)
+        assert dec.check == lzma.CHECK_CRC32 or not d
+        assert n <= len(d) + 3 * ((len(d) + 32767) // 32768) + 72           # the bound pna_cuda_encode_bound promises
+        tot_in += len(d); tot_out += n
+    out = C.create_string_buffer(64)
+    n = hc.hc_encode(4, b"", 0, out)
+    assert out.raw[:n] == lzma.compress(b"", check=lzma.CHECK_CRC32)   # the zero-block stream, byte for byte
+    # a flipped payload bit is caught by the check we wrote
+    d = corpus.make_file(12, 100000)
+    out = C.create_string_buffer(len(d) + 4096)
+    n = hc.hc_encode(4, d, len(d), out)
+    s = bytearray(out.raw[:n]); s[n - 40] ^= 1
+    with pytest.raises(lzma.LZMAError):
+        lzma.decompress(bytes(s))
+
+
 @pytest.mark.parametrize("comp", [1, 2])
 def test_block_writers_table_choices_decode_with_reference_codecs(hc, oracle, comp):
     """The per-block table machinery of the writers (encode_core.cuh): zstd Predefined / RLE / FSE_Compressed per table with the
