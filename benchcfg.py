@@ -196,6 +196,64 @@ def cfg4(pna, host, ctx, files, plain_pinned, p_offs, threads, workers, compress
             "checked": f"{checked} entries decoded by the reference pipeline (oracle: libzstd/zlib + OpenSSL) == source files; " + ("the whole archive extracted by this library == sampled source files" if x_dt else "")}
 
 
+def create_xz(pna, host, ctx, files, plain_pinned, p_offs, threads):
+    """create with Compress::XZ (entry/write.rs:263) on a quarter of the cfg2 shard: GPU LZMA2 (one chunk per 32 KiB segment) +
+    AES-256-CTR + CRC-32; liblzma preset 6 (the reference's encoder and level) on a bounded sample beside it"""
+    import lzma
+    from concurrent.futures import ThreadPoolExecutor
+    import pna_oracle as O
+    n = len(files)
+    U = int(p_offs[n])
+    views = [plain_pinned[int(p_offs[i]):int(p_offs[i + 1])] for i in range(n)]
+    names = [f"corpus/{i:07d}.bin" for i in range(n)]
+    opts = pna.WriteOptions(compression=4, encryption=1, cipher_mode=1, password=b"pw", kdf_params={"i": 1000})
+    rng = np.random.Generator(np.random.PCG64(44))
+    ivs = rng.bytes(16 * n)
+    arch = ctx.pinned(int(U * 1.03) + (64 << 20))
+    state = {}
+
+    def create():
+        state["blob"] = host.create_archive(list(zip(names, views)), compression=4, level=6, encryption=1, cipher_mode=1, key=KEY,
+                                            phsf=opts.phsf, ivs=ivs, max_chunk_size=0, device=ctx.device, workers=4, group_bytes=256 << 20, out=arch)
+    c_dt, _ = _timed(create, 2)
+    blob = state["blob"]
+    ents = [{"plain": v, "compression": 4, "level": 6, "encryption": 1, "cipher_mode": 1, "key": KEY, "iv": ivs[16 * i:16 * i + 16],
+             "max_chunk_size": 0} for i, v in enumerate(views)]
+    eplan = ctx.encode_plan(ents)
+    eplan.run()
+    eplan.run()
+    stage = eplan.stage_ms()
+    k_ms = sum(stage.values())
+    eplan.close()
+    a = pna.Archive.read_header(blob, ctx, verify=False)
+    checked = 0
+    for i, e in enumerate(a.entries()):
+        if i % max(1, n // 16):
+            continue
+        s = b"".join(bytes(b) for b in e.bodies)
+        assert O.decode_stream(s, 4, 1, 1, KEY, None) == files[i], "GPU-created xz entry is not reference-readable"
+        checked += 1
+    back = dict((e.name, d) for e, d in a.read_all(pna.ReadOptions.with_password(b"pw")))   # and all of it by our own xz decoder
+    assert all(bytes(back[nm]) == f for nm, f in zip(names, files))
+    ns = max(1, min(n, threads))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        ref = list(ex.map(lambda f: len(lzma.compress(f, preset=6)), files[:ns]))
+    cpu_dt = time.perf_counter() - t0
+    blob_size = int(blob.size)
+    c_gpu_sample = (float(blob_size) - n * 150.0) * (ns / n)
+    del blob, state, a, back
+    ctx.pinned_free(arch)
+    return {"shape": f"{n} x 4 MiB files ({U} bytes), GPU xz (LZMA2, one chunk per 32 KiB segment, level 6 request) + AES-256-CTR + chunk CRC-32",
+            "plain_bytes": U, "archive_bytes": blob_size, "value": U / (k_ms * 1e-3) / 1e9, "unit": "GB/s", "kernel_ms": k_ms, "stage_ms": stage,
+            "e2e": {"value": U / c_dt / 1e9, "unit": "GB/s", "ms": c_dt * 1e3, "h2d_bytes": U, "d2h_bytes": blob_size},
+            "ratio": U / float(blob_size), "c_gpu_over_c_ref": c_gpu_sample / float(sum(ref)),
+            "c_ref": f"liblzma preset 6 (python lzma = the C library the reference links) on {ns} of the {n} files",
+            "cpu_baseline": {"value": ns * len(files[0]) / cpu_dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "reference",
+                             "sample": f"{ns} x 4 MiB entries, liblzma preset 6, one stream per thread (compression only, no cipher)"},
+            "checked": f"{checked} entries decoded by liblzma + OpenSSL == source files; the whole archive extracted by this library's xz decoder == source files"}
+
+
 def cfg5(pna, host, ctx, files, threads, workers):
     """config 5: solid-mode zstd archive (ONE entry, one reference-written frame), block-parallel decode on 1 GPU vs per-entry mode"""
     import pna_oracle as O
@@ -272,6 +330,8 @@ def run_all(pna, host, ctx, all_files, threads, scale, workers):
         p_offs[i + 1] = pos
     guarded("cfg4_zstd", lambda: cfg4(pna, host, ctx, all_files, plain_pinned, p_offs, threads, workers, 2, 3, "zstd (level 3 request)"))
     guarded("cfg4_deflate", lambda: cfg4(pna, host, ctx, all_files, plain_pinned, p_offs, threads, workers, 1, 6, "deflate (level 6 request)"))
+    nx = max(4, int(256 * scale))
+    guarded("create_xz", lambda: create_xz(pna, host, ctx, all_files[:nx], plain_pinned, p_offs, threads))
     corpus_np = np.frombuffer(plain_pinned, dtype=np.uint8)
     guarded("cfg3", lambda: cfg3(pna, host, ctx, corpus_np, threads, scale, workers))
     guarded("cfg1", lambda: cfg1(pna, host, ctx, corpus_np, threads, scale, workers))

@@ -350,7 +350,7 @@ static int encode_launch_all(pna_plan* P) {
             LAUNCHED();
         }
         if (E->has_xz) {
-            enc::xz_encode_kernel<<<(nsegs + enc::XZ_ENC_WARPS - 1) / enc::XZ_ENC_WARPS, 32 * enc::XZ_ENC_WARPS, enc::XZ_ENC_SMEM_BYTES, ctx->stream>>>(
+            enc::xz_encode_kernel<<<nsegs, 32, enc::XZ_ENC_SMEM_BYTES, ctx->stream>>>(
                 E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_entries.p);
             LAUNCHED();
         }

@@ -284,23 +284,24 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
 }
 
 // ------------------------------------------------------------------------------------------------
-// xz: a warp per segment.  All lanes reset the segment's probability arena (16 KB of shared memory: the dependent
-// load-compare-update chain per coded bit runs at shared-memory latency) and take the CRC-32 of a 1 KiB slice each; lane 0 then
-// runs the range coder over the segment's parse (lzma_enc_core.cuh) and writes the LZMA2 chunk header.  Segments are independent
-// chunks, so a 4 MiB file is 128 coders in flight; 12 segments per SM.
-constexpr int XZ_ENC_WARPS = 4;
-constexpr uint32_t XZ_ENC_PROB_BYTES = (xz::ENC_PROBS * 2u + 15u) & ~15u;
-constexpr uint32_t XZ_ENC_SMEM_BYTES = XZ_ENC_PROB_BYTES * XZ_ENC_WARPS;
-__global__ void __launch_bounds__(32 * XZ_ENC_WARPS) xz_encode_kernel(uint8_t* __restrict__ work, SegRec* __restrict__ segs, uint32_t nsegs,
-                                                                      const Seq* __restrict__ seqs, const EncEntry* __restrict__ entries) {
+// xz: a warp (= a CTA) per segment.  All lanes reset the segment's probability arena (16 KB of shared memory: the dependent
+// load-update-store chain per coded bit runs at shared-memory latency) and take the CRC-32 of a 1 KiB slice each.  Then, sequence by
+// sequence: the lanes turn 32 literals at a time into their coder events (lzma_enc_core.cuh: probability index and bit depend on
+// data and parse only), lane 0 adds the events of the match and runs the one serial loop, the range coder, over the ring.
+// Segments are independent chunks, so a 4 MiB file is 128 coders in flight; 13 per SM.
+constexpr uint32_t XZ_ENC_RING = 32 * xz::EV_PER_LITERAL + xz::EV_PER_MATCH_MAX;   // 32 literals and the match behind them
+constexpr uint32_t XZ_ENC_SMEM_BYTES = ((xz::ENC_PROBS + 2 + XZ_ENC_RING) * 2u + 15u) & ~15u;   // + the scratch slot of direct bits
+__global__ void __launch_bounds__(32) xz_encode_kernel(uint8_t* __restrict__ work, SegRec* __restrict__ segs, uint32_t nsegs,
+                                                       const Seq* __restrict__ seqs, const EncEntry* __restrict__ entries) {
     extern __shared__ __align__(16) uint8_t xz_enc_smem_raw[];
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const uint32_t s = blockIdx.x * XZ_ENC_WARPS + w;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t s = blockIdx.x;
     if (s >= nsegs) return;
     SegRec& sr = segs[s];
     if (entries[sr.entry].compression != 4) return;
-    uint16_t* const probs = reinterpret_cast<uint16_t*>(xz_enc_smem_raw + w * XZ_ENC_PROB_BYTES);
-    for (uint32_t i = lane; i < xz::ENC_PROBS; i += 32) probs[i] = (uint16_t)xz::PROB_INIT;
+    uint16_t* const probs = reinterpret_cast<uint16_t*>(xz_enc_smem_raw);
+    uint16_t* const ring = probs + xz::ENC_PROBS + 2;
+    for (uint32_t i = lane; i < xz::ENC_PROBS + 2; i += 32) probs[i] = (uint16_t)xz::PROB_INIT;
     const uint32_t len = sr.len;
     const uint8_t* const d = work + sr.plain_off;
     const uint32_t lo = lane * (SEG / 32), nl = lo >= len ? 0u : (len - lo < SEG / 32 ? len - lo : SEG / 32);
@@ -312,10 +313,44 @@ __global__ void __launch_bounds__(32 * XZ_ENC_WARPS) xz_encode_kernel(uint8_t* _
         crc = xz::crc_concat(crc, c, pw);
     }
     __syncwarp();
-    if (lane) return;
     uint8_t* const head = work + sr.tmp_off;
     const uint32_t cap = len > 4 ? len - 4 : 0u;   // a compressed chunk must save its three extra header bytes
-    const uint32_t cs = cap ? xz::lzma_encode_segment(d, len, seqs + sr.seq_off, sr.nseq, probs, head + TMP_HEAD, cap) : 0xFFFFFFFFu;
+    xz::RangeEnc rc;                               // lane 0's copy is the coder
+    rc.init(head + TMP_HEAD, head + TMP_HEAD + cap, head + TMP_SEG);
+    uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0, pos = 0;   // the same in every lane
+    const Seq* const sq = seqs + sr.seq_off;
+    const uint32_t nseq = cap ? sr.nseq : 0u;
+    bool over = cap == 0;
+    // one round per sequence, and a last one for the literals behind the last match; ONE call site of the coder loop
+    for (uint32_t q = 0; q <= nseq && !over; q++) {
+        const bool has_match = q < nseq;
+        uint32_t ll = len - pos, ml = 0, dist = 0;
+        if (has_match) { const Seq v = sq[q]; ll = v.llml & 0xFFFFu; ml = v.llml >> 16; dist = v.off - 1u; }
+        const uint32_t rep0_lit = rep0;   // the first literal behind a match looks at the byte at the LAST distance
+        const uint32_t kind = has_match ? xz::rep_classify(dist, rep0, rep1, rep2, rep3) : 0u;
+        uint32_t base = 0;
+        do {
+            const uint32_t j = base + lane, p = pos + j, cnt = ll - base < 32 ? ll - base : 32;
+            if (j < ll) {
+                const uint32_t st = xz::lit_state_after(state, j);
+                xz::gen_literal_events(ring + lane * xz::EV_PER_LITERAL, p, d[p], p ? d[p - 1] : 0u, st, st >= 7 ? d[p - rep0_lit - 1] : 0u);
+            }
+            uint32_t total = cnt * xz::EV_PER_LITERAL;
+            if (lane == 0 && has_match && base + 32 >= ll)
+                total += xz::gen_match_events(ring + total, pos + ll, xz::lit_state_after(state, ll), kind, ml, dist);
+            __syncwarp();
+            if (lane == 0) xz::code_events(rc, probs, ring, total);
+            __syncwarp();
+            base += 32;
+        } while (base < ll);
+        state = xz::lit_state_after(state, ll);
+        if (has_match) state = xz::match_state_next(state, kind);
+        pos += ll + ml;
+        over = __shfl_sync(0xFFFFFFFFu, rc.over ? 1 : 0, 0) != 0;
+    }
+    if (lane) return;
+    rc.flush();
+    const uint32_t cs = (over || rc.over || (uint32_t)(rc.p - (head + TMP_HEAD)) > cap) ? 0xFFFFFFFFu : (uint32_t)(rc.p - (head + TMP_HEAD));
     if (cs == 0xFFFFFFFFu) { sr.head_len = xz::lzma2_chunk_header(head, len, 0); sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0; }
     else { sr.head_len = xz::lzma2_chunk_header(head, len, cs); sr.raw = 0; sr.tail_off = 0; sr.tail_len = cs; }
     sr.adler_a = crc;

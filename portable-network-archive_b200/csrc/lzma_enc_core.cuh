@@ -28,131 +28,191 @@ struct RangeEnc {
     uint64_t low;
     uint32_t range, cache, cache_size;
     uint8_t* p;
-    uint8_t* end;
+    uint8_t* limit;   // a payload that grows past this is given up (the chunk goes out uncompressed)
+    uint8_t* end;     // end of the buffer
     bool over;
-    PNA_HD void init(uint8_t* dst, uint8_t* e) { low = 0; range = 0xFFFFFFFFu; cache = 0; cache_size = 1; p = dst; end = e; over = false; }
-    PNA_HD void put(uint32_t b) { if (p < end) *p++ = (uint8_t)b; else over = true; }
+    PNA_HD void init(uint8_t* dst, uint8_t* lim, uint8_t* e) { low = 0; range = 0xFFFFFFFFu; cache = 0; cache_size = 1; p = dst; limit = lim; end = e; over = false; }
+    // Bytes leave unchecked: every call of shift_low emits at most one byte of its own plus the 0xFF bytes earlier calls held
+    // back, so the stream never grows faster than one byte per coded bit -- room() is asked once per batch of events.
+    PNA_HD bool room(uint32_t n_events) { if (p > limit || p + cache_size + n_events + 8 > end) over = true; return !over; }
     PNA_HD void shift_low() {
-        if ((uint32_t)low < 0xFF000000u || (uint32_t)(low >> 32) != 0) {
-            const uint32_t carry = (uint32_t)(low >> 32);
-            uint32_t c = cache;
-            do { put(c + carry); c = 0xFF; } while (--cache_size);
-            cache = ((uint32_t)low >> 24) & 0xFFu;
+        const uint32_t lo32 = (uint32_t)low, carry = (uint32_t)(low >> 32);
+        if (lo32 < 0xFF000000u || carry != 0) {
+            *p++ = (uint8_t)(cache + carry);
+            if (__builtin_expect(cache_size > 1, 0)) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+                for (uint32_t k = 1; k < cache_size; k++) *p++ = (uint8_t)(0xFFu + carry);
+            }
+            cache = lo32 >> 24;
+            cache_size = 0;
         }
         cache_size++;
-        low = (uint64_t)((uint32_t)low << 8);
+        low = (uint64_t)(lo32 << 8);
     }
-    PNA_HD void bit(uint16_t* prob, uint32_t b) {
-        const uint32_t v = *prob, bound = (range >> 11) * v;
-        if (!b) { range = bound; *prob = (uint16_t)(v + ((2048u - v) >> 5)); }
-        else { low += bound; range -= bound; *prob = (uint16_t)(v - (v >> 5)); }
-        if (range < (1u << 24)) { range <<= 8; shift_low(); }
-    }
-    PNA_HD void tree(uint16_t* probs, int nbits, uint32_t v) {
-        uint32_t m = 1;
-        for (int i = nbits - 1; i >= 0; i--) { const uint32_t b = (v >> i) & 1u; bit(probs + m, b); m = (m << 1) | b; }
-    }
-    PNA_HD void tree_reverse(uint16_t* probs, int nbits, uint32_t v) {
-        uint32_t m = 1;
-        for (int i = 0; i < nbits; i++) { const uint32_t b = (v >> i) & 1u; bit(probs + m, b); m = (m << 1) | b; }
-    }
-    PNA_HD void direct(uint32_t v, int nbits) {
-        for (int i = nbits - 1; i >= 0; i--) {
-            range >>= 1;
-            if ((v >> i) & 1u) low += range;
-            if (range < (1u << 24)) { range <<= 8; shift_low(); }
-        }
-    }
-    PNA_HD void flush() { for (int i = 0; i < 5; i++) shift_low(); }
+    PNA_HD void flush() { if (room(0)) for (int i = 0; i < 5; i++) shift_low(); }
 };
 
-PNA_HD void len_encode(RangeEnc& rc, uint16_t* lc, uint32_t pos_state, uint32_t len) {
-    const uint32_t l = len - 2;
-    if (l < 8) { rc.bit(lc + 0, 0); rc.tree(lc + 2 + pos_state * 8, 3, l); }
-    else if (l < 16) { rc.bit(lc + 0, 1); rc.bit(lc + 1, 0); rc.tree(lc + 2 + 16 * 8 + pos_state * 8, 3, l - 8); }
-    else { rc.bit(lc + 0, 1); rc.bit(lc + 1, 1); rc.tree(lc + 2 + 2 * 16 * 8, 8, l - 16); }
+// ---- The coded bit stream as a list of EVENTS.  Which probability a bit is coded with, and the bit itself, depend on the data and
+// the parse only -- never on the adaptive state of the coder.  So the work splits: any thread can turn a symbol into its events
+// (prob index | bit << 15, or a direct bit), and the one serial thing left, the range coder, is a single small loop over them
+// (one copy of the coder in the instruction stream instead of one per call site: the first version of this encoder spent 3/4 of
+// its stall samples waiting for instruction fetch).
+constexpr uint32_t EV_BIT = 0x8000u, EV_DIRECT = 0x4000u, EV_INDEX = 0x1FFFu;
+static_assert(ENC_PROBS <= EV_INDEX + 1, "prob index fits the event word");
+constexpr uint32_t EV_PER_LITERAL = 9, EV_PER_MATCH_MAX = 40;
+
+PNA_HD uint32_t lit_state_next(uint32_t state) { return state < 4 ? 0 : state < 10 ? state - 3 : state - 6; }
+PNA_HD uint32_t lit_state_after(uint32_t state, uint32_t k) {   // three literals take every state to 0
+    for (uint32_t i = 0; i < k && i < 3; i++) state = lit_state_next(state);
+    return state;
+}
+// the literal `byte` at position pos (state: the coder state in front of it; match_byte: the byte at the last distance, used when
+// state >= 7): EV_PER_LITERAL events
+PNA_HD void gen_literal_events(uint16_t* ev, uint32_t pos, uint32_t byte, uint32_t prev, uint32_t state, uint32_t match_byte) {
+    const uint32_t pb_mask = (1u << ENC_PB) - 1u, lp_mask = (1u << ENC_LP) - 1u;
+    ev[0] = (uint16_t)(Probs::IS_MATCH + state * 16 + (pos & pb_mask));
+    const uint32_t lp = Probs::LITERAL + 0x300u * (((pos & lp_mask) << ENC_LC) + (prev >> (8 - ENC_LC)));
+    uint32_t sym = 1;
+    if (state < 7) {
+        for (int i = 7; i >= 0; i--) { const uint32_t b = (byte >> i) & 1u; ev[8 - i] = (uint16_t)((lp + sym) | (b << 15)); sym = (sym << 1) | b; }
+    } else {
+        uint32_t offs = 0x100;
+        for (int i = 7; i >= 0; i--) {
+            match_byte <<= 1;
+            const uint32_t match_bit = match_byte & offs, b = (byte >> i) & 1u;
+            ev[8 - i] = (uint16_t)((lp + offs + match_bit + sym) | (b << 15));
+            sym = (sym << 1) | b;
+            offs &= b ? match_bit : ~match_bit;
+        }
+    }
+}
+struct EvOut {
+    uint16_t* ev;
+    uint32_t n;
+    PNA_HD void bit(uint32_t idx, uint32_t b) { ev[n++] = (uint16_t)(idx | (b << 15)); }
+    PNA_HD void tree(uint32_t base, int nbits, uint32_t v) {
+        uint32_t m = 1;
+        for (int i = nbits - 1; i >= 0; i--) { const uint32_t b = (v >> i) & 1u; bit(base + m, b); m = (m << 1) | b; }
+    }
+    PNA_HD void tree_reverse(uint32_t base, int nbits, uint32_t v) {
+        uint32_t m = 1;
+        for (int i = 0; i < nbits; i++) { const uint32_t b = (v >> i) & 1u; bit(base + m, b); m = (m << 1) | b; }
+    }
+    PNA_HD void direct(uint32_t v, int nbits) { for (int i = nbits - 1; i >= 0; i--) ev[n++] = (uint16_t)(EV_DIRECT | (((v >> i) & 1u) << 15)); }
+    PNA_HD void len(uint32_t lc, uint32_t pos_state, uint32_t length) {
+        const uint32_t l = length - 2;
+        if (l < 8) { bit(lc + 0, 0); tree(lc + 2 + pos_state * 8, 3, l); }
+        else if (l < 16) { bit(lc + 0, 1); bit(lc + 1, 0); tree(lc + 2 + 16 * 8 + pos_state * 8, 3, l - 8); }
+        else { bit(lc + 0, 1); bit(lc + 1, 1); tree(lc + 2 + 2 * 16 * 8, 8, l - 16); }
+    }
+};
+// which of the last four distances a match repeats (0..3), or 4: a new distance.  Updates the history the way the decoder does.
+PNA_HD uint32_t rep_classify(uint32_t dist, uint32_t& rep0, uint32_t& rep1, uint32_t& rep2, uint32_t& rep3) {
+    if (dist == rep0) return 0;
+    if (dist == rep1) { rep1 = rep0; rep0 = dist; return 1; }
+    if (dist == rep2) { rep2 = rep1; rep1 = rep0; rep0 = dist; return 2; }
+    const uint32_t k = dist == rep3 ? 3u : 4u;
+    rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = dist;
+    return k;
+}
+// a match of ml bytes at distance dist + 1, coded as repeat `kind` (rep_classify) at position pos in state `state`: at most
+// EV_PER_MATCH_MAX events.  Returns their number.
+PNA_HD uint32_t gen_match_events(uint16_t* ev, uint32_t pos, uint32_t state, uint32_t kind, uint32_t ml, uint32_t dist) {
+    EvOut o{ev, 0};
+    const uint32_t pos_state = pos & ((1u << ENC_PB) - 1u);
+    o.bit(Probs::IS_MATCH + state * 16 + pos_state, 1);
+    if (kind < 4) {
+        o.bit(Probs::IS_REP + state, 1);
+        if (kind == 0) { o.bit(Probs::IS_REP_G0 + state, 0); o.bit(Probs::IS_REP0_LONG + state * 16 + pos_state, 1); }
+        else {
+            o.bit(Probs::IS_REP_G0 + state, 1);
+            if (kind == 1) o.bit(Probs::IS_REP_G1 + state, 0);
+            else { o.bit(Probs::IS_REP_G1 + state, 1); o.bit(Probs::IS_REP_G2 + state, kind == 2 ? 0u : 1u); }
+        }
+        o.len(Probs::LEN_REP, pos_state, ml);
+    } else {
+        o.bit(Probs::IS_REP + state, 0);
+        o.len(Probs::LEN_MATCH, pos_state, ml);
+        const uint32_t dist_state = ml < 6 ? ml - 2 : 3;
+        uint32_t slot = dist;
+        if (dist >= 4) {
+            uint32_t n = 31;
+            while (!(dist >> n)) n--;
+            slot = 2 * n + ((dist >> (n - 1)) & 1u);
+        }
+        o.tree(Probs::POS_SLOT + dist_state * 64, 6, slot);
+        if (slot >= 4) {
+            const int nb = (int)(slot >> 1) - 1;
+            const uint32_t base = (2u | (slot & 1u)) << nb, rem = dist - base;
+            if (slot < 14) o.tree_reverse(Probs::POS_SPECIAL + base - slot - 1, nb, rem);
+            else { o.direct(rem >> 4, nb - 4); o.tree_reverse(Probs::POS_ALIGN, 4, rem & 15u); }
+        }
+    }
+    return o.n;
+}
+PNA_HD uint32_t match_state_next(uint32_t state, uint32_t kind) { return kind < 4 ? (state < 7 ? 8u : 11u) : (state < 7 ? 7u : 10u); }
+
+// the serial part: n events through the range coder.  Straight-line per event (selects instead of branches: a warp with one
+// active lane pays an instruction-fetch bubble for every taken branch); a direct bit is a coded bit whose bound is range / 2 and
+// whose probability slot is a scratch word (probs[ENC_PROBS], one entry behind the arena).
+PNA_HD void code_event(RangeEnc& rc, uint16_t* probs, uint32_t e) {
+    const uint32_t b = e >> 15;
+    const bool direct = (e & EV_DIRECT) != 0;
+    uint16_t* const prob = probs + (direct ? ENC_PROBS : (e & EV_INDEX));
+    const uint32_t v = *prob;
+    const uint32_t bound = direct ? rc.range >> 1 : (rc.range >> 11) * v;
+    *prob = (uint16_t)(b ? v - (v >> 5) : v + ((2048u - v) >> 5));
+    rc.low += b ? bound : 0u;
+    rc.range = (b && !direct) ? rc.range - bound : bound;
+    if (__builtin_expect(rc.range < (1u << 24), 0)) { rc.range <<= 8; rc.shift_low(); }   // one event in eight
+}
+PNA_HD void code_events(RangeEnc& rc, uint16_t* probs, const uint16_t* ev, uint32_t n) {
+    if (!rc.room(n)) return;
+    uint32_t i = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (; i + 4 <= n; i += 4) {   // the events are there before the coder needs them: four loads ahead of the dependent chain
+        const uint32_t e0 = ev[i], e1 = ev[i + 1], e2 = ev[i + 2], e3 = ev[i + 3];
+        code_event(rc, probs, e0); code_event(rc, probs, e1); code_event(rc, probs, e2); code_event(rc, probs, e3);
+    }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (; i < n; i++) code_event(rc, probs, ev[i]);
 }
 
 // One segment d[0, len) with its parse (sequences: ll literals, then a match of ml bytes at distance off) as ONE LZMA chunk
-// payload into dst[0, cap): fresh state, fresh probabilities (the caller has set probs[0, ENC_PROBS) to PROB_INIT), positions
+// payload into dst[0, cap) (the buffer itself has room for `phys` bytes): fresh state, fresh probabilities (the caller has set probs[0, ENC_PROBS) to PROB_INIT), positions
 // counted from 0 -- exactly what a reader sees after control byte 0xE0.  Returns the payload size, or 0xFFFFFFFF when it does
 // not fit into cap.  Matches are coded as repeats when their distance is one of the last four (the parse does not look for
-// them; structured data produces them by itself), else as a new distance.
-PNA_HD uint32_t lzma_encode_segment(const uint8_t* d, uint32_t len, const enc::Seq* sq, uint32_t nseq, uint16_t* probs, uint8_t* dst, uint32_t cap) {
+// them; structured data produces them by itself), else as a new distance.  This is the one-thread form (CPU test tier);
+// xz_encode_kernel runs the same generators with a lane per literal and the same coder loop on lane 0.
+PNA_HD uint32_t lzma_encode_segment(const uint8_t* d, uint32_t len, const enc::Seq* sq, uint32_t nseq, uint16_t* probs, uint8_t* dst, uint32_t cap, uint32_t phys) {
     RangeEnc rc;
-    rc.init(dst, dst + cap);
-    const uint32_t pb_mask = (1u << ENC_PB) - 1u, lp_mask = (1u << ENC_LP) - 1u;
-    uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0, pos = 0, prev = 0;
-    auto literal = [&]() {
-        const uint32_t byte = d[pos];
-        rc.bit(probs + Probs::IS_MATCH + state * 16 + (pos & pb_mask), 0);
-        uint16_t* lp = probs + Probs::LITERAL + 0x300u * (((pos & lp_mask) << ENC_LC) + (prev >> (8 - ENC_LC)));
-        uint32_t sym = 1;
-        if (state < 7) {
-            for (int i = 7; i >= 0; i--) { const uint32_t b = (byte >> i) & 1u; rc.bit(lp + sym, b); sym = (sym << 1) | b; }
-        } else {
-            uint32_t match_byte = d[pos - rep0 - 1], offs = 0x100;
-            for (int i = 7; i >= 0; i--) {
-                match_byte <<= 1;
-                const uint32_t match_bit = match_byte & offs, b = (byte >> i) & 1u;
-                rc.bit(lp + offs + match_bit + sym, b);
-                sym = (sym << 1) | b;
-                offs &= b ? match_bit : ~match_bit;
-            }
+    rc.init(dst, dst + cap, dst + phys);
+    uint16_t ev[EV_PER_MATCH_MAX];
+    uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0, pos = 0;
+    auto literals = [&](uint32_t n) {
+        for (uint32_t k = 0; k < n && !rc.over; k++, pos++) {
+            gen_literal_events(ev, pos, d[pos], pos ? d[pos - 1] : 0u, state, state >= 7 ? d[pos - rep0 - 1] : 0u);
+            code_events(rc, probs, ev, EV_PER_LITERAL);
+            state = lit_state_next(state);
         }
-        prev = byte;
-        pos++;
-        state = state < 4 ? 0 : state < 10 ? state - 3 : state - 6;
     };
     for (uint32_t s = 0; s < nseq && !rc.over; s++) {
         const uint32_t ll = sq[s].llml & 0xFFFFu, ml = sq[s].llml >> 16, dist = sq[s].off - 1u;
-        for (uint32_t k = 0; k < ll && !rc.over; k++) literal();
-        const uint32_t pos_state = pos & pb_mask;
-        rc.bit(probs + Probs::IS_MATCH + state * 16 + pos_state, 1);
-        if (dist == rep0 || dist == rep1 || dist == rep2 || dist == rep3) {
-            rc.bit(probs + Probs::IS_REP + state, 1);
-            if (dist == rep0) {
-                rc.bit(probs + Probs::IS_REP_G0 + state, 0);
-                rc.bit(probs + Probs::IS_REP0_LONG + state * 16 + pos_state, 1);
-            } else {
-                rc.bit(probs + Probs::IS_REP_G0 + state, 1);
-                if (dist == rep1) rc.bit(probs + Probs::IS_REP_G1 + state, 0);
-                else {
-                    rc.bit(probs + Probs::IS_REP_G1 + state, 1);
-                    if (dist == rep2) rc.bit(probs + Probs::IS_REP_G2 + state, 0);
-                    else { rc.bit(probs + Probs::IS_REP_G2 + state, 1); rep3 = rep2; }
-                    rep2 = rep1;
-                }
-                rep1 = rep0; rep0 = dist;
-            }
-            len_encode(rc, probs + Probs::LEN_REP, pos_state, ml);
-            state = state < 7 ? 8 : 11;
-        } else {
-            rc.bit(probs + Probs::IS_REP + state, 0);
-            len_encode(rc, probs + Probs::LEN_MATCH, pos_state, ml);
-            state = state < 7 ? 7 : 10;
-            rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = dist;
-            const uint32_t dist_state = ml < 6 ? ml - 2 : 3;
-            uint32_t slot = dist;
-            if (dist >= 4) {
-                uint32_t n = 31;
-                while (!(dist >> n)) n--;
-                slot = 2 * n + ((dist >> (n - 1)) & 1u);
-            }
-            rc.tree(probs + Probs::POS_SLOT + dist_state * 64, 6, slot);
-            if (slot >= 4) {
-                const int nb = (int)(slot >> 1) - 1;
-                const uint32_t base = (2u | (slot & 1u)) << nb, rem = dist - base;
-                if (slot < 14) rc.tree_reverse(probs + Probs::POS_SPECIAL + base - slot - 1, nb, rem);
-                else { rc.direct(rem >> 4, nb - 4); rc.tree_reverse(probs + Probs::POS_ALIGN, 4, rem & 15u); }
-            }
-        }
+        literals(ll);
+        const uint32_t kind = rep_classify(dist, rep0, rep1, rep2, rep3);
+        code_events(rc, probs, ev, gen_match_events(ev, pos, state, kind, ml, dist));
+        state = match_state_next(state, kind);
         pos += ml;
-        prev = d[pos - 1];
     }
-    while (pos < len && !rc.over) literal();
+    literals(len - pos);
     rc.flush();
-    return rc.over ? 0xFFFFFFFFu : (uint32_t)(rc.p - dst);
+    return rc.over || (uint32_t)(rc.p - dst) > cap ? 0xFFFFFFFFu : (uint32_t)(rc.p - dst);
 }
 
 // LZMA2 chunk header for a segment: compressed (6 bytes) or uncompressed (3 bytes).  Returns its length.

@@ -208,16 +208,16 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
         o = xz_write_front(out, nseg == 0);
         uint64_t chunk_bytes = 0;
         uint32_t crc = 0;
-        std::vector<uint16_t> probs(ENC_PROBS);
+        std::vector<uint16_t> probs(ENC_PROBS + 2);
         for (uint64_t s = 0; s < nseg; s++) {
             const uint8_t* d = in + s * SEG;
             const uint32_t n = (uint32_t)(len - s * SEG < SEG ? len - s * SEG : SEG);
             std::vector<Seq> seqs; std::vector<uint8_t> lits;
             greedy_segment(d, n, seqs, lits);
             for (auto& q : probs) q = (uint16_t)PROB_INIT;
-            std::vector<uint8_t> body(SEG + 64);
+            std::vector<uint8_t> body(SEG + SEG / 8 + 128);   // what the kernel has (TMP_SEG)
             const uint32_t cap = n > 4 ? n - 4 : 0;
-            const uint32_t cs = cap ? lzma_encode_segment(d, n, seqs.data(), (uint32_t)seqs.size(), probs.data(), body.data(), cap) : 0xFFFFFFFFu;
+            const uint32_t cs = cap ? lzma_encode_segment(d, n, seqs.data(), (uint32_t)seqs.size(), probs.data(), body.data(), cap, (uint32_t)body.size()) : 0xFFFFFFFFu;
             uint32_t hl;
             if (cs == 0xFFFFFFFFu) { hl = lzma2_chunk_header(out + o, n, 0); o += hl; memcpy(out + o, d, n); o += n; chunk_bytes += hl + n; }
             else { hl = lzma2_chunk_header(out + o, n, cs); o += hl; memcpy(out + o, body.data(), cs); o += cs; chunk_bytes += hl + cs; }
