@@ -213,11 +213,11 @@ def create_xz(pna, host, ctx, files, plain_pinned, p_offs, threads):
     state = {}
 
     def create():
-        state["blob"] = host.create_archive(list(zip(names, views)), compression=4, level=6, encryption=1, cipher_mode=1, key=KEY,
+        state["blob"] = host.create_archive(list(zip(names, views)), compression=4, level=6, encryption=1, cipher_mode=1, key=opts.key,
                                             phsf=opts.phsf, ivs=ivs, max_chunk_size=0, device=ctx.device, workers=4, group_bytes=256 << 20, out=arch)
     c_dt, _ = _timed(create, 2)
     blob = state["blob"]
-    ents = [{"plain": v, "compression": 4, "level": 6, "encryption": 1, "cipher_mode": 1, "key": KEY, "iv": ivs[16 * i:16 * i + 16],
+    ents = [{"plain": v, "compression": 4, "level": 6, "encryption": 1, "cipher_mode": 1, "key": opts.key, "iv": ivs[16 * i:16 * i + 16],
              "max_chunk_size": 0} for i, v in enumerate(views)]
     eplan = ctx.encode_plan(ents)
     eplan.run()
@@ -231,7 +231,7 @@ def create_xz(pna, host, ctx, files, plain_pinned, p_offs, threads):
         if i % max(1, n // 16):
             continue
         s = b"".join(bytes(b) for b in e.bodies)
-        assert O.decode_stream(s, 4, 1, 1, KEY, None) == files[i], "GPU-created xz entry is not reference-readable"
+        assert O.decode_stream(s, 4, 1, 1, opts.key, None) == files[i], "GPU-created xz entry is not reference-readable"
         checked += 1
     back = dict((e.name, d) for e, d in a.read_all(pna.ReadOptions.with_password(b"pw")))   # and all of it by our own xz decoder
     assert all(bytes(back[nm]) == f for nm, f in zip(names, files))

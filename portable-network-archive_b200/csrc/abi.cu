@@ -330,6 +330,12 @@ struct pna_plan {
     DevArr<uint64_t> d_lit_base, d_seq_base;
     DevArr<inf::InfStream> d_inf;
     DevArr<uint32_t> d_xz;
+    // chunk-parallel xz (kernels_xz.cuh): windows of the streams' outputs, built with the output layout
+    std::vector<uint2> h_xz_map;
+    std::vector<uint32_t> h_xz_win_begin;
+    DevArr<uint2> d_xz_map;
+    DevArr<uint32_t> d_xz_win_begin;
+    DevArr<xz::XzWin> d_xz_wins;
     DevArr<uint8_t> d_inf_lits;
     DevArr<zs::SeqRec> d_inf_recs;
     DevArr<zs::ZBlock> d_inf_blocks;
@@ -363,7 +369,7 @@ struct pna_plan {
         d_deflate.release(); d_seqs.release(); d_seq_order.release(); d_lit_order.release(); d_counts.release(); d_lz_order.release(); d_lz_units.release(); d_ze.release(); d_blocks.release();
         d_lit_base.release(); d_seq_base.release(); d_copy.release();
         d_walk.release(); d_pj_segs.release(); d_pj_ptr.release(); d_pj_cpos.release(); d_pj_flags.release(); d_pj_tiles.release();
-        d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release(); d_xz.release();
+        d_inf.release(); d_inf_lits.release(); d_inf_recs.release(); d_inf_blocks.release(); d_inf_ze.release(); d_inf_tr.release(); d_xz.release(); d_xz_map.release(); d_xz_win_begin.release(); d_xz_wins.release();
         if (enc) enc::destroy(enc);
     }
 };
@@ -447,6 +453,7 @@ static int ctx_create_single(pna_ctx** out, int device_id) {
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(crc_tiles_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_WIDE_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(xz::xz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz::XZ_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(xz::xz_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz::XZ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inf::TOKEN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::SEQ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LIT_SMEM_BYTES) == cudaSuccess;
@@ -914,6 +921,25 @@ static int decode_layout_out(pna_plan* P) {
         uint64_t len = std::min(e.comp_len, e.out_cap);
         for (uint64_t o = 0; o < len; o += 256 * 1024) P->h_copy.push_back({e.out_off + o, e.comp_off + o, std::min<uint64_t>(256 * 1024, len - o)});
     }
+    // xz: one window per XZ_WIN bytes of capacity for streams long enough to gain from it (whether a stream qualifies for the
+    // chunk-parallel pass is decided on the device, from its chunk headers)
+    P->h_xz_map.clear(); P->h_xz_win_begin.clear();
+    if (!P->h_xz.empty()) {
+        for (uint32_t k = 0; k < (uint32_t)P->h_xz.size(); k++) {
+            const EntryRec& e = P->h_entries[P->h_xz[k]];
+            P->h_xz_win_begin.push_back((uint32_t)P->h_xz_map.size());
+            if (e.status != ST_OK || e.out_cap == UINT64_MAX) continue;
+            const uint64_t nw = (e.out_cap + xz::XZ_WIN - 1) / xz::XZ_WIN;
+            if (nw < 2 || nw > (1u << 16) || P->h_xz_map.size() + nw > (1u << 26)) continue;
+            for (uint32_t w = 0; w < (uint32_t)nw; w++) P->h_xz_map.push_back(make_uint2(k, w));
+        }
+        P->h_xz_win_begin.push_back((uint32_t)P->h_xz_map.size());
+        if (!P->h_xz_map.empty()) {
+            CK(P->d_xz_map.reserve(P->h_xz_map.size())); CK(P->d_xz_wins.reserve(P->h_xz_map.size())); CK(P->d_xz_win_begin.reserve(P->h_xz_win_begin.size()));
+            CK(cudaMemcpyAsync(P->d_xz_map.p, P->h_xz_map.data(), P->h_xz_map.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(P->d_xz_win_begin.p, P->h_xz_win_begin.data(), P->h_xz_win_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
     // deflate: streams of the two-stage path with their literal / record arenas (sizes from the now final capacities)
     P->h_inf.clear(); P->h_deflate_big.clear();
     {
@@ -1116,7 +1142,13 @@ static int launch_inflate(pna_plan* P, int size_only) {
     pna_ctx* ctx = P->ctx;
     const uint32_t nx = (uint32_t)P->h_xz.size();
     if (nx) {   // xz: a warp per stream (kernels_xz.cuh); sizing reads the chunk headers only
-        xz::xz_decode_kernel<<<nx, 32, xz::XZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_xz.p, nx, P->d_out.p, size_only);
+        const uint32_t nw = size_only ? 0u : (uint32_t)P->h_xz_map.size();
+        if (nw) {   // streams made of independent chunks (this library's writer): a warp per 32 KiB window first
+            xz::xz_window_kernel<<<nw, 32, xz::XZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_xz.p, P->d_xz_map.p, nw, P->d_out.p, P->d_xz_wins.p);
+            LAUNCHED();
+        }
+        xz::xz_decode_kernel<<<nx, 32, xz::XZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_xz.p, nx, P->d_out.p, size_only,
+                                                                         nw ? P->d_xz_win_begin.p : nullptr, nw ? P->d_xz_wins.p : nullptr);
         LAUNCHED();
     }
     if (size_only) {

@@ -259,12 +259,88 @@ PNA_HD int32_t xz_stream_size(const uint8_t* in, uint64_t n, uint64_t* out_len) 
     return ST_OK;
 }
 
+// ---- chunk-parallel decoding.  A stream whose LZMA2 chunks ALL reset the dictionary (control 0x01 or >= 0xE0) -- what this
+// library's writer emits, one chunk per 32 KiB segment (lzma_enc_core.cuh) -- is a list of independent pieces: the output is cut
+// into windows of XZ_WIN bytes, a warp decodes the chunks that START in its window (xz_window_decode), and the ordinary serial
+// walk of xz_decode then only checks the container around them, with the block's CRC32 combined from the windows' partial CRCs.
+// Anything else (chunks that continue the dictionary, several blocks, CRC64 / SHA-256 checks, any irregularity at all) keeps the
+// serial decoder, which also remains the one place that decides error classes: a window that meets a problem just says "bad".
+constexpr uint32_t XZ_WIN = 32 * 1024;
+struct XzWin { uint32_t crc, len, xpow, state; };   // state: 0 not written, 1 ok, 2 bad
+constexpr uint32_t XZ_CRC_POLY = 0xEDB88320u;
+PNA_HD uint32_t xz_crc_mul(uint32_t a, uint32_t b) {   // a * b mod P, reflected (x^0 = 0x80000000)
+    uint32_t p = 0;
+    for (int i = 0; i < 32; i++) {
+        if (a & 0x80000000u) p ^= b;
+        a <<= 1;
+        b = (b >> 1) ^ (XZ_CRC_POLY & (0u - (b & 1u)));
+    }
+    return p;
+}
+PNA_HD uint32_t xz_crc_xpow(uint64_t n_bytes) {        // x^(8n) mod P
+    uint32_t p = 0x80000000u, sq = 0x00800000u;
+    while (n_bytes) {
+        if (n_bytes & 1) p = xz_crc_mul(sq, p);
+        sq = xz_crc_mul(sq, sq);
+        n_bytes >>= 1;
+    }
+    return p;
+}
+// Does the stream qualify, and where do the chunks of window `win` lie?  One block, LZMA2 only, check none or CRC32, every chunk
+// resetting the dictionary, sizes inside the input and inside cap; the index must follow the block.  *first_in / *first_out: input
+// position of the first chunk header that starts in the window and its output offset; *n_chunks: how many start there.
+PNA_HD bool xz_chunked_layout(const uint8_t* in, uint64_t n, uint64_t cap, uint64_t win, uint64_t* first_in, uint64_t* first_out, uint32_t* n_chunks) {
+    *n_chunks = 0;
+    if (n < 12 + 12 || !(in[0] == 0xFD && in[1] == '7' && in[2] == 'z' && in[3] == 'X' && in[4] == 'Z' && in[5] == 0)) return false;
+    if (in[6] != 0 || (in[7] != 0 && in[7] != 1)) return false;
+    const uint32_t check_size = in[7] ? 4 : 0;
+    uint64_t pos = 12;
+    if (in[pos] == 0) return false;                                         // no block at all
+    const uint64_t hsize = ((uint64_t)in[pos] + 1) * 4;
+    if (pos + hsize > n) return false;
+    pos += hsize;
+    const uint64_t block_in = pos, lo = win * XZ_WIN, hi = lo + XZ_WIN;
+    uint64_t op = 0;
+    for (;;) {
+        if (pos >= n) return false;
+        const uint8_t ctl = in[pos];
+        if (ctl == 0) { pos++; break; }
+        if (!(ctl == 1 || ctl >= 0xE0)) return false;
+        uint64_t usize, skip;
+        if (ctl == 1) {
+            if (pos + 3 > n) return false;
+            usize = (((uint32_t)in[pos + 1] << 8) | in[pos + 2]) + 1;
+            skip = 3 + usize;
+        } else {
+            if (pos + 6 > n) return false;
+            usize = (((uint32_t)(ctl & 0x1F) << 16) | ((uint32_t)in[pos + 1] << 8) | in[pos + 2]) + 1;
+            skip = 6 + (((uint32_t)in[pos + 3] << 8) | in[pos + 4]) + 1;
+        }
+        if (pos + skip > n || op + usize > cap) return false;
+        if (op >= lo && op < hi) { if (!*n_chunks) { *first_in = pos; *first_out = op; } (*n_chunks)++; }
+        pos += skip; op += usize;
+    }
+    pos += (4 - ((pos - block_in) & 3)) & 3;
+    pos += check_size;
+    return pos < n && in[pos] == 0;                                         // the index follows: exactly one block
+}
+
 // Decode the first .xz stream of [in, in + n) into out[0, cap).  probs: LZMA_PROBS_MAX entries of scratch.
 // ST_OK (*out_len = decoded bytes), ST_NOSPACE (*out_len = bytes needed, from the chunk headers),
 // ST_UNEXPECTED_EOF (input ends inside the stream: liblzma_rs "premature eof"), ST_INVALID_DATA (everything liblzma calls
 // LZMA_DATA_ERROR / LZMA_FORMAT_ERROR), ST_UNSUPPORTED (filters other than LZMA2, unknown check types: LZMA_OPTIONS_ERROR).
-PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, uint16_t* probs) {
+// wins / n_wins: partial results of the chunk-parallel pass over this stream (null: none) -- used only when the stream qualifies
+// (xz_chunked_layout) and every window that holds chunks came back ok; then the chunk payloads are not decoded again.
+PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_len, uint16_t* probs,
+                         const XzWin* wins = nullptr, uint32_t n_wins = 0) {
     *out_len = 0;
+    bool pre = false;                                                        // payloads already decoded by the window warps
+    if (wins && n_wins) {
+        uint64_t fi = 0, fo = 0;
+        uint32_t nc = 0;
+        pre = xz_chunked_layout(in, n, cap, 0, &fi, &fo, &nc);
+        for (uint32_t w = 0; pre && w < n_wins; w++) if (wins[w].state != 1) pre = false;
+    }
     if (n < 12) return ST_UNEXPECTED_EOF;
     if (!(in[0] == 0xFD && in[1] == '7' && in[2] == 'z' && in[3] == 'X' && in[4] == 'Z' && in[5] == 0)) return ST_INVALID_DATA;
     if (in[6] != 0 || (in[7] & 0xF0)) return ST_UNSUPPORTED;
@@ -323,11 +399,13 @@ PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t c
                     if (S.lc + S.lp > 4) return ST_INVALID_DATA;
                     S.need_props = false;
                 } else if (S.need_props) return ST_INVALID_DATA;
-                if (mode >= 1) { lzma_reset_probs(probs, S.lc, S.lp); S.state = 0; S.rep0 = S.rep1 = S.rep2 = S.rep3 = 0; }
+                if (mode >= 1 && !pre) { lzma_reset_probs(probs, S.lc, S.lp); S.state = 0; S.rep0 = S.rep1 = S.rep2 = S.rep3 = 0; }
                 if (pos + csize > n) return ST_UNEXPECTED_EOF;
                 if (op + usize > cap) { xz_stream_size(in, n, out_len); if (*out_len <= cap) *out_len = cap + 1; return ST_NOSPACE; }
-                const int32_t st = lzma_chunk(S, probs, in + pos, csize, out, op, usize, dict_start);
-                if (st != ST_OK) return st;
+                if (!pre) {
+                    const int32_t st = lzma_chunk(S, probs, in + pos, csize, out, op, usize, dict_start);
+                    if (st != ST_OK) return st;
+                }
                 pos += csize; op += usize;
             } else if (ctl == 1 || ctl == 2) {
                 if (pos + 2 > n) return ST_UNEXPECTED_EOF;
@@ -335,7 +413,7 @@ PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t c
                 pos += 2;
                 if (pos + usize > n) return ST_UNEXPECTED_EOF;
                 if (op + usize > cap) { xz_stream_size(in, n, out_len); if (*out_len <= cap) *out_len = cap + 1; return ST_NOSPACE; }
-                for (uint32_t i = 0; i < usize; i++) out[op + i] = in[pos + i];
+                if (!pre) for (uint32_t i = 0; i < usize; i++) out[op + i] = in[pos + i];
                 pos += usize; op += usize;
             } else return ST_INVALID_DATA;
         }
@@ -344,7 +422,13 @@ PNA_HD int32_t xz_decode(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t c
         // ---- block padding + check
         while ((pos - block_in) & 3) { if (pos >= n) return ST_UNEXPECTED_EOF; if (in[pos++] != 0) return ST_INVALID_DATA; }
         if (pos + check_size > n) return ST_UNEXPECTED_EOF;
-        if (check == 1) { if (xz_crc32(out + block_out, op - block_out) != load_le32(in + pos)) return ST_INVALID_DATA; }
+        if (check == 1 && pre) {
+            uint32_t c = 0;
+            uint64_t total = 0;
+            for (uint32_t w = 0; w < n_wins; w++) { c = xz_crc_mul(wins[w].xpow, c) ^ wins[w].crc; total += wins[w].len; }
+            if (total != op - block_out || c != load_le32(in + pos)) return ST_INVALID_DATA;
+        }
+        else if (check == 1) { if (xz_crc32(out + block_out, op - block_out) != load_le32(in + pos)) return ST_INVALID_DATA; }
         else if (check == 4) {
             const uint64_t want = (uint64_t)load_le32(in + pos) | ((uint64_t)load_le32(in + pos + 4) << 32);
             if (xz_crc64(out + block_out, op - block_out) != want) return ST_INVALID_DATA;

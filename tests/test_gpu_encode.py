@@ -203,3 +203,5 @@ def test_xz_encode_chunks_levels_and_container(ctx, pna, oracle):
         a.add_entry(be)
     blob = a.finalize()
     assert dict(oracle.extract_all(blob, b"pw")) == files
+    ar = pna.Archive.read_header(np.frombuffer(blob, dtype=np.uint8), ctx)
+    assert {e.name: bytes(d) for e, d in ar.read_all(pna.ReadOptions.with_password(b"pw"))} == files

@@ -166,7 +166,7 @@ def test_broken_chunk_detected_by_cpp_host(host, pna, ctx, golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("comp,enc,mode", [(2, 1, 1), (1, 2, 0), (0, 0, 0), (2, 0, 0), (2, 1, 2), (1, 2, 2)])
+@pytest.mark.parametrize("comp,enc,mode", [(2, 1, 1), (1, 2, 0), (0, 0, 0), (2, 0, 0), (2, 1, 2), (1, 2, 2), (4, 1, 1), (4, 0, 0)])
 def test_create_with_cpp_host_is_reference_readable(host, pna, ctx, oracle, comp, enc, mode):
     """create path end to end (FileEntryBuilder -> add_entry -> finalize in C++): the oracle's restatement of the reference
     reader must list and extract the same files; then our own C++ reader too (cli/tests/cli/encrypt.rs round trip)."""

@@ -13,6 +13,7 @@ ap.add_argument("--entries", type=int, default=256)
 ap.add_argument("--ref-entries", type=int, default=16)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--level", type=int, default=6)
+ap.add_argument("--serial", type=int, default=0, help="also decode liblzma-written streams of the same files (serial decoder; takes ~1 min of host time to prepare)")
 a = ap.parse_args()
 ctx = pna.Context(0)
 FILE = 4 << 20
@@ -35,6 +36,20 @@ for k in range(0, a.entries, max(1, a.entries // 8)):
     assert O.decode_stream(streams[k].tobytes(), 4, 1, 1, KEY, None) == files[k]
 back, st2, _ = ctx.decode_batch([{"bodies": [s], "compression": 4, "encryption": 1, "cipher_mode": 1, "key": KEY, "raw_size_hint": FILE} for s in streams])
 assert st2 == [0] * len(ents) and all(b.tobytes() == f for b, f in zip(back, files))
+# extract of what we wrote: chunk-parallel xz decode (a warp per 32 KiB window), kernel-only through a decode plan
+dplan = ctx.decode_plan([{"bodies": [s], "compression": 4, "encryption": 1, "cipher_mode": 1, "key": KEY, "raw_size_hint": FILE} for s in streams])
+for _ in range(2):
+    dplan.run()
+dms = dplan.stage_ms()
+# the same files written by liblzma (one dictionary for the whole stream: the serial decoder, a warp per stream)
+nser = min(a.entries, 64)
+ser = [lzma.compress(f, preset=a.level) for f in files[:nser]] if a.serial else []
+sms = None
+if ser:
+    splan = ctx.decode_plan([{"bodies": [c], "compression": 4, "encryption": 0, "cipher_mode": 0, "key": None, "raw_size_hint": FILE} for c in ser])
+    for _ in range(2):
+        splan.run()
+    sms = splan.stage_ms()
 nref = min(a.ref_entries, a.entries)
 cores = len(os.sched_getaffinity(0))
 t0 = time.perf_counter()
@@ -46,4 +61,6 @@ ms = min(ts)
 print(json.dumps({"workload": f"create {a.entries} x 4 MiB, GPU xz (LZMA2 chunk per 32 KiB) + aes-256-ctr + crc32", "ms_per_step": ms,
                   "GBps": a.entries * FILE / ms / 1e6, "stage_ms": stage, "ratio": a.entries * FILE / c_gpu, "c_gpu_over_c_ref": c_gpu_s / c_ref,
                   "cpu_liblzma": {"GBps": nref * FILE / t_ref / 1e9, "cores": cores, "preset": a.level, "sample": f"{nref} x 4 MiB"},
+                  "extract_back": {"stage_ms": dms, "xz_GBps": a.entries * FILE / dms["inflate"] / 1e6, "how": "decode plan over the streams written above: chunk-parallel pass + container check"},
+                  "extract_liblzma_written": None if sms is None else {"streams": nser, "xz_ms": sms["inflate"], "xz_GBps": nser * FILE / sms["inflate"] / 1e6},
                   "checked": "sampled streams by liblzma + OpenSSL, all streams by our xz decode kernel"}))
