@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--entries", type=int, default=1024, help="4 MiB files per GPU (cfg2: 8192 over 8 GPUs)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=7)
     ap.add_argument("--workers", type=int, default=0, help="host worker threads of the end-to-end path (0: 4, or the rank's cores if fewer)")
     ap.add_argument("--group-mib", type=int, default=128, help="compressed MiB per pipelined entry group (end-to-end path)")
     ap.add_argument("--create-workers", type=int, default=4)
@@ -448,7 +448,7 @@ def main():
                                                              ratio=U / Cbytes, host_cpus_per_rank=threads, e2e_workers=workers),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": world * U / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": arch_bytes * world,
-                    "d2h_bytes_per_step": int(U) * world, "ms_per_step": e2e_s * 1e3, "pcie": pcie,
+                    "d2h_bytes_per_step": int(U) * world, "ms_per_step": e2e_s * 1e3, "ms_all_steps_rank0": [round(t * 1e3, 2) for t in e2e_times], "pcie": pcie,
                     "path": f"pna::Archive::read_header_from_slice + extract_files (C++ host layer, {workers} worker threads x 2 contexts, {args.group_mib} MiB entry groups software-pipelined create->run->fetch): index pass, H2D, chunk CRC check, decrypt, decode, D2H to pinned buffers; host clock"},
             "roofline": roof}
     if cpu:

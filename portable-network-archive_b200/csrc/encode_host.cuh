@@ -28,7 +28,7 @@ struct EncodePlan {
     DevArr<uint8_t> d_stage;                  // coalesced transfers: many small adjacent host spans travel as one copy
     DevArr<CopyJob> d_stage_jobs;
     uint32_t fdat_init = 0;
-    bool has_zstd = false, has_deflate = false, has_xz = false;   // which block writers the batch needs
+    bool has_zstd = false, has_deflate = false, has_xz[4] = {false, false, false, false};   // which block writers the batch needs (xz: by literal-context setting)
     // GCM STREAM: segment / tile slots from the compressed-length bounds (AES slots first, then Camellia)
     std::vector<GcmSlot> h_gcm_slots;
     std::vector<gcm::GcmKeyRef> h_gcm_refs;
@@ -44,7 +44,7 @@ void destroy(EncodePlan* p) { delete p; }
 bool init_attributes() {
     const int aes_smem = 256 * 32 * 4, cam_smem = 2 * 2048 * 4;
     return cudaFuncSetAttribute(lz_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_SMEM_BYTES) == cudaSuccess &&
-           cudaFuncSetAttribute(xz_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XZ_ENC_SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(xz_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz_enc_smem_bytes(xz::ENC_LC_MAX)) == cudaSuccess &&
            cudaFuncSetAttribute(encrypt_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_CTR_SMEM) == cudaSuccess &&
            cudaFuncSetAttribute(encrypt_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cam_smem) == cudaSuccess &&
            cudaFuncSetAttribute(cbc_encrypt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_smem) == cudaSuccess &&
@@ -107,7 +107,7 @@ static int encode_plan_build(pna_ctx* ctx, const pna_encode_desc* descs, uint32_
         e.effort = (uint8_t)enc::enc_effort(d.compression, d.level);
         if (d.compression == PNA_COMPRESSION_ZSTD) E->has_zstd = true;
         if (d.compression == PNA_COMPRESSION_DEFLATE) E->has_deflate = true;
-        if (d.compression == PNA_COMPRESSION_XZ) E->has_xz = true;
+        if (d.compression == PNA_COMPRESSION_XZ) E->has_xz[enc::xz_lc_for_effort(e.effort)] = true;
         memcpy(e.iv, d.iv, 16);
         e.key_idx = -1;
         if (d.compression != PNA_COMPRESSION_NO && d.compression != PNA_COMPRESSION_DEFLATE && d.compression != PNA_COMPRESSION_ZSTD &&
@@ -349,9 +349,9 @@ static int encode_launch_all(pna_plan* P) {
             enc::enc_block_kernel<1><<<bgrid, enc::ENC_BLOCK_THREADS, 0, ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_tables.p, E->d_entries.p);
             LAUNCHED();
         }
-        if (E->has_xz) {
-            enc::xz_encode_kernel<<<nsegs, 32, enc::XZ_ENC_SMEM_BYTES, ctx->stream>>>(
-                E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_entries.p);
+        for (uint32_t lc = 0; lc < 4; lc++) {
+            if (!E->has_xz[lc]) continue;
+            enc::xz_encode_kernel<<<nsegs, 32, enc::xz_enc_smem_bytes(lc), ctx->stream>>>(E->d_work.p, E->d_segs.p, nsegs, E->d_seqs.p, E->d_entries.p, lc);
             LAUNCHED();
         }
     }

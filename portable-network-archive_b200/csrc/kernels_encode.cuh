@@ -41,7 +41,7 @@ struct SegRec {            // one segment (host fills the first group, kernels t
 inline uint32_t enc_effort(uint8_t compression, int32_t level) {
     if (compression == 2) return level <= 0 ? 1u : level <= 2 ? 0u : level <= 5 ? 1u : 2u;
     if (compression == 1) return level < 0 ? 1u : level == 0 ? 3u : level <= 3 ? 0u : level <= 6 ? 1u : 2u;
-    if (compression == 4) return level >= 0 && level <= 3 ? 1u : 2u;   // xz 0..9, default 6 (compress/xz.rs:10-16): presets >= 4 parse lazily
+    if (compression == 4) return level >= 0 && level <= 3 ? 1u : 2u;   // xz 0..9, default 6 (compress/xz.rs:10-16): presets >= 4 parse lazily, lc = 2 (0-3: lc = 0)
     return 1u;
 }
 constexpr uint32_t ENC_BLOCK_THREADS = 128;
@@ -287,21 +287,26 @@ __global__ void __launch_bounds__(128) enc_block_kernel(uint8_t* __restrict__ wo
 // xz: a warp (= a CTA) per segment.  All lanes reset the segment's probability arena (16 KB of shared memory: the dependent
 // load-update-store chain per coded bit runs at shared-memory latency) and take the CRC-32 of a 1 KiB slice each.  Then, sequence by
 // sequence: the lanes turn 32 literals at a time into their coder events (lzma_enc_core.cuh: probability index and bit depend on
-// data and parse only), lane 0 adds the events of the match and runs the one serial loop, the range coder, over the ring.
-// Segments are independent chunks, so a 4 MiB file is 128 coders in flight; 13 per SM.
+// data and parse only), lane 0 adds the events of the match, the warp resolves the events into probability VALUES (the adaptation
+// of a slot depends on the order of the events on that slot only), and lane 0 runs the one serial loop that is left -- bound,
+// low, range, normalise -- over the ring.
+// Segments are independent chunks, so a 4 MiB file is 128 coders in flight; the arena decides how many per SM (lc = 2: 22, lc = 0: 43).
 constexpr uint32_t XZ_ENC_RING = 32 * xz::EV_PER_LITERAL + xz::EV_PER_MATCH_MAX;   // 32 literals and the match behind them
-constexpr uint32_t XZ_ENC_SMEM_BYTES = ((xz::ENC_PROBS + 2 + XZ_ENC_RING) * 2u + 15u) & ~15u;   // + the scratch slot of direct bits
+__host__ __device__ constexpr uint32_t xz_lc_for_effort(uint32_t effort) { return effort <= 1u ? 0u : 2u; }
+__host__ __device__ constexpr uint32_t xz_enc_smem_bytes(uint32_t lc) { return ((xz::enc_probs(lc) + 2 + XZ_ENC_RING) * 2u + 15u) & ~15u; }
+// one launch per literal-context setting (lc): the arena size is a launch parameter
 __global__ void __launch_bounds__(32) xz_encode_kernel(uint8_t* __restrict__ work, SegRec* __restrict__ segs, uint32_t nsegs,
-                                                       const Seq* __restrict__ seqs, const EncEntry* __restrict__ entries) {
+                                                       const Seq* __restrict__ seqs, const EncEntry* __restrict__ entries, uint32_t lc) {
     extern __shared__ __align__(16) uint8_t xz_enc_smem_raw[];
     const uint32_t lane = threadIdx.x;
     const uint32_t s = blockIdx.x;
     if (s >= nsegs) return;
     SegRec& sr = segs[s];
-    if (entries[sr.entry].compression != 4) return;
+    if (entries[sr.entry].compression != 4 || xz_lc_for_effort(sr.effort) != lc) return;
+    const uint32_t n_probs = xz::enc_probs(lc);
     uint16_t* const probs = reinterpret_cast<uint16_t*>(xz_enc_smem_raw);
-    uint16_t* const ring = probs + xz::ENC_PROBS + 2;
-    for (uint32_t i = lane; i < xz::ENC_PROBS + 2; i += 32) probs[i] = (uint16_t)xz::PROB_INIT;
+    uint16_t* const ring = probs + n_probs + 2;
+    for (uint32_t i = lane; i < n_probs; i += 32) probs[i] = (uint16_t)xz::PROB_INIT;
     const uint32_t len = sr.len;
     const uint8_t* const d = work + sr.plain_off;
     const uint32_t lo = lane * (SEG / 32), nl = lo >= len ? 0u : (len - lo < SEG / 32 ? len - lo : SEG / 32);
@@ -333,13 +338,31 @@ __global__ void __launch_bounds__(32) xz_encode_kernel(uint8_t* __restrict__ wor
             const uint32_t j = base + lane, p = pos + j, cnt = ll - base < 32 ? ll - base : 32;
             if (j < ll) {
                 const uint32_t st = xz::lit_state_after(state, j);
-                xz::gen_literal_events(ring + lane * xz::EV_PER_LITERAL, p, d[p], p ? d[p - 1] : 0u, st, st >= 7 ? d[p - rep0_lit - 1] : 0u);
+                xz::gen_literal_events(ring + lane * xz::EV_PER_LITERAL, p, d[p], p ? d[p - 1] : 0u, st, st >= 7 ? d[p - rep0_lit - 1] : 0u, lc);
             }
             uint32_t total = cnt * xz::EV_PER_LITERAL;
             if (lane == 0 && has_match && base + 32 >= ll)
                 total += xz::gen_match_events(ring + total, pos + ll, xz::lit_state_after(state, ll), kind, ml, dist);
+            total = __shfl_sync(0xFFFFFFFFu, total, 0);
             __syncwarp();
-            if (lane == 0) xz::code_events(rc, probs, ring, total);
+            // events -> values: 32 events per round trip; lanes whose events hit the same probability slot take turns in event order
+            for (uint32_t b0 = 0; b0 < total; b0 += 32) {
+                const uint32_t i = b0 + lane;
+                const bool live = i < total;
+                const uint32_t ev = live ? ring[i] : 0u, bit = ev >> 15, idx = ev & xz::EV_INDEX;
+                const bool coded = live && !(ev & xz::EV_DIRECT);
+                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, coded ? idx : (0x10000u | lane));
+                const uint32_t rank = (uint32_t)__popc(grp & ((1u << lane) - 1u));
+                const uint32_t rounds = __reduce_max_sync(0xFFFFFFFFu, coded ? (uint32_t)__popc(grp) : 1u);
+                uint32_t v = 0;
+                for (uint32_t r = 0; r < rounds; r++) {
+                    if (coded && rank == r) { v = probs[idx]; probs[idx] = (uint16_t)xz::prob_step(v, bit); }
+                    __syncwarp();
+                }
+                if (live) ring[i] = (uint16_t)(coded ? (v | (bit << 15)) : (xz::EV_DIRECT | (bit << 15)));
+            }
+            __syncwarp();
+            if (lane == 0) xz::code_values(rc, ring, total);
             __syncwarp();
             base += 32;
         } while (base < ll);
@@ -351,8 +374,8 @@ __global__ void __launch_bounds__(32) xz_encode_kernel(uint8_t* __restrict__ wor
     if (lane) return;
     rc.flush();
     const uint32_t cs = (over || rc.over || (uint32_t)(rc.p - (head + TMP_HEAD)) > cap) ? 0xFFFFFFFFu : (uint32_t)(rc.p - (head + TMP_HEAD));
-    if (cs == 0xFFFFFFFFu) { sr.head_len = xz::lzma2_chunk_header(head, len, 0); sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0; }
-    else { sr.head_len = xz::lzma2_chunk_header(head, len, cs); sr.raw = 0; sr.tail_off = 0; sr.tail_len = cs; }
+    if (cs == 0xFFFFFFFFu) { sr.head_len = xz::lzma2_chunk_header(head, len, 0, lc); sr.raw = 1; sr.tail_off = 0; sr.tail_len = 0; }
+    else { sr.head_len = xz::lzma2_chunk_header(head, len, cs, lc); sr.raw = 0; sr.tail_off = 0; sr.tail_len = cs; }
     sr.adler_a = crc;
 }
 

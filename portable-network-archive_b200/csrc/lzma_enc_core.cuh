@@ -18,9 +18,14 @@
 namespace pna {
 namespace xz {
 
-constexpr uint32_t ENC_LC = 3, ENC_LP = 0, ENC_PB = 2;                     // liblzma's defaults for every preset
-constexpr uint32_t ENC_PROPS = (ENC_PB * 5 + ENC_LP) * 9 + ENC_LC;         // 0x5D
-constexpr uint32_t ENC_PROBS = LZMA_PROBS_FIXED + (0x300u << (ENC_LC + ENC_LP));
+// lp = 0, pb = 2 as in every liblzma preset.  lc (how many bits of the previous byte select a literal's probability set) is
+// liblzma's 3 at most; the literal sets are 3/4 of the probability arena at lc = 3, and the arena is what limits the coders in
+// flight per SM, so the setting trades bytes for speed: lc = 0 costs 0.2-1.8 % of the stream (bench corpus / text) and runs 43
+// segments per SM, lc = 2 costs <= 0.5 % and runs 22, lc = 3 runs 13.  xz_lc_for_effort picks it from the `level`.
+constexpr uint32_t ENC_LC_MAX = 3, ENC_LP = 0, ENC_PB = 2;
+PNA_HD constexpr uint32_t enc_props(uint32_t lc) { return (ENC_PB * 5 + ENC_LP) * 9 + lc; }
+PNA_HD constexpr uint32_t enc_probs(uint32_t lc) { return LZMA_PROBS_FIXED + (0x300u << (lc + ENC_LP)); }
+constexpr uint32_t ENC_PROBS = enc_probs(ENC_LC_MAX);
 constexpr uint8_t ENC_DICT_CODE = 8;                                       // 64 KiB: distances stay below the 32 KiB segment
 constexpr uint32_t XZ_HDR_SCRATCH = 96;                                    // per entry: 24 bytes in front, <= 47 behind
 
@@ -70,10 +75,10 @@ PNA_HD uint32_t lit_state_after(uint32_t state, uint32_t k) {   // three literal
 }
 // the literal `byte` at position pos (state: the coder state in front of it; match_byte: the byte at the last distance, used when
 // state >= 7): EV_PER_LITERAL events
-PNA_HD void gen_literal_events(uint16_t* ev, uint32_t pos, uint32_t byte, uint32_t prev, uint32_t state, uint32_t match_byte) {
+PNA_HD void gen_literal_events(uint16_t* ev, uint32_t pos, uint32_t byte, uint32_t prev, uint32_t state, uint32_t match_byte, uint32_t lc) {
     const uint32_t pb_mask = (1u << ENC_PB) - 1u, lp_mask = (1u << ENC_LP) - 1u;
     ev[0] = (uint16_t)(Probs::IS_MATCH + state * 16 + (pos & pb_mask));
-    const uint32_t lp = Probs::LITERAL + 0x300u * (((pos & lp_mask) << ENC_LC) + (prev >> (8 - ENC_LC)));
+    const uint32_t lp = Probs::LITERAL + 0x300u * (((pos & lp_mask) << lc) + (prev >> (8 - lc)));
     uint32_t sym = 1;
     if (state < 7) {
         for (int i = 7; i >= 0; i--) { const uint32_t b = (byte >> i) & 1u; ev[8 - i] = (uint16_t)((lp + sym) | (b << 15)); sym = (sym << 1) | b; }
@@ -154,50 +159,66 @@ PNA_HD uint32_t gen_match_events(uint16_t* ev, uint32_t pos, uint32_t state, uin
 }
 PNA_HD uint32_t match_state_next(uint32_t state, uint32_t kind) { return kind < 4 ? (state < 7 ? 8u : 11u) : (state < 7 ? 7u : 10u); }
 
-// the serial part: n events through the range coder.  Straight-line per event (selects instead of branches: a warp with one
-// active lane pays an instruction-fetch bubble for every taken branch); a direct bit is a coded bit whose bound is range / 2 and
-// whose probability slot is a scratch word (probs[ENC_PROBS], one entry behind the arena).
-PNA_HD void code_event(RangeEnc& rc, uint16_t* probs, uint32_t e) {
-    const uint32_t b = e >> 15;
-    const bool direct = (e & EV_DIRECT) != 0;
-    uint16_t* const prob = probs + (direct ? ENC_PROBS : (e & EV_INDEX));
-    const uint32_t v = *prob;
-    const uint32_t bound = direct ? rc.range >> 1 : (rc.range >> 11) * v;
-    *prob = (uint16_t)(b ? v - (v >> 5) : v + ((2048u - v) >> 5));
+// ---- From events to the coder.  The probability an event is coded with is the value its slot has after all EARLIER events on the
+// same slot -- a function of the event order per slot, not of range / low.  So that too comes off the serial thread: prob_step
+// is the adaptation rule, the kernel resolves 32 events per round trip (lanes that hit the same slot take turns, by rank), and
+// what is left for the one serial lane is code_values: bound, low, range, normalise.  A value word is v | bit << 15, or
+// EV_DIRECT | bit << 15.
+PNA_HD uint32_t prob_step(uint32_t v, uint32_t b) { return b ? v - (v >> 5) : v + ((2048u - v) >> 5); }
+PNA_HD void resolve_events_serial(uint16_t* probs, const uint16_t* ev, uint16_t* val, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t e = ev[i], b = e >> 15;
+        if (e & EV_DIRECT) { val[i] = (uint16_t)(EV_DIRECT | (b << 15)); continue; }
+        const uint32_t v = probs[e & EV_INDEX];
+        probs[e & EV_INDEX] = (uint16_t)prob_step(v, b);
+        val[i] = (uint16_t)(v | (b << 15));
+    }
+}
+// Straight-line per value (selects instead of branches: a warp with one active lane pays an instruction-fetch bubble for every
+// taken branch); a direct bit is a coded bit whose bound is range / 2.
+PNA_HD void code_value(RangeEnc& rc, uint32_t w) {
+    const uint32_t b = w >> 15;
+    const bool direct = (w & EV_DIRECT) != 0;
+    const uint32_t bound = direct ? rc.range >> 1 : (rc.range >> 11) * (w & 0xFFFu);
     rc.low += b ? bound : 0u;
     rc.range = (b && !direct) ? rc.range - bound : bound;
-    if (__builtin_expect(rc.range < (1u << 24), 0)) { rc.range <<= 8; rc.shift_low(); }   // one event in eight
+    if (__builtin_expect(rc.range < (1u << 24), 0)) { rc.range <<= 8; rc.shift_low(); }   // one value in eight
 }
-PNA_HD void code_events(RangeEnc& rc, uint16_t* probs, const uint16_t* ev, uint32_t n) {
+PNA_HD void code_values(RangeEnc& rc, const uint16_t* val, uint32_t n) {
     if (!rc.room(n)) return;
     uint32_t i = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-    for (; i + 4 <= n; i += 4) {   // the events are there before the coder needs them: four loads ahead of the dependent chain
-        const uint32_t e0 = ev[i], e1 = ev[i + 1], e2 = ev[i + 2], e3 = ev[i + 3];
-        code_event(rc, probs, e0); code_event(rc, probs, e1); code_event(rc, probs, e2); code_event(rc, probs, e3);
+    for (; i + 4 <= n; i += 4) {   // the values are there before the coder needs them: four loads ahead of the dependent chain
+        const uint32_t w0 = val[i], w1 = val[i + 1], w2 = val[i + 2], w3 = val[i + 3];
+        code_value(rc, w0); code_value(rc, w1); code_value(rc, w2); code_value(rc, w3);
     }
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-    for (; i < n; i++) code_event(rc, probs, ev[i]);
+    for (; i < n; i++) code_value(rc, val[i]);
+}
+// one thread doing all of it (CPU test tier)
+PNA_HD void code_events(RangeEnc& rc, uint16_t* probs, uint16_t* ev, uint32_t n) {
+    resolve_events_serial(probs, ev, ev, n);
+    code_values(rc, ev, n);
 }
 
 // One segment d[0, len) with its parse (sequences: ll literals, then a match of ml bytes at distance off) as ONE LZMA chunk
-// payload into dst[0, cap) (the buffer itself has room for `phys` bytes): fresh state, fresh probabilities (the caller has set probs[0, ENC_PROBS) to PROB_INIT), positions
+// payload into dst[0, cap) (the buffer itself has room for `phys` bytes): fresh state, fresh probabilities (the caller has set probs[0, enc_probs(lc)) to PROB_INIT), positions
 // counted from 0 -- exactly what a reader sees after control byte 0xE0.  Returns the payload size, or 0xFFFFFFFF when it does
 // not fit into cap.  Matches are coded as repeats when their distance is one of the last four (the parse does not look for
 // them; structured data produces them by itself), else as a new distance.  This is the one-thread form (CPU test tier);
 // xz_encode_kernel runs the same generators with a lane per literal and the same coder loop on lane 0.
-PNA_HD uint32_t lzma_encode_segment(const uint8_t* d, uint32_t len, const enc::Seq* sq, uint32_t nseq, uint16_t* probs, uint8_t* dst, uint32_t cap, uint32_t phys) {
+PNA_HD uint32_t lzma_encode_segment(const uint8_t* d, uint32_t len, const enc::Seq* sq, uint32_t nseq, uint16_t* probs, uint8_t* dst, uint32_t cap, uint32_t phys, uint32_t lc) {
     RangeEnc rc;
     rc.init(dst, dst + cap, dst + phys);
     uint16_t ev[EV_PER_MATCH_MAX];
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0, pos = 0;
     auto literals = [&](uint32_t n) {
         for (uint32_t k = 0; k < n && !rc.over; k++, pos++) {
-            gen_literal_events(ev, pos, d[pos], pos ? d[pos - 1] : 0u, state, state >= 7 ? d[pos - rep0 - 1] : 0u);
+            gen_literal_events(ev, pos, d[pos], pos ? d[pos - 1] : 0u, state, state >= 7 ? d[pos - rep0 - 1] : 0u, lc);
             code_events(rc, probs, ev, EV_PER_LITERAL);
             state = lit_state_next(state);
         }
@@ -216,12 +237,12 @@ PNA_HD uint32_t lzma_encode_segment(const uint8_t* d, uint32_t len, const enc::S
 }
 
 // LZMA2 chunk header for a segment: compressed (6 bytes) or uncompressed (3 bytes).  Returns its length.
-PNA_HD uint32_t lzma2_chunk_header(uint8_t* h, uint32_t usize, uint32_t csize /* 0: uncompressed chunk */) {
+PNA_HD uint32_t lzma2_chunk_header(uint8_t* h, uint32_t usize, uint32_t csize /* 0: uncompressed chunk */, uint32_t lc) {
     const uint32_t u = usize - 1;
     if (!csize) { h[0] = 0x01; h[1] = (uint8_t)(u >> 8); h[2] = (uint8_t)u; return 3; }
     const uint32_t c = csize - 1;
     h[0] = (uint8_t)(0xE0u | (u >> 16)); h[1] = (uint8_t)(u >> 8); h[2] = (uint8_t)u;
-    h[3] = (uint8_t)(c >> 8); h[4] = (uint8_t)c; h[5] = (uint8_t)ENC_PROPS;
+    h[3] = (uint8_t)(c >> 8); h[4] = (uint8_t)c; h[5] = (uint8_t)enc_props(lc);
     return 6;
 }
 

@@ -198,6 +198,8 @@ static void greedy_segment(const uint8_t* d, uint32_t len, std::vector<pna::enc:
         else { lits.push_back(d[p]); run++; p++; }
     }
 }
+static uint32_t g_xz_lc = 2;
+extern "C" void hc_set_xz_lc(int lc) { g_xz_lc = (uint32_t)lc; }
 extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, uint8_t* out) {
     using namespace pna::enc;
     if (!g_enc_init) { make_enc_tables(&g_enc); g_enc_init = true; }
@@ -217,10 +219,10 @@ extern "C" uint64_t hc_encode(int compression, const uint8_t* in, uint64_t len, 
             for (auto& q : probs) q = (uint16_t)PROB_INIT;
             std::vector<uint8_t> body(SEG + SEG / 8 + 128);   // what the kernel has (TMP_SEG)
             const uint32_t cap = n > 4 ? n - 4 : 0;
-            const uint32_t cs = cap ? lzma_encode_segment(d, n, seqs.data(), (uint32_t)seqs.size(), probs.data(), body.data(), cap, (uint32_t)body.size()) : 0xFFFFFFFFu;
+            const uint32_t cs = cap ? lzma_encode_segment(d, n, seqs.data(), (uint32_t)seqs.size(), probs.data(), body.data(), cap, (uint32_t)body.size(), g_xz_lc) : 0xFFFFFFFFu;
             uint32_t hl;
-            if (cs == 0xFFFFFFFFu) { hl = lzma2_chunk_header(out + o, n, 0); o += hl; memcpy(out + o, d, n); o += n; chunk_bytes += hl + n; }
-            else { hl = lzma2_chunk_header(out + o, n, cs); o += hl; memcpy(out + o, body.data(), cs); o += cs; chunk_bytes += hl + cs; }
+            if (cs == 0xFFFFFFFFu) { hl = lzma2_chunk_header(out + o, n, 0, g_xz_lc); o += hl; memcpy(out + o, d, n); o += n; chunk_bytes += hl + n; }
+            else { hl = lzma2_chunk_header(out + o, n, cs, g_xz_lc); o += hl; memcpy(out + o, body.data(), cs); o += cs; chunk_bytes += hl + cs; }
             // lanes' slices combined the way xz_encode_kernel does
             uint32_t sc = 0;
             for (uint32_t l = 0; l < 32; l++) {

@@ -172,7 +172,7 @@ def test_xz_encode_chunks_levels_and_container(ctx, pna, oracle):
             else:
                 u = (((ctl & 0x1F) << 16) | (s[at + 1] << 8) | s[at + 2]) + 1
                 c = ((s[at + 3] << 8) | s[at + 4]) + 1
-                assert s[at + 5] == 0x5D and c + 3 < u
+                assert s[at + 5] == (0x5A if e["level"] == 0 else 0x5C) and c + 3 < u   # pb = 2, lp = 0, lc = 0 (levels 0-3) or 2
                 at += 6 + c
             assert u <= 32768
             n_chunks += 1; total += u

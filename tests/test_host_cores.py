@@ -183,7 +183,8 @@ def test_xz_writer_core_decodes_with_liblzma(hc):
              b"".join(bytes([i & 255]) * (1 + i % 7) for i in range(30_000)),
              b"".join((b"<row id=%d>" % (i % 10)) + bytes(rnd.randrange(256) for _ in range(3)) + b"</row>\n" for i in range(8000))]
     tot_in = tot_out = 0
-    for d in cases:
+    for k, d in enumerate(cases):
+        hc.hc_set_xz_lc(k % 4)                                               # every literal-context setting the writer can be asked for
         out = C.create_string_buffer(len(d) + len(d) // 1000 + 4096)
         n = hc.hc_encode(4, d, len(d), out)
         s = out.raw[:n]
@@ -192,6 +193,7 @@ def test_xz_writer_core_decodes_with_liblzma(hc):
         assert dec.check == lzma.CHECK_CRC32 or not d
         assert n <= len(d) + 3 * ((len(d) + 32767) // 32768) + 72           # the bound pna_cuda_encode_bound promises
         tot_in += len(d); tot_out += n
+    hc.hc_set_xz_lc(2)
     out = C.create_string_buffer(64)
     n = hc.hc_encode(4, b"", 0, out)
     assert out.raw[:n] == lzma.compress(b"", check=lzma.CHECK_CRC32)   # the zero-block stream, byte for byte

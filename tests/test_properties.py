@@ -29,7 +29,7 @@ def mod(pna):
 
 
 @pytest.mark.parametrize("encryption,mode", [(1, 1), (1, 0), (2, 1), (2, 0), (1, 2), (2, 2)])
-@pytest.mark.parametrize("compression", [0, 2, 1])
+@pytest.mark.parametrize("compression", [0, 2, 1, 4])
 @settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(data=payloads)
 def test_builder_reader_round_trip(ctx, mod, oracle, encryption, mode, compression, data):
