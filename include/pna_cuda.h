@@ -84,8 +84,8 @@ typedef struct {
     int32_t level;          /* <0: reference default (zstd 3 compress/zstandard.rs:46, deflate 6 compress/deflate.rs:89).
                              * Selects the encoder setting: zstd 1-2 / deflate 1-3 fast (greedy parse, Predefined FSE tables);
                              * zstd 3-5 / deflate 4-6 default (per-block FSE tables chosen by cost); zstd >= 6 / deflate 7-9
-                             * high (lazy parse); deflate 0 stored blocks; xz (0..9, default 6 compress/xz.rs:10-16) 0-3 greedy,
-                             * 4-9 lazy parse, always one LZMA2 chunk per 32 KiB segment and a CRC32 check.  Sizes differ from the reference's at the same
+                             * high (lazy parse); deflate 0 stored blocks; xz (0..9, default 6 compress/xz.rs:10-16) 0-3 greedy parse, lc = 0;
+                             * 4-9 lazy parse, lc = 2; always one LZMA2 chunk per 32 KiB segment and a CRC32 check.  Sizes differ from the reference's at the same
                              * level (another encoder); every setting decodes with the reference's codecs. */
     uint8_t key[32];
     uint8_t iv[16];         /* caller-drawn (lib/src/entry/write.rs:108-111, random.rs:8); unused by GCM */

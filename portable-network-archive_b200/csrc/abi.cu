@@ -453,7 +453,7 @@ static int ctx_create_single(pna_ctx** out, int device_id) {
                                     (int)(sizeof(inf::Tables) * inf::INFLATE_CTA)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(crc_tiles_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_WIDE_SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(xz::xz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz::XZ_SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(xz::xz_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz::XZ_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(xz::xz_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xz::XZ_WIN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(inf::inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inf::TOKEN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::SEQ_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(zs::zstd_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs::LIT_SMEM_BYTES) == cudaSuccess;
@@ -1144,7 +1144,7 @@ static int launch_inflate(pna_plan* P, int size_only) {
     if (nx) {   // xz: a warp per stream (kernels_xz.cuh); sizing reads the chunk headers only
         const uint32_t nw = size_only ? 0u : (uint32_t)P->h_xz_map.size();
         if (nw) {   // streams made of independent chunks (this library's writer): a warp per 32 KiB window first
-            xz::xz_window_kernel<<<nw, 32, xz::XZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_xz.p, P->d_xz_map.p, nw, P->d_out.p, P->d_xz_wins.p);
+            xz::xz_window_kernel<<<nw, 32, xz::XZ_WIN_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_xz.p, P->d_xz_map.p, nw, P->d_out.p, P->d_xz_wins.p);
             LAUNCHED();
         }
         xz::xz_decode_kernel<<<nx, 32, xz::XZ_SMEM_BYTES, ctx->stream>>>(P->d_buf.p, P->d_entries.p, P->d_xz.p, nx, P->d_out.p, size_only,

@@ -11,6 +11,10 @@ namespace pna {
 namespace xz {
 
 constexpr uint32_t XZ_SMEM_BYTES = (LZMA_PROBS_MAX * 2u + 15u) & ~15u;
+// the chunk-parallel pass keeps arenas for lc + lp <= 2 only (what this library's writer emits: 10 KB, 22 windows in flight per SM
+// instead of 8); a chunk with more literal-context bits sends its stream to the serial decoder
+constexpr uint32_t XZ_WIN_LCLP_MAX = 2;
+constexpr uint32_t XZ_WIN_SMEM_BYTES = ((LZMA_PROBS_FIXED + (0x300u << XZ_WIN_LCLP_MAX)) * 2u + 15u) & ~15u;
 
 // list[i] = index into EntryRec[].  size_only: the decoded length from the chunk headers (two-pass sizing), no decoding.
 // win_begin (n + 1 entries, null: no chunk-parallel pass ran) / wins: the window records of stream i are wins[win_begin[i] .. win_begin[i + 1])
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(32) xz_window_kernel(const uint8_t* __restrict
             S.pb = props / 45; props -= S.pb * 45;
             S.lp = props / 9; S.lc = props - S.lp * 9;
             S.need_props = false; S.need_dict_reset = false;
-            if (in[pos + 5] > (4 * 5 + 4) * 9 + 8 || S.lc + S.lp > 4) { ok = 0; break; }
+            if (in[pos + 5] > (4 * 5 + 4) * 9 + 8 || S.lc + S.lp > XZ_WIN_LCLP_MAX) { ok = 0; break; }
             const uint32_t np = LZMA_PROBS_FIXED + (0x300u << (S.lc + S.lp));
             for (uint32_t k = lane; k < np; k += 32) probs[k] = (uint16_t)PROB_INIT;
             __syncwarp();

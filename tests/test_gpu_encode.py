@@ -205,3 +205,50 @@ def test_xz_encode_chunks_levels_and_container(ctx, pna, oracle):
     assert dict(oracle.extract_all(blob, b"pw")) == files
     ar = pna.Archive.read_header(np.frombuffer(blob, dtype=np.uint8), ctx)
     assert {e.name: bytes(d) for e, d in ar.read_all(pna.ReadOptions.with_password(b"pw"))} == files
+
+
+def test_xz_chunk_parallel_decode_fallbacks_and_corruption(ctx, pna, built):
+    """The chunk-parallel xz pass (xz_window_kernel) against streams of independent chunks from the writer core at EVERY lc
+    (lc = 3 exceeds the pass's arena: the serial decoder takes the stream), and against corrupted copies of such streams: whatever the
+    windows do, accept / reject and the bytes must equal liblzma's."""
+    import ctypes as C
+    import lzma
+    import random
+    hc = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "libpna_hostcore.so"))
+    hc.hc_encode.restype = C.c_uint64
+    hc.hc_encode.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p]
+    rnd = random.Random(11)
+    plains = [corpus.make_file(40, 200_000), corpus.make_file(41, 70_000) + os.urandom(40_000) + corpus.make_file(42, 33_000), bytes(100_000)]
+    streams, want = [], []
+    for lc in (0, 1, 2, 3):
+        hc.hc_set_xz_lc(lc)
+        for p in plains:
+            out = C.create_string_buffer(len(p) + 4096)
+            n = hc.hc_encode(4, p, len(p), out)
+            streams.append(out.raw[:n])
+            want.append(p)
+    hc.hc_set_xz_lc(2)
+    n_good = len(streams)
+    base = streams[6]                                       # lc = 2, text: goes through the windows
+    for _ in range(60):
+        b = bytearray(base)
+        k = rnd.randrange(len(b))
+        b[k] ^= 1 << rnd.randrange(8)
+        streams.append(bytes(b)); want.append(None)
+    for cut in (13, 30, 1000, len(base) // 2, len(base) - 30, len(base) - 1):
+        streams.append(base[:cut]); want.append(None)
+    outs, st, _ = ctx.decode_batch([{"bodies": [s], "compression": 4, "encryption": 0, "cipher_mode": 0, "key": None, "raw_size_hint": None}
+                                    for s in streams])
+    for i, (s, w) in enumerate(zip(streams, want)):
+        try:
+            d = lzma.LZMADecompressor(format=lzma.FORMAT_XZ)
+            ref = d.decompress(s)
+            ref_ok = d.eof
+        except lzma.LZMAError:
+            ref_ok = False
+        if i < n_good:
+            assert ref_ok and st[i] == 0 and outs[i].tobytes() == w, (i, ref_ok, st[i], len(outs[i]), len(w))
+        else:
+            assert (st[i] == 0) == ref_ok, (i, st[i], ref_ok)
+            if ref_ok:
+                assert outs[i].tobytes() == ref, i
