@@ -368,6 +368,62 @@ extern "C" int hc_xz_decode(const uint8_t* in, uint64_t len, uint8_t* out, uint6
     return pna::xz::xz_decode(in, len, out, cap, out_len, probs.data());
 }
 extern "C" int hc_xz_size(const uint8_t* in, uint64_t len, uint64_t* out_len) { return pna::xz::xz_stream_size(in, len, out_len); }
+// the chunk-parallel pass of kernels_xz.cuh with the windows looped on the host: every window decodes the chunks that start in it
+// (xz_chunked_layout + lzma_chunk, CRC of what it produced), then xz_decode runs with the window records.  *used = 1 when the
+// stream qualified and every window came back ok (the payloads were not decoded again).
+extern "C" int hc_xz_decode_windows(const uint8_t* in, uint64_t len, uint8_t* out, uint64_t cap, uint64_t* out_len, int* used) {
+    using namespace pna::xz;
+    const uint32_t n_wins = (uint32_t)((cap + XZ_WIN - 1) / XZ_WIN);
+    std::vector<XzWin> wins(n_wins);
+    std::vector<uint16_t> probs(LZMA_PROBS_MAX);
+    for (uint32_t w = 0; w < n_wins; w++) {
+        XzWin r{0, 0, 0x80000000u, 2};
+        uint64_t fi = 0, fo = 0;
+        uint32_t nc = 0;
+        bool ok = xz_chunked_layout(in, len, cap, w, &fi, &fo, &nc);
+        uint64_t pos = fi, op = fo;
+        for (uint32_t c = 0; ok && c < nc; c++) {
+            const uint32_t ctl = in[pos];
+            if (ctl == 1) {
+                const uint32_t usize = (((uint32_t)in[pos + 1] << 8) | in[pos + 2]) + 1;
+                memcpy(out + op, in + pos + 3, usize);
+                pos += 3 + usize; op += usize;
+            } else {
+                const uint32_t usize = (((ctl & 0x1Fu) << 16) | ((uint32_t)in[pos + 1] << 8) | in[pos + 2]) + 1;
+                const uint32_t csize = (((uint32_t)in[pos + 3] << 8) | in[pos + 4]) + 1;
+                uint32_t props = in[pos + 5];
+                LzmaState S;
+                S.state = 0; S.rep0 = S.rep1 = S.rep2 = S.rep3 = 0;
+                S.pb = props / 45; props -= S.pb * 45;
+                S.lp = props / 9; S.lc = props - S.lp * 9;
+                S.need_props = false; S.need_dict_reset = false;
+                if (in[pos + 5] > (4 * 5 + 4) * 9 + 8 || S.lc + S.lp > 4) { ok = false; break; }
+                lzma_reset_probs(probs.data(), S.lc, S.lp);
+                if (lzma_chunk(S, probs.data(), in + pos + 6, csize, out, op, usize, op) != pna::ST_OK) { ok = false; break; }
+                pos += 6 + csize; op += usize;
+            }
+        }
+        if (ok) {
+            // lanes' slices combined the way the kernel does
+            const uint64_t L = op - fo, sl = (L + 31) / 32;
+            uint32_t crc = 0;
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint64_t lo = (uint64_t)l * sl, nl = lo >= L ? 0 : (L - lo < sl ? L - lo : sl);
+                crc = xz_crc_mul(xz_crc_xpow(nl), crc) ^ (nl ? xz_crc32(out + fo + lo, nl) : 0u);
+            }
+            r = XzWin{crc, (uint32_t)L, xz_crc_xpow(L), 1};
+        }
+        wins[w] = r;
+    }
+    *used = 0;
+    if (n_wins) {
+        uint64_t fi = 0, fo = 0; uint32_t nc = 0;
+        bool pre = xz_chunked_layout(in, len, cap, 0, &fi, &fo, &nc);
+        for (uint32_t w = 0; pre && w < n_wins; w++) pre = wins[w].state == 1;
+        *used = pre ? 1 : 0;
+    }
+    return xz_decode(in, len, out, cap, out_len, probs.data(), wins.data(), n_wins);
+}
 
 // ---- development aid: where do an encoded stream's bytes go?  stats[0..5] = literals, sequences, bytes of the literal
 // sections, bytes of the sequence sections, empirical-entropy bytes of the (ll, ml, of) codes + extra bits per block, and

@@ -206,6 +206,71 @@ def test_xz_writer_core_decodes_with_liblzma(hc):
         lzma.decompress(bytes(s))
 
 
+def test_xz_chunk_parallel_pass_on_the_host(hc):
+    """The chunk-parallel xz pass (lzma_core.cuh: xz_chunked_layout, per-window CRCs, the container walk of xz_decode over window
+    records) with the windows looped on the host: streams of independent chunks from the writer core take it (and yield liblzma's
+    bytes), liblzma-written streams do not qualify, corrupted / truncated chunked streams are accepted or rejected exactly as
+    liblzma does -- whichever way they go."""
+    import lzma
+    hc.hc_encode.restype = C.c_uint64
+    hc.hc_encode.argtypes = [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p]
+    hc.hc_xz_decode_windows.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+
+    def run(s, cap):
+        out = C.create_string_buffer(max(cap, 1))
+        n, used = C.c_uint64(0), C.c_int(0)
+        st = hc.hc_xz_decode_windows(s, len(s), out, cap, C.byref(n), C.byref(used))
+        return st, out.raw[:n.value], used.value
+
+    def ref(s):
+        try:
+            d = lzma.LZMADecompressor(format=lzma.FORMAT_XZ)
+            o = d.decompress(s)
+            return o if d.eof else None
+        except lzma.LZMAError:
+            return None
+
+    rnd = random.Random(5)
+    plains = [corpus.make_file(50, 200_000), corpus.make_file(51, 40_000) + os.urandom(40_000) + corpus.make_file(52, 33_000), bytes(100_000),
+              corpus.make_file(53, 32_768), corpus.make_file(54, 32_769), b"q"]
+    streams = []
+    for k, p in enumerate(plains):
+        hc.hc_set_xz_lc(k % 4)
+        out = C.create_string_buffer(len(p) + 4096)
+        n = hc.hc_encode(4, p, len(p), out)
+        s = out.raw[:n]
+        streams.append(s)
+        st, got, used = run(s, len(p))
+        assert st == 0 and got == p and used == 1, (k, st, used)
+        st, got, used = run(s, len(p) + 100_000)                      # capacity beyond the stream: empty windows behind it
+        assert st == 0 and got == p and used == 1, k
+        assert run(s, len(p) - 1)[0] == 5                            # NOSPACE from the serial walk, as without the pass
+    hc.hc_set_xz_lc(2)
+    for k, p in enumerate(plains[:3] + [corpus.make_file(55, 3_000_000)]):
+        # liblzma-written: chunks after the first continue the dictionary -- not chunk-parallel, still right (a stream that fits ONE
+        # chunk does qualify, rightly: its only chunk resets the dictionary)
+        s = lzma.compress(p, preset=1, check=lzma.CHECK_CRC32)
+        st, got, used = run(s, len(p))
+        assert st == 0 and got == p, k
+        if k == 3:
+            assert used == 0                                         # several chunks, one dictionary
+    base = streams[0]
+    agree = 0
+    for _ in range(150):
+        b = bytearray(base)
+        k = rnd.randrange(len(b))
+        b[k] ^= 1 << rnd.randrange(8)
+        want = ref(bytes(b))
+        st, got, _ = run(bytes(b), len(plains[0]))
+        assert (st == 0) == (want is not None), (k, st)
+        if want is not None:
+            assert got == want
+        agree += 1
+    for cut in (0, 11, 12, 13, 24, 30, 1000, len(base) // 2, len(base) - 30, len(base) - 1):
+        st, _, _ = run(base[:cut], len(plains[0]))
+        assert st != 0
+
+
 @pytest.mark.parametrize("comp", [1, 2])
 def test_block_writers_table_choices_decode_with_reference_codecs(hc, oracle, comp):
     """The per-block table machinery of the writers (encode_core.cuh): zstd Predefined / RLE / FSE_Compressed per table with the
