@@ -261,7 +261,7 @@ def host_sanitize(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("comp,enc,mode", [(2, 0, 0), (2, 1, 1), (2, 2, 2), (1, 1, 0), (0, 0, 0)])
+@pytest.mark.parametrize("comp,enc,mode", [(2, 0, 0), (2, 1, 1), (2, 2, 2), (1, 1, 0), (0, 0, 0), (4, 0, 0), (4, 2, 1)])
 def test_create_solid_with_cpp_host_is_reference_readable(host, pna, ctx, oracle, comp, enc, mode):
     """Solid create in C++ (write_solid_header -> add_entry -> finalize, archive/write.rs:438-471): the oracle's restatement of the
     reference reader (SolidEntry::entries, inner chunk CRCs included) and our own C++ reader extract the same files
