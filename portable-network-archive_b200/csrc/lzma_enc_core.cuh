@@ -67,6 +67,8 @@ struct RangeEnc {
 constexpr uint32_t EV_BIT = 0x8000u, EV_DIRECT = 0x4000u, EV_INDEX = 0x1FFFu;
 static_assert(ENC_PROBS <= EV_INDEX + 1, "prob index fits the event word");
 constexpr uint32_t EV_PER_LITERAL = 9, EV_PER_MATCH_MAX = 40;
+// a match: is_match, is_rep, length (<= 10), distance slot (6), and for distances below 2^17 at most 11 direct + 4 aligned bits
+static_assert(enc::SEG <= (1u << 17), "EV_PER_MATCH_MAX counts on distances inside one segment");
 
 PNA_HD uint32_t lit_state_next(uint32_t state) { return state < 4 ? 0 : state < 10 ? state - 3 : state - 6; }
 PNA_HD uint32_t lit_state_after(uint32_t state, uint32_t k) {   // three literals take every state to 0
